@@ -1,0 +1,152 @@
+/* fastquick_b200 -- C ABI of the B200-native FASTQuick align+summarize hot path.
+ *
+ * Plain pointers and sizes only; every call returns an int status (0 = ok,
+ * negative = error, text via fqb_last_error()).  No exceptions cross this
+ * boundary.  The reference has no FFI layer for this path (it is a C++ object
+ * graph); each entry point below names the reference seam it replaces
+ * (paths relative to the Griffan/FASTQuick tree).  INTEGRATION.md shows the
+ * shim a maintainer adds on the reference side.
+ */
+#ifndef FASTQUICK_B200_H_
+#define FASTQUICK_B200_H_
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQB_OK            0
+#define FQB_ERR_ARG      -1
+#define FQB_ERR_IO       -2
+#define FQB_ERR_CUDA     -3
+#define FQB_ERR_STATE    -4
+#define FQB_ERR_LIMIT    -5
+
+#define FQB_MAX_READ_LEN 256      /* bwa_seq_t::len is 20 bits in the reference; reads on this path are <= ~250 bp */
+#define FQB_BATCH_PAIRS  0x40000  /* READ_BUFFER_SIZE, src/BwtMapper.h:37 */
+
+/* numeric fields of gap_opt_t (libbwa/bwtaln.h:98-119) that the path reads;
+ * defaults = gap_init_opt() (libbwa/bwtaln.c:24-48) */
+typedef struct {
+    int32_t s_mm, s_gapo, s_gape;
+    int32_t mode;
+    int32_t indel_end_skip, max_del_occ, max_entries;
+    double  fnr;
+    int32_t max_diff, max_gapo, max_gape;
+    int32_t max_seed_diff, seed_len;
+    int32_t max_top2;
+    int32_t trim_qual;
+    int32_t flank_len, flank_long_len;
+    int32_t read_len;
+    int32_t kmer_thresh;            /* BwtIndexer(thresh), src/FASTQuick.cpp:174,362 */
+    int32_t is_il13;                /* --I: qualities are phred+64 (BWA_MODE_IL13) */
+} fqb_gap_opt_t;
+
+/* pe_opt_t (libbwa/bwtaln.h:124-130); defaults = bwa_init_pe_opt() (libbwa/bwape.c:7-20) */
+typedef struct {
+    int32_t  max_isize, force_isize;
+    uint32_t max_occ;
+    int32_t  n_multi, N_multi;
+    int32_t  type, is_sw;
+    double   ap_prior;
+} fqb_pe_opt_t;
+
+void fqb_gap_opt_default(fqb_gap_opt_t *o);
+void fqb_pe_opt_default(fqb_pe_opt_t *o);
+
+/* one SA interval hit: bwt_aln1_t (libbwa/bwtaln.h:34-38) */
+typedef struct {
+    uint32_t k, l;
+    int32_t  score;
+    uint8_t  n_mm, n_gapo, n_gape, a;
+} fqb_aln_t;
+
+/* isize_info_t (libbwa/bwape.h:92-95) */
+typedef struct {
+    double   avg, std, ap_prior;
+    uint32_t low, high, high_bayesian;
+    uint32_t pad_;
+} fqb_isize_t;
+
+#define FQB_MAX_CIGAR 16
+#define FQB_MAX_MULTI 11           /* n_multi/N_multi + 1, src/BwtMapper.cpp:857-871 */
+
+/* per-read result row: the bwa_seq_t fields (libbwa/bwtaln.h:57-86) that
+ * StatCollector::AddAlignment and BwtMapper::SetSamRecord consume */
+typedef struct {
+    uint32_t pos;                  /* pac coordinate */
+    uint32_t sa;
+    uint32_t c1, c2;
+    int32_t  score;
+    int32_t  len, full_len, clip_len;
+    uint8_t  type, strand, filtered, extra_flag;
+    uint8_t  n_mm, n_gapo, n_gape, mapQ;
+    uint8_t  seQ, n_cigar, n_multi, has_cigar;
+    uint16_t nm, n_aln;
+    uint16_t cigar[FQB_MAX_CIGAR]; /* bwa_cigar_t: op<<14 | len */
+} fqb_read_t;
+
+typedef struct fqb_handle fqb_handle;
+
+/* ---- index ------------------------------------------------------------ */
+/* Replaces BwtIndexer::LoadIndex (src/BwtIndexer.cpp:803-837): reads
+ * <prefix>.{bwt,rbwt,sa,rsa,pac,ann,amb,rollhash} unchanged and uploads the
+ * re-laid tables to `device` (CUDA ordinal). */
+int fqb_create(const char *index_prefix, const fqb_gap_opt_t *gopt, const fqb_pe_opt_t *popt,
+               int device, fqb_handle **out);
+void fqb_destroy(fqb_handle *h);
+const char *fqb_last_error(void);
+
+/* index facts the host shim needs (bwt_t / bntseq_t scalars) */
+int fqb_index_info(const fqb_handle *h, int64_t *l_pac, int32_t *n_contigs,
+                   uint32_t *primary /*[2]*/, uint32_t *seed);
+
+/* ---- hot path, one batch of read pairs --------------------------------- */
+/* Replaces the per-batch body of BwtMapper::PairEndMapper
+ * (src/BwtMapper.cpp:1933-1982): bwa_read_seq_with_hash_dev's per-read prep
+ * (476-613), bwa_cal_sa_reg_gap (63-168), bwa_cal_pac_pos_pe (721-907),
+ * bwa_paired_sw (libbwa/bwape.c:463) and bwa_refine_gapped (libbwa/bwase.c:339).
+ * bases/quals: ASCII, n_pairs rows of `stride` bytes per end (host memory,
+ * pinned for full speed); lens: read lengths.  rows[e][i] receives the result
+ * for end e of pair i.  Batches must be submitted in file order (the drand48
+ * stream and last_ii carry over, src/BwtMapper.cpp:1817,780). */
+int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride,
+                    const uint8_t *bases1, const uint8_t *quals1, const int32_t *lens1,
+                    const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2,
+                    fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
+
+/* ---- synthetic fixtures (bench + tests; hs37d5/dbSNP are not available offline) ----
+ * Not part of the drop-in surface: these stand in for `FASTQuick index` output
+ * (src/FASTQuick.cpp:38-157) and for FASTQ input so the hot path can be driven
+ * where the reference binary is absent. */
+typedef struct fqb_synth fqb_synth;
+typedef struct {
+    uint64_t seed;
+    int32_t n_long, n_short, n_x, n_y;
+    int32_t flank_short, flank_long, spacing;
+} fqb_synth_ref_cfg_t;
+typedef struct {
+    uint64_t seed;
+    int32_t read_len;
+    int32_t max_indel_len;
+    double f_on, sub_rate, ins_rate, del_rate, n_rate, isize_mean, isize_sd;
+} fqb_synth_read_cfg_t;
+void fqb_synth_ref_cfg_default(fqb_synth_ref_cfg_t *c);
+void fqb_synth_read_cfg_default(fqb_synth_read_cfg_t *c);
+int fqb_synth_create(const fqb_synth_ref_cfg_t *cfg, fqb_synth **out);
+void fqb_synth_destroy(fqb_synth *s);
+/* genome.fa(+.fai,.amb), markers.vcf, dbsnp.vcf: the inputs of `FASTQuick index --predefinedVCF` */
+int fqb_synth_write_inputs(const fqb_synth *s, const char *dir);
+/* <prefix> = "<out_prefix>.FASTQuick.fa": all files BwtIndexer::BuildIndex + runIndex would leave */
+int fqb_synth_write_index(const fqb_synth *s, const char *genome_path, const char *dbsnp_path,
+                          const char *prefix, int with_rollhash);
+int fqb_synth_reads(const fqb_synth *s, const fqb_synth_read_cfg_t *cfg, int64_t first_pair, int64_t n_pairs,
+                    uint8_t *bases1, uint8_t *quals1, uint8_t *bases2, uint8_t *quals2, int n_threads);
+/* gz FASTQ with fixed-width names r%011lld/1 and /2 */
+int fqb_write_fastq_gz(const char *path, int which_end, int64_t first_pair, int64_t n_pairs, int32_t read_len,
+                       const uint8_t *bases, const uint8_t *quals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
