@@ -52,7 +52,7 @@ void fqb_synth_read_cfg_default(fqb_synth_read_cfg_t *c) {
     fqb::SynthReadConfig d;
     c->seed = d.seed; c->read_len = d.read_len; c->max_indel_len = d.max_indel_len; c->f_on = d.f_on;
     c->sub_rate = d.sub_rate; c->ins_rate = d.ins_rate; c->del_rate = d.del_rate; c->n_rate = d.n_rate;
-    c->isize_mean = d.isize_mean; c->isize_sd = d.isize_sd;
+    c->isize_mean = d.isize_mean; c->isize_sd = d.isize_sd; c->bad_tail_rate = d.bad_tail_rate;
 }
 int fqb_synth_create(const fqb_synth_ref_cfg_t *c, fqb_synth **out) {
     if (!c || !out) { fqb::set_error("null argument"); return FQB_ERR_ARG; }
@@ -86,7 +86,7 @@ int fqb_synth_reads(const fqb_synth *s, const fqb_synth_read_cfg_t *c, int64_t f
     fqb::SynthReadConfig cfg;
     cfg.seed = c->seed; cfg.read_len = c->read_len; cfg.max_indel_len = c->max_indel_len; cfg.f_on = c->f_on;
     cfg.sub_rate = c->sub_rate; cfg.ins_rate = c->ins_rate; cfg.del_rate = c->del_rate; cfg.n_rate = c->n_rate;
-    cfg.isize_mean = c->isize_mean; cfg.isize_sd = c->isize_sd;
+    cfg.isize_mean = c->isize_mean; cfg.isize_sd = c->isize_sd; cfg.bad_tail_rate = c->bad_tail_rate;
     fqb::synth_reads(s->ref, cfg, first_pair, n_pairs, b1, q1, b2, q2, n_threads);
     return FQB_OK;
 }
@@ -111,3 +111,5 @@ int fqb_write_fastq_gz(const char *path, int which_end, int64_t first_pair, int6
 }
 
 }  // extern "C"
+
+std::vector<fqb::FlankSeq> fqb_synth_flanks_internal(const fqb_synth *s) { return fqb::synth_flanks(s->ref); }

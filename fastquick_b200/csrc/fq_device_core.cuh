@@ -1,0 +1,411 @@
+// Per-lane device logic of the align hot path: FM-index rank queries, SA
+// resolution, bwt_cal_width, and the bounded best-first backtracking search
+// (bwt_match_gap).  Everything here is a plain per-thread function over raw
+// pointers so the same code can be instantiated by the CUDA kernels
+// (fq_kernels.cu) and, for CPU-side CI only, by tests/emul (logic check without a
+// GPU; never linked into the product library).
+//
+// Reference anchors: libbwa/bwt.h:89-222 (occ), libbwa/bwt.c:69-79 (bwt_sa),
+// libbwa/bwtaln.c:73-97 (bwt_cal_width), libbwa/bwtgap.c:45-264 (stack + search).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FQB_HD __host__ __device__ __forceinline__
+#else
+#define FQB_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define FQB_POPCLL(x) __popcll(x)
+#define FQB_FFSLL(x) __ffsll((long long)(x))
+#define FQB_LDG4(p) __ldg(p)
+#else
+#define FQB_POPCLL(x) __builtin_popcountll(x)
+#define FQB_FFSLL(x) __builtin_ffsll((long long)(x))
+#define FQB_LDG4(p) (*(p))
+#endif
+
+#if !defined(__CUDACC__)
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+#endif
+
+namespace fqb {
+
+// ---------------------------------------------------------------------------
+// FM index, re-laid for the GPU: one 32-byte block (= one L2 sector) per 64 BWT
+// symbols: uint4 {cumulative A,C,G,T counts before the block} + uint4 {64 bases,
+// 2 bits each, first base in the top bits of .x}.  The reference keeps 48-byte
+// blocks per 128 symbols (libbwa/bwt.h:34,56-62); values returned are identical.
+struct DevBwt {
+    const uint4 *blocks;      // 2 x uint4 per block
+    const uint32_t *sa;       // every 32nd row, sa[0] = 0xffffffff
+    uint32_t primary, seq_len;
+    uint32_t L2[5];
+    uint32_t n_blocks;
+};
+
+constexpr uint32_t kNoRow = 0xffffffffu;
+
+// dynamic index into a 4-vector without forcing it into local memory
+FQB_HD uint32_t pick4(const uint32_t v[4], uint32_t c) {
+    uint32_t lo = (c & 1) ? v[1] : v[0], hi = (c & 1) ? v[3] : v[2];
+    return (c & 2) ? hi : lo;
+}
+
+// counts of A,C,G,T among stored symbols [0, k] (after the primary shift); bwt_occ4
+FQB_HD void occ4_block(const uint4 cnt, const uint4 bases, uint32_t n /*1..64 symbols of this block*/, uint32_t out[4]) {
+    const uint64_t HI = 0xAAAAAAAAAAAAAAAAull;
+    uint64_t w0 = ((uint64_t)bases.x << 32) | bases.y, w1 = ((uint64_t)bases.z << 32) | bases.w;
+    uint32_t n0 = n < 32 ? n : 32, n1 = n - n0;
+    uint64_t m0 = (n0 == 32 ? ~0ull : ~(~0ull >> (2 * n0))) & HI;
+    uint64_t m1 = (n1 == 0 ? 0ull : (n1 == 32 ? ~0ull : ~(~0ull >> (2 * n1)))) & HI;
+    uint64_t h0 = w0 & m0, l0 = (w0 << 1) & m0, h1 = w1 & m1, l1 = (w1 << 1) & m1;
+    uint32_t H = FQB_POPCLL(h0) + FQB_POPCLL(h1);
+    uint32_t L = FQB_POPCLL(l0) + FQB_POPCLL(l1);
+    uint32_t T = FQB_POPCLL(h0 & l0) + FQB_POPCLL(h1 & l1);
+    out[3] = cnt.w + T;
+    out[2] = cnt.z + H - T;
+    out[1] = cnt.y + L - T;
+    out[0] = cnt.x + n - H - L + T;
+}
+
+FQB_HD void occ4(const DevBwt &b, uint32_t k, uint32_t out[4]) {
+    if (k == kNoRow) { out[0] = out[1] = out[2] = out[3] = 0; return; }
+    k -= (k >= b.primary);
+    const uint4 *p = b.blocks + 2 * (size_t)(k >> 6);
+    occ4_block(FQB_LDG4(p), FQB_LDG4(p + 1), (k & 63) + 1, out);
+}
+
+// bwt_2occ4(bwt, k, l): both rank vectors, one block fetch when k and l share a block
+FQB_HD void occ4_pair(const DevBwt &b, uint32_t k, uint32_t l, uint32_t ck[4], uint32_t cl[4]) {
+    if (k == kNoRow) { ck[0] = ck[1] = ck[2] = ck[3] = 0; occ4(b, l, cl); return; }
+    uint32_t kk = k - (k >= b.primary), ll = l - (l >= b.primary);
+    const uint4 *p = b.blocks + 2 * (size_t)(kk >> 6);
+    uint4 c = FQB_LDG4(p), w = FQB_LDG4(p + 1);
+    occ4_block(c, w, (kk & 63) + 1, ck);
+    if ((ll >> 6) != (kk >> 6)) {
+        p = b.blocks + 2 * (size_t)(ll >> 6);
+        c = FQB_LDG4(p); w = FQB_LDG4(p + 1);
+    }
+    occ4_block(c, w, (ll & 63) + 1, cl);
+}
+
+// bwt_sa (libbwa/bwt.c:69-79) with bwt_invPsi (libbwa/bwt.h:66-70)
+FQB_HD uint32_t sa_lookup(const DevBwt &b, uint32_t k) {
+    uint32_t steps = 0;
+    while (k & 31u) {
+        ++steps;
+        if (k == b.primary) { k = 0; continue; }
+        uint32_t kk = k - (k > b.primary);          // stored index of row k's symbol
+        const uint4 *p = b.blocks + 2 * (size_t)(kk >> 6);
+        uint4 c = FQB_LDG4(p), w = FQB_LDG4(p + 1);
+        uint32_t j = kk & 63;
+        uint32_t word = j < 16 ? w.x : j < 32 ? w.y : j < 48 ? w.z : w.w;
+        uint32_t sym = (word >> ((15u - (j & 15u)) << 1)) & 3u;
+        uint32_t cnt[4];
+        occ4_block(c, w, j + 1, cnt);               // occ(k, sym): same block as the symbol itself
+        k = pick4(b.L2, sym) + pick4(cnt, sym);
+    }
+    return steps + b.sa[k >> 5];
+}
+
+// ---------------------------------------------------------------------------
+// width lower bounds, packed: w in the low 27 bits, min(bid, 31) above.
+// (bid is only ever compared with m <= max_diff < 31; gap_shadow stores bid = 1.)
+constexpr uint32_t kWidthBits = 27;
+constexpr uint32_t kWidthMask = (1u << kWidthBits) - 1;
+FQB_HD uint32_t pack_width(uint32_t w, int bid) { return w | ((uint32_t)(bid > 31 ? 31 : bid) << kWidthBits); }
+FQB_HD uint32_t width_w(uint32_t p) { return p & kWidthMask; }
+FQB_HD int width_bid(uint32_t p) { return (int)(p >> kWidthBits); }
+
+// read bases: `fwd` holds nt4 codes in read orientation.  The reference searches
+// seq[0] = reversed read and seq[1] = reverse complement (src/BwtMapper.cpp:580-587):
+// seq[a][i] = a ? comp(fwd[len-1-i]) : fwd[len-1-i].
+FQB_HD uint32_t read_sym(const uint8_t *fwd, int len, int a, int i) {
+    uint32_t c = fwd[len - 1 - i];
+    return (a && c < 4) ? 3 - c : c;
+}
+
+// bwt_cal_width over symbols [first, first+n) of strand-a sequence; writes n+1 packed entries
+FQB_HD void cal_width(const DevBwt &b, const uint8_t *fwd, int len, int a, int first, int n, uint32_t *out) {
+    uint32_t k = 0, l = b.seq_len;
+    int bid = 0;
+    for (int i = 0; i < n; ++i) {
+        uint32_t c = read_sym(fwd, len, a, first + i);
+        if (c < 4) {
+            uint32_t ck[4], cl[4];
+            occ4_pair(b, k - 1, l, ck, cl);
+            k = pick4(b.L2, c) + pick4(ck, c) + 1;
+            l = pick4(b.L2, c) + pick4(cl, c);
+        }
+        if (k > l || c > 3) { k = 0; l = b.seq_len; ++bid; }
+        out[i] = pack_width(l - k + 1, bid);
+    }
+    out[n] = pack_width(0, bid + 1);
+}
+
+// ---------------------------------------------------------------------------
+// search options (gap_opt_t fields used by bwt_match_gap) + per-read limits
+struct SearchOpt {
+    int s_mm, s_gapo, s_gape;
+    int mode;
+    int indel_end_skip, max_del_occ, max_entries;
+    int max_gapo, max_gape;
+    int max_seed_diff, seed_len;
+    int max_top2;
+    int n_buckets;
+};
+constexpr int kModeGapE = 0x01, kModeLogGap = 0x04, kModeNonStop = 0x10;
+constexpr int kStateM = 0, kStateI = 1, kStateD = 2;
+
+struct Hit { uint32_t k, l; int32_t score; uint8_t n_mm, n_gapo, n_gape, a; };   // == fqb_aln_t
+
+// One stack entry = 16 bytes.
+//   x = k, y = l,
+//   z = i:10 | a:1 | state:2 | n_mm:6 | n_gapo:4 | n_gape:5
+//   w = last_diff_pos:10 | prev:22   (prev = next-older entry of the same score bucket)
+constexpr uint32_t kNoSlot = 0x3fffffu;
+FQB_HD uint32_t pack_meta(int i, int a, int state, int mm, int go, int ge) {
+    return (uint32_t)i | (uint32_t)a << 10 | (uint32_t)state << 11 | (uint32_t)mm << 13 | (uint32_t)go << 19 | (uint32_t)ge << 23;
+}
+
+enum LaneStatus { kLaneRunning = 0, kLaneDone = 1, kLaneOverflow = 2 };
+
+// HeadT: uint16_t when the arena holds < 65535 entries (fast pass), uint32_t otherwise.
+template <typename HeadT>
+struct SearchLane {
+    // wiring
+    const DevBwt *bwt;         // [2]
+    const SearchOpt *opt;
+    const uint8_t *fwd;
+    uint32_t *w[2];            // packed widths, len+1 each (mutated by gap_shadow)
+    const uint32_t *sw[2];     // packed seed widths or nullptr
+    uint4 *arena;
+    HeadT *heads; int head_stride;
+    Hit *out; int out_cap;
+    uint32_t arena_cap;
+    // read state
+    int len, max_diff_opt, max_diff, best_score, best_cnt, n_aln, n_entries;
+    uint64_t mask0, mask1;     // non-empty score buckets
+    uint32_t top, free_head, spare;
+    // current entry
+    uint32_t k, l;
+    int i, a, state, n_mm, n_gapo, n_gape, ldp;
+    bool have_cur, exact_mode, overflow;
+    // statistics (for ncu-independent accounting; cheap)
+    uint32_t n_pops, n_occ;
+
+    FQB_HD int score3(int mm, int go, int ge) const { return mm * opt->s_mm + go * opt->s_gapo + ge * opt->s_gape; }
+    FQB_HD HeadT &head(int s) { return heads[(size_t)s * head_stride]; }
+    FQB_HD uint32_t *wa() const { return a ? w[1] : w[0]; }
+    FQB_HD const uint32_t *swa() const { return a ? sw[1] : sw[0]; }
+    FQB_HD bool bucket_set(int s) const { return s < 64 ? (mask0 >> s) & 1 : (mask1 >> (s - 64)) & 1; }
+
+    FQB_HD uint32_t alloc_slot() {
+        uint32_t s;
+        if (spare != kNoSlot) { s = spare; spare = kNoSlot; return s; }
+        if (free_head != kNoSlot) { s = free_head; free_head = arena[s].w & kNoSlot; return s; }
+        if (top < arena_cap) return top++;
+        overflow = true;
+        return kNoSlot;
+    }
+    FQB_HD void release_slot(uint32_t s) {
+        if (spare == kNoSlot) { spare = s; return; }
+        arena[spare].w = free_head;
+        free_head = spare;
+        spare = s;
+    }
+
+    // gap_push (libbwa/bwtgap.c:45-64)
+    FQB_HD void push(int pa, int pi, uint32_t pk, uint32_t pl, int mm, int go, int ge, int st, int pldp) {
+        int sc = score3(mm, go, ge);
+        uint32_t s = alloc_slot();
+        ++n_entries;
+        if (s == kNoSlot) return;
+        uint32_t prev = bucket_set(sc) ? (uint32_t)head(sc) : kNoSlot;
+        arena[s] = make_uint4(pk, pl, pack_meta(pi, pa, st, mm, go, ge), (uint32_t)pldp << 22 | prev);
+        head(sc) = (HeadT)s;
+        if (sc < 64) mask0 |= 1ull << sc; else mask1 |= 1ull << (sc - 64);
+    }
+
+    // gap_pop (libbwa/bwtgap.c:66-79); the exact-match child of the previous expansion is
+    // always the next entry popped, so it never leaves registers.
+    FQB_HD void pop() {
+        --n_entries;
+        ++n_pops;
+        if (have_cur) { have_cur = false; return; }
+        int b = mask0 ? FQB_FFSLL(mask0) - 1 : 63 + FQB_FFSLL(mask1);
+        uint32_t s = (uint32_t)head(b);
+        uint4 e = arena[s];
+        uint32_t prev = e.w & kNoSlot;
+        if (prev == kNoSlot) { if (b < 64) mask0 &= ~(1ull << b); else mask1 &= ~(1ull << (b - 64)); }
+        else head(b) = (HeadT)prev;
+        release_slot(s);
+        k = e.x; l = e.y;
+        i = e.z & 1023; a = (e.z >> 10) & 1; state = (e.z >> 11) & 3;
+        n_mm = (e.z >> 13) & 63; n_gapo = (e.z >> 19) & 15; n_gape = (e.z >> 23) & 31;
+        ldp = (int)(e.w >> 22);
+    }
+
+    // bwt_match_gap prologue (libbwa/bwtgap.c:104-128)
+    FQB_HD LaneStatus begin(int read_len, int read_max_diff) {
+        len = read_len; max_diff_opt = max_diff = read_max_diff;
+        best_score = score3(max_diff_opt + 1, opt->max_gapo + 1, opt->max_gape + 1);
+        best_cnt = 0; n_aln = 0; n_entries = 0;
+        mask0 = mask1 = 0; top = 0; free_head = spare = kNoSlot;
+        have_cur = false; exact_mode = false; overflow = false;
+        n_pops = n_occ = 0;
+        int n_N = 0;
+        for (int j = 0; j < len; ++j) n_N += fwd[j] > 3;
+        if (n_N > max_diff) return kLaneDone;
+        push(0, len, 0, bwt[0].seq_len, 0, 0, 0, kStateM, 0);
+        // second root (strand 1) is the top of bucket 0: keep it in registers
+        k = 0; l = bwt[0].seq_len; i = len; a = 1; state = kStateM; n_mm = n_gapo = n_gape = 0; ldp = 0;
+        have_cur = true; ++n_entries;
+        return overflow ? kLaneOverflow : kLaneRunning;
+    }
+
+    // a hit: libbwa/bwtgap.c:163-199.  Returns true when the search must stop (top2b rule).
+    FQB_HD bool on_hit() {
+        int sc = score3(n_mm, n_gapo, n_gape);
+        if (n_aln == 0) {
+            best_score = sc;
+            int best_diff = n_mm + n_gapo + ((opt->mode & kModeGapE) ? n_gape : 0);
+            if (!(opt->mode & kModeNonStop)) max_diff = (best_diff + 1 > max_diff_opt) ? max_diff_opt : best_diff + 1;
+        }
+        if (sc == best_score) best_cnt += (int)(l - k + 1);
+        else if (best_cnt > opt->max_top2) return true;
+        bool add = true;
+        if (n_gapo) {
+            int n_cmp = n_aln < out_cap ? n_aln : out_cap;
+            for (int j = 0; j < n_cmp; ++j)
+                if (out[j].k == k && out[j].l == l) { add = false; break; }
+        }
+        if (add) {
+            // gap_shadow (libbwa/bwtgap.c:81-91)
+            uint32_t x = l - k + 1, maxv = bwt[1 - a].seq_len;
+            uint32_t *wa_ = wa();
+            int jj = 0;
+            for (int p = 0; p < ldp; ++p) {
+                uint32_t v = wa_[p], ww = width_w(v);
+                if (ww > x) wa_[p] = v - x;
+                else if (ww == x) wa_[p] = pack_width(maxv - (uint32_t)(++jj), 1);
+            }
+            if (n_aln < out_cap) {
+                Hit h; h.k = k; h.l = l; h.score = sc;
+                h.n_mm = (uint8_t)n_mm; h.n_gapo = (uint8_t)n_gapo; h.n_gape = (uint8_t)n_gape; h.a = (uint8_t)a;
+                out[n_aln] = h;
+            } else overflow = true;
+            ++n_aln;
+        }
+        return false;
+    }
+
+    // One iteration: consume stack entries until one needs a rank query, do the query,
+    // then either continue the exact-match tail (bwt_match_exact_alt) or expand children.
+    FQB_HD LaneStatus step() {
+        if (!exact_mode) {
+            for (;;) {
+                if (n_entries == 0) return kLaneDone;
+                if (n_entries > opt->max_entries) return kLaneDone;
+                pop();
+                if (!(opt->mode & kModeNonStop) && score3(n_mm, n_gapo, n_gape) > best_score + opt->s_mm) return kLaneDone;
+                int m = max_diff - (n_mm + n_gapo) - ((opt->mode & kModeGapE) ? n_gape : 0);
+                if (m < 0) continue;
+                if (i > 0 && m < width_bid(wa()[i - 1])) continue;
+                if (i == 0) { if (on_hit()) return kLaneDone; if (overflow) return kLaneOverflow; continue; }
+                if (m == 0 && (state == kStateM || (opt->mode & kModeGapE) || n_gape == opt->max_gape)) {
+                    if (read_sym(fwd, len, a, i - 1) > 3) continue;      // bwt_match_exact_alt: N never matches
+                    exact_mode = true;
+                }
+                break;
+            }
+        }
+        const DevBwt &b = bwt[1 - a];
+        uint32_t ck[4], cl[4];
+        occ4_pair(b, k - 1, l, ck, cl);
+        ++n_occ;
+
+        if (exact_mode) {                           // one step of bwt_match_exact_alt (libbwa/bwt.c:102-117)
+            uint32_t c = read_sym(fwd, len, a, i - 1);
+            k = pick4(b.L2, c) + pick4(ck, c) + 1;
+            l = pick4(b.L2, c) + pick4(cl, c);
+            --i;
+            if (k > l) { exact_mode = false; return kLaneRunning; }
+            if (i == 0) {
+                exact_mode = false;
+                if (on_hit()) return kLaneDone;
+                return overflow ? kLaneOverflow : kLaneRunning;
+            }
+            if (read_sym(fwd, len, a, i - 1) > 3) exact_mode = false;
+            return kLaneRunning;
+        }
+
+        // expansion: libbwa/bwtgap.c:201-259
+        int m = max_diff - (n_mm + n_gapo) - ((opt->mode & kModeGapE) ? n_gape : 0);
+        int m_seed = opt->max_seed_diff - (n_mm + n_gapo) - ((opt->mode & kModeGapE) ? n_gape : 0);
+        --i;
+        uint32_t occ = l - k + 1;
+        bool allow_diff = true, allow_M = true;
+        if (i > 0) {
+            uint32_t wl = wa()[i - 1], wh = wa()[i];
+            if (width_bid(wl) > m - 1) allow_diff = false;
+            else if (width_bid(wl) == m - 1 && width_bid(wh) == m - 1 && width_w(wl) == width_w(wh)) allow_M = false;
+            int ii = i - (len - opt->seed_len);
+            if (sw[0] && ii > 0) {
+                uint32_t sl = swa()[ii - 1], sh = swa()[ii];
+                if (width_bid(sl) > m_seed - 1) allow_diff = false;
+                else if (width_bid(sl) == m_seed - 1 && width_bid(sh) == m_seed - 1 && width_w(sl) == width_w(sh)) allow_M = false;
+            }
+        }
+        int gaps = n_gapo + n_gape;
+        if (opt->mode & kModeLogGap) { int v = gaps, c = 0; while (v >>= 1) ++c; gaps = c / 2 + 1; }
+        if (allow_diff && i >= opt->indel_end_skip + gaps && len - i >= opt->indel_end_skip + gaps) {
+            if (state == kStateM) {
+                if (n_gapo < opt->max_gapo) {
+                    push(a, i, k, l, n_mm, n_gapo + 1, n_gape, kStateI, i);
+                    _Pragma("unroll")
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t kk = b.L2[j] + ck[j] + 1, ll = b.L2[j] + cl[j];
+                        if (kk <= ll) push(a, i + 1, kk, ll, n_mm, n_gapo + 1, n_gape, kStateD, i + 1);
+                    }
+                }
+            } else if (state == kStateI) {
+                if (n_gape < opt->max_gape) push(a, i, k, l, n_mm, n_gapo, n_gape + 1, kStateI, i);
+            } else {
+                if (n_gape < opt->max_gape && (n_gape + n_gapo < max_diff || occ < (uint32_t)opt->max_del_occ)) {
+                    _Pragma("unroll")
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t kk = b.L2[j] + ck[j] + 1, ll = b.L2[j] + cl[j];
+                        if (kk <= ll) push(a, i + 1, kk, ll, n_mm, n_gapo, n_gape + 1, kStateD, i + 1);
+                    }
+                }
+            }
+        }
+        uint32_t s = read_sym(fwd, len, a, i);
+        bool keep = false;
+        uint32_t nk = 0, nl = 0;
+        if (allow_diff && allow_M) {
+            _Pragma("unroll")
+            for (int j = 1; j <= 4; ++j) {
+                uint32_t c = (s + j) & 3;
+                bool is_mm = (j != 4 || s > 3);
+                uint32_t kk = pick4(b.L2, c) + pick4(ck, c) + 1, ll = pick4(b.L2, c) + pick4(cl, c);
+                if (kk > ll) continue;
+                if (is_mm) push(a, i, kk, ll, n_mm + 1, n_gapo, n_gape, kStateM, i);
+                else { keep = true; nk = kk; nl = ll; }
+            }
+        } else if (s < 4) {
+            uint32_t kk = pick4(b.L2, s) + pick4(ck, s) + 1, ll = pick4(b.L2, s) + pick4(cl, s);
+            if (kk <= ll) { keep = true; nk = kk; nl = ll; }
+        }
+        if (keep) {      // exact child: pushed last into the parent's own bucket, hence popped next;
+            k = nk; l = nl; state = kStateM; have_cur = true; ++n_entries;   // inherits last_diff_pos
+        }
+        return overflow ? kLaneOverflow : kLaneRunning;
+    }
+};
+
+}  // namespace fqb

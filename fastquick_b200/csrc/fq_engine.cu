@@ -1,0 +1,396 @@
+// Engine: owns the device-resident index and the per-batch device buffers, and
+// sequences the kernels of the hot path on one CUDA stream.  Exposed through the C
+// ABI in include/fastquick_b200.h.  One engine per GPU (one process per GPU).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fastquick_b200.h"
+#include "fq_common.h"
+#include "fq_hostmath.h"
+#include "fq_index.h"
+#include "fq_kernels.cuh"
+#include "fq_relayout.h"
+#include "fq_synth.h"
+
+std::vector<fqb::FlankSeq> fqb_synth_flanks_internal(const fqb_synth *s);
+
+using namespace fqb;
+
+#define CU_CHECK(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(e_));                      \
+            return FQB_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+namespace {
+constexpr int kAlnCapFast = 8;          // hits kept per read in the fast pass
+constexpr int kAlnCapSlow = 1024;       // per read in the overflow pass
+constexpr uint32_t kArenaFast = 2048;   // stack entries per lane (observed peaks ~1.2k)
+}  // namespace
+
+struct fqb_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    HostIndex hidx;
+    fqb_gap_opt_t gopt;
+    fqb_pe_opt_t popt;
+    // device index
+    uint4 *d_blocks[2] = {nullptr, nullptr};
+    uint32_t *d_sa[2] = {nullptr, nullptr};
+    uint8_t *d_pac = nullptr, *d_roll = nullptr;
+    DevBwt dbwt[2];
+    int32_t *d_maxdiff = nullptr;
+    int32_t h_maxdiff[FQB_MAX_READ_LEN + 1];
+    // batch buffers
+    int cap_reads = 0, lpad = 0, stride_cap = 0;
+    int n_reads = 0, stride = 0;
+    uint8_t *d_in[4] = {nullptr, nullptr, nullptr, nullptr};   // bases1, quals1, bases2, quals2 (staging for host input)
+    int32_t *d_lens_in[2] = {nullptr, nullptr};
+    BatchView bv;
+    WidthView wv;
+    Hit *d_aln = nullptr;
+    int32_t *d_naln = nullptr;
+    uint32_t *d_overflow = nullptr;
+    uint32_t *d_ctrs = nullptr;          // [0] n_work [1] cursor [2] n_overflow [3] cursor2
+    unsigned long long *d_counters = nullptr;
+    // search infrastructure
+    int n_blocks16 = 0;
+    uint4 *d_arena = nullptr;
+    uint4 *d_arena_big = nullptr;
+    uint32_t arena_big_cap = 0;
+    Hit *d_aln_big = nullptr;
+    int32_t *d_spill_slot = nullptr;     // per read: row in d_aln_big or -1
+    int n_spill_cap = 0;
+    std::vector<uint32_t> h_overflow;
+    SearchOpt sopt;
+    bool batch_ready = false;
+};
+
+static void free_batch(fqb_handle *h) {
+    for (auto &p : h->d_in) { cudaFree(p); p = nullptr; }
+    for (auto &p : h->d_lens_in) { cudaFree(p); p = nullptr; }
+    cudaFree(h->bv.codes); cudaFree(h->bv.qual); cudaFree(h->bv.len); cudaFree(h->bv.full_len);
+    cudaFree(h->bv.filtered); cudaFree(h->bv.work);
+    cudaFree(h->wv.w); cudaFree(h->wv.sw);
+    cudaFree(h->d_aln); cudaFree(h->d_naln); cudaFree(h->d_overflow); cudaFree(h->d_spill_slot);
+    memset(&h->bv, 0, sizeof(h->bv)); memset(&h->wv, 0, sizeof(h->wv));
+    h->d_aln = nullptr; h->d_naln = nullptr; h->d_overflow = nullptr; h->d_spill_slot = nullptr;
+    h->cap_reads = 0;
+}
+
+static int ensure_batch(fqb_handle *h, int n_reads, int stride) {
+    if (n_reads <= h->cap_reads && stride <= h->stride_cap) return FQB_OK;
+    free_batch(h);
+    int cap = n_reads > 2 * FQB_BATCH_PAIRS ? n_reads : (n_reads > 65536 ? 2 * FQB_BATCH_PAIRS : 65536 * 2);
+    int lpad = (stride + 15) & ~15;
+    for (int i = 0; i < 4; ++i) CU_CHECK(cudaMalloc(&h->d_in[i], (size_t)(cap / 2) * stride));
+    for (int i = 0; i < 2; ++i) CU_CHECK(cudaMalloc(&h->d_lens_in[i], (size_t)(cap / 2) * 4));
+    CU_CHECK(cudaMalloc(&h->bv.codes, (size_t)cap * lpad));
+    CU_CHECK(cudaMalloc(&h->bv.qual, (size_t)cap * lpad));
+    CU_CHECK(cudaMalloc(&h->bv.len, (size_t)cap * 4));
+    CU_CHECK(cudaMalloc(&h->bv.full_len, (size_t)cap * 4));
+    CU_CHECK(cudaMalloc(&h->bv.filtered, (size_t)cap));
+    CU_CHECK(cudaMalloc(&h->bv.work, (size_t)cap * 4));
+    h->wv.wstride = stride + 1;
+    h->wv.sstride = h->gopt.seed_len + 1;
+    CU_CHECK(cudaMalloc(&h->wv.w, (size_t)cap * 2 * h->wv.wstride * 4));
+    CU_CHECK(cudaMalloc(&h->wv.sw, (size_t)cap * 2 * h->wv.sstride * 4));
+    CU_CHECK(cudaMalloc(&h->d_aln, (size_t)cap * kAlnCapFast * sizeof(Hit)));
+    CU_CHECK(cudaMalloc(&h->d_naln, (size_t)cap * 4));
+    CU_CHECK(cudaMalloc(&h->d_overflow, (size_t)cap * 2 * 4));
+    CU_CHECK(cudaMalloc(&h->d_spill_slot, (size_t)cap * 4));
+    h->cap_reads = cap; h->lpad = lpad; h->stride_cap = stride;
+    return FQB_OK;
+}
+
+extern "C" {
+
+static int create_common(fqb_handle *h, int device, fqb_handle **out);
+static int check_device(int device) {
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        set_error("no CUDA device: fastquick_b200 has no CPU fallback");
+        return FQB_ERR_CUDA;
+    }
+    if (device < 0 || device >= n_dev) { set_error("bad device ordinal"); return FQB_ERR_ARG; }
+    return FQB_OK;
+}
+
+int fqb_create(const char *index_prefix, const fqb_gap_opt_t *gopt, const fqb_pe_opt_t *popt, int device, fqb_handle **out) {
+    if (!index_prefix || !out) { set_error("null argument"); return FQB_ERR_ARG; }
+    if (int rc = check_device(device)) return rc;
+    fqb_handle *h = new fqb_handle();
+    if (gopt) h->gopt = *gopt; else fqb_gap_opt_default(&h->gopt);
+    if (popt) h->popt = *popt; else fqb_pe_opt_default(&h->popt);
+    std::string err;
+    if (!load_index(index_prefix, false, h->hidx, err)) { set_error(err); delete h; return FQB_ERR_IO; }
+    return create_common(h, device, out);
+}
+
+// same engine over an index built in memory from synthetic flanks (bench/tests; skips the 3 GiB .rollhash round trip)
+int fqb_create_from_synth(const fqb_synth *s, const fqb_gap_opt_t *gopt, const fqb_pe_opt_t *popt, int device, fqb_handle **out) {
+    if (!s || !out) { set_error("null argument"); return FQB_ERR_ARG; }
+    if (int rc = check_device(device)) return rc;
+    fqb_handle *h = new fqb_handle();
+    if (gopt) h->gopt = *gopt; else fqb_gap_opt_default(&h->gopt);
+    if (popt) h->popt = *popt; else fqb_pe_opt_default(&h->popt);
+    build_index_from_flanks(fqb_synth_flanks_internal(s), h->gopt.kmer_thresh != 0, h->hidx);
+    return create_common(h, device, out);
+}
+
+static int create_common(fqb_handle *h, int device, fqb_handle **out) {
+    h->device = device;
+    if ((uint64_t)h->hidx.bwt[0].seq_len + 1 >= (1ull << kWidthBits)) {
+        set_error("reduced reference too long for the packed width table (limit 2^27 bases)");
+        delete h; return FQB_ERR_LIMIT;
+    }
+    fill_maxdiff_table(h->gopt, h->h_maxdiff);
+    for (int l = 0; l <= FQB_MAX_READ_LEN; ++l)
+        if (h->h_maxdiff[l] > 30) { set_error("max_diff > 30 is not supported"); delete h; return FQB_ERR_LIMIT; }
+    if (h->gopt.max_gapo > 14 || h->gopt.max_gape > 30 || h->gopt.seed_len > 255 || h->gopt.s_mm < 1 || h->gopt.s_gapo < 1 || h->gopt.s_gape < 1) {
+        set_error("gap options outside the supported range"); delete h; return FQB_ERR_LIMIT;
+    }
+#define CU_CHECK_H(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); fqb_destroy(h); return FQB_ERR_CUDA; } } while (0)
+    CU_CHECK_H(cudaSetDevice(device));
+    CU_CHECK_H(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; ++s) {
+        std::vector<Block32> blocks;
+        relayout_bwt(h->hidx.bwt[s], blocks);
+        CU_CHECK_H(cudaMalloc(&h->d_blocks[s], blocks.size() * sizeof(Block32)));
+        CU_CHECK_H(cudaMemcpy(h->d_blocks[s], blocks.data(), blocks.size() * sizeof(Block32), cudaMemcpyHostToDevice));
+        CU_CHECK_H(cudaMalloc(&h->d_sa[s], h->hidx.bwt[s].sa.size() * 4));
+        CU_CHECK_H(cudaMemcpy(h->d_sa[s], h->hidx.bwt[s].sa.data(), h->hidx.bwt[s].sa.size() * 4, cudaMemcpyHostToDevice));
+        DevBwt &d = h->dbwt[s];
+        d.blocks = h->d_blocks[s]; d.sa = h->d_sa[s];
+        d.primary = h->hidx.bwt[s].primary; d.seq_len = h->hidx.bwt[s].seq_len;
+        for (int i = 0; i < 5; ++i) d.L2[i] = h->hidx.bwt[s].L2[i];
+        d.n_blocks = (uint32_t)blocks.size();
+    }
+    CU_CHECK_H(cudaMalloc(&h->d_pac, h->hidx.pac.size()));
+    CU_CHECK_H(cudaMemcpy(h->d_pac, h->hidx.pac.data(), h->hidx.pac.size(), cudaMemcpyHostToDevice));
+    CU_CHECK_H(cudaMalloc(&h->d_maxdiff, sizeof(h->h_maxdiff)));
+    CU_CHECK_H(cudaMemcpy(h->d_maxdiff, h->h_maxdiff, sizeof(h->h_maxdiff), cudaMemcpyHostToDevice));
+    CU_CHECK_H(cudaMalloc(&h->d_ctrs, 16 * 4));
+    CU_CHECK_H(cudaMalloc(&h->d_counters, 4 * 8));
+    CU_CHECK_H(cudaMemset(h->d_counters, 0, 4 * 8));
+    if (h->gopt.kmer_thresh != 0) {     // 6 x 512 MiB bitmaps, streamed from disk (BwtIndexer::ReadRollHashTable)
+        const size_t total = kRollTableBytes * kNumRollTables;
+        CU_CHECK_H(cudaMalloc(&h->d_roll, total));
+        if (h->hidx.rollhash.size() == total) {
+            CU_CHECK_H(cudaMemcpy(h->d_roll, h->hidx.rollhash.data(), total, cudaMemcpyHostToDevice));
+            std::vector<uint8_t>().swap(h->hidx.rollhash);
+        } else {
+            FILE *fp = fopen(h->hidx.rollhash_path.c_str(), "rb");
+            if (!fp) { set_error("cannot open " + h->hidx.rollhash_path); fqb_destroy(h); return FQB_ERR_IO; }
+            const size_t chunk = 64u << 20;
+            std::vector<uint8_t> buf(chunk);
+            size_t done = 0;
+            while (done < total) {
+                size_t want = total - done < chunk ? total - done : chunk;
+                if (fread(buf.data(), 1, want, fp) != want) { fclose(fp); set_error("short .rollhash"); fqb_destroy(h); return FQB_ERR_IO; }
+                CU_CHECK_H(cudaMemcpy(h->d_roll + done, buf.data(), want, cudaMemcpyHostToDevice));
+                done += want;
+            }
+            fclose(fp);
+        }
+    }
+    *out = h;
+    return FQB_OK;
+}
+
+void fqb_destroy(fqb_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    free_batch(h);
+    for (int s = 0; s < 2; ++s) { cudaFree(h->d_blocks[s]); cudaFree(h->d_sa[s]); }
+    cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_ctrs); cudaFree(h->d_counters);
+    cudaFree(h->d_arena); cudaFree(h->d_arena_big); cudaFree(h->d_aln_big);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int fqb_index_info(const fqb_handle *h, int64_t *l_pac, int32_t *n_contigs, uint32_t *primary, uint32_t *seed) {
+    if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    if (l_pac) *l_pac = h->hidx.l_pac;
+    if (n_contigs) *n_contigs = (int32_t)h->hidx.contigs.size();
+    if (primary) { primary[0] = h->hidx.bwt[0].primary; primary[1] = h->hidx.bwt[1].primary; }
+    if (seed) *seed = h->hidx.seed;
+    return FQB_OK;
+}
+
+// ---- stage-level entry points ------------------------------------------------
+
+int fqb_stage_load(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
+                   const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device) {
+    if (!h || n_pairs < 0 || stride < 1 || stride > FQB_MAX_READ_LEN) { set_error("bad batch shape"); return FQB_ERR_ARG; }
+    CU_CHECK(cudaSetDevice(h->device));
+    int rc = ensure_batch(h, 2 * n_pairs, stride);
+    if (rc) return rc;
+    h->n_reads = 2 * n_pairs; h->stride = stride;
+    const uint8_t *src[4] = {bases1, quals1, bases2, quals2};
+    const int32_t *lsrc[2] = {lens1, lens2};
+    BatchView &b = h->bv;
+    b.n_reads = h->n_reads; b.stride_in = stride; b.lpad = h->lpad;
+    size_t bytes = (size_t)n_pairs * stride;
+    if (on_device) {
+        b.bases_in[0] = bases1; b.quals_in[0] = quals1; b.bases_in[1] = bases2; b.quals_in[1] = quals2;
+        b.lens_in[0] = lens1; b.lens_in[1] = lens2;
+    } else {
+        for (int i = 0; i < 4; ++i) CU_CHECK(cudaMemcpyAsync(h->d_in[i], src[i], bytes, cudaMemcpyHostToDevice, h->stream));
+        for (int i = 0; i < 2; ++i)
+            if (lsrc[i]) CU_CHECK(cudaMemcpyAsync(h->d_lens_in[i], lsrc[i], (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
+        b.bases_in[0] = h->d_in[0]; b.quals_in[0] = h->d_in[1]; b.bases_in[1] = h->d_in[2]; b.quals_in[1] = h->d_in[3];
+        b.lens_in[0] = lens1 ? h->d_lens_in[0] : nullptr; b.lens_in[1] = lens2 ? h->d_lens_in[1] : nullptr;
+    }
+    b.n_work = h->d_ctrs;
+    h->batch_ready = true;
+    return FQB_OK;
+}
+
+// a1..a5 on the resident batch: prep -> widths -> search (+ overflow pass with the big arena)
+int fqb_stage_align(fqb_handle *h) {
+    if (!h || !h->batch_ready) { set_error("no batch loaded"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    CU_CHECK(cudaMemsetAsync(h->d_ctrs, 0, 16 * 4, st));
+    PrepParams pp;
+    pp.trim_qual = h->gopt.trim_qual; pp.kmer_thresh = h->gopt.kmer_thresh; pp.is_il13 = h->gopt.is_il13; pp.roll = h->d_roll;
+    launch_prep(h->bv, pp, st);
+    launch_width(h->bv, h->wv, h->dbwt, h->gopt.seed_len, h->bv.work, h->bv.n_work, h->n_reads, st);
+
+    h->sopt = make_search_opt(h->gopt, h->stride);
+    if (h->sopt.n_buckets > 128) { set_error("more than 128 score buckets"); return FQB_ERR_LIMIT; }
+    if (!h->d_arena) {
+        h->n_blocks16 = search_grid_blocks(h->sopt.n_buckets, true, h->device);
+        CU_CHECK(cudaMalloc(&h->d_arena, (size_t)h->n_blocks16 * kSearchThreads * kArenaFast * sizeof(uint4)));
+    }
+    SearchParams sp;
+    sp.bwt[0] = h->dbwt[0]; sp.bwt[1] = h->dbwt[1];
+    sp.opt = h->sopt; sp.maxdiff = h->d_maxdiff; sp.seed_len_opt = h->gopt.seed_len;
+    sp.work = h->bv.work; sp.n_work = h->d_ctrs; sp.cursor = h->d_ctrs + 1;
+    sp.arena = h->d_arena; sp.arena_cap = kArenaFast;
+    sp.aln = h->d_aln; sp.aln_cap = kAlnCapFast; sp.n_aln = h->d_naln; sp.aln_row = nullptr;
+    sp.overflow = h->d_overflow; sp.n_overflow = h->d_ctrs + 2;
+    sp.counters = h->d_counters;
+    CU_CHECK(cudaMemsetAsync(h->d_naln, 0, (size_t)h->n_reads * 4, st));
+    CU_CHECK(cudaMemsetAsync(h->d_spill_slot, 0xff, (size_t)h->n_reads * 4, st));
+    launch_search(h->bv, h->wv, sp, true, h->n_blocks16, st);
+    CU_CHECK(cudaGetLastError());
+
+    uint32_t n_over = 0;
+    CU_CHECK(cudaMemcpyAsync(&n_over, h->d_ctrs + 2, 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    if (n_over) {       // rare: redo these reads with an arena as deep as the reference allows (max_entries)
+        if ((int)n_over > h->n_spill_cap) {
+            cudaFree(h->d_aln_big);
+            h->n_spill_cap = (int)n_over + 1024;
+            CU_CHECK(cudaMalloc(&h->d_aln_big, (size_t)h->n_spill_cap * kAlnCapSlow * sizeof(Hit)));
+        }
+        if (!h->d_arena_big) {
+            h->arena_big_cap = (uint32_t)h->gopt.max_entries + 64;
+            CU_CHECK(cudaMalloc(&h->d_arena_big, (size_t)kSearchThreads * h->arena_big_cap * sizeof(uint4)));
+        }
+        h->h_overflow.resize(n_over);
+        CU_CHECK(cudaMemcpyAsync(h->h_overflow.data(), h->d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+        // widths were mutated by gap_shadow before the overflow: recompute them for these reads
+        launch_width(h->bv, h->wv, h->dbwt, h->gopt.seed_len, h->d_overflow, h->d_ctrs + 2, (int)n_over, st);
+        std::vector<int32_t> slots(n_over);
+        for (uint32_t j = 0; j < n_over; ++j) {
+            slots[j] = (int32_t)j;
+            CU_CHECK(cudaMemcpyAsync(h->d_spill_slot + h->h_overflow[j], &slots[j], 4, cudaMemcpyHostToDevice, st));
+        }
+        uint32_t ctr[3] = {n_over, 0u, 0u};            // n_work, cursor, second-level overflow count
+        CU_CHECK(cudaMemcpyAsync(h->d_ctrs + 4, ctr, 12, cudaMemcpyHostToDevice, st));
+        SearchParams s2 = sp;
+        s2.work = h->d_overflow; s2.n_work = h->d_ctrs + 4; s2.cursor = h->d_ctrs + 5;
+        s2.arena = h->d_arena_big; s2.arena_cap = h->arena_big_cap;
+        s2.aln = h->d_aln_big; s2.aln_cap = kAlnCapSlow; s2.aln_row = h->d_spill_slot;
+        s2.overflow = h->d_overflow + h->cap_reads; s2.n_overflow = h->d_ctrs + 6;
+        s2.counters = nullptr;
+        launch_search(h->bv, h->wv, s2, false, 1, st);
+        CU_CHECK(cudaGetLastError());
+        CU_CHECK(cudaStreamSynchronize(st));
+        uint32_t still = 0;
+        CU_CHECK(cudaMemcpy(&still, h->d_ctrs + 6, 4, cudaMemcpyDeviceToHost));
+        if (still) { set_error("a read overflowed even the max_entries-deep arena or 1024 hits"); return FQB_ERR_LIMIT; }
+    }
+    return FQB_OK;
+}
+
+int fqb_stage_fetch_prep(fqb_handle *h, int32_t *len, int32_t *full_len, uint8_t *filtered, uint8_t *codes, int32_t codes_stride) {
+    if (!h || !h->batch_ready) { set_error("no batch loaded"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    CU_CHECK(cudaStreamSynchronize(h->stream));
+    size_t n = (size_t)h->n_reads;
+    if (len) CU_CHECK(cudaMemcpy(len, h->bv.len, n * 4, cudaMemcpyDeviceToHost));
+    if (full_len) CU_CHECK(cudaMemcpy(full_len, h->bv.full_len, n * 4, cudaMemcpyDeviceToHost));
+    if (filtered) CU_CHECK(cudaMemcpy(filtered, h->bv.filtered, n, cudaMemcpyDeviceToHost));
+    if (codes) CU_CHECK(cudaMemcpy2D(codes, (size_t)codes_stride, h->bv.codes, (size_t)h->lpad, (size_t)h->stride, n, cudaMemcpyDeviceToHost));
+    return FQB_OK;
+}
+
+// hits per read r = 2*pair+end, padded to `cap` rows; n_aln[r] is the true count
+int fqb_stage_fetch_aln(fqb_handle *h, int32_t cap, fqb_aln_t *out, int32_t *n_aln) {
+    if (!h || !h->batch_ready || cap < 1) { set_error("no batch loaded"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    CU_CHECK(cudaStreamSynchronize(h->stream));
+    size_t n = (size_t)h->n_reads;
+    std::vector<Hit> fast(n * kAlnCapFast);
+    std::vector<int32_t> cnt(n), slot(n);
+    CU_CHECK(cudaMemcpy(fast.data(), h->d_aln, fast.size() * sizeof(Hit), cudaMemcpyDeviceToHost));
+    CU_CHECK(cudaMemcpy(cnt.data(), h->d_naln, n * 4, cudaMemcpyDeviceToHost));
+    CU_CHECK(cudaMemcpy(slot.data(), h->d_spill_slot, n * 4, cudaMemcpyDeviceToHost));
+    std::vector<Hit> row(kAlnCapSlow);
+    memset(out, 0, n * (size_t)cap * sizeof(fqb_aln_t));
+    for (size_t r = 0; r < n; ++r) {
+        const Hit *src = &fast[r * kAlnCapFast];
+        int have = kAlnCapFast;
+        if (slot[r] >= 0) {
+            CU_CHECK(cudaMemcpy(row.data(), h->d_aln_big + (size_t)slot[r] * kAlnCapSlow, sizeof(Hit) * kAlnCapSlow, cudaMemcpyDeviceToHost));
+            src = row.data(); have = kAlnCapSlow;
+        }
+        int m = cnt[r] < cap ? cnt[r] : cap;
+        if (m > have) m = have;
+        for (int j = 0; j < m; ++j) {
+            fqb_aln_t &o = out[r * (size_t)cap + j];
+            o.k = src[j].k; o.l = src[j].l; o.score = src[j].score;
+            o.n_mm = src[j].n_mm; o.n_gapo = src[j].n_gapo; o.n_gape = src[j].n_gape; o.a = src[j].a;
+        }
+        if (n_aln) n_aln[r] = cnt[r];
+    }
+    return FQB_OK;
+}
+
+// [0] stack pops, [1] rank-query pairs issued by the search kernel since creation, [2] overflow reads of the last batch
+int fqb_stage_counters(fqb_handle *h, uint64_t *out3) {
+    if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    CU_CHECK(cudaSetDevice(h->device));
+    CU_CHECK(cudaStreamSynchronize(h->stream));
+    unsigned long long c[2];
+    uint32_t ov = 0;
+    CU_CHECK(cudaMemcpy(c, h->d_counters, 16, cudaMemcpyDeviceToHost));
+    CU_CHECK(cudaMemcpy(&ov, h->d_ctrs + 2, 4, cudaMemcpyDeviceToHost));
+    out3[0] = c[0]; out3[1] = c[1]; out3[2] = ov;
+    return FQB_OK;
+}
+
+int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
+                    const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2,
+                    fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out) {
+    (void)h; (void)n_pairs; (void)stride; (void)bases1; (void)quals1; (void)lens1; (void)bases2; (void)quals2; (void)lens2;
+    (void)rows1; (void)rows2; (void)ii_out;
+    set_error("fqb_align_pairs: pair resolution stages are not built yet (use the fqb_stage_* entry points)");
+    return FQB_ERR_STATE;
+}
+
+void *fqb_stream(fqb_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+}  // extern "C"

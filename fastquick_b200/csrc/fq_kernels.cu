@@ -1,0 +1,259 @@
+// CUDA kernels of the align hot path, hand-written for sm_100a.
+//   prep_kernel    a1+a2: nt4 encode, bwa_trim_read, k-mer pre-filter (warp per read)
+//   width_kernel   a3:    bwt_cal_width (thread per read x {strand, full|seed})
+//   search_kernel  a4+a5: bwt_match_gap, one read per lane, persistent lanes with a
+//                         warp-aggregated work queue; score-bucket heads in shared
+//                         memory, entry arena in (L2-backed) global memory
+#include "fq_kernels.cuh"
+
+#include <climits>
+#include "../../include/fastquick_b200.h"
+
+namespace fqb {
+
+#define FULL_MASK 0xffffffffu
+
+// nst_nt4_table (libbwa/bntseq.c:38-55)
+__device__ __forceinline__ uint32_t nt4_code(uint32_t ch) {
+    uint32_t u = ch & 0xDFu;                       // fold case for letters
+    uint32_t c = 4;
+    c = (u == 'A') ? 0u : c;
+    c = (u == 'C') ? 1u : c;
+    c = (u == 'G') ? 2u : c;
+    c = (u == 'T') ? 3u : c;
+    c = (ch == '-') ? 5u : c;
+    return c;
+}
+
+// KmerShrinkage cases 0..5 (src/BwtIndexer.h:262-315)
+__device__ __forceinline__ uint32_t shrink_kmer(uint64_t kmer, int which) {
+    uint32_t hi = (uint32_t)(kmer >> 32), lo = (uint32_t)kmer;
+    switch (which) {
+    case 0: return hi;
+    case 1: return lo;
+    case 2: return (hi & 0xffff0000u) | (lo & 0xffffu);
+    case 3: return (uint32_t)(kmer >> 16);
+    case 4: return (hi & 0xffff0000u) | (lo >> 16);
+    default: return (hi << 16) | (lo & 0xffffu);
+    }
+}
+
+__global__ void __launch_bounds__(256) prep_kernel(BatchView b, PrepParams p) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < b.n_reads; r += n_warps) {
+        const int e = r & 1, pr = r >> 1;
+        const uint8_t *bi = (e ? b.bases_in[1] : b.bases_in[0]) + (size_t)pr * b.stride_in;
+        const uint8_t *qi = (e ? b.quals_in[1] : b.quals_in[0]) + (size_t)pr * b.stride_in;
+        const int32_t *li = e ? b.lens_in[1] : b.lens_in[0];
+        const int full = li ? li[pr] : b.stride_in;
+        uint8_t *co = b.codes + (size_t)r * b.lpad;
+        uint8_t *qo = b.qual + (size_t)r * b.lpad;
+        const int qadj = p.is_il13 ? 31 : 0;
+        uint32_t c96[3] = {0, 0, 0};
+#pragma unroll
+        for (int t = 0; t < FQB_MAX_READ_LEN / 32; ++t) {
+            int j = lane + 32 * t;
+            if (j < full) {
+                uint32_t code = nt4_code(bi[j]);
+                co[j] = (uint8_t)code;
+                qo[j] = (uint8_t)(qi[j] - qadj);
+                if (t < 3) c96[t] = code;
+            }
+        }
+        // ---- k-mer pre-filter: IsReadInHashByCountMoreChunck (src/BwtIndexer.cpp:441-456).
+        // kmer = (kmer << 2) | code over 32 bases == OR of shifted codes (N = 4 bleeds upward).
+        bool filtered = false;
+        if (p.kmer_thresh != 0) {
+            uint64_t kmer[3];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                uint64_t v = (uint64_t)c96[t] << (2 * (31 - lane));
+                uint32_t lo = __reduce_or_sync(FULL_MASK, (uint32_t)v);
+                uint32_t hi = __reduce_or_sync(FULL_MASK, (uint32_t)(v >> 32));
+                kmer[t] = ((uint64_t)hi << 32) | lo;
+            }
+            uint32_t bit = 0;
+            if (lane < 18) {
+                int ch = lane / 6, tb = lane - 6 * ch;
+                uint64_t km = ch == 0 ? kmer[0] : ch == 1 ? kmer[1] : kmer[2];
+                uint32_t x = shrink_kmer(km, tb);
+                bit = (p.roll[((size_t)tb << 29) + (x >> 3)] >> (x & 7)) & 1u;
+            }
+            int hits = __popc(__ballot_sync(FULL_MASK, bit));
+            filtered = hits < p.kmer_thresh;
+        }
+        // ---- bwa_trim_read (libbwa/bwaseqio.c:75-88), suffix sums by warp scan
+        int len = full;
+        if (p.trim_qual >= 1) {
+            int carry = 0, best = 0, best_l = full - 1;
+            for (int base = full - 1; base >= 34; base -= 32) {
+                int l = base - lane;
+                bool valid = l >= 34;
+                int v = valid ? p.trim_qual - ((int)qi[l] - qadj - 33) : 0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int t = __shfl_up_sync(FULL_MASK, v, d);
+                    if (lane >= d) v += t;
+                }
+                int s = v + carry;
+                unsigned neg = __ballot_sync(FULL_MASK, valid && s < 0);
+                int first_neg = neg ? __ffs(neg) - 1 : 32;
+                bool ok = valid && lane < first_neg;
+                long long key = ok ? (((long long)s << 8) | (long long)(63 - lane)) : LLONG_MIN;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    long long o = __shfl_xor_sync(FULL_MASK, key, d);
+                    key = o > key ? o : key;
+                }
+                if (key != LLONG_MIN) {
+                    int cs = (int)(key >> 8), cl = 63 - (int)(key & 0xff);
+                    if (cs > best) { best = cs; best_l = base - cl; }
+                }
+                carry = __shfl_sync(FULL_MASK, s, 31);
+                if (neg) break;
+            }
+            len = best_l + 1;
+        }
+        if (lane == 0) {
+            b.len[r] = len;
+            b.full_len[r] = full;
+            b.filtered[r] = filtered ? 1 : 0;
+            if (!filtered) b.work[atomicAdd(b.n_work, 1u)] = (uint32_t)r;
+        }
+    }
+}
+
+void launch_prep(const BatchView &b, const PrepParams &p, cudaStream_t s) {
+    int blocks = (b.n_reads + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    prep_kernel<<<blocks, 256, 0, s>>>(b, p);
+}
+
+// ---------------------------------------------------------------------------
+struct WidthParams { DevBwt bwt[2]; };
+
+__global__ void __launch_bounds__(128) width_kernel(BatchView b, WidthView wv, WidthParams wp, int seed_len,
+                                                     const uint32_t *work, const uint32_t *n_work) {
+    // a warp handles 32 reads for one part, so lanes run loops of the same trip count
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t wi = (idx >> 7) * 32 + (idx & 31);
+    const int part = (idx >> 5) & 3;
+    if (wi >= *n_work) return;
+    const uint32_t r = work[wi];
+    const int len = b.len[r];
+    const int a = part & 1;
+    const uint8_t *fwd = b.codes + (size_t)r * b.lpad;
+    const bool seed = part >= 2;
+    if (seed && len <= seed_len) return;
+    const int first = seed ? len - seed_len : 0, n = seed ? seed_len : len;
+    uint32_t *out = seed ? wv.sw + ((size_t)r * 2 + a) * wv.sstride : wv.w + ((size_t)r * 2 + a) * wv.wstride;
+    if (a == 0) cal_width(wp.bwt[0], fwd, len, 0, first, n, out);
+    else cal_width(wp.bwt[1], fwd, len, 1, first, n, out);
+}
+
+void launch_width(const BatchView &b, const WidthView &wv, const DevBwt bwt[2], int seed_len, const uint32_t *work,
+                  const uint32_t *n_work, int max_work, cudaStream_t s) {
+    WidthParams wp;
+    wp.bwt[0] = bwt[0]; wp.bwt[1] = bwt[1];
+    long long threads = ((long long)(max_work + 31) / 32) * 128;
+    int blocks = (int)((threads + 127) / 128);
+    if (blocks < 1) blocks = 1;
+    width_kernel<<<blocks, 128, 0, s>>>(b, wv, wp, seed_len, work, n_work);
+}
+
+// ---------------------------------------------------------------------------
+template <typename HeadT>
+__global__ void __launch_bounds__(kSearchThreads) search_kernel(BatchView b, WidthView wv, SearchParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ DevBwt s_bwt[2];
+    __shared__ SearchOpt s_opt;
+    HeadT *heads = reinterpret_cast<HeadT *>(smem_raw);
+    if (threadIdx.x == 0) { s_bwt[0] = p.bwt[0]; s_bwt[1] = p.bwt[1]; s_opt = p.opt; }
+    __syncthreads();
+
+    const int lane_id = threadIdx.x & 31;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    SearchLane<HeadT> lane;
+    lane.bwt = s_bwt; lane.opt = &s_opt;
+    lane.arena = p.arena + gtid * p.arena_cap; lane.arena_cap = p.arena_cap;
+    lane.heads = heads + threadIdx.x; lane.head_stride = blockDim.x;
+    lane.out_cap = p.aln_cap;
+
+    const uint32_t n_work = *p.n_work;
+    bool active = false, exhausted = false;
+    uint32_t r = 0;
+    unsigned long long pops = 0, occs = 0;
+
+    for (;;) {
+        unsigned need = __ballot_sync(FULL_MASK, !active && !exhausted);
+        if (need) {
+            uint32_t base = 0;
+            int leader = __ffs(need) - 1;
+            if (lane_id == leader) base = atomicAdd(p.cursor, (uint32_t)__popc(need));
+            base = __shfl_sync(FULL_MASK, base, leader);
+            if (!active && !exhausted) {
+                uint32_t idx = base + __popc(need & ((1u << lane_id) - 1u));
+                if (idx >= n_work) exhausted = true;
+                else {
+                    r = p.work[idx];
+                    const int len = b.len[r];
+                    lane.fwd = b.codes + (size_t)r * b.lpad;
+                    lane.w[0] = wv.w + ((size_t)r * 2) * wv.wstride;
+                    lane.w[1] = lane.w[0] + wv.wstride;
+                    bool seeded = len > p.seed_len_opt;
+                    lane.sw[0] = seeded ? wv.sw + ((size_t)r * 2) * wv.sstride : nullptr;
+                    lane.sw[1] = seeded ? lane.sw[0] + wv.sstride : nullptr;
+                    lane.out = p.aln + (size_t)(p.aln_row ? (uint32_t)p.aln_row[r] : r) * p.aln_cap;
+                    LaneStatus st = lane.begin(len, p.maxdiff[len]);
+                    active = st == kLaneRunning;
+                    if (!active) {
+                        p.n_aln[r] = st == kLaneOverflow ? -1 : lane.n_aln;
+                        if (st == kLaneOverflow) p.overflow[atomicAdd(p.n_overflow, 1u)] = r;
+                    }
+                }
+            }
+        }
+        if (__all_sync(FULL_MASK, exhausted && !active)) break;
+        if (active) {
+            LaneStatus st = lane.step();
+            if (st != kLaneRunning) {
+                active = false;
+                pops += lane.n_pops; occs += lane.n_occ;
+                p.n_aln[r] = st == kLaneOverflow ? -1 : lane.n_aln;
+                if (st == kLaneOverflow) p.overflow[atomicAdd(p.n_overflow, 1u)] = r;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        pops += __shfl_xor_sync(FULL_MASK, pops, d);
+        occs += __shfl_xor_sync(FULL_MASK, occs, d);
+    }
+    if (lane_id == 0 && p.counters) { atomicAdd(p.counters, pops); atomicAdd(p.counters + 1, occs); }
+}
+
+int search_grid_blocks(int n_buckets, bool heads16, int device) {
+    int per_sm = 0, n_sm = 148;
+    size_t smem = (size_t)n_buckets * kSearchThreads * (heads16 ? 2 : 4);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (heads16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint16_t>, kSearchThreads, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint32_t>, kSearchThreads, smem);
+    if (per_sm < 1) per_sm = 1;
+    return n_sm * per_sm;
+}
+
+void launch_search(const BatchView &b, const WidthView &wv, const SearchParams &p, bool heads16, int n_blocks, cudaStream_t s) {
+    size_t smem = (size_t)p.opt.n_buckets * kSearchThreads * (heads16 ? 2 : 4);
+    if (heads16) {
+        cudaFuncSetAttribute(search_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        search_kernel<uint16_t><<<n_blocks, kSearchThreads, smem, s>>>(b, wv, p);
+    } else {
+        cudaFuncSetAttribute(search_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        search_kernel<uint32_t><<<n_blocks, kSearchThreads, smem, s>>>(b, wv, p);
+    }
+}
+
+}  // namespace fqb

@@ -224,9 +224,11 @@ static void make_read(Rng &rng, const SynthReadConfig &cfg, const std::string &f
         }
         bases[o++] = (uint8_t)c;
     }
+    int tail_from = L;
+    if (rng.unif() < cfg.bad_tail_rate) tail_from = L / 3 + (int)rng.below((uint32_t)(L - L / 3));
     for (int k = 0; k < L; ++k) {
         if (rng.unif() < cfg.n_rate) bases[k] = 'N';
-        double q = 36.0 - 0.08 * k + 4.0 * rng.normal();
+        double q = (k >= tail_from ? 9.0 : 36.0 - 0.08 * k) + 4.0 * rng.normal();
         int qi = (int)std::floor(q + 0.5);
         qi = std::max(2, std::min(41, qi));
         quals[k] = (uint8_t)(33 + qi);

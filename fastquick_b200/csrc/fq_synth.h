@@ -53,6 +53,7 @@ struct SynthReadConfig {
     int max_indel_len = 1;
     double n_rate = 0.005;
     double isize_mean = 350, isize_sd = 40;
+    double bad_tail_rate = 0.15;  // reads whose 3' qualities collapse (exercises bwa_trim_read under --q 15)
 };
 
 // Fills bases/quals (ASCII, n_pairs rows of read_len bytes per end) for pairs

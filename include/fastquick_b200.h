@@ -115,6 +115,22 @@ int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride,
                     const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2,
                     fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
 
+/* ---- stage-level entry points (parity tests, bench, profiling) ---------------
+ * The same kernels fqb_align_pairs sequences, one group at a time, on the batch
+ * made resident by fqb_stage_load.  Read index r = 2*pair + end. */
+/* on_device != 0: the pointers are device pointers on the handle's GPU (inputs stay where they are) */
+int fqb_stage_load(fqb_handle *h, int32_t n_pairs, int32_t stride,
+                   const uint8_t *bases1, const uint8_t *quals1, const int32_t *lens1,
+                   const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device);
+/* a1-a5: read prep + k-mer filter (src/BwtMapper.cpp:543-590, src/BwtIndexer.cpp:524),
+ * bwt_cal_width (libbwa/bwtaln.c:73) and bwt_match_gap (libbwa/bwtgap.c:104) = bwa_cal_sa_reg_gap */
+int fqb_stage_align(fqb_handle *h);
+int fqb_stage_fetch_prep(fqb_handle *h, int32_t *len, int32_t *full_len, uint8_t *filtered,
+                         uint8_t *codes, int32_t codes_stride);
+int fqb_stage_fetch_aln(fqb_handle *h, int32_t cap, fqb_aln_t *out, int32_t *n_aln);
+int fqb_stage_counters(fqb_handle *h, uint64_t *out3);
+void *fqb_stream(fqb_handle *h);   /* the cudaStream_t the handle launches on (for event timing) */
+
 /* ---- synthetic fixtures (bench + tests; hs37d5/dbSNP are not available offline) ----
  * Not part of the drop-in surface: these stand in for `FASTQuick index` output
  * (src/FASTQuick.cpp:38-157) and for FASTQ input so the hot path can be driven
@@ -129,7 +145,7 @@ typedef struct {
     uint64_t seed;
     int32_t read_len;
     int32_t max_indel_len;
-    double f_on, sub_rate, ins_rate, del_rate, n_rate, isize_mean, isize_sd;
+    double f_on, sub_rate, ins_rate, del_rate, n_rate, isize_mean, isize_sd, bad_tail_rate;
 } fqb_synth_read_cfg_t;
 void fqb_synth_ref_cfg_default(fqb_synth_ref_cfg_t *c);
 void fqb_synth_read_cfg_default(fqb_synth_read_cfg_t *c);
@@ -140,6 +156,9 @@ int fqb_synth_write_inputs(const fqb_synth *s, const char *dir);
 /* <prefix> = "<out_prefix>.FASTQuick.fa": all files BwtIndexer::BuildIndex + runIndex would leave */
 int fqb_synth_write_index(const fqb_synth *s, const char *genome_path, const char *dbsnp_path,
                           const char *prefix, int with_rollhash);
+/* engine over the synthetic index built in memory (no files written) */
+int fqb_create_from_synth(const fqb_synth *s, const fqb_gap_opt_t *gopt, const fqb_pe_opt_t *popt,
+                          int device, fqb_handle **out);
 int fqb_synth_reads(const fqb_synth *s, const fqb_synth_read_cfg_t *cfg, int64_t first_pair, int64_t n_pairs,
                     uint8_t *bases1, uint8_t *quals1, uint8_t *bases2, uint8_t *quals2, int n_threads);
 /* gz FASTQ with fixed-width names r%011lld/1 and /2 */

@@ -1,0 +1,75 @@
+/* TEST INFRASTRUCTURE ONLY -- never linked into the product library.
+ *
+ * CPU restatement (plain C) of the reference algorithm on the align hot path,
+ * written from the reference's behaviour; each function cites the reference
+ * file:line it follows.  Parity is PINNED: tests/test_oracle_vs_ref.py checks
+ * every function here against the reference's own code compiled into
+ * oracle/_ref/libfqref.so (recipe: oracle/Makefile.ref) on seeded inputs, and
+ * against the golden vectors under tests/golden/.
+ */
+#ifndef FQ_ORACLE_H_
+#define FQ_ORACLE_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    uint32_t primary, L2[5], seq_len;
+    const uint32_t *bwt;     /* reference interleaved layout: 4 counts + 8 words per 128 bases */
+    uint32_t sa_intv, n_sa;
+    const uint32_t *sa;      /* sa[0] = 0xffffffff */
+} orc_bwt_t;
+
+typedef struct { uint32_t w; int32_t bid; } orc_width_t;
+
+typedef struct {
+    int s_mm, s_gapo, s_gape, mode;
+    int indel_end_skip, max_del_occ, max_entries;
+    int max_diff, max_gapo, max_gape, max_seed_diff, seed_len, max_top2;
+} orc_gap_opt_t;
+
+typedef struct { uint32_t k, l; int32_t score; uint8_t n_mm, n_gapo, n_gape, a; } orc_aln_t;
+
+/* counts occ-block touches as SURVEY.md §8(d) defines N_blk */
+extern uint64_t orc_blk_touches;
+extern uint64_t orc_pops, orc_peak_entries;
+
+uint32_t orc_occ(const orc_bwt_t *b, uint32_t k, int c);
+void orc_2occ(const orc_bwt_t *b, uint32_t k, uint32_t l, int c, uint32_t *ok, uint32_t *ol);
+void orc_occ4(const orc_bwt_t *b, uint32_t k, uint32_t cnt[4]);
+void orc_2occ4(const orc_bwt_t *b, uint32_t k, uint32_t l, uint32_t ck[4], uint32_t cl[4]);
+uint32_t orc_sa(const orc_bwt_t *b, uint32_t k);
+int orc_match_exact_alt(const orc_bwt_t *b, int len, const uint8_t *str, uint32_t *k0, uint32_t *l0);
+
+int orc_cal_maxdiff(int l, double err, double thres);
+int orc_cal_width(const orc_bwt_t *b, int len, const uint8_t *str, orc_width_t *width);
+
+typedef struct orc_stack orc_stack_t;
+orc_stack_t *orc_stack_new(int n_buckets);
+void orc_stack_free(orc_stack_t *s);
+/* returns n_aln; hits written to out (up to cap; count keeps growing past cap) */
+int orc_match_gap(const orc_bwt_t *const bwts[2], int len, const uint8_t *const seq[2], orc_width_t *const w[2],
+                  orc_width_t *const seed_w[2], const orc_gap_opt_t *opt, orc_stack_t *stack, orc_aln_t *out, int cap);
+
+/* whole per-read driver = body of bwa_cal_sa_reg_gap; fwd = nt4 codes in read orientation */
+int orc_align_read(const orc_bwt_t *const bwts[2], const uint8_t *fwd, int len, const orc_gap_opt_t *opt, double fnr,
+                   int slice_max_gapo, orc_stack_t *stack, orc_aln_t *out, int cap);
+
+/* read prep */
+int orc_trim_len(int trim_qual, const uint8_t *qual, int len);
+int orc_kmer_pass(const uint8_t *const tables[6], const uint8_t *fwd_codes, int thresh);
+
+/* drand48 stream + hit selection */
+typedef struct { uint64_t x; uint64_t n_calls; } orc_rng_t;
+void orc_srand48(orc_rng_t *r, long seed);
+double orc_drand48(orc_rng_t *r);
+typedef struct { uint32_t sa, c1, c2; int32_t score; uint8_t n_mm, n_gapo, n_gape, strand, type; } orc_se_t;
+void orc_aln2seq_main(int n_aln, const orc_aln_t *aln, orc_rng_t *rng, orc_se_t *s);
+int orc_approx_mapq(const orc_se_t *s, int mm, const int g_log_n[256]);
+void orc_fill_log_n(int g_log_n[256]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

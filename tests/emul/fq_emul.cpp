@@ -1,0 +1,87 @@
+// TEST INFRASTRUCTURE ONLY.  Instantiates the per-lane device functions of
+// fastquick_b200/csrc/fq_device_core.cuh on the host, one "lane" at a time, so
+// the kernel LOGIC can be checked against the oracle where no GPU exists.  The
+// product library never contains or calls this.
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../fastquick_b200/csrc/fq_device_core.cuh"
+#include "../../fastquick_b200/csrc/fq_hostmath.h"
+#include "../../fastquick_b200/csrc/fq_index.h"
+#include "../../fastquick_b200/csrc/fq_relayout.h"
+
+using namespace fqb;
+
+struct Emul {
+    HostIndex idx;
+    std::vector<Block32> blocks[2];
+    DevBwt bwt[2];
+};
+
+extern "C" {
+
+void *emul_open(const char *prefix, char *err, int errlen) {
+    Emul *e = new Emul();
+    std::string msg;
+    if (!load_index(prefix, false, e->idx, msg)) { strncpy(err, msg.c_str(), errlen - 1); delete e; return nullptr; }
+    for (int s = 0; s < 2; ++s) {
+        relayout_bwt(e->idx.bwt[s], e->blocks[s]);
+        DevBwt &d = e->bwt[s];
+        d.blocks = reinterpret_cast<const uint4 *>(e->blocks[s].data());
+        d.sa = e->idx.bwt[s].sa.data();
+        d.primary = e->idx.bwt[s].primary; d.seq_len = e->idx.bwt[s].seq_len;
+        for (int i = 0; i < 5; ++i) d.L2[i] = e->idx.bwt[s].L2[i];
+        d.n_blocks = (uint32_t)e->blocks[s].size();
+    }
+    return e;
+}
+void emul_close(void *h) { delete (Emul *)h; }
+
+void emul_occ4(void *h, int which, uint32_t k, uint32_t *out) { occ4(((Emul *)h)->bwt[which], k, out); }
+uint32_t emul_sa(void *h, int which, uint32_t k) { return sa_lookup(((Emul *)h)->bwt[which], k); }
+
+// widths + search for n reads; fwd = nt4 codes, read orientation, `stride` bytes per read
+int emul_align(void *h, const fqb_gap_opt_t *gopt, int n, int stride, const uint8_t *fwd, const int32_t *lens,
+               int arena_cap, int out_cap, fqb_aln_t *out, int32_t *n_aln, int32_t *status, uint32_t *pops_occ) {
+    Emul *e = (Emul *)h;
+    int max_len = 0;
+    for (int r = 0; r < n; ++r) if (lens[r] > max_len) max_len = lens[r];
+    SearchOpt so = make_search_opt(*gopt, max_len);
+    if (so.n_buckets > 128) return -1;
+    int32_t maxdiff[FQB_MAX_READ_LEN + 1];
+    fill_maxdiff_table(*gopt, maxdiff);
+    std::vector<uint4> arena((size_t)arena_cap);
+    std::vector<uint32_t> heads((size_t)so.n_buckets);
+    std::vector<uint16_t> heads16((size_t)so.n_buckets);
+    std::vector<uint32_t> w0(max_len + 1), w1(max_len + 1), s0(so.seed_len + 1), s1(so.seed_len + 1);
+    for (int r = 0; r < n; ++r) {
+        const uint8_t *f = fwd + (size_t)r * stride;
+        int len = lens[r];
+        cal_width(e->bwt[0], f, len, 0, 0, len, w0.data());
+        cal_width(e->bwt[1], f, len, 1, 0, len, w1.data());
+        bool seeded = len > gopt->seed_len;
+        if (seeded) {
+            cal_width(e->bwt[0], f, len, 0, len - gopt->seed_len, gopt->seed_len, s0.data());
+            cal_width(e->bwt[1], f, len, 1, len - gopt->seed_len, gopt->seed_len, s1.data());
+        }
+        SearchOpt lo = so;
+        lo.seed_len = gopt->seed_len < len ? gopt->seed_len : 0x7fffffff;
+        auto run = [&](auto &lane) {
+            lane.bwt = e->bwt; lane.opt = &lo; lane.fwd = f;
+            lane.w[0] = w0.data(); lane.w[1] = w1.data();
+            lane.sw[0] = seeded ? s0.data() : nullptr; lane.sw[1] = seeded ? s1.data() : nullptr;
+            lane.arena = arena.data(); lane.arena_cap = (uint32_t)arena_cap;
+            lane.head_stride = 1;
+            lane.out = reinterpret_cast<Hit *>(out + (size_t)r * out_cap); lane.out_cap = out_cap;
+            LaneStatus st = lane.begin(len, maxdiff[len]);
+            while (st == kLaneRunning) st = lane.step();
+            n_aln[r] = lane.n_aln; status[r] = (int32_t)st;
+            if (pops_occ) { pops_occ[2 * r] = lane.n_pops; pops_occ[2 * r + 1] = lane.n_occ; }
+        };
+        if (arena_cap < 65535) { SearchLane<uint16_t> lane; lane.heads = heads16.data(); run(lane); }
+        else { SearchLane<uint32_t> lane; lane.heads = heads.data(); run(lane); }
+    }
+    return 0;
+}
+
+}  // extern "C"
