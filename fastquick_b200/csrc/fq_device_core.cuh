@@ -171,10 +171,16 @@ FQB_HD uint32_t pack_meta(int i, int a, int state, int mm, int go, int ge) {
     return (uint32_t)i | (uint32_t)a << 10 | (uint32_t)state << 11 | (uint32_t)mm << 13 | (uint32_t)go << 19 | (uint32_t)ge << 23;
 }
 
-enum LaneStatus { kLaneRunning = 0, kLaneDone = 1, kLaneOverflow = 2 };
+enum LaneStatus { kLaneRunning = 0, kLaneDone = 1, kLaneOverflow = 2, kLaneHit = 3 };
+enum LaneMode { kModePop = 0, kModeExpand = 1, kModeExact = 2 };
 
-// HeadT: uint16_t when the arena holds < 65535 entries (fast pass), uint32_t otherwise.
-template <typename HeadT>
+// One search lane = one read.  step() is a flat state machine: every call does at
+// most ONE stack pop and at most ONE pair of rank queries, so the 32 lanes of a warp
+// stay on the same instructions whatever their reads look like.
+//   HeadT:     uint16_t when the arena holds < 65535 entries (fast pass), else uint32_t
+//   kFreeList: recycle popped slots through a free list (overflow pass; the fast pass
+//              only recycles the most recently popped slot and otherwise bump-allocates)
+template <typename HeadT, bool kFreeList>
 struct SearchLane {
     // wiring
     const DevBwt *bwt;         // [2]
@@ -193,8 +199,10 @@ struct SearchLane {
     // current entry
     uint32_t k, l;
     int i, a, state, n_mm, n_gapo, n_gape, ldp;
-    bool have_cur, exact_mode, overflow;
-    // statistics (for ncu-independent accounting; cheap)
+    int mode;
+    bool have_cur, overflow;
+    uint32_t hit_x;            // interval size of the hit whose gap_shadow is pending
+    // statistics
     uint32_t n_pops, n_occ;
 
     FQB_HD int score3(int mm, int go, int ge) const { return mm * opt->s_mm + go * opt->s_gapo + ge * opt->s_gape; }
@@ -202,19 +210,18 @@ struct SearchLane {
     FQB_HD uint32_t *wa() const { return a ? w[1] : w[0]; }
     FQB_HD const uint32_t *swa() const { return a ? sw[1] : sw[0]; }
     FQB_HD bool bucket_set(int s) const { return s < 64 ? (mask0 >> s) & 1 : (mask1 >> (s - 64)) & 1; }
+    FQB_HD int diffs_left() const { return max_diff - (n_mm + n_gapo) - ((opt->mode & kModeGapE) ? n_gape : 0); }
 
     FQB_HD uint32_t alloc_slot() {
         uint32_t s;
         if (spare != kNoSlot) { s = spare; spare = kNoSlot; return s; }
-        if (free_head != kNoSlot) { s = free_head; free_head = arena[s].w & kNoSlot; return s; }
+        if (kFreeList && free_head != kNoSlot) { s = free_head; free_head = arena[s].w & kNoSlot; return s; }
         if (top < arena_cap) return top++;
         overflow = true;
         return kNoSlot;
     }
     FQB_HD void release_slot(uint32_t s) {
-        if (spare == kNoSlot) { spare = s; return; }
-        arena[spare].w = free_head;
-        free_head = spare;
+        if (kFreeList && spare != kNoSlot) { arena[spare].w = free_head; free_head = spare; }
         spare = s;
     }
 
@@ -249,17 +256,15 @@ struct SearchLane {
         ldp = (int)(e.w >> 22);
     }
 
-    // bwt_match_gap prologue (libbwa/bwtgap.c:104-128)
-    FQB_HD LaneStatus begin(int read_len, int read_max_diff) {
+    // bwt_match_gap prologue (libbwa/bwtgap.c:104-128); n_ambig = bases > 3 among the first len
+    FQB_HD LaneStatus begin(int read_len, int read_max_diff, int n_ambig) {
         len = read_len; max_diff_opt = max_diff = read_max_diff;
         best_score = score3(max_diff_opt + 1, opt->max_gapo + 1, opt->max_gape + 1);
         best_cnt = 0; n_aln = 0; n_entries = 0;
         mask0 = mask1 = 0; top = 0; free_head = spare = kNoSlot;
-        have_cur = false; exact_mode = false; overflow = false;
-        n_pops = n_occ = 0;
-        int n_N = 0;
-        for (int j = 0; j < len; ++j) n_N += fwd[j] > 3;
-        if (n_N > max_diff) return kLaneDone;
+        have_cur = false; mode = kModePop; overflow = false;
+        n_pops = n_occ = 0; hit_x = 0;
+        if (n_ambig > max_diff) return kLaneDone;
         push(0, len, 0, bwt[0].seq_len, 0, 0, 0, kStateM, 0);
         // second root (strand 1) is the top of bucket 0: keep it in registers
         k = 0; l = bwt[0].seq_len; i = len; a = 1; state = kStateM; n_mm = n_gapo = n_gape = 0; ldp = 0;
@@ -267,8 +272,9 @@ struct SearchLane {
         return overflow ? kLaneOverflow : kLaneRunning;
     }
 
-    // a hit: libbwa/bwtgap.c:163-199.  Returns true when the search must stop (top2b rule).
-    FQB_HD bool on_hit() {
+    // a hit: libbwa/bwtgap.c:163-199 minus gap_shadow, which the caller runs (warp-cooperatively
+    // on the GPU) when kLaneHit is returned.
+    FQB_HD LaneStatus on_hit() {
         int sc = score3(n_mm, n_gapo, n_gape);
         if (n_aln == 0) {
             best_score = sc;
@@ -276,75 +282,67 @@ struct SearchLane {
             if (!(opt->mode & kModeNonStop)) max_diff = (best_diff + 1 > max_diff_opt) ? max_diff_opt : best_diff + 1;
         }
         if (sc == best_score) best_cnt += (int)(l - k + 1);
-        else if (best_cnt > opt->max_top2) return true;
-        bool add = true;
+        else if (best_cnt > opt->max_top2) return kLaneDone;
         if (n_gapo) {
             int n_cmp = n_aln < out_cap ? n_aln : out_cap;
             for (int j = 0; j < n_cmp; ++j)
-                if (out[j].k == k && out[j].l == l) { add = false; break; }
+                if (out[j].k == k && out[j].l == l) return kLaneRunning;
         }
-        if (add) {
-            // gap_shadow (libbwa/bwtgap.c:81-91)
-            uint32_t x = l - k + 1, maxv = bwt[1 - a].seq_len;
-            uint32_t *wa_ = wa();
-            int jj = 0;
-            for (int p = 0; p < ldp; ++p) {
-                uint32_t v = wa_[p], ww = width_w(v);
-                if (ww > x) wa_[p] = v - x;
-                else if (ww == x) wa_[p] = pack_width(maxv - (uint32_t)(++jj), 1);
-            }
-            if (n_aln < out_cap) {
-                Hit h; h.k = k; h.l = l; h.score = sc;
-                h.n_mm = (uint8_t)n_mm; h.n_gapo = (uint8_t)n_gapo; h.n_gape = (uint8_t)n_gape; h.a = (uint8_t)a;
-                out[n_aln] = h;
-            } else overflow = true;
-            ++n_aln;
-        }
-        return false;
+        if (n_aln < out_cap) {
+            Hit h; h.k = k; h.l = l; h.score = sc;
+            h.n_mm = (uint8_t)n_mm; h.n_gapo = (uint8_t)n_gapo; h.n_gape = (uint8_t)n_gape; h.a = (uint8_t)a;
+            out[n_aln] = h;
+        } else overflow = true;
+        ++n_aln;
+        hit_x = l - k + 1;
+        return overflow ? kLaneOverflow : kLaneHit;
     }
 
-    // One iteration: consume stack entries until one needs a rank query, do the query,
-    // then either continue the exact-match tail (bwt_match_exact_alt) or expand children.
-    FQB_HD LaneStatus step() {
-        if (!exact_mode) {
-            for (;;) {
-                if (n_entries == 0) return kLaneDone;
-                if (n_entries > opt->max_entries) return kLaneDone;
-                pop();
-                if (!(opt->mode & kModeNonStop) && score3(n_mm, n_gapo, n_gape) > best_score + opt->s_mm) return kLaneDone;
-                int m = max_diff - (n_mm + n_gapo) - ((opt->mode & kModeGapE) ? n_gape : 0);
-                if (m < 0) continue;
-                if (i > 0 && m < width_bid(wa()[i - 1])) continue;
-                if (i == 0) { if (on_hit()) return kLaneDone; if (overflow) return kLaneOverflow; continue; }
-                if (m == 0 && (state == kStateM || (opt->mode & kModeGapE) || n_gape == opt->max_gape)) {
-                    if (read_sym(fwd, len, a, i - 1) > 3) continue;      // bwt_match_exact_alt: N never matches
-                    exact_mode = true;
-                }
-                break;
-            }
+    // gap_shadow (libbwa/bwtgap.c:81-91), serial form (host emulation; the kernel has a warp-wide one)
+    FQB_HD void shadow_serial() {
+        uint32_t x = hit_x, maxv = bwt[1 - a].seq_len;
+        uint32_t *wa_ = wa();
+        int jj = 0;
+        for (int p = 0; p < ldp; ++p) {
+            uint32_t v = wa_[p], ww = width_w(v);
+            if (ww > x) wa_[p] = v - x;
+            else if (ww == x) wa_[p] = pack_width(maxv - (uint32_t)(++jj), 1);
         }
-        const DevBwt &b = bwt[1 - a];
+    }
+
+    FQB_HD LaneStatus step() {
+        if (mode == kModePop) {
+            if (n_entries == 0 || n_entries > opt->max_entries) return kLaneDone;
+            pop();
+            if (!(opt->mode & kModeNonStop) && score3(n_mm, n_gapo, n_gape) > best_score + opt->s_mm) return kLaneDone;
+            int m = diffs_left();
+            if (m < 0) return kLaneRunning;
+            if (i == 0) return on_hit();
+            if (m < width_bid(wa()[i - 1])) return kLaneRunning;
+            if (m == 0 && (state == kStateM || (opt->mode & kModeGapE) || n_gape == opt->max_gape)) {
+                if (read_sym(fwd, len, a, i - 1) > 3) return kLaneRunning;   // bwt_match_exact_alt: N never matches
+                mode = kModeExact;
+            } else mode = kModeExpand;
+        }
+        const DevBwt &b = a ? bwt[0] : bwt[1];
         uint32_t ck[4], cl[4];
         occ4_pair(b, k - 1, l, ck, cl);
         ++n_occ;
 
-        if (exact_mode) {                           // one step of bwt_match_exact_alt (libbwa/bwt.c:102-117)
+        if (mode == kModeExact) {                   // one step of bwt_match_exact_alt (libbwa/bwt.c:102-117)
             uint32_t c = read_sym(fwd, len, a, i - 1);
             k = pick4(b.L2, c) + pick4(ck, c) + 1;
             l = pick4(b.L2, c) + pick4(cl, c);
             --i;
-            if (k > l) { exact_mode = false; return kLaneRunning; }
-            if (i == 0) {
-                exact_mode = false;
-                if (on_hit()) return kLaneDone;
-                return overflow ? kLaneOverflow : kLaneRunning;
-            }
-            if (read_sym(fwd, len, a, i - 1) > 3) exact_mode = false;
+            if (k > l) { mode = kModePop; return kLaneRunning; }
+            if (i == 0) { mode = kModePop; return on_hit(); }
+            if (read_sym(fwd, len, a, i - 1) > 3) mode = kModePop;
             return kLaneRunning;
         }
 
         // expansion: libbwa/bwtgap.c:201-259
-        int m = max_diff - (n_mm + n_gapo) - ((opt->mode & kModeGapE) ? n_gape : 0);
+        mode = kModePop;
+        int m = diffs_left();
         int m_seed = opt->max_seed_diff - (n_mm + n_gapo) - ((opt->mode & kModeGapE) ? n_gape : 0);
         --i;
         uint32_t occ = l - k + 1;

@@ -77,7 +77,7 @@ static void free_batch(fqb_handle *h) {
     for (auto &p : h->d_in) { cudaFree(p); p = nullptr; }
     for (auto &p : h->d_lens_in) { cudaFree(p); p = nullptr; }
     cudaFree(h->bv.codes); cudaFree(h->bv.qual); cudaFree(h->bv.len); cudaFree(h->bv.full_len);
-    cudaFree(h->bv.filtered); cudaFree(h->bv.work);
+    cudaFree(h->bv.filtered); cudaFree(h->bv.n_ambig); cudaFree(h->bv.work);
     cudaFree(h->wv.w); cudaFree(h->wv.sw);
     cudaFree(h->d_aln); cudaFree(h->d_naln); cudaFree(h->d_overflow); cudaFree(h->d_spill_slot);
     memset(&h->bv, 0, sizeof(h->bv)); memset(&h->wv, 0, sizeof(h->wv));
@@ -97,6 +97,7 @@ static int ensure_batch(fqb_handle *h, int n_reads, int stride) {
     CU_CHECK(cudaMalloc(&h->bv.len, (size_t)cap * 4));
     CU_CHECK(cudaMalloc(&h->bv.full_len, (size_t)cap * 4));
     CU_CHECK(cudaMalloc(&h->bv.filtered, (size_t)cap));
+    CU_CHECK(cudaMalloc(&h->bv.n_ambig, (size_t)cap));
     CU_CHECK(cudaMalloc(&h->bv.work, (size_t)cap * 4));
     h->wv.wstride = stride + 1;
     h->wv.sstride = h->gopt.seed_len + 1;

@@ -51,15 +51,15 @@ __global__ void __launch_bounds__(256) prep_kernel(BatchView b, PrepParams p) {
         uint8_t *co = b.codes + (size_t)r * b.lpad;
         uint8_t *qo = b.qual + (size_t)r * b.lpad;
         const int qadj = p.is_il13 ? 31 : 0;
-        uint32_t c96[3] = {0, 0, 0};
+        uint32_t codes[FQB_MAX_READ_LEN / 32];
 #pragma unroll
         for (int t = 0; t < FQB_MAX_READ_LEN / 32; ++t) {
             int j = lane + 32 * t;
+            codes[t] = 0;
             if (j < full) {
-                uint32_t code = nt4_code(bi[j]);
-                co[j] = (uint8_t)code;
+                codes[t] = nt4_code(bi[j]);
+                co[j] = (uint8_t)codes[t];
                 qo[j] = (uint8_t)(qi[j] - qadj);
-                if (t < 3) c96[t] = code;
             }
         }
         // ---- k-mer pre-filter: IsReadInHashByCountMoreChunck (src/BwtIndexer.cpp:441-456).
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) prep_kernel(BatchView b, PrepParams p) {
             uint64_t kmer[3];
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
-                uint64_t v = (uint64_t)c96[t] << (2 * (31 - lane));
+                uint64_t v = (uint64_t)codes[t] << (2 * (31 - lane));
                 uint32_t lo = __reduce_or_sync(FULL_MASK, (uint32_t)v);
                 uint32_t hi = __reduce_or_sync(FULL_MASK, (uint32_t)(v >> 32));
                 kmer[t] = ((uint64_t)hi << 32) | lo;
@@ -116,7 +116,12 @@ __global__ void __launch_bounds__(256) prep_kernel(BatchView b, PrepParams p) {
             }
             len = best_l + 1;
         }
+        int n_ambig = 0;
+#pragma unroll
+        for (int t = 0; t < FQB_MAX_READ_LEN / 32; ++t)
+            n_ambig += __popc(__ballot_sync(FULL_MASK, codes[t] > 3 && lane + 32 * t < len));
         if (lane == 0) {
+            b.n_ambig[r] = (uint8_t)(n_ambig > 255 ? 255 : n_ambig);
             b.len[r] = len;
             b.full_len[r] = full;
             b.filtered[r] = filtered ? 1 : 0;
@@ -165,7 +170,38 @@ void launch_width(const BatchView &b, const WidthView &wv, const DevBwt bwt[2], 
 }
 
 // ---------------------------------------------------------------------------
-template <typename HeadT>
+// gap_shadow (libbwa/bwtgap.c:81-91) for every lane of the warp that just recorded a hit, 32 width
+// entries at a time; the running "++j" of the reference becomes a ballot prefix count.
+template <typename Lane>
+__device__ __forceinline__ void warp_shadow(Lane &lane, bool has_hit, int lane_id) {
+    unsigned hm = __ballot_sync(FULL_MASK, has_hit);
+    while (hm) {
+        const int src = __ffs(hm) - 1;
+        hm &= hm - 1;
+        unsigned long long wp_ = __shfl_sync(FULL_MASK, (unsigned long long)(uintptr_t)lane.wa(), src);
+        uint32_t *wp = reinterpret_cast<uint32_t *>((uintptr_t)wp_);
+        const uint32_t x = __shfl_sync(FULL_MASK, lane.hit_x, src);
+        const int a = __shfl_sync(FULL_MASK, lane.a, src);
+        const int ldp = __shfl_sync(FULL_MASK, lane.ldp, src);
+        const uint32_t maxv = (a ? lane.bwt[0] : lane.bwt[1]).seq_len;
+        uint32_t j = 0;
+        for (int base = 0; base < ldp; base += 32) {
+            const int p = base + lane_id;
+            const bool in = p < ldp;
+            const uint32_t v = in ? wp[p] : 0u, ww = width_w(v);
+            const bool eq = in && ww == x;
+            const unsigned em = __ballot_sync(FULL_MASK, eq);
+            if (in) {
+                if (ww > x) wp[p] = v - x;
+                else if (eq) wp[p] = pack_width(maxv - (j + (uint32_t)__popc(em & ((1u << lane_id) - 1u)) + 1u), 1);
+            }
+            j += (uint32_t)__popc(em);
+        }
+    }
+    __syncwarp();
+}
+
+template <typename HeadT, bool kFreeList>
 __global__ void __launch_bounds__(kSearchThreads) search_kernel(BatchView b, WidthView wv, SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ DevBwt s_bwt[2];
@@ -176,11 +212,12 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(BatchView b, Wid
 
     const int lane_id = threadIdx.x & 31;
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    SearchLane<HeadT> lane;
+    SearchLane<HeadT, kFreeList> lane;
     lane.bwt = s_bwt; lane.opt = &s_opt;
     lane.arena = p.arena + gtid * p.arena_cap; lane.arena_cap = p.arena_cap;
     lane.heads = heads + threadIdx.x; lane.head_stride = blockDim.x;
     lane.out_cap = p.aln_cap;
+    lane.w[0] = lane.w[1] = nullptr; lane.a = 0; lane.ldp = 0; lane.hit_x = 0;
 
     const uint32_t n_work = *p.n_work;
     bool active = false, exhausted = false;
@@ -188,6 +225,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(BatchView b, Wid
     unsigned long long pops = 0, occs = 0;
 
     for (;;) {
+        LaneStatus st = kLaneRunning;
         unsigned need = __ballot_sync(FULL_MASK, !active && !exhausted);
         if (need) {
             uint32_t base = 0;
@@ -207,24 +245,19 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(BatchView b, Wid
                     lane.sw[0] = seeded ? wv.sw + ((size_t)r * 2) * wv.sstride : nullptr;
                     lane.sw[1] = seeded ? lane.sw[0] + wv.sstride : nullptr;
                     lane.out = p.aln + (size_t)(p.aln_row ? (uint32_t)p.aln_row[r] : r) * p.aln_cap;
-                    LaneStatus st = lane.begin(len, p.maxdiff[len]);
-                    active = st == kLaneRunning;
-                    if (!active) {
-                        p.n_aln[r] = st == kLaneOverflow ? -1 : lane.n_aln;
-                        if (st == kLaneOverflow) p.overflow[atomicAdd(p.n_overflow, 1u)] = r;
-                    }
+                    st = lane.begin(len, p.maxdiff[len], b.n_ambig[r]);
+                    active = true;
                 }
             }
         }
         if (__all_sync(FULL_MASK, exhausted && !active)) break;
-        if (active) {
-            LaneStatus st = lane.step();
-            if (st != kLaneRunning) {
-                active = false;
-                pops += lane.n_pops; occs += lane.n_occ;
-                p.n_aln[r] = st == kLaneOverflow ? -1 : lane.n_aln;
-                if (st == kLaneOverflow) p.overflow[atomicAdd(p.n_overflow, 1u)] = r;
-            }
+        if (active && st == kLaneRunning) st = lane.step();
+        warp_shadow(lane, active && st == kLaneHit, lane_id);
+        if (active && (st == kLaneDone || st == kLaneOverflow)) {
+            active = false;
+            pops += lane.n_pops; occs += lane.n_occ;
+            p.n_aln[r] = st == kLaneOverflow ? -1 : lane.n_aln;
+            if (st == kLaneOverflow) p.overflow[atomicAdd(p.n_overflow, 1u)] = r;
         }
     }
 #pragma unroll
@@ -239,8 +272,8 @@ int search_grid_blocks(int n_buckets, bool heads16, int device) {
     int per_sm = 0, n_sm = 148;
     size_t smem = (size_t)n_buckets * kSearchThreads * (heads16 ? 2 : 4);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-    if (heads16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint16_t>, kSearchThreads, smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint32_t>, kSearchThreads, smem);
+    if (heads16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint16_t, false>, kSearchThreads, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint32_t, true>, kSearchThreads, smem);
     if (per_sm < 1) per_sm = 1;
     return n_sm * per_sm;
 }
@@ -248,11 +281,11 @@ int search_grid_blocks(int n_buckets, bool heads16, int device) {
 void launch_search(const BatchView &b, const WidthView &wv, const SearchParams &p, bool heads16, int n_blocks, cudaStream_t s) {
     size_t smem = (size_t)p.opt.n_buckets * kSearchThreads * (heads16 ? 2 : 4);
     if (heads16) {
-        cudaFuncSetAttribute(search_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        search_kernel<uint16_t><<<n_blocks, kSearchThreads, smem, s>>>(b, wv, p);
+        cudaFuncSetAttribute(search_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        search_kernel<uint16_t, false><<<n_blocks, kSearchThreads, smem, s>>>(b, wv, p);
     } else {
-        cudaFuncSetAttribute(search_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        search_kernel<uint32_t><<<n_blocks, kSearchThreads, smem, s>>>(b, wv, p);
+        cudaFuncSetAttribute(search_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        search_kernel<uint32_t, true><<<n_blocks, kSearchThreads, smem, s>>>(b, wv, p);
     }
 }
 

@@ -22,6 +22,7 @@ struct BatchView {
     int32_t *len;           // after bwa_trim_read
     int32_t *full_len;
     uint8_t *filtered;
+    uint8_t *n_ambig;       // bases > 3 among the first len (bwt_match_gap's too-many-N test)
     uint32_t *work;         // reads that go through the aligner
     uint32_t *n_work;
 };

@@ -73,13 +73,18 @@ int emul_align(void *h, const fqb_gap_opt_t *gopt, int n, int stride, const uint
             lane.arena = arena.data(); lane.arena_cap = (uint32_t)arena_cap;
             lane.head_stride = 1;
             lane.out = reinterpret_cast<Hit *>(out + (size_t)r * out_cap); lane.out_cap = out_cap;
-            LaneStatus st = lane.begin(len, maxdiff[len]);
-            while (st == kLaneRunning) st = lane.step();
+            int n_ambig = 0;
+            for (int j = 0; j < len; ++j) n_ambig += f[j] > 3;
+            LaneStatus st = lane.begin(len, maxdiff[len], n_ambig);
+            while (st == kLaneRunning || st == kLaneHit) {
+                if (st == kLaneHit) lane.shadow_serial();
+                st = lane.step();
+            }
             n_aln[r] = lane.n_aln; status[r] = (int32_t)st;
             if (pops_occ) { pops_occ[2 * r] = lane.n_pops; pops_occ[2 * r + 1] = lane.n_occ; }
         };
-        if (arena_cap < 65535) { SearchLane<uint16_t> lane; lane.heads = heads16.data(); run(lane); }
-        else { SearchLane<uint32_t> lane; lane.heads = heads.data(); run(lane); }
+        if (arena_cap < 65535) { SearchLane<uint16_t, false> lane; lane.heads = heads16.data(); run(lane); }
+        else { SearchLane<uint32_t, true> lane; lane.heads = heads.data(); run(lane); }
     }
     return 0;
 }
