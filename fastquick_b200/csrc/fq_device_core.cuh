@@ -78,6 +78,15 @@ FQB_HD void occ4(const DevBwt &b, uint32_t k, uint32_t out[4]) {
     occ4_block(FQB_LDG4(p), FQB_LDG4(p + 1), (k & 63) + 1, out);
 }
 
+// Algorithmic occ-block touches of one bwt_2occ/bwt_2occ4(k, l) call as SURVEY.md §8(d) counts
+// them for the roofline: 1 when k == l or both fall in the same 128-symbol reference block, else 2.
+FQB_HD uint32_t ref_block_touches(const DevBwt &b, uint32_t k, uint32_t l) {
+    if (k == l) return 1;
+    if (k == kNoRow || l == kNoRow) return 2;
+    uint32_t kk = k - (k >= b.primary), ll = l - (l >= b.primary);
+    return (kk >> 7) == (ll >> 7) ? 1u : 2u;
+}
+
 // bwt_2occ4(bwt, k, l): both rank vectors, one block fetch when k and l share a block
 FQB_HD void occ4_pair(const DevBwt &b, uint32_t k, uint32_t l, uint32_t ck[4], uint32_t cl[4]) {
     if (k == kNoRow) { ck[0] = ck[1] = ck[2] = ck[3] = 0; occ4(b, l, cl); return; }
@@ -129,14 +138,15 @@ FQB_HD uint32_t read_sym(const uint8_t *fwd, int len, int a, int i) {
 }
 
 // bwt_cal_width over symbols [first, first+n) of strand-a sequence; writes n+1 packed entries
-FQB_HD void cal_width(const DevBwt &b, const uint8_t *fwd, int len, int a, int first, int n, uint32_t *out) {
-    uint32_t k = 0, l = b.seq_len;
+FQB_HD uint32_t cal_width(const DevBwt &b, const uint8_t *fwd, int len, int a, int first, int n, uint32_t *out) {
+    uint32_t k = 0, l = b.seq_len, touches = 0;
     int bid = 0;
     for (int i = 0; i < n; ++i) {
         uint32_t c = read_sym(fwd, len, a, first + i);
         if (c < 4) {
             uint32_t ck[4], cl[4];
             occ4_pair(b, k - 1, l, ck, cl);
+            touches += ref_block_touches(b, k - 1, l);
             k = pick4(b.L2, c) + pick4(ck, c) + 1;
             l = pick4(b.L2, c) + pick4(cl, c);
         }
@@ -144,6 +154,7 @@ FQB_HD void cal_width(const DevBwt &b, const uint8_t *fwd, int len, int a, int f
         out[i] = pack_width(l - k + 1, bid);
     }
     out[n] = pack_width(0, bid + 1);
+    return touches;
 }
 
 // ---------------------------------------------------------------------------
@@ -195,7 +206,7 @@ struct SearchLane {
     // read state
     int len, max_diff_opt, max_diff, best_score, best_cnt, n_aln, n_entries;
     uint64_t mask0, mask1;     // non-empty score buckets
-    uint32_t top, free_head, spare;
+    uint32_t top, free_head;
     // current entry
     uint32_t k, l;
     int i, a, state, n_mm, n_gapo, n_gape, ldp;
@@ -203,7 +214,13 @@ struct SearchLane {
     bool have_cur, overflow;
     uint32_t hit_x;            // interval size of the hit whose gap_shadow is pending
     // statistics
-    uint32_t n_pops, n_occ;
+    uint32_t n_pops, n_occ, n_blk;
+#ifdef FQB_LANE_STATS
+    uint32_t st_iter, st_mempop, st_skip, st_exact, st_expand, st_push, st_hit, st_adiff, st_gapok, st_am;
+#define FQB_STAT(x) (++(x))
+#else
+#define FQB_STAT(x) ((void)0)
+#endif
 
     FQB_HD int score3(int mm, int go, int ge) const { return mm * opt->s_mm + go * opt->s_gapo + ge * opt->s_gape; }
     FQB_HD HeadT &head(int s) { return heads[(size_t)s * head_stride]; }
@@ -213,28 +230,34 @@ struct SearchLane {
     FQB_HD int diffs_left() const { return max_diff - (n_mm + n_gapo) - ((opt->mode & kModeGapE) ? n_gape : 0); }
 
     FQB_HD uint32_t alloc_slot() {
-        uint32_t s;
-        if (spare != kNoSlot) { s = spare; spare = kNoSlot; return s; }
-        if (kFreeList && free_head != kNoSlot) { s = free_head; free_head = arena[s].w & kNoSlot; return s; }
+        if (kFreeList && free_head != kNoSlot) { uint32_t s = free_head; free_head = arena[s].w & kNoSlot; return s; }
         if (top < arena_cap) return top++;
         overflow = true;
         return kNoSlot;
     }
     FQB_HD void release_slot(uint32_t s) {
-        if (kFreeList && spare != kNoSlot) { arena[spare].w = free_head; free_head = spare; }
-        spare = s;
+        if (kFreeList) { arena[s].w = free_head; free_head = s; }
     }
 
-    // gap_push (libbwa/bwtgap.c:45-64)
-    FQB_HD void push(int pa, int pi, uint32_t pk, uint32_t pl, int mm, int go, int ge, int st, int pldp) {
-        int sc = score3(mm, go, ge);
+    // gap_push (libbwa/bwtgap.c:45-64), split in two: emit() stores one entry and chains it behind
+    // `prev`; the caller publishes the last entry of a group as the new head of its score bucket.
+    FQB_HD uint32_t emit(uint32_t pk, uint32_t pl, uint32_t meta, int pldp, uint32_t prev) {
         uint32_t s = alloc_slot();
         ++n_entries;
-        if (s == kNoSlot) return;
-        uint32_t prev = bucket_set(sc) ? (uint32_t)head(sc) : kNoSlot;
-        arena[s] = make_uint4(pk, pl, pack_meta(pi, pa, st, mm, go, ge), (uint32_t)pldp << 22 | prev);
-        head(sc) = (HeadT)s;
+        FQB_STAT(st_push);
+        if (s == kNoSlot) return prev;
+        arena[s] = make_uint4(pk, pl, meta, (uint32_t)pldp << 22 | prev);
+        return s;
+    }
+    FQB_HD uint32_t bucket_head(int sc) { return bucket_set(sc) ? (uint32_t)head(sc) : kNoSlot; }
+    FQB_HD void publish(int sc, uint32_t last) {
+        head(sc) = (HeadT)last;
         if (sc < 64) mask0 |= 1ull << sc; else mask1 |= 1ull << (sc - 64);
+    }
+    FQB_HD void push(int pa, int pi, uint32_t pk, uint32_t pl, int mm, int go, int ge, int st, int pldp) {
+        int sc = score3(mm, go, ge);
+        uint32_t s = emit(pk, pl, pack_meta(pi, pa, st, mm, go, ge), pldp, bucket_head(sc));
+        if (!overflow) publish(sc, s);
     }
 
     // gap_pop (libbwa/bwtgap.c:66-79); the exact-match child of the previous expansion is
@@ -243,6 +266,7 @@ struct SearchLane {
         --n_entries;
         ++n_pops;
         if (have_cur) { have_cur = false; return; }
+        FQB_STAT(st_mempop);
         int b = mask0 ? FQB_FFSLL(mask0) - 1 : 63 + FQB_FFSLL(mask1);
         uint32_t s = (uint32_t)head(b);
         uint4 e = arena[s];
@@ -261,9 +285,9 @@ struct SearchLane {
         len = read_len; max_diff_opt = max_diff = read_max_diff;
         best_score = score3(max_diff_opt + 1, opt->max_gapo + 1, opt->max_gape + 1);
         best_cnt = 0; n_aln = 0; n_entries = 0;
-        mask0 = mask1 = 0; top = 0; free_head = spare = kNoSlot;
+        mask0 = mask1 = 0; top = 0; free_head = kNoSlot;
         have_cur = false; mode = kModePop; overflow = false;
-        n_pops = n_occ = 0; hit_x = 0;
+        n_pops = n_occ = n_blk = 0; hit_x = 0;
         if (n_ambig > max_diff) return kLaneDone;
         push(0, len, 0, bwt[0].seq_len, 0, 0, 0, kStateM, 0);
         // second root (strand 1) is the top of bucket 0: keep it in registers
@@ -311,14 +335,15 @@ struct SearchLane {
     }
 
     FQB_HD LaneStatus step() {
+        FQB_STAT(st_iter);
         if (mode == kModePop) {
             if (n_entries == 0 || n_entries > opt->max_entries) return kLaneDone;
             pop();
             if (!(opt->mode & kModeNonStop) && score3(n_mm, n_gapo, n_gape) > best_score + opt->s_mm) return kLaneDone;
             int m = diffs_left();
-            if (m < 0) return kLaneRunning;
-            if (i == 0) return on_hit();
-            if (m < width_bid(wa()[i - 1])) return kLaneRunning;
+            if (m < 0) { FQB_STAT(st_skip); return kLaneRunning; }
+            if (i == 0) { FQB_STAT(st_hit); return on_hit(); }
+            if (m < width_bid(wa()[i - 1])) { FQB_STAT(st_skip); return kLaneRunning; }
             if (m == 0 && (state == kStateM || (opt->mode & kModeGapE) || n_gape == opt->max_gape)) {
                 if (read_sym(fwd, len, a, i - 1) > 3) return kLaneRunning;   // bwt_match_exact_alt: N never matches
                 mode = kModeExact;
@@ -328,7 +353,9 @@ struct SearchLane {
         uint32_t ck[4], cl[4];
         occ4_pair(b, k - 1, l, ck, cl);
         ++n_occ;
+        n_blk += ref_block_touches(b, k - 1, l);
 
+        if (mode == kModeExact) FQB_STAT(st_exact); else FQB_STAT(st_expand);
         if (mode == kModeExact) {                   // one step of bwt_match_exact_alt (libbwa/bwt.c:102-117)
             uint32_t c = read_sym(fwd, len, a, i - 1);
             k = pick4(b.L2, c) + pick4(ck, c) + 1;
@@ -358,46 +385,57 @@ struct SearchLane {
                 else if (width_bid(sl) == m_seed - 1 && width_bid(sh) == m_seed - 1 && width_w(sl) == width_w(sh)) allow_M = false;
             }
         }
+        if (allow_diff) FQB_STAT(st_adiff);
+        if (allow_diff && allow_M) FQB_STAT(st_am);
         int gaps = n_gapo + n_gape;
         if (opt->mode & kModeLogGap) { int v = gaps, c = 0; while (v >>= 1) ++c; gaps = c / 2 + 1; }
+        // child intervals for the four symbols
+        uint32_t kk[4], ll[4];
+        _Pragma("unroll")
+        for (int j = 0; j < 4; ++j) { kk[j] = b.L2[j] + ck[j] + 1; ll[j] = b.L2[j] + cl[j]; }
+        // gap children share one score bucket: insertion first, then deletions j = 0..3
+        bool do_i = false, do_d = false;
+        int go2 = n_gapo, ge2 = n_gape;
         if (allow_diff && i >= opt->indel_end_skip + gaps && len - i >= opt->indel_end_skip + gaps) {
-            if (state == kStateM) {
-                if (n_gapo < opt->max_gapo) {
-                    push(a, i, k, l, n_mm, n_gapo + 1, n_gape, kStateI, i);
-                    _Pragma("unroll")
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t kk = b.L2[j] + ck[j] + 1, ll = b.L2[j] + cl[j];
-                        if (kk <= ll) push(a, i + 1, kk, ll, n_mm, n_gapo + 1, n_gape, kStateD, i + 1);
-                    }
-                }
-            } else if (state == kStateI) {
-                if (n_gape < opt->max_gape) push(a, i, k, l, n_mm, n_gapo, n_gape + 1, kStateI, i);
-            } else {
-                if (n_gape < opt->max_gape && (n_gape + n_gapo < max_diff || occ < (uint32_t)opt->max_del_occ)) {
-                    _Pragma("unroll")
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t kk = b.L2[j] + ck[j] + 1, ll = b.L2[j] + cl[j];
-                        if (kk <= ll) push(a, i + 1, kk, ll, n_mm, n_gapo, n_gape + 1, kStateD, i + 1);
-                    }
-                }
-            }
+            if (state == kStateM) { if (n_gapo < opt->max_gapo) { do_i = do_d = true; go2 = n_gapo + 1; } }
+            else if (state == kStateI) { if (n_gape < opt->max_gape) { do_i = true; ge2 = n_gape + 1; } }
+            else if (n_gape < opt->max_gape && (n_gape + n_gapo < max_diff || occ < (uint32_t)opt->max_del_occ)) { do_d = true; ge2 = n_gape + 1; }
         }
-        uint32_t s = read_sym(fwd, len, a, i);
+        if (do_i || do_d) {
+            FQB_STAT(st_gapok);
+            const int sc = score3(n_mm, go2, ge2);
+            const uint32_t old = bucket_head(sc);
+            uint32_t last = old;
+            if (do_i) last = emit(k, l, pack_meta(i, a, kStateI, n_mm, go2, ge2), i, last);
+            if (do_d) {
+                const uint32_t meta_d = pack_meta(i + 1, a, kStateD, n_mm, go2, ge2);
+                _Pragma("unroll")
+                for (int j = 0; j < 4; ++j)
+                    if (kk[j] <= ll[j]) last = emit(kk[j], ll[j], meta_d, i + 1, last);
+            }
+            if (last != old) publish(sc, last);
+        }
+        // mismatch children (one bucket), exact child last
+        const uint32_t s = read_sym(fwd, len, a, i);
         bool keep = false;
         uint32_t nk = 0, nl = 0;
         if (allow_diff && allow_M) {
+            const int sc = score3(n_mm + 1, n_gapo, n_gape);
+            const uint32_t meta_m = pack_meta(i, a, kStateM, n_mm + 1, n_gapo, n_gape);
+            const uint32_t old = bucket_head(sc);
+            uint32_t last = old;
             _Pragma("unroll")
             for (int j = 1; j <= 4; ++j) {
-                uint32_t c = (s + j) & 3;
-                bool is_mm = (j != 4 || s > 3);
-                uint32_t kk = pick4(b.L2, c) + pick4(ck, c) + 1, ll = pick4(b.L2, c) + pick4(cl, c);
-                if (kk > ll) continue;
-                if (is_mm) push(a, i, kk, ll, n_mm + 1, n_gapo, n_gape, kStateM, i);
-                else { keep = true; nk = kk; nl = ll; }
+                const uint32_t c = (s + j) & 3;
+                const uint32_t ck_ = pick4(kk, c), cl_ = pick4(ll, c);
+                if (ck_ > cl_) continue;
+                if (j != 4 || s > 3) last = emit(ck_, cl_, meta_m, i, last);
+                else { keep = true; nk = ck_; nl = cl_; }
             }
+            if (last != old) publish(sc, last);
         } else if (s < 4) {
-            uint32_t kk = pick4(b.L2, s) + pick4(ck, s) + 1, ll = pick4(b.L2, s) + pick4(cl, s);
-            if (kk <= ll) { keep = true; nk = kk; nl = ll; }
+            const uint32_t ck_ = pick4(kk, s), cl_ = pick4(ll, s);
+            if (ck_ <= cl_) { keep = true; nk = ck_; nl = cl_; }
         }
         if (keep) {      // exact child: pushed last into the parent's own bucket, hence popped next;
             k = nk; l = nl; state = kStateM; have_cur = true; ++n_entries;   // inherits last_diff_pos

@@ -71,6 +71,7 @@ struct fqb_handle {
     std::vector<uint32_t> h_overflow;
     SearchOpt sopt;
     bool batch_ready = false;
+    uint64_t n_launches = 0;
 };
 
 static void free_batch(fqb_handle *h) {
@@ -264,7 +265,8 @@ int fqb_stage_align(fqb_handle *h) {
     PrepParams pp;
     pp.trim_qual = h->gopt.trim_qual; pp.kmer_thresh = h->gopt.kmer_thresh; pp.is_il13 = h->gopt.is_il13; pp.roll = h->d_roll;
     launch_prep(h->bv, pp, st);
-    launch_width(h->bv, h->wv, h->dbwt, h->gopt.seed_len, h->bv.work, h->bv.n_work, h->n_reads, st);
+    h->n_launches += 3;
+    launch_width(h->bv, h->wv, h->dbwt, h->gopt.seed_len, h->bv.work, h->bv.n_work, h->n_reads, h->d_counters, st);
 
     h->sopt = make_search_opt(h->gopt, h->stride);
     if (h->sopt.n_buckets > 128) { set_error("more than 128 score buckets"); return FQB_ERR_LIMIT; }
@@ -302,7 +304,7 @@ int fqb_stage_align(fqb_handle *h) {
         CU_CHECK(cudaMemcpyAsync(h->h_overflow.data(), h->d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToHost, st));
         CU_CHECK(cudaStreamSynchronize(st));
         // widths were mutated by gap_shadow before the overflow: recompute them for these reads
-        launch_width(h->bv, h->wv, h->dbwt, h->gopt.seed_len, h->d_overflow, h->d_ctrs + 2, (int)n_over, st);
+        launch_width(h->bv, h->wv, h->dbwt, h->gopt.seed_len, h->d_overflow, h->d_ctrs + 2, (int)n_over, nullptr, st);
         std::vector<int32_t> slots(n_over);
         for (uint32_t j = 0; j < n_over; ++j) {
             slots[j] = (int32_t)j;
@@ -317,6 +319,7 @@ int fqb_stage_align(fqb_handle *h) {
         s2.overflow = h->d_overflow + h->cap_reads; s2.n_overflow = h->d_ctrs + 6;
         s2.counters = nullptr;
         launch_search(h->bv, h->wv, s2, false, 1, st);
+        h->n_launches += 2;
         CU_CHECK(cudaGetLastError());
         CU_CHECK(cudaStreamSynchronize(st));
         uint32_t still = 0;
@@ -370,16 +373,17 @@ int fqb_stage_fetch_aln(fqb_handle *h, int32_t cap, fqb_aln_t *out, int32_t *n_a
     return FQB_OK;
 }
 
-// [0] stack pops, [1] rank-query pairs issued by the search kernel since creation, [2] overflow reads of the last batch
-int fqb_stage_counters(fqb_handle *h, uint64_t *out3) {
+// since creation: [0] stack pops, [1] rank-query pairs issued by the search kernel, [2] reference-equivalent
+// occ-block touches N_blk of bwt_cal_width + bwt_match_gap; [3] overflow reads of the last batch
+int fqb_stage_counters(fqb_handle *h, uint64_t *out4) {
     if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
     CU_CHECK(cudaSetDevice(h->device));
     CU_CHECK(cudaStreamSynchronize(h->stream));
-    unsigned long long c[2];
+    unsigned long long c[3];
     uint32_t ov = 0;
-    CU_CHECK(cudaMemcpy(c, h->d_counters, 16, cudaMemcpyDeviceToHost));
+    CU_CHECK(cudaMemcpy(c, h->d_counters, 24, cudaMemcpyDeviceToHost));
     CU_CHECK(cudaMemcpy(&ov, h->d_ctrs + 2, 4, cudaMemcpyDeviceToHost));
-    out3[0] = c[0]; out3[1] = c[1]; out3[2] = ov;
+    out4[0] = c[0]; out4[1] = c[1]; out4[2] = c[2]; out4[3] = ov;
     return FQB_OK;
 }
 
@@ -391,6 +395,8 @@ int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_
     set_error("fqb_align_pairs: pair resolution stages are not built yet (use the fqb_stage_* entry points)");
     return FQB_ERR_STATE;
 }
+
+uint64_t fqb_launch_count(const fqb_handle *h) { return h ? h->n_launches : 0; }
 
 void *fqb_stream(fqb_handle *h) { return h ? (void *)h->stream : nullptr; }
 

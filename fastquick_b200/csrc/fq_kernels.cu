@@ -141,7 +141,7 @@ void launch_prep(const BatchView &b, const PrepParams &p, cudaStream_t s) {
 struct WidthParams { DevBwt bwt[2]; };
 
 __global__ void __launch_bounds__(128) width_kernel(BatchView b, WidthView wv, WidthParams wp, int seed_len,
-                                                     const uint32_t *work, const uint32_t *n_work) {
+                                                     const uint32_t *work, const uint32_t *n_work, unsigned long long *counters) {
     // a warp handles 32 reads for one part, so lanes run loops of the same trip count
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t wi = (idx >> 7) * 32 + (idx & 31);
@@ -155,18 +155,22 @@ __global__ void __launch_bounds__(128) width_kernel(BatchView b, WidthView wv, W
     if (seed && len <= seed_len) return;
     const int first = seed ? len - seed_len : 0, n = seed ? seed_len : len;
     uint32_t *out = seed ? wv.sw + ((size_t)r * 2 + a) * wv.sstride : wv.w + ((size_t)r * 2 + a) * wv.wstride;
-    if (a == 0) cal_width(wp.bwt[0], fwd, len, 0, first, n, out);
-    else cal_width(wp.bwt[1], fwd, len, 1, first, n, out);
+    uint32_t touches = a == 0 ? cal_width(wp.bwt[0], fwd, len, 0, first, n, out) : cal_width(wp.bwt[1], fwd, len, 1, first, n, out);
+    if (counters) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) touches += __shfl_xor_sync(__activemask(), touches, d);
+        if ((threadIdx.x & 31) == 0) atomicAdd(counters + 2, (unsigned long long)touches);
+    }
 }
 
 void launch_width(const BatchView &b, const WidthView &wv, const DevBwt bwt[2], int seed_len, const uint32_t *work,
-                  const uint32_t *n_work, int max_work, cudaStream_t s) {
+                  const uint32_t *n_work, int max_work, unsigned long long *counters, cudaStream_t s) {
     WidthParams wp;
     wp.bwt[0] = bwt[0]; wp.bwt[1] = bwt[1];
     long long threads = ((long long)(max_work + 31) / 32) * 128;
     int blocks = (int)((threads + 127) / 128);
     if (blocks < 1) blocks = 1;
-    width_kernel<<<blocks, 128, 0, s>>>(b, wv, wp, seed_len, work, n_work);
+    width_kernel<<<blocks, 128, 0, s>>>(b, wv, wp, seed_len, work, n_work, counters);
 }
 
 // ---------------------------------------------------------------------------
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(BatchView b, Wid
     const uint32_t n_work = *p.n_work;
     bool active = false, exhausted = false;
     uint32_t r = 0;
-    unsigned long long pops = 0, occs = 0;
+    unsigned long long pops = 0, occs = 0, blks = 0;
 
     for (;;) {
         LaneStatus st = kLaneRunning;
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(BatchView b, Wid
         warp_shadow(lane, active && st == kLaneHit, lane_id);
         if (active && (st == kLaneDone || st == kLaneOverflow)) {
             active = false;
-            pops += lane.n_pops; occs += lane.n_occ;
+            pops += lane.n_pops; occs += lane.n_occ; blks += lane.n_blk;
             p.n_aln[r] = st == kLaneOverflow ? -1 : lane.n_aln;
             if (st == kLaneOverflow) p.overflow[atomicAdd(p.n_overflow, 1u)] = r;
         }
@@ -264,8 +268,9 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(BatchView b, Wid
     for (int d = 16; d > 0; d >>= 1) {
         pops += __shfl_xor_sync(FULL_MASK, pops, d);
         occs += __shfl_xor_sync(FULL_MASK, occs, d);
+        blks += __shfl_xor_sync(FULL_MASK, blks, d);
     }
-    if (lane_id == 0 && p.counters) { atomicAdd(p.counters, pops); atomicAdd(p.counters + 1, occs); }
+    if (lane_id == 0 && p.counters) { atomicAdd(p.counters, pops); atomicAdd(p.counters + 1, occs); atomicAdd(p.counters + 2, blks); }
 }
 
 int search_grid_blocks(int n_buckets, bool heads16, int device) {

@@ -128,7 +128,10 @@ int fqb_stage_align(fqb_handle *h);
 int fqb_stage_fetch_prep(fqb_handle *h, int32_t *len, int32_t *full_len, uint8_t *filtered,
                          uint8_t *codes, int32_t codes_stride);
 int fqb_stage_fetch_aln(fqb_handle *h, int32_t cap, fqb_aln_t *out, int32_t *n_aln);
-int fqb_stage_counters(fqb_handle *h, uint64_t *out3);
+/* since creation: stack pops, rank-query pairs, reference-equivalent occ-block touches (N_blk, the
+ * roofline's algorithmic unit), overflow reads of the last batch */
+int fqb_stage_counters(fqb_handle *h, uint64_t *out4);
+uint64_t fqb_launch_count(const fqb_handle *h);   /* kernels launched by this handle so far */
 void *fqb_stream(fqb_handle *h);   /* the cudaStream_t the handle launches on (for event timing) */
 
 /* ---- synthetic fixtures (bench + tests; hs37d5/dbSNP are not available offline) ----

@@ -95,7 +95,7 @@ def test_counters_and_determinism(small_index):
         b = _run_cuda(lib, h, arrs)
         for x, y in zip(a, b):
             assert (x == y).all()
-        c = (C.c_uint64 * 3)()
+        c = (C.c_uint64 * 4)()
         assert lib.fqb_stage_counters(h, c) == 0
         assert c[0] > 0 and c[1] > 0
     finally:

@@ -50,7 +50,7 @@ def main():
     ptr = [C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_uint8)) for t in dev]
     assert lib.fqb_stage_load(h, n, L, ptr[0], ptr[1], None, ptr[2], ptr[3], None, 1) == 0, lib.fqb_last_error()
     for it in range(a.iters):
-        c0 = (C.c_uint64 * 3)(); lib.fqb_stage_counters(h, c0)
+        c0 = (C.c_uint64 * 4)(); lib.fqb_stage_counters(h, c0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record(stream)
@@ -59,10 +59,10 @@ def main():
         assert rc == 0, lib.fqb_last_error()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        c1 = (C.c_uint64 * 3)(); lib.fqb_stage_counters(h, c1)
+        c1 = (C.c_uint64 * 4)(); lib.fqb_stage_counters(h, c1)
         pops, occ = c1[0] - c0[0], c1[1] - c0[1]
         print("iter %d: %.2f ms  %.3e pairs/s  pops/read %.1f occ/read %.1f overflow %d  occ-steps/s %.3e" % (
-            it, ms, n / ms * 1e3, pops / (2 * n), occ / (2 * n), c1[2], occ / ms * 1e3), flush=True)
+            it, ms, n / ms * 1e3, pops / (2 * n), occ / (2 * n), c1[3], occ / ms * 1e3), flush=True)
     na = np.zeros(2 * n, np.int32)
     aln = np.zeros((2 * n, 8), _abi.ALN_DTYPE)
     assert lib.fqb_stage_fetch_aln(h, 8, aln.ctypes.data_as(C.c_void_p), _abi.i32p(na)) == 0
