@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -32,7 +33,9 @@ using namespace fqb;
 namespace {
 constexpr int kAlnCapFast = 8;          // hits kept per read in the fast pass
 constexpr int kAlnCapSlow = 1024;       // per read in the overflow pass
-constexpr uint32_t kArenaFast = 2048;   // stack entries per lane (observed peaks ~1.2k)
+constexpr uint32_t kArenaFast = 4096;   // stack entries per lane in the fast pass (bump-allocated; pushes/read ~300 mean)
+constexpr uint32_t kArenaMid = 60000;   // overflow tier 1 (still 16-bit bucket heads)
+constexpr int kMidBlocks = 16;
 }  // namespace
 
 struct fqb_handle {
@@ -64,6 +67,7 @@ struct fqb_handle {
     int n_blocks16 = 0;
     uint4 *d_arena = nullptr;
     uint4 *d_arena_big = nullptr;
+    uint4 *d_arena_mid = nullptr;
     uint32_t arena_big_cap = 0;
     Hit *d_aln_big = nullptr;
     int32_t *d_spill_slot = nullptr;     // per read: row in d_aln_big or -1
@@ -72,6 +76,7 @@ struct fqb_handle {
     SearchOpt sopt;
     bool batch_ready = false;
     uint64_t n_launches = 0;
+    uint32_t arena_fast = kArenaFast, arena_mid = kArenaMid;   // FQB_DEBUG_ARENA_FAST/_MID shrink them (tests of the overflow tiers)
 };
 
 static void free_batch(fqb_handle *h) {
@@ -106,7 +111,7 @@ static int ensure_batch(fqb_handle *h, int n_reads, int stride) {
     CU_CHECK(cudaMalloc(&h->wv.sw, (size_t)cap * 2 * h->wv.sstride * 4));
     CU_CHECK(cudaMalloc(&h->d_aln, (size_t)cap * kAlnCapFast * sizeof(Hit)));
     CU_CHECK(cudaMalloc(&h->d_naln, (size_t)cap * 4));
-    CU_CHECK(cudaMalloc(&h->d_overflow, (size_t)cap * 2 * 4));
+    CU_CHECK(cudaMalloc(&h->d_overflow, (size_t)cap * 3 * 4));
     CU_CHECK(cudaMalloc(&h->d_spill_slot, (size_t)cap * 4));
     h->cap_reads = cap; h->lpad = lpad; h->stride_cap = stride;
     return FQB_OK;
@@ -149,6 +154,8 @@ int fqb_create_from_synth(const fqb_synth *s, const fqb_gap_opt_t *gopt, const f
 
 static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     h->device = device;
+    if (const char *e = getenv("FQB_DEBUG_ARENA_FAST")) h->arena_fast = (uint32_t)atoi(e);
+    if (const char *e = getenv("FQB_DEBUG_ARENA_MID")) h->arena_mid = (uint32_t)atoi(e);
     if ((uint64_t)h->hidx.bwt[0].seq_len + 1 >= (1ull << kWidthBits)) {
         set_error("reduced reference too long for the packed width table (limit 2^27 bases)");
         delete h; return FQB_ERR_LIMIT;
@@ -213,7 +220,7 @@ void fqb_destroy(fqb_handle *h) {
     free_batch(h);
     for (int s = 0; s < 2; ++s) { cudaFree(h->d_blocks[s]); cudaFree(h->d_sa[s]); }
     cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_ctrs); cudaFree(h->d_counters);
-    cudaFree(h->d_arena); cudaFree(h->d_arena_big); cudaFree(h->d_aln_big);
+    cudaFree(h->d_arena); cudaFree(h->d_arena_mid); cudaFree(h->d_arena_big); cudaFree(h->d_aln_big);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -272,60 +279,65 @@ int fqb_stage_align(fqb_handle *h) {
     if (h->sopt.n_buckets > 128) { set_error("more than 128 score buckets"); return FQB_ERR_LIMIT; }
     if (!h->d_arena) {
         h->n_blocks16 = search_grid_blocks(h->sopt.n_buckets, true, h->device);
-        CU_CHECK(cudaMalloc(&h->d_arena, (size_t)h->n_blocks16 * kSearchThreads * kArenaFast * sizeof(uint4)));
+        CU_CHECK(cudaMalloc(&h->d_arena, (size_t)h->n_blocks16 * kSearchThreads * h->arena_fast * sizeof(uint4)));
     }
     SearchParams sp;
     sp.bwt[0] = h->dbwt[0]; sp.bwt[1] = h->dbwt[1];
     sp.opt = h->sopt; sp.maxdiff = h->d_maxdiff; sp.seed_len_opt = h->gopt.seed_len;
     sp.work = h->bv.work; sp.n_work = h->d_ctrs; sp.cursor = h->d_ctrs + 1;
-    sp.arena = h->d_arena; sp.arena_cap = kArenaFast;
+    sp.arena = h->d_arena; sp.arena_cap = h->arena_fast;
     sp.aln = h->d_aln; sp.aln_cap = kAlnCapFast; sp.n_aln = h->d_naln; sp.aln_row = nullptr;
     sp.overflow = h->d_overflow; sp.n_overflow = h->d_ctrs + 2;
     sp.counters = h->d_counters;
     CU_CHECK(cudaMemsetAsync(h->d_naln, 0, (size_t)h->n_reads * 4, st));
     CU_CHECK(cudaMemsetAsync(h->d_spill_slot, 0xff, (size_t)h->n_reads * 4, st));
-    launch_search(h->bv, h->wv, sp, true, h->n_blocks16, st);
+    launch_search(h->bv, h->wv, sp, true, false, h->n_blocks16, st);
     CU_CHECK(cudaGetLastError());
 
     uint32_t n_over = 0;
     CU_CHECK(cudaMemcpyAsync(&n_over, h->d_ctrs + 2, 4, cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaStreamSynchronize(st));
-    if (n_over) {       // rare: redo these reads with an arena as deep as the reference allows (max_entries)
+    // Rare reads whose stack or hit list outgrew the fast pass are redone from scratch with deeper arenas:
+    // tier 1 = 60k entries per lane on up to 16 blocks, tier 2 = as deep as the reference allows (max_entries).
+    for (int tier = 1; tier <= 2 && n_over; ++tier) {
         if ((int)n_over > h->n_spill_cap) {
             cudaFree(h->d_aln_big);
             h->n_spill_cap = (int)n_over + 1024;
             CU_CHECK(cudaMalloc(&h->d_aln_big, (size_t)h->n_spill_cap * kAlnCapSlow * sizeof(Hit)));
         }
-        if (!h->d_arena_big) {
-            h->arena_big_cap = (uint32_t)h->gopt.max_entries + 64;
-            CU_CHECK(cudaMalloc(&h->d_arena_big, (size_t)kSearchThreads * h->arena_big_cap * sizeof(uint4)));
-        }
+        const bool heads16 = tier == 1;
+        const uint32_t cap = tier == 1 ? h->arena_mid : (uint32_t)h->gopt.max_entries + 64;
+        int blocks = tier == 1 ? (int)((n_over + kSearchThreads - 1) / kSearchThreads) : 1;
+        if (blocks > kMidBlocks) blocks = kMidBlocks;
+        uint4 *&arena = tier == 1 ? h->d_arena_mid : h->d_arena_big;
+        if (!arena) CU_CHECK(cudaMalloc(&arena, (size_t)(tier == 1 ? kMidBlocks : 1) * kSearchThreads * cap * sizeof(uint4)));
         h->h_overflow.resize(n_over);
-        CU_CHECK(cudaMemcpyAsync(h->h_overflow.data(), h->d_overflow, (size_t)n_over * 4, cudaMemcpyDeviceToHost, st));
+        const uint32_t *list = tier == 1 ? h->d_overflow : h->d_overflow + h->cap_reads;
+        CU_CHECK(cudaMemcpyAsync(h->h_overflow.data(), list, (size_t)n_over * 4, cudaMemcpyDeviceToHost, st));
         CU_CHECK(cudaStreamSynchronize(st));
         // widths were mutated by gap_shadow before the overflow: recompute them for these reads
-        launch_width(h->bv, h->wv, h->dbwt, h->gopt.seed_len, h->d_overflow, h->d_ctrs + 2, (int)n_over, nullptr, st);
+        uint32_t ctr[3] = {n_over, 0u, 0u};            // n_work, cursor, next tier's overflow count
+        uint32_t *d_c = h->d_ctrs + 4 * tier;
+        CU_CHECK(cudaMemcpyAsync(d_c, ctr, 12, cudaMemcpyHostToDevice, st));
+        launch_width(h->bv, h->wv, h->dbwt, h->gopt.seed_len, list, d_c, (int)n_over, nullptr, st);
         std::vector<int32_t> slots(n_over);
-        for (uint32_t j = 0; j < n_over; ++j) {
-            slots[j] = (int32_t)j;
-            CU_CHECK(cudaMemcpyAsync(h->d_spill_slot + h->h_overflow[j], &slots[j], 4, cudaMemcpyHostToDevice, st));
-        }
-        uint32_t ctr[3] = {n_over, 0u, 0u};            // n_work, cursor, second-level overflow count
-        CU_CHECK(cudaMemcpyAsync(h->d_ctrs + 4, ctr, 12, cudaMemcpyHostToDevice, st));
+        for (uint32_t j = 0; j < n_over; ++j) slots[j] = (int32_t)j;
+        if (tier == 1)
+            for (uint32_t j = 0; j < n_over; ++j)
+                CU_CHECK(cudaMemcpyAsync(h->d_spill_slot + h->h_overflow[j], &slots[j], 4, cudaMemcpyHostToDevice, st));
         SearchParams s2 = sp;
-        s2.work = h->d_overflow; s2.n_work = h->d_ctrs + 4; s2.cursor = h->d_ctrs + 5;
-        s2.arena = h->d_arena_big; s2.arena_cap = h->arena_big_cap;
+        s2.work = list; s2.n_work = d_c; s2.cursor = d_c + 1;
+        s2.arena = arena; s2.arena_cap = cap;
         s2.aln = h->d_aln_big; s2.aln_cap = kAlnCapSlow; s2.aln_row = h->d_spill_slot;
-        s2.overflow = h->d_overflow + h->cap_reads; s2.n_overflow = h->d_ctrs + 6;
+        s2.overflow = h->d_overflow + h->cap_reads * (tier == 1 ? 1 : 2); s2.n_overflow = d_c + 2;
         s2.counters = nullptr;
-        launch_search(h->bv, h->wv, s2, false, 1, st);
+        launch_search(h->bv, h->wv, s2, heads16, true, blocks, st);
         h->n_launches += 2;
         CU_CHECK(cudaGetLastError());
+        CU_CHECK(cudaMemcpyAsync(&n_over, d_c + 2, 4, cudaMemcpyDeviceToHost, st));
         CU_CHECK(cudaStreamSynchronize(st));
-        uint32_t still = 0;
-        CU_CHECK(cudaMemcpy(&still, h->d_ctrs + 6, 4, cudaMemcpyDeviceToHost));
-        if (still) { set_error("a read overflowed even the max_entries-deep arena or 1024 hits"); return FQB_ERR_LIMIT; }
     }
+    if (n_over) { set_error("a read overflowed even the max_entries-deep arena or 1024 hits"); return FQB_ERR_LIMIT; }
     return FQB_OK;
 }
 

@@ -283,15 +283,17 @@ int search_grid_blocks(int n_buckets, bool heads16, int device) {
     return n_sm * per_sm;
 }
 
-void launch_search(const BatchView &b, const WidthView &wv, const SearchParams &p, bool heads16, int n_blocks, cudaStream_t s) {
-    size_t smem = (size_t)p.opt.n_buckets * kSearchThreads * (heads16 ? 2 : 4);
-    if (heads16) {
-        cudaFuncSetAttribute(search_kernel<uint16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        search_kernel<uint16_t, false><<<n_blocks, kSearchThreads, smem, s>>>(b, wv, p);
-    } else {
-        cudaFuncSetAttribute(search_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        search_kernel<uint32_t, true><<<n_blocks, kSearchThreads, smem, s>>>(b, wv, p);
-    }
+template <typename HeadT, bool kFreeList>
+static void launch_search_t(const BatchView &b, const WidthView &wv, const SearchParams &p, int n_blocks, cudaStream_t s) {
+    size_t smem = (size_t)p.opt.n_buckets * kSearchThreads * sizeof(HeadT);
+    cudaFuncSetAttribute(search_kernel<HeadT, kFreeList>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    search_kernel<HeadT, kFreeList><<<n_blocks, kSearchThreads, smem, s>>>(b, wv, p);
+}
+
+void launch_search(const BatchView &b, const WidthView &wv, const SearchParams &p, bool heads16, bool free_list, int n_blocks, cudaStream_t s) {
+    if (heads16 && !free_list) launch_search_t<uint16_t, false>(b, wv, p, n_blocks, s);
+    else if (heads16) launch_search_t<uint16_t, true>(b, wv, p, n_blocks, s);
+    else launch_search_t<uint32_t, true>(b, wv, p, n_blocks, s);
 }
 
 }  // namespace fqb

@@ -58,7 +58,7 @@ void launch_width(const BatchView &b, const WidthView &wv, const DevBwt bwt[2], 
                   const uint32_t *n_work, int max_work, unsigned long long *counters, cudaStream_t s);
 // returns the number of thread blocks launched (persistent grid); heads16 selects the 16-bit head table
 int search_grid_blocks(int n_buckets, bool heads16, int device);
-void launch_search(const BatchView &b, const WidthView &wv, const SearchParams &p, bool heads16, int n_blocks, cudaStream_t s);
+void launch_search(const BatchView &b, const WidthView &wv, const SearchParams &p, bool heads16, bool free_list, int n_blocks, cudaStream_t s);
 constexpr int kSearchThreads = 128;
 
 }  // namespace fqb

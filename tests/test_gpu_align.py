@@ -87,6 +87,22 @@ def test_align_no_trim(small_index, ref_required):
     _compare_with_ref(small_index, arrs, "gnotrim", trim_qual=0)
 
 
+def test_overflow_tiers_give_the_same_hits(small_index, ref_required, monkeypatch):
+    """Shrunken arenas push most reads through the deeper overflow tiers; results must not change."""
+    monkeypatch.setenv("FQB_DEBUG_ARENA_FAST", "48")
+    monkeypatch.setenv("FQB_DEBUG_ARENA_MID", "300")
+    arrs = small_index.reads(1500, read_len=100, seed=16)
+    _compare_with_ref(small_index, arrs, "gover")
+    lib, h = _engine(small_index)
+    try:
+        _run_cuda(lib, h, arrs)
+        c = (C.c_uint64 * 4)()
+        assert lib.fqb_stage_counters(h, c) == 0
+        assert c[3] > 100          # reads that overflowed the fast pass
+    finally:
+        lib.fqb_destroy(h)
+
+
 def test_counters_and_determinism(small_index):
     arrs = small_index.reads(2000, read_len=100, seed=15)
     lib, h = _engine(small_index)
