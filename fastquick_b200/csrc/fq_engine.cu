@@ -14,6 +14,7 @@
 #include "fq_hostmath.h"
 #include "fq_index.h"
 #include "fq_kernels.cuh"
+#include "fq_pair_kernels.cuh"
 #include "fq_relayout.h"
 #include "fq_synth.h"
 
@@ -76,6 +77,17 @@ struct fqb_handle {
     SearchOpt sopt;
     bool batch_ready = false;
     uint64_t n_launches = 0;
+    // paired-end resolution stage
+    fqb_read_t *d_rows = nullptr;
+    PeScratch pesc = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t *d_hist = nullptr;          // kIsizeBins + 1 (last = max_len)
+    int32_t *d_penalty = nullptr; size_t penalty_cap = 0;
+    int32_t *d_log_n = nullptr;
+    uint32_t *d_big_list = nullptr; uint64_t *d_pair_scratch = nullptr;
+    std::vector<uint32_t> h_hist;
+    uint64_t rng_x0 = 0, rng_calls = 0;  // srand48(bns->seed) stream position (src/BwtMapper.cpp:1817)
+    fqb_isize_t last_ii, cur_ii;
+    bool align_done = false, pair_done = false;
     uint32_t arena_fast = kArenaFast, arena_mid = kArenaMid;   // FQB_DEBUG_ARENA_FAST/_MID shrink them (tests of the overflow tiers)
 };
 
@@ -86,6 +98,9 @@ static void free_batch(fqb_handle *h) {
     cudaFree(h->bv.filtered); cudaFree(h->bv.n_ambig); cudaFree(h->bv.work);
     cudaFree(h->wv.w); cudaFree(h->wv.sw);
     cudaFree(h->d_aln); cudaFree(h->d_naln); cudaFree(h->d_overflow); cudaFree(h->d_spill_slot);
+    cudaFree(h->d_rows); cudaFree(h->pesc.packed); cudaFree(h->pesc.scanned); cudaFree(h->pesc.scan_tmp); cudaFree(h->pesc.cum_extra);
+    cudaFree(h->pesc.multi_list); cudaFree(h->d_big_list);
+    h->d_rows = nullptr; h->pesc.packed = h->pesc.scanned = h->pesc.scan_tmp = h->pesc.cum_extra = nullptr; h->pesc.multi_list = nullptr; h->d_big_list = nullptr;
     memset(&h->bv, 0, sizeof(h->bv)); memset(&h->wv, 0, sizeof(h->wv));
     h->d_aln = nullptr; h->d_naln = nullptr; h->d_overflow = nullptr; h->d_spill_slot = nullptr;
     h->cap_reads = 0;
@@ -113,6 +128,13 @@ static int ensure_batch(fqb_handle *h, int n_reads, int stride) {
     CU_CHECK(cudaMalloc(&h->d_naln, (size_t)cap * 4));
     CU_CHECK(cudaMalloc(&h->d_overflow, (size_t)cap * 3 * 4));
     CU_CHECK(cudaMalloc(&h->d_spill_slot, (size_t)cap * 4));
+    CU_CHECK(cudaMalloc(&h->d_rows, (size_t)cap * sizeof(fqb_read_t)));
+    CU_CHECK(cudaMalloc(&h->pesc.packed, (size_t)cap * 8));
+    CU_CHECK(cudaMalloc(&h->pesc.scanned, (size_t)cap * 8));
+    CU_CHECK(cudaMalloc(&h->pesc.scan_tmp, ((size_t)cap / 1024 + 2) * 2 * 8));
+    CU_CHECK(cudaMalloc(&h->pesc.cum_extra, (size_t)cap * 8));
+    CU_CHECK(cudaMalloc(&h->pesc.multi_list, (size_t)cap * 4));
+    CU_CHECK(cudaMalloc(&h->d_big_list, (size_t)cap * 2));
     h->cap_reads = cap; h->lpad = lpad; h->stride_cap = stride;
     return FQB_OK;
 }
@@ -187,6 +209,18 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     CU_CHECK_H(cudaMalloc(&h->d_maxdiff, sizeof(h->h_maxdiff)));
     CU_CHECK_H(cudaMemcpy(h->d_maxdiff, h->h_maxdiff, sizeof(h->h_maxdiff), cudaMemcpyHostToDevice));
     CU_CHECK_H(cudaMalloc(&h->d_ctrs, 16 * 4));
+    CU_CHECK_H(cudaMalloc(&h->pesc.totals, 4 * 8));
+    CU_CHECK_H(cudaMalloc(&h->pesc.err_flag, 4));
+    CU_CHECK_H(cudaMalloc(&h->d_hist, (kIsizeBins + 1) * 4));
+    {
+        int32_t g[256];
+        fill_log_n(g);
+        CU_CHECK_H(cudaMalloc(&h->d_log_n, sizeof(g)));
+        CU_CHECK_H(cudaMemcpy(h->d_log_n, g, sizeof(g), cudaMemcpyHostToDevice));
+    }
+    h->rng_x0 = lcg_seed(h->hidx.seed); h->rng_calls = 0;
+    h->last_ii.avg = h->last_ii.std = -1.0; h->last_ii.ap_prior = 0; h->last_ii.low = h->last_ii.high = h->last_ii.high_bayesian = h->last_ii.pad_ = 0;
+    h->cur_ii = h->last_ii;
     CU_CHECK_H(cudaMalloc(&h->d_counters, 4 * 8));
     CU_CHECK_H(cudaMemset(h->d_counters, 0, 4 * 8));
     if (h->gopt.kmer_thresh != 0) {     // 6 x 512 MiB bitmaps, streamed from disk (BwtIndexer::ReadRollHashTable)
@@ -221,6 +255,7 @@ void fqb_destroy(fqb_handle *h) {
     for (int s = 0; s < 2; ++s) { cudaFree(h->d_blocks[s]); cudaFree(h->d_sa[s]); }
     cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_ctrs); cudaFree(h->d_counters);
     cudaFree(h->d_arena); cudaFree(h->d_arena_mid); cudaFree(h->d_arena_big); cudaFree(h->d_aln_big);
+    cudaFree(h->pesc.totals); cudaFree(h->pesc.err_flag); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -259,7 +294,7 @@ int fqb_stage_load(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t
         b.lens_in[0] = lens1 ? h->d_lens_in[0] : nullptr; b.lens_in[1] = lens2 ? h->d_lens_in[1] : nullptr;
     }
     b.n_work = h->d_ctrs;
-    h->batch_ready = true;
+    h->batch_ready = true; h->align_done = h->pair_done = false;
     return FQB_OK;
 }
 
@@ -338,6 +373,96 @@ int fqb_stage_align(fqb_handle *h) {
         CU_CHECK(cudaStreamSynchronize(st));
     }
     if (n_over) { set_error("a read overflowed even the max_entries-deep arena or 1024 hits"); return FQB_ERR_LIMIT; }
+    h->align_done = true;
+    return FQB_OK;
+}
+
+// a6-a9 on the aligned batch: bwa_cal_pac_pos_pe (src/BwtMapper.cpp:721-907)
+int fqb_stage_pair(fqb_handle *h) {
+    if (!h || !h->batch_ready || !h->align_done) { set_error("fqb_stage_pair: run fqb_stage_align first"); return FQB_ERR_STATE; }
+    if (h->n_reads > 1024 * 1024) { set_error("fqb_stage_pair: at most 524,288 pairs per batch"); return FQB_ERR_LIMIT; }
+    CU_CHECK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    PeView v;
+    v.n_reads = h->n_reads;
+    v.aln = h->d_aln; v.aln_cap = kAlnCapFast; v.aln_big = h->d_aln_big; v.aln_big_cap = kAlnCapSlow;
+    v.spill_slot = h->d_spill_slot; v.n_aln = h->d_naln; v.filtered = h->bv.filtered;
+    v.len = h->bv.len; v.full_len = h->bv.full_len; v.rows = h->d_rows;
+    SeParams sp;
+    sp.bwt[0] = h->dbwt[0]; sp.bwt[1] = h->dbwt[1]; sp.maxdiff = h->d_maxdiff; sp.g_log_n = h->d_log_n;
+    RngState rng{h->rng_x0, h->rng_calls};
+    CU_CHECK(cudaMemsetAsync(h->pesc.err_flag, 0, 4, st));
+    CU_CHECK(cudaMemsetAsync(h->d_hist, 0, (kIsizeBins + 1) * 4, st));
+    launch_se(v, sp, rng, h->pesc, st);
+    launch_isize_hist(v, h->d_hist, h->d_hist + kIsizeBins, st);
+    h->n_launches += 9;
+    h->h_hist.resize(kIsizeBins + 1);
+    uint64_t totals[2] = {0, 0};
+    uint32_t err = 0;
+    CU_CHECK(cudaMemcpyAsync(h->h_hist.data(), h->d_hist, (kIsizeBins + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaMemcpyAsync(totals, h->pesc.totals, 16, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaMemcpyAsync(&err, h->pesc.err_flag, 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    CU_CHECK(cudaGetLastError());
+    if (err) { set_error("drand48 returned exactly 0.0 for a read with one best interval (p = 2^-48 per read): unsupported"); return FQB_ERR_LIMIT; }
+    h->rng_calls += totals[0];
+    // infer_isize + fallbacks (src/BwtMapper.cpp:779-786); libm on the host
+    fqb_isize_t ii;
+    infer_isize_hist(h->h_hist.data(), (int)h->h_hist[kIsizeBins], h->popt.ap_prior, (int64_t)h->hidx.bwt[0].seq_len, ii);
+    if (ii.avg < 0.0 && h->last_ii.avg > 0.0) ii = h->last_ii;
+    if (h->popt.force_isize) { ii.low = ii.high = 0; ii.avg = ii.std = -1.0; }
+    h->cur_ii = ii;
+    std::vector<int32_t> pen;
+    fill_isize_penalty(ii, pen);
+    if (pen.size() > h->penalty_cap) {
+        cudaFree(h->d_penalty);
+        h->penalty_cap = pen.size() + 1024;
+        CU_CHECK(cudaMalloc(&h->d_penalty, h->penalty_cap * 4));
+    }
+    if (!pen.empty()) CU_CHECK(cudaMemcpyAsync(h->d_penalty, pen.data(), pen.size() * 4, cudaMemcpyHostToDevice, st));
+    PairParams pp;
+    pp.high = ii.high; pp.high_bayesian = ii.high_bayesian; pp.max_isize = h->popt.max_isize; pp.s_mm = h->gopt.s_mm;
+    pp.max_occ = h->popt.max_occ; pp.n_multi = h->popt.n_multi; pp.N_multi = h->popt.N_multi;
+    pp.penalty = h->d_penalty; pp.g_log_n = h->d_log_n;
+    if (h->popt.type != 1) { set_error("only BWA_PET_STD pairing is supported (SOLiD is dead code in the reference)"); return FQB_ERR_ARG; }
+    CU_CHECK(cudaMemsetAsync(h->d_ctrs + 12, 0, 4, st));
+    launch_pair(v, h->dbwt, pp, h->d_big_list, h->d_ctrs + 12, st);
+    h->n_launches += 1;
+    uint32_t n_big = 0;
+    CU_CHECK(cudaMemcpyAsync(&n_big, h->d_ctrs + 12, 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    if (n_big) {          // pairs with many hit positions (repeats): global-memory scratch, one thread per pair
+        const size_t per_pair = 8192;
+        if (n_big > 4096) { set_error("too many repeat-heavy pairs in one batch"); return FQB_ERR_LIMIT; }
+        if (!h->d_pair_scratch) CU_CHECK(cudaMalloc(&h->d_pair_scratch, (size_t)4096 * per_pair * 8));
+        launch_pair_big(v, h->dbwt, pp, h->d_big_list, h->d_ctrs + 12, (int)n_big, h->d_pair_scratch, per_pair, st);
+        h->n_launches += 1;
+    }
+    CU_CHECK(cudaGetLastError());
+    h->last_ii = ii;
+    h->pair_done = true;
+    return FQB_OK;
+}
+
+// result rows of the last completed stage: rows[e][i] = end e of pair i
+int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out) {
+    if (!h || !h->pair_done) { set_error("fqb_stage_fetch_rows: run fqb_stage_pair first"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    const size_t np = (size_t)h->n_reads / 2;
+    if (np) {
+        CU_CHECK(cudaMemcpy2DAsync(rows1, sizeof(fqb_read_t), h->d_rows, 2 * sizeof(fqb_read_t), sizeof(fqb_read_t), np, cudaMemcpyDeviceToHost, h->stream));
+        CU_CHECK(cudaMemcpy2DAsync(rows2, sizeof(fqb_read_t), h->d_rows + 1, 2 * sizeof(fqb_read_t), sizeof(fqb_read_t), np, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU_CHECK(cudaStreamSynchronize(h->stream));
+    if (ii_out) *ii_out = h->cur_ii;
+    return FQB_OK;
+}
+
+// restart the per-file state: srand48(bns->seed) and last_ii (PairEndMapper runs once per FASTQ pair)
+int fqb_reset_stream(fqb_handle *h) {
+    if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    h->rng_calls = 0;
+    h->last_ii.avg = h->last_ii.std = -1.0; h->last_ii.low = h->last_ii.high = h->last_ii.high_bayesian = 0;
     return FQB_OK;
 }
 

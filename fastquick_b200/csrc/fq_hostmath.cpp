@@ -36,4 +36,57 @@ SearchOpt make_search_opt(const fqb_gap_opt_t &o, int max_len) {
     return s;
 }
 
+bool infer_isize_hist(const uint32_t *hist, int max_len_in, double ap_prior, int64_t L, fqb_isize_t &ii) {
+    ii.avg = ii.std = -1.0; ii.ap_prior = 0.0;
+    ii.low = ii.high = ii.high_bayesian = 0; ii.pad_ = 0;
+    uint64_t tot = 0;
+    for (int v = 0; v < kIsizeBins; ++v) tot += hist[v];
+    if (tot < 20) return false;
+    auto at = [&](uint64_t idx) {           // value at position idx of the sorted array
+        uint64_t c = 0;
+        for (int v = 0; v < kIsizeBins; ++v) { c += hist[v]; if (c > idx) return v; }
+        return kIsizeBins - 1;
+    };
+    const int itot = (int)tot;
+    int p25 = at((uint64_t)(int)(itot * 0.25 + 0.5));
+    int p75 = at((uint64_t)(int)(itot * 0.75 + 0.5));
+    int max_len = max_len_in < 1 ? 1 : max_len_in;
+    int tmp = (int)(p25 - 2.0 * (p75 - p25) + .499);
+    ii.low = tmp > max_len ? (uint32_t)tmp : (uint32_t)max_len;
+    ii.high = (uint32_t)(int)(p75 + 2.0 * (p75 - p25) + .499);
+    uint64_t x = 0;
+    int n = 0;
+    for (uint32_t v = ii.low; v <= ii.high && v < (uint32_t)kIsizeBins; ++v) { n += (int)hist[v]; x += (uint64_t)v * hist[v]; }
+    ii.avg = (double)x / n;
+    for (uint32_t v = ii.low; v <= ii.high && v < (uint32_t)kIsizeBins; ++v) {
+        const double t = ((uint64_t)v - ii.avg) * ((uint64_t)v - ii.avg);
+        for (uint32_t c = 0; c < hist[v]; ++c) ii.std += t;       // one addition per pair, in sorted order, as the reference does
+    }
+    ii.std = std::sqrt(ii.std / n);
+    double y;
+    for (y = 1.0; y < 10.0; y += 0.01)
+        if (.5 * std::erfc(y / M_SQRT2) < ap_prior / L * (y * ii.std + ii.avg)) break;
+    ii.high_bayesian = (uint32_t)(y * ii.std + ii.avg + .499);
+    uint64_t n_ap = 0;
+    for (int v = 0; v < kIsizeBins; ++v) if ((uint32_t)v > ii.high_bayesian) n_ap += hist[v];
+    ii.ap_prior = .01 * (n_ap + .01) / itot;
+    if (ii.ap_prior < ap_prior) ii.ap_prior = ap_prior;
+    if (std::isnan(ii.std) || p75 > 100000) {
+        ii.low = ii.high = ii.high_bayesian = 0; ii.avg = ii.std = -1.0;
+        return false;
+    }
+    for (y = 1.0; y < 10.0; y += 0.01)
+        if (.5 * std::erfc(y / M_SQRT2) < ap_prior / L * (y * ii.std + ii.avg)) break;
+    ii.high_bayesian = (uint32_t)(y * ii.std + ii.avg + .499);
+    return true;
+}
+
+void fill_isize_penalty(const fqb_isize_t &ii, std::vector<int32_t> &t) {
+    t.clear();
+    if (ii.high == 0) return;
+    t.resize((size_t)ii.high_bayesian + 1);
+    for (uint32_t l = 0; l <= ii.high_bayesian; ++l)
+        t[l] = (int32_t)(-4.343 * std::log(.5 * std::erfc(M_SQRT1_2 * std::fabs(l - ii.avg) / ii.std)) + .499);
+}
+
 }  // namespace fqb

@@ -125,6 +125,12 @@ int fqb_stage_load(fqb_handle *h, int32_t n_pairs, int32_t stride,
 /* a1-a5: read prep + k-mer filter (src/BwtMapper.cpp:543-590, src/BwtIndexer.cpp:524),
  * bwt_cal_width (libbwa/bwtaln.c:73) and bwt_match_gap (libbwa/bwtgap.c:104) = bwa_cal_sa_reg_gap */
 int fqb_stage_align(fqb_handle *h);
+/* a6-a9: bwa_cal_pac_pos_pe (src/BwtMapper.cpp:721-907) = bwa_aln2seq (drand48) + bwt_sa + bwa_approx_mapQ,
+ * infer_isize (libbwa/bwape.c:49), pairing (libbwa/bwape.c:119) and the multi-hit counts */
+int fqb_stage_pair(fqb_handle *h);
+int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
+/* new FASTQ pair: restart the drand48 stream and forget last_ii (src/BwtMapper.cpp:1811-1817) */
+int fqb_reset_stream(fqb_handle *h);
 int fqb_stage_fetch_prep(fqb_handle *h, int32_t *len, int32_t *full_len, uint8_t *filtered,
                          uint8_t *codes, int32_t codes_stride);
 int fqb_stage_fetch_aln(fqb_handle *h, int32_t cap, fqb_aln_t *out, int32_t *n_aln);

@@ -69,6 +69,26 @@ void orc_aln2seq_main(int n_aln, const orc_aln_t *aln, orc_rng_t *rng, orc_se_t 
 int orc_approx_mapq(const orc_se_t *s, int mm, const int g_log_n[256]);
 void orc_fill_log_n(int g_log_n[256]);
 
+/* ---- paired-end resolution: bwa_cal_pac_pos_pe (src/BwtMapper.cpp:721-907) ---------------- */
+typedef struct { double avg, std, ap_prior; uint32_t low, high, high_bayesian, pad_; } orc_isize_t;
+typedef struct {
+    int32_t max_isize, force_isize; uint32_t max_occ; int32_t n_multi, N_multi, type, is_sw; double ap_prior;
+} orc_pe_opt_t;
+/* per-read row; same layout as fqb_read_t (include/fastquick_b200.h) so tests can compare bytes */
+typedef struct {
+    uint32_t pos, sa, c1, c2; int32_t score, len, full_len, clip_len;
+    uint8_t type, strand, filtered, extra_flag, n_mm, n_gapo, n_gape, mapQ, seQ, n_cigar, n_multi, has_cigar;
+    uint16_t nm, n_aln; uint16_t cigar[16];
+} orc_row_t;
+/* infer_isize (libbwa/bwape.c:49-117); returns 0 ok / -1 failed */
+int orc_infer_isize(int n_pairs, const orc_row_t *rows /*2n, r=2*pair+end*/, orc_isize_t *ii, double ap_prior, int64_t L);
+/* whole stage for one batch.  rows: in = len/full_len/clip_len/filtered set, rest zero; out = after bwa_cal_pac_pos_pe.
+ * multi_pos (may be null): [2n][11] pac positions of the multi hits. */
+int orc_cal_pac_pos_pe(const orc_bwt_t *const bwts[2], int n_pairs, orc_row_t *rows, const int32_t *n_aln,
+                       const orc_aln_t *aln, int aln_cap, double fnr, int opt_max_diff, int s_mm,
+                       const orc_pe_opt_t *popt, orc_rng_t *rng, const orc_isize_t *last_ii, orc_isize_t *ii,
+                       uint32_t *multi_pos);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,11 +3,13 @@
 // the kernel LOGIC can be checked against the oracle where no GPU exists.  The
 // product library never contains or calls this.
 #define FQB_LANE_STATS 1
+#include <algorithm>
 #include <cstring>
 #include <cstdio>
 #include <string>
 #include <vector>
 #include "../../fastquick_b200/csrc/fq_device_core.cuh"
+#include "../../fastquick_b200/csrc/fq_device_pair.cuh"
 #include "../../fastquick_b200/csrc/fq_hostmath.h"
 #include "../../fastquick_b200/csrc/fq_index.h"
 #include "../../fastquick_b200/csrc/fq_relayout.h"
@@ -93,6 +95,79 @@ int emul_align(void *h, const fqb_gap_opt_t *gopt, int n, int stride, const uint
         if (arena_cap < 65535) { SearchLane<uint16_t, false> lane; lane.heads = heads16.data(); run(lane); }
         else { SearchLane<uint32_t, true> lane; lane.heads = heads.data(); run(lane); }
     }
+    return 0;
+}
+
+
+// Paired-end resolution with the SAME decomposition the kernels use (provisional draw counts -> prefix sum ->
+// sequential pass over multi-interval reads -> per-read jump-ahead; histogram -> host infer_isize -> pair_one).
+int emul_pe_batch(void *h, const fqb_gap_opt_t *gopt, const fqb_pe_opt_t *popt, int n_pairs, const int32_t *len,
+                  const int32_t *full_len, const uint8_t *filtered, const int32_t *n_aln, const fqb_aln_t *aln, int aln_cap,
+                  uint64_t *rng_calls, fqb_isize_t *last_ii, fqb_read_t *rows, fqb_isize_t *ii_out) {
+    Emul *e = (Emul *)h;
+    const int n = 2 * n_pairs;
+    int32_t maxdiff[FQB_MAX_READ_LEN + 1], g_log_n[256];
+    fill_maxdiff_table(*gopt, maxdiff);
+    fill_log_n(g_log_n);
+    const uint64_t x0 = lcg_seed(e->idx.seed);
+    auto hits = [&](int r) { return reinterpret_cast<const Hit *>(aln + (size_t)r * aln_cap); };
+    auto nh = [&](int r) { return filtered[r] ? 0 : n_aln[r]; };
+    std::vector<uint64_t> guess(n), scanned(n), cum_extra;
+    std::vector<uint32_t> multi;
+    uint64_t run = 0;
+    for (int r = 0; r < n; ++r) {
+        int na = nh(r), nb = na ? count_best(hits(r), na) : 0;
+        guess[r] = nb == 1 ? 2 : 0;
+        if (nb > 1) multi.push_back((uint32_t)r);
+        scanned[r] = run; run += guess[r];
+    }
+    uint64_t extra = 0;
+    for (uint32_t r : multi) {
+        fqb_read_t tmp; memset(&tmp, 0, sizeof tmp);
+        extra += se_choose(hits(r), nh(r), lcg_advance(x0, *rng_calls + scanned[r] + extra), tmp);
+        cum_extra.push_back(extra);
+    }
+    for (int r = 0; r < n; ++r) {
+        fqb_read_t &row = rows[r];
+        memset(&row, 0, sizeof row);
+        row.len = len[r]; row.full_len = full_len[r]; row.clip_len = len[r]; row.filtered = filtered[r];
+        row.extra_flag = kSamPaired | ((r & 1) ? kSamRead2 : kSamRead1);
+        int na = nh(r);
+        row.n_aln = (uint16_t)na;
+        if (!na) continue;
+        size_t lo = std::lower_bound(multi.begin(), multi.end(), (uint32_t)r) - multi.begin();
+        uint64_t ex = lo ? cum_extra[lo - 1] : 0;
+        se_choose(hits(r), na, lcg_advance(x0, *rng_calls + scanned[r] + ex), row);
+        row.pos = hit_position(e->bwt, row.strand, row.sa, row.len);
+        row.seQ = row.mapQ = (uint8_t)approx_mapq(row.c1, row.c2, row.n_mm, maxdiff[row.len], g_log_n);
+    }
+    *rng_calls += run + extra;
+    std::vector<uint32_t> hist(kIsizeBins, 0);
+    int max_len = 1;
+    for (int p = 0; p < n_pairs; ++p) {
+        const fqb_read_t &a = rows[2 * p], &b = rows[2 * p + 1];
+        if (a.mapQ >= 20 && b.mapQ >= 20) {
+            uint64_t x = a.pos < b.pos ? (uint64_t)b.pos + b.len - a.pos : (uint64_t)a.pos + a.len - b.pos;
+            if (x < 100000) ++hist[x];
+        }
+        if (a.len > max_len) max_len = a.len;
+        if (b.len > max_len) max_len = b.len;
+    }
+    fqb_isize_t ii;
+    infer_isize_hist(hist.data(), max_len, popt->ap_prior, (int64_t)e->idx.bwt[0].seq_len, ii);
+    if (ii.avg < 0.0 && last_ii->avg > 0.0) ii = *last_ii;
+    if (popt->force_isize) { ii.low = ii.high = 0; ii.avg = ii.std = -1.0; }
+    std::vector<int32_t> pen;
+    fill_isize_penalty(ii, pen);
+    PairParams pp;
+    pp.high = ii.high; pp.high_bayesian = ii.high_bayesian; pp.max_isize = popt->max_isize; pp.s_mm = gopt->s_mm;
+    pp.max_occ = popt->max_occ; pp.n_multi = popt->n_multi; pp.N_multi = popt->N_multi;
+    pp.penalty = pen.data(); pp.g_log_n = g_log_n;
+    std::vector<uint64_t> arr(8192);
+    for (int p = 0; p < n_pairs; ++p)
+        if (!pair_one(e->bwt, &rows[2 * p], &rows[2 * p + 1], hits(2 * p), nh(2 * p), hits(2 * p + 1), nh(2 * p + 1), pp, arr.data(), kPairArrCap))
+            if (!pair_one(e->bwt, &rows[2 * p], &rows[2 * p + 1], hits(2 * p), nh(2 * p), hits(2 * p + 1), nh(2 * p + 1), pp, arr.data(), 8192)) return -2;
+    *ii_out = ii; *last_ii = ii;
     return 0;
 }
 

@@ -37,6 +37,15 @@ def _load_bwt(bwt_path, sa_path):
     return b, (words, sa)
 
 
+class OrcRng(C.Structure):
+    _fields_ = [("x", C.c_uint64), ("n_calls", C.c_uint64)]
+
+
+class OrcPeOpt(C.Structure):
+    _fields_ = [("max_isize", C.c_int32), ("force_isize", C.c_int32), ("max_occ", C.c_uint32), ("n_multi", C.c_int32),
+                ("N_multi", C.c_int32), ("type", C.c_int32), ("is_sw", C.c_int32), ("ap_prior", C.c_double)]
+
+
 class Oracle:
     def __init__(self, prefix):
         self.lib = fx.build_oracle()
@@ -50,6 +59,32 @@ class Oracle:
         self.b1, self._k1 = _load_bwt(prefix + ".rbwt", prefix + ".rsa")
         self.bwts = (C.POINTER(OrcBwt) * 2)(C.pointer(self.b0), C.pointer(self.b1))
         self._roll = None
+        self.rng = OrcRng()
+        self.lib.orc_srand48(C.byref(self.rng), C.c_long(11))       # srand48(bns->seed), src/BwtMapper.cpp:1817
+        self.last_ii = _abi.ISize()
+        self.last_ii.avg = -1.0
+
+    def pe_batch(self, lens, full_lens, filt, out, na, cap=8, want_multi=False):
+        """bwa_cal_pac_pos_pe over one batch: returns (rows[2n] as READ_DTYPE, isize, multi_pos)."""
+        n2 = len(lens)
+        rows = np.zeros(n2, _abi.READ_DTYPE)
+        rows["len"] = lens; rows["full_len"] = full_lens; rows["clip_len"] = lens; rows["filtered"] = filt
+        rows["n_aln"] = np.where(filt != 0, 0, np.minimum(na, 65535))
+        _, g = self.gap_opt()
+        po = OrcPeOpt()
+        pe = _abi.PeOpt(); fx.host_lib().fqb_pe_opt_default(C.byref(pe))
+        for n, _ in OrcPeOpt._fields_:
+            setattr(po, n, getattr(pe, n))
+        ii = _abi.ISize()
+        multi = np.zeros((n2, 11), np.uint32) if want_multi else None
+        na32 = np.ascontiguousarray(np.where(filt != 0, 0, na).astype(np.int32))
+        rc = self.lib.orc_cal_pac_pos_pe(self.bwts, n2 // 2, rows.ctypes.data_as(C.c_void_p), _abi.i32p(na32),
+                                         out.ctypes.data_as(C.c_void_p), cap, C.c_double(g.fnr), g.max_diff, g.s_mm,
+                                         C.byref(po), C.byref(self.rng), C.byref(self.last_ii), C.byref(ii),
+                                         multi.ctypes.data_as(C.c_void_p) if want_multi else None)
+        assert rc == 0
+        self.last_ii = ii
+        return rows, ii, multi
 
     def roll_tables(self):
         if self._roll is None:

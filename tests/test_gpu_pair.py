@@ -1,0 +1,65 @@
+"""GPU parity for rows a6-a9 (bwa_cal_pac_pos_pe): SE hit choice on the glibc drand48 stream, bwt_sa positions,
+SE mapQ, infer_isize and pairing, across two consecutive batches (RNG position and last_ii carry over),
+against the reference's own snapshot taken right after bwa_cal_pac_pos_pe."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import fx
+from fastquick_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+FIELDS = ["pos", "sa", "c1", "c2", "score", "len", "full_len", "clip_len", "type", "strand", "filtered", "extra_flag",
+          "n_mm", "n_gapo", "n_gape", "mapQ", "seQ", "n_multi"]
+
+
+def _run(index, arrs, tag, batch, trim_qual=15, **ref_kw):
+    fq = index.write_fastq(tag, arrs)
+    ref = fx.RefRun(index.prefix, fq[0], fq[1], trim_qual=trim_qual, batch_cap=batch)
+    lib = fx.host_lib()
+    g = _abi.GapOpt()
+    lib.fqb_gap_opt_default(C.byref(g))
+    g.trim_qual = trim_qual
+    h = C.c_void_p()
+    assert lib.fqb_create(index.prefix.encode(), C.byref(g), None, 0, C.byref(h)) == 0, lib.fqb_last_error()
+    try:
+        n_tot, L = arrs[0].shape
+        for b in range(n_tot // batch):
+            assert ref.next_batch() == batch
+            sub = [np.ascontiguousarray(a[b * batch:(b + 1) * batch]) for a in arrs]
+            assert lib.fqb_stage_load(h, batch, L, _abi.u8p(sub[0]), _abi.u8p(sub[1]), None, _abi.u8p(sub[2]), _abi.u8p(sub[3]), None, 0) == 0
+            assert lib.fqb_stage_align(h) == 0, lib.fqb_last_error()
+            assert lib.fqb_stage_pair(h) == 0, lib.fqb_last_error()
+            rows = [np.zeros(batch, _abi.READ_DTYPE) for _ in range(2)]
+            ii = _abi.ISize()
+            assert lib.fqb_stage_fetch_rows(h, rows[0].ctypes.data_as(C.c_void_p), rows[1].ctypes.data_as(C.c_void_p), C.byref(ii)) == 0
+            rii = ref.isize()
+            assert (ii.avg, ii.std, ii.ap_prior, ii.low, ii.high, ii.high_bayesian) == (rii.avg, rii.std, rii.ap_prior, rii.low, rii.high, rii.high_bayesian)
+            for e in (0, 1):
+                rr = ref.rows(1, e)
+                for f in FIELDS:
+                    np.testing.assert_array_equal(rows[e][f], rr[f], err_msg="batch %d end %d field %s" % (b, e, f))
+            yield rows
+    finally:
+        lib.fqb_destroy(h)
+
+
+def test_pair_stage_two_batches(small_index, ref_required):
+    arrs = small_index.reads(6000, read_len=100, seed=51)
+    out = list(_run(small_index, arrs, "p100", 3000))
+    assert len(out) == 2
+    assert ((out[0][0]["extra_flag"] & 2) != 0).mean() > 0.8      # most pairs end up properly paired
+
+
+def test_pair_stage_high_error_150(small_index, ref_required):
+    arrs = small_index.reads(3000, read_len=150, seed=52, sub_rate=0.04, ins_rate=0.01, del_rate=0.01, max_indel_len=3)
+    list(_run(small_index, arrs, "p150", 3000))
+
+
+def test_pair_stage_mostly_filtered_batch_falls_back_to_last_isize(small_index, ref_required):
+    # second batch has too few confident pairs to infer an insert size: ii must fall back to the first batch's
+    a = small_index.reads(3000, read_len=100, seed=53)
+    b = small_index.reads(3000, read_len=100, seed=54, f_on=0.004)
+    arrs = [np.concatenate([x, y]) for x, y in zip(a, b)]
+    list(_run(small_index, arrs, "pfall", 3000))
