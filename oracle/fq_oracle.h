@@ -89,6 +89,16 @@ int orc_cal_pac_pos_pe(const orc_bwt_t *const bwts[2], int n_pairs, orc_row_t *r
                        const orc_pe_opt_t *popt, orc_rng_t *rng, const orc_isize_t *last_ii, orc_isize_t *ii,
                        uint32_t *multi_pos);
 
+/* ---- banded global alignment + gapped refinement (libbwa/stdaln.c:345-524, libbwa/bwase.c:183-337) ---- */
+int orc_global_align(const uint8_t *seq1, int len1, const uint8_t *seq2, int len2, int gap_open, int gap_ext, int gap_end,
+                     int band, uint8_t *ops_out, int *n_ops);
+int orc_ops_to_cigar(const uint8_t *ops, int n_ops, uint16_t *cigar);
+int orc_refine_gapped(int64_t l_pac, const uint8_t *pac, int len, const uint8_t *seq, uint32_t *pos_io, int ext, uint16_t *cigar);
+int orc_cal_nm(int n_cigar, const uint16_t *cigar, int has_cigar, int len, uint32_t pos, const uint8_t *seq, int64_t l_pac, const uint8_t *pac);
+void orc_paired_sw(int64_t l_pac, const uint8_t *pac, int n_pairs, orc_row_t *rows, const uint8_t *codes, int stride,
+                   const orc_pe_opt_t *popt, const orc_isize_t *ii);
+void orc_refine_gapped_batch(int64_t l_pac, const uint8_t *pac, int n_reads, orc_row_t *rows, const uint8_t *codes, int stride);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,9 +32,10 @@ def have_ref():
 
 
 def build_oracle():
-    src = os.path.join(REPO, "oracle", "fq_oracle.c")
-    if not os.path.exists(ORC_LIB) or os.path.getmtime(ORC_LIB) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", src, "-o", ORC_LIB, "-lm"])
+    srcs = [os.path.join(REPO, "oracle", f) for f in ("fq_oracle.c", "fq_oracle_pe.c", "fq_oracle_dp.c")]
+    deps = srcs + [os.path.join(REPO, "oracle", "fq_oracle.h")]
+    if not os.path.exists(ORC_LIB) or os.path.getmtime(ORC_LIB) < max(os.path.getmtime(s) for s in deps):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared"] + srcs + ["-o", ORC_LIB, "-lm"])
     return C.CDLL(ORC_LIB)
 
 

@@ -86,6 +86,30 @@ class Oracle:
         self.last_ii = ii
         return rows, ii, multi
 
+    def pac(self):
+        if not hasattr(self, "_pac"):
+            self._pac = np.fromfile(self.prefix + ".pac", dtype=np.uint8)
+            self._pac = np.concatenate([self._pac, np.zeros(16, np.uint8)])
+        return self._pac
+
+    def sw_and_refine(self, rows, ii, arrs):
+        """bwa_paired_sw then bwa_refine_gapped on the rows of pe_batch(); returns (rows after SW, rows after refine)."""
+        n, rl = arrs[0].shape
+        codes = np.zeros((2 * n, rl), np.uint8)
+        codes[0::2] = fx.NT4[arrs[0]]; codes[1::2] = fx.NT4[arrs[2]]
+        codes = np.ascontiguousarray(codes)
+        po = OrcPeOpt()
+        pe = _abi.PeOpt(); fx.host_lib().fqb_pe_opt_default(C.byref(pe))
+        for nme, _ in OrcPeOpt._fields_:
+            setattr(po, nme, getattr(pe, nme))
+        l_pac = int(self.b0.seq_len)
+        pac = self.pac()
+        rows = rows.copy()
+        self.lib.orc_paired_sw(C.c_int64(l_pac), _abi.u8p(pac), n, rows.ctypes.data_as(C.c_void_p), _abi.u8p(codes), rl, C.byref(po), C.byref(ii))
+        after_sw = rows.copy()
+        self.lib.orc_refine_gapped_batch(C.c_int64(l_pac), _abi.u8p(pac), 2 * n, rows.ctypes.data_as(C.c_void_p), _abi.u8p(codes), rl)
+        return after_sw, rows
+
     def roll_tables(self):
         if self._roll is None:
             self._roll = np.memmap(self.prefix + ".rollhash", dtype=np.uint8, mode="r")
