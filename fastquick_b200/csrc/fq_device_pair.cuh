@@ -102,6 +102,7 @@ struct PairParams {
     int n_multi, N_multi;
     const int32_t *penalty;    // [high_bayesian + 1] or null when high == 0
     const int32_t *g_log_n;    // [256]
+    int sw_on;                 // popt->is_sw && ii.avg >= 0 (bwa_paired_sw runs for this batch)
 };
 
 // pairing() for one pair.  arr = packed hits (pos<<32 | aln_index<<1 | end), sorted ascending.
@@ -190,6 +191,16 @@ FQB_HD void pair_resolve(fqb_read_t *p0, fqb_read_t *p1, const Hit *aln0, const 
         p1->n_mm = r1.n_mm; p1->n_gapo = r1.n_gapo; p1->n_gape = r1.n_gape; p1->strand = r1.a; p1->score = r1.score;
         p1->pos = (uint32_t)(o_pos1 >> 32);
     }
+}
+
+// Head of bwa_paired_sw's per-pair loop (libbwa/bwape.c:489-510): a read filtered by the k-mer test whose mate
+// was not filtered is "expanded" (un-filtered) so that it can be rescued; returns true when the pair qualifies for
+// mate rescue (unpaired and one end with mapQ >= SW_MIN_MAPQ = 17).
+FQB_HD bool sw_candidate(fqb_read_t *p0, fqb_read_t *p1, const PairParams &pp) {
+    if (!pp.sw_on) return false;
+    if (p0->filtered) { if (p1->filtered) return false; p0->filtered = 0; }
+    else if (p1->filtered) p1->filtered = 0;
+    return (p0->mapQ >= 17 || p1->mapQ >= 17) && (p0->extra_flag & kSamProper) == 0;
 }
 
 constexpr int kPairArrCap = 48;   // packed hit positions a thread sorts in place; larger pairs take the scratch path

@@ -15,6 +15,8 @@
 #include "fq_index.h"
 #include "fq_kernels.cuh"
 #include "fq_pair_kernels.cuh"
+#include "fq_dp_kernels.cuh"
+#include <cmath>
 #include "fq_relayout.h"
 #include "fq_synth.h"
 
@@ -87,7 +89,9 @@ struct fqb_handle {
     std::vector<uint32_t> h_hist;
     uint64_t rng_x0 = 0, rng_calls = 0;  // srand48(bns->seed) stream position (src/BwtMapper.cpp:1817)
     fqb_isize_t last_ii, cur_ii;
-    bool align_done = false, pair_done = false;
+    bool align_done = false, pair_done = false, dp_done = false;
+    uint32_t *d_sw_list = nullptr, *d_refine_list = nullptr;
+    DpPool dp_pool = {nullptr, nullptr, 0, 0, 0};
     uint32_t arena_fast = kArenaFast, arena_mid = kArenaMid;   // FQB_DEBUG_ARENA_FAST/_MID shrink them (tests of the overflow tiers)
 };
 
@@ -99,7 +103,8 @@ static void free_batch(fqb_handle *h) {
     cudaFree(h->wv.w); cudaFree(h->wv.sw);
     cudaFree(h->d_aln); cudaFree(h->d_naln); cudaFree(h->d_overflow); cudaFree(h->d_spill_slot);
     cudaFree(h->d_rows); cudaFree(h->pesc.packed); cudaFree(h->pesc.scanned); cudaFree(h->pesc.scan_tmp); cudaFree(h->pesc.cum_extra);
-    cudaFree(h->pesc.multi_list); cudaFree(h->d_big_list);
+    cudaFree(h->pesc.multi_list); cudaFree(h->d_big_list); cudaFree(h->d_sw_list); cudaFree(h->d_refine_list);
+    h->d_sw_list = h->d_refine_list = nullptr;
     h->d_rows = nullptr; h->pesc.packed = h->pesc.scanned = h->pesc.scan_tmp = h->pesc.cum_extra = nullptr; h->pesc.multi_list = nullptr; h->d_big_list = nullptr;
     memset(&h->bv, 0, sizeof(h->bv)); memset(&h->wv, 0, sizeof(h->wv));
     h->d_aln = nullptr; h->d_naln = nullptr; h->d_overflow = nullptr; h->d_spill_slot = nullptr;
@@ -135,6 +140,8 @@ static int ensure_batch(fqb_handle *h, int n_reads, int stride) {
     CU_CHECK(cudaMalloc(&h->pesc.cum_extra, (size_t)cap * 8));
     CU_CHECK(cudaMalloc(&h->pesc.multi_list, (size_t)cap * 4));
     CU_CHECK(cudaMalloc(&h->d_big_list, (size_t)cap * 2));
+    CU_CHECK(cudaMalloc(&h->d_sw_list, (size_t)cap * 2));
+    CU_CHECK(cudaMalloc(&h->d_refine_list, (size_t)cap * 4));
     h->cap_reads = cap; h->lpad = lpad; h->stride_cap = stride;
     return FQB_OK;
 }
@@ -255,7 +262,7 @@ void fqb_destroy(fqb_handle *h) {
     for (int s = 0; s < 2; ++s) { cudaFree(h->d_blocks[s]); cudaFree(h->d_sa[s]); }
     cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_ctrs); cudaFree(h->d_counters);
     cudaFree(h->d_arena); cudaFree(h->d_arena_mid); cudaFree(h->d_arena_big); cudaFree(h->d_aln_big);
-    cudaFree(h->pesc.totals); cudaFree(h->pesc.err_flag); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch);
+    cudaFree(h->pesc.totals); cudaFree(h->pesc.err_flag); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch); cudaFree(h->dp_pool.ints); cudaFree(h->dp_pool.bytes);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -294,7 +301,7 @@ int fqb_stage_load(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t
         b.lens_in[0] = lens1 ? h->d_lens_in[0] : nullptr; b.lens_in[1] = lens2 ? h->d_lens_in[1] : nullptr;
     }
     b.n_work = h->d_ctrs;
-    h->batch_ready = true; h->align_done = h->pair_done = false;
+    h->batch_ready = true; h->align_done = h->pair_done = h->dp_done = false;
     return FQB_OK;
 }
 
@@ -424,9 +431,10 @@ int fqb_stage_pair(fqb_handle *h) {
     pp.high = ii.high; pp.high_bayesian = ii.high_bayesian; pp.max_isize = h->popt.max_isize; pp.s_mm = h->gopt.s_mm;
     pp.max_occ = h->popt.max_occ; pp.n_multi = h->popt.n_multi; pp.N_multi = h->popt.N_multi;
     pp.penalty = h->d_penalty; pp.g_log_n = h->d_log_n;
+    pp.sw_on = 0;       // mate-rescue candidates are collected by fqb_stage_sw_refine
     if (h->popt.type != 1) { set_error("only BWA_PET_STD pairing is supported (SOLiD is dead code in the reference)"); return FQB_ERR_ARG; }
-    CU_CHECK(cudaMemsetAsync(h->d_ctrs + 12, 0, 4, st));
-    launch_pair(v, h->dbwt, pp, h->d_big_list, h->d_ctrs + 12, st);
+    CU_CHECK(cudaMemsetAsync(h->d_ctrs + 12, 0, 16, st));     // [12] n_big [13] n_sw [14] sw cursor [15] dp error
+    launch_pair(v, h->dbwt, pp, h->d_big_list, h->d_ctrs + 12, h->d_sw_list, h->d_ctrs + 13, st);
     h->n_launches += 1;
     uint32_t n_big = 0;
     CU_CHECK(cudaMemcpyAsync(&n_big, h->d_ctrs + 12, 4, cudaMemcpyDeviceToHost, st));
@@ -435,12 +443,52 @@ int fqb_stage_pair(fqb_handle *h) {
         const size_t per_pair = 8192;
         if (n_big > 4096) { set_error("too many repeat-heavy pairs in one batch"); return FQB_ERR_LIMIT; }
         if (!h->d_pair_scratch) CU_CHECK(cudaMalloc(&h->d_pair_scratch, (size_t)4096 * per_pair * 8));
-        launch_pair_big(v, h->dbwt, pp, h->d_big_list, h->d_ctrs + 12, (int)n_big, h->d_pair_scratch, per_pair, st);
+        launch_pair_big(v, h->dbwt, pp, h->d_big_list, h->d_ctrs + 12, (int)n_big, h->d_pair_scratch, per_pair, h->d_sw_list, h->d_ctrs + 13, st);
         h->n_launches += 1;
     }
     CU_CHECK(cudaGetLastError());
     h->last_ii = ii;
-    h->pair_done = true;
+    h->pair_done = true; h->dp_done = false;
+    return FQB_OK;
+}
+
+// a10 + a11 on the paired batch: bwa_paired_sw (libbwa/bwape.c:463) then bwa_refine_gapped (libbwa/bwase.c:339)
+int fqb_stage_sw_refine(fqb_handle *h) {
+    if (!h || !h->pair_done) { set_error("fqb_stage_sw_refine: run fqb_stage_pair first"); return FQB_ERR_STATE; }
+    if (h->dp_done) return FQB_OK;
+    CU_CHECK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    if (!h->dp_pool.ints) {
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
+        h->dp_pool.n_blocks = n_sm * 2;
+        h->dp_pool.ints_per_lane = 6 * 1025;                 // rows of a <= 1024-column window (mate-rescue windows are ~6 sigma + 2L)
+        h->dp_pool.bytes_per_lane = 96 * 1024;               // trace-back + ops
+        const size_t lanes = (size_t)h->dp_pool.n_blocks * kDpThreads;
+        CU_CHECK(cudaMalloc(&h->dp_pool.ints, lanes * h->dp_pool.ints_per_lane * 4));
+        CU_CHECK(cudaMalloc(&h->dp_pool.bytes, lanes * h->dp_pool.bytes_per_lane));
+    }
+    DpView v;
+    v.n_reads = h->n_reads; v.lpad = h->lpad; v.codes = h->bv.codes; v.pac = h->d_pac; v.l_pac = h->hidx.l_pac; v.rows = h->d_rows;
+    const fqb_isize_t &ii = h->cur_ii;
+    if (h->popt.is_sw && ii.avg >= 0.0) {
+        SwParams sp;
+        sp.avg = ii.avg; sp.std = ii.std; sp.l_pac = h->hidx.l_pac;
+        sp.s_old_add = -4.343 * std::log(ii.ap_prior / h->hidx.l_pac);                      // libbwa/bwape.c:577
+        sp.s_new_add = (int)(-4.343 * std::log(.5 * std::erfc(M_SQRT1_2 * 1.5) + .499));     // libbwa/bwape.c:578
+        CU_CHECK(cudaMemsetAsync(h->d_ctrs + 13, 0, 12, st));   // [13] n_sw [14] sw cursor [15] dp error
+        launch_sw(v, sp, h->dp_pool, h->d_sw_list, h->d_ctrs + 13, h->d_ctrs + 14, h->d_ctrs + 15, st);
+        h->n_launches += 2;
+    }
+    CU_CHECK(cudaMemsetAsync(h->d_ctrs + 8, 0, 8, st));       // [8] n_refine [9] refine cursor
+    launch_refine(v, h->dp_pool, h->d_refine_list, h->d_ctrs + 8, h->d_ctrs + 9, h->d_ctrs + 15, st);
+    h->n_launches += 3;
+    uint32_t err = 0;
+    CU_CHECK(cudaMemcpyAsync(&err, h->d_ctrs + 15, 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    CU_CHECK(cudaGetLastError());
+    if (err) { set_error("an alignment needed more DP scratch or CIGAR operations than provisioned"); return FQB_ERR_LIMIT; }
+    h->dp_done = true;
     return FQB_OK;
 }
 

@@ -134,7 +134,8 @@ __global__ void isize_hist_kernel(PeView v, uint32_t *hist, uint32_t *max_len) {
     if ((threadIdx.x & 31) == 0) atomicMax(max_len, ml);
 }
 
-__global__ void __launch_bounds__(128) pair_kernel(PeView v, DevBwt b0, DevBwt b1, PairParams pp, uint32_t *big_list, uint32_t *n_big) {
+__global__ void __launch_bounds__(128) pair_kernel(PeView v, DevBwt b0, DevBwt b1, PairParams pp, uint32_t *big_list, uint32_t *n_big,
+                                                    uint32_t *sw_list, uint32_t *n_sw) {
     __shared__ DevBwt s_bwt[2];
     if (threadIdx.x == 0) { s_bwt[0] = b0; s_bwt[1] = b1; }
     __syncthreads();
@@ -145,12 +146,13 @@ __global__ void __launch_bounds__(128) pair_kernel(PeView v, DevBwt b0, DevBwt b
     bool ok = pair_one(s_bwt, &r0, &r1, hits_of(v, 2 * p), n_hits_of(v, 2 * p), hits_of(v, 2 * p + 1), n_hits_of(v, 2 * p + 1),
                        pp, arr, kPairArrCap);
     if (!ok) { big_list[atomicAdd(n_big, 1u)] = p; return; }
+    if (sw_candidate(&r0, &r1, pp)) sw_list[atomicAdd(n_sw, 1u)] = p;
     v.rows[2 * p] = r0; v.rows[2 * p + 1] = r1;
 }
 
 // pairs with more hit positions than a thread sorts in registers/local memory: one thread each, scratch in global memory
 __global__ void pair_big_kernel(PeView v, DevBwt b0, DevBwt b1, PairParams pp, const uint32_t *big_list, const uint32_t *n_big,
-                                uint64_t *scratch, size_t scratch_per_pair) {
+                                uint64_t *scratch, size_t scratch_per_pair, uint32_t *sw_list, uint32_t *n_sw) {
     __shared__ DevBwt s_bwt[2];
     if (threadIdx.x == 0) { s_bwt[0] = b0; s_bwt[1] = b1; }
     __syncthreads();
@@ -160,6 +162,7 @@ __global__ void pair_big_kernel(PeView v, DevBwt b0, DevBwt b1, PairParams pp, c
     fqb_read_t r0 = v.rows[2 * p], r1 = v.rows[2 * p + 1];
     pair_one(s_bwt, &r0, &r1, hits_of(v, 2 * p), n_hits_of(v, 2 * p), hits_of(v, 2 * p + 1), n_hits_of(v, 2 * p + 1), pp,
              scratch + (size_t)j * scratch_per_pair, (int)scratch_per_pair);
+    if (sw_candidate(&r0, &r1, pp)) sw_list[atomicAdd(n_sw, 1u)] = p;
     v.rows[2 * p] = r0; v.rows[2 * p + 1] = r1;
 }
 
@@ -175,13 +178,14 @@ void launch_isize_hist(const PeView &v, uint32_t *hist, uint32_t *max_len, cudaS
     const int np = v.n_reads / 2;
     isize_hist_kernel<<<(np + 255) / 256, 256, 0, s>>>(v, hist, max_len);
 }
-void launch_pair(const PeView &v, const DevBwt bwt[2], const PairParams &pp, uint32_t *big_list, uint32_t *n_big, cudaStream_t s) {
+void launch_pair(const PeView &v, const DevBwt bwt[2], const PairParams &pp, uint32_t *big_list, uint32_t *n_big, uint32_t *sw_list,
+                 uint32_t *n_sw, cudaStream_t s) {
     const int np = v.n_reads / 2;
-    pair_kernel<<<(np + 127) / 128, 128, 0, s>>>(v, bwt[0], bwt[1], pp, big_list, n_big);
+    pair_kernel<<<(np + 127) / 128, 128, 0, s>>>(v, bwt[0], bwt[1], pp, big_list, n_big, sw_list, n_sw);
 }
 void launch_pair_big(const PeView &v, const DevBwt bwt[2], const PairParams &pp, const uint32_t *big_list, const uint32_t *n_big,
-                     int n_big_host, uint64_t *scratch, size_t scratch_per_pair, cudaStream_t s) {
-    pair_big_kernel<<<(n_big_host + 63) / 64, 64, 0, s>>>(v, bwt[0], bwt[1], pp, big_list, n_big, scratch, scratch_per_pair);
+                     int n_big_host, uint64_t *scratch, size_t scratch_per_pair, uint32_t *sw_list, uint32_t *n_sw, cudaStream_t s) {
+    pair_big_kernel<<<(n_big_host + 63) / 64, 64, 0, s>>>(v, bwt[0], bwt[1], pp, big_list, n_big, scratch, scratch_per_pair, sw_list, n_sw);
 }
 
 }  // namespace fqb

@@ -28,8 +28,9 @@ struct PeScratch {
 
 void launch_se(const PeView &v, const SeParams &sp, const RngState &rng, PeScratch &sc, cudaStream_t s);
 void launch_isize_hist(const PeView &v, uint32_t *hist, uint32_t *max_len, cudaStream_t s);
-void launch_pair(const PeView &v, const DevBwt bwt[2], const PairParams &pp, uint32_t *big_list, uint32_t *n_big, cudaStream_t s);
+void launch_pair(const PeView &v, const DevBwt bwt[2], const PairParams &pp, uint32_t *big_list, uint32_t *n_big, uint32_t *sw_list,
+                 uint32_t *n_sw, cudaStream_t s);
 void launch_pair_big(const PeView &v, const DevBwt bwt[2], const PairParams &pp, const uint32_t *big_list, const uint32_t *n_big,
-                     int n_big_host, uint64_t *scratch, size_t scratch_per_pair, cudaStream_t s);
+                     int n_big_host, uint64_t *scratch, size_t scratch_per_pair, uint32_t *sw_list, uint32_t *n_sw, cudaStream_t s);
 
 }  // namespace fqb

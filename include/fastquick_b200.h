@@ -128,6 +128,9 @@ int fqb_stage_align(fqb_handle *h);
 /* a6-a9: bwa_cal_pac_pos_pe (src/BwtMapper.cpp:721-907) = bwa_aln2seq (drand48) + bwt_sa + bwa_approx_mapQ,
  * infer_isize (libbwa/bwape.c:49), pairing (libbwa/bwape.c:119) and the multi-hit counts */
 int fqb_stage_pair(fqb_handle *h);
+/* a10 + a11: bwa_paired_sw (libbwa/bwape.c:463-625) and bwa_refine_gapped incl. NM and bwa_correct_trimmed
+ * (libbwa/bwase.c:183-418) */
+int fqb_stage_sw_refine(fqb_handle *h);
 int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
 /* new FASTQ pair: restart the drand48 stream and forget last_ii (src/BwtMapper.cpp:1811-1817) */
 int fqb_reset_stream(fqb_handle *h);

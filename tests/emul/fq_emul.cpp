@@ -10,6 +10,8 @@
 #include <vector>
 #include "../../fastquick_b200/csrc/fq_device_core.cuh"
 #include "../../fastquick_b200/csrc/fq_device_pair.cuh"
+#include "../../fastquick_b200/csrc/fq_device_dp.cuh"
+#include <cmath>
 #include "../../fastquick_b200/csrc/fq_hostmath.h"
 #include "../../fastquick_b200/csrc/fq_index.h"
 #include "../../fastquick_b200/csrc/fq_relayout.h"
@@ -162,12 +164,50 @@ int emul_pe_batch(void *h, const fqb_gap_opt_t *gopt, const fqb_pe_opt_t *popt, 
     PairParams pp;
     pp.high = ii.high; pp.high_bayesian = ii.high_bayesian; pp.max_isize = popt->max_isize; pp.s_mm = gopt->s_mm;
     pp.max_occ = popt->max_occ; pp.n_multi = popt->n_multi; pp.N_multi = popt->N_multi;
-    pp.penalty = pen.data(); pp.g_log_n = g_log_n;
+    pp.penalty = pen.data(); pp.g_log_n = g_log_n; pp.sw_on = 0;
     std::vector<uint64_t> arr(8192);
     for (int p = 0; p < n_pairs; ++p)
         if (!pair_one(e->bwt, &rows[2 * p], &rows[2 * p + 1], hits(2 * p), nh(2 * p), hits(2 * p + 1), nh(2 * p + 1), pp, arr.data(), kPairArrCap))
             if (!pair_one(e->bwt, &rows[2 * p], &rows[2 * p + 1], hits(2 * p), nh(2 * p), hits(2 * p + 1), nh(2 * p + 1), pp, arr.data(), 8192)) return -2;
     *ii_out = ii; *last_ii = ii;
+    return 0;
+}
+
+
+// bwa_paired_sw + bwa_refine_gapped with the device functions (stride-1 scratch)
+int emul_sw_refine(void *h, const fqb_pe_opt_t *popt, int n_pairs, int stride, const uint8_t *codes, const fqb_isize_t *ii,
+                   fqb_read_t *rows, fqb_read_t *rows_after_sw) {
+    Emul *e = (Emul *)h;
+    const int64_t l_pac = e->idx.l_pac;
+    const uint8_t *pac = e->idx.pac.data();
+    std::vector<int32_t> ints(6 * 1100);
+    std::vector<uint8_t> bytes(400000);
+    DpScratch sc; sc.ints = ints.data(); sc.n_ints = (int)ints.size(); sc.bytes = bytes.data(); sc.n_bytes = (int)bytes.size(); sc.stride = 1;
+    if (popt->is_sw && ii->avg >= 0.0) {
+        SwParams sp;
+        sp.avg = ii->avg; sp.std = ii->std; sp.l_pac = l_pac;
+        sp.s_old_add = -4.343 * std::log(ii->ap_prior / l_pac);
+        sp.s_new_add = (int)(-4.343 * std::log(.5 * std::erfc(M_SQRT1_2 * 1.5) + .499));
+        for (int p = 0; p < n_pairs; ++p) {
+            fqb_read_t *p0 = rows + 2 * p, *p1 = p0 + 1;
+            if (p0->filtered) { if (p1->filtered) continue; p0->filtered = 0; }
+            else if (p1->filtered) p1->filtered = 0;
+            if ((p0->mapQ >= 17 || p1->mapQ >= 17) && (p0->extra_flag & kSamProper) == 0)
+                if (!paired_sw_one(pac, p0, p1, codes + (size_t)(2 * p) * stride, codes + (size_t)(2 * p + 1) * stride, sp, sc)) return -1;
+        }
+    }
+    if (rows_after_sw) memcpy(rows_after_sw, rows, sizeof(fqb_read_t) * 2 * (size_t)n_pairs);
+    for (int r = 0; r < 2 * n_pairs; ++r) {
+        fqb_read_t &s = rows[r];
+        ReadSeq Q; Q.fwd = codes + (size_t)r * stride; Q.len = s.len; Q.strand = s.strand;
+        if (!s.filtered && !(s.type == kTypeNoMatch || s.type == kTypeMateSW || s.n_gapo == 0)) {
+            int nc = refine_gapped(l_pac, pac, Q, &s.pos, (s.strand ? 1 : -1) * (s.n_gapo + s.n_gape), s.cigar, FQB_MAX_CIGAR, sc);
+            if (nc < 0) return -2;
+            s.n_cigar = (uint8_t)nc; s.has_cigar = 1;
+        }
+        if (s.type != kTypeNoMatch) s.nm = (uint16_t)cal_nm(s, Q, l_pac, pac);
+        correct_trimmed(s);
+    }
     return 0;
 }
 

@@ -63,3 +63,53 @@ def test_pair_stage_mostly_filtered_batch_falls_back_to_last_isize(small_index, 
     b = small_index.reads(3000, read_len=100, seed=54, f_on=0.004)
     arrs = [np.concatenate([x, y]) for x, y in zip(a, b)]
     list(_run(small_index, arrs, "pfall", 3000))
+
+
+# ---- rows a10 + a11: bwa_paired_sw and bwa_refine_gapped (snapshots 2 and 3 of the reference) ----
+FIELDS_FIN = FIELDS + ["n_cigar", "has_cigar", "nm"]
+
+
+def _run_full(index, arrs, tag, batch, trim_qual=15):
+    fq = index.write_fastq(tag, arrs)
+    ref = fx.RefRun(index.prefix, fq[0], fq[1], trim_qual=trim_qual, batch_cap=batch)
+    lib = fx.host_lib()
+    g = _abi.GapOpt()
+    lib.fqb_gap_opt_default(C.byref(g))
+    g.trim_qual = trim_qual
+    h = C.c_void_p()
+    assert lib.fqb_create(index.prefix.encode(), C.byref(g), None, 0, C.byref(h)) == 0, lib.fqb_last_error()
+    stats = {"matesw": 0, "cigars": 0}
+    try:
+        n_tot, L = arrs[0].shape
+        for b in range(n_tot // batch):
+            assert ref.next_batch() == batch
+            sub = [np.ascontiguousarray(a[b * batch:(b + 1) * batch]) for a in arrs]
+            assert lib.fqb_stage_load(h, batch, L, _abi.u8p(sub[0]), _abi.u8p(sub[1]), None, _abi.u8p(sub[2]), _abi.u8p(sub[3]), None, 0) == 0
+            assert lib.fqb_stage_align(h) == 0, lib.fqb_last_error()
+            assert lib.fqb_stage_pair(h) == 0, lib.fqb_last_error()
+            assert lib.fqb_stage_sw_refine(h) == 0, lib.fqb_last_error()
+            rows = [np.zeros(batch, _abi.READ_DTYPE) for _ in range(2)]
+            assert lib.fqb_stage_fetch_rows(h, rows[0].ctypes.data_as(C.c_void_p), rows[1].ctypes.data_as(C.c_void_p), None) == 0
+            for e in (0, 1):
+                rr = ref.rows(3, e)
+                for f in FIELDS_FIN:
+                    np.testing.assert_array_equal(rows[e][f], rr[f], err_msg="batch %d end %d field %s" % (b, e, f))
+                for r in np.where(rr["has_cigar"] != 0)[0]:
+                    k = rr["n_cigar"][r]
+                    assert list(rows[e]["cigar"][r][:k]) == list(rr["cigar"][r][:k]), (b, e, r)
+                stats["matesw"] += int((rr["type"] == 3).sum())
+                stats["cigars"] += int((rr["has_cigar"] != 0).sum())
+    finally:
+        lib.fqb_destroy(h)
+    return stats
+
+
+def test_sw_and_refine_2x100(small_index, ref_required):
+    st = _run_full(small_index, small_index.reads(6000, read_len=100, seed=61), "f100", 3000)
+    assert st["matesw"] > 100 and st["cigars"] > 1000
+
+
+def test_sw_and_refine_indel_rich_150(small_index, ref_required):
+    arrs = small_index.reads(3000, read_len=150, seed=62, sub_rate=0.02, ins_rate=0.004, del_rate=0.004, max_indel_len=3)
+    st = _run_full(small_index, arrs, "f150", 3000)
+    assert st["matesw"] > 200
