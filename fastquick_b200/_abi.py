@@ -8,7 +8,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "libfastquick_b200.so")
 
-FQB_MAX_CIGAR = 16
+FQB_MAX_CIGAR = 24
 FQB_MAX_MULTI = 11
 FQB_BATCH_PAIRS = 0x40000
 
@@ -69,7 +69,7 @@ READ_DTYPE = np.dtype([
     ("nm", "<u2"), ("n_aln", "<u2"),
     ("cigar", "<u2", (FQB_MAX_CIGAR,)),
 ])
-assert READ_DTYPE.itemsize == 80, READ_DTYPE.itemsize
+assert READ_DTYPE.itemsize == 96, READ_DTYPE.itemsize
 
 # every extern "C" symbol include/fastquick_b200.h declares
 EXPORTED_SYMBOLS = [

@@ -68,7 +68,7 @@ typedef struct {
     uint32_t pad_;
 } fqb_isize_t;
 
-#define FQB_MAX_CIGAR 16
+#define FQB_MAX_CIGAR 24
 #define FQB_MAX_MULTI 11           /* n_multi/N_multi + 1, src/BwtMapper.cpp:857-871 */
 
 /* per-read result row: the bwa_seq_t fields (libbwa/bwtaln.h:57-86) that

@@ -78,7 +78,7 @@ typedef struct {
 typedef struct {
     uint32_t pos, sa, c1, c2; int32_t score, len, full_len, clip_len;
     uint8_t type, strand, filtered, extra_flag, n_mm, n_gapo, n_gape, mapQ, seQ, n_cigar, n_multi, has_cigar;
-    uint16_t nm, n_aln; uint16_t cigar[16];
+    uint16_t nm, n_aln; uint16_t cigar[24];
 } orc_row_t;
 /* infer_isize (libbwa/bwape.c:49-117); returns 0 ok / -1 failed */
 int orc_infer_isize(int n_pairs, const orc_row_t *rows /*2n, r=2*pair+end*/, orc_isize_t *ii, double ap_prior, int64_t L);

@@ -424,7 +424,7 @@ void orc_paired_sw(int64_t l_pac, const uint8_t *pac, int n_pairs, orc_row_t *ro
                 if (p[k]->mapQ > mq_adjust[k]) p[k]->mapQ = (uint8_t)mq_adjust[k];
                 if (p[k]->seQ > mq_adjust[k]) p[k]->seQ = (uint8_t)mq_adjust[k];
                 p[k]->n_cigar = (uint8_t)n_cigar[k]; p[k]->has_cigar = 1;
-                for (c = 0; c < n_cigar[k] && c < 16; ++c) p[k]->cigar[c] = cigar[k][c];
+                for (c = 0; c < n_cigar[k] && c < 24; ++c) p[k]->cigar[c] = cigar[k][c];
                 p[k]->type = TYPE_MATESW;
                 p[k]->pos = (uint32_t)beg[k];
                 p[k]->seQ = p[1 - k]->seQ;

@@ -33,7 +33,7 @@ def have_ref():
 
 def build_oracle():
     srcs = [os.path.join(REPO, "oracle", f) for f in ("fq_oracle.c", "fq_oracle_pe.c", "fq_oracle_dp.c")]
-    deps = srcs + [os.path.join(REPO, "oracle", "fq_oracle.h")]
+    deps = srcs + [os.path.join(REPO, "oracle", "fq_oracle.h"), os.path.join(REPO, "include", "fastquick_b200.h")]
     if not os.path.exists(ORC_LIB) or os.path.getmtime(ORC_LIB) < max(os.path.getmtime(s) for s in deps):
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared"] + srcs + ["-o", ORC_LIB, "-lm"])
     return C.CDLL(ORC_LIB)
@@ -42,7 +42,9 @@ def build_oracle():
 def build_emul():
     srcs = [os.path.join(HERE, "emul", "fq_emul.cpp")] + [
         os.path.join(REPO, "fastquick_b200", "csrc", f) for f in ("fq_index.cpp", "fq_relayout.cpp", "fq_hostmath.cpp")]
-    deps = srcs + [os.path.join(REPO, "fastquick_b200", "csrc", "fq_device_core.cuh")]
+    import glob
+    deps = srcs + glob.glob(os.path.join(REPO, "fastquick_b200", "csrc", "*.cuh")) + glob.glob(os.path.join(REPO, "fastquick_b200", "csrc", "*.h")) + \
+        [os.path.join(REPO, "include", "fastquick_b200.h")]
     if not os.path.exists(EMUL_LIB) or os.path.getmtime(EMUL_LIB) < max(os.path.getmtime(s) for s in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", EMUL_LIB] + srcs + ["-lpthread"])
     return C.CDLL(EMUL_LIB)

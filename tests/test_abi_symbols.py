@@ -27,7 +27,7 @@ def test_struct_sizes_match_header():
     # sizes the C side asserts on as well (fq_engine.cu static_asserts)
     assert C.sizeof(_abi.GapOpt) == 88
     assert C.sizeof(_abi.PeOpt) == 40
-    assert _abi.READ_DTYPE.itemsize == 80
+    assert _abi.READ_DTYPE.itemsize == 96
     assert _abi.ALN_DTYPE.itemsize == 16
 
 
