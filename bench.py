@@ -31,7 +31,7 @@ READ_LEN = 100
 WORKLOAD = "synthetic 10M 2x100bp pairs (f_on=1, 1% subst, 0.1%+0.1% indel) vs synthetic 10,197-marker flank index"
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "FASTQuick_ref")
 REF_SAMPLE_PAIRS = 8192          # pairs per step of the reference arm / cpu_baseline sample unit
-STAGES = "prep+kmer-filter+cal_width+match_gap (SURVEY 8 rows a1-a5)"
+STAGES = "prep + k-mer filter + cal_width + match_gap + aln2seq/bwt_sa/mapQ + infer_isize + pairing + mate-rescue SW + gapped refinement (SURVEY 8 rows a1-a11)"
 
 
 def peaks():
@@ -202,15 +202,18 @@ def main_gpu(args):
         d = dev[s]
         assert lib.fqb_stage_load(h, n_pairs, READ_LEN, ptr(d[0]), ptr(d[1]), None, ptr(d[2]), ptr(d[3]), None, 1) == 0, lib.fqb_last_error()
         assert lib.fqb_stage_align(h) == 0, lib.fqb_last_error()
+        assert lib.fqb_stage_pair(h) == 0, lib.fqb_last_error()
+        assert lib.fqb_stage_sw_refine(h) == 0, lib.fqb_last_error()
 
-    n_aln_host = np.empty(2 * n_pairs, np.int32)
-    aln_host = np.empty((2 * n_pairs, 2), _abi.ALN_DTYPE)
+    rows_host = [torch.empty((n_pairs, _abi.READ_DTYPE.itemsize), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    ii_host = _abi.ISize()
 
     def step_e2e(s):
+        # the public per-batch call: pinned host FASTQ arrays in, per-read result rows out
         b = host[s]
-        assert lib.fqb_stage_load(h, n_pairs, READ_LEN, ptr(b[0]), ptr(b[1]), None, ptr(b[2]), ptr(b[3]), None, 0) == 0, lib.fqb_last_error()
-        assert lib.fqb_stage_align(h) == 0, lib.fqb_last_error()
-        assert lib.fqb_stage_fetch_aln(h, 2, aln_host.ctypes.data_as(C.c_void_p), _abi.i32p(n_aln_host)) == 0, lib.fqb_last_error()
+        rc = lib.fqb_align_pairs(h, n_pairs, READ_LEN, ptr(b[0]), ptr(b[1]), None, ptr(b[2]), ptr(b[3]), None,
+                                 C.c_void_p(rows_host[0].data_ptr()), C.c_void_p(rows_host[1].data_ptr()), C.byref(ii_host))
+        assert rc == 0, lib.fqb_last_error()
 
     def barrier():
         if world > 1:
@@ -245,6 +248,7 @@ def main_gpu(args):
         time.sleep(0.3)
     ms, ctr, launches, t0, t1 = timed(step_device)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
+    lib.fqb_reset_stream(h)
     ms_e2e, _, _, _, _ = timed(step_e2e)
 
     total_pairs = args.steps * n_pairs * world
@@ -272,7 +276,7 @@ def main_gpu(args):
                    "l2_policy": "every step reads a different 105 MB batch; per-step working set (inputs+widths+stack arena) exceeds the 126 MB L2",
                    "index": "10,197 markers, l_pac 6,608,697, replicated per GPU"},
         "e2e": {"value": e2e_value, "unit": "read-pairs/s", "h2d_bytes_per_step": 4 * n_pairs * READ_LEN,
-                "d2h_bytes_per_step": int(n_aln_host.nbytes + aln_host.nbytes)},
+                "d2h_bytes_per_step": int(2 * n_pairs * _abi.READ_DTYPE.itemsize)},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

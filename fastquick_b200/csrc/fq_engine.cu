@@ -572,13 +572,22 @@ int fqb_stage_counters(fqb_handle *h, uint64_t *out4) {
     return FQB_OK;
 }
 
+int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
+int fqb_stage_pair(fqb_handle *h);
+int fqb_stage_sw_refine(fqb_handle *h);
+
+// The whole per-batch body of BwtMapper::PairEndMapper up to (not including) the statistics loop.
 int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
                     const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2,
                     fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out) {
-    (void)h; (void)n_pairs; (void)stride; (void)bases1; (void)quals1; (void)lens1; (void)bases2; (void)quals2; (void)lens2;
-    (void)rows1; (void)rows2; (void)ii_out;
-    set_error("fqb_align_pairs: pair resolution stages are not built yet (use the fqb_stage_* entry points)");
-    return FQB_ERR_STATE;
+    int rc = fqb_stage_load(h, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, 0);
+    if (rc) return rc;
+    if ((rc = fqb_stage_align(h))) return rc;
+    if ((rc = fqb_stage_pair(h))) return rc;
+    if ((rc = fqb_stage_sw_refine(h))) return rc;
+    if (rows1 && rows2) return fqb_stage_fetch_rows(h, rows1, rows2, ii_out);
+    if (ii_out) *ii_out = h->cur_ii;
+    return FQB_OK;
 }
 
 uint64_t fqb_launch_count(const fqb_handle *h) { return h ? h->n_launches : 0; }
