@@ -16,6 +16,10 @@
 #include "fq_kernels.cuh"
 #include "fq_pair_kernels.cuh"
 #include "fq_dp_kernels.cuh"
+#include "fq_stats_kernels.cuh"
+#include "fq_stats_host.h"
+#include <algorithm>
+#include <fstream>
 #include <cmath>
 #include "fq_relayout.h"
 #include "fq_synth.h"
@@ -92,6 +96,22 @@ struct fqb_handle {
     bool align_done = false, pair_done = false, dp_done = false;
     uint32_t *d_sw_list = nullptr, *d_refine_list = nullptr;
     DpPool dp_pool = {nullptr, nullptr, 0, 0, 0};
+    // statistics rows (a12-a14)
+    bool stats_open = false, stats_done = false;
+    StatsTables stabs;
+    ContigDev *d_ctg = nullptr;
+    uint32_t *d_site = nullptr; int32_t *d_marker = nullptr;
+    uint32_t *d_depth = nullptr;                 // depth | q20 | q30, n_sites each
+    unsigned long long *d_emp = nullptr;         // [4][256] + isize_dist[4096] + scalars[8]
+    uint32_t *d_contig_ctr = nullptr;            // [n_ctg][4] + first[n_ctg]
+    unsigned long long *d_dup_keys = nullptr; uint32_t dup_cap = 0;
+    PileupTuple *d_tuples = nullptr; uint32_t *d_ntuples = nullptr; uint32_t tuple_cap = 0;
+    PairStat *d_pstat = nullptr;
+    uint64_t pairs_seen = 0;                     // global pair index of the next batch
+    std::vector<PileupColumn> pileup;
+    std::vector<FileCounters> files;
+    std::ofstream isize_table;
+    std::vector<fqb_read_t> h_rows; std::vector<PairStat> h_pstat;
     uint32_t arena_fast = kArenaFast, arena_mid = kArenaMid;   // FQB_DEBUG_ARENA_FAST/_MID shrink them (tests of the overflow tiers)
 };
 
@@ -301,7 +321,7 @@ int fqb_stage_load(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t
         b.lens_in[0] = lens1 ? h->d_lens_in[0] : nullptr; b.lens_in[1] = lens2 ? h->d_lens_in[1] : nullptr;
     }
     b.n_work = h->d_ctrs;
-    h->batch_ready = true; h->align_done = h->pair_done = h->dp_done = false;
+    h->batch_ready = true; h->align_done = h->pair_done = h->dp_done = h->stats_done = false;
     return FQB_OK;
 }
 
@@ -489,6 +509,173 @@ int fqb_stage_sw_refine(fqb_handle *h) {
     CU_CHECK(cudaGetLastError());
     if (err) { set_error("an alignment needed more DP scratch or CIGAR operations than provisioned"); return FQB_ERR_LIMIT; }
     h->dp_done = true;
+    return FQB_OK;
+}
+
+// ---- statistics rows -------------------------------------------------------------------------
+static int drain_tuples(fqb_handle *h) {
+    uint32_t n = 0;
+    CU_CHECK(cudaMemcpy(&n, h->d_ntuples, 4, cudaMemcpyDeviceToHost));
+    if (n > h->tuple_cap) { set_error("pile-up tuple buffer overflow"); return FQB_ERR_LIMIT; }
+    if (!n) return FQB_OK;
+    std::vector<PileupTuple> t(n);
+    CU_CHECK(cudaMemcpy(t.data(), h->d_tuples, (size_t)n * sizeof(PileupTuple), cudaMemcpyDeviceToHost));
+    CU_CHECK(cudaMemset(h->d_ntuples, 0, 4));
+    std::sort(t.begin(), t.end(), [](const PileupTuple &a, const PileupTuple &b) {
+        if (a.key_hi != b.key_hi) return a.key_hi < b.key_hi;
+        return a.key_lo < b.key_lo;
+    });
+    for (const PileupTuple &x : t) {       // UpdateInfoVecAtMarker's appends, in arrival order
+        PileupColumn &c = h->pileup[x.marker];
+        c.seq.push_back("ACGTN"[x.base > 4 ? 4 : x.base]);
+        c.qual.push_back((char)x.qual);
+        c.cycle.push_back(x.cycle);
+        c.maq.push_back(x.mapq);
+        c.strand.push_back(x.strand != 0);
+    }
+    return FQB_OK;
+}
+
+// RestoreVcfSites + SetGenomeSize (src/BwtMapper.cpp:225-226): side tables and accumulators
+int fqb_stats_open(fqb_handle *h, const char *index_prefix) {
+    if (!h || !index_prefix) { set_error("null argument"); return FQB_ERR_ARG; }
+    CU_CHECK(cudaSetDevice(h->device));
+    std::string err;
+    if (!build_stats_tables(h->hidx, index_prefix, h->gopt, h->stabs, err)) { set_error(err); return FQB_ERR_IO; }
+    const StatsTables &T = h->stabs;
+    const size_t nc = T.contigs.size(), ns = T.n_sites ? T.n_sites : 1;
+    CU_CHECK(cudaMalloc(&h->d_ctg, nc * sizeof(ContigDev)));
+    CU_CHECK(cudaMemcpy(h->d_ctg, T.contigs.data(), nc * sizeof(ContigDev), cudaMemcpyHostToDevice));
+    CU_CHECK(cudaMalloc(&h->d_site, T.site.size() * 4));
+    CU_CHECK(cudaMemcpy(h->d_site, T.site.data(), T.site.size() * 4, cudaMemcpyHostToDevice));
+    CU_CHECK(cudaMalloc(&h->d_marker, T.marker_at.size() * 4));
+    CU_CHECK(cudaMemcpy(h->d_marker, T.marker_at.data(), T.marker_at.size() * 4, cudaMemcpyHostToDevice));
+    CU_CHECK(cudaMalloc(&h->d_depth, ns * 3 * 4));
+    CU_CHECK(cudaMemset(h->d_depth, 0, ns * 3 * 4));
+    CU_CHECK(cudaMalloc(&h->d_emp, (4 * 256 + 4096 + 8 + 1) * 8));
+    CU_CHECK(cudaMemset(h->d_emp, 0, (4 * 256 + 4096 + 8 + 1) * 8));
+    CU_CHECK(cudaMalloc(&h->d_contig_ctr, nc * 5 * 4));
+    CU_CHECK(cudaMemset(h->d_contig_ctr, 0, nc * 4 * 4));
+    CU_CHECK(cudaMemset(h->d_contig_ctr + nc * 4, 0xff, nc * 4));
+    h->dup_cap = 1u << 26;                       // 64M-slot open-addressing set of (start, end) keys (512 MB)
+    CU_CHECK(cudaMalloc(&h->d_dup_keys, (size_t)h->dup_cap * 8));
+    CU_CHECK(cudaMemset(h->d_dup_keys, 0, (size_t)h->dup_cap * 8));
+    h->tuple_cap = 1u << 25;
+    CU_CHECK(cudaMalloc(&h->d_tuples, (size_t)h->tuple_cap * sizeof(PileupTuple)));
+    CU_CHECK(cudaMalloc(&h->d_ntuples, 4));
+    CU_CHECK(cudaMemset(h->d_ntuples, 0, 4));
+    h->pileup.assign(T.markers.size(), PileupColumn());
+    h->files.clear();
+    h->pairs_seen = 0;
+    h->stats_open = true;
+    return FQB_OK;
+}
+
+// a new FASTQ pair: FileStatCollector FSC(fq1, fq2) (src/BwtMapper.cpp:249-254); the first call (re)creates <out_prefix>.InsertSizeTable
+int fqb_stats_begin_file(fqb_handle *h, const char *out_prefix, const char *fq1, const char *fq2) {
+    if (!h || !h->stats_open) { set_error("fqb_stats_begin_file: call fqb_stats_open first"); return FQB_ERR_STATE; }
+    if (out_prefix && !h->isize_table.is_open()) {
+        h->isize_table.open(std::string(out_prefix) + ".InsertSizeTable");
+        if (!h->isize_table) { set_error("cannot write the InsertSizeTable"); return FQB_ERR_IO; }
+    }
+    FileCounters f;
+    f.FileName1 = fq1 ? fq1 : ""; f.FileName2 = fq2 ? fq2 : "";
+    h->files.push_back(f);
+    return fqb_reset_stream(h);
+}
+
+// a12 + a13 on the finished batch: AddAlignment's decision tree per pair, then the per-base accumulation
+int fqb_stage_stats(fqb_handle *h) {
+    if (!h || !h->stats_open || !h->dp_done) { set_error("fqb_stage_stats: needs fqb_stats_open and a batch through fqb_stage_sw_refine"); return FQB_ERR_STATE; }
+    if (h->stats_done) return FQB_OK;
+    CU_CHECK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    if (h->files.empty()) h->files.push_back(FileCounters());
+    const size_t np = (size_t)h->n_reads / 2, nc = h->stabs.contigs.size(), ns = h->stabs.n_sites ? h->stabs.n_sites : 1;
+    if (!h->d_pstat) CU_CHECK(cudaMalloc(&h->d_pstat, (size_t)(h->cap_reads / 2) * sizeof(PairStat)));
+    uint32_t nt = 0;
+    CU_CHECK(cudaMemcpyAsync(&nt, h->d_ntuples, 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    if ((uint64_t)nt + (uint64_t)h->n_reads * 2 > h->tuple_cap) { int rc = drain_tuples(h); if (rc) return rc; }
+    StatsView v;
+    v.n_reads = h->n_reads; v.lpad = h->lpad; v.codes = h->bv.codes; v.qual = h->bv.qual; v.rows = h->d_rows; v.pstat = h->d_pstat;
+    v.ctg = h->d_ctg; v.n_ctg = (int)nc; v.pair_base = (uint32_t)h->pairs_seen; v.cal_dup = 1; v.pac = h->d_pac;
+    StatAccum A;
+    A.contig_ctr = h->d_contig_ctr; A.contig_first = h->d_contig_ctr + nc * 4;
+    A.isize_dist = h->d_emp + 4 * 256; A.scalars = h->d_emp + 4 * 256 + 4096;
+    A.dup_keys = h->d_dup_keys; A.dup_cap = h->dup_cap; A.dup_count = h->d_emp + 4 * 256 + 4096 + 8;
+    BaseTables B;
+    B.site = h->d_site; B.marker = h->d_marker; B.depth = h->d_depth; B.q20 = h->d_depth + ns; B.q30 = h->d_depth + 2 * ns;
+    B.emp = h->d_emp; B.tuples = h->d_tuples; B.n_tuples = h->d_ntuples; B.tuple_cap = h->tuple_cap;
+    launch_classify(v, A, st);
+    launch_bases(v, B, st);
+    h->n_launches += 2;
+    CU_CHECK(cudaGetLastError());
+    h->files.back().NumRead += 2 * (long long)np;
+    h->pairs_seen += np;
+    h->stats_done = true;
+    return FQB_OK;
+}
+
+// text emission for the last batch: one InsertSizeTable line per retained pair (ProcessPairStatus's fout lines).
+// names: n_pairs rows of name_stride bytes (NUL-padded), or null for the synthetic r%011lld names.
+int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride) {
+    if (!h || !h->stats_done) { set_error("fqb_stats_emit: run fqb_stage_stats first"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    const size_t np = (size_t)h->n_reads / 2;
+    h->h_rows.resize(2 * np); h->h_pstat.resize(np);
+    CU_CHECK(cudaMemcpyAsync(h->h_rows.data(), h->d_rows, 2 * np * sizeof(fqb_read_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(cudaMemcpyAsync(h->h_pstat.data(), h->d_pstat, np * sizeof(PairStat), cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(cudaStreamSynchronize(h->stream));
+    if (!h->isize_table.is_open()) return FQB_OK;
+    std::string line, nm;
+    char buf[64];
+    const uint64_t first = h->pairs_seen - np;
+    for (size_t i = 0; i < np; ++i) {
+        const PairStat &ps = h->h_pstat[i];
+        if (ps.line_kind == 0) continue;
+        const char *name;
+        if (names) { nm.assign(names + i * (size_t)name_stride, strnlen(names + i * (size_t)name_stride, (size_t)name_stride)); name = nm.c_str(); }
+        else { snprintf(buf, sizeof buf, "r%011llu", (unsigned long long)(first + i)); name = buf; }
+        format_isize_line(h->stabs, ps, h->h_rows[2 * i], h->h_rows[2 * i + 1], name, line);
+        h->isize_table << line;
+    }
+    return FQB_OK;
+}
+
+// ProcessCore (src/StatCollector.cpp:2012-2028): gathers the accumulators and writes every summary file
+int fqb_stats_finish(fqb_handle *h, const char *out_prefix) {
+    if (!h || !h->stats_open || !out_prefix) { set_error("fqb_stats_finish: call fqb_stats_open first"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    CU_CHECK(cudaStreamSynchronize(h->stream));
+    int rc = drain_tuples(h);
+    if (rc) return rc;
+    if (h->isize_table.is_open()) h->isize_table.close();
+    const StatsTables &T = h->stabs;
+    const size_t nc = T.contigs.size(), ns = T.n_sites ? T.n_sites : 1;
+    StatsTotals S;
+    std::vector<uint32_t> d(ns * 3);
+    CU_CHECK(cudaMemcpy(d.data(), h->d_depth, ns * 3 * 4, cudaMemcpyDeviceToHost));
+    S.depth.assign(d.begin(), d.begin() + ns); S.q20.assign(d.begin() + ns, d.begin() + 2 * ns); S.q30.assign(d.begin() + 2 * ns, d.end());
+    std::vector<unsigned long long> e(4 * 256 + 4096 + 8 + 1);
+    CU_CHECK(cudaMemcpy(e.data(), h->d_emp, e.size() * 8, cudaMemcpyDeviceToHost));
+    S.emp.assign(e.begin(), e.begin() + 1024);
+    S.isize_dist.assign(e.begin() + 1024, e.begin() + 1024 + 4096);
+    const unsigned long long *sc = e.data() + 1024 + 4096;
+    if (sc[2]) { set_error("an insert size fell outside InsertSizeDist[4096] (the reference would write out of bounds)"); return FQB_ERR_LIMIT; }
+    S.num_pcr_dup = sc[0]; S.num_pair_reads = sc[1];
+    std::vector<uint32_t> cc(nc * 5);
+    CU_CHECK(cudaMemcpy(cc.data(), h->d_contig_ctr, nc * 5 * 4, cudaMemcpyDeviceToHost));
+    S.contig_ctr.assign(cc.begin(), cc.begin() + nc * 4); S.contig_first.assign(cc.begin() + nc * 4, cc.end());
+    S.pileup = h->pileup;
+    S.files = h->files;
+    // per-file counters: with one FASTQ pair per run the device totals are that file's counters
+    if (S.files.size() == 1) {
+        FileCounters &F = S.files[0];
+        F.TotalFiltered = (long long)sc[3]; F.BwaUnmapped = (long long)sc[4]; F.TotalMAPQ = (long long)sc[5]; F.TotalRetained = (long long)sc[6]; F.NumBase = (long long)sc[7];
+    }
+    std::string err;
+    if (!write_summary_files(T, S, h->gopt, out_prefix, err)) { set_error(err); return FQB_ERR_IO; }
     return FQB_OK;
 }
 

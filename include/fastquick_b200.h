@@ -131,6 +131,20 @@ int fqb_stage_pair(fqb_handle *h);
 /* a10 + a11: bwa_paired_sw (libbwa/bwape.c:463-625) and bwa_refine_gapped incl. NM and bwa_correct_trimmed
  * (libbwa/bwase.c:183-418) */
 int fqb_stage_sw_refine(fqb_handle *h);
+/* ---- a12-a14: StatCollector ----------------------------------------------------------------
+ * fqb_stats_open      = StatCollector::RestoreVcfSites + SetGenomeSize (src/StatCollector.cpp:1742, src/BwtMapper.cpp:225-226)
+ * fqb_stats_begin_file = FileStatCollector FSC(fq1, fq2) per FASTQ pair (src/BwtMapper.cpp:249); restarts drand48 / last_ii
+ * fqb_stage_stats     = StatCollector::AddAlignment for every pair of the batch (src/StatCollector.cpp:950-1101): pair
+ *                       classification, insert-size bookkeeping, PCR-duplicate set, X/Y counters, per-base pile-up / depth /
+ *                       quality / cycle accumulation (424-621) -- all on the device
+ * fqb_stats_emit      = the InsertSizeTable lines of the batch (text; host)
+ * fqb_stats_finish    = StatCollector::ProcessCore (2012-2028): writes <out_prefix>.{DepthDist,GCDist,EmpRepDist,EmpCycleDist,
+ *                       AdjustedInsertSizeDist,RawInsertSizeDist,SexChromInfo,Pileup,FASTQ.csv,Sequence.csv,Summary,vcf} */
+int fqb_stats_open(fqb_handle *h, const char *index_prefix);
+int fqb_stats_begin_file(fqb_handle *h, const char *out_prefix, const char *fastq1, const char *fastq2);
+int fqb_stage_stats(fqb_handle *h);
+int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride);
+int fqb_stats_finish(fqb_handle *h, const char *out_prefix);
 int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
 /* new FASTQ pair: restart the drand48 stream and forget last_ii (src/BwtMapper.cpp:1811-1817) */
 int fqb_reset_stream(fqb_handle *h);
