@@ -194,7 +194,7 @@ void format_isize_line(const StatsTables &T, const PairStat &ps, const fqb_read_
 // ---- InsertSizeEstimator (src/InsertSizeEstimator.cpp:43-173) -------------------------------
 static std::vector<double> adjusted_isize(const std::string &table, const std::string &orientation) {
     const int LIM = 4096;
-    std::vector<double> mis(LIM, 0.), obs(LIM, 0.);
+    std::vector<double> mis(LIM, 1e-6), obs(LIM, 1e-6);     // initEp (src/InsertSizeEstimator.h:60,80-81)
     int total = 0;
     std::ifstream fin(table);
     std::string line;
