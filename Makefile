@@ -12,7 +12,12 @@ CU_SRCS   := $(notdir $(wildcard $(CSRC)/*.cu))
 OBJS      := $(HOST_SRCS:%.cpp=$(OBJ)/%.o) $(CU_SRCS:%.cu=$(OBJ)/%.cu.o)
 LIB       := fastquick_b200/libfastquick_b200.so
 
-all: $(LIB)
+CLI       := fastquick_b200/FASTQuick_b200
+
+all: $(LIB) $(CLI)
+
+$(CLI): $(CSRC)/host/fq_cli.cpp $(CSRC)/host/FastQuickB200.cpp $(CSRC)/host/FastQuickB200.h $(LIB)
+	g++ $(CXXFLAGS) -o $@ $(CSRC)/host/fq_cli.cpp $(CSRC)/host/FastQuickB200.cpp -Lfastquick_b200 -lfastquick_b200 -Wl,-rpath,'$$ORIGIN' -lz -lpthread
 
 $(OBJ):
 	mkdir -p $(OBJ)

@@ -777,6 +777,10 @@ int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_
     return FQB_OK;
 }
 
+// pinned host memory for the FASTQ feeder's batches
+void *fqb_host_alloc(size_t bytes) { void *p = nullptr; return cudaMallocHost(&p, bytes) == cudaSuccess ? p : nullptr; }
+void fqb_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 uint64_t fqb_launch_count(const fqb_handle *h) { return h ? h->n_launches : 0; }
 
 void *fqb_stream(fqb_handle *h) { return h ? (void *)h->stream : nullptr; }

@@ -1,0 +1,227 @@
+#include "FastQuickB200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <sys/time.h>
+#include <thread>
+#include <zlib.h>
+
+namespace fqb200 {
+
+static double realtime() { struct timeval tp; gettimeofday(&tp, nullptr); return tp.tv_sec + tp.tv_usec * 1e-6; }
+void notice(const char *fmt, ...) { va_list ap; va_start(ap, fmt); fprintf(stderr, "NOTICE - "); vfprintf(stderr, fmt, ap); fprintf(stderr, "\n"); va_end(ap); }
+void warning(const char *fmt, ...) { va_list ap; va_start(ap, fmt); fprintf(stderr, "\aWARNING - \n"); vfprintf(stderr, fmt, ap); fprintf(stderr, "\n"); va_end(ap); }
+void error(const char *fmt, ...) { va_list ap; va_start(ap, fmt); fprintf(stderr, "\nFATAL ERROR - \n"); vfprintf(stderr, fmt, ap); fprintf(stderr, "\n"); va_end(ap); exit(EXIT_FAILURE); }
+
+bool BwtIndexer::LoadIndex(std::string &NewRef) {
+    IndexPrefix = NewRef;
+    std::ifstream par(NewRef + ".param");
+    if (!par) error("Open %s failed!", (NewRef + ".param").c_str());
+    std::string k;
+    par >> k >> RefPath;
+    for (const char *ext : {".bwt", ".rbwt", ".sa", ".rsa", ".pac", ".ann", ".amb", ".rollhash"})
+        if (!std::ifstream(NewRef + ext)) error("Open %s failed!", (NewRef + ext).c_str());
+    return true;
+}
+
+int StatCollector::RestoreVcfSites(const std::string &RefPath, const gap_opt_t *) {
+    if (fqb_stats_open(h_, RefPath.c_str()) != FQB_OK) error("%s", fqb_last_error());
+    return 0;
+}
+int StatCollector::ProcessCore(const std::string &statPrefix, const gap_opt_t *) {
+    if (fqb_stats_finish(h_, statPrefix.c_str()) != FQB_OK) error("%s", fqb_last_error());
+    return 0;
+}
+
+// ---- FASTQ feeder: 4-line records from gz, into fixed-stride pinned batches (kseq_read3_fpc's contract, libbwa/kseq.h:327-370)
+struct FastqReader {
+    gzFile fp = nullptr;
+    std::vector<char> buf; size_t pos = 0, end = 0;
+    bool open(const std::string &p) { fp = gzopen(p.c_str(), "rb"); if (fp) { gzbuffer(fp, 1 << 20); buf.resize(1 << 22); } return fp != nullptr; }
+    void close() { if (fp) gzclose(fp); fp = nullptr; }
+    bool getline(std::string &s) {
+        s.clear();
+        for (;;) {
+            if (pos == end) { int n = gzread(fp, buf.data(), (unsigned)buf.size()); if (n <= 0) return !s.empty(); pos = 0; end = (size_t)n; }
+            const char *b = buf.data() + pos, *e = (const char *)memchr(b, '\n', end - pos);
+            if (e) { s.append(b, e - b); pos += (size_t)(e - b) + 1; if (!s.empty() && s.back() == '\r') s.pop_back(); return true; }
+            s.append(b, end - pos); pos = end;
+        }
+    }
+    // returns the number of records read (<= n_max)
+    int fill(int n_max, int stride, uint8_t *bases, uint8_t *quals, int32_t *lens, char *names, int name_stride) {
+        std::string hdr, seq, plus, qual;
+        int n = 0;
+        while (n < n_max && getline(hdr)) {
+            if (hdr.empty()) continue;
+            if (!getline(seq) || !getline(plus) || !getline(qual)) error("truncated FASTQ record");
+            if (seq.size() != qual.size()) error("sequence and quality lengths differ in a FASTQ record");
+            if ((int)seq.size() > stride) error("read longer than %d bases: not supported", stride);
+            memset(bases + (size_t)n * stride, 'N', (size_t)stride);
+            memset(quals + (size_t)n * stride, '!', (size_t)stride);
+            memcpy(bases + (size_t)n * stride, seq.data(), seq.size());
+            memcpy(quals + (size_t)n * stride, qual.data(), qual.size());
+            lens[n] = (int32_t)seq.size();
+            size_t l = hdr.find_first_of(" \t");
+            std::string nm = hdr.substr(1, l == std::string::npos ? std::string::npos : l - 1);
+            if (nm.size() > 2 && nm[nm.size() - 2] == '/' && (nm.back() == '1' || nm.back() == '2')) nm.resize(nm.size() - 2);
+            memset(names + (size_t)n * name_stride, 0, (size_t)name_stride);
+            memcpy(names + (size_t)n * name_stride, nm.data(), std::min(nm.size(), (size_t)name_stride - 1));
+            ++n;
+        }
+        return n;
+    }
+};
+
+BwtMapper::BwtMapper(BwtIndexer &BwtIndex, const std::string &FQList, const std::string &Fastq_1, const std::string &Fastq_2,
+                     const std::string &Prefix, const std::string &RefPath, const pe_opt_t *popt, gap_opt_t *opt,
+                     const std::string &targetRegionPath, int device) : prefix_(Prefix) {
+    if (targetRegionPath != "Empty") error("--targetRegion is not supported by the GPU stage yet");
+    fqb_gap_opt_t g; fqb_gap_opt_default(&g);
+    g.s_mm = opt->s_mm; g.s_gapo = opt->s_gapo; g.s_gape = opt->s_gape; g.mode = opt->mode;
+    g.indel_end_skip = opt->indel_end_skip; g.max_del_occ = opt->max_del_occ; g.max_entries = opt->max_entries;
+    g.fnr = opt->fnr; g.max_diff = opt->max_diff; g.max_gapo = opt->max_gapo; g.max_gape = opt->max_gape;
+    g.max_seed_diff = opt->max_seed_diff; g.seed_len = opt->seed_len; g.max_top2 = opt->max_top2; g.trim_qual = opt->trim_qual;
+    g.flank_len = opt->flank_len; g.flank_long_len = opt->flank_long_len; g.read_len = opt->read_len;
+    g.kmer_thresh = BwtIndex.RollParam.thresh; g.is_il13 = (opt->mode & 0x200) ? 1 : 0;
+    fqb_pe_opt_t p; fqb_pe_opt_default(&p);
+    p.max_isize = popt->max_isize; p.force_isize = popt->force_isize; p.max_occ = popt->max_occ; p.n_multi = popt->n_multi;
+    p.N_multi = popt->N_multi; p.type = popt->type; p.is_sw = popt->is_sw; p.ap_prior = popt->ap_prior;
+    if (fqb_create(RefPath.c_str(), &g, &p, device, &h_) != FQB_OK) error("%s", fqb_last_error());
+    collector.Attach(h_);
+    if (opt->out_bam) warning("%s.bam is not written by the GPU stage yet (BAM emission is the next row of the plan)", Prefix.c_str());
+    double t_tmp = realtime();
+    collector.RestoreVcfSites(RefPath, opt);
+    notice("Restore Variant Site Info...%f sec", realtime() - t_tmp);
+    auto run_pair = [&](const std::string &f1, const std::string &f2) {
+        notice("Processing Pair End mapping\t%s\t%s", f1.c_str(), f2.c_str());
+        double t0 = realtime();
+        FileStatCollector FSC(f1.c_str(), f2.c_str());
+        PairEndMapper(f1, f2, opt, FSC);
+        notice("Processed Pair End mapping in %f sec", realtime() - t0);
+    };
+    if (FQList != "Empty") {
+        notice("Open Fastq List ...");
+        std::ifstream fin(FQList);
+        if (!fin.is_open()) error("Open file %s failed", FQList.c_str());
+        std::string line;
+        while (std::getline(fin, line)) {
+            if (line.empty() || line[0] == '#') continue;
+            std::string a, b;
+            std::stringstream ss(line);
+            ss >> a >> b;
+            if (b.empty()) error("Single End mapping is not supported by the GPU stage yet");
+            run_pair(a, b);
+        }
+    } else if (Fastq_2 != "Empty") run_pair(Fastq_1, Fastq_2);
+    else error("Single End mapping is not supported by the GPU stage yet");
+    double t1 = realtime();
+    collector.ProcessCore(Prefix, opt);
+    notice("Calculate distributions... %f sec", realtime() - t1);
+}
+
+BwtMapper::~BwtMapper() { fqb_destroy(h_); }
+
+bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, const gap_opt_t *opt, FileStatCollector &FSC) {
+    FastqReader r[2];
+    if (!r[0].open(fq1) || !r[1].open(fq2)) error("Open fastq failed: %s / %s", fq1.c_str(), fq2.c_str());
+    if (fqb_stats_begin_file(h_, prefix_.c_str(), fq1.c_str(), fq2.c_str()) != FQB_OK) error("%s", fqb_last_error());
+    const int stride = opt->read_len < FQB_MAX_READ_LEN ? opt->read_len : FQB_MAX_READ_LEN, cap = FQB_BATCH_PAIRS, name_stride = 64;
+    // double-buffered pinned batches: the two IO workers of the reference (src/BwtMapper.cpp:1969-1982) become one reader thread per end
+    struct Buf { uint8_t *b[2], *q[2]; int32_t *l[2]; char *nm[2]; int n[2]; } bufs[2];
+    for (auto &B : bufs)
+        for (int e = 0; e < 2; ++e) {
+            B.b[e] = (uint8_t *)fqb_host_alloc((size_t)cap * stride); B.q[e] = (uint8_t *)fqb_host_alloc((size_t)cap * stride);
+            B.l[e] = (int32_t *)fqb_host_alloc((size_t)cap * 4); B.nm[e] = (char *)fqb_host_alloc((size_t)cap * name_stride);
+            if (!B.b[e] || !B.q[e] || !B.l[e] || !B.nm[e]) error("pinned host allocation failed");
+        }
+    auto load = [&](Buf &B) {
+        std::thread t0([&]() { B.n[0] = r[0].fill(cap, stride, B.b[0], B.q[0], B.l[0], B.nm[0], name_stride); });
+        B.n[1] = r[1].fill(cap, stride, B.b[1], B.q[1], B.l[1], B.nm[1], name_stride);
+        t0.join();
+    };
+    int cur = 0;
+    load(bufs[cur]);
+    while (bufs[cur].n[0] > 0 && bufs[cur].n[1] > 0) {
+        Buf &B = bufs[cur];
+        if (B.n[0] != B.n[1]) error("Abort, please make sure input pair of fastq files are in the same order!");
+        std::thread next([&]() { load(bufs[1 - cur]); });                 // IO(N+1) overlaps GPU(N)
+        if (fqb_align_pairs(h_, B.n[0], stride, B.b[0], B.q[0], B.l[0], B.b[1], B.q[1], B.l[1], nullptr, nullptr, nullptr) != FQB_OK) error("%s", fqb_last_error());
+        if (fqb_stage_stats(h_) != FQB_OK) error("%s", fqb_last_error());
+        if (fqb_stats_emit(h_, B.nm[0], name_stride) != FQB_OK) error("%s", fqb_last_error());
+        FSC.NumRead += 2LL * B.n[0];
+        if (FSC.NumRead % FQB_BATCH_PAIRS == 0) fprintf(stderr, "NOTICE - %lld sequences are processed.\n", FSC.NumRead);
+        next.join();
+        cur = 1 - cur;
+    }
+    notice("%lld sequences are loaded.", FSC.NumRead);
+    for (auto &B : bufs) for (int e = 0; e < 2; ++e) { fqb_host_free(B.b[e]); fqb_host_free(B.q[e]); fqb_host_free(B.l[e]); fqb_host_free(B.nm[e]); }
+    r[0].close(); r[1].close();
+    return 0;
+}
+
+// `FASTQuick align` option table (src/FASTQuick.cpp:177-306): --name value, booleans as bare flags
+int runAlign(int argc, char **argv) {
+    double t_real = realtime();
+    gap_opt_t opt; pe_opt_t popt;
+    std::string Fastq_1("Empty"), Fastq_2("Empty"), FaList("Empty"), BamIn("Empty"), Prefix("Empty"), IndexPrefix("Empty"), ReadGroup("@RG\tID:foo\tSM:bar");
+    int kmer_thresh = 3, opte = -1, device = 0;
+    bool nonstop = false, il13 = false, loggap = false, sam_out = false;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto val = [&]() -> const char * { if (i + 1 >= argc) error("option %s needs a value", a.c_str()); return argv[++i]; };
+        if (a == "--fq_list") FaList = val(); else if (a == "--fastq_1") Fastq_1 = val(); else if (a == "--fastq_2") Fastq_2 = val();
+        else if (a == "--bam_in") BamIn = val(); else if (a == "--sam_out") sam_out = true;
+        else if (a == "--out_prefix") Prefix = val(); else if (a == "--index_prefix") IndexPrefix = val();
+        else if (a == "--kmer_thresh") kmer_thresh = atoi(val()); else if (a == "--n") opt.fnr = atof(val());
+        else if (a == "--o") opt.max_gapo = atoi(val()); else if (a == "--e") opte = atoi(val()); else if (a == "--i") opt.indel_end_skip = atoi(val());
+        else if (a == "--d") opt.max_del_occ = atoi(val()); else if (a == "--l") opt.seed_len = atoi(val()); else if (a == "--k") opt.max_seed_diff = atoi(val());
+        else if (a == "--m") opt.max_entries = atoi(val()); else if (a == "--t") opt.n_threads = atoi(val()); else if (a == "--R") opt.max_top2 = atoi(val());
+        else if (a == "--q") opt.trim_qual = atoi(val()); else if (a == "--RG") ReadGroup = val();
+        else if (a == "--N") nonstop = true; else if (a == "--I") il13 = true; else if (a == "--L") loggap = true;
+        else if (a == "--max_isize") popt.max_isize = atoi(val()); else if (a == "--max_occ") popt.max_occ = (unsigned)atoi(val());
+        else if (a == "--is_sw") popt.is_sw = 1; else if (a == "--n_multi") popt.n_multi = atoi(val()); else if (a == "--N_multi") popt.N_multi = atoi(val());
+        else if (a == "--ap_prior") popt.ap_prior = atof(val()); else if (a == "--force_isize") popt.force_isize = 1;
+        else if (a == "--cal_dup") opt.cal_dup = 1; else if (a == "--frac_samp") opt.frac = atof(val());
+        else if (a == "--device") device = atoi(val());
+        else error("unknown option %s", a.c_str());
+    }
+    if (opt.fnr >= 1.0) { opt.max_diff = (int)opt.fnr; opt.fnr = -1.0; }
+    if (Prefix == "Empty") error("--out_prefix is required");
+    if (IndexPrefix == "Empty") error("--index_prefix is required");
+    if (BamIn != "Empty") error("Input alignments from Bam file is disabled.");
+    if (opt.frac < 1.0) error("--frac_samp < 1 is not supported by the GPU stage yet");
+    if (sam_out) opt.out_bam = 0;
+    opt.RG = ReadGroup;
+    if (opte > 0) { opt.max_gape = opte; opt.mode &= ~0x01; }
+    if (nonstop) { opt.mode |= 0x10; opt.max_top2 = 0x7fffffff; }
+    if (il13) opt.mode |= 0x200;
+    if (loggap) opt.mode |= 0x04;
+    BwtIndexer Indexer(kmer_thresh);
+    std::string NewRef = IndexPrefix + ".FASTQuick.fa";
+    {   // <index>.FASTQuick.fa.param (src/FASTQuick.cpp:365-467)
+        std::ifstream par(NewRef + ".param");
+        if (!par) error("Open %s failed!", (NewRef + ".param").c_str());
+        std::string k, v;
+        while (par >> k >> v) {
+            if (k == "NUM_VAR_LONG") opt.num_variant_long = (unsigned)atoi(v.c_str());
+            else if (k == "NUM_VAR_SHORT") opt.num_variant_short = (unsigned)atoi(v.c_str());
+            else if (k == "SHORT_FLANK_LENGTH") opt.flank_len = atoi(v.c_str());
+            else if (k == "LONG_FLANK_LENGTH") opt.flank_long_len = atoi(v.c_str());
+        }
+    }
+    double t_tmp = realtime();
+    Indexer.LoadIndex(NewRef);
+    notice("Load Index... %f sec", realtime() - t_tmp);
+    t_tmp = realtime();
+    BwtMapper Mapper(Indexer, FaList, Fastq_1, Fastq_2, Prefix, NewRef, &popt, &opt, "Empty", device);
+    notice("Mapping... %f sec", realtime() - t_tmp);
+    notice("Real time: %.3f sec", realtime() - t_real);
+    return 0;
+}
+
+}  // namespace fqb200

@@ -154,6 +154,8 @@ int fqb_stage_fetch_aln(fqb_handle *h, int32_t cap, fqb_aln_t *out, int32_t *n_a
 /* since creation: stack pops, rank-query pairs, reference-equivalent occ-block touches (N_blk, the
  * roofline's algorithmic unit), overflow reads of the last batch */
 int fqb_stage_counters(fqb_handle *h, uint64_t *out4);
+void *fqb_host_alloc(size_t bytes);                /* pinned host memory for the feeder's batches */
+void fqb_host_free(void *p);
 uint64_t fqb_launch_count(const fqb_handle *h);   /* kernels launched by this handle so far */
 void *fqb_stream(fqb_handle *h);   /* the cudaStream_t the handle launches on (for event timing) */
 
