@@ -31,7 +31,8 @@ READ_LEN = 100
 WORKLOAD = "synthetic 10M 2x100bp pairs (f_on=1, 1% subst, 0.1%+0.1% indel) vs synthetic 10,197-marker flank index"
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "FASTQuick_ref")
 REF_SAMPLE_PAIRS = 8192          # pairs per step of the reference arm / cpu_baseline sample unit
-STAGES = "prep + k-mer filter + cal_width + match_gap + aln2seq/bwt_sa/mapQ + infer_isize + pairing + mate-rescue SW + gapped refinement (SURVEY 8 rows a1-a11)"
+STAGES = ("prep + k-mer filter + cal_width + match_gap + aln2seq/bwt_sa/mapQ + infer_isize + pairing + mate-rescue SW + gapped refinement + "
+          "StatCollector pair classification and per-base pile-up/depth/quality/cycle accumulation (SURVEY 8 rows a1-a13)")
 
 
 def peaks():
@@ -162,30 +163,73 @@ def main_reference(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+class Engine:
+    """The per-batch stages of the hot path over this rank's resident shard (interface of fastquick_b200.multigpu)."""
+
+    def __init__(self, lib, h, dev, n_pairs, rank, world):
+        self.lib, self.h, self.dev, self.n, self.rank, self.world = lib, h, dev, n_pairs, rank, world
+        self.base = 0           # local step index of global batch 0 of the current phase
+
+    def _ptr(self, t):
+        return C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_uint8))
+
+    def align(self, b):
+        d = self.dev[self.base + b // self.world]
+        lib, h = self.lib, self.h
+        assert lib.fqb_stage_load(h, self.n, READ_LEN, self._ptr(d[0]), self._ptr(d[1]), None, self._ptr(d[2]), self._ptr(d[3]), None, 1) == 0, lib.fqb_last_error()
+        assert lib.fqb_set_pair_base(h, C.c_uint64(b * self.n)) == 0
+        assert lib.fqb_stage_align(h) == 0, lib.fqb_last_error()
+
+    def pair(self, b):
+        assert self.lib.fqb_stage_pair(self.h) == 0, self.lib.fqb_last_error()
+
+    def finish(self, b):
+        assert self.lib.fqb_stage_sw_refine(self.h) == 0, self.lib.fqb_last_error()
+        assert self.lib.fqb_stage_stats(self.h) == 0, self.lib.fqb_last_error()
+
+    def get_state(self):
+        calls, ii = C.c_uint64(0), _abi.ISize()
+        self.lib.fqb_get_stream_state(self.h, C.byref(calls), C.byref(ii))
+        raw = np.frombuffer(bytes(ii), dtype=np.int64)
+        return [int(calls.value)] + [int(x) for x in raw] + [0] * (7 - len(raw))
+
+    def set_state(self, s):
+        ii = _abi.ISize.from_buffer_copy(np.array(s[1:1 + C.sizeof(_abi.ISize) // 8], dtype=np.int64).tobytes())
+        self.lib.fqb_set_stream_state(self.h, C.c_uint64(int(s[0])), C.byref(ii))
+
+
 def main_gpu(args):
     import torch
     import torch.distributed as dist
+    from fastquick_b200 import multigpu
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=device)
     lib = _abi.load_library()      # raises when the CUDA extension is missing: no CPU fallback
     lib.fqb_stream.restype = C.c_void_p
     lib.fqb_launch_count.restype = C.c_uint64
     synth = make_synth(lib)
     g = _abi.GapOpt()
     lib.fqb_gap_opt_default(C.byref(g))
-    g.trim_qual, g.read_len = 15, READ_LEN           # bin/FASTQuick.sh --steps Align passes --q 15
+    g.trim_qual = 15                                  # bin/FASTQuick.sh --steps Align passes --q 15
     h = C.c_void_p()
     assert lib.fqb_create_from_synth(synth, C.byref(g), None, local, C.byref(h)) == 0, lib.fqb_last_error()
+    # side files of the index (SelectedSite.vcf, .gc, dbSNP subset, .param, genome .fai/.amb) for the statistics tables
+    work = tempfile.mkdtemp(prefix="fqb_bench_r%d_" % rank)
+    prefix = os.path.join(work, "bench.FASTQuick.fa")
+    assert lib.fqb_synth_write_inputs(synth, work.encode()) == 0, lib.fqb_last_error()
+    assert lib.fqb_synth_write_index(synth, os.path.join(work, "genome.fa").encode(), os.path.join(work, "dbsnp.vcf").encode(), prefix.encode(), 0) == 0, lib.fqb_last_error()
+    assert lib.fqb_stats_open(h, prefix.encode()) == 0, lib.fqb_last_error()
     stream = torch.cuda.ExternalStream(lib.fqb_stream(h))
 
     n_steps = args.warmup + args.steps
     n_pairs = args.pairs_per_step
-    # this rank's shard of the workload: batches rank, rank+world, ...
+    # this rank's shard of the workload: global batch b = s * world + rank
     host = []
     for s in range(n_steps):
         first = (s * world + rank) * n_pairs
@@ -194,44 +238,64 @@ def main_gpu(args):
         host.append(bufs)
     dev = [[b.cuda(non_blocking=True) for b in bufs] for bufs in host]   # whole shard resident in HBM
     torch.cuda.synchronize()
+    eng = Engine(lib, h, dev, n_pairs, rank, world)
+
+    # accumulator groups reduced to rank 0 at the end of the timed region (NCCL over NVLink)
+    groups = []
+    for which, dt, op in ((0, torch.int32, "sum"), (1, torch.int64, "sum"), (2, torch.int32, "sum"), (3, torch.int32, "min")):
+        nb = C.c_uint64(0)
+        assert lib.fqb_stats_group_bytes(h, which, C.byref(nb)) == 0
+        groups.append((which, torch.empty(int(nb.value) // (4 if dt == torch.int32 else 8), dtype=dt, device=device), op))
+
+    def reduce_stats():
+        if world == 1:
+            return
+        for which, t, op in groups:
+            assert lib.fqb_stats_export(h, which, C.c_void_p(t.data_ptr())) == 0, lib.fqb_last_error()
+        multigpu.reduce_accumulators([(t, op) for _, t, op in groups], rank, world)
+        if rank == 0:
+            for which, t, op in groups:
+                assert lib.fqb_stats_import(h, which, C.c_void_p(t.data_ptr())) == 0, lib.fqb_last_error()
 
     def ptr(t):
         return C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_uint8))
 
-    def step_device(s):
-        d = dev[s]
-        assert lib.fqb_stage_load(h, n_pairs, READ_LEN, ptr(d[0]), ptr(d[1]), None, ptr(d[2]), ptr(d[3]), None, 1) == 0, lib.fqb_last_error()
-        assert lib.fqb_stage_align(h) == 0, lib.fqb_last_error()
-        assert lib.fqb_stage_pair(h) == 0, lib.fqb_last_error()
-        assert lib.fqb_stage_sw_refine(h) == 0, lib.fqb_last_error()
-
     rows_host = [torch.empty((n_pairs, _abi.READ_DTYPE.itemsize), dtype=torch.uint8).pin_memory() for _ in range(2)]
     ii_host = _abi.ISize()
 
-    def step_e2e(s):
-        # the public per-batch call: pinned host FASTQ arrays in, per-read result rows out
-        b = host[s]
-        rc = lib.fqb_align_pairs(h, n_pairs, READ_LEN, ptr(b[0]), ptr(b[1]), None, ptr(b[2]), ptr(b[3]), None,
-                                 C.c_void_p(rows_host[0].data_ptr()), C.c_void_p(rows_host[1].data_ptr()), C.byref(ii_host))
-        assert rc == 0, lib.fqb_last_error()
+    def run_device(first_step, k):
+        eng.base = first_step
+        multigpu.run_sharded(eng, k * world, rank, world, device)
+
+    def run_e2e(first_step, k):
+        # the public per-batch calls: pinned host FASTQ arrays in, per-read result rows out, statistics accumulated
+        for s in range(first_step, first_step + k):
+            b = host[s]
+            rc = lib.fqb_align_pairs(h, n_pairs, READ_LEN, ptr(b[0]), ptr(b[1]), None, ptr(b[2]), ptr(b[3]), None,
+                                     C.c_void_p(rows_host[0].data_ptr()), C.c_void_p(rows_host[1].data_ptr()), C.byref(ii_host))
+            assert rc == 0, lib.fqb_last_error()
+            assert lib.fqb_stage_stats(h) == 0, lib.fqb_last_error()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn):
-        for s in range(args.warmup):
-            fn(s)
+    def timed(fn, with_reduce):
+        lib.fqb_reset_stream(h)
+        fn(0, args.warmup)
         barrier()
+        lib.fqb_reset_stream(h)
         c0 = (C.c_uint64 * 4)(); lib.fqb_stage_counters(h, c0)
         l0 = lib.fqb_launch_count(h)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         with torch.cuda.stream(stream):
             e0.record(stream)
-            for s in range(args.warmup, n_steps):
-                fn(s)
+            fn(args.warmup, args.steps)
+            if with_reduce:
+                reduce_stats()
+                stream.wait_stream(torch.cuda.current_stream())
             e1.record(stream)
         barrier()
         t1 = time.time()
@@ -246,25 +310,24 @@ def main_gpu(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    ms, ctr, launches, t0, t1 = timed(step_device)
+    ms, ctr, launches, t0, t1 = timed(run_device, True)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    lib.fqb_reset_stream(h)
-    ms_e2e, _, _, _, _ = timed(step_e2e)
+    ms_e2e, _, _, _, _ = timed(run_e2e, True)
 
     total_pairs = args.steps * n_pairs * world
     value = total_pairs / (ms * 1e-3)
     e2e_value = total_pairs / (ms_e2e * 1e-3)
-    # roofline of the dominant kernel (search + width): algorithmic bytes = 64 B x N_blk, N_blk counted
+    # roofline of the dominant kernels (search + width): algorithmic bytes = 64 B x N_blk, N_blk counted
     # on the device for exactly the reads processed in the timed region
     hbm_peak, peak_kind = peaks()
     n_blk = ctr[2]
-    alg_bytes = 64.0 * n_blk
-    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    achieved = 64.0 * n_blk / (ms * 1e-3) / 1e9
     if world > 1:
         t = torch.tensor([achieved], device="cuda"); dist.all_reduce(t); achieved_job = float(t.item())
     else:
         achieved_job = achieved
     if rank != 0:
+        lib.fqb_destroy(h)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -274,7 +337,9 @@ def main_gpu(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_step": n_pairs, "read_len": READ_LEN, "stages": STAGES,
                    "l2_policy": "every step reads a different 105 MB batch; per-step working set (inputs+widths+stack arena) exceeds the 126 MB L2",
-                   "index": "10,197 markers, l_pac 6,608,697, replicated per GPU"},
+                   "index": "10,197 markers, l_pac 6,608,697, replicated per GPU",
+                   "multi_gpu": "batches round-robin over ranks; drand48 position + last_ii handed rank to rank (56 B per batch); "
+                                "accumulators NCCL-reduced to rank 0 inside the timed region"},
         "e2e": {"value": e2e_value, "unit": "read-pairs/s", "h2d_bytes_per_step": 4 * n_pairs * READ_LEN,
                 "d2h_bytes_per_step": int(2 * n_pairs * _abi.READ_DTYPE.itemsize)},
         "gpu_launches": launches,
@@ -286,10 +351,10 @@ def main_gpu(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
-            work = tempfile.mkdtemp(prefix="fqb_cpu_")
+            workc = tempfile.mkdtemp(prefix="fqb_cpu_")
             n_s = 4 * REF_SAMPLE_PAIRS
             if os.path.exists(REF_BIN):
-                rate, sec, cores = run_reference_sample(lib, synth, work, 0, n_s)
+                rate, sec, cores = run_reference_sample(lib, synth, workc, 0, n_s)
                 line["cpu_baseline"] = {"value": rate, "unit": "read-pairs/s", "cores": cores, "kind": "reference",
                                         "sample": "first %d pairs of the workload through FASTQuick_ref align --t %d --q 15 (%.1f s mapping)" % (n_s, cores, sec)}
             else:

@@ -679,6 +679,67 @@ int fqb_stats_finish(fqb_handle *h, const char *out_prefix) {
     return FQB_OK;
 }
 
+// ---- multi-GPU plumbing (row e): reads shard by batch with the index replicated; what crosses GPUs is
+// (1) the position of the drand48 stream + last_ii, handed from the rank that owns batch b to the owner of b+1, and
+// (2) at the end, the integer accumulators (NCCL reduce through torch.distributed on buffers exported here).
+int fqb_get_stream_state(fqb_handle *h, uint64_t *rng_calls, fqb_isize_t *last_ii) {
+    if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    if (rng_calls) *rng_calls = h->rng_calls;
+    if (last_ii) *last_ii = h->last_ii;
+    return FQB_OK;
+}
+int fqb_set_stream_state(fqb_handle *h, uint64_t rng_calls, const fqb_isize_t *last_ii) {
+    if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    h->rng_calls = rng_calls;
+    if (last_ii) h->last_ii = *last_ii;
+    return FQB_OK;
+}
+int fqb_set_pair_base(fqb_handle *h, uint64_t first_pair) {     // global index of the next batch's first pair (pile-up / contig order keys)
+    if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    h->pairs_seen = first_pair;
+    return FQB_OK;
+}
+
+// accumulator groups: 0 = depth|q20|q30 (u32, sum), 1 = quality/cycle histograms + InsertSizeDist + scalars (u64, sum),
+// 2 = per-contig counters (u32, sum), 3 = per-contig first-touch order (u32, min)
+static int stats_group(fqb_handle *h, int which, void **ptr, size_t *bytes) {
+    const size_t nc = h->stabs.contigs.size(), ns = h->stabs.n_sites ? h->stabs.n_sites : 1;
+    switch (which) {
+    case 0: *ptr = h->d_depth; *bytes = ns * 3 * 4; return FQB_OK;
+    case 1: *ptr = h->d_emp; *bytes = (4 * 256 + 4096 + 8) * 8; return FQB_OK;
+    case 2: *ptr = h->d_contig_ctr; *bytes = nc * 4 * 4; return FQB_OK;
+    case 3: *ptr = h->d_contig_ctr + nc * 4; *bytes = nc * 4; return FQB_OK;
+    default: set_error("bad accumulator group"); return FQB_ERR_ARG;
+    }
+}
+int fqb_stats_group_bytes(fqb_handle *h, int which, uint64_t *bytes) {
+    if (!h || !h->stats_open) { set_error("stats not open"); return FQB_ERR_STATE; }
+    void *p; size_t b;
+    int rc = stats_group(h, which, &p, &b);
+    if (rc == FQB_OK) *bytes = b;
+    return rc;
+}
+int fqb_stats_export(fqb_handle *h, int which, void *dst_device) {
+    if (!h || !h->stats_open) { set_error("stats not open"); return FQB_ERR_STATE; }
+    void *p; size_t b;
+    int rc = stats_group(h, which, &p, &b);
+    if (rc) return rc;
+    CU_CHECK(cudaSetDevice(h->device));
+    CU_CHECK(cudaMemcpyAsync(dst_device, p, b, cudaMemcpyDeviceToDevice, h->stream));
+    CU_CHECK(cudaStreamSynchronize(h->stream));
+    return FQB_OK;
+}
+int fqb_stats_import(fqb_handle *h, int which, const void *src_device) {
+    if (!h || !h->stats_open) { set_error("stats not open"); return FQB_ERR_STATE; }
+    void *p; size_t b;
+    int rc = stats_group(h, which, &p, &b);
+    if (rc) return rc;
+    CU_CHECK(cudaSetDevice(h->device));
+    CU_CHECK(cudaMemcpyAsync(p, src_device, b, cudaMemcpyDeviceToDevice, h->stream));
+    CU_CHECK(cudaStreamSynchronize(h->stream));
+    return FQB_OK;
+}
+
 // result rows of the last completed stage: rows[e][i] = end e of pair i
 int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out) {
     if (!h || !h->pair_done) { set_error("fqb_stage_fetch_rows: run fqb_stage_pair first"); return FQB_ERR_STATE; }

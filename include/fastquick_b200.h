@@ -145,6 +145,17 @@ int fqb_stats_begin_file(fqb_handle *h, const char *out_prefix, const char *fast
 int fqb_stage_stats(fqb_handle *h);
 int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride);
 int fqb_stats_finish(fqb_handle *h, const char *out_prefix);
+/* ---- multi-GPU (one process per GPU; reads shard by 262,144-pair batch, index replicated) -----------------
+ * The only cross-batch state of the path is the drand48 position (srand48 once per FASTQ pair,
+ * src/BwtMapper.cpp:1817) and last_ii (src/BwtMapper.cpp:780): the owner of batch b hands both to the owner of
+ * batch b+1 between fqb_stage_align and fqb_stage_pair.  At the end the integer accumulators are combined with
+ * an NCCL reduce (groups 0-2: sum; group 3: min) on buffers moved with fqb_stats_export / fqb_stats_import. */
+int fqb_get_stream_state(fqb_handle *h, uint64_t *rng_calls, fqb_isize_t *last_ii);
+int fqb_set_stream_state(fqb_handle *h, uint64_t rng_calls, const fqb_isize_t *last_ii);
+int fqb_set_pair_base(fqb_handle *h, uint64_t first_pair);
+int fqb_stats_group_bytes(fqb_handle *h, int which, uint64_t *bytes);
+int fqb_stats_export(fqb_handle *h, int which, void *dst_device);
+int fqb_stats_import(fqb_handle *h, int which, const void *src_device);
 int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
 /* new FASTQ pair: restart the drand48 stream and forget last_ii (src/BwtMapper.cpp:1811-1817) */
 int fqb_reset_stream(fqb_handle *h);
