@@ -30,11 +30,11 @@ constexpr int kGapOpen = 26, kGapExt = 9, kGapEnd = 5, kBandWidth = 50;   // aln
 FQB_HD int maq_score(uint32_t a, uint32_t b) { return (a > 3 || b > 3) ? -13 : (a == b ? 11 : -19); }
 
 struct DpScratch {
-    int32_t *ints; int n_ints;       // interleaved int scratch (rows of the DP)
-    uint8_t *bytes; int n_bytes;     // interleaved byte scratch (trace-back matrix, ops)
-    int stride;                      // 32 on the device, 1 on the host
-    FQB_HD int32_t &I(int e) const { return ints[(size_t)e * stride]; }
-    FQB_HD uint8_t &B(int e) const { return bytes[(size_t)e * stride]; }
+    int32_t *ints; int n_ints;       // interleaved int scratch (rows of the DP): shared memory in the fast kernels
+    uint8_t *bytes; int n_bytes;     // interleaved byte scratch (trace-back matrix, ops): global memory
+    int istride, bstride;            // element e of this lane at e * stride (threads per block / 32 on the device, 1 on the host)
+    FQB_HD int32_t &I(int e) const { return ints[(size_t)e * istride]; }
+    FQB_HD uint8_t &B(int e) const { return bytes[(size_t)e * bstride]; }
 };
 
 // reference window and read, both as "sequence of nt4 codes" accessors
@@ -261,17 +261,19 @@ FQB_HD LocalResult local_align(const RefWin &R, int len1, const ReadSeq &Q, int 
     LocalResult res; res.score = -1; res.n_ops = 0; res.start_i = res.start_j = res.end_i = res.end_j = 0; res.too_big = false;
     if (len1 == 0 || len2 == 0) return res;
     const int q = kGapOpen, r = kGapExt, qr = q + r, max_score = 11;
-    if (2 * (len1 + 2) > sc.n_ints) { res.too_big = true; return res; }
-#define EH(i) sc.I(2 * (i))
-#define EE(i) sc.I(2 * (i) + 1)
-    for (int i = 0; i <= len1 + 1; ++i) { EH(i) = 0; EE(i) = 0; }
+    if (len1 + 2 > sc.n_ints) { res.too_big = true; return res; }
+    // one word per column, h in the high half and e in the low half, as the reference packs eh[] (stdaln.c:252-256)
+#define EH(i) (sc.I(i) >> 16)
+#define EE(i) (sc.I(i) & 0xffff)
+#define EHE_SET(i, h, e) (sc.I(i) = ((h) << 16) | (e))
+    for (int i = 0; i <= len1 + 1; ++i) EHE_SET(i, 0, 0);
     int score_f = 0, end_i = 0, end_j = 0;
     for (int j = 1; j <= len2; ++j) {
         int last_h = 0, f = 0;
         const uint32_t qj = Q.at(j - 1);
         int h_here = EH(0), e_here = EE(0);
         for (int i = 1; i <= len1; ++i) {
-            const int h_next = EH(i), e_next = EE(i);
+            const int w_next = sc.I(i), h_next = w_next >> 16, e_next = w_next & 0xffff;
             int curr_h = h_here + maq_score(R.at(i - 1), qj);
             if (curr_h < 0) curr_h = 0;
             if (last_h > 0) { f = (f > last_h - q) ? f - r : last_h - qr; if (curr_h < f) curr_h = f; }
@@ -280,20 +282,20 @@ FQB_HD LocalResult local_align(const RefWin &R, int len1, const ReadSeq &Q, int 
                 e = (e_here > h_next - q) ? e_here - r : h_next - qr;
                 if (curr_h < e) curr_h = e;
             }
-            EH(i - 1) = last_h; EE(i - 1) = e;
+            EHE_SET(i - 1, last_h, e);
             last_h = curr_h;
             if (score_f < curr_h) { score_f = curr_h; end_i = i; end_j = j; }
             h_here = h_next; e_here = e_next;
         }
-        EH(len1) = last_h; EE(len1) = 0;
+        EHE_SET(len1, last_h, 0);
     }
     res.score = score_f;
     if (score_f < 1) return res;
-    for (int i = end_i; i >= 0; --i) { EH(i) = 0; EE(i) = 0; }
+    for (int i = end_i; i >= 0; --i) EHE_SET(i, 0, 0);
     if (end_i == 0 || end_j == 0) return res;
     int score_r = maq_score(R.at(end_i - 1), Q.at(end_j - 1));
     int start_i = end_i, start_j = end_j;
-    EH(end_i) = qr + score_r; EE(end_i) = 0;
+    EHE_SET(end_i, qr + score_r, 0);
     int start = end_i - 1, end = end_i - 3;
     if (end <= 0) end = 0;
     for (int j = end_j - 1; j != 0; --j) {
@@ -302,14 +304,15 @@ FQB_HD LocalResult local_align(const RefWin &R, int len1, const ReadSeq &Q, int 
         const uint32_t qj = Q.at(j - 1);
         int i = start;
         for (; i != end; --i) {
-            int curr_h = EH(i + 1) + maq_score(R.at(i - 1), qj);
+            const int w_here = sc.I(i + 1);
+            int curr_h = (w_here >> 16) + maq_score(R.at(i - 1), qj);
             if (curr_h < 0) curr_h = 0;
             if (last_h > 0) { f = (f > last_h - q) ? f - r : last_h - qr; if (curr_h < f) curr_h = f; }
-            const int curr_last_h = EH(i), e_old = EE(i + 1);
+            const int curr_last_h = EH(i), e_old = w_here & 0xffff;
             int e = (e_old > curr_last_h - q) ? e_old - r : curr_last_h - qr;
             if (e < 0) e = 0;
             if (curr_h < e) curr_h = e;
-            EH(i + 1) = last_h; EE(i + 1) = e;
+            EHE_SET(i + 1, last_h, e);
             last_h = curr_h;
             if (score_r < curr_h) {
                 score_r = curr_h; start_i = i; start_j = j;
@@ -317,7 +320,7 @@ FQB_HD LocalResult local_align(const RefWin &R, int len1, const ReadSeq &Q, int 
             }
         }
         if (stop) break;
-        EH(i + 1) = last_h; EE(i + 1) = 0;
+        EHE_SET(i + 1, last_h, 0);
         if (EH(start) <= qr) --start;
         if (start <= 0) start = 0;
         end = start_i - (start_j - j) - (score_r + (start_j - j) * max_score) / r - 1;
@@ -325,6 +328,7 @@ FQB_HD LocalResult local_align(const RefWin &R, int len1, const ReadSeq &Q, int 
     }
 #undef EH
 #undef EE
+#undef EHE_SET
     score_r -= qr;
     int jmax = (end_i - start_i > end_j - start_j) ? end_i - start_i : end_j - start_j;
     ++jmax;

@@ -6,6 +6,7 @@
 namespace fqb {
 
 constexpr int kDpThreads = 64;
+constexpr int kSwSmemInts = 704;     // mate-rescue windows up to 702 columns keep their rows in shared memory (176 KB per block)
 
 struct DpView {
     int n_reads, lpad;
@@ -19,8 +20,7 @@ struct DpPool {
     int ints_per_lane, bytes_per_lane, n_blocks;
 };
 
-void launch_sw(const DpView &v, const SwParams &sp, const DpPool &pool, uint32_t *list, uint32_t *n_list, uint32_t *cursor,
-               uint32_t *err, cudaStream_t s);
-void launch_refine(const DpView &v, const DpPool &pool, uint32_t *list, uint32_t *n_list, uint32_t *cursor, uint32_t *err, cudaStream_t s);
+void launch_sw(const DpView &v, const SwParams &sp, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, cudaStream_t s);
+void launch_refine(const DpView &v, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, int max_read_len, cudaStream_t s);
 
 }  // namespace fqb

@@ -94,7 +94,8 @@ struct fqb_handle {
     uint64_t rng_x0 = 0, rng_calls = 0;  // srand48(bns->seed) stream position (src/BwtMapper.cpp:1817)
     fqb_isize_t last_ii, cur_ii;
     bool align_done = false, pair_done = false, dp_done = false;
-    uint32_t *d_sw_list = nullptr, *d_refine_list = nullptr;
+    uint32_t *d_sw_list = nullptr, *d_refine_list = nullptr;   // each: work list followed by its retry list
+    uint32_t *d_dpctr = nullptr;                             // [0..3] SW list/cursors, [4..7] refine list/cursors, [8] error
     DpPool dp_pool = {nullptr, nullptr, 0, 0, 0};
     // statistics rows (a12-a14)
     bool stats_open = false, stats_done = false;
@@ -160,8 +161,8 @@ static int ensure_batch(fqb_handle *h, int n_reads, int stride) {
     CU_CHECK(cudaMalloc(&h->pesc.cum_extra, (size_t)cap * 8));
     CU_CHECK(cudaMalloc(&h->pesc.multi_list, (size_t)cap * 4));
     CU_CHECK(cudaMalloc(&h->d_big_list, (size_t)cap * 2));
-    CU_CHECK(cudaMalloc(&h->d_sw_list, (size_t)cap * 2));
-    CU_CHECK(cudaMalloc(&h->d_refine_list, (size_t)cap * 4));
+    CU_CHECK(cudaMalloc(&h->d_sw_list, (size_t)cap * 4));        // n_pairs entries + n_pairs retry entries
+    CU_CHECK(cudaMalloc(&h->d_refine_list, (size_t)cap * 8));    // n_reads entries + n_reads retry entries
     h->cap_reads = cap; h->lpad = lpad; h->stride_cap = stride;
     return FQB_OK;
 }
@@ -248,6 +249,7 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     h->rng_x0 = lcg_seed(h->hidx.seed); h->rng_calls = 0;
     h->last_ii.avg = h->last_ii.std = -1.0; h->last_ii.ap_prior = 0; h->last_ii.low = h->last_ii.high = h->last_ii.high_bayesian = h->last_ii.pad_ = 0;
     h->cur_ii = h->last_ii;
+    CU_CHECK_H(cudaMalloc(&h->d_dpctr, 12 * 4));
     CU_CHECK_H(cudaMalloc(&h->d_counters, 4 * 8));
     CU_CHECK_H(cudaMemset(h->d_counters, 0, 4 * 8));
     if (h->gopt.kmer_thresh != 0) {     // 6 x 512 MiB bitmaps, streamed from disk (BwtIndexer::ReadRollHashTable)
@@ -282,7 +284,7 @@ void fqb_destroy(fqb_handle *h) {
     for (int s = 0; s < 2; ++s) { cudaFree(h->d_blocks[s]); cudaFree(h->d_sa[s]); }
     cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_ctrs); cudaFree(h->d_counters);
     cudaFree(h->d_arena); cudaFree(h->d_arena_mid); cudaFree(h->d_arena_big); cudaFree(h->d_aln_big);
-    cudaFree(h->pesc.totals); cudaFree(h->pesc.err_flag); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch); cudaFree(h->dp_pool.ints); cudaFree(h->dp_pool.bytes);
+    cudaFree(h->pesc.totals); cudaFree(h->pesc.err_flag); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch); cudaFree(h->dp_pool.ints); cudaFree(h->dp_pool.bytes); cudaFree(h->d_dpctr);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -496,15 +498,15 @@ int fqb_stage_sw_refine(fqb_handle *h) {
         sp.avg = ii.avg; sp.std = ii.std; sp.l_pac = h->hidx.l_pac;
         sp.s_old_add = -4.343 * std::log(ii.ap_prior / h->hidx.l_pac);                      // libbwa/bwape.c:577
         sp.s_new_add = (int)(-4.343 * std::log(.5 * std::erfc(M_SQRT1_2 * 1.5) + .499));     // libbwa/bwape.c:578
-        CU_CHECK(cudaMemsetAsync(h->d_ctrs + 13, 0, 12, st));   // [13] n_sw [14] sw cursor [15] dp error
-        launch_sw(v, sp, h->dp_pool, h->d_sw_list, h->d_ctrs + 13, h->d_ctrs + 14, h->d_ctrs + 15, st);
-        h->n_launches += 2;
+        CU_CHECK(cudaMemsetAsync(h->d_dpctr, 0, 12 * 4, st));
+        launch_sw(v, sp, h->dp_pool, h->d_sw_list, h->d_sw_list + h->cap_reads / 2, h->d_dpctr, h->d_dpctr + 8, st);
+        h->n_launches += 3;
     }
-    CU_CHECK(cudaMemsetAsync(h->d_ctrs + 8, 0, 8, st));       // [8] n_refine [9] refine cursor
-    launch_refine(v, h->dp_pool, h->d_refine_list, h->d_ctrs + 8, h->d_ctrs + 9, h->d_ctrs + 15, st);
-    h->n_launches += 3;
+    else CU_CHECK(cudaMemsetAsync(h->d_dpctr, 0, 12 * 4, st));
+    launch_refine(v, h->dp_pool, h->d_refine_list, h->d_refine_list + h->cap_reads, h->d_dpctr + 4, h->d_dpctr + 8, h->stride, st);
+    h->n_launches += 4;
     uint32_t err = 0;
-    CU_CHECK(cudaMemcpyAsync(&err, h->d_ctrs + 15, 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaMemcpyAsync(&err, h->d_dpctr + 8, 4, cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaStreamSynchronize(st));
     CU_CHECK(cudaGetLastError());
     if (err) { set_error("an alignment needed more DP scratch or CIGAR operations than provisioned"); return FQB_ERR_LIMIT; }

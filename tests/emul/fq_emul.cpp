@@ -182,7 +182,7 @@ int emul_sw_refine(void *h, const fqb_pe_opt_t *popt, int n_pairs, int stride, c
     const uint8_t *pac = e->idx.pac.data();
     std::vector<int32_t> ints(6 * 1100);
     std::vector<uint8_t> bytes(400000);
-    DpScratch sc; sc.ints = ints.data(); sc.n_ints = (int)ints.size(); sc.bytes = bytes.data(); sc.n_bytes = (int)bytes.size(); sc.stride = 1;
+    DpScratch sc; sc.ints = ints.data(); sc.n_ints = (int)ints.size(); sc.bytes = bytes.data(); sc.n_bytes = (int)bytes.size(); sc.istride = sc.bstride = 1;
     if (popt->is_sw && ii->avg >= 0.0) {
         SwParams sp;
         sp.avg = ii->avg; sp.std = ii->std; sp.l_pac = l_pac;
