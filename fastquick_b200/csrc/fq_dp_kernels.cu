@@ -139,9 +139,12 @@ void launch_sw(const DpView &v, const SwParams &sp, const DpPool &pool, uint32_t
 void launch_refine(const DpView &v, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, int max_read_len, cudaStream_t s) {
     refine_classify_kernel<<<(v.n_reads + 255) / 256, 256, 0, s>>>(v, list, ctr);
     const int ints = 6 * (max_read_len + 16 + 1);
-    const size_t smem = (size_t)ints * kDpThreads * 4;
+    int threads = (int)((220u * 1024u) / ((size_t)ints * 4)) / 32 * 32;          // as many lanes as fit 220 KB of shared memory
+    if (threads > kDpThreads) threads = kDpThreads;
+    if (threads < 32) threads = 32;
+    const size_t smem = (size_t)ints * threads * 4;
     cudaFuncSetAttribute(refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    refine_kernel<true><<<pool.n_blocks, kDpThreads, smem, s>>>(v, pool, list, ctr, ctr + 1, err, ints, retry, ctr + 2);
+    refine_kernel<true><<<pool.n_blocks, threads, smem, s>>>(v, pool, list, ctr, ctr + 1, err, ints, retry, ctr + 2);
     refine_kernel<false><<<pool.n_blocks, kDpThreads, 0, s>>>(v, pool, retry, ctr + 2, ctr + 3, err, 0, nullptr, nullptr);
     finish_kernel<<<(v.n_reads + 255) / 256, 256, 0, s>>>(v);
 }
