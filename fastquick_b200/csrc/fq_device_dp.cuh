@@ -169,19 +169,22 @@ FQB_HD int ops_to_cigar(const DpScratch &sc, int ops_base, int n_ops, uint16_t *
     return n + 1;
 }
 
-// refine_gapped_core with is_end_correct = 1 (libbwa/bwase.c:183-232).  Returns n_cigar, -1 = scratch too small.
-FQB_HD int refine_gapped(int64_t l_pac, const uint8_t *pac, const ReadSeq &Q, uint32_t *pos_io, int ext, uint16_t *cigar, int cap,
-                         const DpScratch &sc) {
-    const int len = Q.len, ref_len = len + (ext < 0 ? -ext : ext);
-    int64_t pos = *pos_io > (uint32_t)l_pac ? (int64_t)(int32_t)*pos_io : (int64_t)*pos_io;
+// refine_gapped_core with is_end_correct = 1 (libbwa/bwase.c:183-232), in three pieces so that the warp-cooperative
+// kernel can share the scalar parts: the reference window, the alignment, and the CIGAR/position fix-up.
+FQB_HD RefWin refine_window(int64_t l_pac, const uint8_t *pac, int len, uint32_t pos_in, int ext, int64_t *pos_out) {
+    const int ref_len = len + (ext < 0 ? -ext : ext);
+    int64_t pos = pos_in > (uint32_t)l_pac ? (int64_t)(int32_t)pos_in : (int64_t)pos_in;
     RefWin R; R.pac = pac;
     if (ext > 0) { R.beg = pos; int64_t e = pos + ref_len < l_pac ? pos + ref_len : l_pac; R.l = (int)(e > pos ? e - pos : 0); }
     else {
         int64_t x = pos + len, b = x - ref_len > 0 ? x - ref_len : 0, e = x < l_pac ? x : l_pac;
         R.beg = b; R.l = (int)(e > b ? e - b : 0);
     }
-    GlobalResult g = global_align(R, 0, R.l, Q, 0, len, kGapEnd, kBandWidth, sc, 0);
-    if (g.too_big) return -1;
+    *pos_out = pos;
+    return R;
+}
+// path ops at sc.B(0 ..); returns n_cigar (-1 = capacity) and the corrected position
+FQB_HD int refine_post(const GlobalResult &g, int64_t pos, int ext, uint32_t *pos_io, uint16_t *cigar, int cap, const DpScratch &sc) {
     int n_cigar = ops_to_cigar(sc, 0, g.n_ops, cigar, cap);
     if (n_cigar <= 0) return n_cigar < 0 ? -1 : 0;
     if (ext < 0) {
@@ -202,6 +205,14 @@ FQB_HD int refine_gapped(int64_t l_pac, const uint8_t *pac, const ReadSeq &Q, ui
     if ((cigar[0] >> 14) == kOpI) cigar[0] = (uint16_t)(kOpS << 14 | (cigar[0] & 0x3fff));
     *pos_io = (uint32_t)pos;
     return n_cigar;
+}
+FQB_HD int refine_gapped(int64_t l_pac, const uint8_t *pac, const ReadSeq &Q, uint32_t *pos_io, int ext, uint16_t *cigar, int cap,
+                         const DpScratch &sc) {
+    int64_t pos;
+    const RefWin R = refine_window(l_pac, pac, Q.len, *pos_io, ext, &pos);
+    GlobalResult g = global_align(R, 0, R.l, Q, 0, Q.len, kGapEnd, kBandWidth, sc, 0);
+    if (g.too_big) return -1;
+    return refine_post(g, pos, ext, pos_io, cigar, cap, sc);
 }
 
 // NM exactly as bwa_cal_md1 counts it (libbwa/bwase.c:234-296)
@@ -347,18 +358,10 @@ FQB_HD LocalResult local_align(const RefWin &R, int len1, const ReadSeq &Q, int 
 
 constexpr int kSwCigarCap = 48;
 
-// bwa_sw_core (libbwa/bwape.c:359-445).  Returns n_cigar (0 = none), -1 = scratch / cigar capacity exceeded.
-FQB_HD int sw_core(int64_t l_pac, const uint8_t *pac, const ReadSeq &Q, int64_t *beg, int reglen, uint16_t *cigar, uint32_t *cnt,
-                   const DpScratch &sc) {
+// tail of bwa_sw_core (libbwa/bwape.c:385-445): CIGAR, clipping and mismatch/gap counts from the local alignment whose
+// path ops sit at sc.B(0 ..).  Returns n_cigar (0 = none), -1 = cigar capacity exceeded.
+FQB_HD int sw_post(const RefWin &R, const ReadSeq &Q, const LocalResult &lr, int64_t *beg, uint16_t *cigar, uint32_t *cnt, const DpScratch &sc) {
     const int len = Q.len;
-    if (reglen < 20 || l_pac - *beg < len) return 0;
-    int nn = 0;
-    for (int k = 0; k < len; ++k) nn += Q.at(k) >= 4;
-    if ((float)nn / len >= 0.25f || len - nn < 20) return 0;
-    RefWin R; R.pac = pac; R.beg = *beg;
-    { int64_t e = *beg + reglen < l_pac ? *beg + reglen : l_pac; R.l = (int)(e - *beg); }
-    LocalResult lr = local_align(R, R.l, Q, len, sc, 0);
-    if (lr.too_big) return -1;
     if (lr.score < 0 || lr.n_ops == 0) return 0;
     int n_cigar = ops_to_cigar(sc, 0, lr.n_ops, cigar, kSwCigarCap - 2);
     if (n_cigar < 0) return -1;
@@ -368,17 +371,11 @@ FQB_HD int sw_core(int64_t l_pac, const uint8_t *pac, const ReadSeq &Q, int64_t 
         if (op == kOpM) { x += cl; y += cl; } else if (op == kOpD) x += cl; else y += cl;
     }
     if (x < 20 || y < 20) return 0;
-    // path[path_len-1] = first aligned cell, path[0] = last: coordinates follow from the local start/end
-    // (the last path element of aln_global_core is the cell after the first op, in window coordinates)
-    int pi, pj;
-    {
-        // walk the ops backwards from (end_i, end_j) to find the coordinates of path[path_len-1]
-        int ci = lr.end_i, cj = lr.end_j;
-        for (int k = 0; k < lr.n_ops - 1; ++k) {
-            uint32_t op = sc.B(k);
-            if (op == kOpM) { --ci; --cj; } else if (op == kOpI) --cj; else --ci;
-        }
-        pi = ci; pj = cj;
+    // path[path_len-1] = first aligned cell, path[0] = last: walk the ops back from (end_i, end_j)
+    int pi = lr.end_i, pj = lr.end_j;
+    for (int k = 0; k < lr.n_ops - 1; ++k) {
+        uint32_t op = sc.B(k);
+        if (op == kOpM) { --pi; --pj; } else if (op == kOpI) --pj; else --pi;
     }
     *beg += (pi ? pi : 1) - 1;
     const int start = (pj ? pj : 1) - 1, end = lr.end_j;
@@ -398,6 +395,27 @@ FQB_HD int sw_core(int64_t l_pac, const uint8_t *pac, const ReadSeq &Q, int64_t 
     return n_cigar;
 }
 
+// bwa_sw_core (libbwa/bwape.c:359-445).  Returns n_cigar (0 = none), -1 = scratch / cigar capacity exceeded.
+FQB_HD int sw_core(int64_t l_pac, const uint8_t *pac, const ReadSeq &Q, int64_t *beg, int reglen, uint16_t *cigar, uint32_t *cnt,
+                   const DpScratch &sc) {
+    const int len = Q.len;
+    if (reglen < 20 || l_pac - *beg < len) return 0;
+    int nn = 0;
+    for (int k = 0; k < len; ++k) nn += Q.at(k) >= 4;
+    if ((float)nn / len >= 0.25f || len - nn < 20) return 0;
+    RefWin R; R.pac = pac; R.beg = *beg;
+    { int64_t e = *beg + reglen < l_pac ? *beg + reglen : l_pac; R.l = (int)(e - *beg); }
+    LocalResult lr = local_align(R, R.l, Q, len, sc, 0);
+    if (lr.too_big) return -1;
+    return sw_post(R, Q, lr, beg, cigar, cnt, sc);
+}
+struct ThreadSwCore {
+    const DpScratch &sc;
+    FQB_HD int operator()(int64_t l_pac, const uint8_t *pac, const ReadSeq &Q, int64_t *beg, int reglen, uint16_t *cigar, uint32_t *cnt) const {
+        return sw_core(l_pac, pac, Q, beg, reglen, cigar, cnt, sc);
+    }
+};
+
 // per-batch constants of bwa_paired_sw that go through libm (host, glibc): SURVEY A.5
 struct SwParams {
     double avg, std;
@@ -407,8 +425,10 @@ struct SwParams {
 };
 
 // bwa_paired_sw for one pair (libbwa/bwape.c:497-617), BWA_PET_STD.  Returns false if scratch was too small.
-FQB_HD bool paired_sw_one(const uint8_t *pac, fqb_read_t *p0, fqb_read_t *p1, const uint8_t *fwd0, const uint8_t *fwd1,
-                          const SwParams &sp, const DpScratch &sc) {
+// `core` runs bwa_sw_core for one mate (per thread, or cooperatively by a warp whose lanes all call this function).
+template <class Core>
+FQB_HD bool paired_sw_pair(const uint8_t *pac, fqb_read_t *p0, fqb_read_t *p1, const uint8_t *fwd0, const uint8_t *fwd1,
+                           const SwParams &sp, const Core &core) {
     fqb_read_t *p[2] = {p0, p1};
     int n_cigar[2] = {0, 0}, mq_adjust[2] = {255, 255}, mapQ = 0;
     int64_t beg[2] = {0, 0};
@@ -437,7 +457,7 @@ FQB_HD bool paired_sw_one(const uint8_t *pac, fqb_read_t *p0, fqb_read_t *p1, co
             Q.strand = 0;
         }
         beg[k] = b;
-        int nc = sw_core(sp.l_pac, pac, Q, &beg[k], (int)(e - b), cig[k], &cnt[k], sc);
+        int nc = core(sp.l_pac, pac, Q, &beg[k], (int)(e - b), cig[k], &cnt[k]);
         if (nc < 0) return false;
         n_cigar[k] = nc;
         if (nc && pm->type != kTypeNoMatch) {
@@ -477,6 +497,11 @@ FQB_HD bool paired_sw_one(const uint8_t *pac, fqb_read_t *p0, fqb_read_t *p1, co
         po->extra_flag |= kSamProper;
     }
     return true;
+}
+FQB_HD bool paired_sw_one(const uint8_t *pac, fqb_read_t *p0, fqb_read_t *p1, const uint8_t *fwd0, const uint8_t *fwd1,
+                          const SwParams &sp, const DpScratch &sc) {
+    ThreadSwCore core{sc};
+    return paired_sw_pair(pac, p0, p1, fwd0, fwd1, sp, core);
 }
 
 }  // namespace fqb

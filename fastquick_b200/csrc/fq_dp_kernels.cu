@@ -1,8 +1,9 @@
 // CUDA kernels of the dynamic-programming rows (a10 mate rescue, a11 gapped refinement), sm_100a.
-// One alignment per lane; DP rows and trace-back live in warp-interleaved global scratch so the 32
-// lanes of a warp (walking their matrices in lock step) issue coalesced accesses.  Work comes from
-// compacted lists through a warp-aggregated queue, as in the search kernel.
+// Main path: one alignment per WARP (fq_dp_warp.cuh), DP rows in shared memory, trace-back in a warp-private
+// slab of the global pool.  Alignments whose window does not fit go to a retry list handled by the
+// one-alignment-per-lane kernels (rows and trace-back in warp-interleaved global scratch).
 #include "fq_dp_kernels.cuh"
+#include "fq_dp_warp.cuh"
 
 namespace fqb {
 
@@ -17,14 +18,6 @@ __device__ __forceinline__ DpScratch lane_scratch(const DpPool &pool) {
     sc.n_ints = pool.ints_per_lane; sc.n_bytes = pool.bytes_per_lane; sc.istride = sc.bstride = 32;
     return sc;
 }
-// fast variant: DP rows in shared memory (element e of thread t at e * blockDim + t: conflict-free), trace-back bytes in
-// warp-interleaved global scratch (written once, read only by the back-trace)
-__device__ __forceinline__ DpScratch lane_scratch_smem(const DpPool &pool, int32_t *smem, int ints_per_lane) {
-    DpScratch sc = lane_scratch(pool);
-    sc.ints = smem + threadIdx.x; sc.n_ints = ints_per_lane; sc.istride = blockDim.x;
-    return sc;
-}
-
 // warp-aggregated fetch of the next work item; returns false when the list is exhausted
 __device__ __forceinline__ bool next_item(uint32_t *cursor, uint32_t n, uint32_t &idx) {
     const unsigned m = __activemask();
@@ -58,22 +51,55 @@ __global__ void sw_classify_kernel(DpView v, uint32_t *list, uint32_t *n_list) {
     if (need) list[base + __popc(m & ((1u << lane) - 1u))] = p;
 }
 
-// kSmem: rows in shared memory, items that do not fit go to `retry` (processed by the global-scratch variant)
-template <bool kSmem>
-__global__ void __launch_bounds__(kDpThreads) sw_kernel(DpView v, SwParams sp, DpPool pool, const uint32_t *list, const uint32_t *n_list,
-                                                         uint32_t *cursor, uint32_t *err, int smem_ints, uint32_t *retry, uint32_t *n_retry) {
+constexpr int kWarpsPerBlock = 8;
+constexpr size_t kWarpSlab = 256u * 1024u;       // per-warp global slab: path ops + trace-back matrix
+
+__device__ __forceinline__ WarpDp warp_scratch(const DpPool &pool, int32_t *smem, int smem_ints) {
+    const int wid = threadIdx.x >> 5;
+    WarpDp w;
+    w.sm = smem + (size_t)wid * smem_ints; w.n_ints = smem_ints;
+    w.gb = pool.bytes + ((size_t)blockIdx.x * kWarpsPerBlock + wid) * kWarpSlab; w.n_bytes = (int)kWarpSlab;
+    w.lane = threadIdx.x & 31;
+    return w;
+}
+__device__ __forceinline__ bool next_item_warp(uint32_t *cursor, uint32_t n, uint32_t &idx) {
+    uint32_t j = 0;
+    if ((threadIdx.x & 31) == 0) j = atomicAdd(cursor, 1u);
+    idx = __shfl_sync(FULL_MASK, j, 0);
+    return idx < n;
+}
+
+// mate rescue, one pair per warp; pairs whose window exceeds the shared-memory rows go to `retry`
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) sw_warp_kernel(DpView v, SwParams sp, DpPool pool, const uint32_t *list, const uint32_t *n_list,
+                                                                       uint32_t *cursor, int smem_ints, uint32_t *retry, uint32_t *n_retry) {
     extern __shared__ int32_t dp_smem[];
-    DpScratch sc = kSmem ? lane_scratch_smem(pool, dp_smem, smem_ints) : lane_scratch(pool);
+    const WarpDp w = warp_scratch(pool, dp_smem, smem_ints);
+    const uint32_t n = *n_list;
+    uint32_t j;
+    while (next_item_warp(cursor, n, j)) {
+        const uint32_t p = list[j];
+        fqb_read_t r0 = v.rows[2 * p], r1 = v.rows[2 * p + 1];
+        WarpSwCore core{w};
+        const bool ok = paired_sw_pair(v.pac, &r0, &r1, v.codes + (size_t)(2 * p) * v.lpad, v.codes + (size_t)(2 * p + 1) * v.lpad, sp, core);
+        if (w.lane == 0) {
+            if (!ok) retry[atomicAdd(n_retry, 1u)] = p;
+            else { v.rows[2 * p] = r0; v.rows[2 * p + 1] = r1; }
+        }
+        __syncwarp();
+    }
+}
+
+// one pair per lane, everything in global scratch (retry list)
+__global__ void __launch_bounds__(kDpThreads) sw_kernel(DpView v, SwParams sp, DpPool pool, const uint32_t *list, const uint32_t *n_list,
+                                                         uint32_t *cursor, uint32_t *err) {
+    DpScratch sc = lane_scratch(pool);
     const uint32_t n = *n_list;
     uint32_t j;
     while (next_item(cursor, n, j)) {
         const uint32_t p = list[j];
         fqb_read_t r0 = v.rows[2 * p], r1 = v.rows[2 * p + 1];
         bool ok = paired_sw_one(v.pac, &r0, &r1, v.codes + (size_t)(2 * p) * v.lpad, v.codes + (size_t)(2 * p + 1) * v.lpad, sp, sc);
-        if (!ok) {
-            if (kSmem) retry[atomicAdd(n_retry, 1u)] = p; else atomicExch(err, p + 1);
-            continue;
-        }
+        if (!ok) { atomicExch(err, p + 1); continue; }
         v.rows[2 * p] = r0; v.rows[2 * p + 1] = r1;
     }
 }
@@ -94,11 +120,28 @@ __global__ void refine_classify_kernel(DpView v, uint32_t *list, uint32_t *n_lis
     if (need) list[base + __popc(m & ((1u << lane) - 1u))] = r;
 }
 
-template <bool kSmem>
-__global__ void __launch_bounds__(kDpThreads) refine_kernel(DpView v, DpPool pool, const uint32_t *list, const uint32_t *n_list,
-                                                             uint32_t *cursor, uint32_t *err, int smem_ints, uint32_t *retry, uint32_t *n_retry) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) refine_warp_kernel(DpView v, DpPool pool, const uint32_t *list, const uint32_t *n_list,
+                                                                           uint32_t *cursor, int smem_ints, uint32_t *retry, uint32_t *n_retry) {
     extern __shared__ int32_t dp_smem[];
-    DpScratch sc = kSmem ? lane_scratch_smem(pool, dp_smem, smem_ints) : lane_scratch(pool);
+    const WarpDp w = warp_scratch(pool, dp_smem, smem_ints);
+    const uint32_t n = *n_list;
+    uint32_t j;
+    while (next_item_warp(cursor, n, j)) {
+        const uint32_t r = list[j];
+        fqb_read_t s = v.rows[r];
+        ReadSeq Q; Q.fwd = v.codes + (size_t)r * v.lpad; Q.len = s.len; Q.strand = s.strand;
+        const int nc = warp_refine_gapped(v.l_pac, v.pac, Q, &s.pos, (s.strand ? 1 : -1) * (s.n_gapo + s.n_gape), s.cigar, FQB_MAX_CIGAR, w);
+        if (w.lane == 0) {
+            if (nc < 0) retry[atomicAdd(n_retry, 1u)] = r;
+            else { s.n_cigar = (uint8_t)nc; s.has_cigar = 1; v.rows[r] = s; }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kDpThreads) refine_kernel(DpView v, DpPool pool, const uint32_t *list, const uint32_t *n_list,
+                                                             uint32_t *cursor, uint32_t *err) {
+    DpScratch sc = lane_scratch(pool);
     const uint32_t n = *n_list;
     uint32_t j;
     while (next_item(cursor, n, j)) {
@@ -106,10 +149,7 @@ __global__ void __launch_bounds__(kDpThreads) refine_kernel(DpView v, DpPool poo
         fqb_read_t s = v.rows[r];
         ReadSeq Q; Q.fwd = v.codes + (size_t)r * v.lpad; Q.len = s.len; Q.strand = s.strand;
         int nc = refine_gapped(v.l_pac, v.pac, Q, &s.pos, (s.strand ? 1 : -1) * (s.n_gapo + s.n_gape), s.cigar, FQB_MAX_CIGAR, sc);
-        if (nc < 0) {
-            if (kSmem) retry[atomicAdd(n_retry, 1u)] = r; else atomicExch(err, r + 1);
-            continue;
-        }
+        if (nc < 0) { atomicExch(err, r + 1); continue; }
         s.n_cigar = (uint8_t)nc; s.has_cigar = 1;
         v.rows[r] = s;
     }
@@ -128,24 +168,31 @@ __global__ void finish_kernel(DpView v) {
     v.rows[r] = s;
 }
 
+// as many warp slabs as the byte pool holds, at most four blocks per SM (pool.n_blocks = 2 per SM)
+static int warp_blocks(const DpPool &pool) {
+    const size_t pool_bytes = (size_t)pool.n_blocks * kDpThreads * pool.bytes_per_lane;
+    size_t nb = pool_bytes / (kWarpSlab * kWarpsPerBlock);
+    if (nb > (size_t)pool.n_blocks * 2) nb = (size_t)pool.n_blocks * 2;
+    return (int)(nb < 1 ? 1 : nb);
+}
+
 // ctr: [0] n_list [1] cursor [2] n_retry [3] retry cursor (device words)
 void launch_sw(const DpView &v, const SwParams &sp, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, cudaStream_t s) {
     sw_classify_kernel<<<(v.n_reads / 2 + 255) / 256, 256, 0, s>>>(v, list, ctr);
-    const size_t smem = (size_t)kSwSmemInts * kDpThreads * 4;
-    cudaFuncSetAttribute(sw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sw_kernel<true><<<pool.n_blocks, kDpThreads, smem, s>>>(v, sp, pool, list, ctr, ctr + 1, err, kSwSmemInts, retry, ctr + 2);
-    sw_kernel<false><<<pool.n_blocks, kDpThreads, 0, s>>>(v, sp, pool, retry, ctr + 2, ctr + 3, err, 0, nullptr, nullptr);
+    const int ints = 2 * kSwSmemInts;                                    // H and E rows of a <= 702-column window
+    const size_t smem = (size_t)ints * kWarpsPerBlock * 4;
+    cudaFuncSetAttribute(sw_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sw_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, sp, pool, list, ctr, ctr + 1, ints, retry, ctr + 2);
+    sw_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, sp, pool, retry, ctr + 2, ctr + 3, err);
 }
 void launch_refine(const DpView &v, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, int max_read_len, cudaStream_t s) {
     refine_classify_kernel<<<(v.n_reads + 255) / 256, 256, 0, s>>>(v, list, ctr);
-    const int ints = 6 * (max_read_len + 16 + 1);
-    int threads = (int)((220u * 1024u) / ((size_t)ints * 4)) / 32 * 32;          // as many lanes as fit 220 KB of shared memory
-    if (threads > kDpThreads) threads = kDpThreads;
-    if (threads < 32) threads = 32;
-    const size_t smem = (size_t)ints * threads * 4;
-    cudaFuncSetAttribute(refine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    refine_kernel<true><<<pool.n_blocks, threads, smem, s>>>(v, pool, list, ctr, ctr + 1, err, ints, retry, ctr + 2);
-    refine_kernel<false><<<pool.n_blocks, kDpThreads, 0, s>>>(v, pool, retry, ctr + 2, ctr + 3, err, 0, nullptr, nullptr);
+    int ints = 6 * (max_read_len + 16 + 1);                              // M/I/D rows, current and previous
+    if ((size_t)ints * kWarpsPerBlock * 4 > 200u * 1024u) ints = (int)(200u * 1024u / (kWarpsPerBlock * 4));
+    const size_t smem = (size_t)ints * kWarpsPerBlock * 4;
+    cudaFuncSetAttribute(refine_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    refine_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, pool, list, ctr, ctr + 1, ints, retry, ctr + 2);
+    refine_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, pool, retry, ctr + 2, ctr + 3, err);
     finish_kernel<<<(v.n_reads + 255) / 256, 256, 0, s>>>(v);
 }
 
