@@ -35,8 +35,8 @@ namespace fqb {
 
 // ---------------------------------------------------------------------------
 // FM index, re-laid for the GPU: one 32-byte block (= one L2 sector) per 64 BWT
-// symbols: uint4 {cumulative A,C,G,T counts before the block} + uint4 {64 bases,
-// 2 bits each, first base in the top bits of .x}.  The reference keeps 48-byte
+// symbols: uint4 {cumulative A,C,G,T counts before the block} + uint4 {the 64 bases as
+// two bit planes, high bits in .x:.y and low bits in .z:.w, first base in the top bit}.  The reference keeps 48-byte
 // blocks per 128 symbols (libbwa/bwt.h:34,56-62); values returned are identical.
 struct DevBwt {
     const uint4 *blocks;      // 2 x uint4 per block
@@ -54,17 +54,13 @@ FQB_HD uint32_t pick4(const uint32_t v[4], uint32_t c) {
     return (c & 2) ? hi : lo;
 }
 
-// counts of A,C,G,T among stored symbols [0, k] (after the primary shift); bwt_occ4
+// counts of A,C,G,T among stored symbols [0, k] (after the primary shift); bwt_occ4.
+// bases = two 64-bit planes (x:y = high bits of the 64 symbols, z:w = low bits, first symbol in the top bit)
 FQB_HD void occ4_block(const uint4 cnt, const uint4 bases, uint32_t n /*1..64 symbols of this block*/, uint32_t out[4]) {
-    const uint64_t HI = 0xAAAAAAAAAAAAAAAAull;
-    uint64_t w0 = ((uint64_t)bases.x << 32) | bases.y, w1 = ((uint64_t)bases.z << 32) | bases.w;
-    uint32_t n0 = n < 32 ? n : 32, n1 = n - n0;
-    uint64_t m0 = (n0 == 32 ? ~0ull : ~(~0ull >> (2 * n0))) & HI;
-    uint64_t m1 = (n1 == 0 ? 0ull : (n1 == 32 ? ~0ull : ~(~0ull >> (2 * n1)))) & HI;
-    uint64_t h0 = w0 & m0, l0 = (w0 << 1) & m0, h1 = w1 & m1, l1 = (w1 << 1) & m1;
-    uint32_t H = FQB_POPCLL(h0) + FQB_POPCLL(h1);
-    uint32_t L = FQB_POPCLL(l0) + FQB_POPCLL(l1);
-    uint32_t T = FQB_POPCLL(h0 & l0) + FQB_POPCLL(h1 & l1);
+    const uint64_t hi = ((uint64_t)bases.x << 32) | bases.y, lo = ((uint64_t)bases.z << 32) | bases.w;
+    const uint64_t m = ~0ull << (64u - n);
+    const uint64_t h = hi & m, l = lo & m;
+    const uint32_t H = FQB_POPCLL(h), L = FQB_POPCLL(l), T = FQB_POPCLL(h & l);
     out[3] = cnt.w + T;
     out[2] = cnt.z + H - T;
     out[1] = cnt.y + L - T;
@@ -111,8 +107,8 @@ FQB_HD uint32_t sa_lookup(const DevBwt &b, uint32_t k) {
         const uint4 *p = b.blocks + 2 * (size_t)(kk >> 6);
         uint4 c = FQB_LDG4(p), w = FQB_LDG4(p + 1);
         uint32_t j = kk & 63;
-        uint32_t word = j < 16 ? w.x : j < 32 ? w.y : j < 48 ? w.z : w.w;
-        uint32_t sym = (word >> ((15u - (j & 15u)) << 1)) & 3u;
+        const uint32_t sh = 31u - (j & 31u);
+        uint32_t sym = (((j < 32 ? w.x : w.y) >> sh) & 1u) << 1 | (((j < 32 ? w.z : w.w) >> sh) & 1u);
         uint32_t cnt[4];
         occ4_block(c, w, j + 1, cnt);               // occ(k, sym): same block as the symbol itself
         k = pick4(b.L2, sym) + pick4(cnt, sym);
@@ -250,6 +246,33 @@ struct SearchLane {
         return s;
     }
     FQB_HD uint32_t bucket_head(int sc) { return bucket_set(sc) ? (uint32_t)head(sc) : kNoSlot; }
+    // All children of one expansion that land in the same score bucket, pushed in order with ONE allocation
+    // (bump arena) -- slot numbers and chaining are exactly those of N consecutive gap_push calls.
+    template <int N>
+    FQB_HD void emit_group(int sc, const bool (&v)[N], const uint32_t (&ek)[N], const uint32_t (&el)[N], const uint32_t (&em)[N], const uint32_t (&ed)[N]) {
+        if (kFreeList) {
+            const uint32_t old = bucket_head(sc);
+            uint32_t last = old;
+            for (int j = 0; j < N; ++j) if (v[j]) last = emit(ek[j], el[j], em[j], (int)ed[j], last);
+            if (last != old) publish(sc, last);
+            return;
+        }
+        int cnt = 0;
+        _Pragma("unroll")
+        for (int j = 0; j < N; ++j) cnt += v[j] ? 1 : 0;
+        if (cnt == 0) return;
+        n_entries += cnt;
+#ifdef FQB_LANE_STATS
+        st_push += cnt;
+#endif
+        if (top + (uint32_t)cnt > arena_cap) { overflow = true; return; }
+        uint32_t prev = bucket_head(sc), s = top;
+        _Pragma("unroll")
+        for (int j = 0; j < N; ++j)
+            if (v[j]) { arena[s] = make_uint4(ek[j], el[j], em[j], ed[j] << 22 | prev); prev = s; ++s; }
+        top = s;
+        publish(sc, prev);
+    }
     FQB_HD void publish(int sc, uint32_t last) {
         head(sc) = (HeadT)last;
         if (sc < 64) mask0 |= 1ull << sc; else mask1 |= 1ull << (sc - 64);
@@ -340,30 +363,56 @@ struct SearchLane {
             if (n_entries == 0 || n_entries > opt->max_entries) return kLaneDone;
             pop();
             if (!(opt->mode & kModeNonStop) && score3(n_mm, n_gapo, n_gape) > best_score + opt->s_mm) return kLaneDone;
-            int m = diffs_left();
-            if (m < 0) { FQB_STAT(st_skip); return kLaneRunning; }
+            if (diffs_left() < 0) { FQB_STAT(st_skip); return kLaneRunning; }
             if (i == 0) { FQB_STAT(st_hit); return on_hit(); }
-            if (m < width_bid(wa()[i - 1])) { FQB_STAT(st_skip); return kLaneRunning; }
+        }
+        // ---- every load this step can need, issued together (one memory round trip instead of a chain of them):
+        // the two rank blocks, the width bounds of positions i-1 and i-2, their seed counterparts, and two read symbols
+        const DevBwt &b = a ? bwt[0] : bwt[1];
+        const bool no_k = k == 0;                       // bwt_occ4(k - 1) with k - 1 == (bwtint_t)-1
+        const uint32_t kk_ = no_k ? 0 : (k - 1) - ((k - 1) >= b.primary), ll_ = l - (l >= b.primary);
+        const uint4 *pk = b.blocks + 2 * (size_t)(kk_ >> 6), *pl = b.blocks + 2 * (size_t)(ll_ >> 6);
+        const uint4 bk_c = FQB_LDG4(pk), bk_w = FQB_LDG4(pk + 1);
+        const bool same_blk = (kk_ >> 6) == (ll_ >> 6);
+        uint4 bl_c = bk_c, bl_w = bk_w;
+        if (!same_blk) { bl_c = FQB_LDG4(pl); bl_w = FQB_LDG4(pl + 1); }
+        const uint32_t c_here = fwd[len - i];                           // read_sym(i - 1), before complementing
+        const uint32_t c_next = i >= 2 ? fwd[len - i + 1] : 4u;         // read_sym(i - 2)
+        uint32_t w_hi = 0, w_lo = 0, s_hi = 0, s_lo = 0;
+        const int ii = (i - 1) - (len - opt->seed_len);
+        const bool seed_chk = sw[0] && ii > 0;
+        if (mode != kModeExact) {
+            const uint32_t *wp = wa();
+            w_hi = wp[i - 1];
+            if (i >= 2) w_lo = wp[i - 2];
+            if (seed_chk) { const uint32_t *sp = swa(); s_lo = sp[ii - 1]; s_hi = sp[ii]; }
+        }
+        const uint32_t sym_here = (a && c_here < 4) ? 3 - c_here : c_here;
+        const uint32_t sym_next = (a && c_next < 4) ? 3 - c_next : c_next;
+
+        if (mode == kModePop) {
+            const int m = diffs_left();
+            if (m < width_bid(w_hi)) { FQB_STAT(st_skip); return kLaneRunning; }
             if (m == 0 && (state == kStateM || (opt->mode & kModeGapE) || n_gape == opt->max_gape)) {
-                if (read_sym(fwd, len, a, i - 1) > 3) return kLaneRunning;   // bwt_match_exact_alt: N never matches
+                if (sym_here > 3) { return kLaneRunning; }   // bwt_match_exact_alt: N never matches
                 mode = kModeExact;
             } else mode = kModeExpand;
         }
-        const DevBwt &b = a ? bwt[0] : bwt[1];
         uint32_t ck[4], cl[4];
-        occ4_pair(b, k - 1, l, ck, cl);
+        if (no_k) ck[0] = ck[1] = ck[2] = ck[3] = 0;
+        else occ4_block(bk_c, bk_w, (kk_ & 63) + 1, ck);
+        occ4_block(bl_c, bl_w, (ll_ & 63) + 1, cl);
         ++n_occ;
-        n_blk += ref_block_touches(b, k - 1, l);
+        n_blk += 1u + (uint32_t)(no_k || (kk_ >> 7) != (ll_ >> 7));     // == ref_block_touches(b, k - 1, l)
 
         if (mode == kModeExact) FQB_STAT(st_exact); else FQB_STAT(st_expand);
         if (mode == kModeExact) {                   // one step of bwt_match_exact_alt (libbwa/bwt.c:102-117)
-            uint32_t c = read_sym(fwd, len, a, i - 1);
-            k = pick4(b.L2, c) + pick4(ck, c) + 1;
-            l = pick4(b.L2, c) + pick4(cl, c);
+            k = b.L2[sym_here] + pick4(ck, sym_here) + 1;
+            l = b.L2[sym_here] + pick4(cl, sym_here);
             --i;
             if (k > l) { mode = kModePop; return kLaneRunning; }
             if (i == 0) { mode = kModePop; return on_hit(); }
-            if (read_sym(fwd, len, a, i - 1) > 3) mode = kModePop;
+            if (sym_next > 3) { mode = kModePop; }
             return kLaneRunning;
         }
 
@@ -375,12 +424,11 @@ struct SearchLane {
         uint32_t occ = l - k + 1;
         bool allow_diff = true, allow_M = true;
         if (i > 0) {
-            uint32_t wl = wa()[i - 1], wh = wa()[i];
+            const uint32_t wl = w_lo, wh = w_hi;
             if (width_bid(wl) > m - 1) allow_diff = false;
             else if (width_bid(wl) == m - 1 && width_bid(wh) == m - 1 && width_w(wl) == width_w(wh)) allow_M = false;
-            int ii = i - (len - opt->seed_len);
-            if (sw[0] && ii > 0) {
-                uint32_t sl = swa()[ii - 1], sh = swa()[ii];
+            if (seed_chk) {
+                const uint32_t sl = s_lo, sh = s_hi;
                 if (width_bid(sl) > m_seed - 1) allow_diff = false;
                 else if (width_bid(sl) == m_seed - 1 && width_bid(sh) == m_seed - 1 && width_w(sl) == width_w(sh)) allow_M = false;
             }
@@ -403,43 +451,33 @@ struct SearchLane {
         }
         if (do_i || do_d) {
             FQB_STAT(st_gapok);
-            const int sc = score3(n_mm, go2, ge2);
-            const uint32_t old = bucket_head(sc);
-            uint32_t last = old;
-            if (do_i) last = emit(k, l, pack_meta(i, a, kStateI, n_mm, go2, ge2), i, last);
-            if (do_d) {
-                const uint32_t meta_d = pack_meta(i + 1, a, kStateD, n_mm, go2, ge2);
-                _Pragma("unroll")
-                for (int j = 0; j < 4; ++j)
-                    if (kk[j] <= ll[j]) last = emit(kk[j], ll[j], meta_d, i + 1, last);
-            }
-            if (last != old) publish(sc, last);
+            const uint32_t meta_i = pack_meta(i, a, kStateI, n_mm, go2, ge2), meta_d = pack_meta(i + 1, a, kStateD, n_mm, go2, ge2);
+            const bool v[5] = {do_i, do_d && kk[0] <= ll[0], do_d && kk[1] <= ll[1], do_d && kk[2] <= ll[2], do_d && kk[3] <= ll[3]};
+            const uint32_t ek[5] = {k, kk[0], kk[1], kk[2], kk[3]}, el[5] = {l, ll[0], ll[1], ll[2], ll[3]};
+            const uint32_t em[5] = {meta_i, meta_d, meta_d, meta_d, meta_d};
+            const uint32_t ed[5] = {(uint32_t)i, (uint32_t)i + 1, (uint32_t)i + 1, (uint32_t)i + 1, (uint32_t)i + 1};
+            emit_group<5>(score3(n_mm, go2, ge2), v, ek, el, em, ed);
         }
-        // mismatch children (one bucket), exact child last
-        const uint32_t s = read_sym(fwd, len, a, i);
+        // mismatch children (one bucket) in the order (s+1)&3, (s+2)&3, (s+3)&3 [, s&3 when s is N]; the exact child is kept
+        const uint32_t s = sym_here;
         bool keep = false;
         uint32_t nk = 0, nl = 0;
-        if (allow_diff && allow_M) {
-            const int sc = score3(n_mm + 1, n_gapo, n_gape);
-            const uint32_t meta_m = pack_meta(i, a, kStateM, n_mm + 1, n_gapo, n_gape);
-            const uint32_t old = bucket_head(sc);
-            uint32_t last = old;
+        {
+            uint32_t ck4[4], cl4[4];
             _Pragma("unroll")
-            for (int j = 1; j <= 4; ++j) {
-                const uint32_t c = (s + j) & 3;
-                const uint32_t ck_ = pick4(kk, c), cl_ = pick4(ll, c);
-                if (ck_ > cl_) continue;
-                if (j != 4 || s > 3) last = emit(ck_, cl_, meta_m, i, last);
-                else { keep = true; nk = ck_; nl = cl_; }
+            for (int j = 1; j <= 4; ++j) { const uint32_t c = (s + j) & 3; ck4[j - 1] = pick4(kk, c); cl4[j - 1] = pick4(ll, c); }
+            if (allow_diff && allow_M) {
+                const uint32_t meta_m = pack_meta(i, a, kStateM, n_mm + 1, n_gapo, n_gape);
+                const bool v[4] = {ck4[0] <= cl4[0], ck4[1] <= cl4[1], ck4[2] <= cl4[2], s > 3 && ck4[3] <= cl4[3]};
+                const uint32_t em[4] = {meta_m, meta_m, meta_m, meta_m}, ed[4] = {(uint32_t)i, (uint32_t)i, (uint32_t)i, (uint32_t)i};
+                emit_group<4>(score3(n_mm + 1, n_gapo, n_gape), v, ck4, cl4, em, ed);
             }
-            if (last != old) publish(sc, last);
-        } else if (s < 4) {
-            const uint32_t ck_ = pick4(kk, s), cl_ = pick4(ll, s);
-            if (ck_ <= cl_) { keep = true; nk = ck_; nl = cl_; }
+            if (s < 4 && ck4[3] <= cl4[3]) { keep = true; nk = ck4[3]; nl = cl4[3]; }
         }
         if (keep) {      // exact child: pushed last into the parent's own bucket, hence popped next;
             k = nk; l = nl; state = kStateM; have_cur = true; ++n_entries;   // inherits last_diff_pos
         }
+       
         return overflow ? kLaneOverflow : kLaneRunning;
     }
 };

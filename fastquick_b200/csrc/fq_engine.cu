@@ -69,6 +69,7 @@ struct fqb_handle {
     int32_t *d_naln = nullptr;
     uint32_t *d_overflow = nullptr;
     uint32_t *d_ctrs = nullptr;          // [0] n_work [1] cursor [2] n_overflow [3] cursor2
+    uint32_t *d_work_sorted = nullptr, *d_order_bins = nullptr;   // search queue, longest first
     unsigned long long *d_counters = nullptr;
     // search infrastructure
     int n_blocks16 = 0;
@@ -120,7 +121,7 @@ static void free_batch(fqb_handle *h) {
     for (auto &p : h->d_in) { cudaFree(p); p = nullptr; }
     for (auto &p : h->d_lens_in) { cudaFree(p); p = nullptr; }
     cudaFree(h->bv.codes); cudaFree(h->bv.qual); cudaFree(h->bv.len); cudaFree(h->bv.full_len);
-    cudaFree(h->bv.filtered); cudaFree(h->bv.n_ambig); cudaFree(h->bv.work);
+    cudaFree(h->bv.filtered); cudaFree(h->bv.n_ambig); cudaFree(h->bv.work); cudaFree(h->d_work_sorted); h->d_work_sorted = nullptr;
     cudaFree(h->wv.w); cudaFree(h->wv.sw);
     cudaFree(h->d_aln); cudaFree(h->d_naln); cudaFree(h->d_overflow); cudaFree(h->d_spill_slot);
     cudaFree(h->d_rows); cudaFree(h->pesc.packed); cudaFree(h->pesc.scanned); cudaFree(h->pesc.scan_tmp); cudaFree(h->pesc.cum_extra);
@@ -146,6 +147,8 @@ static int ensure_batch(fqb_handle *h, int n_reads, int stride) {
     CU_CHECK(cudaMalloc(&h->bv.filtered, (size_t)cap));
     CU_CHECK(cudaMalloc(&h->bv.n_ambig, (size_t)cap));
     CU_CHECK(cudaMalloc(&h->bv.work, (size_t)cap * 4));
+    CU_CHECK(cudaMalloc(&h->d_work_sorted, (size_t)cap * 4));
+    if (!h->d_order_bins) CU_CHECK(cudaMalloc(&h->d_order_bins, 32 * 4));
     h->wv.wstride = stride + 1;
     h->wv.sstride = h->gopt.seed_len + 1;
     CU_CHECK(cudaMalloc(&h->wv.w, (size_t)cap * 2 * h->wv.wstride * 4));
@@ -250,8 +253,8 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     h->last_ii.avg = h->last_ii.std = -1.0; h->last_ii.ap_prior = 0; h->last_ii.low = h->last_ii.high = h->last_ii.high_bayesian = h->last_ii.pad_ = 0;
     h->cur_ii = h->last_ii;
     CU_CHECK_H(cudaMalloc(&h->d_dpctr, 12 * 4));
-    CU_CHECK_H(cudaMalloc(&h->d_counters, 4 * 8));
-    CU_CHECK_H(cudaMemset(h->d_counters, 0, 4 * 8));
+    CU_CHECK_H(cudaMalloc(&h->d_counters, 16 * 8));
+    CU_CHECK_H(cudaMemset(h->d_counters, 0, 16 * 8));
     if (h->gopt.kmer_thresh != 0) {     // 6 x 512 MiB bitmaps, streamed from disk (BwtIndexer::ReadRollHashTable)
         const size_t total = kRollTableBytes * kNumRollTables;
         CU_CHECK_H(cudaMalloc(&h->d_roll, total));
@@ -282,7 +285,7 @@ void fqb_destroy(fqb_handle *h) {
     cudaSetDevice(h->device);
     free_batch(h);
     for (int s = 0; s < 2; ++s) { cudaFree(h->d_blocks[s]); cudaFree(h->d_sa[s]); }
-    cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_ctrs); cudaFree(h->d_counters);
+    cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_ctrs); cudaFree(h->d_order_bins); cudaFree(h->d_counters);
     cudaFree(h->d_arena); cudaFree(h->d_arena_mid); cudaFree(h->d_arena_big); cudaFree(h->d_aln_big);
     cudaFree(h->pesc.totals); cudaFree(h->pesc.err_flag); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch); cudaFree(h->dp_pool.ints); cudaFree(h->dp_pool.bytes); cudaFree(h->d_dpctr);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -349,6 +352,11 @@ int fqb_stage_align(fqb_handle *h) {
     sp.bwt[0] = h->dbwt[0]; sp.bwt[1] = h->dbwt[1];
     sp.opt = h->sopt; sp.maxdiff = h->d_maxdiff; sp.seed_len_opt = h->gopt.seed_len;
     sp.work = h->bv.work; sp.n_work = h->d_ctrs; sp.cursor = h->d_ctrs + 1;
+    if (!getenv("FQB_NO_ORDER")) {
+        launch_order(h->bv, h->wv, h->bv.work, h->bv.n_work, h->n_reads, h->d_order_bins, h->d_work_sorted, st);
+        h->n_launches += 2;
+        sp.work = h->d_work_sorted;
+    }
     sp.arena = h->d_arena; sp.arena_cap = h->arena_fast;
     sp.aln = h->d_aln; sp.aln_cap = kAlnCapFast; sp.n_aln = h->d_naln; sp.aln_row = nullptr;
     sp.overflow = h->d_overflow; sp.n_overflow = h->d_ctrs + 2;
@@ -817,6 +825,13 @@ int fqb_stage_counters(fqb_handle *h, uint64_t *out4) {
     unsigned long long c[3];
     uint32_t ov = 0;
     CU_CHECK(cudaMemcpy(c, h->d_counters, 24, cudaMemcpyDeviceToHost));
+    if (getenv("FQB_KSTATS_PRINT")) {
+        unsigned long long k[16];
+        cudaMemcpy(k, h->d_counters, 16 * 8, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "kstats iter %llu step %llu exh %llu hist", k[4], k[5], k[6]);
+        for (int q = 0; q < 9; ++q) fprintf(stderr, " %llu", k[7 + q]);
+        fprintf(stderr, "\n");
+    }
     CU_CHECK(cudaMemcpy(&ov, h->d_ctrs + 2, 4, cudaMemcpyDeviceToHost));
     out4[0] = c[0]; out4[1] = c[1]; out4[2] = c[2]; out4[3] = ov;
     return FQB_OK;

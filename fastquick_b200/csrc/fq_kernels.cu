@@ -4,6 +4,7 @@
 //   search_kernel  a4+a5: bwt_match_gap, one read per lane, persistent lanes with a
 //                         warp-aggregated work queue; score-bucket heads in shared
 //                         memory, entry arena in (L2-backed) global memory
+#include <cstdlib>
 #include "fq_kernels.cuh"
 
 #include <climits>
@@ -174,6 +175,55 @@ void launch_width(const BatchView &b, const WidthView &wv, const DevBwt bwt[2], 
 }
 
 // ---------------------------------------------------------------------------
+// Longest-first ordering of the search queue.  The cost of bwt_match_gap grows steeply with the number of
+// differences a read needs; bwt_cal_width's total lower bound (bid of the last position, the smaller of the
+// two strands) is known before the search starts, so the queue is bucket-sorted by it, descending.  Reads are
+// independent, so the order changes nothing but the load balance of the persistent lanes.
+constexpr int kOrderBins = 16;
+__device__ __forceinline__ int order_key(const BatchView &b, const WidthView &wv, uint32_t r) {
+    const int len = b.len[r];
+    if (len < 1) return 0;
+    const int b0 = width_bid(wv.w[((size_t)r * 2) * wv.wstride + len - 1]), b1 = width_bid(wv.w[((size_t)r * 2 + 1) * wv.wstride + len - 1]);
+    const int k = b0 < b1 ? b0 : b1;
+    return k < kOrderBins ? k : kOrderBins - 1;
+}
+__global__ void __launch_bounds__(256) order_hist_kernel(BatchView b, WidthView wv, const uint32_t *work, const uint32_t *n_work, uint32_t *bins) {
+    __shared__ uint32_t sh[kOrderBins];
+    if (threadIdx.x < kOrderBins) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < *n_work) atomicAdd(&sh[order_key(b, wv, work[idx])], 1u);
+    __syncthreads();
+    if (threadIdx.x < kOrderBins && sh[threadIdx.x]) atomicAdd(&bins[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) order_scatter_kernel(BatchView b, WidthView wv, const uint32_t *work, const uint32_t *n_work,
+                                                             const uint32_t *bins, uint32_t *fill, uint32_t *out) {
+    __shared__ uint32_t sh[kOrderBins], base[kOrderBins];
+    if (threadIdx.x < kOrderBins) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = idx < *n_work;
+    uint32_t r = 0, rank = 0;
+    int key = 0;
+    if (in) { r = work[idx]; key = order_key(b, wv, r); rank = atomicAdd(&sh[key], 1u); }
+    __syncthreads();
+    if (threadIdx.x < kOrderBins) {
+        uint32_t start = 0;
+        for (int k = kOrderBins - 1; k > (int)threadIdx.x; --k) start += bins[k];       // heavier bins first
+        base[threadIdx.x] = start + (sh[threadIdx.x] ? atomicAdd(&fill[threadIdx.x], sh[threadIdx.x]) : 0u);
+    }
+    __syncthreads();
+    if (in) out[base[key] + rank] = r;
+}
+void launch_order(const BatchView &b, const WidthView &wv, const uint32_t *work, const uint32_t *n_work, int max_work,
+                  uint32_t *bins /* 2 x 16 words, zeroed here */, uint32_t *out, cudaStream_t s) {
+    cudaMemsetAsync(bins, 0, 2 * kOrderBins * 4, s);
+    const int blocks = (max_work + 255) / 256 < 1 ? 1 : (max_work + 255) / 256;
+    order_hist_kernel<<<blocks, 256, 0, s>>>(b, wv, work, n_work, bins);
+    order_scatter_kernel<<<blocks, 256, 0, s>>>(b, wv, work, n_work, bins, bins + kOrderBins, out);
+}
+
+// ---------------------------------------------------------------------------
 // gap_shadow (libbwa/bwtgap.c:81-91) for every lane of the warp that just recorded a hit, 32 width
 // entries at a time; the running "++j" of the reference becomes a ballot prefix count.
 template <typename Lane>
@@ -205,14 +255,14 @@ __device__ __forceinline__ void warp_shadow(Lane &lane, bool has_hit, int lane_i
     __syncwarp();
 }
 
-template <typename HeadT, bool kFreeList>
-__global__ void __launch_bounds__(kSearchThreads) search_kernel(BatchView b, WidthView wv, SearchParams p) {
+template <typename HeadT, bool kFreeList, int kMinBlocks = 5>
+__global__ void __launch_bounds__(kSearchThreads, kMinBlocks) search_kernel(const __grid_constant__ BatchView b, const __grid_constant__ WidthView wv,
+                                                                            const __grid_constant__ SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ DevBwt s_bwt[2];
-    __shared__ SearchOpt s_opt;
     HeadT *heads = reinterpret_cast<HeadT *>(smem_raw);
-    if (threadIdx.x == 0) { s_bwt[0] = p.bwt[0]; s_bwt[1] = p.bwt[1]; s_opt = p.opt; }
-    __syncthreads();
+    // search options and index descriptors are read straight from the kernel-parameter constant bank
+    const DevBwt *s_bwt = p.bwt;
+    const SearchOpt &s_opt = p.opt;
 
     const int lane_id = threadIdx.x & 31;
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -227,6 +277,9 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(BatchView b, Wid
     bool active = false, exhausted = false;
     uint32_t r = 0;
     unsigned long long pops = 0, occs = 0, blks = 0;
+#ifdef FQB_KSTATS
+    unsigned long long ks_iter = 0, ks_step = 0, ks_exh = 0; unsigned ks_hist[9] = {0,0,0,0,0,0,0,0,0};
+#endif
 
     for (;;) {
         LaneStatus st = kLaneRunning;
@@ -255,6 +308,10 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(BatchView b, Wid
             }
         }
         if (__all_sync(FULL_MASK, exhausted && !active)) break;
+#ifdef FQB_KSTATS
+        { unsigned m1 = __ballot_sync(FULL_MASK, active && st == kLaneRunning), m2 = __ballot_sync(FULL_MASK, exhausted && !active);
+          if (lane_id == 0) { ks_iter++; ks_step += __popc(m1); ks_exh += __popc(m2); ks_hist[__popc(m1) >> 2]++; } }
+#endif
         if (active && st == kLaneRunning) st = lane.step();
         warp_shadow(lane, active && st == kLaneHit, lane_id);
         if (active && (st == kLaneDone || st == kLaneOverflow)) {
@@ -271,27 +328,42 @@ __global__ void __launch_bounds__(kSearchThreads) search_kernel(BatchView b, Wid
         blks += __shfl_xor_sync(FULL_MASK, blks, d);
     }
     if (lane_id == 0 && p.counters) { atomicAdd(p.counters, pops); atomicAdd(p.counters + 1, occs); atomicAdd(p.counters + 2, blks); }
+#ifdef FQB_KSTATS
+    if (lane_id == 0 && p.counters) { atomicAdd(p.counters + 4, ks_iter); atomicAdd(p.counters + 5, ks_step); atomicAdd(p.counters + 6, ks_exh);
+        for (int q = 0; q < 9; ++q) atomicAdd(p.counters + 7 + q, (unsigned long long)ks_hist[q]); }
+#endif
+}
+
+static int search_occ_variant() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("FQB_SEARCH_OCC"); v = e ? atoi(e) : 1; }
+    return v;
 }
 
 int search_grid_blocks(int n_buckets, bool heads16, int device) {
     int per_sm = 0, n_sm = 148;
     size_t smem = (size_t)n_buckets * kSearchThreads * (heads16 ? 2 : 4);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-    if (heads16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint16_t, false>, kSearchThreads, smem);
+    if (heads16 && search_occ_variant() == 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint16_t, false, 6>, kSearchThreads, smem);
+    else if (heads16 && search_occ_variant() == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint16_t, false, 8>, kSearchThreads, smem);
+    else if (heads16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint16_t, false>, kSearchThreads, smem);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint32_t, true>, kSearchThreads, smem);
     if (per_sm < 1) per_sm = 1;
+    if (const char *e = getenv("FQB_SEARCH_BLOCKS_PER_SM")) { int c = atoi(e); if (c >= 1 && c < per_sm) per_sm = c; }
     return n_sm * per_sm;
 }
 
-template <typename HeadT, bool kFreeList>
+template <typename HeadT, bool kFreeList, int kMinBlocks = 5>
 static void launch_search_t(const BatchView &b, const WidthView &wv, const SearchParams &p, int n_blocks, cudaStream_t s) {
     size_t smem = (size_t)p.opt.n_buckets * kSearchThreads * sizeof(HeadT);
-    cudaFuncSetAttribute(search_kernel<HeadT, kFreeList>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    search_kernel<HeadT, kFreeList><<<n_blocks, kSearchThreads, smem, s>>>(b, wv, p);
+    cudaFuncSetAttribute(search_kernel<HeadT, kFreeList, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    search_kernel<HeadT, kFreeList, kMinBlocks><<<n_blocks, kSearchThreads, smem, s>>>(b, wv, p);
 }
 
 void launch_search(const BatchView &b, const WidthView &wv, const SearchParams &p, bool heads16, bool free_list, int n_blocks, cudaStream_t s) {
-    if (heads16 && !free_list) launch_search_t<uint16_t, false>(b, wv, p, n_blocks, s);
+    if (heads16 && !free_list && search_occ_variant() == 6) launch_search_t<uint16_t, false, 6>(b, wv, p, n_blocks, s);
+    else if (heads16 && !free_list && search_occ_variant() == 8) launch_search_t<uint16_t, false, 8>(b, wv, p, n_blocks, s);
+    else if (heads16 && !free_list) launch_search_t<uint16_t, false>(b, wv, p, n_blocks, s);
     else if (heads16) launch_search_t<uint16_t, true>(b, wv, p, n_blocks, s);
     else launch_search_t<uint32_t, true>(b, wv, p, n_blocks, s);
 }

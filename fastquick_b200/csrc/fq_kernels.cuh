@@ -54,6 +54,8 @@ struct SearchParams {
 };
 
 void launch_prep(const BatchView &b, const PrepParams &p, cudaStream_t s);
+void launch_order(const BatchView &b, const WidthView &wv, const uint32_t *work, const uint32_t *n_work, int max_work,
+                  uint32_t *bins, uint32_t *out, cudaStream_t s);
 void launch_width(const BatchView &b, const WidthView &wv, const DevBwt bwt[2], int seed_len, const uint32_t *work,
                   const uint32_t *n_work, int max_work, unsigned long long *counters, cudaStream_t s);
 // returns the number of thread blocks launched (persistent grid); heads16 selects the 16-bit head table

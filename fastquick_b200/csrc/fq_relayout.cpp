@@ -16,7 +16,9 @@ void relayout_bwt(const HostBwt &b, std::vector<Block32> &out) {
             // stored symbol `pos` in the reference layout: word (pos/128)*12 + 4 + (pos%128)/16
             uint32_t word = b.bwt[(size_t)(pos / 128) * 12 + 4 + (pos % 128) / 16];
             uint32_t sym = (word >> ((15u - (pos & 15u)) << 1)) & 3u;
-            o.bases[j >> 4] |= sym << ((15u - (j & 15u)) << 1);
+            // two bit planes of 64 bits each: bases[0..1] = high bits, bases[2..3] = low bits, symbol j at bit 31 - (j & 31)
+            o.bases[(j >> 5)] |= (sym >> 1) << (31u - (j & 31u));
+            o.bases[2 + (j >> 5)] |= (sym & 1u) << (31u - (j & 31u));
             ++run[sym];
         }
     }

@@ -101,6 +101,18 @@ int emul_align(void *h, const fqb_gap_opt_t *gopt, int n, int stride, const uint
 }
 
 
+// bwt_cal_width's total lower bound per read and strand (the search queue is ordered by the smaller one)
+extern "C" int emul_width_bid(void *h, int n, int stride, const uint8_t *fwd, const int32_t *lens, int32_t *bid2) {
+    Emul *e = (Emul *)h;
+    std::vector<uint32_t> w(FQB_MAX_READ_LEN + 2);
+    for (int r = 0; r < n; ++r)
+        for (int a = 0; a < 2; ++a) {
+            cal_width(e->bwt[a], fwd + (size_t)r * stride, lens[r], a, 0, lens[r], w.data());
+            bid2[2 * r + a] = width_bid(w[lens[r] - 1]);
+        }
+    return 0;
+}
+
 // Paired-end resolution with the SAME decomposition the kernels use (provisional draw counts -> prefix sum ->
 // sequential pass over multi-interval reads -> per-read jump-ahead; histogram -> host infer_isize -> pair_one).
 int emul_pe_batch(void *h, const fqb_gap_opt_t *gopt, const fqb_pe_opt_t *popt, int n_pairs, const int32_t *len,
