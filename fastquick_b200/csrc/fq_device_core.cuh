@@ -295,7 +295,13 @@ struct SearchLane {
         uint4 e = arena[s];
         uint32_t prev = e.w & kNoSlot;
         if (prev == kNoSlot) { if (b < 64) mask0 &= ~(1ull << b); else mask1 &= ~(1ull << (b - 64)); }
-        else head(b) = (HeadT)prev;
+        else {
+            head(b) = (HeadT)prev;
+#if defined(__CUDA_ARCH__) && defined(FQB_POP_PREFETCH)
+            // the next pop from this bucket follows the chain: start pulling it towards the SM now (a whole step early)
+            asm volatile(FQB_POP_PREFETCH " [%0];" ::"l"(arena + prev));
+#endif
+        }
         release_slot(s);
         k = e.x; l = e.y;
         i = e.z & 1023; a = (e.z >> 10) & 1; state = (e.z >> 11) & 3;
