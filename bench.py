@@ -271,6 +271,9 @@ def main_gpu(args):
         # the public per-batch calls: pinned host FASTQ arrays in, per-read result rows out, statistics accumulated
         for s in range(first_step, first_step + k):
             b = host[s]
+            if s + 1 < first_step + k:                       # upload of the next batch overlaps this batch's kernels
+                nb = host[s + 1]
+                assert lib.fqb_prefetch_pairs(h, n_pairs, READ_LEN, ptr(nb[0]), ptr(nb[1]), None, ptr(nb[2]), ptr(nb[3]), None) == 0, lib.fqb_last_error()
             rc = lib.fqb_align_pairs(h, n_pairs, READ_LEN, ptr(b[0]), ptr(b[1]), None, ptr(b[2]), ptr(b[3]), None,
                                      C.c_void_p(rows_host[0].data_ptr()), C.c_void_p(rows_host[1].data_ptr()), C.byref(ii_host))
             assert rc == 0, lib.fqb_last_error()

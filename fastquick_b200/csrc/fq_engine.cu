@@ -61,8 +61,17 @@ struct fqb_handle {
     // batch buffers
     int cap_reads = 0, lpad = 0, stride_cap = 0;
     int n_reads = 0, stride = 0;
-    uint8_t *d_in[4] = {nullptr, nullptr, nullptr, nullptr};   // bases1, quals1, bases2, quals2 (staging for host input)
-    int32_t *d_lens_in[2] = {nullptr, nullptr};
+    // staging for host input, double-buffered: bases1, quals1, bases2, quals2 (+ lengths) of the batch being
+    // processed and of the batch fqb_prefetch_pairs is uploading on the copy stream meanwhile
+    uint8_t *d_in[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    int32_t *d_lens_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr};      // upload of set s complete
+    cudaEvent_t ev_free[2] = {nullptr, nullptr};    // prep_kernel has consumed set s
+    int cur_set = 0;                                // set the resident batch was loaded from
+    int pre_set = -1;                               // set holding a prefetched batch, -1 = none
+    const void *pre_key[4] = {nullptr, nullptr, nullptr, nullptr};
+    int pre_pairs = 0, pre_stride = 0;
     BatchView bv;
     WidthView wv;
     Hit *d_aln = nullptr;
@@ -85,7 +94,7 @@ struct fqb_handle {
     bool batch_ready = false;
     uint64_t n_launches = 0;
     // paired-end resolution stage
-    fqb_read_t *d_rows = nullptr;
+    fqb_read_t *d_rows = nullptr, *d_rows_split = nullptr;
     PeScratch pesc = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint32_t *d_hist = nullptr;          // kIsizeBins + 1 (last = max_len)
     int32_t *d_penalty = nullptr; size_t penalty_cap = 0;
@@ -118,13 +127,14 @@ struct fqb_handle {
 };
 
 static void free_batch(fqb_handle *h) {
-    for (auto &p : h->d_in) { cudaFree(p); p = nullptr; }
-    for (auto &p : h->d_lens_in) { cudaFree(p); p = nullptr; }
+    for (auto &set : h->d_in) for (auto &p : set) { cudaFree(p); p = nullptr; }
+    for (auto &set : h->d_lens_in) for (auto &p : set) { cudaFree(p); p = nullptr; }
+    h->pre_set = -1;
     cudaFree(h->bv.codes); cudaFree(h->bv.qual); cudaFree(h->bv.len); cudaFree(h->bv.full_len);
     cudaFree(h->bv.filtered); cudaFree(h->bv.n_ambig); cudaFree(h->bv.work); cudaFree(h->d_work_sorted); h->d_work_sorted = nullptr;
     cudaFree(h->wv.w); cudaFree(h->wv.sw);
     cudaFree(h->d_aln); cudaFree(h->d_naln); cudaFree(h->d_overflow); cudaFree(h->d_spill_slot);
-    cudaFree(h->d_rows); cudaFree(h->pesc.packed); cudaFree(h->pesc.scanned); cudaFree(h->pesc.scan_tmp); cudaFree(h->pesc.cum_extra);
+    cudaFree(h->d_rows); cudaFree(h->d_rows_split); cudaFree(h->pesc.packed); cudaFree(h->pesc.scanned); cudaFree(h->pesc.scan_tmp); cudaFree(h->pesc.cum_extra);
     cudaFree(h->pesc.multi_list); cudaFree(h->d_big_list); cudaFree(h->d_sw_list); cudaFree(h->d_refine_list);
     h->d_sw_list = h->d_refine_list = nullptr;
     h->d_rows = nullptr; h->pesc.packed = h->pesc.scanned = h->pesc.scan_tmp = h->pesc.cum_extra = nullptr; h->pesc.multi_list = nullptr; h->d_big_list = nullptr;
@@ -138,8 +148,10 @@ static int ensure_batch(fqb_handle *h, int n_reads, int stride) {
     free_batch(h);
     int cap = n_reads > 2 * FQB_BATCH_PAIRS ? n_reads : (n_reads > 65536 ? 2 * FQB_BATCH_PAIRS : 65536 * 2);
     int lpad = (stride + 15) & ~15;
-    for (int i = 0; i < 4; ++i) CU_CHECK(cudaMalloc(&h->d_in[i], (size_t)(cap / 2) * stride));
-    for (int i = 0; i < 2; ++i) CU_CHECK(cudaMalloc(&h->d_lens_in[i], (size_t)(cap / 2) * 4));
+    for (int st = 0; st < 2; ++st) {
+        for (int i = 0; i < 4; ++i) CU_CHECK(cudaMalloc(&h->d_in[st][i], (size_t)(cap / 2) * stride));
+        for (int i = 0; i < 2; ++i) CU_CHECK(cudaMalloc(&h->d_lens_in[st][i], (size_t)(cap / 2) * 4));
+    }
     CU_CHECK(cudaMalloc(&h->bv.codes, (size_t)cap * lpad));
     CU_CHECK(cudaMalloc(&h->bv.qual, (size_t)cap * lpad));
     CU_CHECK(cudaMalloc(&h->bv.len, (size_t)cap * 4));
@@ -158,6 +170,7 @@ static int ensure_batch(fqb_handle *h, int n_reads, int stride) {
     CU_CHECK(cudaMalloc(&h->d_overflow, (size_t)cap * 3 * 4));
     CU_CHECK(cudaMalloc(&h->d_spill_slot, (size_t)cap * 4));
     CU_CHECK(cudaMalloc(&h->d_rows, (size_t)cap * sizeof(fqb_read_t)));
+    CU_CHECK(cudaMalloc(&h->d_rows_split, (size_t)cap * sizeof(fqb_read_t)));
     CU_CHECK(cudaMalloc(&h->pesc.packed, (size_t)cap * 8));
     CU_CHECK(cudaMalloc(&h->pesc.scanned, (size_t)cap * 8));
     CU_CHECK(cudaMalloc(&h->pesc.scan_tmp, ((size_t)cap / 1024 + 2) * 2 * 8));
@@ -222,6 +235,11 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
 #define CU_CHECK_H(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); fqb_destroy(h); return FQB_ERR_CUDA; } } while (0)
     CU_CHECK_H(cudaSetDevice(device));
     CU_CHECK_H(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU_CHECK_H(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU_CHECK_H(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+        CU_CHECK_H(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+    }
     for (int s = 0; s < 2; ++s) {
         std::vector<Block32> blocks;
         relayout_bwt(h->hidx.bwt[s], blocks);
@@ -288,6 +306,8 @@ void fqb_destroy(fqb_handle *h) {
     cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_ctrs); cudaFree(h->d_order_bins); cudaFree(h->d_counters);
     cudaFree(h->d_arena); cudaFree(h->d_arena_mid); cudaFree(h->d_arena_big); cudaFree(h->d_aln_big);
     cudaFree(h->pesc.totals); cudaFree(h->pesc.err_flag); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch); cudaFree(h->dp_pool.ints); cudaFree(h->dp_pool.bytes); cudaFree(h->d_dpctr);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -319,11 +339,22 @@ int fqb_stage_load(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t
         b.bases_in[0] = bases1; b.quals_in[0] = quals1; b.bases_in[1] = bases2; b.quals_in[1] = quals2;
         b.lens_in[0] = lens1; b.lens_in[1] = lens2;
     } else {
-        for (int i = 0; i < 4; ++i) CU_CHECK(cudaMemcpyAsync(h->d_in[i], src[i], bytes, cudaMemcpyHostToDevice, h->stream));
-        for (int i = 0; i < 2; ++i)
-            if (lsrc[i]) CU_CHECK(cudaMemcpyAsync(h->d_lens_in[i], lsrc[i], (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
-        b.bases_in[0] = h->d_in[0]; b.quals_in[0] = h->d_in[1]; b.bases_in[1] = h->d_in[2]; b.quals_in[1] = h->d_in[3];
-        b.lens_in[0] = lens1 ? h->d_lens_in[0] : nullptr; b.lens_in[1] = lens2 ? h->d_lens_in[1] : nullptr;
+        int set;
+        if (h->pre_set >= 0 && h->pre_pairs == n_pairs && h->pre_stride == stride && h->pre_key[0] == bases1 && h->pre_key[1] == quals1 &&
+            h->pre_key[2] == bases2 && h->pre_key[3] == quals2) {
+            set = h->pre_set;                                   // uploaded ahead of time by fqb_prefetch_pairs
+            CU_CHECK(cudaStreamWaitEvent(h->stream, h->ev_in[set], 0));
+        } else {
+            set = h->pre_set >= 0 ? 1 - h->pre_set : 0;         // do not disturb a pending prefetch of another batch
+            CU_CHECK(cudaStreamWaitEvent(h->stream, h->ev_free[set], 0));
+            for (int i = 0; i < 4; ++i) CU_CHECK(cudaMemcpyAsync(h->d_in[set][i], src[i], bytes, cudaMemcpyHostToDevice, h->stream));
+            for (int i = 0; i < 2; ++i)
+                if (lsrc[i]) CU_CHECK(cudaMemcpyAsync(h->d_lens_in[set][i], lsrc[i], (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
+        }
+        if (set == h->pre_set) h->pre_set = -1;
+        h->cur_set = set;
+        b.bases_in[0] = h->d_in[set][0]; b.quals_in[0] = h->d_in[set][1]; b.bases_in[1] = h->d_in[set][2]; b.quals_in[1] = h->d_in[set][3];
+        b.lens_in[0] = lens1 ? h->d_lens_in[set][0] : nullptr; b.lens_in[1] = lens2 ? h->d_lens_in[set][1] : nullptr;
     }
     b.n_work = h->d_ctrs;
     h->batch_ready = true; h->align_done = h->pair_done = h->dp_done = h->stats_done = false;
@@ -339,6 +370,7 @@ int fqb_stage_align(fqb_handle *h) {
     PrepParams pp;
     pp.trim_qual = h->gopt.trim_qual; pp.kmer_thresh = h->gopt.kmer_thresh; pp.is_il13 = h->gopt.is_il13; pp.roll = h->d_roll;
     launch_prep(h->bv, pp, st);
+    CU_CHECK(cudaEventRecord(h->ev_free[h->cur_set], st));       // the staging set may be refilled from here on
     h->n_launches += 3;
     launch_width(h->bv, h->wv, h->dbwt, h->gopt.seed_len, h->bv.work, h->bv.n_work, h->n_reads, h->d_counters, st);
 
@@ -751,13 +783,28 @@ int fqb_stats_import(fqb_handle *h, int which, const void *src_device) {
 }
 
 // result rows of the last completed stage: rows[e][i] = end e of pair i
+}  // extern "C" (reopened below)
+// out[end][pair] = in[pair][end], moved as 16-byte words (sizeof(fqb_read_t) = 6 x 16)
+static __global__ void split_rows_kernel(const uint4 *in, uint4 *out, size_t n_pairs) {
+    constexpr size_t kW = sizeof(fqb_read_t) / 16;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pairs * 2 * kW) return;
+    const size_t row = t / kW, w = t % kW, pair = row >> 1, end = row & 1;
+    out[(end * n_pairs + pair) * kW + w] = in[t];
+}
+extern "C" {
 int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out) {
     if (!h || !h->pair_done) { set_error("fqb_stage_fetch_rows: run fqb_stage_pair first"); return FQB_ERR_STATE; }
     CU_CHECK(cudaSetDevice(h->device));
     const size_t np = (size_t)h->n_reads / 2;
     if (np) {
-        CU_CHECK(cudaMemcpy2DAsync(rows1, sizeof(fqb_read_t), h->d_rows, 2 * sizeof(fqb_read_t), sizeof(fqb_read_t), np, cudaMemcpyDeviceToHost, h->stream));
-        CU_CHECK(cudaMemcpy2DAsync(rows2, sizeof(fqb_read_t), h->d_rows + 1, 2 * sizeof(fqb_read_t), sizeof(fqb_read_t), np, cudaMemcpyDeviceToHost, h->stream));
+        // rows are interleaved by end on the device (r = 2*pair + end); split them there so that the two
+        // device-to-host copies are contiguous (strided 96-byte copies crawl over PCIe)
+        split_rows_kernel<<<(unsigned)((np * 2 * (sizeof(fqb_read_t) / 16) + 255) / 256), 256, 0, h->stream>>>(
+            reinterpret_cast<const uint4 *>(h->d_rows), reinterpret_cast<uint4 *>(h->d_rows_split), np);
+        ++h->n_launches;
+        CU_CHECK(cudaMemcpyAsync(rows1, h->d_rows_split, np * sizeof(fqb_read_t), cudaMemcpyDeviceToHost, h->stream));
+        CU_CHECK(cudaMemcpyAsync(rows2, h->d_rows_split + np, np * sizeof(fqb_read_t), cudaMemcpyDeviceToHost, h->stream));
     }
     CU_CHECK(cudaStreamSynchronize(h->stream));
     if (ii_out) *ii_out = h->cur_ii;
@@ -842,6 +889,27 @@ int fqb_stage_pair(fqb_handle *h);
 int fqb_stage_sw_refine(fqb_handle *h);
 
 // The whole per-batch body of BwtMapper::PairEndMapper up to (not including) the statistics loop.
+// Upload the NEXT batch on the copy stream while the current one is being processed; the following
+// fqb_align_pairs / fqb_stage_load call with the same host pointers and shape picks it up without copying.
+int fqb_prefetch_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
+                       const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2) {
+    if (!h || n_pairs < 0 || stride < 1 || stride > FQB_MAX_READ_LEN) { set_error("bad batch shape"); return FQB_ERR_ARG; }
+    CU_CHECK(cudaSetDevice(h->device));
+    if (2 * n_pairs > h->cap_reads || stride > h->stride_cap) return FQB_OK;      // buffers not sized yet: the load will copy
+    const int set = 1 - h->cur_set;
+    const uint8_t *src[4] = {bases1, quals1, bases2, quals2};
+    const int32_t *lsrc[2] = {lens1, lens2};
+    const size_t bytes = (size_t)n_pairs * stride;
+    CU_CHECK(cudaStreamWaitEvent(h->copy_stream, h->ev_free[set], 0));
+    for (int i = 0; i < 4; ++i) CU_CHECK(cudaMemcpyAsync(h->d_in[set][i], src[i], bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    for (int i = 0; i < 2; ++i)
+        if (lsrc[i]) CU_CHECK(cudaMemcpyAsync(h->d_lens_in[set][i], lsrc[i], (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->copy_stream));
+    CU_CHECK(cudaEventRecord(h->ev_in[set], h->copy_stream));
+    h->pre_set = set; h->pre_pairs = n_pairs; h->pre_stride = stride;
+    for (int i = 0; i < 4; ++i) h->pre_key[i] = src[i];
+    return FQB_OK;
+}
+
 int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
                     const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2,
                     fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out) {

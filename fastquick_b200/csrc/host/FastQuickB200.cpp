@@ -131,32 +131,38 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
     if (!r[0].open(fq1) || !r[1].open(fq2)) error("Open fastq failed: %s / %s", fq1.c_str(), fq2.c_str());
     if (fqb_stats_begin_file(h_, prefix_.c_str(), fq1.c_str(), fq2.c_str()) != FQB_OK) error("%s", fqb_last_error());
     const int stride = opt->read_len < FQB_MAX_READ_LEN ? opt->read_len : FQB_MAX_READ_LEN, cap = FQB_BATCH_PAIRS, name_stride = 64;
-    // double-buffered pinned batches: the two IO workers of the reference (src/BwtMapper.cpp:1969-1982) become one reader thread per end
-    struct Buf { uint8_t *b[2], *q[2]; int32_t *l[2]; char *nm[2]; int n[2]; } bufs[2];
+    // three pinned batches in flight: the GPU maps batch N, the copy stream uploads batch N+1, the reader threads decode batch N+2
+    // (the two IO workers of the reference, src/BwtMapper.cpp:1969-1982, become one reader thread per end)
+    struct Buf { uint8_t *b[2], *q[2]; int32_t *l[2]; char *nm[2]; int n[2]; } bufs[3];
     for (auto &B : bufs)
         for (int e = 0; e < 2; ++e) {
             B.b[e] = (uint8_t *)fqb_host_alloc((size_t)cap * stride); B.q[e] = (uint8_t *)fqb_host_alloc((size_t)cap * stride);
             B.l[e] = (int32_t *)fqb_host_alloc((size_t)cap * 4); B.nm[e] = (char *)fqb_host_alloc((size_t)cap * name_stride);
             if (!B.b[e] || !B.q[e] || !B.l[e] || !B.nm[e]) error("pinned host allocation failed");
+            B.n[e] = 0;
         }
     auto load = [&](Buf &B) {
         std::thread t0([&]() { B.n[0] = r[0].fill(cap, stride, B.b[0], B.q[0], B.l[0], B.nm[0], name_stride); });
         B.n[1] = r[1].fill(cap, stride, B.b[1], B.q[1], B.l[1], B.nm[1], name_stride);
         t0.join();
     };
+    auto good = [](const Buf &B) { return B.n[0] > 0 && B.n[1] > 0; };
     int cur = 0;
-    load(bufs[cur]);
-    while (bufs[cur].n[0] > 0 && bufs[cur].n[1] > 0) {
-        Buf &B = bufs[cur];
+    load(bufs[0]);
+    if (good(bufs[0])) load(bufs[1]);
+    while (good(bufs[cur])) {
+        Buf &B = bufs[cur], &N1 = bufs[(cur + 1) % 3], &N2 = bufs[(cur + 2) % 3];
         if (B.n[0] != B.n[1]) error("Abort, please make sure input pair of fastq files are in the same order!");
-        std::thread next([&]() { load(bufs[1 - cur]); });                 // IO(N+1) overlaps GPU(N)
+        if (good(N1) && N1.n[0] == N1.n[1] &&
+            fqb_prefetch_pairs(h_, N1.n[0], stride, N1.b[0], N1.q[0], N1.l[0], N1.b[1], N1.q[1], N1.l[1]) != FQB_OK) error("%s", fqb_last_error());
+        std::thread next([&]() { if (good(N1)) load(N2); else N2.n[0] = N2.n[1] = 0; });      // IO(N+2) overlaps GPU(N) and H2D(N+1)
         if (fqb_align_pairs(h_, B.n[0], stride, B.b[0], B.q[0], B.l[0], B.b[1], B.q[1], B.l[1], nullptr, nullptr, nullptr) != FQB_OK) error("%s", fqb_last_error());
         if (fqb_stage_stats(h_) != FQB_OK) error("%s", fqb_last_error());
         if (fqb_stats_emit(h_, B.nm[0], name_stride) != FQB_OK) error("%s", fqb_last_error());
         FSC.NumRead += 2LL * B.n[0];
         if (FSC.NumRead % FQB_BATCH_PAIRS == 0) fprintf(stderr, "NOTICE - %lld sequences are processed.\n", FSC.NumRead);
         next.join();
-        cur = 1 - cur;
+        cur = (cur + 1) % 3;
     }
     notice("%lld sequences are loaded.", FSC.NumRead);
     for (auto &B : bufs) for (int e = 0; e < 2; ++e) { fqb_host_free(B.b[e]); fqb_host_free(B.q[e]); fqb_host_free(B.l[e]); fqb_host_free(B.nm[e]); }

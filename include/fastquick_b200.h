@@ -115,6 +115,15 @@ int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride,
                     const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2,
                     fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
 
+/* The reference's IO workers read batch n+1 while batch n is being mapped
+ * (src/BwtMapper.cpp:1905-1931).  Same overlap here: upload the NEXT batch on a
+ * copy stream into the second staging set; the following fqb_align_pairs /
+ * fqb_stage_load with the same host pointers and shape uses it without copying.
+ * The host buffers must stay untouched until that call. */
+int fqb_prefetch_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride,
+                       const uint8_t *bases1, const uint8_t *quals1, const int32_t *lens1,
+                       const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2);
+
 /* ---- stage-level entry points (parity tests, bench, profiling) ---------------
  * The same kernels fqb_align_pairs sequences, one group at a time, on the batch
  * made resident by fqb_stage_load.  Read index r = 2*pair + end. */
