@@ -97,6 +97,10 @@ int orc_refine_gapped(int64_t l_pac, const uint8_t *pac, int len, const uint8_t 
 int orc_cal_nm(int n_cigar, const uint16_t *cigar, int has_cigar, int len, uint32_t pos, const uint8_t *seq, int64_t l_pac, const uint8_t *pac);
 void orc_paired_sw(int64_t l_pac, const uint8_t *pac, int n_pairs, orc_row_t *rows, const uint8_t *codes, int stride,
                    const orc_pe_opt_t *popt, const orc_isize_t *ii);
+/* MD tag (bwa_cal_md1, libbwa/bwase.c:234-296) and StatCollector::RecoverRefseqByMDandCigar (src/StatCollector.cpp:101-172) */
+int orc_cal_md(int n_cigar, const uint16_t *cigar, int has_cigar, int len, uint32_t pos, const uint8_t *seq, int64_t l_pac,
+               const uint8_t *pac, char *out, int cap);
+int orc_recover_refseq(const char *read, const char *md, const uint16_t *cigar, int n_cigar, char *out, int cap);
 void orc_refine_gapped_batch(int64_t l_pac, const uint8_t *pac, int n_reads, orc_row_t *rows, const uint8_t *codes, int stride);
 
 #ifdef __cplusplus

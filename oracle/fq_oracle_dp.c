@@ -4,6 +4,8 @@
  * (libbwa/bwase.c:183-232), bwa_cal_md1's NM count (bwase.c:234-296) and bwa_correct_trimmed
  * (bwase.c:298-337).  Pinned against oracle/_ref. */
 #include "fq_oracle.h"
+#include <ctype.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -479,4 +481,96 @@ void orc_refine_gapped_batch(int64_t l_pac, const uint8_t *pac, int n_reads, orc
         }
         s->len = s->full_len;
     }
+}
+
+/* ---- MD tag and its inverse (test infrastructure for rows a11/a13) ---------------------------------------
+ * orc_cal_md: the MD string and NM of bwa_cal_md1 (libbwa/bwase.c:234-296). `seq` is the read in alignment
+ * orientation.  Returns NM, writes a NUL-terminated string (truncated at cap-1). */
+static int md_put(char *out, int cap, int o, const char *s) { while (*s && o < cap - 1) out[o++] = *s++; out[o] = 0; return o; }
+static int md_num(char *out, int cap, int o, int u) { char b[16]; snprintf(b, sizeof b, "%d", u); return md_put(out, cap, o, b); }
+static int md_chr(char *out, int cap, int o, char c) { char b[2] = {c, 0}; return md_put(out, cap, o, b); }
+
+int orc_cal_md(int n_cigar, const uint16_t *cigar, int has_cigar, int len, uint32_t pos, const uint8_t *seq, int64_t l_pac,
+               const uint8_t *pac, char *out, int cap)
+{
+    int nm = 0, u = 0, o = 0, k, z;
+    uint32_t x = pos, y = 0;
+    out[0] = 0;
+    if (has_cigar) {
+        for (k = 0; k < n_cigar; ++k) {
+            int l = cigar[k] & 0x3fff, op = cigar[k] >> 14;
+            if (op == 0) {
+                for (z = 0; z < l && (int64_t)x + z < l_pac; ++z) {
+                    int c = pac_base(pac, (int64_t)x + z);
+                    if (seq[y + z] > 3 || c != seq[y + z]) { o = md_num(out, cap, o, u); o = md_chr(out, cap, o, "ACGTN"[c]); ++nm; u = 0; }
+                    else ++u;
+                }
+                x += l; y += l;
+            } else if (op == 1 || op == 3) { y += l; if (op == 1) nm += l; }
+            else {
+                o = md_num(out, cap, o, u); o = md_chr(out, cap, o, '^');
+                for (z = 0; z < l && (int64_t)x + z < l_pac; ++z) o = md_chr(out, cap, o, "ACGT"[pac_base(pac, (int64_t)x + z)]);
+                u = 0; x += l; nm += l;
+            }
+        }
+    } else {
+        for (z = 0; z < len; ++z) {
+            int c = pac_base(pac, (int64_t)x + z);
+            if (seq[y + z] > 3 || c != seq[y + z]) { o = md_num(out, cap, o, u); o = md_chr(out, cap, o, "ACGTN"[c]); ++nm; u = 0; }
+            else ++u;
+        }
+    }
+    md_num(out, cap, o, u);
+    return nm;
+}
+
+/* StatCollector::RecoverRefseqByMDandCigar (src/StatCollector.cpp:101-172): the reference bases under a read,
+ * rebuilt from the read, its MD tag and CIGAR; quirks kept (upper-casing, the perfect-match shortcut, M pieces
+ * only, deletions spliced in at the running MD coordinate).  Returns the length written (NUL-terminated). */
+int orc_recover_refseq(const char *read, const char *md_in, const uint16_t *cigar, int n_cigar, char *out, int cap)
+{
+    char md[2048];
+    int n = 0, i, k, rl = (int)strlen(read), ml;
+    int last = 0, total = 0, has_base = 0;
+    for (i = 0; md_in[i] && i < (int)sizeof md - 1; ++i) md[i] = (char)toupper((unsigned char)md_in[i]);
+    md[i] = 0; ml = i;
+    for (i = 0; i < ml; ++i) if (strchr("ATCGN", md[i])) has_base = 1;
+    if (!has_base && atol(md) == (long)rl) { n = rl < cap - 1 ? rl : cap - 1; memcpy(out, read, (size_t)n); out[n] = 0; return n; }
+    if (n_cigar > 0) {
+        int at = 0;
+        for (k = 0; k < n_cigar; ++k) {
+            int cl = cigar[k] & 0x3fff, op = cigar[k] >> 14;
+            if (op == 0) {                                /* substr(at, cl): clipped at the end of the read */
+                int take = at >= rl ? 0 : (at + cl > rl ? rl - at : cl);
+                if (n + take > cap - 1) take = cap - 1 - n;
+                memcpy(out + n, read + at, (size_t)take); n += take; at += cl;
+            } else if (op == 3 || op == 1) at += cl;
+        }
+    } else { n = rl < cap - 1 ? rl : cap - 1; memcpy(out, read, (size_t)n); }
+    out[n] = 0;
+    for (i = 0; i < ml; ++i) {
+        if (isdigit((unsigned char)md[i])) continue;
+        if (md[i] == '^') {
+            char num[32], del[512];
+            int len, start, dl = 0, m = i - last < 31 ? i - last : 31;
+            memcpy(num, md + last, (size_t)m); num[m] = 0;
+            len = atoi(num); total += len; start = total;
+            ++i;
+            while (md[i] && !isdigit((unsigned char)md[i]) && dl < (int)sizeof del - 1) { del[dl++] = md[i]; ++i; ++total; }
+            if (start > n) start = n;
+            if (n + dl > cap - 1) dl = cap - 1 - n;
+            memmove(out + start + dl, out + start, (size_t)(n - start));
+            memcpy(out + start, del, (size_t)dl);
+            n += dl; out[n] = 0;
+            last = i;
+        } else {
+            char num[32];
+            int len, m = i - last < 31 ? i - last : 31;
+            memcpy(num, md + last, (size_t)m); num[m] = 0;
+            len = atoi(num) + 1; total += len;
+            if (total - 1 < n) out[total - 1] = md[i];
+            last = i + 1;
+        }
+    }
+    return n;
 }
