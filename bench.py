@@ -30,6 +30,7 @@ BATCH = _abi.FQB_BATCH_PAIRS
 READ_LEN = 100
 WORKLOAD = "synthetic 10M 2x100bp pairs (f_on=1, 1% subst, 0.1%+0.1% indel) vs synthetic 10,197-marker flank index"
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "FASTQuick_ref")
+NCU_DRAM_BYTES_PER_LAUNCH = 7.341e9   # search_kernel, one 262,144-pair launch: 3.499 GB read + 3.843 GB written (ncu capture r1f)
 REF_SAMPLE_PAIRS = 8192          # pairs per step of the reference arm / cpu_baseline sample unit
 STAGES = ("prep + k-mer filter + cal_width + match_gap + aln2seq/bwt_sa/mapQ + infer_isize + pairing + mate-rescue SW + gapped refinement + "
           "StatCollector pair classification and per-base pile-up/depth/quality/cycle accumulation (SURVEY 8 rows a1-a13)")
@@ -279,6 +280,11 @@ def main_gpu(args):
             assert rc == 0, lib.fqb_last_error()
             assert lib.fqb_stage_stats(h) == 0, lib.fqb_last_error()
 
+    def rq_time():
+        ms, nl = C.c_double(0.0), C.c_uint64(0)
+        assert lib.fqb_rank_query_time(h, C.byref(ms), C.byref(nl)) == 0
+        return ms.value, int(nl.value)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -291,6 +297,7 @@ def main_gpu(args):
         lib.fqb_reset_stream(h)
         c0 = (C.c_uint64 * 4)(); lib.fqb_stage_counters(h, c0)
         l0 = lib.fqb_launch_count(h)
+        rq0 = rq_time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         with torch.cuda.stream(stream):
@@ -305,30 +312,35 @@ def main_gpu(args):
         ms = e0.elapsed_time(e1)
         c1 = (C.c_uint64 * 4)(); lib.fqb_stage_counters(h, c1)
         launches = lib.fqb_launch_count(h) - l0
+        rq1 = rq_time()
+        rq = (rq1[0] - rq0[0], rq1[1] - rq0[1])
         if world > 1:
             t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-        return ms, [int(c1[i] - c0[i]) for i in range(3)], int(launches), t0, t1
+        return ms, [int(c1[i] - c0[i]) for i in range(3)], int(launches), t0, t1, rq
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    ms, ctr, launches, t0, t1 = timed(run_device, True)
+    ms, ctr, launches, t0, t1, rq = timed(run_device, True)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    ms_e2e, _, _, _, _ = timed(run_e2e, True)
+    ms_e2e = timed(run_e2e, True)[0]
 
     total_pairs = args.steps * n_pairs * world
     value = total_pairs / (ms * 1e-3)
     e2e_value = total_pairs / (ms_e2e * 1e-3)
-    # roofline of the dominant kernels (search + width): algorithmic bytes = 64 B x N_blk, N_blk counted
-    # on the device for exactly the reads processed in the timed region
+    # roofline of the dominant kernels (bwt_cal_width + bwt_match_gap): algorithmic bytes = 64 B x N_blk,
+    # N_blk counted on the device for exactly the reads processed in the timed region; clock = CUDA events recorded by
+    # the engine around those launches on its own stream, averaged over the launches of the timed region
     hbm_peak, peak_kind = peaks()
     n_blk = ctr[2]
-    achieved = 64.0 * n_blk / (ms * 1e-3) / 1e9
+    rq_ms_per_launch = rq[0] / max(rq[1], 1)
+    bytes_per_launch = 64.0 * n_blk / max(rq[1], 1)
+    achieved = bytes_per_launch / (rq_ms_per_launch * 1e-3) / 1e9
+    touches_job = float(n_blk)
     if world > 1:
-        t = torch.tensor([achieved], device="cuda"); dist.all_reduce(t); achieved_job = float(t.item())
-    else:
-        achieved_job = achieved
+        t = torch.tensor([touches_job], device="cuda", dtype=torch.float64); dist.all_reduce(t); touches_job = float(t.item())
+    touches_per_s_job = touches_job / (ms * 1e-3)
     if rank != 0:
         lib.fqb_destroy(h)
         if world > 1:
@@ -348,9 +360,15 @@ def main_gpu(args):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_kind": peak_kind + " HBM copy bandwidth (MEASURED_PEAKS.json)",
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n_pairs == BATCH else None,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of search_kernel, ncu --set full capture r1f (profiles/r01_search_kernel_ncu.md)",
+                     "peak_kind": peak_kind + " HBM copy bandwidth (MEASURED_PEAKS.json)",
+                     "kernel": "width_kernel + search_kernel (rank queries of one 262,144-pair batch)",
+                     "kernel_ms_per_launch": rq_ms_per_launch, "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "share_of_step": rq_ms_per_launch / (ms / args.steps),
                      "algorithmic": "64 B x N_blk occ-block touches of bwt_cal_width+bwt_match_gap, per GPU; N_blk/pair = %.1f" % (n_blk / (args.steps * n_pairs)),
-                     "occ_block_touches_per_s_job": achieved_job * 1e9 / 64.0},
+                     "note": "the FM index (10 MB) is L2-resident: these kernels are bound by issue slots and stack-pop latency, not by HBM bandwidth (DESIGN.md 3.3)",
+                     "occ_block_touches_per_s_job": touches_per_s_job},
     }
     if world == 1 and not args.no_cpu_baseline:
         try:

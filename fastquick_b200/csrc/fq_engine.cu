@@ -68,6 +68,8 @@ struct fqb_handle {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr};      // upload of set s complete
     cudaEvent_t ev_free[2] = {nullptr, nullptr};    // prep_kernel has consumed set s
+    cudaEvent_t ev_rq[2] = {nullptr, nullptr};      // around the rank-query kernels (width + search) of a batch
+    double rq_ms = 0.0; uint64_t rq_launches = 0;   // accumulated device time of those launches
     int cur_set = 0;                                // set the resident batch was loaded from
     int pre_set = -1;                               // set holding a prefetched batch, -1 = none
     const void *pre_key[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -239,6 +241,7 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     for (int i = 0; i < 2; ++i) {
         CU_CHECK_H(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
         CU_CHECK_H(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+        CU_CHECK_H(cudaEventCreate(&h->ev_rq[i]));
     }
     for (int s = 0; s < 2; ++s) {
         std::vector<Block32> blocks;
@@ -307,7 +310,7 @@ void fqb_destroy(fqb_handle *h) {
     cudaFree(h->d_arena); cudaFree(h->d_arena_mid); cudaFree(h->d_arena_big); cudaFree(h->d_aln_big);
     cudaFree(h->pesc.totals); cudaFree(h->pesc.err_flag); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch); cudaFree(h->dp_pool.ints); cudaFree(h->dp_pool.bytes); cudaFree(h->d_dpctr);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
-    for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); }
+    for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); if (h->ev_rq[i]) cudaEventDestroy(h->ev_rq[i]); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -372,6 +375,7 @@ int fqb_stage_align(fqb_handle *h) {
     launch_prep(h->bv, pp, st);
     CU_CHECK(cudaEventRecord(h->ev_free[h->cur_set], st));       // the staging set may be refilled from here on
     h->n_launches += 3;
+    CU_CHECK(cudaEventRecord(h->ev_rq[0], st));
     launch_width(h->bv, h->wv, h->dbwt, h->gopt.seed_len, h->bv.work, h->bv.n_work, h->n_reads, h->d_counters, st);
 
     h->sopt = make_search_opt(h->gopt, h->stride);
@@ -397,10 +401,12 @@ int fqb_stage_align(fqb_handle *h) {
     CU_CHECK(cudaMemsetAsync(h->d_spill_slot, 0xff, (size_t)h->n_reads * 4, st));
     launch_search(h->bv, h->wv, sp, true, false, h->n_blocks16, st);
     CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaEventRecord(h->ev_rq[1], st));
 
     uint32_t n_over = 0;
     CU_CHECK(cudaMemcpyAsync(&n_over, h->d_ctrs + 2, 4, cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaStreamSynchronize(st));
+    { float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev_rq[0], h->ev_rq[1]) == cudaSuccess) { h->rq_ms += ms; ++h->rq_launches; } }
     // Rare reads whose stack or hit list outgrew the fast pass are redone from scratch with deeper arenas:
     // tier 1 = 60k entries per lane on up to 16 blocks, tier 2 = as deep as the reference allows (max_entries).
     for (int tier = 1; tier <= 2 && n_over; ++tier) {
@@ -928,6 +934,15 @@ void *fqb_host_alloc(size_t bytes) { void *p = nullptr; return cudaMallocHost(&p
 void fqb_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 uint64_t fqb_launch_count(const fqb_handle *h) { return h ? h->n_launches : 0; }
+
+// device time (CUDA events on the handle's stream) spent in the rank-query kernels -- bwt_cal_width + queue ordering +
+// bwt_match_gap fast pass -- since creation, and the number of batches it covers; the roofline's "dominant kernel" clock
+int fqb_rank_query_time(const fqb_handle *h, double *ms, uint64_t *launches) {
+    if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    if (ms) *ms = h->rq_ms;
+    if (launches) *launches = h->rq_launches;
+    return FQB_OK;
+}
 
 void *fqb_stream(fqb_handle *h) { return h ? (void *)h->stream : nullptr; }
 

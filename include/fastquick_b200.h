@@ -177,6 +177,9 @@ int fqb_stage_counters(fqb_handle *h, uint64_t *out4);
 void *fqb_host_alloc(size_t bytes);                /* pinned host memory for the feeder's batches */
 void fqb_host_free(void *p);
 uint64_t fqb_launch_count(const fqb_handle *h);   /* kernels launched by this handle so far */
+/* accumulated device time (ms, CUDA events on the handle's stream) of the rank-query kernels of
+ * fqb_stage_align (bwt_cal_width + bwt_match_gap fast pass) and the number of batches covered */
+int fqb_rank_query_time(const fqb_handle *h, double *ms, uint64_t *launches);
 void *fqb_stream(fqb_handle *h);   /* the cudaStream_t the handle launches on (for event timing) */
 
 /* ---- synthetic fixtures (bench + tests; hs37d5/dbSNP are not available offline) ----
