@@ -54,10 +54,12 @@ __global__ void sw_classify_kernel(DpView v, uint32_t *list, uint32_t *n_list) {
 constexpr int kWarpsPerBlock = 8;
 constexpr size_t kWarpSlab = 256u * 1024u;       // per-warp global slab: path ops + trace-back matrix
 
-__device__ __forceinline__ WarpDp warp_scratch(const DpPool &pool, int32_t *smem, int smem_ints) {
+// shared memory of a block: kWarpsPerBlock x smem_ints words of DP rows, then kWarpsPerBlock x ref_cap bytes of reference codes
+__device__ __forceinline__ WarpDp warp_scratch(const DpPool &pool, int32_t *smem, int smem_ints, int ref_cap) {
     const int wid = threadIdx.x >> 5;
     WarpDp w;
     w.sm = smem + (size_t)wid * smem_ints; w.n_ints = smem_ints;
+    w.refc = reinterpret_cast<uint8_t *>(smem + (size_t)kWarpsPerBlock * smem_ints) + (size_t)wid * ref_cap; w.n_refc = ref_cap;
     w.gb = pool.bytes + ((size_t)blockIdx.x * kWarpsPerBlock + wid) * kWarpSlab; w.n_bytes = (int)kWarpSlab;
     w.lane = threadIdx.x & 31;
     return w;
@@ -71,9 +73,9 @@ __device__ __forceinline__ bool next_item_warp(uint32_t *cursor, uint32_t n, uin
 
 // mate rescue, one pair per warp; pairs whose window exceeds the shared-memory rows go to `retry`
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) sw_warp_kernel(DpView v, SwParams sp, DpPool pool, const uint32_t *list, const uint32_t *n_list,
-                                                                       uint32_t *cursor, int smem_ints, uint32_t *retry, uint32_t *n_retry) {
+                                                                       uint32_t *cursor, int smem_ints, int ref_cap, uint32_t *retry, uint32_t *n_retry) {
     extern __shared__ int32_t dp_smem[];
-    const WarpDp w = warp_scratch(pool, dp_smem, smem_ints);
+    const WarpDp w = warp_scratch(pool, dp_smem, smem_ints, ref_cap);
     const uint32_t n = *n_list;
     uint32_t j;
     while (next_item_warp(cursor, n, j)) {
@@ -121,9 +123,9 @@ __global__ void refine_classify_kernel(DpView v, uint32_t *list, uint32_t *n_lis
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) refine_warp_kernel(DpView v, DpPool pool, const uint32_t *list, const uint32_t *n_list,
-                                                                           uint32_t *cursor, int smem_ints, uint32_t *retry, uint32_t *n_retry) {
+                                                                           uint32_t *cursor, int smem_ints, int ref_cap, uint32_t *retry, uint32_t *n_retry) {
     extern __shared__ int32_t dp_smem[];
-    const WarpDp w = warp_scratch(pool, dp_smem, smem_ints);
+    const WarpDp w = warp_scratch(pool, dp_smem, smem_ints, ref_cap);
     const uint32_t n = *n_list;
     uint32_t j;
     while (next_item_warp(cursor, n, j)) {
@@ -180,18 +182,20 @@ static int warp_blocks(const DpPool &pool) {
 void launch_sw(const DpView &v, const SwParams &sp, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, cudaStream_t s) {
     sw_classify_kernel<<<(v.n_reads / 2 + 255) / 256, 256, 0, s>>>(v, list, ctr);
     const int ints = 2 * kSwSmemInts;                                    // H and E rows of a <= 702-column window
-    const size_t smem = (size_t)ints * kWarpsPerBlock * 4;
+    const int ref_cap = kSwSmemInts;                                     // reference codes of the window, one byte each
+    const size_t smem = (size_t)ints * kWarpsPerBlock * 4 + (size_t)ref_cap * kWarpsPerBlock;
     cudaFuncSetAttribute(sw_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sw_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, sp, pool, list, ctr, ctr + 1, ints, retry, ctr + 2);
+    sw_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, sp, pool, list, ctr, ctr + 1, ints, ref_cap, retry, ctr + 2);
     sw_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, sp, pool, retry, ctr + 2, ctr + 3, err);
 }
 void launch_refine(const DpView &v, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, int max_read_len, cudaStream_t s) {
     refine_classify_kernel<<<(v.n_reads + 255) / 256, 256, 0, s>>>(v, list, ctr);
     int ints = 6 * (max_read_len + 16 + 1);                              // M/I/D rows, current and previous
     if ((size_t)ints * kWarpsPerBlock * 4 > 200u * 1024u) ints = (int)(200u * 1024u / (kWarpsPerBlock * 4));
-    const size_t smem = (size_t)ints * kWarpsPerBlock * 4;
+    const int ref_cap = (ints / 6 + 3) & ~3;                             // window columns + 1, padded to a word
+    const size_t smem = (size_t)ints * kWarpsPerBlock * 4 + (size_t)ref_cap * kWarpsPerBlock;
     cudaFuncSetAttribute(refine_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    refine_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, pool, list, ctr, ctr + 1, ints, retry, ctr + 2);
+    refine_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, pool, list, ctr, ctr + 1, ints, ref_cap, retry, ctr + 2);
     refine_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, pool, retry, ctr + 2, ctr + 3, err);
     finish_kernel<<<(v.n_reads + 255) / 256, 256, 0, s>>>(v);
 }

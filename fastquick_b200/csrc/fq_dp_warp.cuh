@@ -14,6 +14,7 @@ namespace fqb {
 
 struct WarpDp {
     int32_t *sm; int n_ints;          // per-warp shared-memory rows
+    uint8_t *refc; int n_refc;        // per-warp shared-memory copy of the reference window, one nt4 code per byte
     uint8_t *gb; int n_bytes;         // per-warp global slab: [0, ops_cap) path ops, then the trace matrix
     int lane;
 };
@@ -25,6 +26,16 @@ __device__ __forceinline__ int warp_incl_max(int v, int lane) {
 }
 
 constexpr int kVeryNeg = -2000000000;
+
+// unpack the 2-bit reference window once per alignment; the DP loops then read one shared-memory byte per cell
+__device__ __forceinline__ bool warp_load_ref(const RefWin &R, const WarpDp &w) {
+    if (R.l > w.n_refc) return false;
+    for (int i = w.lane; i < R.l; i += 32) w.refc[i] = (uint8_t)R.at(i);
+    __syncwarp();
+    return true;
+}
+// aln_sm_maq with a reference base that is never N: row-constant part hoisted (qn = read base is N)
+__device__ __forceinline__ int maq_row_score(uint32_t a, uint32_t qj, bool qn) { return qn ? -13 : (a == qj ? 11 : -19); }
 
 // aln_global_core, row-parallel.  Result broadcast to all lanes; path ops in w.gb[0 .. n_ops).
 __device__ GlobalResult warp_global_align(const RefWin &R, int r0, int len1, const ReadSeq &Q, int q0, int len2, int gap_end, int band,
@@ -61,6 +72,7 @@ __device__ GlobalResult warp_global_align(const RefWin &R, int r0, int len1, con
         const bool last_row_d = head ? (j == tmp_end + 1) : (!mid && j == len2);
         const int d_ge = last_row_d ? end_ge : kGapExt;
         const uint32_t qj = Q.at(q0 + j - 1);
+        const bool qn = qj > 3;
         int first, endc;
         int bM = kNegInf, bD = kNegInf;                  // boundary cell of this row (column `first`)
         if (head) {
@@ -77,6 +89,9 @@ __device__ GlobalResult warp_global_align(const RefWin &R, int r0, int len1, con
             endc = mid ? j + b1 - 1 : len1;
             if (lane == 0) { WROW(cur, 0, first) = kNegInf; WROW(cur, 1, first) = kNegInf; WROW(cur, 2, first) = kNegInf; }
         }
+        // the last column of a row: whether the cell above exists, and set_end_I's extension penalty (row constants)
+        const bool last_have_up = head ? (j + b1 - 1 > len1) : !mid;
+        const int last_ige = (head || !mid) ? end_ge : kGapExt;
         int carryM = bM, carryD = bD, carryP = bD + first * d_ge;
         for (int base = first + 1; base <= endc; base += 32) {
             const int i = base + lane;
@@ -84,15 +99,11 @@ __device__ GlobalResult warp_global_align(const RefWin &R, int r0, int len1, con
             int m = kVeryNeg, iv = kNegInf, d;
             uint32_t tm = 0, ti = 0, td;
             if (on) {
-                const int sco = maq_score(R.at(r0 + i - 1), qj);
+                const int sco = maq_row_score(w.refc[r0 + i - 1], qj, qn);
                 dp_from_diag(WROW(last, 0, i - 1), WROW(last, 1, i - 1), WROW(last, 2, i - 1), sco, m, tm);
                 const bool lastc = i == endc;
-                bool have_up = true;
-                if (lastc) { if (head) have_up = j + b1 - 1 > len1; else if (mid) have_up = false; }
-                if (have_up) {
-                    const int ige = (lastc && (head || !mid)) ? end_ge : kGapExt;
-                    dp_gap(WROW(last, 0, i), WROW(last, 1, i), kGapOpen, ige, kOpI, iv, ti);
-                }
+                if (!lastc || last_have_up)
+                    dp_gap(WROW(last, 0, i), WROW(last, 1, i), kGapOpen, lastc ? last_ige : kGapExt, kOpI, iv, ti);
             }
             // D(i) = max(M(i-1) - go, D(i-1)) - ge  ==  max_k<i (M(k) - go + k ge) - i ge   (prefix max over the row)
             int mprev = __shfl_up_sync(FQB_FULL, m, 1);
@@ -149,13 +160,14 @@ __device__ LocalResult warp_local_align(const RefWin &R, int len1, const ReadSeq
     LocalResult res; res.score = -1; res.n_ops = 0; res.start_i = res.start_j = res.end_i = res.end_j = 0; res.too_big = false;
     if (len1 == 0 || len2 == 0) return res;
     const int lane = w.lane, q = kGapOpen, r = kGapExt, qr = q + r, max_score = 11, W = len1 + 2;
-    if (2 * W > w.n_ints) { res.too_big = true; return res; }
+    if (2 * W > w.n_ints || !warp_load_ref(R, w)) { res.too_big = true; return res; }
     int32_t *H = w.sm, *E = w.sm + W;
     for (int i = lane; i < W; i += 32) { H[i] = 0; E[i] = 0; }
     __syncwarp();
     int score_f = 0, end_i = 0, end_j = 0;
     for (int j = 1; j <= len2; ++j) {
         const uint32_t qj = Q.at(j - 1);
+        const bool qn = qj > 3;
         int carry_g = kVeryNeg;               // max over the columns of earlier chunks of h'(k) + k r
         int carry_diag = 0;                   // h(base - 1, j - 1); column 0 holds 0
         int row_best = 0, row_best_i = 0;
@@ -167,7 +179,7 @@ __device__ LocalResult warp_local_align(const RefWin &R, int len1, const ReadSeq
             if (lane == 0) hd = carry_diag;
             int e = 0;
             if (hp >= qr + 1) { e = ep - r; if (hp - qr > e) e = hp - qr; }
-            int h1 = on ? hd + maq_score(R.at(i - 1), qj) : 0;
+            int h1 = on ? hd + maq_row_score(w.refc[i - 1], qj, qn) : 0;
             if (h1 < 0) h1 = 0;
             if (h1 < e) h1 = e;
             // f(i) = max_{k < i} (h'(k) - q - (i - k) r): the gap along the row as a prefix maximum
@@ -200,7 +212,7 @@ __device__ LocalResult warp_local_align(const RefWin &R, int len1, const ReadSeq
     for (int i = lane; i <= end_i; i += 32) { H[i] = 0; E[i] = 0; }
     __syncwarp();
     if (end_i == 0 || end_j == 0) return res;
-    int score_r = maq_score(R.at(end_i - 1), Q.at(end_j - 1));
+    int score_r = maq_score(w.refc[end_i - 1], Q.at(end_j - 1));
     int start_i = end_i, start_j = end_j;
     if (lane == 0) H[end_i] = qr + score_r;
     __syncwarp();
@@ -211,6 +223,7 @@ __device__ LocalResult warp_local_align(const RefWin &R, int len1, const ReadSeq
     if (end <= 0) end = 0;
     for (int j = end_j - 1; j != 0; --j) {
         const uint32_t qj = Q.at(j - 1);
+        const bool qn = qj > 3;
         int carry_g = kVeryNeg, carry_h = 0;
         int row_best = score_r, row_best_i = 0;
         int hit_i = 0;
@@ -219,7 +232,7 @@ __device__ LocalResult warp_local_align(const RefWin &R, int len1, const ReadSeq
             const int i = base - lane;
             const bool on = i > end;
             const int hd = on ? H[i + 1] : 0, hu = on ? H[i] : 0, eo = on ? E[i] : 0;
-            int h1 = on ? hd + maq_score(R.at(i - 1), qj) : 0;
+            int h1 = on ? hd + maq_row_score(w.refc[i - 1], qj, qn) : 0;
             if (h1 < 0) h1 = 0;
             int e = eo - r; if (hu - qr > e) e = hu - qr;
             if (e < 0) e = 0;
@@ -317,6 +330,7 @@ __device__ int warp_refine_gapped(int64_t l_pac, const uint8_t *pac, const ReadS
                                   const WarpDp &w) {
     int64_t pos;
     const RefWin R = refine_window(l_pac, pac, Q.len, *pos_io, ext, &pos);
+    if (!warp_load_ref(R, w)) return -1;
     GlobalResult g = warp_global_align(R, 0, R.l, Q, 0, Q.len, kGapEnd, kBandWidth, w);
     if (g.too_big) return -1;
     int nc = 0;
