@@ -388,6 +388,7 @@ int fqb_stage_align(fqb_handle *h) {
     sp.bwt[0] = h->dbwt[0]; sp.bwt[1] = h->dbwt[1];
     sp.opt = h->sopt; sp.maxdiff = h->d_maxdiff; sp.seed_len_opt = h->gopt.seed_len;
     sp.work = h->bv.work; sp.n_work = h->d_ctrs; sp.cursor = h->d_ctrs + 1;
+    sp.pops_out = nullptr;
     if (!getenv("FQB_NO_ORDER")) {
         launch_order(h->bv, h->wv, h->bv.work, h->bv.n_work, h->n_reads, h->d_order_bins, h->d_work_sorted, st);
         h->n_launches += 2;
@@ -440,7 +441,7 @@ int fqb_stage_align(fqb_handle *h) {
         s2.arena = arena; s2.arena_cap = cap;
         s2.aln = h->d_aln_big; s2.aln_cap = kAlnCapSlow; s2.aln_row = h->d_spill_slot;
         s2.overflow = h->d_overflow + h->cap_reads * (tier == 1 ? 1 : 2); s2.n_overflow = d_c + 2;
-        s2.counters = nullptr;
+        s2.counters = nullptr; s2.pops_out = nullptr;
         launch_search(h->bv, h->wv, s2, heads16, true, blocks, st);
         h->n_launches += 2;
         CU_CHECK(cudaGetLastError());

@@ -180,24 +180,25 @@ void launch_width(const BatchView &b, const WidthView &wv, const DevBwt bwt[2], 
 // two strands) is known before the search starts, so the queue is bucket-sorted by it, descending.  Reads are
 // independent, so the order changes nothing but the load balance of the persistent lanes.
 constexpr int kOrderBins = 16;
-__device__ __forceinline__ int order_key(const BatchView &b, const WidthView &wv, uint32_t r) {
+__device__ __forceinline__ int order_key(const BatchView &b, const WidthView &wv, uint32_t r, const uint32_t *hint) {
+    if (hint) { const uint32_t k = hint[r] >> 8; return k < (uint32_t)kOrderBins ? (int)k : kOrderBins - 1; }
     const int len = b.len[r];
     if (len < 1) return 0;
     const int b0 = width_bid(wv.w[((size_t)r * 2) * wv.wstride + len - 1]), b1 = width_bid(wv.w[((size_t)r * 2 + 1) * wv.wstride + len - 1]);
     const int k = b0 < b1 ? b0 : b1;
     return k < kOrderBins ? k : kOrderBins - 1;
 }
-__global__ void __launch_bounds__(256) order_hist_kernel(BatchView b, WidthView wv, const uint32_t *work, const uint32_t *n_work, uint32_t *bins) {
+__global__ void __launch_bounds__(256) order_hist_kernel(BatchView b, WidthView wv, const uint32_t *work, const uint32_t *n_work, uint32_t *bins, const uint32_t *hint) {
     __shared__ uint32_t sh[kOrderBins];
     if (threadIdx.x < kOrderBins) sh[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < *n_work) atomicAdd(&sh[order_key(b, wv, work[idx])], 1u);
+    if (idx < *n_work) atomicAdd(&sh[order_key(b, wv, work[idx], hint)], 1u);
     __syncthreads();
     if (threadIdx.x < kOrderBins && sh[threadIdx.x]) atomicAdd(&bins[threadIdx.x], sh[threadIdx.x]);
 }
 __global__ void __launch_bounds__(256) order_scatter_kernel(BatchView b, WidthView wv, const uint32_t *work, const uint32_t *n_work,
-                                                             const uint32_t *bins, uint32_t *fill, uint32_t *out) {
+                                                             const uint32_t *bins, uint32_t *fill, uint32_t *out, const uint32_t *hint) {
     __shared__ uint32_t sh[kOrderBins], base[kOrderBins];
     if (threadIdx.x < kOrderBins) sh[threadIdx.x] = 0;
     __syncthreads();
@@ -205,7 +206,7 @@ __global__ void __launch_bounds__(256) order_scatter_kernel(BatchView b, WidthVi
     const bool in = idx < *n_work;
     uint32_t r = 0, rank = 0;
     int key = 0;
-    if (in) { r = work[idx]; key = order_key(b, wv, r); rank = atomicAdd(&sh[key], 1u); }
+    if (in) { r = work[idx]; key = order_key(b, wv, r, hint); rank = atomicAdd(&sh[key], 1u); }
     __syncthreads();
     if (threadIdx.x < kOrderBins) {
         uint32_t start = 0;
@@ -216,11 +217,11 @@ __global__ void __launch_bounds__(256) order_scatter_kernel(BatchView b, WidthVi
     if (in) out[base[key] + rank] = r;
 }
 void launch_order(const BatchView &b, const WidthView &wv, const uint32_t *work, const uint32_t *n_work, int max_work,
-                  uint32_t *bins /* 2 x 16 words, zeroed here */, uint32_t *out, cudaStream_t s) {
+                  uint32_t *bins /* 2 x 16 words, zeroed here */, uint32_t *out, cudaStream_t s, const uint32_t *cost_hint) {
     cudaMemsetAsync(bins, 0, 2 * kOrderBins * 4, s);
     const int blocks = (max_work + 255) / 256 < 1 ? 1 : (max_work + 255) / 256;
-    order_hist_kernel<<<blocks, 256, 0, s>>>(b, wv, work, n_work, bins);
-    order_scatter_kernel<<<blocks, 256, 0, s>>>(b, wv, work, n_work, bins, bins + kOrderBins, out);
+    order_hist_kernel<<<blocks, 256, 0, s>>>(b, wv, work, n_work, bins, cost_hint);
+    order_scatter_kernel<<<blocks, 256, 0, s>>>(b, wv, work, n_work, bins, bins + kOrderBins, out, cost_hint);
 }
 
 // ---------------------------------------------------------------------------
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(kSearchThreads, kMinBlocks) search_kernel(cons
             active = false;
             pops += lane.n_pops; occs += lane.n_occ; blks += lane.n_blk;
             p.n_aln[r] = st == kLaneOverflow ? -1 : lane.n_aln;
+            if (p.pops_out) p.pops_out[r] = lane.n_pops;
             if (st == kLaneOverflow) p.overflow[atomicAdd(p.n_overflow, 1u)] = r;
         }
     }

@@ -50,12 +50,13 @@ struct SearchParams {
     const int32_t *aln_row;  // optional: read -> row of aln (overflow pass); null = row r
     int32_t *n_aln;
     uint32_t *overflow; uint32_t *n_overflow;   // reads to redo with the big arena
+    uint32_t *pops_out;                         // optional (experiments): stack pops of each read
     unsigned long long *counters;               // [0] pops, [1] rank-query pairs, [2] reference-equivalent occ-block touches (N_blk)
 };
 
 void launch_prep(const BatchView &b, const PrepParams &p, cudaStream_t s);
 void launch_order(const BatchView &b, const WidthView &wv, const uint32_t *work, const uint32_t *n_work, int max_work,
-                  uint32_t *bins, uint32_t *out, cudaStream_t s);
+                  uint32_t *bins, uint32_t *out, cudaStream_t s, const uint32_t *cost_hint = nullptr);
 void launch_width(const BatchView &b, const WidthView &wv, const DevBwt bwt[2], int seed_len, const uint32_t *work,
                   const uint32_t *n_work, int max_work, unsigned long long *counters, cudaStream_t s);
 // returns the number of thread blocks launched (persistent grid); heads16 selects the 16-bit head table
