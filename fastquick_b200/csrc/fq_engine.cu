@@ -20,6 +20,7 @@
 #include "fq_stats_host.h"
 #include <algorithm>
 #include <fstream>
+#include <thread>
 #include <cmath>
 #include "fq_relayout.h"
 #include "fq_synth.h"
@@ -122,9 +123,12 @@ struct fqb_handle {
     PairStat *d_pstat = nullptr;
     uint64_t pairs_seen = 0;                     // global pair index of the next batch
     std::vector<PileupColumn> pileup;
+    std::vector<PileupTuple> tuples_host;          // pile-up entries drained from the device (own batches + imported ones)
     std::vector<FileCounters> files;
     std::ofstream isize_table;
-    std::vector<fqb_read_t> h_rows; std::vector<PairStat> h_pstat;
+    std::string isize_table_path;
+    std::vector<std::pair<uint64_t, uint64_t>> isize_table_idx;   // (first global pair, bytes) of every emitted batch, in emission order
+    fqb_read_t *h_rows = nullptr; PairStat *h_pstat = nullptr; size_t h_rows_cap = 0;     // pinned staging of fqb_stats_emit
     uint32_t arena_fast = kArenaFast, arena_mid = kArenaMid;   // FQB_DEBUG_ARENA_FAST/_MID shrink them (tests of the overflow tiers)
 };
 
@@ -309,6 +313,7 @@ void fqb_destroy(fqb_handle *h) {
     cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_ctrs); cudaFree(h->d_order_bins); cudaFree(h->d_counters);
     cudaFree(h->d_arena); cudaFree(h->d_arena_mid); cudaFree(h->d_arena_big); cudaFree(h->d_aln_big);
     cudaFree(h->pesc.totals); cudaFree(h->pesc.err_flag); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch); cudaFree(h->dp_pool.ints); cudaFree(h->dp_pool.bytes); cudaFree(h->d_dpctr);
+    cudaFreeHost(h->h_rows); cudaFreeHost(h->h_pstat);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); if (h->ev_rq[i]) cudaEventDestroy(h->ev_rq[i]); }
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -562,19 +567,31 @@ int fqb_stage_sw_refine(fqb_handle *h) {
 }
 
 // ---- statistics rows -------------------------------------------------------------------------
+// d_emp: 4 x 256 quality/cycle histograms, InsertSizeDist[4096], 9 scalars (NumPCRDup, NumPairReads, out-of-range inserts,
+// TotalFiltered, BwaUnmapped, TotalMAPQ, TotalRetained, NumBase, NumRead), then the number of distinct duplicate keys
+static __global__ void add_scalar_kernel(unsigned long long *p, unsigned long long v) { *p += v; }
+constexpr int kEmpScalars = 9, kEmpWords = 4 * 256 + 4096 + kEmpScalars;
+
 static int drain_tuples(fqb_handle *h) {
     uint32_t n = 0;
     CU_CHECK(cudaMemcpy(&n, h->d_ntuples, 4, cudaMemcpyDeviceToHost));
     if (n > h->tuple_cap) { set_error("pile-up tuple buffer overflow"); return FQB_ERR_LIMIT; }
     if (!n) return FQB_OK;
-    std::vector<PileupTuple> t(n);
-    CU_CHECK(cudaMemcpy(t.data(), h->d_tuples, (size_t)n * sizeof(PileupTuple), cudaMemcpyDeviceToHost));
+    const size_t at = h->tuples_host.size();
+    h->tuples_host.resize(at + n);
+    CU_CHECK(cudaMemcpy(h->tuples_host.data() + at, h->d_tuples, (size_t)n * sizeof(PileupTuple), cudaMemcpyDeviceToHost));
     CU_CHECK(cudaMemset(h->d_ntuples, 0, 4));
+    return FQB_OK;
+}
+// UpdateInfoVecAtMarker's appends in arrival order = (global pair, end, offset on the read), whichever handle saw the pair
+static void build_pileup(fqb_handle *h) {
+    std::vector<PileupTuple> &t = h->tuples_host;
     std::sort(t.begin(), t.end(), [](const PileupTuple &a, const PileupTuple &b) {
         if (a.key_hi != b.key_hi) return a.key_hi < b.key_hi;
         return a.key_lo < b.key_lo;
     });
-    for (const PileupTuple &x : t) {       // UpdateInfoVecAtMarker's appends, in arrival order
+    h->pileup.assign(h->stabs.markers.size(), PileupColumn());
+    for (const PileupTuple &x : t) {
         PileupColumn &c = h->pileup[x.marker];
         c.seq.push_back("ACGTN"[x.base > 4 ? 4 : x.base]);
         c.qual.push_back((char)x.qual);
@@ -582,7 +599,6 @@ static int drain_tuples(fqb_handle *h) {
         c.maq.push_back(x.mapq);
         c.strand.push_back(x.strand != 0);
     }
-    return FQB_OK;
 }
 
 // RestoreVcfSites + SetGenomeSize (src/BwtMapper.cpp:225-226): side tables and accumulators
@@ -601,8 +617,8 @@ int fqb_stats_open(fqb_handle *h, const char *index_prefix) {
     CU_CHECK(cudaMemcpy(h->d_marker, T.marker_at.data(), T.marker_at.size() * 4, cudaMemcpyHostToDevice));
     CU_CHECK(cudaMalloc(&h->d_depth, ns * 3 * 4));
     CU_CHECK(cudaMemset(h->d_depth, 0, ns * 3 * 4));
-    CU_CHECK(cudaMalloc(&h->d_emp, (4 * 256 + 4096 + 8 + 1) * 8));
-    CU_CHECK(cudaMemset(h->d_emp, 0, (4 * 256 + 4096 + 8 + 1) * 8));
+    CU_CHECK(cudaMalloc(&h->d_emp, (kEmpWords + 1) * 8));
+    CU_CHECK(cudaMemset(h->d_emp, 0, (kEmpWords + 1) * 8));
     CU_CHECK(cudaMalloc(&h->d_contig_ctr, nc * 5 * 4));
     CU_CHECK(cudaMemset(h->d_contig_ctr, 0, nc * 4 * 4));
     CU_CHECK(cudaMemset(h->d_contig_ctr + nc * 4, 0xff, nc * 4));
@@ -624,7 +640,9 @@ int fqb_stats_open(fqb_handle *h, const char *index_prefix) {
 int fqb_stats_begin_file(fqb_handle *h, const char *out_prefix, const char *fq1, const char *fq2) {
     if (!h || !h->stats_open) { set_error("fqb_stats_begin_file: call fqb_stats_open first"); return FQB_ERR_STATE; }
     if (out_prefix && !h->isize_table.is_open()) {
-        h->isize_table.open(std::string(out_prefix) + ".InsertSizeTable");
+        h->isize_table_path = std::string(out_prefix) + ".InsertSizeTable";
+        h->isize_table.open(h->isize_table_path);
+        h->isize_table_idx.clear();
         if (!h->isize_table) { set_error("cannot write the InsertSizeTable"); return FQB_ERR_IO; }
     }
     FileCounters f;
@@ -652,7 +670,7 @@ int fqb_stage_stats(fqb_handle *h) {
     StatAccum A;
     A.contig_ctr = h->d_contig_ctr; A.contig_first = h->d_contig_ctr + nc * 4;
     A.isize_dist = h->d_emp + 4 * 256; A.scalars = h->d_emp + 4 * 256 + 4096;
-    A.dup_keys = h->d_dup_keys; A.dup_cap = h->dup_cap; A.dup_count = h->d_emp + 4 * 256 + 4096 + 8;
+    A.dup_keys = h->d_dup_keys; A.dup_cap = h->dup_cap; A.dup_count = h->d_emp + kEmpWords;
     BaseTables B;
     B.site = h->d_site; B.marker = h->d_marker; B.depth = h->d_depth; B.q20 = h->d_depth + ns; B.q30 = h->d_depth + 2 * ns;
     B.emp = h->d_emp; B.tuples = h->d_tuples; B.n_tuples = h->d_ntuples; B.tuple_cap = h->tuple_cap;
@@ -661,6 +679,7 @@ int fqb_stage_stats(fqb_handle *h) {
     h->n_launches += 2;
     CU_CHECK(cudaGetLastError());
     h->files.back().NumRead += 2 * (long long)np;
+    add_scalar_kernel<<<1, 1, 0, st>>>(h->d_emp + 4 * 256 + 4096 + 8, 2ull * np);     // NumRead, kept on the device too so that sharded runs sum it
     h->pairs_seen += np;
     h->stats_done = true;
     return FQB_OK;
@@ -672,23 +691,89 @@ int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride) {
     if (!h || !h->stats_done) { set_error("fqb_stats_emit: run fqb_stage_stats first"); return FQB_ERR_STATE; }
     CU_CHECK(cudaSetDevice(h->device));
     const size_t np = (size_t)h->n_reads / 2;
-    h->h_rows.resize(2 * np); h->h_pstat.resize(np);
-    CU_CHECK(cudaMemcpyAsync(h->h_rows.data(), h->d_rows, 2 * np * sizeof(fqb_read_t), cudaMemcpyDeviceToHost, h->stream));
-    CU_CHECK(cudaMemcpyAsync(h->h_pstat.data(), h->d_pstat, np * sizeof(PairStat), cudaMemcpyDeviceToHost, h->stream));
+    if (np > h->h_rows_cap) {
+        cudaFreeHost(h->h_rows); cudaFreeHost(h->h_pstat);
+        h->h_rows = nullptr; h->h_pstat = nullptr; h->h_rows_cap = 0;
+        CU_CHECK(cudaMallocHost(&h->h_rows, 2 * np * sizeof(fqb_read_t)));
+        CU_CHECK(cudaMallocHost(&h->h_pstat, np * sizeof(PairStat)));
+        h->h_rows_cap = np;
+    }
+    CU_CHECK(cudaMemcpyAsync(h->h_rows, h->d_rows, 2 * np * sizeof(fqb_read_t), cudaMemcpyDeviceToHost, h->stream));
+    CU_CHECK(cudaMemcpyAsync(h->h_pstat, h->d_pstat, np * sizeof(PairStat), cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(cudaStreamSynchronize(h->stream));
     if (!h->isize_table.is_open()) return FQB_OK;
-    std::string line, nm;
-    char buf[64];
     const uint64_t first = h->pairs_seen - np;
-    for (size_t i = 0; i < np; ++i) {
-        const PairStat &ps = h->h_pstat[i];
-        if (ps.line_kind == 0) continue;
-        const char *name;
-        if (names) { nm.assign(names + i * (size_t)name_stride, strnlen(names + i * (size_t)name_stride, (size_t)name_stride)); name = nm.c_str(); }
-        else { snprintf(buf, sizeof buf, "r%011llu", (unsigned long long)(first + i)); name = buf; }
-        format_isize_line(h->stabs, ps, h->h_rows[2 * i], h->h_rows[2 * i + 1], name, line);
-        h->isize_table << line;
+    // format on several host threads (contiguous slices of the batch), write the slices in order
+    unsigned nthr = std::thread::hardware_concurrency();
+    if (nthr < 1) nthr = 1;
+    if (nthr > 16) nthr = 16;
+    if (np < 4096) nthr = 1;
+    std::vector<std::string> parts(nthr);
+    auto work = [&](unsigned t) {
+        std::string &o = parts[t];
+        const size_t lo = np * t / nthr, hi = np * (t + 1) / nthr;
+        o.reserve((hi - lo) * 96);
+        char buf[64];
+        std::string nm;
+        for (size_t i = lo; i < hi; ++i) {
+            const PairStat &ps = h->h_pstat[i];
+            if (ps.line_kind == 0) continue;
+            const char *name;
+            if (names) { nm.assign(names + i * (size_t)name_stride, strnlen(names + i * (size_t)name_stride, (size_t)name_stride)); name = nm.c_str(); }
+            else { snprintf(buf, sizeof buf, "r%011llu", (unsigned long long)(first + i)); name = buf; }
+            append_isize_line(h->stabs, ps, h->h_rows[2 * i], h->h_rows[2 * i + 1], name, o);
+        }
+    };
+    if (nthr == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthr; ++t) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
     }
+    uint64_t bytes = 0;
+    for (auto &o : parts) { h->isize_table.write(o.data(), (std::streamsize)o.size()); bytes += o.size(); }
+    h->isize_table_idx.emplace_back(first, bytes);
+    return FQB_OK;
+}
+
+// Sharded runs: every rank writes the InsertSizeTable lines of its own batches.  close_table() finishes a rank's file
+// and leaves "<file>.idx" (first global pair and byte count of each batch) next to it; merge_tables(), called on the
+// rank that will run fqb_stats_finish, splices all ranks' batches back into file order, so the table (and the
+// InsertSizeEstimator that reads it) is exactly that of an unsharded run.
+int fqb_stats_close_table(fqb_handle *h) {
+    if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    if (h->isize_table.is_open()) h->isize_table.close();
+    if (h->isize_table_path.empty()) return FQB_OK;
+    std::ofstream idx(h->isize_table_path + ".idx");
+    for (auto &e : h->isize_table_idx) idx << e.first << "\t" << e.second << "\n";
+    if (!idx) { set_error("cannot write the InsertSizeTable index"); return FQB_ERR_IO; }
+    return FQB_OK;
+}
+
+int fqb_stats_merge_tables(fqb_handle *h, const char *const *other_prefixes, int32_t n_others) {
+    if (!h || n_others < 0 || (n_others && !other_prefixes)) { set_error("bad arguments"); return FQB_ERR_ARG; }
+    int rc = fqb_stats_close_table(h);
+    if (rc) return rc;
+    if (h->isize_table_path.empty()) { set_error("fqb_stats_merge_tables: no InsertSizeTable open on this handle"); return FQB_ERR_STATE; }
+    std::vector<std::pair<uint64_t, std::string>> chunks;
+    auto load = [&](const std::string &path) -> bool {
+        std::ifstream idx(path + ".idx"), tab(path, std::ios::binary);
+        if (!idx || !tab) return false;
+        uint64_t first, bytes;
+        while (idx >> first >> bytes) {
+            std::string c(bytes, '\0');
+            if (bytes && !tab.read(&c[0], (std::streamsize)bytes)) return false;
+            chunks.emplace_back(first, std::move(c));
+        }
+        return true;
+    };
+    if (!load(h->isize_table_path)) { set_error("cannot read " + h->isize_table_path); return FQB_ERR_IO; }
+    for (int i = 0; i < n_others; ++i)
+        if (!load(std::string(other_prefixes[i]) + ".InsertSizeTable")) { set_error(std::string("cannot read the InsertSizeTable of ") + other_prefixes[i]); return FQB_ERR_IO; }
+    std::stable_sort(chunks.begin(), chunks.end(), [](const std::pair<uint64_t, std::string> &a, const std::pair<uint64_t, std::string> &b) { return a.first < b.first; });
+    std::ofstream out(h->isize_table_path, std::ios::binary | std::ios::trunc);
+    for (auto &c : chunks) out << c.second;
+    if (!out) { set_error("cannot rewrite " + h->isize_table_path); return FQB_ERR_IO; }
     return FQB_OK;
 }
 
@@ -706,7 +791,7 @@ int fqb_stats_finish(fqb_handle *h, const char *out_prefix) {
     std::vector<uint32_t> d(ns * 3);
     CU_CHECK(cudaMemcpy(d.data(), h->d_depth, ns * 3 * 4, cudaMemcpyDeviceToHost));
     S.depth.assign(d.begin(), d.begin() + ns); S.q20.assign(d.begin() + ns, d.begin() + 2 * ns); S.q30.assign(d.begin() + 2 * ns, d.end());
-    std::vector<unsigned long long> e(4 * 256 + 4096 + 8 + 1);
+    std::vector<unsigned long long> e(kEmpWords + 1);
     CU_CHECK(cudaMemcpy(e.data(), h->d_emp, e.size() * 8, cudaMemcpyDeviceToHost));
     S.emp.assign(e.begin(), e.begin() + 1024);
     S.isize_dist.assign(e.begin() + 1024, e.begin() + 1024 + 4096);
@@ -716,12 +801,14 @@ int fqb_stats_finish(fqb_handle *h, const char *out_prefix) {
     std::vector<uint32_t> cc(nc * 5);
     CU_CHECK(cudaMemcpy(cc.data(), h->d_contig_ctr, nc * 5 * 4, cudaMemcpyDeviceToHost));
     S.contig_ctr.assign(cc.begin(), cc.begin() + nc * 4); S.contig_first.assign(cc.begin() + nc * 4, cc.end());
+    build_pileup(h);
     S.pileup = h->pileup;
     S.files = h->files;
     // per-file counters: with one FASTQ pair per run the device totals are that file's counters
     if (S.files.size() == 1) {
         FileCounters &F = S.files[0];
         F.TotalFiltered = (long long)sc[3]; F.BwaUnmapped = (long long)sc[4]; F.TotalMAPQ = (long long)sc[5]; F.TotalRetained = (long long)sc[6]; F.NumBase = (long long)sc[7];
+        F.NumRead = (long long)sc[8];
     }
     std::string err;
     if (!write_summary_files(T, S, h->gopt, out_prefix, err)) { set_error(err); return FQB_ERR_IO; }
@@ -755,7 +842,7 @@ static int stats_group(fqb_handle *h, int which, void **ptr, size_t *bytes) {
     const size_t nc = h->stabs.contigs.size(), ns = h->stabs.n_sites ? h->stabs.n_sites : 1;
     switch (which) {
     case 0: *ptr = h->d_depth; *bytes = ns * 3 * 4; return FQB_OK;
-    case 1: *ptr = h->d_emp; *bytes = (4 * 256 + 4096 + 8) * 8; return FQB_OK;
+    case 1: *ptr = h->d_emp; *bytes = (size_t)kEmpWords * 8; return FQB_OK;
     case 2: *ptr = h->d_contig_ctr; *bytes = nc * 4 * 4; return FQB_OK;
     case 3: *ptr = h->d_contig_ctr + nc * 4; *bytes = nc * 4; return FQB_OK;
     default: set_error("bad accumulator group"); return FQB_ERR_ARG;
@@ -786,6 +873,82 @@ int fqb_stats_import(fqb_handle *h, int which, const void *src_device) {
     CU_CHECK(cudaSetDevice(h->device));
     CU_CHECK(cudaMemcpyAsync(p, src_device, b, cudaMemcpyDeviceToDevice, h->stream));
     CU_CHECK(cudaStreamSynchronize(h->stream));
+    return FQB_OK;
+}
+
+}  // extern "C" (reopened below)
+static __global__ void dup_compact_kernel(const unsigned long long *keys, uint32_t cap, unsigned long long *out, unsigned long long *n_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap && keys[i]) out[atomicAdd(n_out, 1ull)] = keys[i];
+}
+// insert another handle's distinct keys; a key already present is one more duplicated pair (NumPCRDup += 2)
+static __global__ void dup_merge_kernel(unsigned long long *keys, uint32_t cap, const unsigned long long *in, unsigned long long n,
+                                        unsigned long long *n_distinct, unsigned long long *num_pcr_dup) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = in[i];
+    uint32_t hh = (uint32_t)(hash64(key) % cap);
+    for (;;) {
+        const unsigned long long old = atomicCAS(keys + hh, 0ull, key);
+        if (old == 0) { atomicAdd(n_distinct, 1ull); return; }
+        if (old == key) { atomicAdd(num_pcr_dup, 2ull); return; }
+        hh = hh + 1 == cap ? 0 : hh + 1;
+    }
+}
+extern "C" {
+// Variable-size statistics state of a sharded run: which = 0 pile-up entries (sizeof(PileupTuple) = 20 bytes each),
+// which = 1 the distinct PCR-duplicate keys (8 bytes each).  The handle that writes the files imports the other
+// handles' state AFTER the fixed-size groups (fqb_stats_import overwrites the scalar counters the key merge adds to).
+int fqb_stats_var_count(fqb_handle *h, int which, uint64_t *n) {
+    if (!h || !h->stats_open || !n) { set_error("fqb_stats_var_count: call fqb_stats_open first"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    CU_CHECK(cudaStreamSynchronize(h->stream));
+    if (which == 0) { int rc = drain_tuples(h); if (rc) return rc; *n = h->tuples_host.size(); return FQB_OK; }
+    if (which == 1) {
+        unsigned long long c = 0;
+        CU_CHECK(cudaMemcpy(&c, h->d_emp + kEmpWords, 8, cudaMemcpyDeviceToHost));
+        *n = c; return FQB_OK;
+    }
+    set_error("bad variable-size group"); return FQB_ERR_ARG;
+}
+int fqb_stats_var_export(fqb_handle *h, int which, void *dst_host, uint64_t cap) {
+    uint64_t n = 0;
+    int rc = fqb_stats_var_count(h, which, &n);
+    if (rc) return rc;
+    if (n > cap) { set_error("fqb_stats_var_export: destination too small"); return FQB_ERR_ARG; }
+    if (!n) return FQB_OK;
+    if (which == 0) { memcpy(dst_host, h->tuples_host.data(), n * sizeof(PileupTuple)); return FQB_OK; }
+    unsigned long long *tmp = nullptr, *cnt = nullptr;
+    CU_CHECK(cudaMalloc(&tmp, n * 8)); CU_CHECK(cudaMalloc(&cnt, 8)); CU_CHECK(cudaMemset(cnt, 0, 8));
+    dup_compact_kernel<<<(h->dup_cap + 255) / 256, 256, 0, h->stream>>>(h->d_dup_keys, h->dup_cap, tmp, cnt);
+    ++h->n_launches;
+    cudaError_t e = cudaMemcpyAsync(dst_host, tmp, n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp); cudaFree(cnt);
+    if (e != cudaSuccess) { set_error(std::string("CUDA: ") + cudaGetErrorString(e)); return FQB_ERR_CUDA; }
+    return FQB_OK;
+}
+int fqb_stats_var_import(fqb_handle *h, int which, const void *src_host, uint64_t n) {
+    if (!h || !h->stats_open || (n && !src_host)) { set_error("fqb_stats_var_import: call fqb_stats_open first"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    if (!n) return FQB_OK;
+    if (which == 0) {
+        const PileupTuple *t = static_cast<const PileupTuple *>(src_host);
+        h->tuples_host.insert(h->tuples_host.end(), t, t + n);
+        return FQB_OK;
+    }
+    if (which != 1) { set_error("bad variable-size group"); return FQB_ERR_ARG; }
+    unsigned long long *tmp = nullptr;
+    CU_CHECK(cudaMalloc(&tmp, n * 8));
+    cudaError_t e = cudaMemcpyAsync(tmp, src_host, n * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        dup_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_dup_keys, h->dup_cap, tmp, n, h->d_emp + kEmpWords,
+                                                                             h->d_emp + (4 * 256 + 4096));
+        ++h->n_launches;
+        e = cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(tmp);
+    if (e != cudaSuccess) { set_error(std::string("CUDA: ") + cudaGetErrorString(e)); return FQB_ERR_CUDA; }
     return FQB_OK;
 }
 

@@ -166,29 +166,44 @@ bool build_stats_tables(const HostIndex &idx, const std::string &prefix, const f
     return true;
 }
 
-static std::string cigar_string(const fqb_read_t &p) {      // Cigar2String (src/StatCollector.cpp:56-71)
-    std::string s;
-    if (!p.has_cigar) return std::to_string(p.len) + "M";
-    for (int k = 0; k < p.n_cigar; ++k) { s += std::to_string(p.cigar[k] & 0x3fff); s.push_back("MIDS"[p.cigar[k] >> 14]); }
-    return s;
+// decimal append without iostreams: the table has ~1 line per pair, so this is the host hot spot of the statistics stage
+static inline void put_int(std::string &o, long long v) {
+    char buf[24];
+    int n = 0;
+    unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    do { buf[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) o.push_back('-');
+    while (n) o.push_back(buf[--n]);
+}
+static inline void put_cigar(std::string &o, const fqb_read_t &p) {      // Cigar2String (src/StatCollector.cpp:56-71)
+    if (!p.has_cigar) { put_int(o, p.len); o.push_back('M'); return; }
+    for (int k = 0; k < p.n_cigar; ++k) { put_int(o, p.cigar[k] & 0x3fff); o.push_back("MIDS"[p.cigar[k] >> 14]); }
 }
 
-void format_isize_line(const StatsTables &T, const PairStat &ps, const fqb_read_t &p, const fqb_read_t &q, const char *name, std::string &out) {
+// appends the line (nothing when the pair prints none)
+void append_isize_line(const StatsTables &T, const PairStat &ps, const fqb_read_t &p, const fqb_read_t &q, const char *name, std::string &o) {
     static const char *kStatus[] = {"", "PropPair", "PartialPair", "NotPair", "LowQual", "FwdOnly", "RevOnly"};
-    out.clear();
     if (ps.line_kind == 0) return;
-    std::ostringstream o;
-    o << name << "\t" << ps.max_insert << "\t" << ps.max_insert2 << "\t" << ps.actual_insert << "\t";
-    if (ps.line_kind & 1) {
-        const ContigDev &c = T.contigs[ps.seqid[0]];
-        o << T.contig_names[ps.seqid[0]] << "\t" << (int64_t)p.pos - c.offset + 1 << "\t" << ps.flag[0] << "\t" << p.len << "\t" << cigar_string(p) << "\t";
-    } else o << "*\t*\t" << ps.flag[0] << "\t" << 0 << "\t*\t";
-    if (ps.line_kind & 2) {
-        const ContigDev &c = T.contigs[ps.seqid[1]];
-        o << T.contig_names[ps.seqid[1]] << "\t" << (int64_t)q.pos - c.offset + 1 << "\t" << ps.flag[1] << "\t" << q.len << "\t" << cigar_string(q) << "\t";
-    } else o << "*\t*\t" << ps.flag[1] << "\t" << 0 << "\t*\t";
-    o << kStatus[ps.status] << "\n";
-    out = o.str();
+    o += name; o.push_back('\t');
+    put_int(o, ps.max_insert); o.push_back('\t'); put_int(o, ps.max_insert2); o.push_back('\t'); put_int(o, ps.actual_insert); o.push_back('\t');
+    const fqb_read_t *rd[2] = {&p, &q};
+    for (int e = 0; e < 2; ++e) {
+        if (ps.line_kind & (1 << e)) {
+            const ContigDev &c = T.contigs[ps.seqid[e]];
+            o += T.contig_names[ps.seqid[e]]; o.push_back('\t');
+            put_int(o, (long long)rd[e]->pos - c.offset + 1); o.push_back('\t');
+            put_int(o, ps.flag[e]); o.push_back('\t');
+            put_int(o, rd[e]->len); o.push_back('\t');
+            put_cigar(o, *rd[e]); o.push_back('\t');
+        } else {
+            o += "*\t*\t"; put_int(o, ps.flag[e]); o += "\t0\t*\t";
+        }
+    }
+    o += kStatus[ps.status]; o.push_back('\n');
+}
+void format_isize_line(const StatsTables &T, const PairStat &ps, const fqb_read_t &p, const fqb_read_t &q, const char *name, std::string &out) {
+    out.clear();
+    append_isize_line(T, ps, p, q, name, out);
 }
 
 // ---- InsertSizeEstimator (src/InsertSizeEstimator.cpp:43-173) -------------------------------

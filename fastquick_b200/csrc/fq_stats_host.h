@@ -58,6 +58,7 @@ struct StatsTotals {
 
 // One InsertSizeTable line (or nothing) for a pair, exactly as ProcessPairStatus prints it.
 void format_isize_line(const StatsTables &T, const PairStat &ps, const fqb_read_t &p, const fqb_read_t &q, const char *name, std::string &out);
+void append_isize_line(const StatsTables &T, const PairStat &ps, const fqb_read_t &p, const fqb_read_t &q, const char *name, std::string &out);
 
 // ProcessCore: writes <prefix>.{DepthDist,GCDist,EmpRepDist,EmpCycleDist,AdjustedInsertSizeDist,RawInsertSizeDist,
 // SexChromInfo,Pileup,FASTQ.csv,Sequence.csv,Summary,vcf}; <prefix>.InsertSizeTable must already be complete.

@@ -154,6 +154,12 @@ int fqb_stats_begin_file(fqb_handle *h, const char *out_prefix, const char *fast
 int fqb_stage_stats(fqb_handle *h);
 int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride);
 int fqb_stats_finish(fqb_handle *h, const char *out_prefix);
+/* Sharded runs (one handle per GPU, batches dealt round-robin): each handle writes the InsertSizeTable lines
+ * (StatCollector::AddAlignment's `fout`, src/StatCollector.cpp:950) of its own batches.  fqb_stats_close_table
+ * finishes a handle's file; fqb_stats_merge_tables, on the handle that will call fqb_stats_finish, splices the
+ * batches of the other handles' files (<other_prefix>.InsertSizeTable) back into file order. */
+int fqb_stats_close_table(fqb_handle *h);
+int fqb_stats_merge_tables(fqb_handle *h, const char *const *other_prefixes, int32_t n_others);
 /* ---- multi-GPU (one process per GPU; reads shard by 262,144-pair batch, index replicated) -----------------
  * The only cross-batch state of the path is the drand48 position (srand48 once per FASTQ pair,
  * src/BwtMapper.cpp:1817) and last_ii (src/BwtMapper.cpp:780): the owner of batch b hands both to the owner of
@@ -165,6 +171,13 @@ int fqb_set_pair_base(fqb_handle *h, uint64_t first_pair);
 int fqb_stats_group_bytes(fqb_handle *h, int which, uint64_t *bytes);
 int fqb_stats_export(fqb_handle *h, int which, void *dst_device);
 int fqb_stats_import(fqb_handle *h, int which, const void *src_device);
+/* Variable-size statistics state of a sharded run (host buffers): which = 0 the marker pile-up entries
+ * (20 bytes each; they carry their global pair index, so the merged pile-up keeps file order), which = 1 the
+ * distinct PCR-duplicate keys of StatCollector's duplicateTable (8 bytes each; a key two handles both hold is
+ * one more duplicated pair).  Import on the handle that will call fqb_stats_finish, after fqb_stats_import. */
+int fqb_stats_var_count(fqb_handle *h, int which, uint64_t *n);
+int fqb_stats_var_export(fqb_handle *h, int which, void *dst_host, uint64_t cap);
+int fqb_stats_var_import(fqb_handle *h, int which, const void *src_host, uint64_t n);
 int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
 /* new FASTQ pair: restart the drand48 stream and forget last_ii (src/BwtMapper.cpp:1811-1817) */
 int fqb_reset_stream(fqb_handle *h);
