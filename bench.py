@@ -188,6 +188,21 @@ class Engine:
         assert self.lib.fqb_stage_sw_refine(self.h) == 0, self.lib.fqb_last_error()
         assert self.lib.fqb_stage_stats(self.h) == 0, self.lib.fqb_last_error()
 
+    def var_export(self, which):
+        import torch
+        n = C.c_uint64(0)
+        assert self.lib.fqb_stats_var_count(self.h, which, C.byref(n)) == 0, self.lib.fqb_last_error()
+        item = 20 if which == 0 else 8
+        t = torch.empty(int(n.value) * item, dtype=torch.uint8, device="cuda")       # exported device to device
+        if n.value:
+            assert self.lib.fqb_stats_var_export(self.h, which, C.c_void_p(t.data_ptr()), n) == 0, self.lib.fqb_last_error()
+        return t
+
+    def var_import(self, which, t):
+        item = 20 if which == 0 else 8
+        t = t.contiguous()
+        assert self.lib.fqb_stats_var_import(self.h, which, C.c_void_p(t.data_ptr()), C.c_uint64(t.numel() // item)) == 0, self.lib.fqb_last_error()
+
     def get_state(self):
         calls, ii = C.c_uint64(0), _abi.ISize()
         self.lib.fqb_get_stream_state(self.h, C.byref(calls), C.byref(ii))
@@ -251,12 +266,18 @@ def main_gpu(args):
     def reduce_stats():
         if world == 1:
             return
+        tt = [time.time()]
         for which, t, op in groups:
             assert lib.fqb_stats_export(h, which, C.c_void_p(t.data_ptr())) == 0, lib.fqb_last_error()
         multigpu.reduce_accumulators([(t, op) for _, t, op in groups], rank, world)
         if rank == 0:
             for which, t, op in groups:
                 assert lib.fqb_stats_import(h, which, C.c_void_p(t.data_ptr())) == 0, lib.fqb_last_error()
+        torch.cuda.synchronize(); tt.append(time.time())
+        multigpu.gather_variable(eng, rank, world, device)      # pile-up entries + duplicate keys, after the sums
+        torch.cuda.synchronize(); tt.append(time.time())
+        if os.environ.get("FQB_BENCH_VERBOSE") and rank == 0:
+            print("reduce: fixed groups %.1f ms, variable state %.1f ms" % ((tt[1] - tt[0]) * 1e3, (tt[2] - tt[1]) * 1e3), file=sys.stderr, flush=True)
 
     def ptr(t):
         return C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_uint8))
@@ -293,6 +314,8 @@ def main_gpu(args):
     def timed(fn, with_reduce):
         lib.fqb_reset_stream(h)
         fn(0, args.warmup)
+        if with_reduce:
+            reduce_stats()          # warm-up of the end-of-run exchange too (NCCL sets up its channels lazily)
         barrier()
         lib.fqb_reset_stream(h)
         c0 = (C.c_uint64 * 4)(); lib.fqb_stage_counters(h, c0)
@@ -354,7 +377,7 @@ def main_gpu(args):
                    "l2_policy": "every step reads a different 105 MB batch; per-step working set (inputs+widths+stack arena) exceeds the 126 MB L2",
                    "index": "10,197 markers, l_pac 6,608,697, replicated per GPU",
                    "multi_gpu": "batches round-robin over ranks; drand48 position + last_ii handed rank to rank (56 B per batch); "
-                                "accumulators NCCL-reduced to rank 0 inside the timed region"},
+                                "accumulators NCCL-reduced and pile-up entries / duplicate keys gathered to rank 0 inside the timed region"},
         "e2e": {"value": e2e_value, "unit": "read-pairs/s", "h2d_bytes_per_step": 4 * n_pairs * READ_LEN,
                 "d2h_bytes_per_step": int(2 * n_pairs * _abi.READ_DTYPE.itemsize)},
         "gpu_launches": launches,

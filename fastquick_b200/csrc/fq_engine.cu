@@ -903,7 +903,12 @@ int fqb_stats_var_count(fqb_handle *h, int which, uint64_t *n) {
     if (!h || !h->stats_open || !n) { set_error("fqb_stats_var_count: call fqb_stats_open first"); return FQB_ERR_STATE; }
     CU_CHECK(cudaSetDevice(h->device));
     CU_CHECK(cudaStreamSynchronize(h->stream));
-    if (which == 0) { int rc = drain_tuples(h); if (rc) return rc; *n = h->tuples_host.size(); return FQB_OK; }
+    if (which == 0) {
+        uint32_t nd = 0;
+        CU_CHECK(cudaMemcpy(&nd, h->d_ntuples, 4, cudaMemcpyDeviceToHost));
+        if (nd > h->tuple_cap) { set_error("pile-up tuple buffer overflow"); return FQB_ERR_LIMIT; }
+        *n = h->tuples_host.size() + nd; return FQB_OK;
+    }
     if (which == 1) {
         unsigned long long c = 0;
         CU_CHECK(cudaMemcpy(&c, h->d_emp + kEmpWords, 8, cudaMemcpyDeviceToHost));
@@ -911,36 +916,45 @@ int fqb_stats_var_count(fqb_handle *h, int which, uint64_t *n) {
     }
     set_error("bad variable-size group"); return FQB_ERR_ARG;
 }
-int fqb_stats_var_export(fqb_handle *h, int which, void *dst_host, uint64_t cap) {
+// dst / src may be host or device memory (unified addressing decides the copy direction)
+int fqb_stats_var_export(fqb_handle *h, int which, void *dst, uint64_t cap) {
     uint64_t n = 0;
     int rc = fqb_stats_var_count(h, which, &n);
     if (rc) return rc;
     if (n > cap) { set_error("fqb_stats_var_export: destination too small"); return FQB_ERR_ARG; }
     if (!n) return FQB_OK;
-    if (which == 0) { memcpy(dst_host, h->tuples_host.data(), n * sizeof(PileupTuple)); return FQB_OK; }
+    if (which == 0) {
+        const size_t nh = h->tuples_host.size(), nd = (size_t)n - nh;
+        if (nh) CU_CHECK(cudaMemcpyAsync(dst, h->tuples_host.data(), nh * sizeof(PileupTuple), cudaMemcpyDefault, h->stream));
+        if (nd) CU_CHECK(cudaMemcpyAsync(static_cast<char *>(dst) + nh * sizeof(PileupTuple), h->d_tuples, nd * sizeof(PileupTuple), cudaMemcpyDefault, h->stream));
+        CU_CHECK(cudaStreamSynchronize(h->stream));
+        return FQB_OK;
+    }
     unsigned long long *tmp = nullptr, *cnt = nullptr;
-    CU_CHECK(cudaMalloc(&tmp, n * 8)); CU_CHECK(cudaMalloc(&cnt, 8)); CU_CHECK(cudaMemset(cnt, 0, 8));
+    CU_CHECK(cudaMalloc(&tmp, n * 8)); CU_CHECK(cudaMalloc(&cnt, 8)); CU_CHECK(cudaMemsetAsync(cnt, 0, 8, h->stream));
     dup_compact_kernel<<<(h->dup_cap + 255) / 256, 256, 0, h->stream>>>(h->d_dup_keys, h->dup_cap, tmp, cnt);
     ++h->n_launches;
-    cudaError_t e = cudaMemcpyAsync(dst_host, tmp, n * 8, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaMemcpyAsync(dst, tmp, n * 8, cudaMemcpyDefault, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(tmp); cudaFree(cnt);
     if (e != cudaSuccess) { set_error(std::string("CUDA: ") + cudaGetErrorString(e)); return FQB_ERR_CUDA; }
     return FQB_OK;
 }
-int fqb_stats_var_import(fqb_handle *h, int which, const void *src_host, uint64_t n) {
-    if (!h || !h->stats_open || (n && !src_host)) { set_error("fqb_stats_var_import: call fqb_stats_open first"); return FQB_ERR_STATE; }
+int fqb_stats_var_import(fqb_handle *h, int which, const void *src, uint64_t n) {
+    if (!h || !h->stats_open || (n && !src)) { set_error("fqb_stats_var_import: call fqb_stats_open first"); return FQB_ERR_STATE; }
     CU_CHECK(cudaSetDevice(h->device));
     if (!n) return FQB_OK;
     if (which == 0) {
-        const PileupTuple *t = static_cast<const PileupTuple *>(src_host);
-        h->tuples_host.insert(h->tuples_host.end(), t, t + n);
+        const size_t at = h->tuples_host.size();
+        h->tuples_host.resize(at + n);
+        CU_CHECK(cudaMemcpyAsync(h->tuples_host.data() + at, src, n * sizeof(PileupTuple), cudaMemcpyDefault, h->stream));
+        CU_CHECK(cudaStreamSynchronize(h->stream));
         return FQB_OK;
     }
     if (which != 1) { set_error("bad variable-size group"); return FQB_ERR_ARG; }
     unsigned long long *tmp = nullptr;
     CU_CHECK(cudaMalloc(&tmp, n * 8));
-    cudaError_t e = cudaMemcpyAsync(tmp, src_host, n * 8, cudaMemcpyHostToDevice, h->stream);
+    cudaError_t e = cudaMemcpyAsync(tmp, src, n * 8, cudaMemcpyDefault, h->stream);
     if (e == cudaSuccess) {
         dup_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_dup_keys, h->dup_cap, tmp, n, h->d_emp + kEmpWords,
                                                                              h->d_emp + (4 * 256 + 4096));

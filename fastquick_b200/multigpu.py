@@ -5,7 +5,9 @@ no data-path collective.  What does cross ranks:
 
   * between `fqb_stage_align` and `fqb_stage_pair` of batch b, the owner of batch b-1 sends the position of the global
     drand48 stream (draws consumed so far) and its insert-size estimate (`last_ii`): 8 + 48 bytes, point to point;
-  * at the end, the integer accumulators are reduced to rank 0 (sum; first-touch order: min).
+  * at the end, the integer accumulators are reduced to rank 0 (sum; first-touch order: min), and the variable-size
+    state -- marker pile-up entries (tagged with their global pair index) and the distinct PCR-duplicate keys --
+    is gathered there; rank 0 then splices the ranks' InsertSizeTable batches into file order and writes the files.
 
 The engine is any object with the small interface used below, so the protocol is testable on CPU with gloo
 (tests/test_multigpu_protocol.py) and runs on NCCL in bench.py.
@@ -47,3 +49,31 @@ def reduce_accumulators(groups, rank, world):
         return
     for t, op in groups:
         dist.reduce(t, dst=0, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MIN)
+
+
+VAR_ITEM_BYTES = {0: 20, 1: 8}     # pile-up entries, duplicate keys (fqb_stats_var_*)
+
+
+def gather_variable(engine, rank, world, device):
+    """Gather the variable-size statistics state onto rank 0 (after reduce_accumulators + import of the sums).
+
+    engine.var_export(which) -> 1-D uint8 torch tensor (on `device` or on the host);  engine.var_import(which, uint8
+    tensor on `device`) on rank 0.
+    """
+    if world == 1:
+        return
+    for which in sorted(VAR_ITEM_BYTES):
+        mine = engine.var_export(which)
+        n = torch.tensor([mine.numel()], dtype=torch.int64, device=device)
+        sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+        dist.all_gather(sizes, n)
+        sizes = [int(x.item()) for x in sizes]
+        cap = max(max(sizes), 1)
+        buf = torch.zeros(cap, dtype=torch.uint8, device=device)
+        buf[: mine.numel()] = mine.to(device)
+        out = [torch.zeros(cap, dtype=torch.uint8, device=device) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, out, dst=0)
+        if rank == 0:
+            for r in range(1, world):
+                if sizes[r]:
+                    engine.var_import(which, out[r][: sizes[r]])

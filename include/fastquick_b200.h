@@ -171,13 +171,13 @@ int fqb_set_pair_base(fqb_handle *h, uint64_t first_pair);
 int fqb_stats_group_bytes(fqb_handle *h, int which, uint64_t *bytes);
 int fqb_stats_export(fqb_handle *h, int which, void *dst_device);
 int fqb_stats_import(fqb_handle *h, int which, const void *src_device);
-/* Variable-size statistics state of a sharded run (host buffers): which = 0 the marker pile-up entries
+/* Variable-size statistics state of a sharded run (host OR device buffers): which = 0 the marker pile-up entries
  * (20 bytes each; they carry their global pair index, so the merged pile-up keeps file order), which = 1 the
  * distinct PCR-duplicate keys of StatCollector's duplicateTable (8 bytes each; a key two handles both hold is
  * one more duplicated pair).  Import on the handle that will call fqb_stats_finish, after fqb_stats_import. */
 int fqb_stats_var_count(fqb_handle *h, int which, uint64_t *n);
-int fqb_stats_var_export(fqb_handle *h, int which, void *dst_host, uint64_t cap);
-int fqb_stats_var_import(fqb_handle *h, int which, const void *src_host, uint64_t n);
+int fqb_stats_var_export(fqb_handle *h, int which, void *dst, uint64_t cap);
+int fqb_stats_var_import(fqb_handle *h, int which, const void *src, uint64_t n);
 int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
 /* new FASTQ pair: restart the drand48 stream and forget last_ii (src/BwtMapper.cpp:1811-1817) */
 int fqb_reset_stream(fqb_handle *h);

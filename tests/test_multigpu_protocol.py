@@ -18,6 +18,7 @@ class FakeEngine:
 
     def __init__(self):
         self.calls, self.ii, self.log, self.acc = 0, [0] * 7, {}, torch.zeros(16, dtype=torch.int64)
+        self.var, self.got = {0: [], 1: []}, {}
 
     def align(self, b):
         pass
@@ -30,6 +31,14 @@ class FakeEngine:
 
     def finish(self, b):
         self.acc[b % 16] += b + 1
+        self.var[0] += [b] * (b % 3)          # a batch-dependent amount of variable-size state
+        self.var[1] += [100 + b]
+
+    def var_export(self, which):
+        return torch.tensor(self.var[which], dtype=torch.uint8)
+
+    def var_import(self, which, t):
+        self.got.setdefault(which, []).append(t.tolist())
 
     def get_state(self):
         return [self.calls] + list(self.ii)
@@ -44,7 +53,8 @@ def _worker(rank, world, n_batches, port, out):
     eng = FakeEngine()
     multigpu.run_sharded(eng, n_batches, rank, world, torch.device("cpu"))
     multigpu.reduce_accumulators([(eng.acc, "sum")], rank, world)
-    out[rank] = (dict(eng.log), eng.acc.clone())
+    multigpu.gather_variable(eng, rank, world, torch.device("cpu"))
+    out[rank] = (dict(eng.log), eng.acc.clone(), dict(eng.var), dict(eng.got))
     dist.destroy_process_group()
 
 
@@ -60,3 +70,6 @@ def test_ring_hand_off_matches_single_process():
         merged.update(out[r][0])
     assert merged == single.log
     assert torch.equal(out[0][1], single.acc)
+    # rank 0 received exactly the variable-size state of rank 1
+    assert out[0][3] == {0: [out[1][2][0]], 1: [out[1][2][1]]}
+    assert sorted(out[0][2][1] + out[1][2][1]) == sorted(single.var[1])
