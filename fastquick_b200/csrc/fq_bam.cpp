@@ -1,0 +1,396 @@
+#include "fq_bam.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <sstream>
+#include <thread>
+
+namespace fqb {
+
+// ---------------------------------------------------------------------------------------------- BGZF
+namespace {
+constexpr size_t kBlockIn = 0xff00;       // payload bytes per block (htslib's BGZF_BLOCK_SIZE)
+
+std::string bgzf_block(const char *data, size_t n) {
+    std::string out(18 + compressBound((uLong)n) + 8, '\0');
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    deflateInit2(&zs, 4, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+    zs.next_in = (Bytef *)data; zs.avail_in = (uInt)n;
+    zs.next_out = (Bytef *)&out[18]; zs.avail_out = (uInt)(out.size() - 18 - 8);
+    deflate(&zs, Z_FINISH);
+    const size_t clen = zs.total_out;
+    deflateEnd(&zs);
+    const size_t total = 18 + clen + 8;
+    static const unsigned char hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+    memcpy(&out[0], hdr, 16);
+    out[16] = (char)((total - 1) & 0xff); out[17] = (char)((total - 1) >> 8);
+    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)data, (uInt)n), isz = (uint32_t)n;
+    memcpy(&out[18 + clen], &crc, 4);
+    memcpy(&out[18 + clen + 4], &isz, 4);
+    out.resize(total);
+    return out;
+}
+}  // namespace
+
+bool BgzfWriter::open(const std::string &path, std::string &err) {
+    fp_ = fopen(path.c_str(), "wb");
+    if (!fp_) { err = "cannot write " + path; return false; }
+    pending_.clear(); failed_ = false;
+    return true;
+}
+void BgzfWriter::write(const void *data, size_t n) {
+    pending_.append((const char *)data, n);
+    if (pending_.size() >= 64 * kBlockIn) flush(false);
+}
+void BgzfWriter::flush(bool all) {
+    const size_t n_blocks = all ? (pending_.size() + kBlockIn - 1) / kBlockIn : pending_.size() / kBlockIn;
+    if (!n_blocks) return;
+    std::vector<std::string> comp(n_blocks);
+    unsigned nthr = std::thread::hardware_concurrency();
+    if (nthr < 1) nthr = 1;
+    if (nthr > 16) nthr = 16;
+    if (nthr > n_blocks) nthr = (unsigned)n_blocks;
+    auto work = [&](unsigned t) {
+        for (size_t b = t; b < n_blocks; b += nthr) {
+            const size_t off = b * kBlockIn, len = std::min(kBlockIn, pending_.size() - off);
+            comp[b] = bgzf_block(pending_.data() + off, len);
+        }
+    };
+    if (nthr == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthr; ++t) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    for (auto &c : comp)
+        if (fwrite(c.data(), 1, c.size(), fp_) != c.size()) failed_ = true;
+    pending_.erase(0, std::min(pending_.size(), n_blocks * kBlockIn));
+}
+bool BgzfWriter::close(std::string &err) {
+    if (!fp_) return true;
+    flush(true);
+    static const unsigned char eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (fwrite(eof, 1, 28, fp_) != 28) failed_ = true;
+    if (fclose(fp_) != 0) failed_ = true;
+    fp_ = nullptr;
+    if (failed_) { err = "write error on the BAM file"; return false; }
+    return true;
+}
+BgzfWriter::~BgzfWriter() { if (fp_) fclose(fp_); }
+
+// ---------------------------------------------------------------------------------------------- header
+static void put32(std::string &o, int32_t v) { o.append((const char *)&v, 4); }
+
+bool bam_prepare(const HostIndex &idx, const fqb_gap_opt_t &g, const std::vector<std::pair<std::string, int>> &genome_contigs,
+                 const std::string &rg_line, BamContext &ctx, std::string &hb, std::string &err) {
+    ctx.idx = &idx; ctx.gopt = g; ctx.refs = genome_contigs; ctx.rg_id.clear();
+    // SetSamFileHeader: @PG, then the @RG tags of --RG, then one @SQ per line of <reference>.fai
+    std::string text = "@PG\tID:FASTQuick\tVN:0.0.1\n";
+    if (rg_line.compare(0, 3, "@RG") == 0) {
+        // bwa_set_rg (libbwa): the ID value becomes bwa_rg_id; SetSamFileHeader re-emits every TAG:value token
+        std::string line = rg_line;
+        for (size_t k = 0; k + 1 < line.size(); ++k)
+            if (line[k] == '\\' && line[k + 1] == 't') { line[k] = '\t'; line.erase(k + 1, 1); }
+        std::stringstream ss(line);
+        std::string tok, out = "@RG";
+        while (ss >> tok) {
+            if (tok == "@RG" || tok.size() < 3) continue;
+            if (tok.compare(0, 3, "ID:") == 0) ctx.rg_id = tok.substr(3);
+        }
+        // libStatGen prints ID first, then the other tags in the order they were set
+        std::stringstream s2(line);
+        if (!ctx.rg_id.empty()) out += "\tID:" + ctx.rg_id;
+        while (s2 >> tok) {
+            if (tok == "@RG" || tok.size() < 3 || tok.compare(0, 3, "ID:") == 0) continue;
+            out += "\t" + tok;
+        }
+        text += out + "\n";
+    }
+    std::map<std::string, int> ref_id;
+    for (size_t i = 0; i < ctx.refs.size(); ++i) {
+        text += "@SQ\tSN:" + ctx.refs[i].first + "\tLN:" + std::to_string(ctx.refs[i].second) + "\n";
+        ref_id[ctx.refs[i].first] = (int)i;
+    }
+    hb.assign("BAM\1", 4);
+    put32(hb, (int32_t)text.size());
+    hb += text;
+    put32(hb, (int32_t)ctx.refs.size());
+    for (auto &r : ctx.refs) { put32(hb, (int32_t)r.first.size() + 1); hb.append(r.first.c_str(), r.first.size() + 1); put32(hb, r.second); }
+    // genome coordinates of the flanks: "<chrom>:<pos>@<ref>/<alt>[L]" (SetSamRecord's BAM_DEBUG branch)
+    const size_t nc = idx.contigs.size();
+    ctx.ref_of_contig.assign(nc, -1); ctx.ref_coord.assign(nc, 0); ctx.is_long.assign(nc, 0); ctx.chrom_of_contig.assign(nc, "");
+    for (size_t c = 0; c < nc; ++c) {
+        const std::string &nm = idx.contigs[c].name;
+        const size_t colon = nm.find(':');
+        ctx.chrom_of_contig[c] = nm.substr(0, colon);
+        if (colon != std::string::npos) ctx.ref_coord[c] = (int)strtol(nm.c_str() + colon + 1, nullptr, 10);
+        ctx.is_long[c] = !nm.empty() && nm.back() == 'L';
+        auto it = ref_id.find(ctx.chrom_of_contig[c]);
+        if (it == ref_id.end()) { err = "chromosome " + ctx.chrom_of_contig[c] + " of flank " + nm + " is not in the reference .fai"; return false; }
+        ctx.ref_of_contig[c] = it->second;
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------- records
+namespace {
+enum { FPD = 1, FPP = 2, FSU = 4, FMU = 8, FSR = 16, FMR = 32 };
+constexpr int kNoMatch = 0, kMateSW = 3;
+
+struct Coor { int seqid; int nn; };
+// bns_coor_pac2real (libbwa/bntseq.c:268-303)
+Coor pac2real(const HostIndex &I, int64_t pac, int len) {
+    int left = 0, mid = 0, right = (int)I.contigs.size();
+    while (left < right) {
+        mid = (left + right) >> 1;
+        if (pac >= I.contigs[mid].offset) {
+            if (mid == (int)I.contigs.size() - 1) break;
+            if (pac < I.contigs[mid + 1].offset) break;
+            left = mid + 1;
+        } else right = mid;
+    }
+    Coor c; c.seqid = mid; c.nn = 0;
+    int l = 0, r = (int)I.holes.size();
+    while (l < r) {
+        const int m = (l + r) >> 1;
+        const Hole &h = I.holes[m];
+        if (pac >= h.offset + h.len) l = m + 1;
+        else if (pac + len <= h.offset) r = m;
+        else {
+            if (pac >= h.offset) c.nn += h.offset + h.len < pac + len ? (int)(h.offset + h.len - pac) : len;
+            else c.nn += h.offset + h.len < pac + len ? h.len : (int)(len - (h.offset - pac));
+            break;
+        }
+    }
+    return c;
+}
+int64_t pos_end(const fqb_read_t &p) {
+    if (p.has_cigar) {
+        int64_t x = p.pos;
+        for (int j = 0; j < p.n_cigar; ++j) { const int op = p.cigar[j] >> 14; if (op == 0 || op == 2) x += p.cigar[j] & 0x3fff; }
+        return x;
+    }
+    return (int64_t)p.pos + p.len;
+}
+int64_t pos_5(const fqb_read_t &p) { return p.type != kNoMatch ? (p.strand ? pos_end(p) : (int64_t)p.pos) : -1; }
+int real_start(const BamContext &C, int seqid, int64_t pac_pos) {
+    const int pos = (int)(pac_pos - C.idx->contigs[seqid].offset + 1);
+    return C.ref_coord[seqid] - (C.is_long[seqid] ? C.gopt.flank_long_len : C.gopt.flank_len) + pos - 1;
+}
+int reg2bin(int32_t beg, int32_t end) {
+    --end;
+    if (beg >> 14 == end >> 14) return ((1 << 15) - 1) / 7 + (beg >> 14);
+    if (beg >> 17 == end >> 17) return ((1 << 12) - 1) / 7 + (beg >> 17);
+    if (beg >> 20 == end >> 20) return ((1 << 9) - 1) / 7 + (beg >> 20);
+    if (beg >> 23 == end >> 23) return ((1 << 6) - 1) / 7 + (beg >> 23);
+    if (beg >> 26 == end >> 26) return ((1 << 3) - 1) / 7 + (beg >> 26);
+    return 0;
+}
+void tag_int(std::string &o, const char *t, int v) {        // SamRecord::addIntTag's choice of the BAM integer type
+    o.append(t, 2);
+    if (v < 0) {
+        if (v > -128) { o.push_back('c'); o.push_back((char)(int8_t)v); }
+        else if (v > -32768) { o.push_back('s'); int16_t x = (int16_t)v; o.append((const char *)&x, 2); }
+        else { o.push_back('i'); o.append((const char *)&v, 4); }
+    } else {
+        if (v < 255) { o.push_back('C'); o.push_back((char)(uint8_t)v); }
+        else if (v < 65535) { o.push_back('S'); uint16_t x = (uint16_t)v; o.append((const char *)&x, 2); }
+        else { o.push_back('I'); uint32_t x = (uint32_t)v; o.append((const char *)&x, 4); }
+    }
+}
+void tag_str(std::string &o, const char *t, const std::string &v) { o.append(t, 2); o.push_back('Z'); o.append(v.c_str(), v.size() + 1); }
+void put_num(std::string &o, long long v) { o += std::to_string(v); }
+
+// the read in alignment orientation as nt4 codes
+void oriented(const uint8_t *bases, int len, int strand, std::vector<uint8_t> &out) {
+    const uint8_t *t = nt4_table();
+    out.resize((size_t)len);
+    for (int j = 0; j < len; ++j) {
+        if (!strand) { const uint8_t c = t[bases[j]]; out[j] = c > 4 ? 4 : c; }
+        else { const uint8_t c = t[bases[len - 1 - j]]; out[j] = c < 4 ? (uint8_t)(3 - c) : 4; }
+    }
+}
+// MD tag of bwa_cal_md1 (libbwa/bwase.c:234-296); seq = the trimmed read in alignment orientation
+std::string md_string(const HostIndex &I, const fqb_read_t &s, const uint16_t *cigar, int n_cigar, bool has_cigar, int len, const uint8_t *seq) {
+    std::string o;
+    auto base = [&](int64_t k) { return (I.pac[(size_t)(k >> 2)] >> ((~k & 3) << 1)) & 3; };
+    int u = 0;
+    int64_t x = s.pos, y = 0;
+    if (has_cigar) {
+        for (int k = 0; k < n_cigar; ++k) {
+            const int l = cigar[k] & 0x3fff, op = cigar[k] >> 14;
+            if (op == 0) {
+                for (int z = 0; z < l && x + z < I.l_pac; ++z) {
+                    const int c = base(x + z);
+                    if (seq[y + z] > 3 || c != seq[y + z]) { put_num(o, u); o.push_back("ACGTN"[c]); u = 0; } else ++u;
+                }
+                x += l; y += l;
+            } else if (op == 1 || op == 3) y += l;
+            else {
+                put_num(o, u); o.push_back('^');
+                for (int z = 0; z < l && x + z < I.l_pac; ++z) o.push_back("ACGT"[base(x + z)]);
+                u = 0; x += l;
+            }
+        }
+    } else {
+        for (int z = 0; z < len; ++z) {
+            const int c = base(x + z);
+            if (seq[y + z] > 3 || c != seq[y + z]) { put_num(o, u); o.push_back("ACGTN"[c]); u = 0; } else ++u;
+        }
+    }
+    put_num(o, u);
+    return o;
+}
+
+void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t &mate, const char *name, const uint8_t *bases, const uint8_t *quals,
+                const XaHit *xa, int n_xa, std::string &out) {
+    const HostIndex &I = *C.idx;
+    int flag = p.extra_flag, j, am = 0;
+    if (p.type == kNoMatch && mate.type == kNoMatch) {
+        // SetSamRecord's "this read has no match" branch (1227-1259): reachable when the bridge check demoted the pair
+        flag |= FSU | FMU;
+        const int L = p.len;
+        const uint8_t *t = nt4_table();
+        std::string seq((size_t)L, 'N'), qual((size_t)L, '\0'), tags;
+        for (int k = 0; k < L; ++k) {
+            if (!p.strand) { const uint8_t c = t[bases[k]]; seq[k] = "ACGTN"[c > 4 ? 4 : c]; }
+            else { const uint8_t c = t[bases[L - 1 - k]]; seq[k] = "TGCAN"[c > 4 ? 4 : c]; }
+            qual[k] = (char)((p.strand ? quals[L - 1 - k] : quals[k]) - 33);
+        }
+        if (!C.rg_id.empty()) tag_str(tags, "RG", C.rg_id);
+        if (p.clip_len < p.full_len) tag_int(tags, "XC", p.clip_len);
+        const int l_name = (int)strlen(name) + 1;
+        put32(out, 32 + l_name + (L + 1) / 2 + L + (int)tags.size());
+        put32(out, -1); put32(out, -1);
+        out.push_back((char)l_name); out.push_back((char)0);
+        { uint16_t b = (uint16_t)reg2bin(-1, 0); out.append((const char *)&b, 2); }
+        { uint16_t n = 0; out.append((const char *)&n, 2); }
+        { uint16_t f = (uint16_t)flag; out.append((const char *)&f, 2); }
+        put32(out, L); put32(out, -1); put32(out, -1); put32(out, 0);
+        out.append(name, (size_t)l_name);
+        for (int k = 0; k < L; k += 2) {
+            static const char *codes = "=ACMGRSVTWYHKDBN";
+            const int hi = (int)(strchr(codes, seq[k]) - codes), lo = k + 1 < L ? (int)(strchr(codes, seq[k + 1]) - codes) : 0;
+            out.push_back((char)(hi << 4 | lo));
+        }
+        out += qual; out += tags;
+        return;
+    }
+    if (p.type == kNoMatch) { p.pos = mate.pos; p.strand = mate.strand; flag |= FSU; j = 1; }
+    else j = (int)(pos_end(p) - p.pos);
+    const Coor co = pac2real(I, p.pos, j);
+    const int seqid = co.seqid;
+    int nn = co.nn;
+    if (p.type != kNoMatch && (int64_t)p.pos + j - I.contigs[seqid].offset > I.contigs[seqid].len) flag |= FSU;
+    if (p.strand) flag |= FSR;
+    if (mate.type != kNoMatch) { if (mate.strand) flag |= FMR; } else flag |= FMU;
+    int ref_id = -1, pos1 = 0, read_real_start = 0;
+    if (p.type != kNoMatch) { read_real_start = real_start(C, seqid, p.pos); ref_id = C.ref_of_contig[seqid]; pos1 = read_real_start; }
+    // CIGAR
+    std::vector<uint32_t> cig;
+    if (p.type != kNoMatch) {
+        if (p.has_cigar) for (int k = 0; k < p.n_cigar; ++k) { static const int opmap[4] = {0, 1, 2, 4}; cig.push_back((uint32_t)(p.cigar[k] & 0x3fff) << 4 | opmap[p.cigar[k] >> 14]); }
+        else cig.push_back((uint32_t)p.len << 4);
+    }
+    // mate fields
+    int mref = -1, mpos1 = 0;
+    long long isize = 0;
+    if (mate.type != kNoMatch) {
+        am = mate.seQ < p.seQ ? mate.seQ : p.seQ;
+        const Coor mc = pac2real(I, mate.pos, mate.len);
+        const int m_start = real_start(C, mc.seqid, mate.pos);
+        mref = seqid == mc.seqid ? ref_id : C.ref_of_contig[mc.seqid];       // "=" resolves to this record's own reference name
+        isize = seqid == mc.seqid ? pos_5(mate) - pos_5(p) : 0;
+        if (p.type == kNoMatch) isize = 0;
+        mpos1 = m_start;
+        read_real_start = m_start;                // the reference reuses the variable; only read again when the mate is unmapped
+    } else { mref = ref_id; mpos1 = read_real_start; isize = 0; }
+    // sequence and qualities in alignment orientation (full length)
+    const int L = p.full_len;
+    const uint8_t *t = nt4_table();
+    std::string seq((size_t)L, 'N'), qual((size_t)L, '\0');
+    for (int k = 0; k < L; ++k) {
+        if (!p.strand) { const uint8_t c = t[bases[k]]; seq[k] = "ACGTN"[c > 4 ? 4 : c]; }
+        else { const uint8_t c = t[bases[L - 1 - k]]; seq[k] = "TGCAN"[c > 4 ? 4 : c]; }
+        qual[k] = (char)((p.strand ? quals[L - 1 - k] : quals[k]) - 33);
+    }
+    // tags
+    std::string tags;
+    if (!C.rg_id.empty()) tag_str(tags, "RG", C.rg_id);
+    if (p.clip_len < p.full_len) tag_int(tags, "XC", p.clip_len);
+    if (p.type != kNoMatch) {
+        char xt = "NURM"[p.type & 3];
+        if (nn > 10) xt = 'N';
+        tags.append("XTA", 3); tags.push_back(xt);
+        tag_int(tags, (C.gopt.mode & 0x02) ? "NM" : "CM", p.nm);          // BWA_MODE_COMPREAD
+        if (nn) tag_int(tags, "XN", nn);
+        tag_int(tags, "SM", p.seQ);
+        tag_int(tags, "AM", am);
+        if (p.type != kMateSW) {
+            tag_int(tags, "X0", (int)p.c1);
+            if ((int)p.c1 <= C.gopt.max_top2) tag_int(tags, "X1", (int)p.c2);
+        }
+        tag_int(tags, "XM", p.n_mm);
+        tag_int(tags, "XO", p.n_gapo);
+        tag_int(tags, "XG", p.n_gapo + p.n_gape);
+        // MD over the trimmed read: strip the soft clip bwa_correct_trimmed appended
+        {
+            std::vector<uint8_t> sq;
+            oriented(bases, L, p.strand, sq);
+            tag_str(tags, "MD", md_string(I, p, p.cigar, p.n_cigar, p.has_cigar != 0, p.len, sq.data()));
+        }
+        if (n_xa) {
+            std::string s;
+            for (int i = 0; i < n_xa; ++i) {
+                const XaHit &q = xa[i];
+                int64_t e = q.pos;
+                if (q.has_cigar) { for (int k = 0; k < q.n_cigar; ++k) { const int op = q.cigar[k] >> 14; if (op == 0 || op == 2) e += q.cigar[k] & 0x3fff; } }
+                else e += p.len;
+                const Coor qc = pac2real(I, q.pos, (int)(e - q.pos));
+                s += I.contigs[qc.seqid].name; s.push_back(',');
+                s.push_back(q.strand ? '-' : '+');
+                put_num(s, (long long)q.pos - I.contigs[qc.seqid].offset + 1); s.push_back(',');
+                if (q.has_cigar) for (int k = 0; k < q.n_cigar; ++k) { put_num(s, q.cigar[k] & 0x3fff); s.push_back("MIDS"[q.cigar[k] >> 14]); }
+                else { put_num(s, p.len); s.push_back('M'); }
+                s.push_back(','); put_num(s, q.gap + q.mm); s.push_back(';');
+            }
+            tag_str(tags, "XA", s);
+        }
+    }
+    // assemble
+    const int l_name = (int)strlen(name) + 1;
+    const int32_t pos0 = pos1 - 1, aln_len = p.type != kNoMatch ? (int32_t)(pos_end(p) - p.pos) : 0;
+    const int32_t end1 = aln_len ? pos0 + aln_len : pos0 + 1;
+    const int bin = reg2bin(pos0, end1);
+    const int32_t block = 32 + l_name + 4 * (int)cig.size() + (L + 1) / 2 + L + (int)tags.size();
+    put32(out, block);
+    put32(out, ref_id); put32(out, pos0);
+    out.push_back((char)l_name); out.push_back((char)p.mapQ);
+    { uint16_t b = (uint16_t)bin; out.append((const char *)&b, 2); }
+    { uint16_t n = (uint16_t)cig.size(); out.append((const char *)&n, 2); }
+    { uint16_t f = (uint16_t)flag; out.append((const char *)&f, 2); }
+    put32(out, L); put32(out, mref); put32(out, mpos1 - 1); put32(out, (int32_t)isize);
+    out.append(name, (size_t)l_name);
+    for (uint32_t c : cig) out.append((const char *)&c, 4);
+    for (int k = 0; k < L; k += 2) {
+        static const char *codes = "=ACMGRSVTWYHKDBN";
+        const int hi = (int)(strchr(codes, seq[k]) - codes), lo = k + 1 < L ? (int)(strchr(codes, seq[k + 1]) - codes) : 0;
+        out.push_back((char)(hi << 4 | lo));
+    }
+    out += qual;
+    out += tags;
+}
+}  // namespace
+
+void bam_append_pair(const BamContext &C, fqb_read_t p, fqb_read_t q, const char *name, const uint8_t *bases_p, const uint8_t *quals_p,
+                     const uint8_t *bases_q, const uint8_t *quals_q, const XaHit *xa_p, int n_xa_p, const XaHit *xa_q, int n_xa_q, std::string &out) {
+    one_record(C, p, q, name, bases_p, quals_p, xa_p, n_xa_p, out);        // may rewrite p's pos/strand (unmapped read of a half-mapped pair)
+    one_record(C, q, p, name, bases_q, quals_q, xa_q, n_xa_q, out);
+}
+
+}  // namespace fqb

@@ -1,0 +1,58 @@
+// BAM emission for the align stage: the records BwtMapper::SetSamRecord builds
+// (src/BwtMapper.cpp:977-1264, compiled with BAM_DEBUG: genome coordinates recovered from the flank
+// names) and the header of SetSamFileHeader (947-975), written as BGZF by host threads.
+// Input: the per-read result rows computed on the GPU, the multi-hit list kernel's output, and the
+// host copies of the reads.  Everything here is formatting; no alignment decision is taken on the host.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/fastquick_b200.h"
+#include "fq_index.h"
+
+namespace fqb {
+
+// BGZF: independent <= 64 KiB gzip members, compressed by a few host threads, written in order
+class BgzfWriter {
+public:
+    bool open(const std::string &path, std::string &err);
+    void write(const void *data, size_t n);
+    bool close(std::string &err);                   // flushes, writes the EOF block
+    ~BgzfWriter();
+private:
+    void flush(bool all);
+    FILE *fp_ = nullptr;
+    std::string pending_;
+    bool failed_ = false;
+};
+
+struct XaHit { uint32_t pos; uint8_t strand, gap, mm, has_cigar, n_cigar; uint16_t cigar[FQB_MAX_CIGAR]; };
+
+struct BamContext {
+    const HostIndex *idx = nullptr;
+    fqb_gap_opt_t gopt;
+    std::string rg_id;                              // bwa_rg_id ("" = no RG tag)
+    std::vector<std::pair<std::string, int>> refs;  // @SQ: BwtIndexer::contigSize (<reference>.fai)
+    std::vector<int> ref_of_contig;                 // flank contig -> index into refs (-1 = chromosome not in the .fai)
+    std::vector<int> ref_coord;                     // marker coordinate parsed from the flank name
+    std::vector<uint8_t> is_long;                   // flank name ends in 'L'
+    std::vector<std::string> chrom_of_contig;
+};
+
+// "@PG ... @RG ... @SQ ..." text + binary reference list; rg_line as passed to --RG (or empty)
+bool bam_prepare(const HostIndex &idx, const fqb_gap_opt_t &g, const std::vector<std::pair<std::string, int>> &genome_contigs,
+                 const std::string &rg_line, BamContext &ctx, std::string &header_bytes, std::string &err);
+
+// Appends the two records of one pair (nothing when both reads are filtered or both unmapped; the caller decides
+// that with the types the reads had BEFORE StatCollector::AddAlignment's bridge check demoted any of them, as
+// the reference's loop does, src/BwtMapper.cpp:2058-2066).
+// p, q: result rows (taken by value: SetSamRecord edits the unmapped read of a half-mapped pair).
+// bases/quals: the reads as they came from the FASTQ files (ASCII), full_len bytes each.
+void bam_append_pair(const BamContext &ctx, fqb_read_t p, fqb_read_t q, const char *name, const uint8_t *bases_p, const uint8_t *quals_p,
+                     const uint8_t *bases_q, const uint8_t *quals_q, const XaHit *xa_p, int n_xa_p, const XaHit *xa_q, int n_xa_q,
+                     std::string &out);
+
+}  // namespace fqb

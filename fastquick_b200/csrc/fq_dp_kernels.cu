@@ -2,6 +2,7 @@
 // Main path: one alignment per WARP (fq_dp_warp.cuh), DP rows in shared memory, trace-back in a warp-private
 // slab of the global pool.  Alignments whose window does not fit go to a retry list handled by the
 // one-alignment-per-lane kernels (rows and trace-back in warp-interleaved global scratch).
+#include <cstdlib>
 #include "fq_dp_kernels.cuh"
 #include "fq_dp_warp.cuh"
 
@@ -157,6 +158,55 @@ __global__ void __launch_bounds__(kDpThreads) refine_kernel(DpView v, DpPool poo
     }
 }
 
+// ---- XA: the other hits of reads that keep a multi list (rare: n_occ <= n_multi + 1) ----
+__global__ void multi_classify_kernel(DpView v, uint32_t *list, uint32_t *ctr) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (uint32_t)v.n_reads) return;
+    const fqb_read_t &s = v.rows[r];
+    if (s.filtered || s.type == kTypeNoMatch || s.n_multi == 0) return;
+    const uint32_t i = atomicAdd(ctr, 1u);
+    list[2 * i] = r;
+    list[2 * i + 1] = atomicAdd(ctr + 1, (uint32_t)s.n_multi);
+}
+__global__ void __launch_bounds__(kDpThreads) multi_kernel(DpView v, MultiView mv, DpPool pool, const uint32_t *list, uint32_t *ctr, MultiOut *out,
+                                                            uint32_t out_cap, uint32_t *err) {
+    DpScratch sc = lane_scratch(pool);
+    const uint32_t n = ctr[0];
+    uint32_t it;
+    while (next_item(ctr + 2, n, it)) {
+        const uint32_t r = list[2 * it], base = list[2 * it + 1];
+        const fqb_read_t s = v.rows[r];
+        const int spill = mv.spill_slot[r];
+        const Hit *al = spill >= 0 ? mv.aln_big + (size_t)spill * mv.aln_big_cap : mv.aln + (size_t)r * mv.aln_cap;
+        const int na = mv.n_aln[r], len = s.clip_len;          // positions and CIGARs use the trimmed read, as the reference does at that point
+        int z = 0;
+        for (int k = 0; k < na && z < s.n_multi; ++k)
+            for (uint32_t row = al[k].k; row <= al[k].l && z < s.n_multi; ++row) {
+                if (row == s.sa) continue;
+                if (base + z >= out_cap) { atomicExch(err, r + 1); return; }
+                MultiOut o;
+                o.read = r; o.j = (uint8_t)z; o.strand = al[k].a; o.gap = (uint8_t)(al[k].n_gapo + al[k].n_gape); o.mm = al[k].n_mm;
+                o.pos = hit_position(mv.bwt, al[k].a, row, len);
+                o.n_cigar = 0; o.has_cigar = 0; o.pad_[0] = o.pad_[1] = 0;
+                for (int c = 0; c < FQB_MAX_CIGAR; ++c) o.cigar[c] = 0;
+                if (o.gap) {
+                    ReadSeq Q; Q.fwd = v.codes + (size_t)r * v.lpad; Q.len = len; Q.strand = o.strand;
+                    const int nc = refine_gapped(v.l_pac, v.pac, Q, &o.pos, (o.strand ? 1 : -1) * (int)o.gap, o.cigar, FQB_MAX_CIGAR, sc);
+                    if (nc < 0) { atomicExch(err, r + 1); return; }
+                    o.n_cigar = (uint8_t)nc; o.has_cigar = 1;
+                }
+                out[base + z] = o;
+                ++z;
+            }
+    }
+}
+void launch_multi(const DpView &v, const MultiView &mv, const DpPool &pool, uint32_t *list, uint32_t *ctr, MultiOut *out, uint32_t out_cap,
+                  uint32_t *err, cudaStream_t s) {
+    cudaMemsetAsync(ctr, 0, 3 * 4, s);
+    multi_classify_kernel<<<(v.n_reads + 255) / 256, 256, 0, s>>>(v, list, ctr);
+    multi_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, mv, pool, list, ctr, out, out_cap, err);
+}
+
 // NM (bwa_cal_md1's count) + bwa_correct_trimmed for every read
 __global__ void finish_kernel(DpView v) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,8 +235,12 @@ void launch_sw(const DpView &v, const SwParams &sp, const DpPool &pool, uint32_t
     const int ref_cap = kSwSmemInts;                                     // reference codes of the window, one byte each
     const size_t smem = (size_t)ints * kWarpsPerBlock * 4 + (size_t)ref_cap * kWarpsPerBlock;
     cudaFuncSetAttribute(sw_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sw_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, sp, pool, list, ctr, ctr + 1, ints, ref_cap, retry, ctr + 2);
-    sw_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, sp, pool, retry, ctr + 2, ctr + 3, err);
+    if (getenv("FQB_DP_NO_WARP"))        // debugging aid: everything through the one-alignment-per-lane kernels
+        sw_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, sp, pool, list, ctr, ctr + 1, err);
+    else {
+        sw_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, sp, pool, list, ctr, ctr + 1, ints, ref_cap, retry, ctr + 2);
+        sw_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, sp, pool, retry, ctr + 2, ctr + 3, err);
+    }
 }
 void launch_refine(const DpView &v, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, int max_read_len, cudaStream_t s) {
     refine_classify_kernel<<<(v.n_reads + 255) / 256, 256, 0, s>>>(v, list, ctr);
@@ -195,8 +249,12 @@ void launch_refine(const DpView &v, const DpPool &pool, uint32_t *list, uint32_t
     const int ref_cap = (ints / 6 + 3) & ~3;                             // window columns + 1, padded to a word
     const size_t smem = (size_t)ints * kWarpsPerBlock * 4 + (size_t)ref_cap * kWarpsPerBlock;
     cudaFuncSetAttribute(refine_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    refine_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, pool, list, ctr, ctr + 1, ints, ref_cap, retry, ctr + 2);
-    refine_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, pool, retry, ctr + 2, ctr + 3, err);
+    if (getenv("FQB_DP_NO_WARP"))
+        refine_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, pool, list, ctr, ctr + 1, err);
+    else {
+        refine_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, pool, list, ctr, ctr + 1, ints, ref_cap, retry, ctr + 2);
+        refine_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, pool, retry, ctr + 2, ctr + 3, err);
+    }
     finish_kernel<<<(v.n_reads + 255) / 256, 256, 0, s>>>(v);
 }
 

@@ -20,6 +20,24 @@ struct DpPool {
     int ints_per_lane, bytes_per_lane, n_blocks;
 };
 
+// Alternative hits of a read for the XA tag (bwa_aln2seq_core's multi list, libbwa/bwase.c:47-95; positions as in
+// bwa_cal_pac_pos_pe, src/BwtMapper.cpp:877-885; CIGARs of gapped ones as in bwa_refine_gapped, libbwa/bwase.c:361-368)
+struct MultiOut {
+    uint32_t read, pos;
+    uint8_t strand, gap, mm, n_cigar;
+    uint8_t j, has_cigar, pad_[2];
+    uint16_t cigar[FQB_MAX_CIGAR];
+};
+struct MultiView {
+    const Hit *aln; int aln_cap;
+    const Hit *aln_big; int aln_big_cap;
+    const int32_t *spill_slot, *n_aln;
+    DevBwt bwt[2];
+};
+// list: 2 words per selected read (read, first output slot); ctr: [0] n_list [1] n_out [2] cursor
+void launch_multi(const DpView &v, const MultiView &mv, const DpPool &pool, uint32_t *list, uint32_t *ctr, MultiOut *out, uint32_t out_cap,
+                  uint32_t *err, cudaStream_t s);
+
 void launch_sw(const DpView &v, const SwParams &sp, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, cudaStream_t s);
 void launch_refine(const DpView &v, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, int max_read_len, cudaStream_t s);
 

@@ -224,7 +224,7 @@ __device__ LocalResult warp_local_align(const RefWin &R, int len1, const ReadSeq
     for (int j = end_j - 1; j != 0; --j) {
         const uint32_t qj = Q.at(j - 1);
         const bool qn = qj > 3;
-        int carry_g = kVeryNeg, carry_h = 0;
+        int carry_g = kVeryNeg, carry_h = 0, carry_hmax = kVeryNeg;
         int row_best = score_r, row_best_i = 0;
         int hit_i = 0;
         bool hit = false;
@@ -254,7 +254,16 @@ __device__ LocalResult warp_local_align(const RefWin &R, int len1, const ReadSeq
                 H[i + 1] = hnext; E[i] = e;
                 if (h > row_best) { row_best = h; row_best_i = i; }     // descending i per lane, strict > keeps the first
             }
-            const unsigned hm = __ballot_sync(FQB_FULL, on && h - qr == score_f && h > score_r);
+            // the reference stops at a cell only if it is a NEW running maximum (cells are visited in descending i) that
+            // equals score_f + qr; the reverse pass can exceed that value elsewhere in the row (the forward pass cuts
+            // e-chains below q + r, the reverse pass does not), so the running maximum has to be reproduced exactly
+            const int hx = warp_incl_max(on ? h : kVeryNeg, lane);
+            int run = __shfl_up_sync(FQB_FULL, hx, 1);
+            if (lane == 0) run = kVeryNeg;
+            if (carry_hmax > run) run = carry_hmax;
+            if (score_r > run) run = score_r;
+            { const int t = __shfl_sync(FQB_FULL, hx, nact - 1); if (t > carry_hmax) carry_hmax = t; }
+            const unsigned hm = __ballot_sync(FQB_FULL, on && h > run && h - qr == score_f);
             if (hm) { hit = true; hit_i = base - (__ffs(hm) - 1); break; }
         }
         if (hit) { score_r = score_f + qr; start_i = hit_i; start_j = j; break; }

@@ -18,6 +18,7 @@
 #include "fq_dp_kernels.cuh"
 #include "fq_stats_kernels.cuh"
 #include "fq_stats_host.h"
+#include "fq_bam.h"
 #include <algorithm>
 #include <fstream>
 #include <thread>
@@ -125,6 +126,10 @@ struct fqb_handle {
     std::vector<PileupColumn> pileup;
     std::vector<PileupTuple> tuples_host;          // pile-up entries drained from the device (own batches + imported ones)
     std::vector<FileCounters> files;
+    // BAM emission (row f1)
+    BgzfWriter bam; bool bam_open = false; BamContext bam_ctx;
+    MultiOut *d_multi_out = nullptr; uint32_t *d_multi_list = nullptr, *d_multi_ctr = nullptr; uint32_t multi_cap = 0;
+    fqb_read_t *h_bam_rows = nullptr; size_t h_bam_rows_cap = 0;
     std::ofstream isize_table;
     std::string isize_table_path;
     std::vector<std::pair<uint64_t, uint64_t>> isize_table_idx;   // (first global pair, bytes) of every emitted batch, in emission order
@@ -313,7 +318,9 @@ void fqb_destroy(fqb_handle *h) {
     cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_ctrs); cudaFree(h->d_order_bins); cudaFree(h->d_counters);
     cudaFree(h->d_arena); cudaFree(h->d_arena_mid); cudaFree(h->d_arena_big); cudaFree(h->d_aln_big);
     cudaFree(h->pesc.totals); cudaFree(h->pesc.err_flag); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch); cudaFree(h->dp_pool.ints); cudaFree(h->dp_pool.bytes); cudaFree(h->d_dpctr);
-    cudaFreeHost(h->h_rows); cudaFreeHost(h->h_pstat);
+    cudaFreeHost(h->h_rows); cudaFreeHost(h->h_pstat); cudaFreeHost(h->h_bam_rows);
+    cudaFree(h->d_multi_out); cudaFree(h->d_multi_list); cudaFree(h->d_multi_ctr);
+    if (h->bam_open) { std::string e; h->bam.close(e); }
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); if (h->ev_rq[i]) cudaEventDestroy(h->ev_rq[i]); }
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1071,6 +1078,129 @@ int fqb_stage_counters(fqb_handle *h, uint64_t *out4) {
 int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
 int fqb_stage_pair(fqb_handle *h);
 int fqb_stage_sw_refine(fqb_handle *h);
+
+// ---- BAM emission (row f1): SetSamFileHeader / SetSamRecord / BamIO.writeRecord (src/BwtMapper.cpp:947-1264, 2068-2074) ----
+int fqb_bam_open(fqb_handle *h, const char *path, const char *rg_line) {
+    if (!h || !path) { set_error("null argument"); return FQB_ERR_ARG; }
+    if (!h->stats_open) { set_error("fqb_bam_open: call fqb_stats_open first (it loads the reference's contig list)"); return FQB_ERR_STATE; }
+    if (h->bam_open) { set_error("a BAM file is already open on this handle"); return FQB_ERR_STATE; }
+    std::string err, header;
+    if (!bam_prepare(h->hidx, h->gopt, h->stabs.genome_contigs, rg_line ? rg_line : "", h->bam_ctx, header, err)) { set_error(err); return FQB_ERR_IO; }
+    if (!h->bam.open(path, err)) { set_error(err); return FQB_ERR_IO; }
+    h->bam.write(header.data(), header.size());
+    h->bam_open = true;
+    return FQB_OK;
+}
+
+int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const uint8_t *bases1, const uint8_t *quals1,
+                 const uint8_t *bases2, const uint8_t *quals2, int32_t stride) {
+    if (!h || !h->bam_open) { set_error("fqb_bam_emit: no BAM file open"); return FQB_ERR_STATE; }
+    if (!h->dp_done || (h->stats_open && !h->stats_done)) { set_error("fqb_bam_emit: the batch must be through fqb_stage_sw_refine and fqb_stage_stats"); return FQB_ERR_STATE; }
+    if (!bases1 || !quals1 || !bases2 || !quals2 || stride < 1) { set_error("fqb_bam_emit: the reads of the batch are required"); return FQB_ERR_ARG; }
+    CU_CHECK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const size_t np = (size_t)h->n_reads / 2;
+    // the other hits of reads that keep a multi list (XA): positions and CIGARs come from the device
+    if (h->multi_cap < (uint32_t)h->cap_reads) {
+        cudaFree(h->d_multi_out); cudaFree(h->d_multi_list); cudaFree(h->d_multi_ctr);
+        h->multi_cap = (uint32_t)h->cap_reads;                                    // multi lists are rare (n_occ <= n_multi + 1); one slot per read is ample
+        CU_CHECK(cudaMalloc(&h->d_multi_out, (size_t)h->multi_cap * sizeof(MultiOut)));
+        CU_CHECK(cudaMalloc(&h->d_multi_list, (size_t)h->cap_reads * 2 * 4));
+        CU_CHECK(cudaMalloc(&h->d_multi_ctr, 4 * 4));
+    }
+    DpView dv;
+    dv.n_reads = h->n_reads; dv.lpad = h->lpad; dv.codes = h->bv.codes; dv.pac = h->d_pac; dv.l_pac = h->hidx.l_pac; dv.rows = h->d_rows;
+    MultiView mv;
+    mv.aln = h->d_aln; mv.aln_cap = kAlnCapFast; mv.aln_big = h->d_aln_big; mv.aln_big_cap = kAlnCapSlow; mv.spill_slot = h->d_spill_slot; mv.n_aln = h->d_naln;
+    mv.bwt[0] = h->dbwt[0]; mv.bwt[1] = h->dbwt[1];
+    CU_CHECK(cudaMemsetAsync((h->d_dpctr + 8), 0, 4, st));
+    launch_multi(dv, mv, h->dp_pool, h->d_multi_list, h->d_multi_ctr, h->d_multi_out, h->multi_cap, (h->d_dpctr + 8), st);
+    h->n_launches += 2;
+    uint32_t ctr[2] = {0, 0}, derr = 0;
+    CU_CHECK(cudaMemcpyAsync(ctr, h->d_multi_ctr, 8, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaMemcpyAsync(&derr, (h->d_dpctr + 8), 4, cudaMemcpyDeviceToHost, st));
+    if (np > h->h_bam_rows_cap) {
+        cudaFreeHost(h->h_bam_rows); h->h_bam_rows = nullptr; h->h_bam_rows_cap = 0;
+        CU_CHECK(cudaMallocHost(&h->h_bam_rows, 2 * np * sizeof(fqb_read_t)));
+        h->h_bam_rows_cap = np;
+    }
+    CU_CHECK(cudaMemcpyAsync(h->h_bam_rows, h->d_rows, 2 * np * sizeof(fqb_read_t), cudaMemcpyDeviceToHost, st));
+    const bool have_ps = h->stats_done && h->d_pstat;
+    if (have_ps) {
+        if (np > h->h_rows_cap) {
+            cudaFreeHost(h->h_rows); cudaFreeHost(h->h_pstat);
+            h->h_rows = nullptr; h->h_pstat = nullptr; h->h_rows_cap = 0;
+            CU_CHECK(cudaMallocHost(&h->h_rows, 2 * np * sizeof(fqb_read_t)));
+            CU_CHECK(cudaMallocHost(&h->h_pstat, np * sizeof(PairStat)));
+            h->h_rows_cap = np;
+        }
+        CU_CHECK(cudaMemcpyAsync(h->h_pstat, h->d_pstat, np * sizeof(PairStat), cudaMemcpyDeviceToHost, st));
+    }
+    CU_CHECK(cudaStreamSynchronize(st));
+    if (derr) { set_error("multi-hit list: capacity exceeded for read " + std::to_string(derr - 1)); return FQB_ERR_LIMIT; }
+    std::vector<MultiOut> mo(ctr[1]);
+    if (ctr[1]) CU_CHECK(cudaMemcpy(mo.data(), h->d_multi_out, (size_t)ctr[1] * sizeof(MultiOut), cudaMemcpyDeviceToHost));
+    std::sort(mo.begin(), mo.end(), [](const MultiOut &a, const MultiOut &b) { return a.read != b.read ? a.read < b.read : a.j < b.j; });
+    std::vector<XaHit> xa(mo.size());
+    for (size_t i = 0; i < mo.size(); ++i) {
+        XaHit &x = xa[i];
+        x.pos = mo[i].pos; x.strand = mo[i].strand; x.gap = mo[i].gap; x.mm = mo[i].mm; x.has_cigar = mo[i].has_cigar; x.n_cigar = mo[i].n_cigar;
+        memcpy(x.cigar, mo[i].cigar, sizeof x.cigar);
+    }
+    auto xa_of = [&](uint32_t r, int &n) -> const XaHit * {
+        auto lo = std::lower_bound(mo.begin(), mo.end(), r, [](const MultiOut &a, uint32_t v) { return a.read < v; });
+        auto hi = lo;
+        while (hi != mo.end() && hi->read == r) ++hi;
+        n = (int)(hi - lo);
+        return n ? &xa[(size_t)(lo - mo.begin())] : nullptr;
+    };
+    // records are formatted by several host threads over contiguous slices of the batch and written in order
+    const uint64_t first = h->pairs_seen - (h->stats_done ? np : 0);
+    unsigned nthr = std::thread::hardware_concurrency();
+    if (nthr < 1) nthr = 1;
+    if (nthr > 16) nthr = 16;
+    if (np < 4096) nthr = 1;
+    std::vector<std::string> parts(nthr);
+    auto work = [&](unsigned t) {
+        std::string &o = parts[t];
+        const size_t lo = np * t / nthr, hi = np * (t + 1) / nthr;
+        o.reserve((hi - lo) * 2 * (size_t)(160 + 3 * stride / 2));
+        char buf[64];
+        std::string nm;
+        for (size_t i = lo; i < hi; ++i) {
+            const fqb_read_t &p = h->h_bam_rows[2 * i], &q = h->h_bam_rows[2 * i + 1];
+            // skip decisions use the types the reads had before AddAlignment's bridge check (kept in the pair record)
+            if (have_ps ? (h->h_pstat[i].both_filtered || h->h_pstat[i].both_unmapped)
+                        : ((p.filtered && q.filtered) || (p.type == kTypeNoMatch && q.type == kTypeNoMatch))) continue;
+            const char *name;
+            if (names) { nm.assign(names + i * (size_t)name_stride, strnlen(names + i * (size_t)name_stride, (size_t)name_stride)); name = nm.c_str(); }
+            else { snprintf(buf, sizeof buf, "r%011llu", (unsigned long long)(first + i)); name = buf; }
+            int n0 = 0, n1 = 0;
+            const XaHit *x0 = p.n_multi ? xa_of((uint32_t)(2 * i), n0) : nullptr, *x1 = q.n_multi ? xa_of((uint32_t)(2 * i + 1), n1) : nullptr;
+            bam_append_pair(h->bam_ctx, p, q, name, bases1 + i * (size_t)stride, quals1 + i * (size_t)stride, bases2 + i * (size_t)stride,
+                            quals2 + i * (size_t)stride, x0, n0, x1, n1, o);
+        }
+    };
+    if (nthr == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nthr; ++t) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    size_t total = 0;
+    for (auto &o : parts) { h->bam.write(o.data(), o.size()); total += o.size(); }
+    if (getenv("FQB_BAM_DEBUG")) fprintf(stderr, "bam_emit: %zu pairs, %u multi hits, %zu bytes, have_ps %d, threads %u\n", np, ctr[1], total, (int)have_ps, nthr);
+    return FQB_OK;
+}
+
+int fqb_bam_close(fqb_handle *h) {
+    if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    if (!h->bam_open) return FQB_OK;
+    h->bam_open = false;
+    std::string err;
+    if (!h->bam.close(err)) { set_error(err); return FQB_ERR_IO; }
+    return FQB_OK;
+}
 
 // The whole per-batch body of BwtMapper::PairEndMapper up to (not including) the statistics loop.
 // Upload the NEXT batch on the copy stream while the current one is being processed; the following

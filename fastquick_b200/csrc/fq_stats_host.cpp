@@ -159,7 +159,7 @@ bool build_stats_tables(const HostIndex &idx, const std::string &prefix, const f
         par >> k >> ref_path;
         std::ifstream fai(ref_path + ".fai");
         std::string line;
-        while (std::getline(fai, line)) { std::stringstream ss(line); std::string chr, len; ss >> chr >> len; T.ref_genome_size += (uint64_t)atoi(len.c_str()); }
+        while (std::getline(fai, line)) { std::stringstream ss(line); std::string chr, len; ss >> chr >> len; T.ref_genome_size += (uint64_t)atoi(len.c_str()); T.genome_contigs.emplace_back(chr, atoi(len.c_str())); }
         std::ifstream amb(ref_path + ".amb");
         while (std::getline(amb, line)) { std::stringstream ss(line); std::string off, nlen; ss >> off >> nlen; T.ref_N_size += (uint64_t)atoi(nlen.c_str()); }
     }

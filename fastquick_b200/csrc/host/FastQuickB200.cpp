@@ -93,10 +93,11 @@ BwtMapper::BwtMapper(BwtIndexer &BwtIndex, const std::string &FQList, const std:
     p.N_multi = popt->N_multi; p.type = popt->type; p.is_sw = popt->is_sw; p.ap_prior = popt->ap_prior;
     if (fqb_create(RefPath.c_str(), &g, &p, device, &h_) != FQB_OK) error("%s", fqb_last_error());
     collector.Attach(h_);
-    if (opt->out_bam) warning("%s.bam is not written by the GPU stage yet (BAM emission is the next row of the plan)", Prefix.c_str());
     double t_tmp = realtime();
     collector.RestoreVcfSites(RefPath, opt);
     notice("Restore Variant Site Info...%f sec", realtime() - t_tmp);
+    bam_out_ = opt->out_bam != 0;
+    if (bam_out_ && fqb_bam_open(h_, (Prefix + ".bam").c_str(), opt->RG.c_str()) != FQB_OK) error("%s", fqb_last_error());   // SetSamFileHeader + writeHeader
     auto run_pair = [&](const std::string &f1, const std::string &f2) {
         notice("Processing Pair End mapping\t%s\t%s", f1.c_str(), f2.c_str());
         double t0 = realtime();
@@ -119,6 +120,7 @@ BwtMapper::BwtMapper(BwtIndexer &BwtIndex, const std::string &FQList, const std:
         }
     } else if (Fastq_2 != "Empty") run_pair(Fastq_1, Fastq_2);
     else error("Single End mapping is not supported by the GPU stage yet");
+    if (bam_out_ && fqb_bam_close(h_) != FQB_OK) error("%s", fqb_last_error());
     double t1 = realtime();
     collector.ProcessCore(Prefix, opt);
     notice("Calculate distributions... %f sec", realtime() - t1);
@@ -159,6 +161,7 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
         if (fqb_align_pairs(h_, B.n[0], stride, B.b[0], B.q[0], B.l[0], B.b[1], B.q[1], B.l[1], nullptr, nullptr, nullptr) != FQB_OK) error("%s", fqb_last_error());
         if (fqb_stage_stats(h_) != FQB_OK) error("%s", fqb_last_error());
         if (fqb_stats_emit(h_, B.nm[0], name_stride) != FQB_OK) error("%s", fqb_last_error());
+        if (bam_out_ && fqb_bam_emit(h_, B.nm[0], name_stride, B.b[0], B.q[0], B.b[1], B.q[1], stride) != FQB_OK) error("%s", fqb_last_error());
         FSC.NumRead += 2LL * B.n[0];
         if (FSC.NumRead % FQB_BATCH_PAIRS == 0) fprintf(stderr, "NOTICE - %lld sequences are processed.\n", FSC.NumRead);
         next.join();

@@ -75,6 +75,7 @@ private:
     fqb_handle *h_ = nullptr;
     StatCollector collector;
     std::string prefix_;
+    bool bam_out_ = false;
 };
 
 int runAlign(int argc, char **argv);

@@ -115,6 +115,16 @@ int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride,
                     const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2,
                     fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
 
+/* ---- BAM output (SetSamFileHeader / SetSamRecord / BamIO.writeRecord, src/BwtMapper.cpp:947-1264, 2068-2074) ----
+ * fqb_bam_open needs fqb_stats_open first (it loads <reference>.fai for the @SQ lines); rg_line is the --RG value
+ * ("@RG\tID:foo\tSM:bar") or NULL.  fqb_bam_emit appends the records of the resident batch, after
+ * fqb_stage_sw_refine and -- when statistics are collected -- after fqb_stage_stats, as the reference writes them
+ * after StatCollector::AddAlignment; names as for fqb_stats_emit; bases/quals are the batch's host arrays. */
+int fqb_bam_open(fqb_handle *h, const char *path, const char *rg_line);
+int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride,
+                 const uint8_t *bases1, const uint8_t *quals1, const uint8_t *bases2, const uint8_t *quals2, int32_t stride);
+int fqb_bam_close(fqb_handle *h);
+
 /* The reference's IO workers read batch n+1 while batch n is being mapped
  * (src/BwtMapper.cpp:1905-1931).  Same overlap here: upload the NEXT batch on a
  * copy stream into the second staging set; the following fqb_align_pairs /

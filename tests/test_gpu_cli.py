@@ -1,11 +1,15 @@
 """Drop-in check at the CLI level: `FASTQuick_b200 align` (C++ host over the C ABI) vs the reference's own
 `FASTQuick align` (oracle/_ref/FASTQuick_ref), same flags as bin/FASTQuick.sh --steps Align passes, same FASTQ files;
-every summary file must be identical (BAM emission is the next row and is not compared)."""
+every summary file must be identical, and the BAM files must hold the same header and the same records (every fixed
+field and every tag; tag order inside a record is libStatGen's hash order and is not compared)."""
 import os
 import subprocess
 
 import pytest
 
+import numpy as np
+
+import bamio
 import fx
 from test_gpu_stats import TEXT_FILES, _compare_files
 
@@ -32,3 +36,49 @@ def test_cli_align_matches_reference(small_index, ref_required):
     va = [l for l in open(outs["ref"] + ".vcf") if not l.startswith("##fileDate")]
     vb = [l for l in open(outs["b200"] + ".vcf") if not l.startswith("##fileDate")]
     assert va == vb
+
+
+def _compare_bams(p_ref, p_mine):
+    ta, ra, a = bamio.read_bam(p_ref)
+    tb, rb, b = bamio.read_bam(p_mine)
+    assert ta == tb, "BAM header text differs"
+    assert ra == rb
+    assert len(a) == len(b), (len(a), len(b))
+    for i, (x, y) in enumerate(zip(a, b)):
+        if x != y:
+            j = i ^ 1
+            strip = lambda r: {k: v for k, v in r.items() if k not in ("qual", "seq")}
+            raise AssertionError((i, {k: (x[k], y[k]) for k in x if x[k] != y[k]}, strip(x), strip(y), strip(a[j]), strip(b[j])))
+    return a
+
+
+def test_cli_bam_matches_reference(small_index, ref_required):
+    """Row f1: the records of BwtMapper::SetSamRecord.  The input mixes well-behaved pairs, indel-rich pairs (gapped
+    CIGARs, MD with deletions, XA of gapped alternative hits), quality-trimmed reads (XC, soft clips), half-mapped pairs
+    (one end replaced by noise: mate-unmapped flags, the unmapped read placed at its mate) and off-target pairs."""
+    if not os.path.exists(fx.REF_BIN):
+        pytest.skip("FASTQuick_ref not built")
+    a = small_index.reads(3000, read_len=100, seed=83, f_on=0.9)
+    b = small_index.reads(1500, read_len=100, seed=84, sub_rate=0.03, ins_rate=0.006, del_rate=0.006, max_indel_len=3)
+    arrs = [np.concatenate([x, y]) for x, y in zip(a, b)]
+    rng = np.random.default_rng(7)
+    junk = rng.choice(len(arrs[0]), 300, replace=False)
+    for i in junk:                                   # one end becomes random sequence
+        e = 0 if i % 2 else 2
+        arrs[e][i] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, arrs[e].shape[1])]
+    fq = small_index.write_fastq("clibam", arrs)
+    idx_prefix = small_index.prefix[: -len(".FASTQuick.fa")]
+    outs = {}
+    for tag, exe in (("ref", fx.REF_BIN), ("b200", CLI)):
+        out = os.path.join(small_index.dir, "clibam_" + tag)
+        cmd = [exe, "align", "--fastq_1", fq[0], "--fastq_2", fq[1], "--index_prefix", idx_prefix, "--out_prefix", out, "--t", "4", "--q", "15"]
+        r = subprocess.run(cmd, cwd=small_index.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-3000:]
+        outs[tag] = out
+    recs = _compare_bams(outs["ref"] + ".bam", outs["b200"] + ".bam")
+    assert len(recs) > 7000
+    assert sum(1 for r in recs if r["flag"] & 4) > 50          # unmapped reads of half-mapped pairs
+    assert sum(1 for r in recs if "XC" in r["tags"]) > 300     # quality-trimmed reads
+    assert sum(1 for r in recs if "D" in r["cigar"] or "I" in r["cigar"]) > 300
+    for ext in TEXT_FILES:
+        _compare_files(outs["ref"] + "." + ext, outs["b200"] + "." + ext)

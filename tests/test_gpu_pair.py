@@ -113,3 +113,40 @@ def test_sw_and_refine_indel_rich_150(small_index, ref_required):
     arrs = small_index.reads(3000, read_len=150, seed=62, sub_rate=0.02, ins_rate=0.004, del_rate=0.004, max_indel_len=3)
     st = _run_full(small_index, arrs, "f150", 3000)
     assert st["matesw"] > 200
+
+
+def test_sw_long_indels_near_read_ends(small_index, ref_required):
+    """Mate rescue of reads whose indel sits a few bases from the read start: the forward pass of aln_local_core cuts
+    the gap chain there (h < q + r), the reverse pass does not, so the reverse score overtakes score_f + q + r and the
+    reference's stop rule must be reproduced as a running maximum (regression test for the warp-cooperative kernel)."""
+    arrs = small_index.reads(6000, read_len=100, seed=84, sub_rate=0.03, ins_rate=0.006, del_rate=0.006, max_indel_len=3)
+    st = _run_full(small_index, arrs, "fends", 3000)
+    assert st["matesw"] > 300
+
+
+def test_warp_and_per_lane_dp_kernels_agree(small_index):
+    """The one-alignment-per-warp kernels and the per-lane kernels (FQB_DP_NO_WARP, the retry path) give identical rows."""
+    import os
+    import zlib
+    arrs = small_index.reads(8000, read_len=100, seed=85, sub_rate=0.03, ins_rate=0.008, del_rate=0.008, max_indel_len=4)
+    lib = fx.host_lib()
+    g = _abi.GapOpt()
+    lib.fqb_gap_opt_default(C.byref(g))
+    g.trim_qual = 15
+    crcs = []
+    for no_warp in (False, True):
+        if no_warp:
+            os.environ["FQB_DP_NO_WARP"] = "1"
+        try:
+            h = C.c_void_p()
+            assert lib.fqb_create(small_index.prefix.encode(), C.byref(g), None, 0, C.byref(h)) == 0, lib.fqb_last_error()
+            n, L = arrs[0].shape
+            rows = [np.zeros(n, _abi.READ_DTYPE) for _ in range(2)]
+            assert lib.fqb_align_pairs(h, n, L, _abi.u8p(arrs[0]), _abi.u8p(arrs[1]), None, _abi.u8p(arrs[2]), _abi.u8p(arrs[3]), None,
+                                       rows[0].ctypes.data_as(C.c_void_p), rows[1].ctypes.data_as(C.c_void_p), None) == 0, lib.fqb_last_error()
+            lib.fqb_destroy(h)
+            crcs.append((zlib.crc32(rows[0].tobytes()), zlib.crc32(rows[1].tobytes())))
+        finally:
+            os.environ.pop("FQB_DP_NO_WARP", None)
+    assert crcs[0] == crcs[1]
+    assert int((rows[0]["type"] == 3).sum() + (rows[1]["type"] == 3).sum()) > 500
