@@ -247,13 +247,19 @@ std::string md_string(const HostIndex &I, const fqb_read_t &s, const uint16_t *c
     return o;
 }
 
-void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t &mate, const char *name, const uint8_t *bases, const uint8_t *quals,
+// mate_ptr == nullptr: single-end input (SetSamRecord(..., mate = 0, ...))
+void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t *mate_ptr, const char *name, const uint8_t *bases, const uint8_t *quals,
                 const XaHit *xa, int n_xa, std::string &out) {
+    fqb_read_t absent;
+    memset(&absent, 0, sizeof absent);
+    const bool has_mate = mate_ptr != nullptr;
+    const fqb_read_t &mate = has_mate ? *mate_ptr : absent;
     const HostIndex &I = *C.idx;
     int flag = p.extra_flag, j, am = 0;
     if (p.type == kNoMatch && mate.type == kNoMatch) {
         // SetSamRecord's "this read has no match" branch (1227-1259): reachable when the bridge check demoted the pair
-        flag |= FSU | FMU;
+        flag |= FSU;
+        if (has_mate) flag |= FMU;
         const int L = p.len;
         const uint8_t *t = nt4_table();
         std::string seq((size_t)L, 'N'), qual((size_t)L, '\0'), tags;
@@ -288,7 +294,7 @@ void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t &mate, cons
     int nn = co.nn;
     if (p.type != kNoMatch && (int64_t)p.pos + j - I.contigs[seqid].offset > I.contigs[seqid].len) flag |= FSU;
     if (p.strand) flag |= FSR;
-    if (mate.type != kNoMatch) { if (mate.strand) flag |= FMR; } else flag |= FMU;
+    if (has_mate) { if (mate.type != kNoMatch) { if (mate.strand) flag |= FMR; } else flag |= FMU; }
     int ref_id = -1, pos1 = 0, read_real_start = 0;
     if (p.type != kNoMatch) { read_real_start = real_start(C, seqid, p.pos); ref_id = C.ref_of_contig[seqid]; pos1 = read_real_start; }
     // CIGAR
@@ -309,7 +315,8 @@ void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t &mate, cons
         if (p.type == kNoMatch) isize = 0;
         mpos1 = m_start;
         read_real_start = m_start;                // the reference reuses the variable; only read again when the mate is unmapped
-    } else { mref = ref_id; mpos1 = read_real_start; isize = 0; }
+    } else if (has_mate) { mref = ref_id; mpos1 = read_real_start; isize = 0; }
+    else { mref = -1; mpos1 = 0; isize = 0; }
     // sequence and qualities in alignment orientation (full length)
     const int L = p.full_len;
     const uint8_t *t = nt4_table();
@@ -329,8 +336,7 @@ void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t &mate, cons
         tags.append("XTA", 3); tags.push_back(xt);
         tag_int(tags, (C.gopt.mode & 0x02) ? "NM" : "CM", p.nm);          // BWA_MODE_COMPREAD
         if (nn) tag_int(tags, "XN", nn);
-        tag_int(tags, "SM", p.seQ);
-        tag_int(tags, "AM", am);
+        if (has_mate) { tag_int(tags, "SM", p.seQ); tag_int(tags, "AM", am); }
         if (p.type != kMateSW) {
             tag_int(tags, "X0", (int)p.c1);
             if ((int)p.c1 <= C.gopt.max_top2) tag_int(tags, "X1", (int)p.c2);
@@ -389,8 +395,13 @@ void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t &mate, cons
 
 void bam_append_pair(const BamContext &C, fqb_read_t p, fqb_read_t q, const char *name, const uint8_t *bases_p, const uint8_t *quals_p,
                      const uint8_t *bases_q, const uint8_t *quals_q, const XaHit *xa_p, int n_xa_p, const XaHit *xa_q, int n_xa_q, std::string &out) {
-    one_record(C, p, q, name, bases_p, quals_p, xa_p, n_xa_p, out);        // may rewrite p's pos/strand (unmapped read of a half-mapped pair)
-    one_record(C, q, p, name, bases_q, quals_q, xa_q, n_xa_q, out);
+    one_record(C, p, &q, name, bases_p, quals_p, xa_p, n_xa_p, out);       // may rewrite p's pos/strand (unmapped read of a half-mapped pair)
+    one_record(C, q, &p, name, bases_q, quals_q, xa_q, n_xa_q, out);
+}
+
+void bam_append_single(const BamContext &C, fqb_read_t p, const char *name, const uint8_t *bases, const uint8_t *quals, const XaHit *xa, int n_xa,
+                       std::string &out) {
+    one_record(C, p, nullptr, name, bases, quals, xa, n_xa, out);
 }
 
 }  // namespace fqb

@@ -55,4 +55,8 @@ void bam_append_pair(const BamContext &ctx, fqb_read_t p, fqb_read_t q, const ch
                      const uint8_t *bases_q, const uint8_t *quals_q, const XaHit *xa_p, int n_xa_p, const XaHit *xa_q, int n_xa_q,
                      std::string &out);
 
+// Single-end input: the record SetSamRecord(bns, p, 0, ...) builds (SingleEndMapper, src/BwtMapper.cpp:1384-1388)
+void bam_append_single(const BamContext &ctx, fqb_read_t p, const char *name, const uint8_t *bases, const uint8_t *quals, const XaHit *xa, int n_xa,
+                       std::string &out);
+
 }  // namespace fqb

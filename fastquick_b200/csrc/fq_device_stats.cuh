@@ -112,6 +112,8 @@ FQB_HD uint16_t sam_flag(const fqb_read_t &p) { return (uint16_t)(p.extra_flag |
 FQB_HD int pair_status(const ContigDev *ctg, int n_ctg, const fqb_read_t &p, const fqb_read_t &q, int type, const StatAccum &A, PairStat &o) {
     int maxInsert = -1, maxInsert2 = -1;
     o.flag[0] = sam_flag(p); o.flag[1] = sam_flag(q);
+    if (q.full_len == 0) o.flag[1] = 0;          // single-end input: the reference passes q = NULL (flag2 stays 0)
+    if (p.full_len == 0) o.flag[0] = 0;
     o.actual_insert = -1;
     if (type != 1) {                                   // single end: e = the aligned read
         const fqb_read_t &e = type == 0 ? p : q;

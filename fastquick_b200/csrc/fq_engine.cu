@@ -108,6 +108,7 @@ struct fqb_handle {
     uint64_t rng_x0 = 0, rng_calls = 0;  // srand48(bns->seed) stream position (src/BwtMapper.cpp:1817)
     fqb_isize_t last_ii, cur_ii;
     bool align_done = false, pair_done = false, dp_done = false;
+    bool single_end = false;                     // the resident batch came without second reads (SingleEndMapper)
     uint32_t *d_sw_list = nullptr, *d_refine_list = nullptr;   // each: work list followed by its retry list
     uint32_t *d_dpctr = nullptr;                             // [0..3] SW list/cursors, [4..7] refine list/cursors, [8] error
     DpPool dp_pool = {nullptr, nullptr, 0, 0, 0};
@@ -345,6 +346,8 @@ int fqb_stage_load(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t
     int rc = ensure_batch(h, 2 * n_pairs, stride);
     if (rc) return rc;
     h->n_reads = 2 * n_pairs; h->stride = stride;
+    if (!bases1 || !quals1 || (bases2 && !quals2)) { set_error("bases and qualities are required"); return FQB_ERR_ARG; }
+    h->single_end = bases2 == nullptr;
     const uint8_t *src[4] = {bases1, quals1, bases2, quals2};
     const int32_t *lsrc[2] = {lens1, lens2};
     BatchView &b = h->bv;
@@ -362,13 +365,14 @@ int fqb_stage_load(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t
         } else {
             set = h->pre_set >= 0 ? 1 - h->pre_set : 0;         // do not disturb a pending prefetch of another batch
             CU_CHECK(cudaStreamWaitEvent(h->stream, h->ev_free[set], 0));
-            for (int i = 0; i < 4; ++i) CU_CHECK(cudaMemcpyAsync(h->d_in[set][i], src[i], bytes, cudaMemcpyHostToDevice, h->stream));
+            for (int i = 0; i < 4; ++i) if (src[i]) CU_CHECK(cudaMemcpyAsync(h->d_in[set][i], src[i], bytes, cudaMemcpyHostToDevice, h->stream));
             for (int i = 0; i < 2; ++i)
                 if (lsrc[i]) CU_CHECK(cudaMemcpyAsync(h->d_lens_in[set][i], lsrc[i], (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
         }
         if (set == h->pre_set) h->pre_set = -1;
         h->cur_set = set;
-        b.bases_in[0] = h->d_in[set][0]; b.quals_in[0] = h->d_in[set][1]; b.bases_in[1] = h->d_in[set][2]; b.quals_in[1] = h->d_in[set][3];
+        b.bases_in[0] = h->d_in[set][0]; b.quals_in[0] = h->d_in[set][1];
+        b.bases_in[1] = bases2 ? h->d_in[set][2] : nullptr; b.quals_in[1] = bases2 ? h->d_in[set][3] : nullptr;
         b.lens_in[0] = lens1 ? h->d_lens_in[set][0] : nullptr; b.lens_in[1] = lens2 ? h->d_lens_in[set][1] : nullptr;
     }
     b.n_work = h->d_ctrs;
@@ -475,10 +479,27 @@ int fqb_stage_pair(fqb_handle *h) {
     v.n_reads = h->n_reads;
     v.aln = h->d_aln; v.aln_cap = kAlnCapFast; v.aln_big = h->d_aln_big; v.aln_big_cap = kAlnCapSlow;
     v.spill_slot = h->d_spill_slot; v.n_aln = h->d_naln; v.filtered = h->bv.filtered;
-    v.len = h->bv.len; v.full_len = h->bv.full_len; v.rows = h->d_rows;
+    v.len = h->bv.len; v.full_len = h->bv.full_len; v.rows = h->d_rows; v.single_end = h->single_end ? 1 : 0;
     SeParams sp;
     sp.bwt[0] = h->dbwt[0]; sp.bwt[1] = h->dbwt[1]; sp.maxdiff = h->d_maxdiff; sp.g_log_n = h->d_log_n;
     RngState rng{h->rng_x0, h->rng_calls};
+    if (h->single_end) {
+        // SingleEndMapper (src/BwtMapper.cpp:1335-1348): bwa_aln2seq_core(..., 1, N_OCC) + bwa_cal_pac_pos; no insert size, no pairing
+        CU_CHECK(cudaMemsetAsync(h->pesc.err_flag, 0, 4, st));
+        launch_se(v, sp, rng, h->pesc, st);
+        h->n_launches += 8;
+        uint64_t totals[2] = {0, 0};
+        uint32_t err = 0;
+        CU_CHECK(cudaMemcpyAsync(totals, h->pesc.totals, 16, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaMemcpyAsync(&err, h->pesc.err_flag, 4, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaMemsetAsync(h->d_ctrs + 12, 0, 16, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+        CU_CHECK(cudaGetLastError());
+        if (err) { set_error("drand48 returned exactly 0.0 for a read with one best interval (p = 2^-48 per read): unsupported"); return FQB_ERR_LIMIT; }
+        h->rng_calls += totals[0];
+        h->pair_done = true; h->dp_done = false;
+        return FQB_OK;
+    }
     CU_CHECK(cudaMemsetAsync(h->pesc.err_flag, 0, 4, st));
     CU_CHECK(cudaMemsetAsync(h->d_hist, 0, (kIsizeBins + 1) * 4, st));
     launch_se(v, sp, rng, h->pesc, st);
@@ -552,7 +573,7 @@ int fqb_stage_sw_refine(fqb_handle *h) {
     DpView v;
     v.n_reads = h->n_reads; v.lpad = h->lpad; v.codes = h->bv.codes; v.pac = h->d_pac; v.l_pac = h->hidx.l_pac; v.rows = h->d_rows;
     const fqb_isize_t &ii = h->cur_ii;
-    if (h->popt.is_sw && ii.avg >= 0.0) {
+    if (h->popt.is_sw && ii.avg >= 0.0 && !h->single_end) {
         SwParams sp;
         sp.avg = ii.avg; sp.std = ii.std; sp.l_pac = h->hidx.l_pac;
         sp.s_old_add = -4.343 * std::log(ii.ap_prior / h->hidx.l_pac);                      // libbwa/bwape.c:577
@@ -685,8 +706,9 @@ int fqb_stage_stats(fqb_handle *h) {
     launch_bases(v, B, st);
     h->n_launches += 2;
     CU_CHECK(cudaGetLastError());
-    h->files.back().NumRead += 2 * (long long)np;
-    add_scalar_kernel<<<1, 1, 0, st>>>(h->d_emp + 4 * 256 + 4096 + 8, 2ull * np);     // NumRead, kept on the device too so that sharded runs sum it
+    const unsigned long long n_in = h->single_end ? np : 2ull * np;        // reads that came from the FASTQ file(s)
+    h->files.back().NumRead += (long long)n_in;
+    add_scalar_kernel<<<1, 1, 0, st>>>(h->d_emp + 4 * 256 + 4096 + 8, n_in);     // NumRead, kept on the device too so that sharded runs sum it
     h->pairs_seen += np;
     h->stats_done = true;
     return FQB_OK;
@@ -1096,7 +1118,7 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
                  const uint8_t *bases2, const uint8_t *quals2, int32_t stride) {
     if (!h || !h->bam_open) { set_error("fqb_bam_emit: no BAM file open"); return FQB_ERR_STATE; }
     if (!h->dp_done || (h->stats_open && !h->stats_done)) { set_error("fqb_bam_emit: the batch must be through fqb_stage_sw_refine and fqb_stage_stats"); return FQB_ERR_STATE; }
-    if (!bases1 || !quals1 || !bases2 || !quals2 || stride < 1) { set_error("fqb_bam_emit: the reads of the batch are required"); return FQB_ERR_ARG; }
+    if (!bases1 || !quals1 || stride < 1 || (!h->single_end && (!bases2 || !quals2))) { set_error("fqb_bam_emit: the reads of the batch are required"); return FQB_ERR_ARG; }
     CU_CHECK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const size_t np = (size_t)h->n_reads / 2;
@@ -1177,8 +1199,9 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
             else { snprintf(buf, sizeof buf, "r%011llu", (unsigned long long)(first + i)); name = buf; }
             int n0 = 0, n1 = 0;
             const XaHit *x0 = p.n_multi ? xa_of((uint32_t)(2 * i), n0) : nullptr, *x1 = q.n_multi ? xa_of((uint32_t)(2 * i + 1), n1) : nullptr;
-            bam_append_pair(h->bam_ctx, p, q, name, bases1 + i * (size_t)stride, quals1 + i * (size_t)stride, bases2 + i * (size_t)stride,
-                            quals2 + i * (size_t)stride, x0, n0, x1, n1, o);
+            if (h->single_end) bam_append_single(h->bam_ctx, p, name, bases1 + i * (size_t)stride, quals1 + i * (size_t)stride, x0, n0, o);
+            else bam_append_pair(h->bam_ctx, p, q, name, bases1 + i * (size_t)stride, quals1 + i * (size_t)stride, bases2 + i * (size_t)stride,
+                                 quals2 + i * (size_t)stride, x0, n0, x1, n1, o);
         }
     };
     if (nthr == 1) work(0);
@@ -1215,7 +1238,7 @@ int fqb_prefetch_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uin
     const int32_t *lsrc[2] = {lens1, lens2};
     const size_t bytes = (size_t)n_pairs * stride;
     CU_CHECK(cudaStreamWaitEvent(h->copy_stream, h->ev_free[set], 0));
-    for (int i = 0; i < 4; ++i) CU_CHECK(cudaMemcpyAsync(h->d_in[set][i], src[i], bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    for (int i = 0; i < 4; ++i) if (src[i]) CU_CHECK(cudaMemcpyAsync(h->d_in[set][i], src[i], bytes, cudaMemcpyHostToDevice, h->copy_stream));
     for (int i = 0; i < 2; ++i)
         if (lsrc[i]) CU_CHECK(cudaMemcpyAsync(h->d_lens_in[set][i], lsrc[i], (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->copy_stream));
     CU_CHECK(cudaEventRecord(h->ev_in[set], h->copy_stream));

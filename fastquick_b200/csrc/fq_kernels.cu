@@ -45,6 +45,10 @@ __global__ void __launch_bounds__(256) prep_kernel(BatchView b, PrepParams p) {
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (int r = warp; r < b.n_reads; r += n_warps) {
         const int e = r & 1, pr = r >> 1;
+        if (e && !b.bases_in[1]) {          // single-end input: the second read of every slot is absent
+            if (lane == 0) { b.n_ambig[r] = 0; b.len[r] = 0; b.full_len[r] = 0; b.filtered[r] = 1; }
+            continue;
+        }
         const uint8_t *bi = (e ? b.bases_in[1] : b.bases_in[0]) + (size_t)pr * b.stride_in;
         const uint8_t *qi = (e ? b.quals_in[1] : b.quals_in[0]) + (size_t)pr * b.stride_in;
         const int32_t *li = e ? b.lens_in[1] : b.lens_in[0];

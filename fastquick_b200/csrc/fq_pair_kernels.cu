@@ -99,7 +99,7 @@ __global__ void se_final_kernel(PeView v, SeParams sp, const uint64_t *packed, c
     for (int i = 0; i < (int)(sizeof(row) / 4); ++i) rw[i] = 0;
     row.len = v.len[r]; row.full_len = v.full_len[r]; row.clip_len = row.len;
     row.filtered = v.filtered[r];
-    row.extra_flag = kSamPaired | ((r & 1) ? kSamRead2 : kSamRead1);
+    row.extra_flag = v.single_end ? 0 : (kSamPaired | ((r & 1) ? kSamRead2 : kSamRead1));
     const int na = n_hits_of(v, r);
     row.n_aln = (uint16_t)(na > 65535 ? 65535 : na);
     if (na > 0) {
@@ -113,6 +113,16 @@ __global__ void se_final_kernel(PeView v, SeParams sp, const uint64_t *packed, c
         const int max_diff = sp.maxdiff[row.len];
         row.pos = hit_position(sp.bwt, row.strand, row.sa, row.len);
         row.seQ = row.mapQ = (uint8_t)approx_mapq(row.c1, row.c2, row.n_mm, max_diff, sp.g_log_n);
+        if (v.single_end) {
+            // bwa_aln2seq_core(..., set_main = 1, n_multi = N_OCC = 3): keep the other hits only when there are at most N_OCC of them
+            const Hit *al = hits_of(v, r);
+            uint32_t n_occ = 0, others = 0;
+            for (int k = 0; k < na; ++k) {
+                n_occ += al[k].l - al[k].k + 1;
+                others += al[k].l - al[k].k + 1 - ((row.sa >= al[k].k && row.sa <= al[k].l) ? 1u : 0u);
+            }
+            row.n_multi = n_occ > 3u + 1u ? 0 : (uint8_t)(others < 3u ? others : 3u);
+        }
     }
     v.rows[r] = row;
 }

@@ -14,6 +14,7 @@ struct PeView {
     const uint8_t *filtered;
     const int32_t *len, *full_len;
     fqb_read_t *rows;
+    int single_end;                 // SingleEndMapper: no pairing flags, multi list of up to N_OCC hits (src/BwtMapper.cpp:1340)
 };
 struct SeParams {
     DevBwt bwt[2];

@@ -105,6 +105,13 @@ BwtMapper::BwtMapper(BwtIndexer &BwtIndex, const std::string &FQList, const std:
         PairEndMapper(f1, f2, opt, FSC);
         notice("Processed Pair End mapping in %f sec", realtime() - t0);
     };
+    auto run_single = [&](const std::string &f1) {
+        notice("Processing Single End mapping\t%s\n", f1.c_str());
+        double t0 = realtime();
+        FileStatCollector FSC(f1.c_str());
+        SingleEndMapper(f1, opt, FSC);
+        notice("Processed Single End mapping in %f sec", realtime() - t0);
+    };
     if (FQList != "Empty") {
         notice("Open Fastq List ...");
         std::ifstream fin(FQList);
@@ -115,11 +122,10 @@ BwtMapper::BwtMapper(BwtIndexer &BwtIndex, const std::string &FQList, const std:
             std::string a, b;
             std::stringstream ss(line);
             ss >> a >> b;
-            if (b.empty()) error("Single End mapping is not supported by the GPU stage yet");
-            run_pair(a, b);
+            if (b.empty()) run_single(a); else run_pair(a, b);
         }
     } else if (Fastq_2 != "Empty") run_pair(Fastq_1, Fastq_2);
-    else error("Single End mapping is not supported by the GPU stage yet");
+    else run_single(Fastq_1);
     if (bam_out_ && fqb_bam_close(h_) != FQB_OK) error("%s", fqb_last_error());
     double t1 = realtime();
     collector.ProcessCore(Prefix, opt);
@@ -170,6 +176,41 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
     notice("%lld sequences are loaded.", FSC.NumRead);
     for (auto &B : bufs) for (int e = 0; e < 2; ++e) { fqb_host_free(B.b[e]); fqb_host_free(B.q[e]); fqb_host_free(B.l[e]); fqb_host_free(B.nm[e]); }
     r[0].close(); r[1].close();
+    return 0;
+}
+
+// BwtMapper::SingleEndMapper (src/BwtMapper.cpp:1266-1407): same stages on batches that carry first reads only
+bool BwtMapper::SingleEndMapper(const std::string &fq1, const gap_opt_t *opt, FileStatCollector &FSC) {
+    FastqReader r;
+    if (!r.open(fq1)) error("Open fastq failed: %s", fq1.c_str());
+    if (fqb_stats_begin_file(h_, prefix_.c_str(), fq1.c_str(), "") != FQB_OK) error("%s", fqb_last_error());
+    const int stride = opt->read_len < FQB_MAX_READ_LEN ? opt->read_len : FQB_MAX_READ_LEN, cap = FQB_BATCH_PAIRS, name_stride = 64;
+    struct Buf { uint8_t *b, *q; int32_t *l; char *nm; int n; } bufs[3];
+    for (auto &B : bufs) {
+        B.b = (uint8_t *)fqb_host_alloc((size_t)cap * stride); B.q = (uint8_t *)fqb_host_alloc((size_t)cap * stride);
+        B.l = (int32_t *)fqb_host_alloc((size_t)cap * 4); B.nm = (char *)fqb_host_alloc((size_t)cap * name_stride);
+        if (!B.b || !B.q || !B.l || !B.nm) error("pinned host allocation failed");
+        B.n = 0;
+    }
+    auto load = [&](Buf &B) { B.n = r.fill(cap, stride, B.b, B.q, B.l, B.nm, name_stride); };
+    int cur = 0;
+    load(bufs[0]);
+    if (bufs[0].n > 0) load(bufs[1]);
+    while (bufs[cur].n > 0) {
+        Buf &B = bufs[cur], &N1 = bufs[(cur + 1) % 3], &N2 = bufs[(cur + 2) % 3];
+        if (N1.n > 0 && fqb_prefetch_pairs(h_, N1.n, stride, N1.b, N1.q, N1.l, nullptr, nullptr, nullptr) != FQB_OK) error("%s", fqb_last_error());
+        std::thread next([&]() { if (N1.n > 0) load(N2); else N2.n = 0; });
+        if (fqb_align_pairs(h_, B.n, stride, B.b, B.q, B.l, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr) != FQB_OK) error("%s", fqb_last_error());
+        if (fqb_stage_stats(h_) != FQB_OK) error("%s", fqb_last_error());
+        if (fqb_stats_emit(h_, B.nm, name_stride) != FQB_OK) error("%s", fqb_last_error());
+        if (bam_out_ && fqb_bam_emit(h_, B.nm, name_stride, B.b, B.q, nullptr, nullptr, stride) != FQB_OK) error("%s", fqb_last_error());
+        FSC.NumRead += B.n;
+        next.join();
+        cur = (cur + 1) % 3;
+    }
+    notice("%lld sequences are loaded.", FSC.NumRead);
+    for (auto &B : bufs) { fqb_host_free(B.b); fqb_host_free(B.q); fqb_host_free(B.l); fqb_host_free(B.nm); }
+    r.close();
     return 0;
 }
 

@@ -51,6 +51,7 @@ public:
     std::string FileName1, FileName2;
     FileStatCollector() = default;
     FileStatCollector(const char *f1, const char *f2) : FileName1(f1), FileName2(f2) {}
+    explicit FileStatCollector(const char *f1) : FileName1(f1), FileName2("") {}      // src/StatCollector.h:58
 };
 
 // StatCollector: accumulation lives on the GPU inside the engine; this object is the handle-side view
@@ -71,6 +72,7 @@ public:
               const std::string &targetRegionPath, int device = 0);
     ~BwtMapper();
     bool PairEndMapper(const std::string &fq1, const std::string &fq2, const gap_opt_t *opt, FileStatCollector &FSC);
+    bool SingleEndMapper(const std::string &fq1, const gap_opt_t *opt, FileStatCollector &FSC);
 private:
     fqb_handle *h_ = nullptr;
     StatCollector collector;

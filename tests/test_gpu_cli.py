@@ -82,3 +82,30 @@ def test_cli_bam_matches_reference(small_index, ref_required):
     assert sum(1 for r in recs if "D" in r["cigar"] or "I" in r["cigar"]) > 300
     for ext in TEXT_FILES:
         _compare_files(outs["ref"] + "." + ext, outs["b200"] + "." + ext)
+
+
+def test_cli_single_end_matches_reference(small_index, ref_required):
+    """Row f3: SingleEndMapper (src/BwtMapper.cpp:1266-1407) -- bwa_aln2seq_core with a multi list of up to 3 hits,
+    bwa_cal_pac_pos, gapped refinement, AddAlignment(p, 0), SetSamRecord(p, 0): every summary file and every BAM record."""
+    if not os.path.exists(fx.REF_BIN):
+        pytest.skip("FASTQuick_ref not built")
+    a = small_index.reads(4000, read_len=100, seed=87, f_on=0.9)
+    b = small_index.reads(1500, read_len=100, seed=88, sub_rate=0.03, ins_rate=0.006, del_rate=0.006, max_indel_len=3)
+    arrs = [np.concatenate([x, y]) for x, y in zip(a, b)]
+    fq = small_index.write_fastq("clise", arrs)
+    idx_prefix = small_index.prefix[: -len(".FASTQuick.fa")]
+    outs = {}
+    for tag, exe in (("ref", fx.REF_BIN), ("b200", CLI)):
+        out = os.path.join(small_index.dir, "clise_" + tag)
+        cmd = [exe, "align", "--fastq_1", fq[0], "--index_prefix", idx_prefix, "--out_prefix", out, "--t", "4", "--q", "15"]
+        r = subprocess.run(cmd, cwd=small_index.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-3000:]
+        assert "Processed Single End mapping in" in r.stdout
+        outs[tag] = out
+    for ext in TEXT_FILES:
+        _compare_files(outs["ref"] + "." + ext, outs["b200"] + "." + ext)
+    va = [l for l in open(outs["ref"] + ".vcf") if not l.startswith("##fileDate")]
+    vb = [l for l in open(outs["b200"] + ".vcf") if not l.startswith("##fileDate")]
+    assert va == vb
+    recs = _compare_bams(outs["ref"] + ".bam", outs["b200"] + ".bam")
+    assert len(recs) > 4000 and sum(1 for r in recs if "XC" in r["tags"]) > 300
