@@ -1,4 +1,5 @@
 #include "FastQuickB200.h"
+#include <random>
 
 #include <cstdarg>
 #include <cstdio>
@@ -52,13 +53,19 @@ struct FastqReader {
             s.append(b, end - pos); pos = end;
         }
     }
-    // returns the number of records read (<= n_max)
-    int fill(int n_max, int stride, uint8_t *bases, uint8_t *quals, int32_t *lens, char *names, int name_stride) {
+    // returns the number of records kept (<= n_max).  frac < 1: --frac_samp, the reference's per-record draw from a Mersenne
+    // twister re-seeded with the IO round of the batch (src/BwtMapper.cpp:483-505; VerifyBamID/Random.cpp:155-198), so both
+    // files of a pair drop the same records
+    int fill(int n_max, int stride, uint8_t *bases, uint8_t *quals, int32_t *lens, char *names, int name_stride, double frac = 1.0, uint32_t seed = 0) {
         std::string hdr, seq, plus, qual;
+        std::mt19937 mt(seed);
         int n = 0;
-        while (n < n_max && getline(hdr)) {
+        while (n < n_max) {
+            const double rand_num = ((double)mt() + 0.5) * (1.0 / 4294967296.0);
+            if (!getline(hdr)) break;
             if (hdr.empty()) continue;
             if (!getline(seq) || !getline(plus) || !getline(qual)) error("truncated FASTQ record");
+            if (rand_num > frac) continue;
             if (seq.size() != qual.size()) error("sequence and quality lengths differ in a FASTQ record");
             if ((int)seq.size() > stride) error("read longer than %d bases: not supported", stride);
             memset(bases + (size_t)n * stride, 'N', (size_t)stride);
@@ -149,9 +156,12 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
             if (!B.b[e] || !B.q[e] || !B.l[e] || !B.nm[e]) error("pinned host allocation failed");
             B.n[e] = 0;
         }
+    int n_loaded = 0;                     // IO rounds: the reference reads batches 0 and 1 with round 0, batch k >= 1 with round k - 1
     auto load = [&](Buf &B) {
-        std::thread t0([&]() { B.n[0] = r[0].fill(cap, stride, B.b[0], B.q[0], B.l[0], B.nm[0], name_stride); });
-        B.n[1] = r[1].fill(cap, stride, B.b[1], B.q[1], B.l[1], B.nm[1], name_stride);
+        const uint32_t seed = n_loaded ? (uint32_t)(n_loaded - 1) : 0u;
+        ++n_loaded;
+        std::thread t0([&]() { B.n[0] = r[0].fill(cap, stride, B.b[0], B.q[0], B.l[0], B.nm[0], name_stride, opt->frac, seed); });
+        B.n[1] = r[1].fill(cap, stride, B.b[1], B.q[1], B.l[1], B.nm[1], name_stride, opt->frac, seed);
         t0.join();
     };
     auto good = [](const Buf &B) { return B.n[0] > 0 && B.n[1] > 0; };
@@ -244,7 +254,7 @@ int runAlign(int argc, char **argv) {
     if (Prefix == "Empty") error("--out_prefix is required");
     if (IndexPrefix == "Empty") error("--index_prefix is required");
     if (BamIn != "Empty") error("Input alignments from Bam file is disabled.");
-    if (opt.frac < 1.0) error("--frac_samp < 1 is not supported by the GPU stage yet");
+    if (opt.frac < 1.0 && Fastq_2 == "Empty" && FaList == "Empty") error("--frac_samp < 1 with single-end input is seeded from clock() in the reference and is not reproducible; not supported");
     if (sam_out) opt.out_bam = 0;
     opt.RG = ReadGroup;
     if (opte > 0) { opt.max_gape = opte; opt.mode &= ~0x01; }

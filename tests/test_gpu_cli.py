@@ -109,3 +109,24 @@ def test_cli_single_end_matches_reference(small_index, ref_required):
     assert va == vb
     recs = _compare_bams(outs["ref"] + ".bam", outs["b200"] + ".bam")
     assert len(recs) > 4000 and sum(1 for r in recs if "XC" in r["tags"]) > 300
+
+
+def test_cli_frac_samp_matches_reference(small_index, ref_required):
+    """--frac_samp: both implementations drop the same records (Mersenne twister re-seeded per IO round)."""
+    if not os.path.exists(fx.REF_BIN):
+        pytest.skip("FASTQuick_ref not built")
+    arrs = small_index.reads(6000, read_len=100, seed=89)
+    fq = small_index.write_fastq("clifrac", arrs)
+    idx_prefix = small_index.prefix[: -len(".FASTQuick.fa")]
+    outs = {}
+    for tag, exe in (("ref", fx.REF_BIN), ("b200", CLI)):
+        out = os.path.join(small_index.dir, "clifrac_" + tag)
+        cmd = [exe, "align", "--fastq_1", fq[0], "--fastq_2", fq[1], "--index_prefix", idx_prefix, "--out_prefix", out, "--t", "4", "--q", "15",
+               "--frac_samp", "0.4"]
+        r = subprocess.run(cmd, cwd=small_index.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-3000:]
+        outs[tag] = out
+    for ext in TEXT_FILES + ["FASTQ.csv"]:
+        _compare_files(outs["ref"] + "." + ext, outs["b200"] + "." + ext)
+    recs = _compare_bams(outs["ref"] + ".bam", outs["b200"] + ".bam")
+    assert 3500 < len(recs) < 6000          # about 40 % of 6000 pairs, two records each
