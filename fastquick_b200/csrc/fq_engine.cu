@@ -114,6 +114,7 @@ struct fqb_handle {
     DpPool dp_pool = {nullptr, nullptr, 0, 0, 0};
     // statistics rows (a12-a14)
     bool stats_open = false, stats_done = false;
+    std::string target_bed;                      // --targetRegion, set before fqb_stats_open
     StatsTables stabs;
     ContigDev *d_ctg = nullptr;
     uint32_t *d_site = nullptr; int32_t *d_marker = nullptr;
@@ -629,12 +630,20 @@ static void build_pileup(fqb_handle *h) {
     }
 }
 
+// StatCollector::SetTargetRegion (src/BwtMapper.cpp:227-228): restrict the regular-site statistics to a BED file
+int fqb_stats_set_target_region(fqb_handle *h, const char *bed_path) {
+    if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    if (h->stats_open) { set_error("fqb_stats_set_target_region: call it before fqb_stats_open"); return FQB_ERR_STATE; }
+    h->target_bed = bed_path ? bed_path : "";
+    return FQB_OK;
+}
+
 // RestoreVcfSites + SetGenomeSize (src/BwtMapper.cpp:225-226): side tables and accumulators
 int fqb_stats_open(fqb_handle *h, const char *index_prefix) {
     if (!h || !index_prefix) { set_error("null argument"); return FQB_ERR_ARG; }
     CU_CHECK(cudaSetDevice(h->device));
     std::string err;
-    if (!build_stats_tables(h->hidx, index_prefix, h->gopt, h->stabs, err)) { set_error(err); return FQB_ERR_IO; }
+    if (!build_stats_tables(h->hidx, index_prefix, h->gopt, h->target_bed, h->stabs, err)) { set_error(err); return FQB_ERR_IO; }
     const StatsTables &T = h->stabs;
     const size_t nc = T.contigs.size(), ns = T.n_sites ? T.n_sites : 1;
     CU_CHECK(cudaMalloc(&h->d_ctg, nc * sizeof(ContigDev)));

@@ -67,6 +67,54 @@ struct Regions {
         }
         r = t;
     }
+    uint64_t size() const {                 // RegionList::Size(): set by Collapse
+        uint64_t len = 0;
+        for (auto &kv : r) for (auto &iv : kv.second) len += (uint64_t)(iv.second - iv.first) + 1;
+        return len;
+    }
+    // RegionList::ReadRegionList(path, autoCollapse = true) (src/RegionList.cpp:15-45)
+    bool read_bed(const std::string &path) {
+        std::ifstream fin(path);
+        if (!fin.is_open()) return false;
+        std::string line;
+        while (std::getline(fin, line)) {
+            std::string chr;
+            int start = 0, end = 0;
+            std::stringstream ss(line);
+            ss >> chr >> start >> end;
+            chr = norm_chrom(chr);
+            auto &m = r[chr];
+            auto it = m.find(start);
+            if (it != m.end()) { if (it->second < end) it->second = end; } else m[start] = end;
+        }
+        collapse();
+        return true;
+    }
+    // RegionList::Join(b, isUnion = false) (src/RegionList.cpp:120-173)
+    void inner_join(const Regions &b) {
+        collapse();
+        Regions t;
+        for (auto &kv : b.r) {
+            auto mine = r.find(kv.first);
+            if (mine == r.end()) continue;
+            auto a = mine->second.begin();
+            auto it = kv.second.begin();
+            while (a != mine->second.end() && it != kv.second.end()) {
+                const int b1 = a->first, e1 = a->second, b2 = it->first, e2 = it->second;
+                if (b1 <= b2) {
+                    if (e1 > e2) { t.r[kv.first][b2] = e2; ++it; }
+                    else if (e1 > b2) { t.r[kv.first][b2] = e1; ++a; }
+                    else ++a;
+                } else {
+                    if (e1 <= e2) { t.r[kv.first][b1] = e1; ++a; }
+                    else if (e1 > b2 && b1 < e2) { t.r[kv.first][b1] = e2; ++it; }
+                    else ++it;
+                }
+            }
+        }
+        r = t.r;
+        collapse();
+    }
     bool has(const std::string &chr, int pos) const {
         auto c = r.find(chr);
         if (c == r.end()) return false;
@@ -77,7 +125,8 @@ struct Regions {
     }
 };
 
-bool build_stats_tables(const HostIndex &idx, const std::string &prefix, const fqb_gap_opt_t &g, StatsTables &T, std::string &err) {
+bool build_stats_tables(const HostIndex &idx, const std::string &prefix, const fqb_gap_opt_t &g, const std::string &target_bed, StatsTables &T,
+                        std::string &err) {
     T = StatsTables();
     if (!read_vcf(prefix + ".SelectedSite.vcf", T.markers, err)) return false;
     std::ifstream fgc(prefix + ".gc", std::ios::binary);
@@ -102,6 +151,12 @@ bool build_stats_tables(const HostIndex &idx, const std::string &prefix, const f
         flank.add(m.chrom, m.pos - fl + T.chopped_read_len, m.pos + fl - T.chopped_read_len);
     }
     flank.collapse();
+    if (!target_bed.empty()) {              // StatCollector::SetTargetRegion (src/StatCollector.cpp:2284-2288)
+        Regions target;
+        if (!target.read_bed(target_bed)) { err = "Region list bed file:" + target_bed + " open failed!"; return false; }
+        flank.inner_join(target);
+        T.has_target = true; T.flank_region_size = flank.size(); T.target_region_size = target.size();
+    }
     {
         std::vector<MarkerRec> db;
         if (!read_vcf(prefix + ".dbSNP.subset.vcf", db, err)) return false;
@@ -283,7 +338,8 @@ bool write_summary_files(const StatsTables &T, StatsTotals &S, const fqb_gap_opt
         if (i >= 10) Cov10 += DepthDist[i];
     }
     const int ch = T.chopped_read_len;
-    const uint64_t total_region_size = (uint64_t)(((g.flank_len - ch) * 2 + 1)) * T.n_short + (uint64_t)(((g.flank_long_len - ch) * 2 + 1)) * T.n_long +
+    const uint64_t total_region_size = T.has_target ? T.flank_region_size :
+                                       (uint64_t)(((g.flank_len - ch) * 2 + 1)) * T.n_short + (uint64_t)(((g.flank_long_len - ch) * 2 + 1)) * T.n_long +
                                        (uint64_t)(((g.flank_len - ch) * 2 + 1)) * T.n_xy;
     {
         std::ofstream f(prefix + ".DepthDist");
@@ -380,7 +436,7 @@ bool write_summary_files(const StatsTables &T, StatsTotals &S, const fqb_gap_opt
         fc.close();
         std::ofstream f(prefix + ".Summary");
         f << "Statistics : " << "Value\n";
-        auto report_genome_size = (T.ref_genome_size - T.ref_N_size);
+        auto report_genome_size = T.has_target ? T.target_region_size : (T.ref_genome_size - T.ref_N_size);
         double estimated_total_mapped_reads = (double)NumBaseMapped / avgReadLen * report_genome_size / total_region_size;
         f << "Estimated Read Mapping Rate : " << estimated_total_mapped_reads / total_reads << "\n";
         f << "Estimated Read PCR Duplication Rate : " << S.num_pcr_dup / ((double)S.num_pair_reads) << "[" << (uint64_t)S.num_pcr_dup << "/" << (double)S.num_pair_reads << "]\n";

@@ -33,10 +33,13 @@ struct StatsTables {
     uint64_t n_short = 0, n_long = 0, n_xy = 0;
     int chopped_read_len = 0;
     uint64_t ref_genome_size = 0, ref_N_size = 0;   // BwtIndexer::LoadContigSize (src/BwtIndexer.cpp:764-802)
+    bool has_target = false; uint64_t flank_region_size = 0, target_region_size = 0;   // flankRegion.Size() after InnerJoin, targetRegion.Size()
     std::vector<std::pair<std::string, int>> genome_contigs;   // BwtIndexer::contigSize: the lines of <reference>.fai (BAM header @SQ)
 };
 
-bool build_stats_tables(const HostIndex &idx, const std::string &index_prefix, const fqb_gap_opt_t &g, StatsTables &out, std::string &err);
+// target_bed: --targetRegion (StatCollector::SetTargetRegion), or empty
+bool build_stats_tables(const HostIndex &idx, const std::string &index_prefix, const fqb_gap_opt_t &g, const std::string &target_bed, StatsTables &out,
+                        std::string &err);
 
 // FileStatCollector (src/StatCollector.h:46-62)
 struct FileCounters {

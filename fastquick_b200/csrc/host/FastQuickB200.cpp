@@ -87,7 +87,7 @@ struct FastqReader {
 BwtMapper::BwtMapper(BwtIndexer &BwtIndex, const std::string &FQList, const std::string &Fastq_1, const std::string &Fastq_2,
                      const std::string &Prefix, const std::string &RefPath, const pe_opt_t *popt, gap_opt_t *opt,
                      const std::string &targetRegionPath, int device) : prefix_(Prefix) {
-    if (targetRegionPath != "Empty") error("--targetRegion is not supported by the GPU stage yet");
+
     fqb_gap_opt_t g; fqb_gap_opt_default(&g);
     g.s_mm = opt->s_mm; g.s_gapo = opt->s_gapo; g.s_gape = opt->s_gape; g.mode = opt->mode;
     g.indel_end_skip = opt->indel_end_skip; g.max_del_occ = opt->max_del_occ; g.max_entries = opt->max_entries;
@@ -100,6 +100,7 @@ BwtMapper::BwtMapper(BwtIndexer &BwtIndex, const std::string &FQList, const std:
     p.N_multi = popt->N_multi; p.type = popt->type; p.is_sw = popt->is_sw; p.ap_prior = popt->ap_prior;
     if (fqb_create(RefPath.c_str(), &g, &p, device, &h_) != FQB_OK) error("%s", fqb_last_error());
     collector.Attach(h_);
+    if (targetRegionPath != "Empty" && fqb_stats_set_target_region(h_, targetRegionPath.c_str()) != FQB_OK) error("%s", fqb_last_error());
     double t_tmp = realtime();
     collector.RestoreVcfSites(RefPath, opt);
     notice("Restore Variant Site Info...%f sec", realtime() - t_tmp);
@@ -262,13 +263,14 @@ int runAlign(int argc, char **argv) {
     if (il13) opt.mode |= 0x200;
     if (loggap) opt.mode |= 0x04;
     BwtIndexer Indexer(kmer_thresh);
-    std::string NewRef = IndexPrefix + ".FASTQuick.fa";
+    std::string NewRef = IndexPrefix + ".FASTQuick.fa", TargetRegionPath("Empty");
     {   // <index>.FASTQuick.fa.param (src/FASTQuick.cpp:365-467)
         std::ifstream par(NewRef + ".param");
         if (!par) error("Open %s failed!", (NewRef + ".param").c_str());
         std::string k, v;
         while (par >> k >> v) {
-            if (k == "NUM_VAR_LONG") opt.num_variant_long = (unsigned)atoi(v.c_str());
+            if (k == "TARGET_REGION_PATH") TargetRegionPath = v;          // set at index time by --regionList
+            else if (k == "NUM_VAR_LONG") opt.num_variant_long = (unsigned)atoi(v.c_str());
             else if (k == "NUM_VAR_SHORT") opt.num_variant_short = (unsigned)atoi(v.c_str());
             else if (k == "SHORT_FLANK_LENGTH") opt.flank_len = atoi(v.c_str());
             else if (k == "LONG_FLANK_LENGTH") opt.flank_long_len = atoi(v.c_str());
@@ -278,7 +280,8 @@ int runAlign(int argc, char **argv) {
     Indexer.LoadIndex(NewRef);
     notice("Load Index... %f sec", realtime() - t_tmp);
     t_tmp = realtime();
-    BwtMapper Mapper(Indexer, FaList, Fastq_1, Fastq_2, Prefix, NewRef, &popt, &opt, "Empty", device);
+    if (TargetRegionPath != "Empty") notice("Read in target region from %s", TargetRegionPath.c_str());
+    BwtMapper Mapper(Indexer, FaList, Fastq_1, Fastq_2, Prefix, NewRef, &popt, &opt, TargetRegionPath, device);
     notice("Mapping... %f sec", realtime() - t_tmp);
     notice("Real time: %.3f sec", realtime() - t_real);
     return 0;

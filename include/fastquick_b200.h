@@ -159,6 +159,8 @@ int fqb_stage_sw_refine(fqb_handle *h);
  * fqb_stats_emit      = the InsertSizeTable lines of the batch (text; host)
  * fqb_stats_finish    = StatCollector::ProcessCore (2012-2028): writes <out_prefix>.{DepthDist,GCDist,EmpRepDist,EmpCycleDist,
  *                       AdjustedInsertSizeDist,RawInsertSizeDist,SexChromInfo,Pileup,FASTQ.csv,Sequence.csv,Summary,vcf} */
+/* --targetRegion: StatCollector::SetTargetRegion (src/StatCollector.cpp:2284-2288); call before fqb_stats_open */
+int fqb_stats_set_target_region(fqb_handle *h, const char *bed_path);
 int fqb_stats_open(fqb_handle *h, const char *index_prefix);
 int fqb_stats_begin_file(fqb_handle *h, const char *out_prefix, const char *fastq1, const char *fastq2);
 int fqb_stage_stats(fqb_handle *h);

@@ -97,6 +97,11 @@ int orc_refine_gapped(int64_t l_pac, const uint8_t *pac, int len, const uint8_t 
 int orc_cal_nm(int n_cigar, const uint16_t *cigar, int has_cigar, int len, uint32_t pos, const uint8_t *seq, int64_t l_pac, const uint8_t *pac);
 void orc_paired_sw(int64_t l_pac, const uint8_t *pac, int n_pairs, orc_row_t *rows, const uint8_t *codes, int stride,
                    const orc_pe_opt_t *popt, const orc_isize_t *ii);
+/* RegionList of the reference for one chromosome (src/RegionList.cpp): arrays of (start, end) pairs sorted by start */
+int orc_regions_add(int *r, int n, int start, int end);
+int orc_regions_collapse(int *r, int n, long long *len);
+int orc_regions_join(int *a, int na, const int *b, int nb, long long *len);
+int orc_regions_overlapped(const int *r, int n, int pos);
 /* MD tag (bwa_cal_md1, libbwa/bwase.c:234-296) and StatCollector::RecoverRefseqByMDandCigar (src/StatCollector.cpp:101-172) */
 int orc_cal_md(int n_cigar, const uint16_t *cigar, int has_cigar, int len, uint32_t pos, const uint8_t *seq, int64_t l_pac,
                const uint8_t *pac, char *out, int cap);

@@ -32,7 +32,7 @@ def have_ref():
 
 
 def build_oracle():
-    srcs = [os.path.join(REPO, "oracle", f) for f in ("fq_oracle.c", "fq_oracle_pe.c", "fq_oracle_dp.c")]
+    srcs = [os.path.join(REPO, "oracle", f) for f in ("fq_oracle.c", "fq_oracle_pe.c", "fq_oracle_dp.c", "fq_oracle_regions.c")]
     deps = srcs + [os.path.join(REPO, "oracle", "fq_oracle.h"), os.path.join(REPO, "include", "fastquick_b200.h")]
     if not os.path.exists(ORC_LIB) or os.path.getmtime(ORC_LIB) < max(os.path.getmtime(s) for s in deps):
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared"] + srcs + ["-o", ORC_LIB, "-lm"])

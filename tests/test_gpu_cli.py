@@ -130,3 +130,49 @@ def test_cli_frac_samp_matches_reference(small_index, ref_required):
         _compare_files(outs["ref"] + "." + ext, outs["b200"] + "." + ext)
     recs = _compare_bams(outs["ref"] + ".bam", outs["b200"] + ".bam")
     assert 3500 < len(recs) < 6000          # about 40 % of 6000 pairs, two records each
+
+
+def test_cli_target_region_matches_reference(small_index, ref_required, tmp_path):
+    """TARGET_REGION_PATH of the index's .param (set by `index --regionList`): StatCollector::SetTargetRegion restricts the
+    regular-site statistics to flankRegion (inner join) targetRegion and changes the size terms of DepthDist / Summary."""
+    if not os.path.exists(fx.REF_BIN):
+        pytest.skip("FASTQuick_ref not built")
+    # a copy of the index whose .param names a BED file: windows around every third marker, some overlapping, some off-flank
+    d = str(tmp_path)
+    base = os.path.basename(small_index.prefix)
+    for f in os.listdir(small_index.dir):
+        if f.startswith(base) and not f.endswith(".param"):
+            os.symlink(os.path.join(small_index.dir, f), os.path.join(d, f))
+    bed = os.path.join(d, "target.bed")
+    with open(bed, "w") as fo:
+        for i, line in enumerate(l for l in open(small_index.prefix + ".SelectedSite.vcf") if not l.startswith("#")):
+            chrom, pos = line.split("\t")[:2]
+            pos = int(pos)
+            if i % 3 == 0:
+                fo.write("%s\t%d\t%d\n" % (chrom, pos - 180, pos + 60))
+                fo.write("chr%s\t%d\t%d\n" % (chrom, pos + 40, pos + 120))
+            elif i % 3 == 1:
+                fo.write("%s\t%d\t%d\n" % (chrom, pos + 5000, pos + 5200))
+    with open(os.path.join(d, base + ".param"), "w") as fo:
+        for l in open(small_index.prefix + ".param"):
+            fo.write("TARGET_REGION_PATH\t%s\n" % bed if l.startswith("TARGET_REGION_PATH") else l)
+    arrs = small_index.reads(5000, read_len=100, seed=90)
+    fq = small_index.write_fastq("clitr", arrs)
+    idx_prefix = os.path.join(d, base)[: -len(".FASTQuick.fa")]
+    outs = {}
+    for tag, exe in (("ref", fx.REF_BIN), ("b200", CLI)):
+        out = os.path.join(d, "clitr_" + tag)
+        cmd = [exe, "align", "--fastq_1", fq[0], "--fastq_2", fq[1], "--index_prefix", idx_prefix, "--out_prefix", out, "--t", "4", "--q", "15"]
+        r = subprocess.run(cmd, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-3000:]
+        assert "Read in target region from" in r.stdout
+        outs[tag] = out
+    for ext in TEXT_FILES + ["FASTQ.csv"]:
+        _compare_files(outs["ref"] + "." + ext, outs["b200"] + "." + ext)
+    va = [l for l in open(outs["ref"] + ".vcf") if not l.startswith("##fileDate")]
+    vb = [l for l in open(outs["b200"] + ".vcf") if not l.startswith("##fileDate")]
+    assert va == vb
+    # and the restriction really changed something
+    full = os.path.join(small_index.dir, "cli_ref.DepthDist")
+    if os.path.exists(full):
+        assert open(full).read() != open(outs["ref"] + ".DepthDist").read()
