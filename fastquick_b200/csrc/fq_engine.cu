@@ -115,6 +115,7 @@ struct fqb_handle {
     // statistics rows (a12-a14)
     bool stats_open = false, stats_done = false;
     std::string target_bed;                      // --targetRegion, set before fqb_stats_open
+    long long files_closed[6] = {0, 0, 0, 0, 0, 0}; // device totals already attributed to finished files
     StatsTables stabs;
     ContigDev *d_ctg = nullptr;
     uint32_t *d_site = nullptr; int32_t *d_marker = nullptr;
@@ -668,14 +669,29 @@ int fqb_stats_open(fqb_handle *h, const char *index_prefix) {
     CU_CHECK(cudaMemset(h->d_ntuples, 0, 4));
     h->pileup.assign(T.markers.size(), PileupColumn());
     h->files.clear();
+    for (auto &x : h->files_closed) x = 0;
     h->pairs_seen = 0;
     h->stats_open = true;
+    return FQB_OK;
+}
+
+// The FileStatCollector counters live on the device as running totals; a file's own counters are the totals at its
+// end minus the totals when it began (collector.AddFSC(FSC), src/BwtMapper.cpp:254).
+static int close_current_file(fqb_handle *h) {
+    if (h->files.empty()) return FQB_OK;
+    CU_CHECK(cudaStreamSynchronize(h->stream));
+    unsigned long long sc[kEmpScalars];
+    CU_CHECK(cudaMemcpy(sc, h->d_emp + 4 * 256 + 4096, sizeof sc, cudaMemcpyDeviceToHost));
+    FileCounters &F = h->files.back();
+    long long *dst[6] = {&F.TotalFiltered, &F.BwaUnmapped, &F.TotalMAPQ, &F.TotalRetained, &F.NumBase, &F.NumRead};
+    for (int k = 0; k < 6; ++k) { *dst[k] = (long long)sc[3 + k] - h->files_closed[k]; h->files_closed[k] = (long long)sc[3 + k]; }
     return FQB_OK;
 }
 
 // a new FASTQ pair: FileStatCollector FSC(fq1, fq2) (src/BwtMapper.cpp:249-254); the first call (re)creates <out_prefix>.InsertSizeTable
 int fqb_stats_begin_file(fqb_handle *h, const char *out_prefix, const char *fq1, const char *fq2) {
     if (!h || !h->stats_open) { set_error("fqb_stats_begin_file: call fqb_stats_open first"); return FQB_ERR_STATE; }
+    { int rc = close_current_file(h); if (rc) return rc; }
     if (out_prefix && !h->isize_table.is_open()) {
         h->isize_table_path = std::string(out_prefix) + ".InsertSizeTable";
         h->isize_table.open(h->isize_table_path);
@@ -841,13 +857,9 @@ int fqb_stats_finish(fqb_handle *h, const char *out_prefix) {
     S.contig_ctr.assign(cc.begin(), cc.begin() + nc * 4); S.contig_first.assign(cc.begin() + nc * 4, cc.end());
     build_pileup(h);
     S.pileup = h->pileup;
+    rc = close_current_file(h);           // the last file's counters (in a sharded run: after the totals were imported)
+    if (rc) return rc;
     S.files = h->files;
-    // per-file counters: with one FASTQ pair per run the device totals are that file's counters
-    if (S.files.size() == 1) {
-        FileCounters &F = S.files[0];
-        F.TotalFiltered = (long long)sc[3]; F.BwaUnmapped = (long long)sc[4]; F.TotalMAPQ = (long long)sc[5]; F.TotalRetained = (long long)sc[6]; F.NumBase = (long long)sc[7];
-        F.NumRead = (long long)sc[8];
-    }
     std::string err;
     if (!write_summary_files(T, S, h->gopt, out_prefix, err)) { set_error(err); return FQB_ERR_IO; }
     return FQB_OK;

@@ -194,7 +194,7 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
 bool BwtMapper::SingleEndMapper(const std::string &fq1, const gap_opt_t *opt, FileStatCollector &FSC) {
     FastqReader r;
     if (!r.open(fq1)) error("Open fastq failed: %s", fq1.c_str());
-    if (fqb_stats_begin_file(h_, prefix_.c_str(), fq1.c_str(), "") != FQB_OK) error("%s", fqb_last_error());
+    if (fqb_stats_begin_file(h_, prefix_.c_str(), fq1.c_str(), fq1.c_str()) != FQB_OK) error("%s", fqb_last_error());
     const int stride = opt->read_len < FQB_MAX_READ_LEN ? opt->read_len : FQB_MAX_READ_LEN, cap = FQB_BATCH_PAIRS, name_stride = 64;
     struct Buf { uint8_t *b, *q; int32_t *l; char *nm; int n; } bufs[3];
     for (auto &B : bufs) {

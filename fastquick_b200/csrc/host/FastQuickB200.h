@@ -51,7 +51,7 @@ public:
     std::string FileName1, FileName2;
     FileStatCollector() = default;
     FileStatCollector(const char *f1, const char *f2) : FileName1(f1), FileName2(f2) {}
-    explicit FileStatCollector(const char *f1) : FileName1(f1), FileName2("") {}      // src/StatCollector.h:58
+    explicit FileStatCollector(const char *f1) : FileName1(f1), FileName2(f1) {}      // src/StatCollector.h:58
 };
 
 // StatCollector: accumulation lives on the GPU inside the engine; this object is the handle-side view

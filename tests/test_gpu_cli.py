@@ -176,3 +176,28 @@ def test_cli_target_region_matches_reference(small_index, ref_required, tmp_path
     full = os.path.join(small_index.dir, "cli_ref.DepthDist")
     if os.path.exists(full):
         assert open(full).read() != open(outs["ref"] + ".DepthDist").read()
+
+
+def test_cli_fastq_list_matches_reference(small_index, ref_required):
+    """--fq_list with two paired files and one single-end file: per-file counters (FASTQ.csv), the RNG restart per file,
+    and pile-up / InsertSizeTable order across files."""
+    if not os.path.exists(fx.REF_BIN):
+        pytest.skip("FASTQuick_ref not built")
+    fqa = small_index.write_fastq("clila", small_index.reads(2500, read_len=100, seed=92))
+    fqb = small_index.write_fastq("clilb", small_index.reads(1800, read_len=100, seed=93, f_on=0.8, sub_rate=0.02))
+    fqc = small_index.write_fastq("clilc", small_index.reads(1200, read_len=100, seed=94))
+    lst = os.path.join(small_index.dir, "clil.list")
+    with open(lst, "w") as fo:
+        fo.write("# list of FASTQ files\n%s\t%s\n%s\n%s\t%s\n" % (fqa[0], fqa[1], fqc[0], fqb[0], fqb[1]))
+    idx_prefix = small_index.prefix[: -len(".FASTQuick.fa")]
+    outs = {}
+    for tag, exe in (("ref", fx.REF_BIN), ("b200", CLI)):
+        out = os.path.join(small_index.dir, "clil_" + tag)
+        cmd = [exe, "align", "--fq_list", lst, "--index_prefix", idx_prefix, "--out_prefix", out, "--t", "4", "--q", "15"]
+        r = subprocess.run(cmd, cwd=small_index.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-3000:]
+        outs[tag] = out
+    for ext in TEXT_FILES + ["FASTQ.csv"]:
+        _compare_files(outs["ref"] + "." + ext, outs["b200"] + "." + ext)
+    assert sum(1 for _ in open(outs["ref"] + ".FASTQ.csv")) == 4          # header + three files
+    _compare_bams(outs["ref"] + ".bam", outs["b200"] + ".bam")
