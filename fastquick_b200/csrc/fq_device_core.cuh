@@ -67,6 +67,27 @@ FQB_HD void occ4_block(const uint4 cnt, const uint4 bases, uint32_t n /*1..64 sy
     out[0] = cnt.x + n - H - L + T;
 }
 
+// count of ONE symbol c among the first n symbols of a block (bwt_occ): a single masked popc
+FQB_HD uint32_t occ1_block(const uint4 cnt, const uint4 bases, uint32_t n, uint32_t c) {
+    const uint64_t hi = ((uint64_t)bases.x << 32) | bases.y, lo = ((uint64_t)bases.z << 32) | bases.w;
+    const uint64_t m = ~0ull << (64u - n);
+    const uint64_t xh = (c & 2) ? hi : ~hi, xl = (c & 1) ? lo : ~lo;
+    const uint32_t base = (c & 2) ? ((c & 1) ? cnt.w : cnt.z) : ((c & 1) ? cnt.y : cnt.x);
+    return base + (uint32_t)FQB_POPCLL(xh & xl & m);
+}
+// bwt_2occ(bwt, k, l, c): both ranks of one symbol, one block fetch when k and l share a block
+FQB_HD void occ1_pair(const DevBwt &b, uint32_t k, uint32_t l, uint32_t c, uint32_t &ok, uint32_t &ol) {
+    uint32_t ll = l - (l >= b.primary);
+    const uint4 *pl = b.blocks + 2 * (size_t)(ll >> 6);
+    if (k == kNoRow) { ok = 0; ol = occ1_block(FQB_LDG4(pl), FQB_LDG4(pl + 1), (ll & 63) + 1, c); return; }
+    uint32_t kk = k - (k >= b.primary);
+    const uint4 *pk = b.blocks + 2 * (size_t)(kk >> 6);
+    uint4 cc = FQB_LDG4(pk), w = FQB_LDG4(pk + 1);
+    ok = occ1_block(cc, w, (kk & 63) + 1, c);
+    if ((ll >> 6) != (kk >> 6)) { cc = FQB_LDG4(pl); w = FQB_LDG4(pl + 1); }
+    ol = occ1_block(cc, w, (ll & 63) + 1, c);
+}
+
 FQB_HD void occ4(const DevBwt &b, uint32_t k, uint32_t out[4]) {
     if (k == kNoRow) { out[0] = out[1] = out[2] = out[3] = 0; return; }
     k -= (k >= b.primary);
@@ -140,11 +161,11 @@ FQB_HD uint32_t cal_width(const DevBwt &b, const uint8_t *fwd, int len, int a, i
     for (int i = 0; i < n; ++i) {
         uint32_t c = read_sym(fwd, len, a, first + i);
         if (c < 4) {
-            uint32_t ck[4], cl[4];
-            occ4_pair(b, k - 1, l, ck, cl);
+            uint32_t ok, ol;
+            occ1_pair(b, k - 1, l, c, ok, ol);
             touches += ref_block_touches(b, k - 1, l);
-            k = pick4(b.L2, c) + pick4(ck, c) + 1;
-            l = pick4(b.L2, c) + pick4(cl, c);
+            k = pick4(b.L2, c) + ok + 1;
+            l = pick4(b.L2, c) + ol;
         }
         if (k > l || c > 3) { k = 0; l = b.seq_len; ++bid; }
         out[i] = pack_width(l - k + 1, bid);

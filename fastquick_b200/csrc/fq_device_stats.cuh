@@ -73,9 +73,13 @@ FQB_HD void touch_contig(const StatAccum &A, int seqid, uint32_t pair, int which
     if (pair < A.contig_first[seqid]) A.contig_first[seqid] = pair;
 #endif
 }
+// counter += v.  On the device the lanes of a warp that hit the same counter with the same increment elect one leader
+// (most pairs bump the same few scalars and insert-size bins, so this removes almost all same-address atomics).
 FQB_HD void bump64(unsigned long long *p, unsigned long long v) {
 #if defined(__CUDA_ARCH__)
-    atomicAdd(p, v);
+    const unsigned act = __activemask();
+    const unsigned peers = __match_any_sync(act, (unsigned long long)(uintptr_t)p) & __match_any_sync(act, v);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(p, v * (unsigned long long)__popc(peers));
 #else
     *p += v;
 #endif

@@ -11,20 +11,31 @@ namespace fqb {
 #define FULL_MASK 0xffffffffu
 
 __global__ void __launch_bounds__(128) classify_kernel(StatsView v, StatAccum A) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= (uint32_t)v.n_reads / 2) return;
-    fqb_read_t r0 = v.rows[2 * p], r1 = v.rows[2 * p + 1];
-    PairStat o;
-    classify_pair(v.ctg, v.n_ctg, r0, r1, v.pair_base + p, v.cal_dup, A, o);
-    if (o.demoted[0]) v.rows[2 * p].type = kTypeNoMatch;        // AddAlignment mutates p/q before SetSamRecord sees them
-    if (o.demoted[1]) v.rows[2 * p + 1].type = kTypeNoMatch;
-    v.pstat[p] = o;
-    // FileStatCollector counters of the main-thread loop (src/BwtMapper.cpp:2059-2076)
-    bump64(A.scalars + 3, o.both_filtered);
-    bump64(A.scalars + 4, o.both_unmapped);
-    bump64(A.scalars + 5, o.low_mapq);
-    bump64(A.scalars + 6, o.retained);
-    bump64(A.scalars + 7, (unsigned long long)(r0.full_len + r1.full_len));
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p < (uint32_t)v.n_reads / 2;
+    unsigned long long c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
+    if (valid) {
+        fqb_read_t r0 = v.rows[2 * p], r1 = v.rows[2 * p + 1];
+        PairStat o;
+        classify_pair(v.ctg, v.n_ctg, r0, r1, v.pair_base + p, v.cal_dup, A, o);
+        if (o.demoted[0]) v.rows[2 * p].type = kTypeNoMatch;        // AddAlignment mutates p/q before SetSamRecord sees them
+        if (o.demoted[1]) v.rows[2 * p + 1].type = kTypeNoMatch;
+        v.pstat[p] = o;
+        c3 = o.both_filtered; c4 = o.both_unmapped; c5 = o.low_mapq; c6 = o.retained; c7 = (unsigned long long)(r0.full_len + r1.full_len);
+    }
+    // FileStatCollector counters of the main-thread loop (src/BwtMapper.cpp:2059-2076): one atomic per warp and counter
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        c3 += __shfl_xor_sync(FULL_MASK, c3, d); c4 += __shfl_xor_sync(FULL_MASK, c4, d); c5 += __shfl_xor_sync(FULL_MASK, c5, d);
+        c6 += __shfl_xor_sync(FULL_MASK, c6, d); c7 += __shfl_xor_sync(FULL_MASK, c7, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (c3) atomicAdd(A.scalars + 3, c3);
+        if (c4) atomicAdd(A.scalars + 4, c4);
+        if (c5) atomicAdd(A.scalars + 5, c5);
+        if (c6) atomicAdd(A.scalars + 6, c6);
+        if (c7) atomicAdd(A.scalars + 7, c7);
+    }
 }
 
 // smem histogram bump with warp aggregation: lanes that share a bin elect one leader
