@@ -88,7 +88,7 @@ FQB_HD void bump64(unsigned long long *p, unsigned long long v) {
 FQB_HD bool dup_insert(const StatAccum &A, uint32_t start, uint32_t end) {
     const unsigned long long key = ((unsigned long long)start << 32 | end) + 1;      // 0 = empty slot
     uint32_t h = (uint32_t)(hash64(key) % A.dup_cap);
-    for (;;) {
+    for (uint32_t probes = 0; probes < A.dup_cap; ++probes) {
 #if defined(__CUDA_ARCH__)
         unsigned long long old = atomicCAS(A.dup_keys + h, 0ull, key);
 #else
@@ -99,6 +99,8 @@ FQB_HD bool dup_insert(const StatAccum &A, uint32_t start, uint32_t end) {
         if (old == key) return true;
         h = h + 1 == A.dup_cap ? 0 : h + 1;
     }
+    bump64(A.scalars + 2, 1);          // table full: reported by fqb_stats_finish as a limit error, never silently dropped
+    return false;
 }
 
 struct ClipInfo { int cl_left, cl_right; };

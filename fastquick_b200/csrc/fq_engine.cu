@@ -20,6 +20,7 @@
 #include "fq_stats_host.h"
 #include "fq_bam.h"
 #include <algorithm>
+#include <chrono>
 #include <fstream>
 #include <thread>
 #include <cmath>
@@ -660,7 +661,7 @@ int fqb_stats_open(fqb_handle *h, const char *index_prefix) {
     CU_CHECK(cudaMalloc(&h->d_contig_ctr, nc * 5 * 4));
     CU_CHECK(cudaMemset(h->d_contig_ctr, 0, nc * 4 * 4));
     CU_CHECK(cudaMemset(h->d_contig_ctr + nc * 4, 0xff, nc * 4));
-    h->dup_cap = 1u << 26;                       // 64M-slot open-addressing set of (start, end) keys (512 MB)
+    h->dup_cap = 1u << 28;                       // 268M-slot open-addressing set of (start, end) keys (2 GiB): room for the 200M-pair configuration
     CU_CHECK(cudaMalloc(&h->d_dup_keys, (size_t)h->dup_cap * 8));
     CU_CHECK(cudaMemset(h->d_dup_keys, 0, (size_t)h->dup_cap * 8));
     h->tuple_cap = 1u << 25;
@@ -850,7 +851,7 @@ int fqb_stats_finish(fqb_handle *h, const char *out_prefix) {
     S.emp.assign(e.begin(), e.begin() + 1024);
     S.isize_dist.assign(e.begin() + 1024, e.begin() + 1024 + 4096);
     const unsigned long long *sc = e.data() + 1024 + 4096;
-    if (sc[2]) { set_error("an insert size fell outside InsertSizeDist[4096] (the reference would write out of bounds)"); return FQB_ERR_LIMIT; }
+    if (sc[2]) { set_error("an insert size fell outside InsertSizeDist[4096] (the reference would write out of bounds), or the duplicate-key table is full"); return FQB_ERR_LIMIT; }
     S.num_pcr_dup = sc[0]; S.num_pair_reads = sc[1];
     std::vector<uint32_t> cc(nc * 5);
     CU_CHECK(cudaMemcpy(cc.data(), h->d_contig_ctr, nc * 5 * 4, cudaMemcpyDeviceToHost));
@@ -938,12 +939,13 @@ static __global__ void dup_merge_kernel(unsigned long long *keys, uint32_t cap, 
     if (i >= n) return;
     const unsigned long long key = in[i];
     uint32_t hh = (uint32_t)(hash64(key) % cap);
-    for (;;) {
+    for (uint32_t probes = 0; probes < cap; ++probes) {
         const unsigned long long old = atomicCAS(keys + hh, 0ull, key);
         if (old == 0) { atomicAdd(n_distinct, 1ull); return; }
         if (old == key) { atomicAdd(num_pcr_dup, 2ull); return; }
         hh = hh + 1 == cap ? 0 : hh + 1;
     }
+    atomicAdd(num_pcr_dup + 2, 1ull);      // scalars[2]: table full, reported as a limit error by fqb_stats_finish
 }
 extern "C" {
 // Variable-size statistics state of a sharded run: which = 0 pile-up entries (sizeof(PileupTuple) = 20 bytes each),
@@ -1143,6 +1145,7 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
     CU_CHECK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const size_t np = (size_t)h->n_reads / 2;
+    const auto t_begin = std::chrono::steady_clock::now();
     // the other hits of reads that keep a multi list (XA): positions and CIGARs come from the device
     if (h->multi_cap < (uint32_t)h->cap_reads) {
         cudaFree(h->d_multi_out); cudaFree(h->d_multi_list); cudaFree(h->d_multi_ctr);
@@ -1198,6 +1201,7 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
         return n ? &xa[(size_t)(lo - mo.begin())] : nullptr;
     };
     // records are formatted by several host threads over contiguous slices of the batch and written in order
+    const auto t_dev = std::chrono::steady_clock::now();
     const uint64_t first = h->pairs_seen - (h->stats_done ? np : 0);
     unsigned nthr = std::thread::hardware_concurrency();
     if (nthr < 1) nthr = 1;
@@ -1231,9 +1235,15 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
         for (unsigned t = 0; t < nthr; ++t) th.emplace_back(work, t);
         for (auto &x : th) x.join();
     }
+    const auto t_fmt = std::chrono::steady_clock::now();
     size_t total = 0;
     for (auto &o : parts) { h->bam.write(o.data(), o.size()); total += o.size(); }
-    if (getenv("FQB_BAM_DEBUG")) fprintf(stderr, "bam_emit: %zu pairs, %u multi hits, %zu bytes, have_ps %d, threads %u\n", np, ctr[1], total, (int)have_ps, nthr);
+    if (getenv("FQB_BAM_DEBUG")) {
+        const auto t_end = std::chrono::steady_clock::now();
+        fprintf(stderr, "bam_emit: %zu pairs, %u multi hits, %zu bytes, threads %u; device+copies %.1f ms, format %.1f ms, bgzf %.1f ms\n", np, ctr[1], total, nthr,
+                std::chrono::duration<double, std::milli>(t_dev - t_begin).count(), std::chrono::duration<double, std::milli>(t_fmt - t_dev).count(),
+                std::chrono::duration<double, std::milli>(t_end - t_fmt).count());
+    }
     return FQB_OK;
 }
 

@@ -38,46 +38,71 @@ int StatCollector::ProcessCore(const std::string &statPrefix, const gap_opt_t *)
     return 0;
 }
 
-// ---- FASTQ feeder: 4-line records from gz, into fixed-stride pinned batches (kseq_read3_fpc's contract, libbwa/kseq.h:327-370)
+// ---- FASTQ feeder: 4-line records from gz, into fixed-stride pinned batches (kseq_read3_fpc's contract, libbwa/kseq.h:327-370).
+// Lines are located in place in the inflate buffer (memchr); only a line cut by the end of the buffer is moved.
 struct FastqReader {
     gzFile fp = nullptr;
     std::vector<char> buf; size_t pos = 0, end = 0;
-    bool open(const std::string &p) { fp = gzopen(p.c_str(), "rb"); if (fp) { gzbuffer(fp, 1 << 20); buf.resize(1 << 22); } return fp != nullptr; }
+    bool eof = false;
+    bool open(const std::string &p) {
+        fp = gzopen(p.c_str(), "rb");
+        if (fp) { gzbuffer(fp, 1 << 20); buf.resize((size_t)8 << 20); pos = end = 0; eof = false; }
+        return fp != nullptr;
+    }
     void close() { if (fp) gzclose(fp); fp = nullptr; }
-    bool getline(std::string &s) {
-        s.clear();
+    // next line as [b, e) inside buf (without the terminator); false at end of file
+    bool line(const char *&b, const char *&e) {
         for (;;) {
-            if (pos == end) { int n = gzread(fp, buf.data(), (unsigned)buf.size()); if (n <= 0) return !s.empty(); pos = 0; end = (size_t)n; }
-            const char *b = buf.data() + pos, *e = (const char *)memchr(b, '\n', end - pos);
-            if (e) { s.append(b, e - b); pos += (size_t)(e - b) + 1; if (!s.empty() && s.back() == '\r') s.pop_back(); return true; }
-            s.append(b, end - pos); pos = end;
+            const char *s = buf.data() + pos;
+            const char *nl = pos < end ? (const char *)memchr(s, '\n', end - pos) : nullptr;
+            if (nl) { b = s; e = nl; pos = (size_t)(nl - buf.data()) + 1; if (e > b && e[-1] == '\r') --e; return true; }
+            if (eof) {
+                if (pos == end) return false;
+                b = s; e = buf.data() + end; pos = end; if (e > b && e[-1] == '\r') --e; return true;      // last line without a newline
+            }
+            // refill: keep the partial line at the front
+            const size_t keep = end - pos;
+            if (keep && pos) memmove(buf.data(), buf.data() + pos, keep);
+            pos = 0; end = keep;
+            if (end == buf.size()) buf.resize(buf.size() * 2);
+            const int n = gzread(fp, buf.data() + end, (unsigned)(buf.size() - end));
+            if (n <= 0) eof = true; else end += (size_t)n;
         }
     }
     // returns the number of records kept (<= n_max).  frac < 1: --frac_samp, the reference's per-record draw from a Mersenne
     // twister re-seeded with the IO round of the batch (src/BwtMapper.cpp:483-505; VerifyBamID/Random.cpp:155-198), so both
     // files of a pair drop the same records
     int fill(int n_max, int stride, uint8_t *bases, uint8_t *quals, int32_t *lens, char *names, int name_stride, double frac = 1.0, uint32_t seed = 0) {
-        std::string hdr, seq, plus, qual;
         std::mt19937 mt(seed);
+        std::string nm;
         int n = 0;
         while (n < n_max) {
             const double rand_num = ((double)mt() + 0.5) * (1.0 / 4294967296.0);
-            if (!getline(hdr)) break;
-            if (hdr.empty()) continue;
-            if (!getline(seq) || !getline(plus) || !getline(qual)) error("truncated FASTQ record");
-            if (rand_num > frac) continue;
-            if (seq.size() != qual.size()) error("sequence and quality lengths differ in a FASTQ record");
-            if ((int)seq.size() > stride) error("read longer than %d bases: not supported", stride);
-            memset(bases + (size_t)n * stride, 'N', (size_t)stride);
-            memset(quals + (size_t)n * stride, '!', (size_t)stride);
-            memcpy(bases + (size_t)n * stride, seq.data(), seq.size());
-            memcpy(quals + (size_t)n * stride, qual.data(), qual.size());
-            lens[n] = (int32_t)seq.size();
-            size_t l = hdr.find_first_of(" \t");
-            std::string nm = hdr.substr(1, l == std::string::npos ? std::string::npos : l - 1);
+            const char *hb, *he, *sb, *se, *pb, *pe, *qb, *qe;
+            if (!line(hb, he)) break;
+            if (hb == he) continue;
+            nm.assign(hb + 1, he);                     // the header may move when the buffer refills: copy it first
+            if (!line(sb, se)) error("truncated FASTQ record");
+            const size_t sl = (size_t)(se - sb);
+            if ((int)sl > stride) error("read longer than %d bases: not supported", stride);
+            const bool keep = !(rand_num > frac);
+            if (keep) {
+                memcpy(bases + (size_t)n * stride, sb, sl);
+                memset(bases + (size_t)n * stride + sl, 'N', (size_t)stride - sl);
+            }
+            if (!line(pb, pe) || !line(qb, qe)) error("truncated FASTQ record");
+            if ((size_t)(qe - qb) != sl) error("sequence and quality lengths differ in a FASTQ record");
+            if (!keep) continue;
+            memcpy(quals + (size_t)n * stride, qb, sl);
+            memset(quals + (size_t)n * stride + sl, '!', (size_t)stride - sl);
+            lens[n] = (int32_t)sl;
+            const size_t l = nm.find_first_of(" \t");
+            if (l != std::string::npos) nm.resize(l);
             if (nm.size() > 2 && nm[nm.size() - 2] == '/' && (nm.back() == '1' || nm.back() == '2')) nm.resize(nm.size() - 2);
-            memset(names + (size_t)n * name_stride, 0, (size_t)name_stride);
-            memcpy(names + (size_t)n * name_stride, nm.data(), std::min(nm.size(), (size_t)name_stride - 1));
+            char *dst = names + (size_t)n * name_stride;
+            const size_t nl = std::min(nm.size(), (size_t)name_stride - 1);
+            memcpy(dst, nm.data(), nl);
+            memset(dst + nl, 0, (size_t)name_stride - nl);
             ++n;
         }
         return n;

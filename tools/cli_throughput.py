@@ -12,5 +12,7 @@ for tag, exe, extra in (("b200", os.path.join(fx.REPO, "fastquick_b200", "FASTQu
     t0 = time.time()
     r = subprocess.run(cmd, cwd=idx.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     dt = time.time() - t0
+    for l in r.stdout.splitlines():
+        if "bam_emit" in l: print("   ", l)
     line = [l for l in r.stdout.splitlines() if "Processed Pair End mapping" in l]
     print(tag, "rc", r.returncode, "wall %.2fs" % dt, line[-1] if line else r.stdout[-300:], "bam %.1f MB" % (os.path.getsize(out + ".bam") / 1e6 if os.path.exists(out + ".bam") else 0), flush=True)
