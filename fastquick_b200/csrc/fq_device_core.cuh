@@ -33,6 +33,19 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 
 namespace fqb {
 
+// One 32-byte rank block in ONE load: sm_100a has 256-bit global loads (LDG.E.256), so a rank query costs a single
+// request to a single L2 sector (the blocks are 32-byte aligned).  Host builds read the two halves.
+FQB_HD void load_block(const uint4 *p, uint4 &cnt, uint4 &bases) {
+#if defined(__CUDA_ARCH__)
+    unsigned long long a, b, c, d;
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    cnt.x = (uint32_t)a; cnt.y = (uint32_t)(a >> 32); cnt.z = (uint32_t)b; cnt.w = (uint32_t)(b >> 32);
+    bases.x = (uint32_t)c; bases.y = (uint32_t)(c >> 32); bases.z = (uint32_t)d; bases.w = (uint32_t)(d >> 32);
+#else
+    cnt = p[0]; bases = p[1];
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // FM index, re-laid for the GPU: one 32-byte block (= one L2 sector) per 64 BWT
 // symbols: uint4 {cumulative A,C,G,T counts before the block} + uint4 {the 64 bases as
@@ -79,12 +92,13 @@ FQB_HD uint32_t occ1_block(const uint4 cnt, const uint4 bases, uint32_t n, uint3
 FQB_HD void occ1_pair(const DevBwt &b, uint32_t k, uint32_t l, uint32_t c, uint32_t &ok, uint32_t &ol) {
     uint32_t ll = l - (l >= b.primary);
     const uint4 *pl = b.blocks + 2 * (size_t)(ll >> 6);
-    if (k == kNoRow) { ok = 0; ol = occ1_block(FQB_LDG4(pl), FQB_LDG4(pl + 1), (ll & 63) + 1, c); return; }
+    uint4 cc, w;
+    if (k == kNoRow) { ok = 0; load_block(pl, cc, w); ol = occ1_block(cc, w, (ll & 63) + 1, c); return; }
     uint32_t kk = k - (k >= b.primary);
     const uint4 *pk = b.blocks + 2 * (size_t)(kk >> 6);
-    uint4 cc = FQB_LDG4(pk), w = FQB_LDG4(pk + 1);
+    load_block(pk, cc, w);
     ok = occ1_block(cc, w, (kk & 63) + 1, c);
-    if ((ll >> 6) != (kk >> 6)) { cc = FQB_LDG4(pl); w = FQB_LDG4(pl + 1); }
+    if ((ll >> 6) != (kk >> 6)) load_block(pl, cc, w);
     ol = occ1_block(cc, w, (ll & 63) + 1, c);
 }
 
@@ -92,7 +106,9 @@ FQB_HD void occ4(const DevBwt &b, uint32_t k, uint32_t out[4]) {
     if (k == kNoRow) { out[0] = out[1] = out[2] = out[3] = 0; return; }
     k -= (k >= b.primary);
     const uint4 *p = b.blocks + 2 * (size_t)(k >> 6);
-    occ4_block(FQB_LDG4(p), FQB_LDG4(p + 1), (k & 63) + 1, out);
+    uint4 c_, w_;
+    load_block(p, c_, w_);
+    occ4_block(c_, w_, (k & 63) + 1, out);
 }
 
 // Algorithmic occ-block touches of one bwt_2occ/bwt_2occ4(k, l) call as SURVEY.md §8(d) counts
@@ -109,11 +125,12 @@ FQB_HD void occ4_pair(const DevBwt &b, uint32_t k, uint32_t l, uint32_t ck[4], u
     if (k == kNoRow) { ck[0] = ck[1] = ck[2] = ck[3] = 0; occ4(b, l, cl); return; }
     uint32_t kk = k - (k >= b.primary), ll = l - (l >= b.primary);
     const uint4 *p = b.blocks + 2 * (size_t)(kk >> 6);
-    uint4 c = FQB_LDG4(p), w = FQB_LDG4(p + 1);
+    uint4 c, w;
+    load_block(p, c, w);
     occ4_block(c, w, (kk & 63) + 1, ck);
     if ((ll >> 6) != (kk >> 6)) {
         p = b.blocks + 2 * (size_t)(ll >> 6);
-        c = FQB_LDG4(p); w = FQB_LDG4(p + 1);
+        load_block(p, c, w);
     }
     occ4_block(c, w, (ll & 63) + 1, cl);
 }
@@ -126,7 +143,8 @@ FQB_HD uint32_t sa_lookup(const DevBwt &b, uint32_t k) {
         if (k == b.primary) { k = 0; continue; }
         uint32_t kk = k - (k > b.primary);          // stored index of row k's symbol
         const uint4 *p = b.blocks + 2 * (size_t)(kk >> 6);
-        uint4 c = FQB_LDG4(p), w = FQB_LDG4(p + 1);
+        uint4 c, w;
+        load_block(p, c, w);
         uint32_t j = kk & 63;
         const uint32_t sh = 31u - (j & 31u);
         uint32_t sym = (((j < 32 ? w.x : w.y) >> sh) & 1u) << 1 | (((j < 32 ? w.z : w.w) >> sh) & 1u);
@@ -399,10 +417,11 @@ struct SearchLane {
         const bool no_k = k == 0;                       // bwt_occ4(k - 1) with k - 1 == (bwtint_t)-1
         const uint32_t kk_ = no_k ? 0 : (k - 1) - ((k - 1) >= b.primary), ll_ = l - (l >= b.primary);
         const uint4 *pk = b.blocks + 2 * (size_t)(kk_ >> 6), *pl = b.blocks + 2 * (size_t)(ll_ >> 6);
-        const uint4 bk_c = FQB_LDG4(pk), bk_w = FQB_LDG4(pk + 1);
+        uint4 bk_c, bk_w;
+        load_block(pk, bk_c, bk_w);
         const bool same_blk = (kk_ >> 6) == (ll_ >> 6);
         uint4 bl_c = bk_c, bl_w = bk_w;
-        if (!same_blk) { bl_c = FQB_LDG4(pl); bl_w = FQB_LDG4(pl + 1); }
+        if (!same_blk) load_block(pl, bl_c, bl_w);
         const uint32_t c_here = fwd[len - i];                           // read_sym(i - 1), before complementing
         const uint32_t c_next = i >= 2 ? fwd[len - i + 1] : 4u;         // read_sym(i - 2)
         uint32_t w_hi = 0, w_lo = 0, s_hi = 0, s_lo = 0;
