@@ -31,7 +31,7 @@ READ_LEN = 100
 WORKLOAD = "synthetic 10M 2x100bp pairs (f_on=1, 1% subst, 0.1%+0.1% indel) vs synthetic 10,197-marker flank index"
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "FASTQuick_ref")
 NCU_DRAM_BYTES_PER_LAUNCH = 7.341e9   # search_kernel, one 262,144-pair launch: 3.499 GB read + 3.843 GB written (ncu capture r1f)
-REF_SAMPLE_PAIRS = 8192          # pairs per step of the reference arm / cpu_baseline sample unit
+REF_SAMPLE_PAIRS = 32768         # pairs per step of the reference arm / cpu_baseline sample unit
 STAGES = ("prep + k-mer filter + cal_width + match_gap + aln2seq/bwt_sa/mapQ + infer_isize + pairing + mate-rescue SW + gapped refinement + "
           "StatCollector pair classification and per-base pile-up/depth/quality/cycle accumulation (SURVEY 8 rows a1-a13)")
 
@@ -396,7 +396,7 @@ def main_gpu(args):
     if world == 1 and not args.no_cpu_baseline:
         try:
             workc = tempfile.mkdtemp(prefix="fqb_cpu_")
-            n_s = 4 * REF_SAMPLE_PAIRS
+            n_s = REF_SAMPLE_PAIRS
             if os.path.exists(REF_BIN):
                 rate, sec, cores = run_reference_sample(lib, synth, workc, 0, n_s)
                 line["cpu_baseline"] = {"value": rate, "unit": "read-pairs/s", "cores": cores, "kind": "reference",
