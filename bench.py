@@ -282,7 +282,7 @@ def main_gpu(args):
     def ptr(t):
         return C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_uint8))
 
-    rows_host = [torch.empty((n_pairs, _abi.READ_DTYPE.itemsize), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    rows_host = [[torch.empty((n_pairs, _abi.READ_DTYPE.itemsize), dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(2)]
     ii_host = _abi.ISize()
 
     def run_device(first_step, k):
@@ -290,16 +290,19 @@ def main_gpu(args):
         multigpu.run_sharded(eng, k * world, rank, world, device)
 
     def run_e2e(first_step, k):
-        # the public per-batch calls: pinned host FASTQ arrays in, per-read result rows out, statistics accumulated
+        # the public per-batch calls: pinned host FASTQ arrays in, per-read result rows out, statistics accumulated.
+        # Uploads of batch s+1 and the row copies of batch s overlap the kernels of the neighbouring batches.
         for s in range(first_step, first_step + k):
             b = host[s]
-            if s + 1 < first_step + k:                       # upload of the next batch overlaps this batch's kernels
+            if s + 1 < first_step + k:
                 nb = host[s + 1]
                 assert lib.fqb_prefetch_pairs(h, n_pairs, READ_LEN, ptr(nb[0]), ptr(nb[1]), None, ptr(nb[2]), ptr(nb[3]), None) == 0, lib.fqb_last_error()
-            rc = lib.fqb_align_pairs(h, n_pairs, READ_LEN, ptr(b[0]), ptr(b[1]), None, ptr(b[2]), ptr(b[3]), None,
-                                     C.c_void_p(rows_host[0].data_ptr()), C.c_void_p(rows_host[1].data_ptr()), C.byref(ii_host))
+            rc = lib.fqb_align_pairs(h, n_pairs, READ_LEN, ptr(b[0]), ptr(b[1]), None, ptr(b[2]), ptr(b[3]), None, None, None, C.byref(ii_host))
             assert rc == 0, lib.fqb_last_error()
             assert lib.fqb_stage_stats(h) == 0, lib.fqb_last_error()
+            dst = rows_host[s & 1]
+            assert lib.fqb_stage_fetch_rows_async(h, C.c_void_p(dst[0].data_ptr()), C.c_void_p(dst[1].data_ptr())) == 0, lib.fqb_last_error()
+        assert lib.fqb_rows_wait(h) == 0, lib.fqb_last_error()
 
     def rq_time():
         ms, nl = C.c_double(0.0), C.c_uint64(0)

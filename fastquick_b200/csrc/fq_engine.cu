@@ -68,7 +68,8 @@ struct fqb_handle {
     // processed and of the batch fqb_prefetch_pairs is uploading on the copy stream meanwhile
     uint8_t *d_in[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
     int32_t *d_lens_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_rows[3] = {nullptr, nullptr, nullptr};   // rows final on the main stream / split done / copies done
     cudaEvent_t ev_in[2] = {nullptr, nullptr};      // upload of set s complete
     cudaEvent_t ev_free[2] = {nullptr, nullptr};    // prep_kernel has consumed set s
     cudaEvent_t ev_rq[2] = {nullptr, nullptr};      // around the rank-query kernels (width + search) of a batch
@@ -251,6 +252,8 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     CU_CHECK_H(cudaSetDevice(device));
     CU_CHECK_H(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU_CHECK_H(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CU_CHECK_H(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+    for (auto &e : h->ev_rows) CU_CHECK_H(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         CU_CHECK_H(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
         CU_CHECK_H(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
@@ -326,6 +329,8 @@ void fqb_destroy(fqb_handle *h) {
     cudaFree(h->d_multi_out); cudaFree(h->d_multi_list); cudaFree(h->d_multi_ctr);
     if (h->bam_open) { std::string e; h->bam.close(e); }
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
+    for (auto &e : h->ev_rows) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); if (h->ev_rq[i]) cudaEventDestroy(h->ev_rq[i]); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1033,6 +1038,7 @@ int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fq
     if (!h || !h->pair_done) { set_error("fqb_stage_fetch_rows: run fqb_stage_pair first"); return FQB_ERR_STATE; }
     CU_CHECK(cudaSetDevice(h->device));
     const size_t np = (size_t)h->n_reads / 2;
+    CU_CHECK(cudaStreamWaitEvent(h->stream, h->ev_rows[2], 0));          // a pending asynchronous fetch still reads d_rows_split
     if (np) {
         // rows are interleaved by end on the device (r = 2*pair + end); split them there so that the two
         // device-to-host copies are contiguous (strided 96-byte copies crawl over PCIe)
@@ -1044,6 +1050,36 @@ int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fq
     }
     CU_CHECK(cudaStreamSynchronize(h->stream));
     if (ii_out) *ii_out = h->cur_ii;
+    return FQB_OK;
+}
+
+// The same copy, asynchronous: the rows of the resident batch are split and copied on a second stream while the caller
+// goes on to the next batch (the engine only waits for the 20-us split before it overwrites its row buffer).
+// fqb_rows_wait blocks until the destination buffers of the last fqb_stage_fetch_rows_async are complete.
+int fqb_stage_fetch_rows_async(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2) {
+    if (!h || !h->pair_done || !rows1 || !rows2) { set_error("fqb_stage_fetch_rows_async: run fqb_stage_pair first"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    const size_t np = (size_t)h->n_reads / 2;
+    CU_CHECK(cudaEventRecord(h->ev_rows[0], h->stream));
+    CU_CHECK(cudaStreamWaitEvent(h->d2h_stream, h->ev_rows[0], 0));
+    if (np) {
+        split_rows_kernel<<<(unsigned)((np * 2 * (sizeof(fqb_read_t) / 16) + 255) / 256), 256, 0, h->d2h_stream>>>(
+            reinterpret_cast<const uint4 *>(h->d_rows), reinterpret_cast<uint4 *>(h->d_rows_split), np);
+        ++h->n_launches;
+    }
+    CU_CHECK(cudaEventRecord(h->ev_rows[1], h->d2h_stream));
+    CU_CHECK(cudaStreamWaitEvent(h->stream, h->ev_rows[1], 0));          // later stages may overwrite d_rows only after the split
+    if (np) {
+        CU_CHECK(cudaMemcpyAsync(rows1, h->d_rows_split, np * sizeof(fqb_read_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+        CU_CHECK(cudaMemcpyAsync(rows2, h->d_rows_split + np, np * sizeof(fqb_read_t), cudaMemcpyDeviceToHost, h->d2h_stream));
+    }
+    CU_CHECK(cudaEventRecord(h->ev_rows[2], h->d2h_stream));
+    return FQB_OK;
+}
+int fqb_rows_wait(fqb_handle *h) {
+    if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    CU_CHECK(cudaSetDevice(h->device));
+    CU_CHECK(cudaEventSynchronize(h->ev_rows[2]));
     return FQB_OK;
 }
 

@@ -191,6 +191,10 @@ int fqb_stats_var_count(fqb_handle *h, int which, uint64_t *n);
 int fqb_stats_var_export(fqb_handle *h, int which, void *dst, uint64_t cap);
 int fqb_stats_var_import(fqb_handle *h, int which, const void *src, uint64_t n);
 int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
+/* asynchronous variant: the copies run on a side stream while the next batch is processed; fqb_rows_wait blocks until
+ * rows1/rows2 of the last call are complete (pinned destination buffers for real overlap) */
+int fqb_stage_fetch_rows_async(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2);
+int fqb_rows_wait(fqb_handle *h);
 /* new FASTQ pair: restart the drand48 stream and forget last_ii (src/BwtMapper.cpp:1811-1817) */
 int fqb_reset_stream(fqb_handle *h);
 int fqb_stage_fetch_prep(fqb_handle *h, int32_t *len, int32_t *full_len, uint8_t *filtered,

@@ -150,3 +150,28 @@ def test_warp_and_per_lane_dp_kernels_agree(small_index):
             os.environ.pop("FQB_DP_NO_WARP", None)
     assert crcs[0] == crcs[1]
     assert int((rows[0]["type"] == 3).sum() + (rows[1]["type"] == 3).sum()) > 500
+
+
+def test_async_row_fetch_equals_sync(small_index):
+    arrs = small_index.reads(3000, read_len=100, seed=86)
+    lib = fx.host_lib()
+    g = _abi.GapOpt()
+    lib.fqb_gap_opt_default(C.byref(g))
+    g.trim_qual = 15
+    h = C.c_void_p()
+    assert lib.fqb_create(small_index.prefix.encode(), C.byref(g), None, 0, C.byref(h)) == 0, lib.fqb_last_error()
+    try:
+        n, L = arrs[0].shape
+        sync = [np.zeros(n, _abi.READ_DTYPE) for _ in range(2)]
+        assert lib.fqb_align_pairs(h, n, L, _abi.u8p(arrs[0]), _abi.u8p(arrs[1]), None, _abi.u8p(arrs[2]), _abi.u8p(arrs[3]), None,
+                                   sync[0].ctypes.data_as(C.c_void_p), sync[1].ctypes.data_as(C.c_void_p), None) == 0, lib.fqb_last_error()
+        asy = [np.zeros(n, _abi.READ_DTYPE) for _ in range(2)]
+        assert lib.fqb_stage_fetch_rows_async(h, asy[0].ctypes.data_as(C.c_void_p), asy[1].ctypes.data_as(C.c_void_p)) == 0, lib.fqb_last_error()
+        # the next batch may start right away; its pair stage overwrites the device rows only after they were split off
+        assert lib.fqb_stage_load(h, n, L, _abi.u8p(arrs[2]), _abi.u8p(arrs[3]), None, _abi.u8p(arrs[0]), _abi.u8p(arrs[1]), None, 0) == 0
+        assert lib.fqb_stage_align(h) == 0 and lib.fqb_stage_pair(h) == 0, lib.fqb_last_error()
+        assert lib.fqb_rows_wait(h) == 0
+        for e in (0, 1):
+            assert asy[e].tobytes() == sync[e].tobytes()
+    finally:
+        lib.fqb_destroy(h)
