@@ -425,6 +425,29 @@ struct SwParams {
 };
 
 // bwa_paired_sw for one pair (libbwa/bwape.c:497-617), BWA_PET_STD.  Returns false if scratch was too small.
+// __set_rght_coor / __set_left_coor of bwa_paired_sw (libbwa/bwape.c:510-523): where to look for `pm` given its mate `pref`
+FQB_HD void sw_window(const fqb_read_t &pref_, const fqb_read_t &pm_, const SwParams &sp, int64_t &b, int64_t &e, int &strand) {
+    const fqb_read_t *pref = &pref_, *pm = &pm_;
+    const double dlen = (double)pm->len;
+    if (pref->strand == 0) {        // mate on the reverse strand, to the right
+        double a = FQB_DSUB(FQB_DSUB(FQB_DADD((double)(int64_t)pref->pos, sp.avg), FQB_DMUL(3.0, sp.std)), FQB_DMUL(dlen, 1.5));
+        b = (int64_t)a;
+        e = (int64_t)FQB_DADD(FQB_DADD((double)b, FQB_DMUL(6.0, sp.std)), (double)(2 * pm->len));
+        // the reference assigns `_pref->pos + _pref->len` here, a 32-bit sum: it wraps when the gapped read's provisional
+        // position underflowed (a forward read with an insertion at the very start of the first contig)
+        if (b < (int64_t)pref->pos + pref->len) b = (int64_t)(uint32_t)(pref->pos + (uint32_t)pref->len);
+        if (e > sp.l_pac) e = sp.l_pac;
+        strand = 1;
+    } else {                        // mate on the forward strand, to the left
+        double a = FQB_DSUB(FQB_DSUB(FQB_DSUB((double)((int64_t)pref->pos + pref->len), sp.avg), FQB_DMUL(3.0, sp.std)), FQB_DMUL(dlen, 0.5));
+        b = (int64_t)a;
+        e = (int64_t)FQB_DADD(FQB_DADD((double)b, FQB_DMUL(6.0, sp.std)), (double)(2 * pm->len));
+        if (b < 0) b = 0;
+        if (e > (int64_t)pref->pos) e = pref->pos;
+        strand = 0;
+    }
+}
+
 // `core` runs bwa_sw_core for one mate (per thread, or cooperatively by a warp whose lanes all call this function).
 template <class Core>
 FQB_HD bool paired_sw_pair(const uint8_t *pac, fqb_read_t *p0, fqb_read_t *p1, const uint8_t *fwd0, const uint8_t *fwd1,
@@ -440,22 +463,7 @@ FQB_HD bool paired_sw_pair(const uint8_t *pac, fqb_read_t *p0, fqb_read_t *p1, c
         if (pref->type == kTypeNoMatch) continue;
         ReadSeq Q; Q.fwd = k ? fwd1 : fwd0; Q.len = pm->len;
         int64_t b, e;
-        const double dlen = (double)pm->len;
-        if (pref->strand == 0) {        // mate on the reverse strand, to the right
-            double a = FQB_DSUB(FQB_DSUB(FQB_DADD((double)(int64_t)pref->pos, sp.avg), FQB_DMUL(3.0, sp.std)), FQB_DMUL(dlen, 1.5));
-            b = (int64_t)a;
-            e = (int64_t)FQB_DADD(FQB_DADD((double)b, FQB_DMUL(6.0, sp.std)), (double)(2 * pm->len));
-            if (b < (int64_t)pref->pos + pref->len) b = (int64_t)pref->pos + pref->len;
-            if (e > sp.l_pac) e = sp.l_pac;
-            Q.strand = 1;
-        } else {                        // mate on the forward strand, to the left
-            double a = FQB_DSUB(FQB_DSUB(FQB_DSUB((double)((int64_t)pref->pos + pref->len), sp.avg), FQB_DMUL(3.0, sp.std)), FQB_DMUL(dlen, 0.5));
-            b = (int64_t)a;
-            e = (int64_t)FQB_DADD(FQB_DADD((double)b, FQB_DMUL(6.0, sp.std)), (double)(2 * pm->len));
-            if (b < 0) b = 0;
-            if (e > (int64_t)pref->pos) e = pref->pos;
-            Q.strand = 0;
-        }
+        sw_window(*pref, *pm, sp, b, e, Q.strand);
         beg[k] = b;
         int nc = core(sp.l_pac, pac, Q, &beg[k], (int)(e - b), cig[k], &cnt[k]);
         if (nc < 0) return false;

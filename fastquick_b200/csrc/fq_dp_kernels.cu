@@ -53,6 +53,7 @@ __global__ void sw_classify_kernel(DpView v, uint32_t *list, uint32_t *n_list) {
 }
 
 constexpr int kWarpsPerBlock = 8;
+constexpr uint32_t kHugeMaxPairs = 64, kHugeMaxJobs = 128, kHugeMaxSlices = 1u << 16;   // very wide windows per batch (rare)
 constexpr size_t kWarpSlab = 256u * 1024u;       // per-warp global slab: path ops + trace-back matrix
 
 // shared memory of a block: kWarpsPerBlock x smem_ints words of DP rows, then kWarpsPerBlock x ref_cap bytes of reference codes
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) sw_warp_kernel(DpView v, 
     while (next_item_warp(cursor, n, j)) {
         const uint32_t p = list[j];
         fqb_read_t r0 = v.rows[2 * p], r1 = v.rows[2 * p + 1];
-        WarpSwCore core{w};
+        WarpSwCore core{w, nullptr, p, 0};
         const bool ok = paired_sw_pair(v.pac, &r0, &r1, v.codes + (size_t)(2 * p) * v.lpad, v.codes + (size_t)(2 * p + 1) * v.lpad, sp, core);
         if (w.lane == 0) {
             if (!ok) retry[atomicAdd(n_retry, 1u)] = p;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) sw_warp_kernel(DpView v, 
 
 // one pair per lane, everything in global scratch (retry list)
 __global__ void __launch_bounds__(kDpThreads) sw_kernel(DpView v, SwParams sp, DpPool pool, const uint32_t *list, const uint32_t *n_list,
-                                                         uint32_t *cursor, uint32_t *err) {
+                                                         uint32_t *cursor, uint32_t *err, uint32_t *huge_list, uint32_t *n_huge) {
     DpScratch sc = lane_scratch(pool);
     const uint32_t n = *n_list;
     uint32_t j;
@@ -102,8 +103,86 @@ __global__ void __launch_bounds__(kDpThreads) sw_kernel(DpView v, SwParams sp, D
         const uint32_t p = list[j];
         fqb_read_t r0 = v.rows[2 * p], r1 = v.rows[2 * p + 1];
         bool ok = paired_sw_one(v.pac, &r0, &r1, v.codes + (size_t)(2 * p) * v.lpad, v.codes + (size_t)(2 * p + 1) * v.lpad, sp, sc);
-        if (!ok) { atomicExch(err, p + 1); continue; }
+        if (!ok) {                      // a window wider than the per-lane scratch: the sliced-scan path takes it
+            const uint32_t slot = atomicAdd(n_huge, 1u);
+            if (slot < kHugeMaxPairs) huge_list[slot] = p; else atomicExch(err, p + 1);
+            continue;
+        }
         v.rows[2 * p] = r0; v.rows[2 * p + 1] = r1;
+    }
+}
+
+// ---- very wide mate-rescue windows (fq_dp_warp.cuh): prepare the scan jobs, scan the slices, finish the pairs ----
+struct HugeBuf { HugeJob *jobs; uint32_t *slice_job; ScanBest *slice_best; uint32_t *ctr; };   // ctr: [0] n_jobs [1] n_slices [2] scan cursor [3] finish cursor
+
+__global__ void sw_huge_prepare_kernel(DpView v, SwParams sp, const uint32_t *huge_list, const uint32_t *n_huge, HugeBuf hb, int ref_cap, uint32_t *err) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = *n_huge < kHugeMaxPairs ? *n_huge : kHugeMaxPairs;
+    if (t >= n) return;
+    const uint32_t p = huge_list[t];
+    const fqb_read_t r[2] = {v.rows[2 * p], v.rows[2 * p + 1]};
+    for (int k = 0; k < 2; ++k) {
+        const fqb_read_t &pref = r[1 - k], &pm = r[k];
+        if (pref.type == kTypeNoMatch) continue;
+        int64_t b, e; int strand;
+        sw_window(pref, pm, sp, b, e, strand);
+        const int reglen = (int)(e - b), len = pm.len;
+        if (reglen < 20 || sp.l_pac - b < len) continue;                                   // bwa_sw_core's own early exits
+        const int64_t end = b + reglen < sp.l_pac ? b + reglen : sp.l_pac;
+        const int wlen = (int)(end - b);
+        if (wlen + 2 <= ref_cap) continue;                                                  // the finishing warp aligns it in shared memory
+        if (len + 11 * len / 9 + 2 > kScanOverlap) { atomicExch(err, p + 1); return; }     // overlap argument needs short reads
+        const uint32_t j = atomicAdd(hb.ctr, 1u);
+        const int n_sl = (wlen + kScanCore - 1) / kScanCore;
+        const uint32_t s0 = atomicAdd(hb.ctr + 1, (uint32_t)n_sl);
+        if (j >= kHugeMaxJobs || s0 + n_sl > kHugeMaxSlices) { atomicExch(err, p + 1); return; }
+        HugeJob J; J.pair = p; J.k = k; J.beg = b; J.reglen = reglen; J.strand = strand; J.n_slices = n_sl; J.first_slice = (int)s0;
+        hb.jobs[j] = J;
+        for (int q = 0; q < n_sl; ++q) hb.slice_job[s0 + q] = j;
+    }
+}
+
+__global__ void __launch_bounds__(4 * 32) sw_huge_scan_kernel(DpView v, SwParams sp, HugeBuf hb, int smem_ints, int ref_cap) {
+    extern __shared__ int32_t dp_smem[];
+    const int wid = threadIdx.x >> 5;
+    WarpDp w;
+    w.sm = dp_smem + (size_t)wid * smem_ints; w.n_ints = smem_ints;
+    w.refc = reinterpret_cast<uint8_t *>(dp_smem + (size_t)4 * smem_ints) + (size_t)wid * ref_cap; w.n_refc = ref_cap;
+    w.gb = nullptr; w.n_bytes = 0; w.lane = threadIdx.x & 31;
+    const uint32_t n_sl = hb.ctr[1] < kHugeMaxSlices ? hb.ctr[1] : kHugeMaxSlices;
+    uint32_t sidx;
+    while (next_item_warp(hb.ctr + 2, n_sl, sidx)) {
+        const HugeJob J = hb.jobs[hb.slice_job[sidx]];
+        const int q = (int)sidx - J.first_slice;
+        const fqb_read_t pm = v.rows[2 * J.pair + J.k];
+        ReadSeq Q; Q.fwd = v.codes + (size_t)(2 * J.pair + J.k) * v.lpad; Q.len = pm.len; Q.strand = J.strand;
+        RefWin R; R.pac = v.pac; R.beg = J.beg;
+        { const int64_t end = J.beg + J.reglen < sp.l_pac ? J.beg + J.reglen : sp.l_pac; R.l = (int)(end - J.beg); }
+        const int lo = q * kScanCore + 1, hi = (q + 1) * kScanCore < R.l ? (q + 1) * kScanCore : R.l;
+        // bwa_sw_core's N check is repeated by the finishing kernel; a window that fails it is never looked up
+        const ScanBest sb = warp_local_scan_slice(R, lo, hi, Q, pm.len, w);
+        if (w.lane == 0) hb.slice_best[sidx] = sb;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) sw_huge_finish_kernel(DpView v, SwParams sp, DpPool pool, const uint32_t *huge_list, const uint32_t *n_huge,
+                                                                              HugeBuf hb, int smem_ints, int ref_cap, uint32_t *err) {
+    extern __shared__ int32_t dp_smem[];
+    const WarpDp w = warp_scratch(pool, dp_smem, smem_ints, ref_cap);
+    const uint32_t n = *n_huge < kHugeMaxPairs ? *n_huge : kHugeMaxPairs;
+    HugeView hv; hv.jobs = hb.jobs; hv.slice_best = hb.slice_best; hv.n_jobs = (int)(hb.ctr[0] < kHugeMaxJobs ? hb.ctr[0] : kHugeMaxJobs);
+    uint32_t j;
+    while (next_item_warp(hb.ctr + 3, n, j)) {
+        const uint32_t p = huge_list[j];
+        fqb_read_t r0 = v.rows[2 * p], r1 = v.rows[2 * p + 1];
+        WarpSwCore core{w, &hv, p, 0};
+        const bool ok = paired_sw_pair(v.pac, &r0, &r1, v.codes + (size_t)(2 * p) * v.lpad, v.codes + (size_t)(2 * p + 1) * v.lpad, sp, core);
+        if (w.lane == 0) {
+            if (!ok) atomicExch(err, p + 1);
+            else { v.rows[2 * p] = r0; v.rows[2 * p + 1] = r1; }
+        }
+        __syncwarp();
     }
 }
 
@@ -229,18 +308,40 @@ static int warp_blocks(const DpPool &pool) {
 }
 
 // ctr: [0] n_list [1] cursor [2] n_retry [3] retry cursor (device words)
-void launch_sw(const DpView &v, const SwParams &sp, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, cudaStream_t s) {
+void launch_sw(const DpView &v, const SwParams &sp, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, void *huge_mem,
+               cudaStream_t s) {
     sw_classify_kernel<<<(v.n_reads / 2 + 255) / 256, 256, 0, s>>>(v, list, ctr);
     const int ints = 2 * kSwSmemInts;                                    // H and E rows of a <= 702-column window
     const int ref_cap = kSwSmemInts;                                     // reference codes of the window, one byte each
     const size_t smem = (size_t)ints * kWarpsPerBlock * 4 + (size_t)ref_cap * kWarpsPerBlock;
-    cudaFuncSetAttribute(sw_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // the rare very wide windows: buffers carved from huge_mem (launch_sw_huge_bytes())
+    HugeBuf hb;
+    char *hm = static_cast<char *>(huge_mem);
+    hb.ctr = reinterpret_cast<uint32_t *>(hm); hm += 64;
+    uint32_t *huge_list = reinterpret_cast<uint32_t *>(hm); hm += kHugeMaxPairs * 4;
+    hb.jobs = reinterpret_cast<HugeJob *>(hm); hm += kHugeMaxJobs * sizeof(HugeJob);
+    hb.slice_job = reinterpret_cast<uint32_t *>(hm); hm += (size_t)kHugeMaxSlices * 4;
+    hb.slice_best = reinterpret_cast<ScanBest *>(hm);
+    uint32_t *n_huge = hb.ctr + 4;
+    cudaMemsetAsync(hb.ctr, 0, 64, s);
     if (getenv("FQB_DP_NO_WARP"))        // debugging aid: everything through the one-alignment-per-lane kernels
-        sw_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, sp, pool, list, ctr, ctr + 1, err);
+        sw_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, sp, pool, list, ctr, ctr + 1, err, huge_list, n_huge);
     else {
+        cudaFuncSetAttribute(sw_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         sw_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, sp, pool, list, ctr, ctr + 1, ints, ref_cap, retry, ctr + 2);
-        sw_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, sp, pool, retry, ctr + 2, ctr + 3, err);
+        sw_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, sp, pool, retry, ctr + 2, ctr + 3, err, huge_list, n_huge);
     }
+    // windows wider than the per-lane scratch: sliced forward scan over all SMs, then the pair is finished by one warp
+    sw_huge_prepare_kernel<<<1, kHugeMaxPairs, 0, s>>>(v, sp, huge_list, n_huge, hb, ref_cap, err);
+    const int scan_ints = 2 * (kScanCore + kScanOverlap + 2), scan_ref = kScanCore + kScanOverlap;
+    const size_t scan_smem = (size_t)scan_ints * 4 * 4 + (size_t)scan_ref * 4;
+    cudaFuncSetAttribute(sw_huge_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
+    sw_huge_scan_kernel<<<pool.n_blocks, 4 * 32, scan_smem, s>>>(v, sp, hb, scan_ints, scan_ref);
+    cudaFuncSetAttribute(sw_huge_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    sw_huge_finish_kernel<<<8, kWarpsPerBlock * 32, smem, s>>>(v, sp, pool, huge_list, n_huge, hb, ints, ref_cap, err);
+}
+size_t launch_sw_huge_bytes() {
+    return 64 + kHugeMaxPairs * 4 + kHugeMaxJobs * sizeof(HugeJob) + (size_t)kHugeMaxSlices * 4 + (size_t)kHugeMaxSlices * sizeof(ScanBest);
 }
 void launch_refine(const DpView &v, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, int max_read_len, cudaStream_t s) {
     refine_classify_kernel<<<(v.n_reads + 255) / 256, 256, 0, s>>>(v, list, ctr);

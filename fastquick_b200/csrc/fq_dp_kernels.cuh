@@ -38,7 +38,10 @@ struct MultiView {
 void launch_multi(const DpView &v, const MultiView &mv, const DpPool &pool, uint32_t *list, uint32_t *ctr, MultiOut *out, uint32_t out_cap,
                   uint32_t *err, cudaStream_t s);
 
-void launch_sw(const DpView &v, const SwParams &sp, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, cudaStream_t s);
+// huge_mem: launch_sw_huge_bytes() bytes of device memory for the very-wide-window path
+void launch_sw(const DpView &v, const SwParams &sp, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, void *huge_mem,
+               cudaStream_t s);
+size_t launch_sw_huge_bytes();
 void launch_refine(const DpView &v, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, int max_read_len, cudaStream_t s);
 
 }  // namespace fqb

@@ -297,10 +297,82 @@ __device__ LocalResult warp_local_align(const RefWin &R, int len1, const ReadSeq
     return res;
 }
 
+// ---- very wide mate-rescue windows -----------------------------------------------------------------------------------
+// (they arise when a gapped forward read's provisional position underflowed and bwa_paired_sw's window arithmetic wraps:
+// the reference then runs aln_local_core over almost the whole reduced reference.)  The forward pass is split into column
+// slices that are scanned independently: a local alignment of a len2-base read with a positive score spans fewer than
+// len2 + 11 len2 / 9 columns, so a slice that starts kScanOverlap columns before its core computes exact H values on the
+// core.  Each slice reports its first maximum in row-major order; the smallest (row, column) among the slices that reach the
+// global maximum is the cell the reference's single pass would report.
+constexpr int kScanCore = 1792, kScanOverlap = 256;       // columns per slice / overlap (>= 100 + 1100 / 9 for reads <= 100 bp... checked at run time)
+struct ScanBest { int score, j, i; };
+
+__device__ ScanBest warp_local_scan_slice(const RefWin &R, int core_lo, int core_hi, const ReadSeq &Q, int len2, const WarpDp &w) {
+    ScanBest best; best.score = 0; best.j = 0; best.i = 0;
+    const int lane = w.lane, q = kGapOpen, r = kGapExt, qr = q + r;
+    const int c0 = core_lo - kScanOverlap > 1 ? core_lo - kScanOverlap : 1;     // first column computed (1-based in the window)
+    const int wl = core_hi - c0 + 1, W = wl + 2;
+    if (2 * W > w.n_ints || wl > w.n_refc) { best.score = -2; return best; }
+    int32_t *H = w.sm, *E = w.sm + W;
+    for (int i = lane; i < W; i += 32) { H[i] = 0; E[i] = 0; }
+    for (int i = lane; i < wl; i += 32) w.refc[i] = (uint8_t)R.at(c0 - 1 + i);
+    __syncwarp();
+    const int first_core = core_lo - c0 + 1;                                   // local index of the first core column
+    for (int j = 1; j <= len2; ++j) {
+        const uint32_t qj = Q.at(j - 1);
+        const bool qn = qj > 3;
+        int carry_g = kVeryNeg, carry_diag = 0, row_best = 0, row_best_i = 0;
+        for (int base = 1; base <= wl; base += 32) {
+            const int i = base + lane;
+            const bool on = i <= wl;
+            const int hp = on ? H[i] : 0, ep = on ? E[i] : 0;
+            int hd = __shfl_up_sync(FQB_FULL, hp, 1);
+            if (lane == 0) hd = carry_diag;
+            int e = 0;
+            if (hp >= qr + 1) { e = ep - r; if (hp - qr > e) e = hp - qr; }
+            int h1 = on ? hd + maq_row_score(w.refc[i - 1], qj, qn) : 0;
+            if (h1 < 0) h1 = 0;
+            if (h1 < e) h1 = e;
+            const int g = on ? h1 + i * r : kVeryNeg;
+            const int pm = warp_incl_max(g, lane);
+            int pe = __shfl_up_sync(FQB_FULL, pm, 1);
+            if (lane == 0) pe = kVeryNeg;
+            if (carry_g > pe) pe = carry_g;
+            int h = h1;
+            if (pe > kVeryNeg / 2) { const int f = pe - q - i * r; if (f > h) h = f; }
+            const int lastl = (wl - base) < 31 ? (wl - base) : 31;
+            carry_diag = __shfl_sync(FQB_FULL, hp, lastl);
+            { const int t = __shfl_sync(FQB_FULL, pm, lastl); if (t > carry_g) carry_g = t; }
+            __syncwarp();
+            if (on) {
+                H[i] = h; E[i] = e;
+                if (i >= first_core && h > row_best) { row_best = h; row_best_i = i; }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int ob = __shfl_xor_sync(FQB_FULL, row_best, d), oi = __shfl_xor_sync(FQB_FULL, row_best_i, d);
+            if (ob > row_best || (ob == row_best && oi < row_best_i)) { row_best = ob; row_best_i = oi; }
+        }
+        if (row_best > best.score) { best.score = row_best; best.j = j; best.i = c0 - 1 + row_best_i; }
+        __syncwarp();
+    }
+    return best;
+}
+
+struct HugeJob {                      // one very wide window of one mate
+    uint32_t pair; int32_t k;
+    long long beg; int32_t reglen, strand;
+    int32_t n_slices, first_slice;
+};
+struct HugeView { const HugeJob *jobs; const ScanBest *slice_best; int n_jobs; };
+
 // bwa_sw_core by a warp: all lanes run the checks and the DP, lane 0 turns the path into the CIGAR and counts, and
 // the values the caller's control flow depends on are broadcast (the other lanes' cigar[] holds only the end elements).
 struct WarpSwCore {
     const WarpDp &w;
+    const HugeView *huge;             // scan results for the windows that do not fit the shared-memory rows (or nullptr)
+    uint32_t pair; int k_hint;        // which pair is being processed (to find its scan results); k_hint is advanced per call
     __device__ int operator()(int64_t l_pac, const uint8_t *pac, const ReadSeq &Q, int64_t *beg, int reglen, uint16_t *cigar, uint32_t *cnt) const {
         const int len = Q.len, lane = w.lane;
         if (reglen < 20 || l_pac - *beg < len) return 0;
@@ -311,7 +383,32 @@ struct WarpSwCore {
         if ((float)nn / len >= 0.25f || len - nn < 20) return 0;
         RefWin R; R.pac = pac; R.beg = *beg;
         { int64_t e = *beg + reglen < l_pac ? *beg + reglen : l_pac; R.l = (int)(e - *beg); }
-        LocalResult lr = warp_local_align(R, R.l, Q, len, w);
+        LocalResult lr;
+        if (R.l + 2 <= w.n_refc || !huge) lr = warp_local_align(R, R.l, Q, len, w);
+        else {
+            // a scanned window: the slices found where the forward pass ends; everything else happens in a narrow
+            // sub-window that ends at that column (the reverse pass and the final global alignment never leave it)
+            int jid = -1;
+            for (int t = 0; t < huge->n_jobs; ++t)
+                if (huge->jobs[t].pair == pair && huge->jobs[t].beg == (long long)*beg && huge->jobs[t].reglen == reglen && huge->jobs[t].strand == Q.strand) { jid = t; break; }
+            if (jid < 0) return -1;
+            const HugeJob &J = huge->jobs[jid];
+            ScanBest best; best.score = 0; best.j = 0; best.i = 0;
+            for (int t = 0; t < J.n_slices; ++t) {
+                const ScanBest sb = huge->slice_best[J.first_slice + t];
+                if (sb.score < 0) return -1;
+                if (sb.score > best.score || (sb.score == best.score && sb.score > 0 && (sb.j < best.j || (sb.j == best.j && sb.i < best.i)))) best = sb;
+            }
+            lr.score = best.score; lr.n_ops = 0; lr.start_i = lr.start_j = lr.end_i = lr.end_j = 0; lr.too_big = false;
+            if (best.score >= 1) {
+                const int span = w.n_refc - 2 < 640 ? w.n_refc - 2 : 640;
+                const int off = best.i > span ? best.i - span : 0;
+                RefWin R2; R2.pac = pac; R2.beg = R.beg + off; R2.l = best.i - off;
+                lr = warp_local_align(R2, R2.l, Q, len, w);
+                if (lr.too_big || lr.end_i != R2.l || lr.end_j != best.j) return -1;       // must end where the full pass ends
+                lr.start_i += off; lr.end_i += off;
+            }
+        }
         if (lr.too_big) return -1;
         int nc = 0;
         long long b = *beg;

@@ -112,6 +112,7 @@ struct fqb_handle {
     bool align_done = false, pair_done = false, dp_done = false;
     bool single_end = false;                     // the resident batch came without second reads (SingleEndMapper)
     uint32_t *d_sw_list = nullptr, *d_refine_list = nullptr;   // each: work list followed by its retry list
+    void *d_sw_huge = nullptr;                                 // buffers of the very-wide-window mate-rescue path
     uint32_t *d_dpctr = nullptr;                             // [0..3] SW list/cursors, [4..7] refine list/cursors, [8] error
     DpPool dp_pool = {nullptr, nullptr, 0, 0, 0};
     // statistics rows (a12-a14)
@@ -324,7 +325,7 @@ void fqb_destroy(fqb_handle *h) {
     for (int s = 0; s < 2; ++s) { cudaFree(h->d_blocks[s]); cudaFree(h->d_sa[s]); }
     cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_ctrs); cudaFree(h->d_order_bins); cudaFree(h->d_counters);
     cudaFree(h->d_arena); cudaFree(h->d_arena_mid); cudaFree(h->d_arena_big); cudaFree(h->d_aln_big);
-    cudaFree(h->pesc.totals); cudaFree(h->pesc.err_flag); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch); cudaFree(h->dp_pool.ints); cudaFree(h->dp_pool.bytes); cudaFree(h->d_dpctr);
+    cudaFree(h->pesc.totals); cudaFree(h->pesc.err_flag); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch); cudaFree(h->dp_pool.ints); cudaFree(h->dp_pool.bytes); cudaFree(h->d_dpctr); cudaFree(h->d_sw_huge);
     cudaFreeHost(h->h_rows); cudaFreeHost(h->h_pstat); cudaFreeHost(h->h_bam_rows);
     cudaFree(h->d_multi_out); cudaFree(h->d_multi_list); cudaFree(h->d_multi_ctr);
     if (h->bam_open) { std::string e; h->bam.close(e); }
@@ -587,8 +588,9 @@ int fqb_stage_sw_refine(fqb_handle *h) {
         sp.s_old_add = -4.343 * std::log(ii.ap_prior / h->hidx.l_pac);                      // libbwa/bwape.c:577
         sp.s_new_add = (int)(-4.343 * std::log(.5 * std::erfc(M_SQRT1_2 * 1.5) + .499));     // libbwa/bwape.c:578
         CU_CHECK(cudaMemsetAsync(h->d_dpctr, 0, 12 * 4, st));
-        launch_sw(v, sp, h->dp_pool, h->d_sw_list, h->d_sw_list + h->cap_reads / 2, h->d_dpctr, h->d_dpctr + 8, st);
-        h->n_launches += 3;
+        if (!h->d_sw_huge) CU_CHECK(cudaMalloc(&h->d_sw_huge, launch_sw_huge_bytes()));
+        launch_sw(v, sp, h->dp_pool, h->d_sw_list, h->d_sw_list + h->cap_reads / 2, h->d_dpctr, h->d_dpctr + 8, h->d_sw_huge, st);
+        h->n_launches += 6;      // classify, warp kernel, per-lane retry, and the three kernels of the very-wide-window path
     }
     else CU_CHECK(cudaMemsetAsync(h->d_dpctr, 0, 12 * 4, st));
     launch_refine(v, h->dp_pool, h->d_refine_list, h->d_refine_list + h->cap_reads, h->d_dpctr + 4, h->d_dpctr + 8, h->stride, st);

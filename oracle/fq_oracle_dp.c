@@ -390,7 +390,7 @@ void orc_paired_sw(int64_t l_pac, const uint8_t *pac, int n_pairs, orc_row_t *ro
                 if (pref->strand == 0) {
                     beg[k] = (int64_t)((int64_t)pref->pos + ii->avg - 3 * ii->std - pm->len * 1.5);
                     end[k] = (int64_t)(beg[k] + 6 * ii->std + 2 * pm->len);
-                    if (beg[k] < (int64_t)pref->pos + pref->len) beg[k] = (int64_t)pref->pos + pref->len;
+                    if (beg[k] < (int64_t)pref->pos + pref->len) beg[k] = (int64_t)(uint32_t)(pref->pos + (uint32_t)pref->len);   /* 32-bit sum in the reference (bwape.c:513) */
                     if (end[k] > l_pac) end[k] = l_pac;
                     oriented(codes + (size_t)(2 * i + k) * stride, pm->len, 1, seq);
                 } else {

@@ -201,3 +201,31 @@ def test_cli_fastq_list_matches_reference(small_index, ref_required):
         _compare_files(outs["ref"] + "." + ext, outs["b200"] + "." + ext)
     assert sum(1 for _ in open(outs["ref"] + ".FASTQ.csv")) == 4          # header + three files
     _compare_bams(outs["ref"] + ".bam", outs["b200"] + ".bam")
+
+
+def test_cli_two_reference_sized_batches(small_index, ref_required):
+    """300,000 pairs = one full 262,144-pair batch plus a partial one at the reference's real batch size: the drand48
+    position, last_ii and every accumulator cross the batch boundary exactly as in the reference (about 40 s of CPU for
+    the reference run)."""
+    if not os.path.exists(fx.REF_BIN):
+        pytest.skip("FASTQuick_ref not built")
+    arrs = small_index.reads(300000, read_len=100, seed=95)
+    fq = small_index.write_fastq("clibig", arrs)
+    idx_prefix = small_index.prefix[: -len(".FASTQuick.fa")]
+    outs = {}
+    for tag, exe in (("ref", fx.REF_BIN), ("b200", CLI)):
+        out = os.path.join(small_index.dir, "clibig_" + tag)
+        cmd = [exe, "align", "--fastq_1", fq[0], "--fastq_2", fq[1], "--index_prefix", idx_prefix, "--out_prefix", out, "--t", str(os.cpu_count() or 4),
+               "--q", "15"]
+        r = subprocess.run(cmd, cwd=small_index.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-3000:]
+        outs[tag] = out
+    for ext in TEXT_FILES + ["FASTQ.csv"]:
+        _compare_files(outs["ref"] + "." + ext, outs["b200"] + "." + ext)
+    recs = _compare_bams(outs["ref"] + ".bam", outs["b200"] + ".bam")
+    assert len(recs) > 590000
+    for tag in outs:                                   # half a gigabyte of outputs: clean up
+        for ext in ("bam", "InsertSizeTable"):
+            os.remove(outs[tag] + "." + ext)
+    for f in fq:
+        os.remove(f)
