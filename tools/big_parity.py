@@ -6,11 +6,18 @@ import numpy as np
 import fx, bamio
 from test_gpu_stats import TEXT_FILES, _compare_files
 CLI = os.path.join(fx.REPO, "fastquick_b200", "FASTQuick_b200")
-idx = fx.SynthIndex("small", n_long=40, n_short=160, n_x=5, n_y=5, with_rollhash=True)
-cases = {
+if os.environ.get("FQB_BIG_INDEX") == "10k":      # the BASELINE marker set: 1000 long + 9000 short + 100 X + 97 Y flanks
+    idx = fx.SynthIndex("bench10k", n_long=1000, n_short=9000, n_x=100, n_y=97, with_rollhash=True)
+else:
+    idx = fx.SynthIndex("small", n_long=40, n_short=160, n_x=5, n_y=5, with_rollhash=True)
+all_cases = {
+    "err100": (300000, dict(read_len=100, seed=203, sub_rate=0.04, ins_rate=0.01, del_rate=0.01, max_indel_len=4)),
+    "off100": (400000, dict(read_len=100, seed=204, f_on=0.3, sub_rate=0.015)),
     "big100": (int(sys.argv[1]) if len(sys.argv) > 1 else 1000000, dict(read_len=100, seed=201, f_on=0.95, sub_rate=0.012, ins_rate=0.002, del_rate=0.002, max_indel_len=3)),
     "big150": (int(sys.argv[2]) if len(sys.argv) > 2 else 300000, dict(read_len=150, seed=202, sub_rate=0.02, ins_rate=0.004, del_rate=0.004, max_indel_len=4)),
 }
+sel = os.environ.get("FQB_BIG_CASES", "big100,big150").split(",")
+cases = {k: all_cases[k] for k in sel}
 for name, (n, kw) in cases.items():
     t0 = time.time()
     arrs = idx.reads(n, **kw)
