@@ -131,6 +131,7 @@ struct fqb_handle {
     uint64_t pairs_seen = 0;                     // global pair index of the next batch
     std::vector<PileupColumn> pileup;
     std::vector<PileupTuple> tuples_host;          // pile-up entries drained from the device (own batches + imported ones)
+    PileupTuple *d_tuples_imp = nullptr; size_t n_tuples_imp = 0, cap_tuples_imp = 0;   // entries imported from other handles, kept on the device until the files are written
     std::vector<FileCounters> files;
     // BAM emission (row f1)
     BgzfWriter bam; bool bam_open = false; BamContext bam_ctx;
@@ -327,7 +328,7 @@ void fqb_destroy(fqb_handle *h) {
     cudaFree(h->d_arena); cudaFree(h->d_arena_mid); cudaFree(h->d_arena_big); cudaFree(h->d_aln_big);
     cudaFree(h->pesc.totals); cudaFree(h->pesc.err_flag); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch); cudaFree(h->dp_pool.ints); cudaFree(h->dp_pool.bytes); cudaFree(h->d_dpctr); cudaFree(h->d_sw_huge);
     cudaFreeHost(h->h_rows); cudaFreeHost(h->h_pstat); cudaFreeHost(h->h_bam_rows);
-    cudaFree(h->d_multi_out); cudaFree(h->d_multi_list); cudaFree(h->d_multi_ctr);
+    cudaFree(h->d_multi_out); cudaFree(h->d_multi_list); cudaFree(h->d_multi_ctr); cudaFree(h->d_tuples_imp);
     if (h->bam_open) { std::string e; h->bam.close(e); }
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
@@ -624,6 +625,12 @@ static int drain_tuples(fqb_handle *h) {
 // UpdateInfoVecAtMarker's appends in arrival order = (global pair, end, offset on the read), whichever handle saw the pair
 static void build_pileup(fqb_handle *h) {
     std::vector<PileupTuple> &t = h->tuples_host;
+    if (h->n_tuples_imp) {
+        const size_t at = t.size();
+        t.resize(at + h->n_tuples_imp);
+        cudaMemcpy(t.data() + at, h->d_tuples_imp, h->n_tuples_imp * sizeof(PileupTuple), cudaMemcpyDeviceToHost);
+        h->n_tuples_imp = 0;
+    }
     std::sort(t.begin(), t.end(), [](const PileupTuple &a, const PileupTuple &b) {
         if (a.key_hi != b.key_hi) return a.key_hi < b.key_hi;
         return a.key_lo < b.key_lo;
@@ -966,7 +973,7 @@ int fqb_stats_var_count(fqb_handle *h, int which, uint64_t *n) {
         uint32_t nd = 0;
         CU_CHECK(cudaMemcpy(&nd, h->d_ntuples, 4, cudaMemcpyDeviceToHost));
         if (nd > h->tuple_cap) { set_error("pile-up tuple buffer overflow"); return FQB_ERR_LIMIT; }
-        *n = h->tuples_host.size() + nd; return FQB_OK;
+        *n = h->tuples_host.size() + nd + h->n_tuples_imp; return FQB_OK;
     }
     if (which == 1) {
         unsigned long long c = 0;
@@ -983,9 +990,10 @@ int fqb_stats_var_export(fqb_handle *h, int which, void *dst, uint64_t cap) {
     if (n > cap) { set_error("fqb_stats_var_export: destination too small"); return FQB_ERR_ARG; }
     if (!n) return FQB_OK;
     if (which == 0) {
-        const size_t nh = h->tuples_host.size(), nd = (size_t)n - nh;
+        const size_t nh = h->tuples_host.size(), ni = h->n_tuples_imp, nd = (size_t)n - nh - ni;
         if (nh) CU_CHECK(cudaMemcpyAsync(dst, h->tuples_host.data(), nh * sizeof(PileupTuple), cudaMemcpyDefault, h->stream));
         if (nd) CU_CHECK(cudaMemcpyAsync(static_cast<char *>(dst) + nh * sizeof(PileupTuple), h->d_tuples, nd * sizeof(PileupTuple), cudaMemcpyDefault, h->stream));
+        if (ni) CU_CHECK(cudaMemcpyAsync(static_cast<char *>(dst) + (nh + nd) * sizeof(PileupTuple), h->d_tuples_imp, ni * sizeof(PileupTuple), cudaMemcpyDefault, h->stream));
         CU_CHECK(cudaStreamSynchronize(h->stream));
         return FQB_OK;
     }
@@ -1004,10 +1012,19 @@ int fqb_stats_var_import(fqb_handle *h, int which, const void *src, uint64_t n) 
     CU_CHECK(cudaSetDevice(h->device));
     if (!n) return FQB_OK;
     if (which == 0) {
-        const size_t at = h->tuples_host.size();
-        h->tuples_host.resize(at + n);
-        CU_CHECK(cudaMemcpyAsync(h->tuples_host.data() + at, src, n * sizeof(PileupTuple), cudaMemcpyDefault, h->stream));
+        // staged on the device (a device-to-device copy when the source is a gathered NCCL buffer); they reach the host once, in fqb_stats_finish
+        if (h->n_tuples_imp + n > h->cap_tuples_imp) {
+            const size_t cap = (h->n_tuples_imp + n) * 2;
+            PileupTuple *nb = nullptr;
+            CU_CHECK(cudaMalloc(&nb, cap * sizeof(PileupTuple)));
+            if (h->n_tuples_imp) CU_CHECK(cudaMemcpyAsync(nb, h->d_tuples_imp, h->n_tuples_imp * sizeof(PileupTuple), cudaMemcpyDeviceToDevice, h->stream));
+            CU_CHECK(cudaStreamSynchronize(h->stream));
+            cudaFree(h->d_tuples_imp);
+            h->d_tuples_imp = nb; h->cap_tuples_imp = cap;
+        }
+        CU_CHECK(cudaMemcpyAsync(h->d_tuples_imp + h->n_tuples_imp, src, n * sizeof(PileupTuple), cudaMemcpyDefault, h->stream));
         CU_CHECK(cudaStreamSynchronize(h->stream));
+        h->n_tuples_imp += n;
         return FQB_OK;
     }
     if (which != 1) { set_error("bad variable-size group"); return FQB_ERR_ARG; }

@@ -62,8 +62,14 @@ def gather_variable(engine, rank, world, device):
     """
     if world == 1:
         return
+    import os
+    import time
+    verbose = bool(os.environ.get("FQB_BENCH_VERBOSE")) and rank == 0 and device.type == "cuda"
     for which in sorted(VAR_ITEM_BYTES):
+        t0 = time.time()
         mine = engine.var_export(which)
+        if verbose:
+            torch.cuda.synchronize(); t1 = time.time()
         n = torch.tensor([mine.numel()], dtype=torch.int64, device=device)
         sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
         dist.all_gather(sizes, n)
@@ -73,7 +79,13 @@ def gather_variable(engine, rank, world, device):
         buf[: mine.numel()] = mine.to(device)
         out = [torch.zeros(cap, dtype=torch.uint8, device=device) for _ in range(world)] if rank == 0 else None
         dist.gather(buf, out, dst=0)
+        if verbose:
+            torch.cuda.synchronize(); t2 = time.time()
         if rank == 0:
             for r in range(1, world):
                 if sizes[r]:
                     engine.var_import(which, out[r][: sizes[r]])
+        if verbose:
+            torch.cuda.synchronize(); t3 = time.time()
+            print("  var group %d: export %.1f ms, gather %.1f ms (%d bytes max), import %.1f ms" % (
+                which, (t1 - t0) * 1e3, (t2 - t1) * 1e3, cap, (t3 - t2) * 1e3), flush=True)
