@@ -11,6 +11,8 @@ if os.environ.get("FQB_BIG_INDEX") == "10k":      # the BASELINE marker set: 100
 else:
     idx = fx.SynthIndex("small", n_long=40, n_short=160, n_x=5, n_y=5, with_rollhash=True)
 all_cases = {
+    "seed301": (1500000, dict(read_len=100, seed=301, f_on=0.97, sub_rate=0.01, ins_rate=0.0015, del_rate=0.0015, max_indel_len=3)),
+    "se100": (500000, dict(read_len=100, seed=302, sub_rate=0.012, ins_rate=0.002, del_rate=0.002, max_indel_len=3)),
     "err100": (300000, dict(read_len=100, seed=203, sub_rate=0.04, ins_rate=0.01, del_rate=0.01, max_indel_len=4)),
     "off100": (400000, dict(read_len=100, seed=204, f_on=0.3, sub_rate=0.015)),
     "big100": (int(sys.argv[1]) if len(sys.argv) > 1 else 1000000, dict(read_len=100, seed=201, f_on=0.95, sub_rate=0.012, ins_rate=0.002, del_rate=0.002, max_indel_len=3)),
@@ -29,7 +31,7 @@ for name, (n, kw) in cases.items():
     outs = {}
     for tag, exe in (("ref", fx.REF_BIN), ("b200", CLI)):
         out = os.path.join(idx.dir, name + "_" + tag)
-        cmd = [exe, "align", "--fastq_1", fq[0], "--fastq_2", fq[1], "--index_prefix", idx.prefix[:-len(".FASTQuick.fa")], "--out_prefix", out,
+        cmd = [exe, "align", "--fastq_1", fq[0]] + ([] if name.startswith("se") else ["--fastq_2", fq[1]]) + ["--index_prefix", idx.prefix[:-len(".FASTQuick.fa")], "--out_prefix", out,
                "--t", str(os.cpu_count() or 4), "--q", "15"]
         t1 = time.time()
         r = subprocess.run(cmd, cwd=idx.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
