@@ -248,8 +248,11 @@ std::string md_string(const HostIndex &I, const fqb_read_t &s, const uint16_t *c
 }
 
 // mate_ptr == nullptr: single-end input (SetSamRecord(..., mate = 0, ...))
+// rseq: what the reference's p->rseq buffer holds for this read slot (nt4 codes, full_len bytes): the reverse complement of
+// the trimmed read followed by whatever an earlier occupant of the slot left there (nullptr = zeros, the single-end reader
+// callocs the buffer per read).  Only SetSamRecord's "no match" branch looks at it.
 void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t *mate_ptr, const char *name, const uint8_t *bases, const uint8_t *quals,
-                const XaHit *xa, int n_xa, std::string &out) {
+                const XaHit *xa, int n_xa, const uint8_t *rseq, std::string &out) {
     fqb_read_t absent;
     memset(&absent, 0, sizeof absent);
     const bool has_mate = mate_ptr != nullptr;
@@ -265,7 +268,9 @@ void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t *mate_ptr, 
         std::string seq((size_t)L, 'N'), qual((size_t)L, '\0'), tags;
         for (int k = 0; k < L; ++k) {
             if (!p.strand) { const uint8_t c = t[bases[k]]; seq[k] = "ACGTN"[c > 4 ? 4 : c]; }
-            else { const uint8_t c = t[bases[L - 1 - k]]; seq[k] = "TGCAN"[c > 4 ? 4 : c]; }
+            else if (rseq) { const uint8_t c = rseq[k]; seq[k] = "ACGTN"[c > 4 ? 4 : c]; }       // s = p->rseq, printed over the FULL length
+            else if (k < p.clip_len) { const uint8_t c = t[bases[p.clip_len - 1 - k]]; seq[k] = "TGCAN"[c > 4 ? 4 : c]; }
+            else seq[k] = 'A';                                                                   // calloc'ed tail of the single-end reader
             qual[k] = (char)((p.strand ? quals[L - 1 - k] : quals[k]) - 33);
         }
         if (!C.rg_id.empty()) tag_str(tags, "RG", C.rg_id);
@@ -394,14 +399,15 @@ void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t *mate_ptr, 
 }  // namespace
 
 void bam_append_pair(const BamContext &C, fqb_read_t p, fqb_read_t q, const char *name, const uint8_t *bases_p, const uint8_t *quals_p,
-                     const uint8_t *bases_q, const uint8_t *quals_q, const XaHit *xa_p, int n_xa_p, const XaHit *xa_q, int n_xa_q, std::string &out) {
-    one_record(C, p, &q, name, bases_p, quals_p, xa_p, n_xa_p, out);       // may rewrite p's pos/strand (unmapped read of a half-mapped pair)
-    one_record(C, q, &p, name, bases_q, quals_q, xa_q, n_xa_q, out);
+                     const uint8_t *bases_q, const uint8_t *quals_q, const XaHit *xa_p, int n_xa_p, const XaHit *xa_q, int n_xa_q,
+                     const uint8_t *rseq_p, const uint8_t *rseq_q, std::string &out) {
+    one_record(C, p, &q, name, bases_p, quals_p, xa_p, n_xa_p, rseq_p, out);       // may rewrite p's pos/strand (unmapped read of a half-mapped pair)
+    one_record(C, q, &p, name, bases_q, quals_q, xa_q, n_xa_q, rseq_q, out);
 }
 
 void bam_append_single(const BamContext &C, fqb_read_t p, const char *name, const uint8_t *bases, const uint8_t *quals, const XaHit *xa, int n_xa,
                        std::string &out) {
-    one_record(C, p, nullptr, name, bases, quals, xa, n_xa, out);
+    one_record(C, p, nullptr, name, bases, quals, xa, n_xa, nullptr, out);
 }
 
 }  // namespace fqb

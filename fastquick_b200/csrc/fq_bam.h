@@ -53,7 +53,8 @@ bool bam_prepare(const HostIndex &idx, const fqb_gap_opt_t &g, const std::vector
 // bases/quals: the reads as they came from the FASTQ files (ASCII), full_len bytes each.
 void bam_append_pair(const BamContext &ctx, fqb_read_t p, fqb_read_t q, const char *name, const uint8_t *bases_p, const uint8_t *quals_p,
                      const uint8_t *bases_q, const uint8_t *quals_q, const XaHit *xa_p, int n_xa_p, const XaHit *xa_q, int n_xa_q,
-                     std::string &out);
+                     const uint8_t *rseq_p, const uint8_t *rseq_q, std::string &out);
+// rseq_p / rseq_q: the slot's p->rseq buffer as the reference's paired reader leaves it (see fqb_bam_emit), or nullptr
 
 // Single-end input: the record SetSamRecord(bns, p, 0, ...) builds (SingleEndMapper, src/BwtMapper.cpp:1384-1388)
 void bam_append_single(const BamContext &ctx, fqb_read_t p, const char *name, const uint8_t *bases, const uint8_t *quals, const XaHit *xa, int n_xa,

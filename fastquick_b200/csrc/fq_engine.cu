@@ -137,6 +137,9 @@ struct fqb_handle {
     BgzfWriter bam; bool bam_open = false; BamContext bam_ctx;
     MultiOut *d_multi_out = nullptr; uint32_t *d_multi_list = nullptr, *d_multi_ctr = nullptr; uint32_t multi_cap = 0;
     fqb_read_t *h_bam_rows = nullptr; size_t h_bam_rows_cap = 0;
+    // the reference's paired reader reuses its per-slot rseq buffers every second batch without clearing them, and SetSamRecord's
+    // "no match" branch prints such a buffer over the full read length: [parity of the batch][end][slot * stride]
+    std::vector<uint8_t> rseq_shadow[2][2]; size_t rseq_stride = 0; uint64_t bam_batches = 0;
     std::ofstream isize_table;
     std::string isize_table_path;
     std::vector<std::pair<uint64_t, uint64_t>> isize_table_idx;   // (first global pair, bytes) of every emitted batch, in emission order
@@ -713,6 +716,8 @@ int fqb_stats_begin_file(fqb_handle *h, const char *out_prefix, const char *fq1,
         h->isize_table_idx.clear();
         if (!h->isize_table) { set_error("cannot write the InsertSizeTable"); return FQB_ERR_IO; }
     }
+    for (auto &a : h->rseq_shadow) for (auto &b : a) std::fill(b.begin(), b.end(), 0);      // PairEndMapper allocates fresh read buffers per file
+    h->bam_batches = 0;
     FileCounters f;
     f.FileName1 = fq1 ? fq1 : ""; f.FileName2 = fq2 ? fq2 : "";
     h->files.push_back(f);
@@ -1263,14 +1268,33 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
     if (nthr > 16) nthr = 16;
     if (np < 4096) nthr = 1;
     std::vector<std::string> parts(nthr);
+    const int par = (int)(h->bam_batches & 1);
+    if (!h->single_end) {
+        if (h->rseq_stride != (size_t)stride) { for (auto &a : h->rseq_shadow) for (auto &b : a) b.clear(); h->rseq_stride = (size_t)stride; }
+        for (int e = 0; e < 2; ++e) if (h->rseq_shadow[par][e].size() < (size_t)(FQB_BATCH_PAIRS > np ? FQB_BATCH_PAIRS : np) * stride)
+            h->rseq_shadow[par][e].resize((size_t)(FQB_BATCH_PAIRS > np ? FQB_BATCH_PAIRS : np) * stride, 0);
+    }
+    ++h->bam_batches;
     auto work = [&](unsigned t) {
         std::string &o = parts[t];
         const size_t lo = np * t / nthr, hi = np * (t + 1) / nthr;
         o.reserve((hi - lo) * 2 * (size_t)(160 + 3 * stride / 2));
         char buf[64];
         std::string nm;
+        const uint8_t *nt4 = nt4_table();
         for (size_t i = lo; i < hi; ++i) {
             const fqb_read_t &p = h->h_bam_rows[2 * i], &q = h->h_bam_rows[2 * i + 1];
+            const uint8_t *rs[2] = {nullptr, nullptr};
+            if (!h->single_end) {                      // what bwa_read_seq_with_hash_dev / expand_seq wrote into the slot's rseq
+                const fqb_read_t *rw[2] = {&p, &q};
+                const uint8_t *bs[2] = {bases1 + i * (size_t)stride, bases2 + i * (size_t)stride};
+                for (int e = 0; e < 2; ++e) {
+                    uint8_t *dst = h->rseq_shadow[par][e].data() + i * (size_t)stride;
+                    if (!rw[e]->filtered)
+                        for (int k = 0; k < rw[e]->clip_len; ++k) { const uint8_t c = nt4[bs[e][rw[e]->clip_len - 1 - k]]; dst[k] = c < 4 ? (uint8_t)(3 - c) : (uint8_t)4; }
+                    rs[e] = dst;
+                }
+            }
             // skip decisions use the types the reads had before AddAlignment's bridge check (kept in the pair record)
             if (have_ps ? (h->h_pstat[i].both_filtered || h->h_pstat[i].both_unmapped)
                         : ((p.filtered && q.filtered) || (p.type == kTypeNoMatch && q.type == kTypeNoMatch))) continue;
@@ -1281,7 +1305,7 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
             const XaHit *x0 = p.n_multi ? xa_of((uint32_t)(2 * i), n0) : nullptr, *x1 = q.n_multi ? xa_of((uint32_t)(2 * i + 1), n1) : nullptr;
             if (h->single_end) bam_append_single(h->bam_ctx, p, name, bases1 + i * (size_t)stride, quals1 + i * (size_t)stride, x0, n0, o);
             else bam_append_pair(h->bam_ctx, p, q, name, bases1 + i * (size_t)stride, quals1 + i * (size_t)stride, bases2 + i * (size_t)stride,
-                                 quals2 + i * (size_t)stride, x0, n0, x1, n1, o);
+                                 quals2 + i * (size_t)stride, x0, n0, x1, n1, rs[0], rs[1], o);
         }
     };
     if (nthr == 1) work(0);
