@@ -80,6 +80,15 @@ int fqb_synth_write_index(const fqb_synth *s, const char *genome_path, const cha
     if (!fqb::synth_write_index_side_files(s->ref, genome_path, dbsnp_path, prefix, err)) { fqb::set_error(err); return FQB_ERR_IO; }
     return FQB_OK;
 }
+int fqb_index_from_flank_fasta(const char *flank_fasta, const char *prefix, int with_rollhash) {
+    std::string err;
+    std::vector<fqb::FlankSeq> flanks;
+    if (!fqb::read_flank_fasta(flank_fasta, flanks, err)) { fqb::set_error(err); return FQB_ERR_IO; }
+    fqb::HostIndex idx;
+    fqb::build_index_from_flanks(flanks, with_rollhash != 0, idx);
+    if (!fqb::dump_index(idx, prefix, err)) { fqb::set_error(err); return FQB_ERR_IO; }
+    return FQB_OK;
+}
 int fqb_synth_reads(const fqb_synth *s, const fqb_synth_read_cfg_t *c, int64_t first_pair, int64_t n_pairs,
                     uint8_t *b1, uint8_t *q1, uint8_t *b2, uint8_t *q2, int n_threads) {
     if (!s || !c || c->read_len < 35 || c->read_len > FQB_MAX_READ_LEN) { fqb::set_error("bad read config"); return FQB_ERR_ARG; }

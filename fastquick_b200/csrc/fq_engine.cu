@@ -14,6 +14,7 @@
 #include "fq_hostmath.h"
 #include "fq_index.h"
 #include "fq_kernels.cuh"
+#include "fq_kmer.cuh"
 #include "fq_pair_kernels.cuh"
 #include "fq_dp_kernels.cuh"
 #include "fq_stats_kernels.cuh"
@@ -58,6 +59,7 @@ struct fqb_handle {
     uint4 *d_blocks[2] = {nullptr, nullptr};
     uint32_t *d_sa[2] = {nullptr, nullptr};
     uint8_t *d_pac = nullptr, *d_roll = nullptr;
+    int kmer_origin = 0;      // 0 no tables (kmer_thresh == 0), 1 built on the device, 2 uploaded from memory, 3 streamed from <prefix>.rollhash
     DevBwt dbwt[2];
     int32_t *d_maxdiff = nullptr;
     int32_t h_maxdiff[FQB_MAX_READ_LEN + 1];
@@ -235,7 +237,7 @@ int fqb_create_from_synth(const fqb_synth *s, const fqb_gap_opt_t *gopt, const f
     fqb_handle *h = new fqb_handle();
     if (gopt) h->gopt = *gopt; else fqb_gap_opt_default(&h->gopt);
     if (popt) h->popt = *popt; else fqb_pe_opt_default(&h->popt);
-    build_index_from_flanks(fqb_synth_flanks_internal(s), h->gopt.kmer_thresh != 0, h->hidx);
+    build_index_from_flanks(fqb_synth_flanks_internal(s), h->gopt.kmer_thresh != 0 && getenv("FQB_ROLLHASH_FROM_FILE"), h->hidx);
     return create_common(h, device, out);
 }
 
@@ -297,13 +299,43 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     CU_CHECK_H(cudaMalloc(&h->d_dpctr, 12 * 4));
     CU_CHECK_H(cudaMalloc(&h->d_counters, 16 * 8));
     CU_CHECK_H(cudaMemset(h->d_counters, 0, 16 * 8));
-    if (h->gopt.kmer_thresh != 0) {     // 6 x 512 MiB bitmaps, streamed from disk (BwtIndexer::ReadRollHashTable)
+    if (h->gopt.kmer_thresh != 0) {     // 6 x 512 MiB membership tables (BwtIndexer::roll_hash_table)
         const size_t total = kRollTableBytes * kNumRollTables;
         CU_CHECK_H(cudaMalloc(&h->d_roll, total));
+        KmerBuildInputs kin;
         if (h->hidx.rollhash.size() == total) {
             CU_CHECK_H(cudaMemcpy(h->d_roll, h->hidx.rollhash.data(), total, cudaMemcpyHostToDevice));
             std::vector<uint8_t>().swap(h->hidx.rollhash);
-        } else {
+            h->kmer_origin = 2;
+        } else if (!getenv("FQB_ROLLHASH_FROM_FILE") && kmer_build_inputs(h->hidx, kin)) {
+            // built here from the flank text (row f4): same bits as <prefix>.rollhash, without the 3 GiB read
+            const size_t nj = kin.special.size();
+            std::vector<int64_t> jf(nj), jl(nj); std::vector<int32_t> jn(nj), jt(nj);
+            for (size_t j = 0; j < nj; ++j) { jf[j] = kin.special[j].first; jl[j] = kin.special[j].last; jn[j] = kin.special[j].len; jt[j] = kin.special[j].table; }
+            uint8_t *d_codes = nullptr, *d_alleles = nullptr, *d_sp = nullptr; int64_t *d_off = nullptr, *d_jf = nullptr, *d_jl = nullptr; int32_t *d_jn = nullptr, *d_jt = nullptr;
+            auto up = [&](auto **dst, const void *src, size_t bytes) -> cudaError_t {
+                cudaError_t e = cudaMalloc((void **)dst, bytes + 64);
+                return e != cudaSuccess ? e : cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+            };
+            CU_CHECK_H(up(&d_codes, kin.codes.data(), kin.codes.size()));
+            CU_CHECK_H(up(&d_alleles, kin.alleles.data(), kin.alleles.size()));
+            CU_CHECK_H(up(&d_off, kin.offsets.data(), kin.offsets.size() * 8));
+            CU_CHECK_H(up(&d_sp, kin.special_codes.data(), kin.special_codes.size()));
+            CU_CHECK_H(up(&d_jf, jf.data(), nj * 8)); CU_CHECK_H(up(&d_jl, jl.data(), nj * 8));
+            CU_CHECK_H(up(&d_jn, jn.data(), nj * 4)); CU_CHECK_H(up(&d_jt, jt.data(), nj * 4));
+            CU_CHECK_H(cudaMemsetAsync(h->d_roll, 0, total, h->stream));
+            KmerBuildView kv;
+            kv.codes = d_codes; kv.offset = d_off; kv.alleles = d_alleles; kv.n_flanks = (int)h->hidx.contigs.size();
+            kv.n_bases = h->hidx.l_pac; kv.tables = reinterpret_cast<uint32_t *>(h->d_roll);
+            launch_kmer_build(kv, h->stream);
+            KmerSpecialView sv;
+            sv.codes = d_sp; sv.first = d_jf; sv.last = d_jl; sv.len = d_jn; sv.table = d_jt; sv.n_jobs = (int)nj; sv.tables = kv.tables;
+            launch_kmer_build_special(sv, h->stream);
+            CU_CHECK_H(cudaGetLastError());
+            CU_CHECK_H(cudaStreamSynchronize(h->stream));
+            cudaFree(d_codes); cudaFree(d_alleles); cudaFree(d_off); cudaFree(d_sp); cudaFree(d_jf); cudaFree(d_jl); cudaFree(d_jn); cudaFree(d_jt);
+            h->kmer_origin = 1;
+        } else {                        // streamed from disk (BwtIndexer::ReadRollHashTable)
             FILE *fp = fopen(h->hidx.rollhash_path.c_str(), "rb");
             if (!fp) { set_error("cannot open " + h->hidx.rollhash_path); fqb_destroy(h); return FQB_ERR_IO; }
             const size_t chunk = 64u << 20;
@@ -316,9 +348,22 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
                 done += want;
             }
             fclose(fp);
+            h->kmer_origin = 3;
         }
     }
     *out = h;
+    return FQB_OK;
+}
+
+int fqb_kmer_tables_origin(const fqb_handle *h) { return h ? h->kmer_origin : 0; }
+
+int fqb_kmer_tables_fetch(fqb_handle *h, uint64_t offset, uint64_t n_bytes, uint8_t *out) {
+    if (!h || !out) { set_error("null argument"); return FQB_ERR_ARG; }
+    if (!h->d_roll) { set_error("no k-mer tables (kmer_thresh == 0)"); return FQB_ERR_ARG; }
+    if (offset + n_bytes > kRollTableBytes * kNumRollTables) { set_error("range outside the k-mer tables"); return FQB_ERR_ARG; }
+    cudaSetDevice(h->device);
+    cudaError_t e = cudaMemcpy(out, h->d_roll + offset, n_bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error(std::string("cudaMemcpy: ") + cudaGetErrorString(e)); return FQB_ERR_CUDA; }
     return FQB_OK;
 }
 

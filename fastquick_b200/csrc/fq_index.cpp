@@ -141,35 +141,110 @@ static inline uint32_t shrink(uint64_t kmer, int which) {
     }
 }
 
-// Same k-mer enumeration as BwtIndexer::AddSeq2HashCore (src/BwtIndexer.cpp:611-713):
-// every 32-mer of the flank, with the centre base replaced by each allele for the
-// 32 windows that cover it; after the allele loop the rolling value continues from
-// the LAST allele's window.  Codes are nt4 (N = 4 bleeds into the neighbour bits).
+// Same k-mer enumeration as BwtIndexer::AddSeq2HashCore (src/BwtIndexer.cpp:611-713), once per table as AddSeq2Hash
+// (src/BwtIndexer.h:317-323) calls it: every 32-mer of the flank, with the centre base replaced by each allele for the
+// 32 windows that cover it; after the allele loop the rolling value continues from the LAST allele's window.
+// NST_NT4_TABLE (src/BwtIndexer.cpp:59-61) turns every code >= 4 into rand() % 4, drawn afresh at each visit, from
+// glibc's never-seeded rand() stream (the caller calls srand(1) so the fixture is reproducible within a process).
 static void add_seq_kmers(const std::string &s, const char alleles[2], uint8_t *tables) {
     const size_t n = s.size(), half = n / 2;
     if (n < 32) return;
-    auto setbits = [&](uint64_t kmer) {
-        for (int t = 0; t < kNumRollTables; ++t) {
+    auto code = [](char ch) -> uint64_t { const uint8_t c = g_nt4[(uint8_t)ch]; return c < 4 ? c : (uint64_t)(rand() % 4); };
+    for (int t = 0; t < kNumRollTables; ++t) {
+        auto setbit = [&](uint64_t kmer) {
             uint32_t x = shrink(kmer, t);
             tables[(uint64_t)t * kRollTableBytes + (x >> 3)] |= (uint8_t)(1u << (x & 7));
+        };
+        uint64_t datum = 0;
+        size_t i = 0;
+        for (; i < 32; ++i) datum = (datum << 2) | code(s[i]);
+        setbit(datum);
+        for (; i < half; ++i) { datum = (datum << 2) | code(s[i]); setbit(datum); }
+        uint64_t tmp = datum;
+        for (int a = 0; a < 2; ++a) {
+            tmp = datum;
+            for (size_t j = i; j < half + 32 && j < n + 32; ++j) {
+                tmp = (tmp << 2) | code(j == half ? alleles[a] : s[j]);
+                setbit(tmp);
+            }
         }
-    };
-    uint64_t datum = 0;
-    size_t i = 0;
-    for (; i < 32; ++i) datum = (datum << 2) | g_nt4[(uint8_t)s[i]];
-    setbits(datum);
-    for (; i < half; ++i) { datum = (datum << 2) | g_nt4[(uint8_t)s[i]]; setbits(datum); }
-    uint64_t tmp = datum;
-    for (int a = 0; a < 2; ++a) {
-        tmp = datum;
-        for (size_t j = i; j < half + 32 && j < n + 32; ++j) {
-            uint8_t c = (j == half) ? g_nt4[(uint8_t)alleles[a]] : g_nt4[(uint8_t)s[j]];
-            tmp = (tmp << 2) | c;
-            setbits(tmp);
+        datum = tmp;
+        for (i = half + 32; i < n; ++i) { datum = (datum << 2) | code(s[i]); setbit(datum); }
+    }
+}
+
+namespace {
+// glibc's rand() (random_r TYPE_3: r[i] = r[i-3] + r[i-31], output >> 1) from its default state srand(1), kept local so the
+// library never touches the process-wide generator
+struct GlibcRand {
+    std::vector<uint32_t> hist;
+    GlibcRand() {
+        hist.resize(344);
+        int32_t x = 1;
+        hist[0] = 1;
+        for (int i = 1; i < 31; ++i) {
+            int64_t v = (16807LL * x) % 2147483647LL;
+            if (v < 0) v += 2147483647LL;
+            x = (int32_t)v; hist[i] = (uint32_t)x;
+        }
+        for (int i = 31; i < 34; ++i) hist[i] = hist[i - 31];
+        for (int i = 34; i < 344; ++i) hist[i] = hist[i - 31] + hist[i - 3];
+    }
+    uint32_t next() {
+        const size_t k = hist.size();
+        hist.push_back(hist[k - 31] + hist[k - 3]);
+        return hist.back() >> 1;
+    }
+};
+}  // namespace
+
+bool kmer_build_inputs(const HostIndex &idx, KmerBuildInputs &o) {
+    o = KmerBuildInputs();
+    for (const Contig &c : idx.contigs) {
+        const size_t at = c.name.find('@');
+        if (at == std::string::npos || at + 3 >= c.name.size() || c.len < 65) return false;
+        o.offsets.push_back(c.offset);
+        o.alleles.push_back(g_nt4[(uint8_t)c.name[at + 1]]);
+        o.alleles.push_back(g_nt4[(uint8_t)c.name[at + 3]]);
+    }
+    o.offsets.push_back(idx.l_pac);
+    o.codes.resize((size_t)idx.l_pac);
+    for (int64_t i = 0; i < idx.l_pac; ++i) o.codes[i] = (idx.pac[i >> 2] >> ((3 - (i & 3)) << 1)) & 3;
+    for (const Hole &h : idx.holes)
+        for (int64_t i = 0; i < h.len; ++i) o.codes[h.offset + i] = g_nt4[(uint8_t)h.amb];
+    GlibcRand rng;
+    for (size_t f = 0; f < idx.contigs.size(); ++f) {                    // flank order == the order Fa2Pac hashes them in
+        const int64_t off = o.offsets[f];
+        const int n = (int)(o.offsets[f + 1] - off), half = n / 2;
+        bool special = o.alleles[2 * f] >= 4 || o.alleles[2 * f + 1] >= 4;
+        for (int i = 0; i < n && !special; ++i) special = o.codes[off + i] >= 4;
+        if (!special) continue;
+        o.alleles[2 * f] |= 0x80;
+        std::vector<uint8_t> str(n);
+        for (int strand = 0; strand < 2; ++strand) {
+            for (int i = 0; i < n; ++i) {
+                const uint8_t c = strand ? o.codes[off + n - 1 - i] : o.codes[off + i];
+                str[i] = strand ? (c < 4 ? (uint8_t)(3 - c) : (uint8_t)4) : c;     // ReverseComplement: anything else -> '\0' -> code 4
+            }
+            for (int t = 0; t < kNumRollTables; ++t) {
+                auto draw = [&](uint8_t c) -> uint8_t { return c < 4 ? c : (uint8_t)(rng.next() % 4); };
+                KmerSpecialJob job;
+                job.len = n; job.table = t;
+                job.first = (int64_t)o.special_codes.size();
+                o.special_codes.resize(o.special_codes.size() + 2 * (size_t)n);
+                job.last = job.first + n;
+                uint8_t *c0 = o.special_codes.data() + job.first, *c1 = o.special_codes.data() + job.last;
+                for (int i = 0; i < half; ++i) c0[i] = c1[i] = draw(str[i]);
+                for (int a = 0; a < 2; ++a) {
+                    uint8_t *ca = a ? c1 : c0;
+                    for (int j = half; j < half + 32; ++j) ca[j] = draw(j == half ? (uint8_t)(o.alleles[2 * f + a] & 0x7f) : str[j]);
+                }
+                for (int i = half + 32; i < n; ++i) c0[i] = c1[i] = draw(str[i]);
+                o.special.push_back(job);
+            }
         }
     }
-    datum = tmp;
-    for (i = half + 32; i < n; ++i) { datum = (datum << 2) | g_nt4[(uint8_t)s[i]]; setbits(datum); }
+    return true;
 }
 
 static std::string revcomp_ascii(const std::string &s) {
@@ -261,6 +336,7 @@ void build_index_from_flanks(const std::vector<FlankSeq> &flanks, bool with_roll
     idx = HostIndex();
     idx.seed = 11;                                      // src/BwtIndexer.cpp:849
     srand48(idx.seed);
+    srand(1);                                           // the state a fresh process's rand() starts in (see add_seq_kmers)
     std::vector<uint8_t> T;
     if (with_rollhash) idx.rollhash.assign(kRollTableBytes * kNumRollTables, 0);
     for (const FlankSeq &f : flanks) {

@@ -47,6 +47,20 @@ struct HostIndex {
 bool load_bwt(const std::string &bwt_path, const std::string &sa_path, HostBwt &out, std::string &err);
 bool load_index(const std::string &prefix, bool with_rollhash_in_memory, HostIndex &out, std::string &err);
 
+// Inputs of the device-side k-mer table build (fq_kmer_build.cu): the flank text as nt4 codes (.pac with the .amb holes put
+// back), flank boundaries, and the two allele characters after '@' in each flank name (src/BwtIndexer.cpp:873-875).
+// A flank holding an ambiguous base (or an allele character outside ACGT) is flagged 0x80 in alleles[2 f] and listed in
+// `special` instead: there the reference substitutes rand() % 4 at every visit (NST_NT4_TABLE, src/BwtIndexer.cpp:59-61), so
+// each of its 2 strands x 6 tables walks its own string; the draws are reproduced here on the host, in the reference's order.
+// false = a flank name has no "@x/y" part or a flank is shorter than 65 bases (the reference's loops assume neither).
+struct KmerSpecialJob { int64_t first, last; int32_t len, table; };   // offsets into `special_codes` of the two allele passes' strings
+struct KmerBuildInputs {
+    std::vector<uint8_t> codes, alleles, special_codes;
+    std::vector<int64_t> offsets;
+    std::vector<KmerSpecialJob> special;
+};
+bool kmer_build_inputs(const HostIndex &idx, KmerBuildInputs &out);
+
 // nst_nt4_table semantics (libbwa/bntseq.c:38-55): A0 C1 G2 T3, '-' 5, else 4.
 const uint8_t *nt4_table();
 

@@ -10,6 +10,8 @@
 #include <climits>
 #include "../../include/fastquick_b200.h"
 
+#include "fq_kmer.cuh"
+
 namespace fqb {
 
 #define FULL_MASK 0xffffffffu
@@ -24,19 +26,6 @@ __device__ __forceinline__ uint32_t nt4_code(uint32_t ch) {
     c = (u == 'T') ? 3u : c;
     c = (ch == '-') ? 5u : c;
     return c;
-}
-
-// KmerShrinkage cases 0..5 (src/BwtIndexer.h:262-315)
-__device__ __forceinline__ uint32_t shrink_kmer(uint64_t kmer, int which) {
-    uint32_t hi = (uint32_t)(kmer >> 32), lo = (uint32_t)kmer;
-    switch (which) {
-    case 0: return hi;
-    case 1: return lo;
-    case 2: return (hi & 0xffff0000u) | (lo & 0xffffu);
-    case 3: return (uint32_t)(kmer >> 16);
-    case 4: return (hi & 0xffff0000u) | (lo >> 16);
-    default: return (hi << 16) | (lo & 0xffffu);
-    }
 }
 
 __global__ void __launch_bounds__(256) prep_kernel(BatchView b, PrepParams p) {

@@ -24,7 +24,7 @@ bool BwtIndexer::LoadIndex(std::string &NewRef) {
     if (!par) error("Open %s failed!", (NewRef + ".param").c_str());
     std::string k;
     par >> k >> RefPath;
-    for (const char *ext : {".bwt", ".rbwt", ".sa", ".rsa", ".pac", ".ann", ".amb", ".rollhash"})
+    for (const char *ext : {".bwt", ".rbwt", ".sa", ".rsa", ".pac", ".ann", ".amb"})       // .rollhash is rebuilt on the device
         if (!std::ifstream(NewRef + ext)) error("Open %s failed!", (NewRef + ext).c_str());
     return true;
 }

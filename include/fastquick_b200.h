@@ -90,10 +90,18 @@ typedef struct fqb_handle fqb_handle;
 
 /* ---- index ------------------------------------------------------------ */
 /* Replaces BwtIndexer::LoadIndex (src/BwtIndexer.cpp:803-837): reads
- * <prefix>.{bwt,rbwt,sa,rsa,pac,ann,amb,rollhash} unchanged and uploads the
- * re-laid tables to `device` (CUDA ordinal). */
+ * <prefix>.{bwt,rbwt,sa,rsa,pac,ann,amb} unchanged and uploads the re-laid tables to `device`
+ * (CUDA ordinal).  The k-mer tables of ReadRollHashTable (src/BwtIndexer.cpp:569-579, 3 GiB in
+ * <prefix>.rollhash) are rebuilt on the device from the flank text, bit for bit what
+ * AddSeq2HashCore (611-713) produced; the file is only read when a flank name carries no "@x/y"
+ * alleles or FQB_ROLLHASH_FROM_FILE is set in the environment. */
 int fqb_create(const char *index_prefix, const fqb_gap_opt_t *gopt, const fqb_pe_opt_t *popt,
                int device, fqb_handle **out);
+/* where the k-mer tables came from: 0 none (kmer_thresh == 0), 1 built on the device,
+ * 2 uploaded from memory, 3 streamed from <prefix>.rollhash */
+int fqb_kmer_tables_origin(const fqb_handle *h);
+/* bytes [offset, offset + n_bytes) of the 6 x 2^29-byte tables, in .rollhash file order (tests) */
+int fqb_kmer_tables_fetch(fqb_handle *h, uint64_t offset, uint64_t n_bytes, uint8_t *out);
 void fqb_destroy(fqb_handle *h);
 const char *fqb_last_error(void);
 
@@ -236,6 +244,9 @@ int fqb_synth_write_inputs(const fqb_synth *s, const char *dir);
 /* <prefix> = "<out_prefix>.FASTQuick.fa": all files BwtIndexer::BuildIndex + runIndex would leave */
 int fqb_synth_write_index(const fqb_synth *s, const char *genome_path, const char *dbsnp_path,
                           const char *prefix, int with_rollhash);
+/* fixture side: the BwtIndexer::BuildIndex files for an arbitrary flank FASTA (">chr:pos@R/A" names, one line per
+ * sequence, as <prefix> itself is laid out); used to test flanks with N, lower case and '-' */
+int fqb_index_from_flank_fasta(const char *flank_fasta, const char *prefix, int with_rollhash);
 /* engine over the synthetic index built in memory (no files written) */
 int fqb_create_from_synth(const fqb_synth *s, const fqb_gap_opt_t *gopt, const fqb_pe_opt_t *popt,
                           int device, fqb_handle **out);
