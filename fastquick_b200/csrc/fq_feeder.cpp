@@ -1,0 +1,433 @@
+// Host feeder: FASTQ text -> fixed-stride batches in pinned memory, decoded in parallel.
+// Replaces the reference's reader for this path: kseq_read3_fpc (libbwa/kseq.h:327-370) called record by record from
+// bwa_read_seq_with_hash_dev (src/BwtMapper.cpp:476-613) on the two IO workers of PairEndMapper (:1969-1982).
+//
+//   producer thread   file -> text blocks of ~4 MiB, in order.  Three sources:
+//                       BGZF (bgzip / bcl2fastq output: gzip members <= 64 KiB that carry their own size) - members
+//                            are inflated independently by the worker pool, 64 at a time;
+//                       any other gzip stream - one zlib inflate() stream (inherently serial), multi-member aware;
+//                       plain text.
+//   fill()            walks the blocks, finds the record boundaries (memchr), cuts the text into runs of whole records
+//                     and hands each run to the worker pool together with the batch slot of its first record;
+//                     a record cut by a block boundary is stitched and parsed inline.
+//   worker pool       parses runs into the batch: bases, qualities, lengths, names (what the GPU prep kernel and the
+//                     writers consume); shared by all open feeders.
+// The nt4 encoding, trimming and the k-mer filter of bwa_read_seq_with_hash_dev stay on the GPU (prep_kernel).
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/fastquick_b200.h"
+#include "fq_common.h"
+
+namespace fqb {
+namespace {
+
+constexpr size_t kBlockBytes = (size_t)4 << 20;
+constexpr int kRunRecords = 4096;          // records per parse job
+constexpr int kQueueDepth = 8;             // text blocks buffered ahead of fill()
+constexpr int kBgzfGroup = 64;             // BGZF members per inflate job
+constexpr int kBgzfWindow = 12;            // inflate jobs in flight
+
+class WorkPool {
+public:
+    explicit WorkPool(unsigned n) {
+        for (unsigned i = 0; i < n; ++i) th_.emplace_back([this]() { run(); });
+    }
+    ~WorkPool() {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    void submit(std::function<void()> f) {
+        { std::lock_guard<std::mutex> l(m_); q_.push_back(std::move(f)); }
+        cv_.notify_one();
+    }
+    unsigned size() const { return (unsigned)th_.size(); }
+private:
+    void run() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&]() { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                f = std::move(q_.front()); q_.pop_front();
+            }
+            f();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_; std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+    bool stop_ = false;
+};
+
+WorkPool &pool(int n_threads) {
+    static std::mutex m;
+    static std::unique_ptr<WorkPool> p;
+    std::lock_guard<std::mutex> l(m);
+    const unsigned want = n_threads > 0 ? (unsigned)n_threads : std::min(16u, std::max(2u, std::thread::hardware_concurrency()));
+    if (!p) p.reset(new WorkPool(want));                         // sized by the first feeder, shared by all later ones
+    return *p;
+}
+
+struct Latch {
+    std::mutex m; std::condition_variable cv; int pending = 0;
+    void add() { std::lock_guard<std::mutex> l(m); ++pending; }
+    void done() { std::lock_guard<std::mutex> l(m); if (--pending == 0) cv.notify_all(); }
+    void wait() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&]() { return pending == 0; }); }
+};
+
+struct Block { std::vector<char> text; size_t n = 0; };
+using BlockPtr = std::shared_ptr<Block>;
+
+struct Batch {
+    int stride, name_stride;
+    uint8_t *bases, *quals; int32_t *lens; char *names;
+};
+
+// first failure of any job of this feeder; reported by fill()
+struct Failure {
+    std::mutex m; std::string msg; std::atomic<bool> set{false};
+    void raise(const std::string &s) { std::lock_guard<std::mutex> l(m); if (!set.load()) { msg = s; set.store(true); } }
+};
+
+inline const char *line_end(const char *p, const char *end) {
+    const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+    return nl ? nl : end;
+}
+
+// one record whose four lines are [p, end): header, bases, '+', qualities (kseq's contract: name up to the first blank,
+// a trailing /1 or /2 removed as bwa_read_seq_with_hash_dev does, src/BwtMapper.cpp:598-603)
+bool parse_record(const char *p, const char *end, const Batch &B, int slot, Failure &fail, const char **next) {
+    const char *l[4], *e[4];
+    for (int k = 0; k < 4; ++k) {
+        l[k] = p;
+        const char *nl = line_end(p, end);
+        e[k] = (nl > p && nl[-1] == '\r') ? nl - 1 : nl;
+        p = nl < end ? nl + 1 : end;
+    }
+    *next = p;
+    if (l[0] == e[0] || l[0][0] != '@') { fail.raise("malformed FASTQ record: header line does not start with '@'"); return false; }
+    const size_t sl = (size_t)(e[1] - l[1]);
+    if ((int)sl > B.stride) { fail.raise("read longer than " + std::to_string(B.stride) + " bases: not supported"); return false; }
+    if ((size_t)(e[3] - l[3]) != sl) { fail.raise("sequence and quality lengths differ in a FASTQ record"); return false; }
+    uint8_t *b = B.bases + (size_t)slot * B.stride, *q = B.quals + (size_t)slot * B.stride;
+    memcpy(b, l[1], sl); memset(b + sl, 'N', (size_t)B.stride - sl);
+    memcpy(q, l[3], sl); memset(q + sl, '!', (size_t)B.stride - sl);
+    B.lens[slot] = (int32_t)sl;
+    const char *nb = l[0] + 1, *ne = nb;
+    while (ne < e[0] && *ne != ' ' && *ne != '\t') ++ne;
+    if (ne - nb > 2 && ne[-2] == '/' && (ne[-1] == '1' || ne[-1] == '2')) ne -= 2;
+    char *dst = B.names + (size_t)slot * B.name_stride;
+    const size_t nl = std::min((size_t)(ne - nb), (size_t)B.name_stride - 1);
+    memcpy(dst, nb, nl); memset(dst + nl, 0, (size_t)B.name_stride - nl);
+    return true;
+}
+
+}  // namespace
+
+class Feeder {
+public:
+    ~Feeder() { close(); }
+    bool open(const std::string &path, int n_threads, std::string &err) {
+        fp_ = fopen(path.c_str(), "rb");
+        if (!fp_) { err = "cannot open " + path; return false; }
+        pool_ = &pool(n_threads);
+        unsigned char head[18];
+        const size_t got = fread(head, 1, sizeof(head), fp_);
+        rewind(fp_);
+        kind_ = 0;
+        if (got >= 2 && head[0] == 0x1f && head[1] == 0x8b) {
+            kind_ = 1;
+            if (got >= 18 && (head[3] & 4) && head[12] == 'B' && head[13] == 'C' && head[14] == 2 && head[15] == 0) kind_ = 2;
+        }
+        stop_ = false; done_ = false;
+        producer_ = std::thread([this]() { produce(); });
+        return true;
+    }
+    void close() {
+        if (producer_.joinable()) {
+            { std::lock_guard<std::mutex> l(qm_); stop_ = true; }
+            qcv_.notify_all();
+            producer_.join();
+        }
+        if (fp_) fclose(fp_);
+        fp_ = nullptr; cur_.reset(); queue_.clear(); carry_.clear();
+    }
+    int kind() const { return kind_; }
+
+    // up to n_max records into the batch; 0 at end of file; -1 on a malformed input (message in err)
+    int fill(int n_max, const Batch &B, std::string &err) {
+        Latch latch;
+        int n = 0;
+        while (n < n_max && !fail_.set.load()) {
+            if (!cur_ || pos_ == cur_->n) {
+                cur_ = next_block();
+                pos_ = 0;
+                if (!cur_) {                                   // end of input: a last record without its final newline
+                    if (!carry_.empty()) {
+                        const char *nx;
+                        int nl = 0; for (char c : carry_) nl += c == '\n';
+                        if (nl < 3) fail_.raise("truncated FASTQ record");
+                        else if (parse_record(carry_.data(), carry_.data() + carry_.size(), B, n, fail_, &nx)) ++n;
+                        carry_.clear();
+                    }
+                    break;
+                }
+            }
+            const char *base = cur_->text.data(), *end = base + cur_->n, *p = base + pos_;
+            if (!carry_.empty()) {                              // finish the record the previous block cut
+                int nl = 0; for (char c : carry_) nl += c == '\n';
+                const char *q = p;
+                while (nl < 4 && q < end) { const char *e = line_end(q, end); if (e == end) { q = end; break; } q = e + 1; ++nl; }
+                carry_.append(p, q);
+                pos_ = (size_t)(q - base);
+                if (nl < 4) continue;                           // still incomplete: next block
+                const char *nx;
+                if (parse_record(carry_.data(), carry_.data() + carry_.size(), B, n, fail_, &nx)) ++n;
+                carry_.clear();
+                continue;
+            }
+            // runs of whole records
+            while (n < n_max && p < end) {
+                const char *run = p; int k = 0;
+                const int want = std::min(kRunRecords, n_max - n);
+                const char *rec = p;
+                while (k < want) {
+                    while (rec < end && (*rec == '\n' || *rec == '\r')) ++rec;     // blank lines between records
+                    if (k == 0) run = rec;
+                    const char *q = rec; int nl = 0;
+                    while (nl < 4) { const char *e = line_end(q, end); if (e == end) break; q = e + 1; ++nl; }
+                    if (nl < 4) break;
+                    rec = q; ++k;
+                }
+                if (k > 0) {
+                    BlockPtr keep = cur_;
+                    const int first = n;
+                    const char *run_end = rec;
+                    latch.add();
+                    pool_->submit([keep, run, run_end, first, k, B, this, &latch]() {
+                        const char *q = run;
+                        for (int i = 0; i < k && !fail_.set.load(); ++i) {
+                            while (q < run_end && (*q == '\n' || *q == '\r')) ++q;
+                            if (!parse_record(q, run_end, B, first + i, fail_, &q)) break;
+                        }
+                        latch.done();
+                    });
+                    n += k;
+                    p = rec;
+                }
+                if (k < want) {                                 // the block ends inside a record (or in blank lines)
+                    while (p < end && (*p == '\n' || *p == '\r')) ++p;
+                    carry_.assign(p, end);
+                    p = end;
+                }
+            }
+            pos_ = (size_t)(p - base);
+        }
+        latch.wait();
+        if (fail_.set.load()) { err = fail_.msg; return -1; }
+        return n;
+    }
+
+private:
+    BlockPtr next_block() {
+        std::unique_lock<std::mutex> l(qm_);
+        qcv_.wait(l, [&]() { return !queue_.empty() || done_; });
+        if (queue_.empty()) return nullptr;
+        BlockPtr b = queue_.front(); queue_.pop_front();
+        l.unlock();
+        qcv_.notify_all();
+        return b;
+    }
+    bool push_block(BlockPtr b) {
+        std::unique_lock<std::mutex> l(qm_);
+        qcv_.wait(l, [&]() { return stop_ || (int)queue_.size() < kQueueDepth; });
+        if (stop_) return false;
+        queue_.push_back(std::move(b));
+        l.unlock();
+        qcv_.notify_all();
+        return true;
+    }
+    void finish() {
+        { std::lock_guard<std::mutex> l(qm_); done_ = true; }
+        qcv_.notify_all();
+    }
+    static BlockPtr new_block(size_t cap = kBlockBytes) {
+        BlockPtr b = std::make_shared<Block>();
+        b->text.resize(cap);
+        return b;
+    }
+
+    void produce() {
+        if (kind_ == 0) produce_text(); else if (kind_ == 1) produce_gzip(); else produce_bgzf();
+        finish();
+    }
+    void produce_text() {
+        for (;;) {
+            BlockPtr b = new_block();
+            b->n = fread(b->text.data(), 1, b->text.size(), fp_);
+            if (b->n == 0) return;
+            if (!push_block(b)) return;
+        }
+    }
+    void produce_gzip() {
+        z_stream zs; memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, 31) != Z_OK) { fail_.raise("inflateInit2 failed"); return; }
+        std::vector<unsigned char> in((size_t)1 << 20);
+        BlockPtr b = new_block();
+        zs.next_out = (Bytef *)b->text.data(); zs.avail_out = (uInt)b->text.size();
+        bool eof = false, ok = true;
+        while (ok && !eof) {
+            zs.avail_in = (uInt)fread(in.data(), 1, in.size(), fp_);
+            zs.next_in = in.data();
+            if (zs.avail_in == 0) break;
+            while (zs.avail_in > 0) {
+                const int rc = inflate(&zs, Z_NO_FLUSH);
+                if (rc == Z_STREAM_END) {                       // next gzip member, if any
+                    if (inflateReset(&zs) != Z_OK) { fail_.raise("inflateReset failed"); ok = false; break; }
+                } else if (rc != Z_OK && rc != Z_BUF_ERROR) { fail_.raise("corrupt gzip stream"); ok = false; break; }
+                if (zs.avail_out == 0) {
+                    b->n = b->text.size();
+                    if (!push_block(b)) { ok = false; break; }
+                    b = new_block();
+                    zs.next_out = (Bytef *)b->text.data(); zs.avail_out = (uInt)b->text.size();
+                }
+            }
+        }
+        b->n = b->text.size() - zs.avail_out;
+        if (ok && b->n) push_block(b);
+        inflateEnd(&zs);
+    }
+    struct Group {
+        std::vector<unsigned char> comp;                        // whole members back to back
+        std::vector<std::pair<uint32_t, uint32_t>> member;      // offset in comp, size
+        BlockPtr out;
+        std::mutex m; std::condition_variable cv; bool ready = false;
+    };
+    void produce_bgzf() {
+        std::deque<std::shared_ptr<Group>> flight;
+        std::vector<unsigned char> buf; size_t have = 0, at = 0;
+        buf.resize((size_t)8 << 20);
+        bool eof = false;
+        auto drain_one = [&]() -> bool {
+            std::shared_ptr<Group> g = flight.front(); flight.pop_front();
+            { std::unique_lock<std::mutex> l(g->m); g->cv.wait(l, [&]() { return g->ready; }); }
+            if (g->out->n == 0) return true;
+            return push_block(g->out);
+        };
+        for (;;) {
+            auto g = std::make_shared<Group>();
+            while ((int)g->member.size() < kBgzfGroup) {
+                if (have - at < 18 + 8 && !eof) {                // refill, keeping the unread tail
+                    memmove(buf.data(), buf.data() + at, have - at); have -= at; at = 0;
+                    const size_t r = fread(buf.data() + have, 1, buf.size() - have, fp_);
+                    if (r == 0) eof = true;
+                    have += r;
+                }
+                if (have - at == 0) break;
+                if (have - at < 18) { fail_.raise("truncated BGZF member"); break; }
+                const unsigned char *h = buf.data() + at;
+                if (h[0] != 0x1f || h[1] != 0x8b || !(h[3] & 4) || h[12] != 'B' || h[13] != 'C') { fail_.raise("not a BGZF member"); break; }
+                const size_t bsize = (size_t)(h[16] | (h[17] << 8)) + 1;
+                if (have - at < bsize) {
+                    if (eof) { fail_.raise("truncated BGZF member"); break; }
+                    memmove(buf.data(), buf.data() + at, have - at); have -= at; at = 0;
+                    const size_t r = fread(buf.data() + have, 1, buf.size() - have, fp_);
+                    if (r == 0) eof = true;
+                    have += r;
+                    continue;
+                }
+                g->member.emplace_back((uint32_t)g->comp.size(), (uint32_t)bsize);
+                g->comp.insert(g->comp.end(), h, h + bsize);
+                at += bsize;
+            }
+            if (fail_.set.load() || g->member.empty()) break;
+            flight.push_back(g);
+            Failure *fail = &fail_;
+            pool_->submit([g, fail]() {
+                size_t total = 0;
+                for (auto &mb : g->member) {
+                    const unsigned char *t = g->comp.data() + mb.first + mb.second - 4;
+                    total += (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);     // ISIZE
+                }
+                g->out = new_block(std::max<size_t>(total, 1));
+                z_stream zs; memset(&zs, 0, sizeof(zs));
+                bool ok = inflateInit2(&zs, -15) == Z_OK;
+                size_t o = 0;
+                for (auto &mb : g->member) {
+                    if (!ok) break;
+                    const unsigned char *h = g->comp.data() + mb.first;
+                    const size_t xlen = (size_t)h[10] | ((size_t)h[11] << 8);
+                    zs.next_in = const_cast<Bytef *>(h + 12 + xlen); zs.avail_in = (uInt)(mb.second - 12 - xlen - 8);
+                    zs.next_out = (Bytef *)g->out->text.data() + o; zs.avail_out = (uInt)(total - o);
+                    const int rc = inflate(&zs, Z_FINISH);
+                    if (rc != Z_STREAM_END) { ok = false; break; }
+                    o = total - zs.avail_out;
+                    ok = inflateReset(&zs) == Z_OK;
+                }
+                inflateEnd(&zs);
+                if (!ok || o != total) fail->raise("corrupt BGZF member");
+                g->out->n = ok ? o : 0;
+                { std::lock_guard<std::mutex> l(g->m); g->ready = true; }
+                g->cv.notify_all();
+            });
+            if ((int)flight.size() >= kBgzfWindow && !drain_one()) { while (!flight.empty()) { auto f = flight.front(); flight.pop_front(); std::unique_lock<std::mutex> l(f->m); f->cv.wait(l, [&]() { return f->ready; }); } return; }
+        }
+        while (!flight.empty()) if (!drain_one()) { while (!flight.empty()) { auto f = flight.front(); flight.pop_front(); std::unique_lock<std::mutex> l(f->m); f->cv.wait(l, [&]() { return f->ready; }); } return; }
+    }
+
+    FILE *fp_ = nullptr;
+    int kind_ = 0;                                              // 0 text, 1 gzip stream, 2 BGZF
+    WorkPool *pool_ = nullptr;
+    std::thread producer_;
+    std::mutex qm_; std::condition_variable qcv_;
+    std::deque<BlockPtr> queue_;
+    bool stop_ = false, done_ = false;
+    BlockPtr cur_; size_t pos_ = 0;
+    std::string carry_;
+    Failure fail_;
+};
+
+}  // namespace fqb
+
+struct fqb_feeder { fqb::Feeder f; };
+
+extern "C" {
+
+int fqb_feeder_open(const char *path, int n_threads, fqb_feeder **out) {
+    if (!path || !out) { fqb::set_error("null argument"); return FQB_ERR_ARG; }
+    fqb_feeder *f = new fqb_feeder();
+    std::string err;
+    if (!f->f.open(path, n_threads, err)) { fqb::set_error(err); delete f; return FQB_ERR_IO; }
+    *out = f;
+    return FQB_OK;
+}
+
+int fqb_feeder_format(const fqb_feeder *f) { return f ? f->f.kind() : -1; }
+
+int64_t fqb_feeder_fill(fqb_feeder *f, int32_t n_max, int32_t stride, uint8_t *bases, uint8_t *quals, int32_t *lens, char *names, int32_t name_stride) {
+    if (!f || !bases || !quals || !lens || !names || n_max < 0 || stride < 1 || name_stride < 2) { fqb::set_error("bad argument"); return -1; }
+    fqb::Batch B{stride, name_stride, bases, quals, lens, names};
+    std::string err;
+    const int n = f->f.fill(n_max, B, err);
+    if (n < 0) fqb::set_error(err);
+    return n;
+}
+
+void fqb_feeder_close(fqb_feeder *f) { delete f; }
+
+}  // extern "C"

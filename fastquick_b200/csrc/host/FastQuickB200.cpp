@@ -38,8 +38,9 @@ int StatCollector::ProcessCore(const std::string &statPrefix, const gap_opt_t *)
     return 0;
 }
 
-// ---- FASTQ feeder: 4-line records from gz, into fixed-stride pinned batches (kseq_read3_fpc's contract, libbwa/kseq.h:327-370).
-// Lines are located in place in the inflate buffer (memchr); only a line cut by the end of the buffer is moved.
+// ---- serial FASTQ reader, used only with --frac_samp < 1 (the draws follow the records in file order); every other run
+// reads through the parallel feeder of the library (fqb_feeder_*, fq_feeder.cpp).  4-line records from gz, into fixed-stride
+// pinned batches (kseq_read3_fpc's contract, libbwa/kseq.h:327-370); lines are located in place in the inflate buffer.
 struct FastqReader {
     gzFile fp = nullptr;
     std::vector<char> buf; size_t pos = 0, end = 0;
@@ -168,8 +169,12 @@ BwtMapper::BwtMapper(BwtIndexer &BwtIndex, const std::string &FQList, const std:
 BwtMapper::~BwtMapper() { fqb_destroy(h_); }
 
 bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, const gap_opt_t *opt, FileStatCollector &FSC) {
+    // --frac_samp draws once per record in file order (FastqReader::fill); everything else goes through the parallel feeder
+    const bool sampled = opt->frac < 1.0;
     FastqReader r[2];
-    if (!r[0].open(fq1) || !r[1].open(fq2)) error("Open fastq failed: %s / %s", fq1.c_str(), fq2.c_str());
+    fqb_feeder *fd[2] = {nullptr, nullptr};
+    if (sampled) { if (!r[0].open(fq1) || !r[1].open(fq2)) error("Open fastq failed: %s / %s", fq1.c_str(), fq2.c_str()); }
+    else if (fqb_feeder_open(fq1.c_str(), 0, &fd[0]) != FQB_OK || fqb_feeder_open(fq2.c_str(), 0, &fd[1]) != FQB_OK) error("Open fastq failed: %s", fqb_last_error());
     if (fqb_stats_begin_file(h_, prefix_.c_str(), fq1.c_str(), fq2.c_str()) != FQB_OK) error("%s", fqb_last_error());
     const int stride = opt->read_len < FQB_MAX_READ_LEN ? opt->read_len : FQB_MAX_READ_LEN, cap = FQB_BATCH_PAIRS, name_stride = 64;
     // three pinned batches in flight: the GPU maps batch N, the copy stream uploads batch N+1, the reader threads decode batch N+2
@@ -186,8 +191,14 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
     auto load = [&](Buf &B) {
         const uint32_t seed = n_loaded ? (uint32_t)(n_loaded - 1) : 0u;
         ++n_loaded;
-        std::thread t0([&]() { B.n[0] = r[0].fill(cap, stride, B.b[0], B.q[0], B.l[0], B.nm[0], name_stride, opt->frac, seed); });
-        B.n[1] = r[1].fill(cap, stride, B.b[1], B.q[1], B.l[1], B.nm[1], name_stride, opt->frac, seed);
+        auto one = [&](int e) {
+            if (sampled) { B.n[e] = r[e].fill(cap, stride, B.b[e], B.q[e], B.l[e], B.nm[e], name_stride, opt->frac, seed); return; }
+            const int64_t n = fqb_feeder_fill(fd[e], cap, stride, B.b[e], B.q[e], B.l[e], B.nm[e], name_stride);
+            if (n < 0) error("%s", fqb_last_error());
+            B.n[e] = (int)n;
+        };
+        std::thread t0([&]() { one(0); });
+        one(1);
         t0.join();
     };
     auto good = [](const Buf &B) { return B.n[0] > 0 && B.n[1] > 0; };
@@ -212,13 +223,14 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
     notice("%lld sequences are loaded.", FSC.NumRead);
     for (auto &B : bufs) for (int e = 0; e < 2; ++e) { fqb_host_free(B.b[e]); fqb_host_free(B.q[e]); fqb_host_free(B.l[e]); fqb_host_free(B.nm[e]); }
     r[0].close(); r[1].close();
+    fqb_feeder_close(fd[0]); fqb_feeder_close(fd[1]);
     return 0;
 }
 
 // BwtMapper::SingleEndMapper (src/BwtMapper.cpp:1266-1407): same stages on batches that carry first reads only
 bool BwtMapper::SingleEndMapper(const std::string &fq1, const gap_opt_t *opt, FileStatCollector &FSC) {
-    FastqReader r;
-    if (!r.open(fq1)) error("Open fastq failed: %s", fq1.c_str());
+    fqb_feeder *fd = nullptr;
+    if (fqb_feeder_open(fq1.c_str(), 0, &fd) != FQB_OK) error("Open fastq failed: %s", fqb_last_error());
     if (fqb_stats_begin_file(h_, prefix_.c_str(), fq1.c_str(), fq1.c_str()) != FQB_OK) error("%s", fqb_last_error());
     const int stride = opt->read_len < FQB_MAX_READ_LEN ? opt->read_len : FQB_MAX_READ_LEN, cap = FQB_BATCH_PAIRS, name_stride = 64;
     struct Buf { uint8_t *b, *q; int32_t *l; char *nm; int n; } bufs[3];
@@ -228,7 +240,11 @@ bool BwtMapper::SingleEndMapper(const std::string &fq1, const gap_opt_t *opt, Fi
         if (!B.b || !B.q || !B.l || !B.nm) error("pinned host allocation failed");
         B.n = 0;
     }
-    auto load = [&](Buf &B) { B.n = r.fill(cap, stride, B.b, B.q, B.l, B.nm, name_stride); };
+    auto load = [&](Buf &B) {
+        const int64_t n = fqb_feeder_fill(fd, cap, stride, B.b, B.q, B.l, B.nm, name_stride);
+        if (n < 0) error("%s", fqb_last_error());
+        B.n = (int)n;
+    };
     int cur = 0;
     load(bufs[0]);
     if (bufs[0].n > 0) load(bufs[1]);
@@ -246,7 +262,7 @@ bool BwtMapper::SingleEndMapper(const std::string &fq1, const gap_opt_t *opt, Fi
     }
     notice("%lld sequences are loaded.", FSC.NumRead);
     for (auto &B : bufs) { fqb_host_free(B.b); fqb_host_free(B.q); fqb_host_free(B.l); fqb_host_free(B.nm); }
-    r.close();
+    fqb_feeder_close(fd);
     return 0;
 }
 

@@ -211,6 +211,22 @@ int fqb_stage_fetch_aln(fqb_handle *h, int32_t cap, fqb_aln_t *out, int32_t *n_a
 /* since creation: stack pops, rank-query pairs, reference-equivalent occ-block touches (N_blk, the
  * roofline's algorithmic unit), overflow reads of the last batch */
 int fqb_stage_counters(fqb_handle *h, uint64_t *out4);
+/* ---- host feeder (row f2) ------------------------------------------------
+ * FASTQ file -> the fixed-stride batches fqb_align_pairs / fqb_prefetch_pairs take, decoded in parallel.
+ * Replaces the record-by-record kseq_read3_fpc (libbwa/kseq.h:327-370) loop of bwa_read_seq_with_hash_dev
+ * (src/BwtMapper.cpp:476-613): a producer thread turns the file into text blocks (BGZF members are inflated
+ * independently by a worker pool; any other gzip stream by one zlib stream; plain text is read as is) and the
+ * pool parses runs of whole records straight into the caller's (pinned) batch.  n_threads <= 0 = one per
+ * host core, at most 16; the pool is shared by all feeders of the process.
+ * fill: up to n_max records; bases padded with 'N' and qualities with '!' to `stride`; names cut at the first
+ * blank with a trailing /1 or /2 removed, zero-padded to name_stride.  Returns the number of records
+ * (0 = end of file) or -1 (fqb_last_error: malformed record, read longer than stride, corrupt stream). */
+typedef struct fqb_feeder fqb_feeder;
+int fqb_feeder_open(const char *path, int n_threads, fqb_feeder **out);
+int fqb_feeder_format(const fqb_feeder *f);         /* 0 plain text, 1 gzip stream, 2 BGZF */
+int64_t fqb_feeder_fill(fqb_feeder *f, int32_t n_max, int32_t stride, uint8_t *bases, uint8_t *quals,
+                        int32_t *lens, char *names, int32_t name_stride);
+void fqb_feeder_close(fqb_feeder *f);
 void *fqb_host_alloc(size_t bytes);                /* pinned host memory for the feeder's batches */
 void fqb_host_free(void *p);
 uint64_t fqb_launch_count(const fqb_handle *h);   /* kernels launched by this handle so far */

@@ -1,0 +1,126 @@
+"""Row f2: the parallel FASTQ feeder (fqb_feeder_*) against a plain Python parse of the same records, for the three
+container formats (text, gzip stream incl. multi-member, BGZF), odd batch sizes, CRLF, a missing final newline, blank
+lines, names with comments and /1 suffixes, and its error reporting."""
+import ctypes as C
+import gzip
+import os
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+import fx
+from fastquick_b200 import _abi
+
+
+def _records(n, seed, max_len=100, min_len=35):
+    rng = np.random.default_rng(seed)
+    recs = []
+    for i in range(n):
+        L = int(rng.integers(min_len, max_len + 1))
+        seq = bytes(np.frombuffer(b"ACGTN", np.uint8)[rng.integers(0, 5, L)])
+        qual = bytes((rng.integers(33, 74, L)).astype(np.uint8))
+        tail = [b"", b"/1", b"/2", b" 1:N:0:ACGT", b"\tcomment", b"/1 extra"][i % 6]
+        recs.append((b"r%d_%d" % (seed, i), tail, seq, qual))
+    return recs
+
+
+def _text(recs, eol=b"\n", final_newline=True, blank_tail=0):
+    out = bytearray()
+    for k, (name, tail, seq, qual) in enumerate(recs):
+        out += b"@" + name + tail + eol + seq + eol + b"+" + eol + qual
+        if k + 1 < len(recs) or final_newline: out += eol
+    out += eol * blank_tail
+    return bytes(out)
+
+
+def _bgzf(data, block=0xff00):
+    out = bytearray()
+    for off in list(range(0, len(data), block)) + [None]:
+        chunk = b"" if off is None else data[off:off + block]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        comp = co.compress(chunk) + co.flush()
+        out += struct.pack("<BBBBIBBHBBHH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, ord("B"), ord("C"), 2, len(comp) + 25)
+        out += comp + struct.pack("<II", zlib.crc32(chunk), len(chunk))
+    return bytes(out)
+
+
+def _read_all(path, stride, batch, n_threads=4, name_stride=64):
+    lib = fx.host_lib()
+    lib.fqb_feeder_fill.restype = C.c_int64
+    lib.fqb_feeder_fill.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+    lib.fqb_feeder_close.argtypes = [C.c_void_p]
+    lib.fqb_feeder_format.argtypes = [C.c_void_p]
+    f = C.c_void_p()
+    assert lib.fqb_feeder_open(path.encode(), n_threads, C.byref(f)) == 0, lib.fqb_last_error()
+    fmt = lib.fqb_feeder_format(f)
+    got = []
+    try:
+        while True:
+            b = np.zeros((batch, stride), np.uint8); q = np.zeros((batch, stride), np.uint8)
+            l = np.zeros(batch, np.int32); nm = np.zeros((batch, name_stride), np.uint8)
+            n = lib.fqb_feeder_fill(f, batch, stride, b.ctypes.data, q.ctypes.data, l.ctypes.data, nm.ctypes.data, name_stride)
+            if n < 0: raise RuntimeError(lib.fqb_last_error().decode())
+            if n == 0: break
+            for i in range(n):
+                got.append((bytes(nm[i]).rstrip(b"\0"), bytes(b[i]), bytes(q[i]), int(l[i])))
+    finally:
+        lib.fqb_feeder_close(f)
+    return fmt, got
+
+
+def _expect(recs, stride):
+    return [(name, seq + b"N" * (stride - len(seq)), qual + b"!" * (stride - len(qual)), len(seq)) for name, _, seq, qual in recs]
+
+
+@pytest.fixture(scope="module")
+def recs():
+    return _records(40000, 7)          # ~7.5 MB of text: crosses the 4 MiB block size and many parse runs
+
+
+@pytest.mark.parametrize("fmt", ["text", "gzip", "gzip_members", "bgzf"])
+@pytest.mark.parametrize("batch", [40000, 9973])
+def test_feeder_formats(tmp_path, recs, fmt, batch):
+    data = _text(recs)
+    p = str(tmp_path / ("r.fq" if fmt == "text" else "r.fq.gz"))
+    if fmt == "text": blob = data
+    elif fmt == "gzip": blob = gzip.compress(data, 1)
+    elif fmt == "gzip_members": blob = b"".join(gzip.compress(data[o:o + 1500000], 1) for o in range(0, len(data), 1500000))
+    else: blob = _bgzf(data)
+    open(p, "wb").write(blob)
+    kind, got = _read_all(p, 100, batch)
+    assert kind == {"text": 0, "gzip": 1, "gzip_members": 1, "bgzf": 2}[fmt]
+    assert got == _expect(recs, 100)
+
+
+@pytest.mark.parametrize("variant", ["crlf", "no_final_newline", "blank_tail", "one_thread"])
+def test_feeder_text_quirks(tmp_path, variant):
+    recs = _records(3000, 11)
+    data = _text(recs, eol=b"\r\n" if variant == "crlf" else b"\n", final_newline=variant != "no_final_newline", blank_tail=3 if variant == "blank_tail" else 0)
+    p = str(tmp_path / "q.fq.gz")
+    open(p, "wb").write(_bgzf(data, block=777) if variant != "one_thread" else gzip.compress(data))
+    _, got = _read_all(p, 128, 1024, n_threads=0)
+    assert got == _expect(recs, 128)
+
+
+def test_feeder_errors(tmp_path):
+    recs = _records(10, 3)
+    good = _text(recs)
+    cases = {
+        "long": (_text(_records(5, 4, max_len=100, min_len=100)), 64, "longer"),
+        "qual": (good.replace(recs[4][3], recs[4][3][:-1], 1), 100, "lengths differ"),
+        "header": (good.replace(b"@" + recs[6][0], b">" + recs[6][0], 1), 100, "'@'"),
+        "truncated": (good[:good.rindex(recs[-1][2]) + 10], 100, "truncated"),
+    }
+    for tag, (data, stride, msg) in cases.items():
+        p = str(tmp_path / (tag + ".fq"))
+        open(p, "wb").write(data)
+        with pytest.raises(RuntimeError, match=msg):
+            _read_all(p, stride, 64)
+    lib = fx.host_lib()
+    f = C.c_void_p()
+    assert lib.fqb_feeder_open(str(tmp_path / "missing.fq").encode(), 2, C.byref(f)) != 0
+    open(str(tmp_path / "bad.fq.gz"), "wb").write(gzip.compress(good)[:-40] + b"x" * 40)
+    with pytest.raises(RuntimeError):
+        _read_all(str(tmp_path / "bad.fq.gz"), 100, 64)

@@ -1,18 +1,31 @@
-"""Wall-clock of `FASTQuick_b200 align` (and optionally the reference CLI) on a FASTQ pair of N synthetic pairs."""
-import os, subprocess, sys, time
+"""Wall-clock of `FASTQuick_b200 align` (and optionally the reference CLI) on a FASTQ pair of N synthetic pairs, for the input
+containers the feeder distinguishes (gzip stream, BGZF, plain text), with and without BAM output.
+usage: python tools/cli_throughput.py [n_pairs] [--ref]"""
+import gzip, os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import fx
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 524288
+from test_feeder import _bgzf
+n = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 524288
 idx = fx.SynthIndex("small", n_long=40, n_short=160, n_x=5, n_y=5, with_rollhash=True)
-t0 = time.time(); arrs = idx.reads(n, read_len=100, seed=99); fq = idx.write_fastq("thr", arrs); print("fastq written %.1fs" % (time.time() - t0), flush=True)
-for tag, exe, extra in (("b200", os.path.join(fx.REPO, "fastquick_b200", "FASTQuick_b200"), []), ("b200-nobam", os.path.join(fx.REPO, "fastquick_b200", "FASTQuick_b200"), ["--sam_out"])) + ((("ref", fx.REF_BIN, []),) if "--ref" in sys.argv else ()):
-    out = os.path.join(idx.dir, "thr_" + tag)
-    cmd = [exe, "align", "--fastq_1", fq[0], "--fastq_2", fq[1], "--index_prefix", idx.prefix[:-len(".FASTQuick.fa")], "--out_prefix", out, "--t", str(os.cpu_count()), "--q", "15"] + extra
+t0 = time.time(); arrs = idx.reads(n, read_len=100, seed=99); fq = idx.write_fastq("thr", arrs)
+inputs = {"gzip": fq, "bgzf": [], "text": []}
+for f in fq:
+    text = gzip.open(f).read()
+    inputs["text"].append(f[:-3]); open(f[:-3], "wb").write(text)
+    inputs["bgzf"].append(f[:-6] + ".bgzf.fq.gz"); open(inputs["bgzf"][-1], "wb").write(_bgzf(text))
+print("fastq written %.1fs" % (time.time() - t0), flush=True)
+CLI = os.path.join(fx.REPO, "fastquick_b200", "FASTQuick_b200")
+runs = [("b200 %s%s" % (k, " +bam" if bam else ""), CLI, inputs[k], [] if bam else ["--sam_out"]) for k in ("gzip", "bgzf", "text") for bam in (False, True)]
+if "--ref" in sys.argv: runs.append(("ref gzip +bam", fx.REF_BIN, fq, []))
+for tag, exe, files, extra in runs:
+    out = os.path.join(idx.dir, "thr_out")
+    cmd = [exe, "align", "--fastq_1", files[0], "--fastq_2", files[1], "--index_prefix", idx.prefix[:-len(".FASTQuick.fa")], "--out_prefix", out, "--t", str(os.cpu_count()), "--q", "15"] + extra
     t0 = time.time()
     r = subprocess.run(cmd, cwd=idx.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     dt = time.time() - t0
-    for l in r.stdout.splitlines():
-        if "bam_emit" in l: print("   ", l)
-    line = [l for l in r.stdout.splitlines() if "Processed Pair End mapping" in l]
-    print(tag, "rc", r.returncode, "wall %.2fs" % dt, line[-1] if line else r.stdout[-300:], "bam %.1f MB" % (os.path.getsize(out + ".bam") / 1e6 if os.path.exists(out + ".bam") else 0), flush=True)
+    sec = [l for l in r.stdout.splitlines() if "Processed Pair End mapping" in l]
+    load = [l for l in r.stdout.splitlines() if "Restore Variant" in l or "Load Index" in l]
+    t_map = float(sec[-1].split(" in ")[1].split()[0]) if sec else float("nan")
+    print("%-16s rc %d  wall %.2fs  mapping %.2fs = %.0f pairs/s   %s" % (tag, r.returncode, dt, t_map, n / t_map, "; ".join(l.split(" - ")[-1] for l in load)), flush=True)
+    if r.returncode: print(r.stdout[-500:])
