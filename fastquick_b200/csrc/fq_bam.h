@@ -5,8 +5,12 @@
 // host copies of the reads.  Everything here is formatting; no alignment decision is taken on the host.
 #pragma once
 #include <cstdint>
+#include <condition_variable>
 #include <cstdio>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -15,18 +19,26 @@
 
 namespace fqb {
 
-// BGZF: independent <= 64 KiB gzip members, compressed by a few host threads, written in order
+// BGZF: independent <= 64 KiB gzip members.  write() only queues the bytes; a writer thread compresses each queued chunk
+// with a few host threads and writes the members in order, so compression overlaps the next batch's GPU work.
 class BgzfWriter {
 public:
     bool open(const std::string &path, std::string &err);
     void write(const void *data, size_t n);
-    bool close(std::string &err);                   // flushes, writes the EOF block
+    void write_owned(std::string &&data);           // whole records; becomes its own run of members, no copy
+    bool close(std::string &err);                   // drains the queue, writes the EOF block
     ~BgzfWriter();
 private:
-    void flush(bool all);
+    void hand_over(bool all);
+    void run();
+    void compress_and_write(const std::string &chunk);
     FILE *fp_ = nullptr;
     std::string pending_;
     bool failed_ = false;
+    std::thread writer_;
+    std::mutex m_; std::condition_variable cv_;
+    std::deque<std::string> queue_;
+    bool closing_ = false;
 };
 
 struct XaHit { uint32_t pos; uint8_t strand, gap, mm, has_cigar, n_cigar; uint16_t cigar[FQB_MAX_CIGAR]; };

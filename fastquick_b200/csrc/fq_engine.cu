@@ -1361,7 +1361,7 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
     }
     const auto t_fmt = std::chrono::steady_clock::now();
     size_t total = 0;
-    for (auto &o : parts) { h->bam.write(o.data(), o.size()); total += o.size(); }
+    for (auto &o : parts) { total += o.size(); h->bam.write_owned(std::move(o)); }
     if (getenv("FQB_BAM_DEBUG")) {
         const auto t_end = std::chrono::steady_clock::now();
         fprintf(stderr, "bam_emit: %zu pairs, %u multi hits, %zu bytes, threads %u; device+copies %.1f ms, format %.1f ms, bgzf %.1f ms\n", np, ctr[1], total, nthr,

@@ -21,11 +21,18 @@ if "--ref" in sys.argv: runs.append(("ref gzip +bam", fx.REF_BIN, fq, []))
 for tag, exe, files, extra in runs:
     out = os.path.join(idx.dir, "thr_out")
     cmd = [exe, "align", "--fastq_1", files[0], "--fastq_2", files[1], "--index_prefix", idx.prefix[:-len(".FASTQuick.fa")], "--out_prefix", out, "--t", str(os.cpu_count()), "--q", "15"] + extra
-    t0 = time.time()
-    r = subprocess.run(cmd, cwd=idx.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    dt = time.time() - t0
-    sec = [l for l in r.stdout.splitlines() if "Processed Pair End mapping" in l]
-    load = [l for l in r.stdout.splitlines() if "Restore Variant" in l or "Load Index" in l]
-    t_map = float(sec[-1].split(" in ")[1].split()[0]) if sec else float("nan")
-    print("%-16s rc %d  wall %.2fs  mapping %.2fs = %.0f pairs/s   %s" % (tag, r.returncode, dt, t_map, n / t_map, "; ".join(l.split(" - ")[-1] for l in load)), flush=True)
+    best = None
+    for rep in range(3):                 # the boxes are shared: best of three
+        t0 = time.time()
+        r = subprocess.run(cmd, cwd=idx.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        dt = time.time() - t0
+        sec = [l for l in r.stdout.splitlines() if "Processed Pair End mapping" in l]
+        t_map = float(sec[-1].split(" in ")[1].split()[0]) if sec else float("nan")
+        if best is None or t_map < best[1]: best = (dt, t_map)
+        if r.returncode: break
+    dt, t_map = best
+    print("%-16s rc %d  wall %.2fs  mapping %.2fs = %.0f pairs/s" % (tag, r.returncode, dt, t_map, n / t_map), flush=True)
     if r.returncode: print(r.stdout[-500:])
+    if os.environ.get("FQB_BAM_DEBUG"):
+        for l in r.stdout.splitlines():
+            if "bam_emit" in l: print("     ", l)
