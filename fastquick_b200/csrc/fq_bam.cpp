@@ -252,7 +252,16 @@ void tag_int(std::string &o, const char *t, int v) {        // SamRecord::addInt
     }
 }
 void tag_str(std::string &o, const char *t, const std::string &v) { o.append(t, 2); o.push_back('Z'); o.append(v.c_str(), v.size() + 1); }
-void put_num(std::string &o, long long v) { o += std::to_string(v); }
+void put_num(std::string &o, long long v) {
+    char b[24]; int n = 0;
+    unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    do { b[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+    if (v < 0) b[n++] = '-';
+    while (n) o.push_back(b[--n]);
+}
+// per-thread scratch of the formatter (records are formatted by a few host threads, one batch slice each)
+struct Scratch { std::string tags, md, xa; std::vector<uint8_t> sq; };
+thread_local Scratch g_scratch;
 
 // the read in alignment orientation as nt4 codes
 void oriented(const uint8_t *bases, int len, int strand, std::vector<uint8_t> &out) {
@@ -264,8 +273,8 @@ void oriented(const uint8_t *bases, int len, int strand, std::vector<uint8_t> &o
     }
 }
 // MD tag of bwa_cal_md1 (libbwa/bwase.c:234-296); seq = the trimmed read in alignment orientation
-std::string md_string(const HostIndex &I, const fqb_read_t &s, const uint16_t *cigar, int n_cigar, bool has_cigar, int len, const uint8_t *seq) {
-    std::string o;
+void md_string(const HostIndex &I, const fqb_read_t &s, const uint16_t *cigar, int n_cigar, bool has_cigar, int len, const uint8_t *seq, std::string &o) {
+    o.clear();
     auto base = [&](int64_t k) { return (I.pac[(size_t)(k >> 2)] >> ((~k & 3) << 1)) & 3; };
     int u = 0;
     int64_t x = s.pos, y = 0;
@@ -292,7 +301,6 @@ std::string md_string(const HostIndex &I, const fqb_read_t &s, const uint16_t *c
         }
     }
     put_num(o, u);
-    return o;
 }
 
 // mate_ptr == nullptr: single-end input (SetSamRecord(..., mate = 0, ...))
@@ -351,10 +359,10 @@ void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t *mate_ptr, 
     int ref_id = -1, pos1 = 0, read_real_start = 0;
     if (p.type != kNoMatch) { read_real_start = real_start(C, seqid, p.pos); ref_id = C.ref_of_contig[seqid]; pos1 = read_real_start; }
     // CIGAR
-    std::vector<uint32_t> cig;
+    uint32_t cig[FQB_MAX_CIGAR + 1]; int n_cig = 0;
     if (p.type != kNoMatch) {
-        if (p.has_cigar) for (int k = 0; k < p.n_cigar; ++k) { static const int opmap[4] = {0, 1, 2, 4}; cig.push_back((uint32_t)(p.cigar[k] & 0x3fff) << 4 | opmap[p.cigar[k] >> 14]); }
-        else cig.push_back((uint32_t)p.len << 4);
+        if (p.has_cigar) for (int k = 0; k < p.n_cigar; ++k) { static const int opmap[4] = {0, 1, 2, 4}; cig[n_cig++] = (uint32_t)(p.cigar[k] & 0x3fff) << 4 | opmap[p.cigar[k] >> 14]; }
+        else cig[n_cig++] = (uint32_t)p.len << 4;
     }
     // mate fields
     int mref = -1, mpos1 = 0;
@@ -370,17 +378,12 @@ void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t *mate_ptr, 
         read_real_start = m_start;                // the reference reuses the variable; only read again when the mate is unmapped
     } else if (has_mate) { mref = ref_id; mpos1 = read_real_start; isize = 0; }
     else { mref = -1; mpos1 = 0; isize = 0; }
-    // sequence and qualities in alignment orientation (full length)
+    // sequence and qualities in alignment orientation (full length) are written straight into the record below
     const int L = p.full_len;
     const uint8_t *t = nt4_table();
-    std::string seq((size_t)L, 'N'), qual((size_t)L, '\0');
-    for (int k = 0; k < L; ++k) {
-        if (!p.strand) { const uint8_t c = t[bases[k]]; seq[k] = "ACGTN"[c > 4 ? 4 : c]; }
-        else { const uint8_t c = t[bases[L - 1 - k]]; seq[k] = "TGCAN"[c > 4 ? 4 : c]; }
-        qual[k] = (char)((p.strand ? quals[L - 1 - k] : quals[k]) - 33);
-    }
     // tags
-    std::string tags;
+    std::string &tags = g_scratch.tags;
+    tags.clear();
     if (!C.rg_id.empty()) tag_str(tags, "RG", C.rg_id);
     if (p.clip_len < p.full_len) tag_int(tags, "XC", p.clip_len);
     if (p.type != kNoMatch) {
@@ -399,12 +402,14 @@ void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t *mate_ptr, 
         tag_int(tags, "XG", p.n_gapo + p.n_gape);
         // MD over the trimmed read: strip the soft clip bwa_correct_trimmed appended
         {
-            std::vector<uint8_t> sq;
+            std::vector<uint8_t> &sq = g_scratch.sq;
             oriented(bases, L, p.strand, sq);
-            tag_str(tags, "MD", md_string(I, p, p.cigar, p.n_cigar, p.has_cigar != 0, p.len, sq.data()));
+            md_string(I, p, p.cigar, p.n_cigar, p.has_cigar != 0, p.len, sq.data(), g_scratch.md);
+            tag_str(tags, "MD", g_scratch.md);
         }
         if (n_xa) {
-            std::string s;
+            std::string &s = g_scratch.xa;
+            s.clear();
             for (int i = 0; i < n_xa; ++i) {
                 const XaHit &q = xa[i];
                 int64_t e = q.pos;
@@ -426,23 +431,29 @@ void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t *mate_ptr, 
     const int32_t pos0 = pos1 - 1, aln_len = p.type != kNoMatch ? (int32_t)(pos_end(p) - p.pos) : 0;
     const int32_t end1 = aln_len ? pos0 + aln_len : pos0 + 1;
     const int bin = reg2bin(pos0, end1);
-    const int32_t block = 32 + l_name + 4 * (int)cig.size() + (L + 1) / 2 + L + (int)tags.size();
-    put32(out, block);
-    put32(out, ref_id); put32(out, pos0);
-    out.push_back((char)l_name); out.push_back((char)p.mapQ);
-    { uint16_t b = (uint16_t)bin; out.append((const char *)&b, 2); }
-    { uint16_t n = (uint16_t)cig.size(); out.append((const char *)&n, 2); }
-    { uint16_t f = (uint16_t)flag; out.append((const char *)&f, 2); }
-    put32(out, L); put32(out, mref); put32(out, mpos1 - 1); put32(out, (int32_t)isize);
-    out.append(name, (size_t)l_name);
-    for (uint32_t c : cig) out.append((const char *)&c, 4);
-    for (int k = 0; k < L; k += 2) {
-        static const char *codes = "=ACMGRSVTWYHKDBN";
-        const int hi = (int)(strchr(codes, seq[k]) - codes), lo = k + 1 < L ? (int)(strchr(codes, seq[k + 1]) - codes) : 0;
-        out.push_back((char)(hi << 4 | lo));
-    }
-    out += qual;
-    out += tags;
+    const int32_t block = 32 + l_name + 4 * n_cig + (L + 1) / 2 + L + (int)tags.size();
+    const size_t at = out.size();
+    out.resize(at + 4 + (size_t)block);
+    uint8_t *w = (uint8_t *)&out[at];
+    auto w32 = [&](int32_t v) { memcpy(w, &v, 4); w += 4; };
+    auto w16 = [&](uint16_t v) { memcpy(w, &v, 2); w += 2; };
+    w32(block); w32(ref_id); w32(pos0);
+    *w++ = (uint8_t)l_name; *w++ = (uint8_t)p.mapQ;
+    w16((uint16_t)bin); w16((uint16_t)n_cig); w16((uint16_t)flag);
+    w32(L); w32(mref); w32(mpos1 - 1); w32((int32_t)isize);
+    memcpy(w, name, (size_t)l_name); w += l_name;
+    memcpy(w, cig, 4 * (size_t)n_cig); w += 4 * n_cig;
+    // 4-bit bases "=ACMGRSVTWYHKDBN": A 1, C 2, G 4, T 8, N 15; the reverse strand prints the complement of the reversed read
+    static const uint8_t nib_f[5] = {1, 2, 4, 8, 15}, nib_r[5] = {8, 4, 2, 1, 15};
+    auto nib = [&](int k) -> uint8_t {
+        if (k >= L) return 0;
+        const uint8_t c = p.strand ? t[bases[L - 1 - k]] : t[bases[k]];
+        return p.strand ? nib_r[c > 4 ? 4 : c] : nib_f[c > 4 ? 4 : c];
+    };
+    for (int k = 0; k < L; k += 2) *w++ = (uint8_t)(nib(k) << 4 | nib(k + 1));
+    if (p.strand) for (int k = 0; k < L; ++k) *w++ = (uint8_t)(quals[L - 1 - k] - 33);
+    else for (int k = 0; k < L; ++k) *w++ = (uint8_t)(quals[k] - 33);
+    memcpy(w, tags.data(), tags.size());
 }
 }  // namespace
 

@@ -229,3 +229,29 @@ def test_cli_two_reference_sized_batches(small_index, ref_required):
             os.remove(outs[tag] + "." + ext)
     for f in fq:
         os.remove(f)
+
+
+def test_cli_input_containers_give_the_same_files(small_index):
+    """Row f2 at the CLI level: the same reads as a gzip stream, as BGZF (member-parallel inflate) and as plain text go
+    through different producers of the feeder and must leave identical summary files and BAM records."""
+    import gzip
+    from test_feeder import _bgzf
+    arrs = small_index.reads(20000, read_len=100, seed=87, f_on=0.95)
+    fq = small_index.write_fastq("clifmt", arrs)
+    inputs = {"gzip": fq, "bgzf": [], "text": []}
+    for f in fq:
+        text = gzip.open(f).read()
+        inputs["text"].append(f[:-3]); open(f[:-3], "wb").write(text)
+        inputs["bgzf"].append(f[:-6] + ".bgzf.fq.gz"); open(inputs["bgzf"][-1], "wb").write(_bgzf(text))
+    idx_prefix = small_index.prefix[: -len(".FASTQuick.fa")]
+    outs = {}
+    for tag, files in inputs.items():
+        out = os.path.join(small_index.dir, "clifmt_" + tag)
+        cmd = [CLI, "align", "--fastq_1", files[0], "--fastq_2", files[1], "--index_prefix", idx_prefix, "--out_prefix", out, "--q", "15"]
+        r = subprocess.run(cmd, cwd=small_index.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-3000:]
+        outs[tag] = out
+    for tag in ("bgzf", "text"):
+        for ext in TEXT_FILES:
+            _compare_files(outs["gzip"] + "." + ext, outs[tag] + "." + ext)
+        assert len(_compare_bams(outs["gzip"] + ".bam", outs[tag] + ".bam")) > 30000
