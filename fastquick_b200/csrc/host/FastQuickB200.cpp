@@ -124,10 +124,12 @@ BwtMapper::BwtMapper(BwtIndexer &BwtIndex, const std::string &FQList, const std:
     fqb_pe_opt_t p; fqb_pe_opt_default(&p);
     p.max_isize = popt->max_isize; p.force_isize = popt->force_isize; p.max_occ = popt->max_occ; p.n_multi = popt->n_multi;
     p.N_multi = popt->N_multi; p.type = popt->type; p.is_sw = popt->is_sw; p.ap_prior = popt->ap_prior;
+    double t_tmp = realtime();
     if (fqb_create(RefPath.c_str(), &g, &p, device, &h_) != FQB_OK) error("%s", fqb_last_error());
+    notice("Index on the device (FM index, SA, pac, k-mer tables)...%f sec", realtime() - t_tmp);
     collector.Attach(h_);
     if (targetRegionPath != "Empty" && fqb_stats_set_target_region(h_, targetRegionPath.c_str()) != FQB_OK) error("%s", fqb_last_error());
-    double t_tmp = realtime();
+    t_tmp = realtime();
     collector.RestoreVcfSites(RefPath, opt);
     notice("Restore Variant Site Info...%f sec", realtime() - t_tmp);
     bam_out_ = opt->out_bam != 0;
