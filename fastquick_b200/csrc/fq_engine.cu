@@ -23,6 +23,8 @@
 #include <algorithm>
 #include <chrono>
 #include <fstream>
+#include <future>
+#include <mutex>
 #include <thread>
 #include <cmath>
 #include "fq_relayout.h"
@@ -146,6 +148,11 @@ struct fqb_handle {
     std::string isize_table_path;
     std::vector<std::pair<uint64_t, uint64_t>> isize_table_idx;   // (first global pair, bytes) of every emitted batch, in emission order
     fqb_read_t *h_rows = nullptr; PairStat *h_pstat = nullptr; size_t h_rows_cap = 0;     // pinned staging of fqb_stats_emit
+    // Host phases (formatting + writing) of the last fqb_stats_emit / fqb_bam_emit: they run on their own thread while the
+    // caller submits the next batch, and are joined before their staging is written again (drain_post)
+    std::future<void> post_stats, post_bam;
+    std::mutex post_m; std::string post_err;
+    uint64_t h_pstat_first = ~0ull;        // first global pair of the batch h_pstat holds
     uint32_t arena_fast = kArenaFast, arena_mid = kArenaMid;   // FQB_DEBUG_ARENA_FAST/_MID shrink them (tests of the overflow tiers)
 };
 
@@ -355,6 +362,8 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     return FQB_OK;
 }
 
+static int drain_post(fqb_handle *h, bool stats, bool bam);
+
 int fqb_kmer_tables_origin(const fqb_handle *h) { return h ? h->kmer_origin : 0; }
 
 int fqb_kmer_tables_fetch(fqb_handle *h, uint64_t offset, uint64_t n_bytes, uint8_t *out) {
@@ -368,6 +377,7 @@ int fqb_kmer_tables_fetch(fqb_handle *h, uint64_t offset, uint64_t n_bytes, uint
 }
 
 void fqb_destroy(fqb_handle *h) {
+    if (h) drain_post(h, true, true);
     if (!h) return;
     cudaSetDevice(h->device);
     free_batch(h);
@@ -740,7 +750,18 @@ int fqb_stats_open(fqb_handle *h, const char *index_prefix) {
 
 // The FileStatCollector counters live on the device as running totals; a file's own counters are the totals at its
 // end minus the totals when it began (collector.AddFSC(FSC), src/BwtMapper.cpp:254).
+// joins the deferred host phases; reports the first failure one of them met
+static int drain_post(fqb_handle *h, bool stats, bool bam) {
+    if (stats && h->post_stats.valid()) h->post_stats.get();
+    if (bam && h->post_bam.valid()) h->post_bam.get();
+    std::lock_guard<std::mutex> l(h->post_m);
+    if (!h->post_err.empty()) { set_error(h->post_err); h->post_err.clear(); return FQB_ERR_IO; }
+    return FQB_OK;
+}
+static bool emit_inline() { static const bool v = getenv("FQB_SYNC_EMIT") != nullptr; return v; }
+
 static int close_current_file(fqb_handle *h) {
+    if (int rc = drain_post(h, true, true)) return rc;
     if (h->files.empty()) return FQB_OK;
     CU_CHECK(cudaStreamSynchronize(h->stream));
     unsigned long long sc[kEmpScalars];
@@ -809,6 +830,7 @@ int fqb_stage_stats(fqb_handle *h) {
 int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride) {
     if (!h || !h->stats_done) { set_error("fqb_stats_emit: run fqb_stage_stats first"); return FQB_ERR_STATE; }
     CU_CHECK(cudaSetDevice(h->device));
+    if (int rc = drain_post(h, true, true)) return rc;                  // the previous batch's host phases read the staging written below
     const size_t np = (size_t)h->n_reads / 2;
     if (np > h->h_rows_cap) {
         cudaFreeHost(h->h_rows); cudaFreeHost(h->h_pstat);
@@ -817,42 +839,54 @@ int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride) {
         CU_CHECK(cudaMallocHost(&h->h_pstat, np * sizeof(PairStat)));
         h->h_rows_cap = np;
     }
+    const uint64_t first = h->pairs_seen - np;
     CU_CHECK(cudaMemcpyAsync(h->h_rows, h->d_rows, 2 * np * sizeof(fqb_read_t), cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(cudaMemcpyAsync(h->h_pstat, h->d_pstat, np * sizeof(PairStat), cudaMemcpyDeviceToHost, h->stream));
     CU_CHECK(cudaStreamSynchronize(h->stream));
+    h->h_pstat_first = first;
     if (!h->isize_table.is_open()) return FQB_OK;
-    const uint64_t first = h->pairs_seen - np;
-    // format on several host threads (contiguous slices of the batch), write the slices in order
-    unsigned nthr = std::thread::hardware_concurrency();
-    if (nthr < 1) nthr = 1;
-    if (nthr > 16) nthr = 16;
-    if (np < 4096) nthr = 1;
-    std::vector<std::string> parts(nthr);
-    auto work = [&](unsigned t) {
-        std::string &o = parts[t];
-        const size_t lo = np * t / nthr, hi = np * (t + 1) / nthr;
-        o.reserve((hi - lo) * 96);
-        char buf[64];
-        std::string nm;
-        for (size_t i = lo; i < hi; ++i) {
-            const PairStat &ps = h->h_pstat[i];
-            if (ps.line_kind == 0) continue;
-            const char *name;
-            if (names) { nm.assign(names + i * (size_t)name_stride, strnlen(names + i * (size_t)name_stride, (size_t)name_stride)); name = nm.c_str(); }
-            else { snprintf(buf, sizeof buf, "r%011llu", (unsigned long long)(first + i)); name = buf; }
-            append_isize_line(h->stabs, ps, h->h_rows[2 * i], h->h_rows[2 * i + 1], name, o);
+    // host phase: format on several host threads (contiguous slices of the batch), write the slices in order.  `names` must
+    // stay valid until the next fqb_stats_emit / fqb_bam_emit / fqb_stats_finish / fqb_bam_close call on this handle returns.
+    auto host_phase = [h, np, names, name_stride, first]() {
+        unsigned nthr = std::thread::hardware_concurrency();
+        if (nthr < 1) nthr = 1;
+        if (nthr > 16) nthr = 16;
+        if (np < 4096) nthr = 1;
+        std::vector<std::string> parts(nthr);
+        auto work = [&](unsigned t) {
+            std::string &o = parts[t];
+            const size_t lo = np * t / nthr, hi = np * (t + 1) / nthr;
+            o.reserve((hi - lo) * 96);
+            char buf[64];
+            std::string nm;
+            for (size_t i = lo; i < hi; ++i) {
+                const PairStat &ps = h->h_pstat[i];
+                if (ps.line_kind == 0) continue;
+                const char *name;
+                if (names) { nm.assign(names + i * (size_t)name_stride, strnlen(names + i * (size_t)name_stride, (size_t)name_stride)); name = nm.c_str(); }
+                else { snprintf(buf, sizeof buf, "r%011llu", (unsigned long long)(first + i)); name = buf; }
+                append_isize_line(h->stabs, ps, h->h_rows[2 * i], h->h_rows[2 * i + 1], name, o);
+            }
+        };
+        if (nthr == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nthr; ++t) th.emplace_back(work, t);
+            for (auto &x : th) x.join();
         }
+        uint64_t bytes = 0;
+        for (auto &o : parts) { h->isize_table.write(o.data(), (std::streamsize)o.size()); bytes += o.size(); }
+        h->isize_table_idx.emplace_back(first, bytes);
+        if (!h->isize_table) { std::lock_guard<std::mutex> l(h->post_m); if (h->post_err.empty()) h->post_err = "write error on the InsertSizeTable"; }
     };
-    if (nthr == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nthr; ++t) th.emplace_back(work, t);
-        for (auto &x : th) x.join();
-    }
-    uint64_t bytes = 0;
-    for (auto &o : parts) { h->isize_table.write(o.data(), (std::streamsize)o.size()); bytes += o.size(); }
-    h->isize_table_idx.emplace_back(first, bytes);
+    if (emit_inline()) { host_phase(); return drain_post(h, true, true); }
+    h->post_stats = std::async(std::launch::async, host_phase);
     return FQB_OK;
+}
+
+int fqb_emit_sync(fqb_handle *h) {
+    if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    return drain_post(h, true, true);
 }
 
 // Sharded runs: every rank writes the InsertSizeTable lines of its own batches.  close_table() finishes a rank's file
@@ -861,6 +895,7 @@ int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride) {
 // InsertSizeEstimator that reads it) is exactly that of an unsharded run.
 int fqb_stats_close_table(fqb_handle *h) {
     if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    if (int rc = drain_post(h, true, true)) return rc;
     if (h->isize_table.is_open()) h->isize_table.close();
     if (h->isize_table_path.empty()) return FQB_OK;
     std::ofstream idx(h->isize_table_path + ".idx");
@@ -901,7 +936,9 @@ int fqb_stats_finish(fqb_handle *h, const char *out_prefix) {
     if (!h || !h->stats_open || !out_prefix) { set_error("fqb_stats_finish: call fqb_stats_open first"); return FQB_ERR_STATE; }
     CU_CHECK(cudaSetDevice(h->device));
     CU_CHECK(cudaStreamSynchronize(h->stream));
-    int rc = drain_tuples(h);
+    int rc = drain_post(h, true, true);
+    if (rc) return rc;
+    rc = drain_tuples(h);
     if (rc) return rc;
     if (h->isize_table.is_open()) h->isize_table.close();
     const StatsTables &T = h->stabs;
@@ -1248,6 +1285,7 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
     if (!h->dp_done || (h->stats_open && !h->stats_done)) { set_error("fqb_bam_emit: the batch must be through fqb_stage_sw_refine and fqb_stage_stats"); return FQB_ERR_STATE; }
     if (!bases1 || !quals1 || stride < 1 || (!h->single_end && (!bases2 || !quals2))) { set_error("fqb_bam_emit: the reads of the batch are required"); return FQB_ERR_ARG; }
     CU_CHECK(cudaSetDevice(h->device));
+    if (int rc = drain_post(h, false, true)) return rc;      // the previous batch's records are out; fqb_stats_emit's host phase of THIS batch may still run
     cudaStream_t st = h->stream;
     const size_t np = (size_t)h->n_reads / 2;
     const auto t_begin = std::chrono::steady_clock::now();
@@ -1277,7 +1315,9 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
     }
     CU_CHECK(cudaMemcpyAsync(h->h_bam_rows, h->d_rows, 2 * np * sizeof(fqb_read_t), cudaMemcpyDeviceToHost, st));
     const bool have_ps = h->stats_done && h->d_pstat;
-    if (have_ps) {
+    const uint64_t first = h->pairs_seen - (h->stats_done ? np : 0);
+    if (have_ps && h->h_pstat_first != first) {              // not staged by fqb_stats_emit already
+        if (int rc = drain_post(h, true, true)) return rc;
         if (np > h->h_rows_cap) {
             cudaFreeHost(h->h_rows); cudaFreeHost(h->h_pstat);
             h->h_rows = nullptr; h->h_pstat = nullptr; h->h_rows_cap = 0;
@@ -1286,33 +1326,21 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
             h->h_rows_cap = np;
         }
         CU_CHECK(cudaMemcpyAsync(h->h_pstat, h->d_pstat, np * sizeof(PairStat), cudaMemcpyDeviceToHost, st));
+        h->h_pstat_first = first;
     }
     CU_CHECK(cudaStreamSynchronize(st));
     if (derr) { set_error("multi-hit list: capacity exceeded for read " + std::to_string(derr - 1)); return FQB_ERR_LIMIT; }
-    std::vector<MultiOut> mo(ctr[1]);
+    auto mo_p = std::make_shared<std::vector<MultiOut>>(ctr[1]);
+    std::vector<MultiOut> &mo = *mo_p;
     if (ctr[1]) CU_CHECK(cudaMemcpy(mo.data(), h->d_multi_out, (size_t)ctr[1] * sizeof(MultiOut), cudaMemcpyDeviceToHost));
     std::sort(mo.begin(), mo.end(), [](const MultiOut &a, const MultiOut &b) { return a.read != b.read ? a.read < b.read : a.j < b.j; });
-    std::vector<XaHit> xa(mo.size());
+    auto xa_p = std::make_shared<std::vector<XaHit>>(mo.size());
     for (size_t i = 0; i < mo.size(); ++i) {
-        XaHit &x = xa[i];
+        XaHit &x = (*xa_p)[i];
         x.pos = mo[i].pos; x.strand = mo[i].strand; x.gap = mo[i].gap; x.mm = mo[i].mm; x.has_cigar = mo[i].has_cigar; x.n_cigar = mo[i].n_cigar;
         memcpy(x.cigar, mo[i].cigar, sizeof x.cigar);
     }
-    auto xa_of = [&](uint32_t r, int &n) -> const XaHit * {
-        auto lo = std::lower_bound(mo.begin(), mo.end(), r, [](const MultiOut &a, uint32_t v) { return a.read < v; });
-        auto hi = lo;
-        while (hi != mo.end() && hi->read == r) ++hi;
-        n = (int)(hi - lo);
-        return n ? &xa[(size_t)(lo - mo.begin())] : nullptr;
-    };
-    // records are formatted by several host threads over contiguous slices of the batch and written in order
     const auto t_dev = std::chrono::steady_clock::now();
-    const uint64_t first = h->pairs_seen - (h->stats_done ? np : 0);
-    unsigned nthr = std::thread::hardware_concurrency();
-    if (nthr < 1) nthr = 1;
-    if (nthr > 16) nthr = 16;
-    if (np < 4096) nthr = 1;
-    std::vector<std::string> parts(nthr);
     const int par = (int)(h->bam_batches & 1);
     if (!h->single_end) {
         if (h->rseq_stride != (size_t)stride) { for (auto &a : h->rseq_shadow) for (auto &b : a) b.clear(); h->rseq_stride = (size_t)stride; }
@@ -1320,6 +1348,25 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
             h->rseq_shadow[par][e].resize((size_t)(FQB_BATCH_PAIRS > np ? FQB_BATCH_PAIRS : np) * stride, 0);
     }
     ++h->bam_batches;
+    const unsigned n_multi_hits = ctr[1];
+    // host phase: records are formatted by several host threads over contiguous slices of the batch and handed to the BGZF
+    // writer in order.  names / bases / quals must stay valid until the next fqb_stats_emit / fqb_bam_emit / fqb_stats_finish /
+    // fqb_bam_close call on this handle returns.
+    auto host_phase = [=]() {
+    const std::vector<MultiOut> &mo = *mo_p;
+    const std::vector<XaHit> &xa = *xa_p;
+    auto xa_of = [&](uint32_t r, int &n) -> const XaHit * {
+        auto lo = std::lower_bound(mo.begin(), mo.end(), r, [](const MultiOut &a, uint32_t v) { return a.read < v; });
+        auto hi = lo;
+        while (hi != mo.end() && hi->read == r) ++hi;
+        n = (int)(hi - lo);
+        return n ? &xa[(size_t)(lo - mo.begin())] : nullptr;
+    };
+    unsigned nthr = std::thread::hardware_concurrency();
+    if (nthr < 1) nthr = 1;
+    if (nthr > 16) nthr = 16;
+    if (np < 4096) nthr = 1;
+    std::vector<std::string> parts(nthr);
     auto work = [&](unsigned t) {
         std::string &o = parts[t];
         const size_t lo = np * t / nthr, hi = np * (t + 1) / nthr;
@@ -1364,20 +1411,24 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
     for (auto &o : parts) { total += o.size(); h->bam.write_owned(std::move(o)); }
     if (getenv("FQB_BAM_DEBUG")) {
         const auto t_end = std::chrono::steady_clock::now();
-        fprintf(stderr, "bam_emit: %zu pairs, %u multi hits, %zu bytes, threads %u; device+copies %.1f ms, format %.1f ms, bgzf %.1f ms\n", np, ctr[1], total, nthr,
+        fprintf(stderr, "bam_emit: %zu pairs, %u multi hits, %zu bytes, threads %u; device+copies %.1f ms, format %.1f ms, hand-over %.1f ms\n", np, n_multi_hits, total, nthr,
                 std::chrono::duration<double, std::milli>(t_dev - t_begin).count(), std::chrono::duration<double, std::milli>(t_fmt - t_dev).count(),
                 std::chrono::duration<double, std::milli>(t_end - t_fmt).count());
     }
+    };
+    if (emit_inline()) { host_phase(); return drain_post(h, true, true); }
+    h->post_bam = std::async(std::launch::async, host_phase);
     return FQB_OK;
 }
 
 int fqb_bam_close(fqb_handle *h) {
     if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
     if (!h->bam_open) return FQB_OK;
+    const int rc = drain_post(h, true, true);
     h->bam_open = false;
     std::string err;
     if (!h->bam.close(err)) { set_error(err); return FQB_ERR_IO; }
-    return FQB_OK;
+    return rc;
 }
 
 // The whole per-batch body of BwtMapper::PairEndMapper up to (not including) the statistics loop.

@@ -179,9 +179,11 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
     else if (fqb_feeder_open(fq1.c_str(), 0, &fd[0]) != FQB_OK || fqb_feeder_open(fq2.c_str(), 0, &fd[1]) != FQB_OK) error("Open fastq failed: %s", fqb_last_error());
     if (fqb_stats_begin_file(h_, prefix_.c_str(), fq1.c_str(), fq2.c_str()) != FQB_OK) error("%s", fqb_last_error());
     const int stride = opt->read_len < FQB_MAX_READ_LEN ? opt->read_len : FQB_MAX_READ_LEN, cap = FQB_BATCH_PAIRS, name_stride = 64;
-    // three pinned batches in flight: the GPU maps batch N, the copy stream uploads batch N+1, the reader threads decode batch N+2
-    // (the two IO workers of the reference, src/BwtMapper.cpp:1969-1982, become one reader thread per end)
-    struct Buf { uint8_t *b[2], *q[2]; int32_t *l[2]; char *nm[2]; int n[2]; } bufs[3];
+    // four pinned batches in flight: the GPU maps batch N, the copy stream uploads batch N+1, the feeder decodes batch N+2, and
+    // the library's writer threads still format the InsertSizeTable lines and BAM records of batch N-1 from its reads and names
+    // (the two IO workers of the reference, src/BwtMapper.cpp:1969-1982, become one feeder per end)
+    constexpr int kBufs = 4;
+    struct Buf { uint8_t *b[2], *q[2]; int32_t *l[2]; char *nm[2]; int n[2]; } bufs[kBufs];
     for (auto &B : bufs)
         for (int e = 0; e < 2; ++e) {
             B.b[e] = (uint8_t *)fqb_host_alloc((size_t)cap * stride); B.q[e] = (uint8_t *)fqb_host_alloc((size_t)cap * stride);
@@ -208,7 +210,7 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
     load(bufs[0]);
     if (good(bufs[0])) load(bufs[1]);
     while (good(bufs[cur])) {
-        Buf &B = bufs[cur], &N1 = bufs[(cur + 1) % 3], &N2 = bufs[(cur + 2) % 3];
+        Buf &B = bufs[cur], &N1 = bufs[(cur + 1) % kBufs], &N2 = bufs[(cur + 2) % kBufs];
         if (B.n[0] != B.n[1]) error("Abort, please make sure input pair of fastq files are in the same order!");
         if (good(N1) && N1.n[0] == N1.n[1] &&
             fqb_prefetch_pairs(h_, N1.n[0], stride, N1.b[0], N1.q[0], N1.l[0], N1.b[1], N1.q[1], N1.l[1]) != FQB_OK) error("%s", fqb_last_error());
@@ -220,9 +222,10 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
         FSC.NumRead += 2LL * B.n[0];
         if (FSC.NumRead % FQB_BATCH_PAIRS == 0) fprintf(stderr, "NOTICE - %lld sequences are processed.\n", FSC.NumRead);
         next.join();
-        cur = (cur + 1) % 3;
+        cur = (cur + 1) % kBufs;
     }
     notice("%lld sequences are loaded.", FSC.NumRead);
+    if (fqb_emit_sync(h_) != FQB_OK) error("%s", fqb_last_error());      // joins the writer threads before the buffers go
     for (auto &B : bufs) for (int e = 0; e < 2; ++e) { fqb_host_free(B.b[e]); fqb_host_free(B.q[e]); fqb_host_free(B.l[e]); fqb_host_free(B.nm[e]); }
     r[0].close(); r[1].close();
     fqb_feeder_close(fd[0]); fqb_feeder_close(fd[1]);
@@ -235,7 +238,8 @@ bool BwtMapper::SingleEndMapper(const std::string &fq1, const gap_opt_t *opt, Fi
     if (fqb_feeder_open(fq1.c_str(), 0, &fd) != FQB_OK) error("Open fastq failed: %s", fqb_last_error());
     if (fqb_stats_begin_file(h_, prefix_.c_str(), fq1.c_str(), fq1.c_str()) != FQB_OK) error("%s", fqb_last_error());
     const int stride = opt->read_len < FQB_MAX_READ_LEN ? opt->read_len : FQB_MAX_READ_LEN, cap = FQB_BATCH_PAIRS, name_stride = 64;
-    struct Buf { uint8_t *b, *q; int32_t *l; char *nm; int n; } bufs[3];
+    constexpr int kBufs = 4;               // see PairEndMapper
+    struct Buf { uint8_t *b, *q; int32_t *l; char *nm; int n; } bufs[kBufs];
     for (auto &B : bufs) {
         B.b = (uint8_t *)fqb_host_alloc((size_t)cap * stride); B.q = (uint8_t *)fqb_host_alloc((size_t)cap * stride);
         B.l = (int32_t *)fqb_host_alloc((size_t)cap * 4); B.nm = (char *)fqb_host_alloc((size_t)cap * name_stride);
@@ -251,7 +255,7 @@ bool BwtMapper::SingleEndMapper(const std::string &fq1, const gap_opt_t *opt, Fi
     load(bufs[0]);
     if (bufs[0].n > 0) load(bufs[1]);
     while (bufs[cur].n > 0) {
-        Buf &B = bufs[cur], &N1 = bufs[(cur + 1) % 3], &N2 = bufs[(cur + 2) % 3];
+        Buf &B = bufs[cur], &N1 = bufs[(cur + 1) % kBufs], &N2 = bufs[(cur + 2) % kBufs];
         if (N1.n > 0 && fqb_prefetch_pairs(h_, N1.n, stride, N1.b, N1.q, N1.l, nullptr, nullptr, nullptr) != FQB_OK) error("%s", fqb_last_error());
         std::thread next([&]() { if (N1.n > 0) load(N2); else N2.n = 0; });
         if (fqb_align_pairs(h_, B.n, stride, B.b, B.q, B.l, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr) != FQB_OK) error("%s", fqb_last_error());
@@ -260,9 +264,10 @@ bool BwtMapper::SingleEndMapper(const std::string &fq1, const gap_opt_t *opt, Fi
         if (bam_out_ && fqb_bam_emit(h_, B.nm, name_stride, B.b, B.q, nullptr, nullptr, stride) != FQB_OK) error("%s", fqb_last_error());
         FSC.NumRead += B.n;
         next.join();
-        cur = (cur + 1) % 3;
+        cur = (cur + 1) % kBufs;
     }
     notice("%lld sequences are loaded.", FSC.NumRead);
+    if (fqb_emit_sync(h_) != FQB_OK) error("%s", fqb_last_error());
     for (auto &B : bufs) { fqb_host_free(B.b); fqb_host_free(B.q); fqb_host_free(B.l); fqb_host_free(B.nm); }
     fqb_feeder_close(fd);
     return 0;
