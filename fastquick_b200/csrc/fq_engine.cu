@@ -148,8 +148,8 @@ struct fqb_handle {
     std::string isize_table_path;
     std::vector<std::pair<uint64_t, uint64_t>> isize_table_idx;   // (first global pair, bytes) of every emitted batch, in emission order
     fqb_read_t *h_rows = nullptr; PairStat *h_pstat = nullptr; size_t h_rows_cap = 0;     // pinned staging of fqb_stats_emit
-    // Host phases (formatting + writing) of the last fqb_stats_emit / fqb_bam_emit: they run on their own thread while the
-    // caller submits the next batch, and are joined before their staging is written again (drain_post)
+    // Host phases (formatting + writing) of the last fqb_stats_emit / fqb_bam_emit when FQB_ASYNC_EMIT is set: they run on
+    // their own thread while the caller submits the next batch, and are joined before their staging is written again (drain_post)
     std::future<void> post_stats, post_bam;
     std::mutex post_m; std::string post_err;
     uint64_t h_pstat_first = ~0ull;        // first global pair of the batch h_pstat holds
@@ -758,7 +758,10 @@ static int drain_post(fqb_handle *h, bool stats, bool bam) {
     if (!h->post_err.empty()) { set_error(h->post_err); h->post_err.clear(); return FQB_ERR_IO; }
     return FQB_OK;
 }
-static bool emit_inline() { static const bool v = getenv("FQB_SYNC_EMIT") != nullptr; return v; }
+// Host phases run inline unless FQB_ASYNC_EMIT is set: on the 16-core GPU box the threaded variant lost to the inline one
+// (text + BAM 7.1e5 against 9.5e5 pairs/s, BGZF + BAM 4.4e5 against 9.4e5: the formatter threads take the cores the feeder's
+// inflate / parse workers need), so it stays an option for hosts with cores to spare.
+static bool emit_inline() { static const bool v = getenv("FQB_ASYNC_EMIT") == nullptr; return v; }
 
 static int close_current_file(fqb_handle *h) {
     if (int rc = drain_post(h, true, true)) return rc;

@@ -180,7 +180,7 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
     if (fqb_stats_begin_file(h_, prefix_.c_str(), fq1.c_str(), fq2.c_str()) != FQB_OK) error("%s", fqb_last_error());
     const int stride = opt->read_len < FQB_MAX_READ_LEN ? opt->read_len : FQB_MAX_READ_LEN, cap = FQB_BATCH_PAIRS, name_stride = 64;
     // four pinned batches in flight: the GPU maps batch N, the copy stream uploads batch N+1, the feeder decodes batch N+2, and
-    // the library's writer threads still format the InsertSizeTable lines and BAM records of batch N-1 from its reads and names
+    // with FQB_ASYNC_EMIT the library's writer threads still format the InsertSizeTable lines and BAM records of batch N-1
     // (the two IO workers of the reference, src/BwtMapper.cpp:1969-1982, become one feeder per end)
     constexpr int kBufs = 4;
     struct Buf { uint8_t *b[2], *q[2]; int32_t *l[2]; char *nm[2]; int n[2]; } bufs[kBufs];

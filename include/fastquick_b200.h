@@ -173,11 +173,12 @@ int fqb_stats_open(fqb_handle *h, const char *index_prefix);
 int fqb_stats_begin_file(fqb_handle *h, const char *out_prefix, const char *fastq1, const char *fastq2);
 int fqb_stage_stats(fqb_handle *h);
 int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride);
-/* fqb_stats_emit and fqb_bam_emit copy what they need from the device, then format and write on threads of their own while
- * the caller submits the next batch.  The host arrays passed to them (names, bases, quals) must stay untouched until the
- * next fqb_stats_emit on the handle returns (it joins both), or fqb_emit_sync / fqb_stats_finish / fqb_stats_close_table /
- * fqb_bam_close / fqb_stats_begin_file does.  A write error met by those threads is returned by the call that joins them.
- * FQB_SYNC_EMIT=1 in the environment runs the host phases inline. */
+/* fqb_stats_emit and fqb_bam_emit copy what they need from the device, then format and write.  With FQB_ASYNC_EMIT=1 in the
+ * environment that host phase runs on threads of its own while the caller submits the next batch (off by default: it only
+ * pays on hosts with idle cores); the host arrays passed to the two calls (names, bases, quals) must then stay untouched
+ * until the next fqb_stats_emit on the handle returns (it joins both), or fqb_emit_sync / fqb_stats_finish /
+ * fqb_stats_close_table / fqb_bam_close / fqb_stats_begin_file does, and a write error met by those threads is returned by
+ * the call that joins them.  fqb_emit_sync is a no-op otherwise. */
 int fqb_emit_sync(fqb_handle *h);
 int fqb_stats_finish(fqb_handle *h, const char *out_prefix);
 /* Sharded runs (one handle per GPU, batches dealt round-robin): each handle writes the InsertSizeTable lines

@@ -17,14 +17,18 @@ for f in fq:
 print("fastq written %.1fs" % (time.time() - t0), flush=True)
 CLI = os.path.join(fx.REPO, "fastquick_b200", "FASTQuick_b200")
 runs = [("b200 %s%s" % (k, " +bam" if bam else ""), CLI, inputs[k], [] if bam else ["--sam_out"]) for k in ("gzip", "bgzf", "text") for bam in (False, True)]
+if "--emit-modes" in sys.argv:          # host phases of the emit calls inline (default) against FQB_ASYNC_EMIT=1 (own threads), BAM runs only
+    runs = [(tag + (" sync-emit" if sync else " async-emit"), exe, files, extra + (["#sync"] if sync else [])) for tag, exe, files, extra in runs if "+bam" in tag for sync in (True, False)]
 if "--ref" in sys.argv: runs.append(("ref gzip +bam", fx.REF_BIN, fq, []))
 for tag, exe, files, extra in runs:
     out = os.path.join(idx.dir, "thr_out")
-    cmd = [exe, "align", "--fastq_1", files[0], "--fastq_2", files[1], "--index_prefix", idx.prefix[:-len(".FASTQuick.fa")], "--out_prefix", out, "--t", str(os.cpu_count()), "--q", "15"] + extra
+    env = dict(os.environ)
+    if "--emit-modes" in sys.argv and "#sync" not in extra: env["FQB_ASYNC_EMIT"] = "1"
+    cmd = [exe, "align", "--fastq_1", files[0], "--fastq_2", files[1], "--index_prefix", idx.prefix[:-len(".FASTQuick.fa")], "--out_prefix", out, "--t", str(os.cpu_count()), "--q", "15"] + [x for x in extra if x != "#sync"]
     best = None
     for rep in range(3):                 # the boxes are shared: best of three
         t0 = time.time()
-        r = subprocess.run(cmd, cwd=idx.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        r = subprocess.run(cmd, cwd=idx.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
         dt = time.time() - t0
         sec = [l for l in r.stdout.splitlines() if "Processed Pair End mapping" in l]
         t_map = float(sec[-1].split(" in ")[1].split()[0]) if sec else float("nan")
