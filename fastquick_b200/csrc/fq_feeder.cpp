@@ -5,7 +5,9 @@
 //   producer thread   file -> text blocks of ~4 MiB, in order.  Three sources:
 //                       BGZF (bgzip / bcl2fastq output: gzip members <= 64 KiB that carry their own size) - members
 //                            are inflated independently by the worker pool, 64 at a time;
-//                       any other gzip stream - one zlib inflate() stream (inherently serial), multi-member aware;
+//                       any other gzip stream - inherently serial: the file is memory-mapped and decoded by this
+//                            library's own inflate loop (fq_inflate.cpp), each member's CRC-32 and length checked;
+//                            zlib's inflate() when the file cannot be mapped or FQB_GZIP_ZLIB is set;
 //                       plain text.
 //   fill()            walks the blocks, finds the record boundaries (memchr), cuts the text into runs of whole records
 //                     and hands each run to the worker pool together with the batch slot of its first record;
@@ -13,6 +15,8 @@
 //   worker pool       parses runs into the batch: bases, qualities, lengths, names (what the GPU prep kernel and the
 //                     writers consume); shared by all open feeders.
 // The nt4 encoding, trimming and the k-mer filter of bwa_read_seq_with_hash_dev stay on the GPU (prep_kernel).
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -30,6 +34,7 @@
 
 #include "../../include/fastquick_b200.h"
 #include "fq_common.h"
+#include "fq_inflate.h"
 
 namespace fqb {
 namespace {
@@ -90,7 +95,7 @@ struct Latch {
     void wait() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&]() { return pending == 0; }); }
 };
 
-struct Block { std::vector<char> text; size_t n = 0; };
+struct Block { std::vector<char> text; size_t off = 0, n = 0; };       // the text is [off, off + n)
 using BlockPtr = std::shared_ptr<Block>;
 
 struct Batch {
@@ -103,6 +108,71 @@ struct Failure {
     std::mutex m; std::string msg; std::atomic<bool> set{false};
     void raise(const std::string &s) { std::lock_guard<std::mutex> l(m); if (!set.load()) { msg = s; set.store(true); } }
 };
+
+BlockPtr new_block(size_t cap) {
+    BlockPtr b = std::make_shared<Block>();
+    b->text.resize(cap);
+    return b;
+}
+
+// A whole gzip file (one or more members, zero padding behind the last one tolerated as gzip(1) does) held in memory
+// -> text blocks of about block_bytes, through fqb::Inflater.  Each block starts with the last 32 KiB of the block
+// before it (the deflate window), so a match never leaves its block.  Every member's CRC-32 and length are checked.
+// false = corrupt input (err set) or push() refused a block (err empty).
+bool gunzip_blocks(const uint8_t *p, const uint8_t *const end, size_t block_bytes, const std::function<bool(BlockPtr)> &push, std::string &err) {
+    constexpr size_t W = Inflater::kWindow;
+    if (block_bytes < 2 * Inflater::kOutSlack) block_bytes = 2 * Inflater::kOutSlack;
+    std::unique_ptr<Inflater> inf(new Inflater());
+    BlockPtr b = new_block(W + block_bytes);
+    b->off = W;
+    uint8_t *out = (uint8_t *)b->text.data() + W, *out_end = (uint8_t *)b->text.data() + b->text.size();
+    auto hand_over = [&](const uint8_t *floor, const uint8_t **new_floor) -> bool {
+        b->n = (size_t)(out - ((uint8_t *)b->text.data() + W));
+        const size_t hist = std::min(W, (size_t)(out - floor));
+        BlockPtr nb = new_block(W + block_bytes);
+        nb->off = W;
+        memcpy(nb->text.data() + W - hist, out - hist, hist);
+        const bool ok = b->n == 0 || push(b);
+        b = nb;
+        out = (uint8_t *)b->text.data() + W; out_end = (uint8_t *)b->text.data() + b->text.size();
+        *new_floor = out - hist;
+        return ok;
+    };
+    while (p < end) {
+        if (end - p < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || (p[3] & 0xe0)) {
+            for (const uint8_t *q = p; q < end; ++q) if (*q) { err = "corrupt gzip stream: no member header where one is due"; return false; }
+            break;
+        }
+        const unsigned flg = p[3];
+        const uint8_t *q = p + 10;
+        if (flg & 4) q += 2 + ((size_t)q[0] | ((size_t)q[1] << 8));                       // FEXTRA (end - p >= 18 covers the length field)
+        if (flg & 8) { while (q < end && *q) ++q; ++q; }                                  // FNAME
+        if (flg & 16) { while (q < end && *q) ++q; ++q; }                                 // FCOMMENT
+        if (flg & 2) q += 2;                                                              // FHCRC
+        if (q >= end) { err = "corrupt gzip stream: truncated member header"; return false; }
+        inf->reset(q, end);
+        const uint8_t *floor = out, *chunk = out;
+        uLong crc = crc32(0L, Z_NULL, 0);
+        uint64_t isize = 0;
+        for (;;) {
+            const Inflater::Status s = inf->run(out, out_end, floor);
+            if (s == Inflater::kError) { err = std::string("corrupt gzip stream: ") + inf->error(); return false; }
+            crc = crc32_z(crc, chunk, (size_t)(out - chunk));
+            isize += (uint64_t)(out - chunk);
+            if (s == Inflater::kStreamEnd) break;
+            if (!hand_over(floor, &floor)) return false;
+            chunk = out;
+        }
+        const uint8_t *t = inf->in_pos();
+        if (end - t < 8) { err = "corrupt gzip stream: truncated member"; return false; }
+        const uint32_t want_crc = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+        const uint32_t want_len = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+        if (want_crc != (uint32_t)crc || want_len != (uint32_t)isize) { err = "corrupt gzip stream: member checksum or length mismatch"; return false; }
+        p = t + 8;
+    }
+    b->n = (size_t)(out - ((uint8_t *)b->text.data() + W));
+    return b->n == 0 || push(b);
+}
 
 inline const char *line_end(const char *p, const char *end) {
     const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
@@ -188,7 +258,7 @@ public:
                     break;
                 }
             }
-            const char *base = cur_->text.data(), *end = base + cur_->n, *p = base + pos_;
+            const char *base = cur_->text.data() + cur_->off, *end = base + cur_->n, *p = base + pos_;
             if (!carry_.empty()) {                              // finish the record the previous block cut
                 int nl = 0; for (char c : carry_) nl += c == '\n';
                 const char *q = p;
@@ -266,29 +336,41 @@ private:
         { std::lock_guard<std::mutex> l(qm_); done_ = true; }
         qcv_.notify_all();
     }
-    static BlockPtr new_block(size_t cap = kBlockBytes) {
-        BlockPtr b = std::make_shared<Block>();
-        b->text.resize(cap);
-        return b;
-    }
 
     void produce() {
-        if (kind_ == 0) produce_text(); else if (kind_ == 1) produce_gzip(); else produce_bgzf();
+        if (kind_ == 0) produce_text();
+        else if (kind_ == 2) produce_bgzf();
+        else if (getenv("FQB_GZIP_ZLIB") || !produce_gzip_mapped()) produce_gzip();
         finish();
     }
     void produce_text() {
         for (;;) {
-            BlockPtr b = new_block();
+            BlockPtr b = new_block(kBlockBytes);
             b->n = fread(b->text.data(), 1, b->text.size(), fp_);
             if (b->n == 0) return;
             if (!push_block(b)) return;
         }
     }
+    // gzip stream from a memory-mapped file through gunzip_blocks().  false = the file could not be mapped and nothing
+    // has been produced.
+    bool produce_gzip_mapped() {
+        struct stat st;
+        if (fstat(fileno(fp_), &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 18) return false;
+        const size_t size = (size_t)st.st_size;
+        void *map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fileno(fp_), 0);
+        if (map == MAP_FAILED) return false;
+        madvise(map, size, MADV_SEQUENTIAL);
+        std::string err;
+        if (!gunzip_blocks((const uint8_t *)map, (const uint8_t *)map + size, kBlockBytes, [this](BlockPtr b) { return push_block(std::move(b)); }, err) && !err.empty())
+            fail_.raise(err);
+        munmap(map, size);
+        return true;
+    }
     void produce_gzip() {
         z_stream zs; memset(&zs, 0, sizeof(zs));
         if (inflateInit2(&zs, 31) != Z_OK) { fail_.raise("inflateInit2 failed"); return; }
         std::vector<unsigned char> in((size_t)1 << 20);
-        BlockPtr b = new_block();
+        BlockPtr b = new_block(kBlockBytes);
         zs.next_out = (Bytef *)b->text.data(); zs.avail_out = (uInt)b->text.size();
         bool eof = false, ok = true;
         while (ok && !eof) {
@@ -303,7 +385,7 @@ private:
                 if (zs.avail_out == 0) {
                     b->n = b->text.size();
                     if (!push_block(b)) { ok = false; break; }
-                    b = new_block();
+                    b = new_block(kBlockBytes);
                     zs.next_out = (Bytef *)b->text.data(); zs.avail_out = (uInt)b->text.size();
                 }
             }
@@ -429,5 +511,21 @@ int64_t fqb_feeder_fill(fqb_feeder *f, int32_t n_max, int32_t stride, uint8_t *b
 }
 
 void fqb_feeder_close(fqb_feeder *f) { delete f; }
+
+int fqb_gunzip(const uint8_t *gz, int64_t n_gz, uint8_t *out, int64_t cap, int32_t block_bytes, int64_t *n_out) {
+    if (!gz || n_gz < 0 || (!out && cap > 0) || cap < 0 || !n_out) { fqb::set_error("bad argument"); return FQB_ERR_ARG; }
+    int64_t n = 0;
+    bool fits = true;
+    std::string err;
+    const bool ok = fqb::gunzip_blocks(gz, gz + n_gz, block_bytes > 0 ? (size_t)block_bytes : fqb::kBlockBytes, [&](fqb::BlockPtr b) {
+        if (n + (int64_t)b->n > cap) { fits = false; return false; }
+        memcpy(out + n, b->text.data() + b->off, b->n);
+        n += (int64_t)b->n;
+        return true;
+    }, err);
+    *n_out = n;
+    if (!ok) { fqb::set_error(fits ? err : "output buffer too small"); return fits ? FQB_ERR_IO : FQB_ERR_ARG; }
+    return FQB_OK;
+}
 
 }  // extern "C"

@@ -222,7 +222,8 @@ int fqb_stage_counters(fqb_handle *h, uint64_t *out4);
  * FASTQ file -> the fixed-stride batches fqb_align_pairs / fqb_prefetch_pairs take, decoded in parallel.
  * Replaces the record-by-record kseq_read3_fpc (libbwa/kseq.h:327-370) loop of bwa_read_seq_with_hash_dev
  * (src/BwtMapper.cpp:476-613): a producer thread turns the file into text blocks (BGZF members are inflated
- * independently by a worker pool; any other gzip stream by one zlib stream; plain text is read as is) and the
+ * independently by a worker pool; any other gzip stream is memory-mapped and decoded serially by the library's
+ * own inflate loop, zlib's when the file cannot be mapped or FQB_GZIP_ZLIB is set; plain text is read as is) and the
  * pool parses runs of whole records straight into the caller's (pinned) batch.  n_threads <= 0 = one per
  * host core, at most 16; the pool is shared by all feeders of the process.
  * fill: up to n_max records; bases padded with 'N' and qualities with '!' to `stride`; names cut at the first
@@ -234,6 +235,10 @@ int fqb_feeder_format(const fqb_feeder *f);         /* 0 plain text, 1 gzip stre
 int64_t fqb_feeder_fill(fqb_feeder *f, int32_t n_max, int32_t stride, uint8_t *bases, uint8_t *quals,
                         int32_t *lens, char *names, int32_t name_stride);
 void fqb_feeder_close(fqb_feeder *f);
+/* The feeder's gzip-stream path on a buffer: all members of gz[0..n_gz) decoded into out[0..cap), through text
+ * blocks of block_bytes (<= 0: the feeder's 4 MiB) exactly as the feeder chains them; *n_out = bytes written.
+ * FQB_ERR_IO on a corrupt stream (CRC-32 / length / code checks), FQB_ERR_ARG if cap is too small. */
+int fqb_gunzip(const uint8_t *gz, int64_t n_gz, uint8_t *out, int64_t cap, int32_t block_bytes, int64_t *n_out);
 void *fqb_host_alloc(size_t bytes);                /* pinned host memory for the feeder's batches */
 void fqb_host_free(void *p);
 uint64_t fqb_launch_count(const fqb_handle *h);   /* kernels launched by this handle so far */

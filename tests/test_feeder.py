@@ -124,3 +124,74 @@ def test_feeder_errors(tmp_path):
     open(str(tmp_path / "bad.fq.gz"), "wb").write(gzip.compress(good)[:-40] + b"x" * 40)
     with pytest.raises(RuntimeError):
         _read_all(str(tmp_path / "bad.fq.gz"), 100, 64)
+
+
+def _gunzip(blob, cap, block_bytes=0):
+    lib = fx.host_lib()
+    lib.fqb_gunzip.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int64)]
+    out = np.zeros(max(cap, 1), np.uint8)
+    n = C.c_int64()
+    rc = lib.fqb_gunzip(blob, len(blob), out.ctypes.data, cap, block_bytes, C.byref(n))
+    return rc, bytes(out[:n.value])
+
+
+@pytest.fixture(scope="module")
+def payloads():
+    rng = np.random.default_rng(5)
+    p = {
+        "empty": b"",
+        "tiny": b"hello",
+        "random": rng.integers(0, 256, 300000, dtype=np.uint8).tobytes(),               # stored blocks
+        "zeros": bytes(600000),                                                         # distance 1, length 258
+        "period3": b"abc" * 100000, "period7": b"abcdefg" * 60000,                      # overlapping short-distance copies
+        "text": b"".join(b"line %d of some text, value=%d\n" % (i, i * i) for i in range(40000)),
+        "dna": np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 1000000)].tobytes(),  # short matches at long distances
+    }
+    p["mixed"] = p["random"][:70000] + p["text"][:200000] + p["zeros"][:100000] + p["dna"][:300000] + p["random"][:5000]
+    return p
+
+
+def test_inflate_matches_zlib(payloads):
+    """fqb::Inflater (the serial gzip path of the feeder) against zlib's own output: every deflate block type, code
+    shape and copy case, decoded through text blocks small enough that the stop/resume and window hand-over run often."""
+    for name, data in payloads.items():
+        blobs = [gzip.compress(data, lvl) for lvl in (0, 1, 6, 9)]
+        for strategy in (zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
+            co = zlib.compressobj(6, zlib.DEFLATED, 31, 9, strategy)
+            blobs.append(co.compress(data) + co.flush())
+        co = zlib.compressobj(6, zlib.DEFLATED, 31)                                     # sync flushes: empty stored blocks mid-stream
+        blobs.append(b"".join(co.compress(data[o:o + 50000]) + co.flush(zlib.Z_SYNC_FLUSH) for o in range(0, len(data), 50000)) + co.flush())
+        for k, blob in enumerate(blobs):
+            for block_bytes in (0, 640, 4096, 65536):
+                rc, out = _gunzip(blob, len(data), block_bytes)
+                assert rc == 0 and out == data, (name, k, block_bytes, fx.host_lib().fqb_last_error())
+    whole = b"".join(payloads.values())
+    blob = b"".join(gzip.compress(d, 6) for d in payloads.values()) + bytes(512)       # members back to back + zero padding
+    rc, out = _gunzip(blob, len(whole), 5000)
+    assert rc == 0 and out == whole
+
+
+def test_inflate_rejects_corrupt_streams(payloads):
+    data = payloads["text"]
+    blob = gzip.compress(data, 6)
+    rng = np.random.default_rng(9)
+    for _ in range(200):                                                                # single bit flips: never accepted
+        b = bytearray(blob)
+        b[int(rng.integers(10, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        rc, out = _gunzip(bytes(b), len(data) + 100000, 4096)
+        assert rc != 0
+    for cut in (5, 17, 18, 30, 100, len(blob) - 9, len(blob) - 8, len(blob) - 1):       # truncations
+        assert _gunzip(blob[:cut], len(data), 0)[0] != 0
+    assert _gunzip(blob + b"trailing garbage", len(data), 0)[0] != 0
+    assert _gunzip(blob, 1000, 0)[0] != 0                                               # output buffer too small
+
+
+def test_feeder_gzip_zlib_switch(tmp_path, monkeypatch):
+    """FQB_GZIP_ZLIB=1 keeps zlib's inflate for gzip streams; both paths give the same records."""
+    recs = _records(20000, 13)
+    p = str(tmp_path / "z.fq.gz")
+    open(p, "wb").write(gzip.compress(_text(recs), 6))
+    _, a = _read_all(p, 100, 7777)
+    monkeypatch.setenv("FQB_GZIP_ZLIB", "1")
+    _, b = _read_all(p, 100, 7777)
+    assert a == b == _expect(recs, 100)
