@@ -446,22 +446,23 @@ private:
                     const unsigned char *t = g->comp.data() + mb.first + mb.second - 4;
                     total += (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);     // ISIZE
                 }
-                g->out = new_block(std::max<size_t>(total, 1));
-                z_stream zs; memset(&zs, 0, sizeof(zs));
-                bool ok = inflateInit2(&zs, -15) == Z_OK;
+                g->out = new_block(total + Inflater::kOutSlack);
+                std::unique_ptr<Inflater> inf(new Inflater());
+                uint8_t *const base = (uint8_t *)g->out->text.data(), *const out_end = base + g->out->text.size();
+                bool ok = true;
                 size_t o = 0;
-                for (auto &mb : g->member) {
-                    if (!ok) break;
-                    const unsigned char *h = g->comp.data() + mb.first;
+                for (auto &mb : g->member) {                    // each member: raw deflate between the header and CRC32 + ISIZE
+                    const unsigned char *h = g->comp.data() + mb.first, *t = h + mb.second - 8;
                     const size_t xlen = (size_t)h[10] | ((size_t)h[11] << 8);
-                    zs.next_in = const_cast<Bytef *>(h + 12 + xlen); zs.avail_in = (uInt)(mb.second - 12 - xlen - 8);
-                    zs.next_out = (Bytef *)g->out->text.data() + o; zs.avail_out = (uInt)(total - o);
-                    const int rc = inflate(&zs, Z_FINISH);
-                    if (rc != Z_STREAM_END) { ok = false; break; }
-                    o = total - zs.avail_out;
-                    ok = inflateReset(&zs) == Z_OK;
+                    if (12 + xlen + 8 > mb.second) { ok = false; break; }
+                    const uint32_t want_crc = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+                    const uint32_t want_len = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+                    uint8_t *out = base + o;
+                    inf->reset(h + 12 + xlen, t);
+                    if (inf->run(out, out_end, base + o) != Inflater::kStreamEnd || (size_t)(out - (base + o)) != want_len ||
+                        (uint32_t)crc32_z(crc32(0L, Z_NULL, 0), base + o, want_len) != want_crc) { ok = false; break; }
+                    o += want_len;
                 }
-                inflateEnd(&zs);
                 if (!ok || o != total) fail->raise("corrupt BGZF member");
                 g->out->n = ok ? o : 0;
                 { std::lock_guard<std::mutex> l(g->m); g->ready = true; }

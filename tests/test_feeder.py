@@ -195,3 +195,17 @@ def test_feeder_gzip_zlib_switch(tmp_path, monkeypatch):
     monkeypatch.setenv("FQB_GZIP_ZLIB", "1")
     _, b = _read_all(p, 100, 7777)
     assert a == b == _expect(recs, 100)
+
+
+def test_feeder_bgzf_member_checks(tmp_path):
+    """A BGZF member is accepted only if it inflates to exactly ISIZE bytes whose CRC-32 is the stored one."""
+    recs = _records(2000, 17)
+    blob = bytearray(_bgzf(_text(recs), block=20000))
+    size0 = (blob[16] | blob[17] << 8) + 1                                              # first member
+    for tag, at, delta in (("payload", 18 + 40, 0x10), ("crc", size0 - 8, 1), ("isize", size0 - 4, 1)):
+        b = bytearray(blob)
+        b[at] ^= delta
+        p = str(tmp_path / (tag + ".fq.gz"))
+        open(p, "wb").write(bytes(b))
+        with pytest.raises(RuntimeError, match="BGZF"):
+            _read_all(p, 100, 512)
