@@ -23,11 +23,14 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <deque>
 #include <functional>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -95,7 +98,48 @@ struct Latch {
     void wait() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&]() { return pending == 0; }); }
 };
 
-struct Block { std::vector<char> text; size_t off = 0, n = 0; };       // the text is [off, off + n)
+// Text blocks come from a free list: a fresh 4 MiB allocation costs its page faults (and a zero fill) every time, which
+// on the serial gzip path is paid by the one thread that sets the pace.
+class BufferPool {
+public:
+    static constexpr size_t kBufBytes = kBlockBytes + 32768 + 1024;       // every request of the feeder fits
+    static constexpr size_t kKeep = 48;                                   // buffers kept for reuse (~200 MiB at most)
+    static BufferPool &get() { static BufferPool *p = new BufferPool(); return *p; }
+    char *take(size_t cap, bool &pooled) {
+        pooled = cap <= kBufBytes;
+        if (pooled) {
+            std::lock_guard<std::mutex> l(m_);
+            if (!free_.empty()) { char *p = free_.back(); free_.pop_back(); return p; }
+        }
+        char *p = (char *)malloc(pooled ? kBufBytes : cap);
+        if (!p) throw std::bad_alloc();
+        return p;
+    }
+    void give(char *p, bool pooled) {
+        if (pooled) {
+            std::lock_guard<std::mutex> l(m_);
+            if (free_.size() < kKeep) { free_.push_back(p); return; }
+        }
+        free(p);
+    }
+private:
+    std::mutex m_;
+    std::vector<char *> free_;
+};
+
+struct Block {
+    struct Text {                                                          // the buffer: data() .. data() + size()
+        char *p = nullptr; size_t cap = 0;
+        char *data() const { return p; }
+        size_t size() const { return cap; }
+    } text;
+    size_t off = 0, n = 0;                                                 // the text is [off, off + n)
+    bool pooled = false;
+    Block() = default;
+    Block(const Block &) = delete;
+    Block &operator=(const Block &) = delete;
+    ~Block() { if (text.p) BufferPool::get().give(text.p, pooled); }
+};
 using BlockPtr = std::shared_ptr<Block>;
 
 struct Batch {
@@ -111,17 +155,24 @@ struct Failure {
 
 BlockPtr new_block(size_t cap) {
     BlockPtr b = std::make_shared<Block>();
-    b->text.resize(cap);
+    b->text.p = BufferPool::get().take(cap, b->pooled);
+    b->text.cap = cap;
     return b;
 }
 
 // A whole gzip file (one or more members, zero padding behind the last one tolerated as gzip(1) does) held in memory
 // -> text blocks of about block_bytes, through fqb::Inflater.  Each block starts with the last 32 KiB of the block
 // before it (the deflate window), so a match never leaves its block.  Every member's CRC-32 and length are checked.
-// false = corrupt input (err set) or push() refused a block (err empty).
-bool gunzip_blocks(const uint8_t *p, const uint8_t *const end, size_t block_bytes, const std::function<bool(BlockPtr)> &push, std::string &err) {
+// With submit (the worker pool) the checksums are computed off the calling thread, one job per block, and folded with
+// crc32_combine when the member ends.  false = corrupt input (err set) or push() refused a block (err empty).
+bool gunzip_blocks(const uint8_t *p, const uint8_t *const end, size_t block_bytes, const std::function<bool(BlockPtr)> &push,
+                   const std::function<void(std::function<void()>)> &submit, std::string &err) {
     constexpr size_t W = Inflater::kWindow;
     if (block_bytes < 2 * Inflater::kOutSlack) block_bytes = 2 * Inflater::kOutSlack;
+    struct CrcPart { BlockPtr keep; const uint8_t *p; size_t n; uLong crc; };
+    std::vector<std::shared_ptr<CrcPart>> parts;
+    Latch sums;
+    struct WaitAll { Latch &l; ~WaitAll() { l.wait(); } } wait_all{sums};       // no checksum job may outlive this frame
     std::unique_ptr<Inflater> inf(new Inflater());
     BlockPtr b = new_block(W + block_bytes);
     b->off = W;
@@ -152,17 +203,25 @@ bool gunzip_blocks(const uint8_t *p, const uint8_t *const end, size_t block_byte
         if (q >= end) { err = "corrupt gzip stream: truncated member header"; return false; }
         inf->reset(q, end);
         const uint8_t *floor = out, *chunk = out;
-        uLong crc = crc32(0L, Z_NULL, 0);
         uint64_t isize = 0;
+        parts.clear();
         for (;;) {
             const Inflater::Status s = inf->run(out, out_end, floor);
             if (s == Inflater::kError) { err = std::string("corrupt gzip stream: ") + inf->error(); return false; }
-            crc = crc32_z(crc, chunk, (size_t)(out - chunk));
-            isize += (uint64_t)(out - chunk);
+            if (out > chunk) {
+                auto part = std::make_shared<CrcPart>(CrcPart{b, chunk, (size_t)(out - chunk), 0});
+                parts.push_back(part);
+                if (submit) { sums.add(); Latch *l = &sums; submit([part, l]() { part->crc = crc32_z(crc32(0L, Z_NULL, 0), part->p, part->n); l->done(); }); }
+                else part->crc = crc32_z(crc32(0L, Z_NULL, 0), part->p, part->n);
+                isize += part->n;
+            }
             if (s == Inflater::kStreamEnd) break;
             if (!hand_over(floor, &floor)) return false;
             chunk = out;
         }
+        sums.wait();
+        uLong crc = crc32(0L, Z_NULL, 0);
+        for (auto &part : parts) crc = crc32_combine(crc, part->crc, (z_off_t)part->n);
         const uint8_t *t = inf->in_pos();
         if (end - t < 8) { err = "corrupt gzip stream: truncated member"; return false; }
         const uint32_t want_crc = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
@@ -341,6 +400,11 @@ private:
         if (kind_ == 0) produce_text();
         else if (kind_ == 2) produce_bgzf();
         else if (getenv("FQB_GZIP_ZLIB") || !produce_gzip_mapped()) produce_gzip();
+        if (getenv("FQB_FEEDER_DEBUG")) {                         // what the serial side of this file cost
+            struct timespec ts;
+            clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+            fprintf(stderr, "feeder: producer thread of a %s input used %.3f s of CPU\n", kind_ == 0 ? "text" : kind_ == 1 ? "gzip" : "BGZF", (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec);
+        }
         finish();
     }
     void produce_text() {
@@ -361,7 +425,8 @@ private:
         if (map == MAP_FAILED) return false;
         madvise(map, size, MADV_SEQUENTIAL);
         std::string err;
-        if (!gunzip_blocks((const uint8_t *)map, (const uint8_t *)map + size, kBlockBytes, [this](BlockPtr b) { return push_block(std::move(b)); }, err) && !err.empty())
+        if (!gunzip_blocks((const uint8_t *)map, (const uint8_t *)map + size, kBlockBytes, [this](BlockPtr b) { return push_block(std::move(b)); },
+                           getenv("FQB_AB") ? std::function<void(std::function<void()>)>() : [this](std::function<void()> f) { pool_->submit(std::move(f)); }, err) && !err.empty())
             fail_.raise(err);
         munmap(map, size);
         return true;
@@ -523,7 +588,7 @@ int fqb_gunzip(const uint8_t *gz, int64_t n_gz, uint8_t *out, int64_t cap, int32
         memcpy(out + n, b->text.data() + b->off, b->n);
         n += (int64_t)b->n;
         return true;
-    }, err);
+    }, nullptr, err);
     *n_out = n;
     if (!ok) { fqb::set_error(fits ? err : "output buffer too small"); return fits ? FQB_ERR_IO : FQB_ERR_ARG; }
     return FQB_OK;

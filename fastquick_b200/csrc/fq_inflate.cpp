@@ -9,8 +9,9 @@
 namespace fqb {
 namespace {
 
-// entry = value << 16 | flags << 8 | bits; the low nibble of flags is the number of extra bits of a length / distance,
-// or 1 on a literal entry that carries two bytes
+// entry = value << 16 | flags << 8 | bits to drop.  Length / distance entries drop their extra bits together with the
+// code and keep the code's own length in the low nibble of flags (value + the dropped bits shifted right by it is the
+// length / distance); on a literal entry that nibble is 1 when the entry carries two bytes.
 constexpr uint32_t kLit = 0x8000, kEob = 0x4000, kSub = 0x2000, kBad = 0x1000;
 
 const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -76,16 +77,22 @@ bool Inflater::build(const uint8_t *lens, int n, int root, uint32_t *tab, int ca
         for (int k = 0; k < (1 << sb); ++k) tab[used + k] = kBad | 1;
         used += 1 << sb;
     }
+    // final form of an entry whose code takes cl bits at this level: a length / distance entry drops its extra bits
+    // together with the code (low byte = cl + extra) and keeps cl in the flag nibble to shift the code away
+    auto finish = [kind](uint32_t e, int cl) -> uint32_t {
+        if (kind == 0 || (e & (kLit | kEob | kBad))) return e | (uint32_t)cl;
+        return (e & ~0xf00u) | ((uint32_t)cl << 8) | ((uint32_t)cl + ((e >> 8) & 15));
+    };
     for (int s = 0; s < n; ++s) {
         const int l = lens[s];
         if (!l) continue;
         const uint32_t e = symbol_entry(s, kind);
         if (l <= root) {
-            for (int k = rev[s]; k < size; k += 1 << l) tab[k] = e | (uint32_t)l;
+            for (int k = rev[s]; k < size; k += 1 << l) tab[k] = finish(e, l);
         } else {
             const uint32_t sub = tab[rev[s] & (uint32_t)(size - 1)];
             const int off = (int)(sub >> 16), sb = (int)(sub & 0xff);
-            for (int k = rev[s] >> root; k < (1 << sb); k += 1 << (l - root)) tab[off + k] = e | (uint32_t)(l - root);
+            for (int k = rev[s] >> root; k < (1 << sb); k += 1 << (l - root)) tab[off + k] = finish(e, l - root);
         }
     }
     if (kind == 1) {
@@ -212,6 +219,7 @@ Inflater::Step Inflater::huff_fast(uint8_t *&out_ref, uint8_t *out_end, const ui
             FQB_DROP(kLitBits);
             e = lit[(e >> 16) + (bb & ((1u << (e & 0xff)) - 1))];
         }
+        uint32_t saved = (uint32_t)bb;
         FQB_DROP(e & 0xff);
         if (e & (kLit | kEob | kBad)) {
             if (e & kLit) {                                   // a literal with a long code
@@ -224,19 +232,16 @@ Inflater::Step Inflater::huff_fast(uint8_t *&out_ref, uint8_t *out_end, const ui
             if (e & kBad) { err_ = "invalid literal/length code in the stream"; result = kFault; } else result = kBlockEnd;
             break;
         }
-        unsigned xb = (e >> 8) & 15;
-        const unsigned len = (e >> 16) + (unsigned)(bb & ((1u << xb) - 1));
-        FQB_DROP(xb);
+        const unsigned len = (e >> 16) + ((saved & ((1u << (e & 0xff)) - 1)) >> ((e >> 8) & 15));
         e = dtab[bb & ((1u << kDistBits) - 1)];
         if (e & kSub) {
             FQB_DROP(kDistBits);
             e = dtab[(e >> 16) + (bb & ((1u << (e & 0xff)) - 1))];
         }
+        saved = (uint32_t)bb;
         FQB_DROP(e & 0xff);
         if (e & kBad) { err_ = "invalid distance code in the stream"; result = kFault; break; }
-        xb = (e >> 8) & 15;
-        const size_t dist = (e >> 16) + (size_t)(bb & ((1u << xb) - 1));
-        FQB_DROP(xb);
+        const size_t dist = (e >> 16) + (size_t)((saved & ((1u << (e & 0xff)) - 1)) >> ((e >> 8) & 15));
         if (dist > (size_t)(out - floor)) { err_ = "match distance reaches before the start of the output"; result = kFault; break; }
         FQB_REFILL();
         e = FQB_LOOKUP();
@@ -283,26 +288,24 @@ Inflater::Step Inflater::huff_tail(uint8_t *&out_ref, uint8_t *out_end, const ui
             FQB_DROP(kLitBits);
             e = lit_[(e >> 16) + (bb & ((1u << (e & 0xff)) - 1))];
         }
+        uint32_t saved = (uint32_t)bb;
         FQB_DROP(e & 0xff);
         if (e & kLit) { *out++ = (uint8_t)(e >> 16); if (e & 0x100) *out++ = (uint8_t)(e >> 24); continue; }
         if (e & (kEob | kBad)) {
             if (e & kBad) { err_ = "invalid literal/length code in the stream"; result = kFault; } else result = kBlockEnd;
             break;
         }
-        unsigned xb = (e >> 8) & 15;
-        const unsigned len = (e >> 16) + (unsigned)(bb & ((1u << xb) - 1));
-        FQB_DROP(xb);
+        const unsigned len = (e >> 16) + ((saved & ((1u << (e & 0xff)) - 1)) >> ((e >> 8) & 15));
         FQB_FILL();
         e = dist_[bb & ((1u << kDistBits) - 1)];
         if (e & kSub) {
             FQB_DROP(kDistBits);
             e = dist_[(e >> 16) + (bb & ((1u << (e & 0xff)) - 1))];
         }
+        saved = (uint32_t)bb;
         FQB_DROP(e & 0xff);
         if (e & kBad) { err_ = "invalid distance code in the stream"; result = kFault; break; }
-        xb = (e >> 8) & 15;
-        const size_t dist = (e >> 16) + (size_t)(bb & ((1u << xb) - 1));
-        FQB_DROP(xb);
+        const size_t dist = (e >> 16) + (size_t)((saved & ((1u << (e & 0xff)) - 1)) >> ((e >> 8) & 15));
         if (dist > (size_t)(out - floor)) { err_ = "match distance reaches before the start of the output"; result = kFault; break; }
         for (unsigned k = 0; k < len; ++k) out[k] = out[(ptrdiff_t)k - (ptrdiff_t)dist];
         out += len;
