@@ -426,7 +426,7 @@ private:
         madvise(map, size, MADV_SEQUENTIAL);
         std::string err;
         if (!gunzip_blocks((const uint8_t *)map, (const uint8_t *)map + size, kBlockBytes, [this](BlockPtr b) { return push_block(std::move(b)); },
-                           getenv("FQB_AB") ? std::function<void(std::function<void()>)>() : [this](std::function<void()> f) { pool_->submit(std::move(f)); }, err) && !err.empty())
+                           [this](std::function<void()> f) { pool_->submit(std::move(f)); }, err) && !err.empty())
             fail_.raise(err);
         munmap(map, size);
         return true;
