@@ -7,7 +7,7 @@ OBJ       := build/obj
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v --expt-relaxed-constexpr
 CXXFLAGS  := -O2 -std=c++17 -fPIC -Wall -I/usr/local/cuda/include
-HOST_SRCS := fq_index.cpp fq_synth.cpp fq_capi_host.cpp fq_relayout.cpp fq_hostmath.cpp fq_stats_host.cpp fq_bam.cpp fq_feeder.cpp fq_inflate.cpp
+HOST_SRCS := fq_index.cpp fq_synth.cpp fq_capi_host.cpp fq_relayout.cpp fq_hostmath.cpp fq_stats_host.cpp fq_bam.cpp fq_feeder.cpp fq_inflate.cpp fq_deflate.cpp
 CU_SRCS   := $(notdir $(wildcard $(CSRC)/*.cu))
 OBJS      := $(HOST_SRCS:%.cpp=$(OBJ)/%.o) $(CU_SRCS:%.cu=$(OBJ)/%.cu.o)
 LIB       := fastquick_b200/libfastquick_b200.so

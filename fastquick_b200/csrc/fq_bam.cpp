@@ -1,5 +1,9 @@
 #include "fq_bam.h"
 
+#include "../../include/fastquick_b200.h"
+#include "fq_common.h"
+#include "fq_deflate.h"
+
 #include <zlib.h>
 
 #include <algorithm>
@@ -15,23 +19,30 @@ namespace fqb {
 namespace {
 constexpr size_t kBlockIn = 0xff00;       // payload bytes per block (htslib's BGZF_BLOCK_SIZE)
 
-// deflate level of the BAM members: 1 by default (2.3x the speed of level 4 for files ~5 % larger on FASTQ-like payload);
-// FQB_BAM_LEVEL=0..9 overrides it.  The records, not the compressed bytes, are what is compared with the reference's file.
+// The BAM members are compressed by this library's one-shot deflate (fq_deflate.cpp: 2.5-3x the speed of zlib's level 1
+// for members ~3 % larger on FASTQ-like payload); FQB_BAM_LEVEL=0..9 asks for zlib at that level instead.  The records,
+// not the compressed bytes, are what is compared with the reference's file.
 int bgzf_level() {
-    static const int lvl = []() { const char *e = getenv("FQB_BAM_LEVEL"); const int v = e ? atoi(e) : 1; return v < 0 || v > 9 ? 1 : v; }();
+    static const int lvl = []() { const char *e = getenv("FQB_BAM_LEVEL"); const int v = e ? atoi(e) : -1; return v < 0 || v > 9 ? -1 : v; }();
     return lvl;
 }
 
 std::string bgzf_block(const char *data, size_t n) {
-    std::string out(18 + compressBound((uLong)n) + 8 + 64, '\0');
-    z_stream zs;
-    memset(&zs, 0, sizeof zs);
-    deflateInit2(&zs, bgzf_level(), Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
-    zs.next_in = (Bytef *)data; zs.avail_in = (uInt)n;
-    zs.next_out = (Bytef *)&out[18]; zs.avail_out = (uInt)(out.size() - 18 - 8);
-    deflate(&zs, Z_FINISH);
-    const size_t clen = zs.total_out;
-    deflateEnd(&zs);
+    const int level = bgzf_level();
+    std::string out(18 + std::max<size_t>(compressBound((uLong)n), deflate_fast_bound(n)) + 8 + 64, '\0');
+    size_t clen;
+    if (level < 0) {
+        clen = deflate_fast((const uint8_t *)data, n, (uint8_t *)&out[18], out.size() - 18 - 8);
+    } else {
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+        zs.next_in = (Bytef *)data; zs.avail_in = (uInt)n;
+        zs.next_out = (Bytef *)&out[18]; zs.avail_out = (uInt)(out.size() - 18 - 8);
+        deflate(&zs, Z_FINISH);
+        clen = zs.total_out;
+        deflateEnd(&zs);
+    }
     const size_t total = 18 + clen + 8;
     static const unsigned char hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
     memcpy(&out[0], hdr, 16);
@@ -470,3 +481,18 @@ void bam_append_single(const BamContext &C, fqb_read_t p, const char *name, cons
 }
 
 }  // namespace fqb
+
+// The BAM writer's member format on a buffer (test hook): data[0..n) cut into 0xff00-byte payloads, each compressed into
+// one BGZF member exactly as BgzfWriter does, members back to back in out, no end-of-file member.
+extern "C" int fqb_bgzf_compress(const uint8_t *data, int64_t n, uint8_t *out, int64_t cap, int64_t *n_out) {
+    if ((!data && n > 0) || n < 0 || (!out && cap > 0) || cap < 0 || !n_out) { fqb::set_error("bad argument"); return FQB_ERR_ARG; }
+    int64_t o = 0;
+    for (int64_t off = 0; off < n; off += (int64_t)fqb::kBlockIn) {
+        const std::string m = fqb::bgzf_block((const char *)data + off, (size_t)std::min<int64_t>((int64_t)fqb::kBlockIn, n - off));
+        if (o + (int64_t)m.size() > cap) { fqb::set_error("output buffer too small"); return FQB_ERR_ARG; }
+        memcpy(out + o, m.data(), m.size());
+        o += (int64_t)m.size();
+    }
+    *n_out = o;
+    return FQB_OK;
+}

@@ -239,6 +239,10 @@ void fqb_feeder_close(fqb_feeder *f);
  * blocks of block_bytes (<= 0: the feeder's 4 MiB) exactly as the feeder chains them; *n_out = bytes written.
  * FQB_ERR_IO on a corrupt stream (CRC-32 / length / code checks), FQB_ERR_ARG if cap is too small. */
 int fqb_gunzip(const uint8_t *gz, int64_t n_gz, uint8_t *out, int64_t cap, int32_t block_bytes, int64_t *n_out);
+/* The BAM writer's member format on a buffer: data[0..n) cut into 0xff00-byte payloads, each compressed into one BGZF
+ * member exactly as fqb_bam_emit's writer does (the library's own deflate, or zlib at FQB_BAM_LEVEL), members back to
+ * back in out[0..cap), no end-of-file member; *n_out = bytes written.  cap >= n + 64 * (n / 0xff00 + 1) always fits. */
+int fqb_bgzf_compress(const uint8_t *data, int64_t n, uint8_t *out, int64_t cap, int64_t *n_out);
 void *fqb_host_alloc(size_t bytes);                /* pinned host memory for the feeder's batches */
 void fqb_host_free(void *p);
 uint64_t fqb_launch_count(const fqb_handle *h);   /* kernels launched by this handle so far */
