@@ -226,20 +226,26 @@ size_t deflate_fast(const uint8_t *in, size_t n, uint8_t *out, size_t cap) {
         if (s >= 16) bw.put(rl_extra[i], s == 16 ? 2 : s == 17 ? 3 : 7);
         bw.flush();
     }
+    uint32_t lit_enc[256];                                         // code | length << 16: one load per literal
+    for (int s = 0; s < 256; ++s) lit_enc[s] = lit_code[s] | ((uint32_t)lit_len[s] << 16);
     for (size_t i = 0; i < n_tok; ++i) {
         const uint32_t t = tok[i];
-        if (!(t & 0x80000000u)) {
-            bw.put(lit_code[t], lit_len[t]);
-        } else {
+        if (!(t & 0x80000000u)) {                                   // literals: flush once 32 bits have gathered (< 32 + 15 held)
+            const uint32_t e = lit_enc[t];
+            bw.put(e & 0xffff, e >> 16);
+            if (bw.bc >= 32) bw.flush();
+        } else {                                                    // a match adds up to 48 bits: start from fewer than 8
+            if (bw.bc >= 8) bw.flush();
             const unsigned len = (t >> 16) & 0x1ff, dist = t & 0xffff;
             const int ls = kT.len_sym[len], ds = dist_symbol(dist);
             bw.put(lit_code[257 + ls], lit_len[257 + ls]);
             bw.put(len - kLenBase[ls], kLenExtra[ls]);
             bw.put(dist_code[ds], dist_len[ds]);
             bw.put(dist - kDistBase[ds], kDistExtra[ds]);
+            bw.flush();
         }
-        bw.flush();
     }
+    bw.flush();
     bw.put(lit_code[256], lit_len[256]);
     return (size_t)(bw.finish() - out);
 }
