@@ -7,6 +7,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -27,31 +28,32 @@ int bgzf_level() {
     return lvl;
 }
 
-std::string bgzf_block(const char *data, size_t n) {
+constexpr size_t kSlot = 18 + kBlockIn + 1024 + 8;      // room for any member: compressBound(0xff00) = 0xff00 + 33 with these settings
+
+// one BGZF member for data[0..n), n <= kBlockIn, written to out[0..kSlot); returns its size
+size_t bgzf_block(const char *data, size_t n, char *out) {
     const int level = bgzf_level();
-    std::string out(18 + std::max<size_t>(compressBound((uLong)n), deflate_fast_bound(n)) + 8 + 64, '\0');
     size_t clen;
     if (level < 0) {
-        clen = deflate_fast((const uint8_t *)data, n, (uint8_t *)&out[18], out.size() - 18 - 8);
+        clen = deflate_fast((const uint8_t *)data, n, (uint8_t *)out + 18, kSlot - 18 - 8);
     } else {
         z_stream zs;
         memset(&zs, 0, sizeof zs);
         deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
         zs.next_in = (Bytef *)data; zs.avail_in = (uInt)n;
-        zs.next_out = (Bytef *)&out[18]; zs.avail_out = (uInt)(out.size() - 18 - 8);
+        zs.next_out = (Bytef *)out + 18; zs.avail_out = (uInt)(kSlot - 18 - 8);
         deflate(&zs, Z_FINISH);
         clen = zs.total_out;
         deflateEnd(&zs);
     }
     const size_t total = 18 + clen + 8;
     static const unsigned char hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
-    memcpy(&out[0], hdr, 16);
+    memcpy(out, hdr, 16);
     out[16] = (char)((total - 1) & 0xff); out[17] = (char)((total - 1) >> 8);
     const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)data, (uInt)n), isz = (uint32_t)n;
-    memcpy(&out[18 + clen], &crc, 4);
-    memcpy(&out[18 + clen + 4], &isz, 4);
-    out.resize(total);
-    return out;
+    memcpy(out + 18 + clen, &crc, 4);
+    memcpy(out + 18 + clen + 4, &isz, 4);
+    return total;
 }
 }  // namespace
 
@@ -92,40 +94,69 @@ void BgzfWriter::hand_over(bool all) {
     }
     cv_.notify_all();
 }
+// The writer thread and its helpers: the helpers live as long as the file is open (a thread per chunk would cost more than
+// a chunk's members now that compressing one takes a few hundred microseconds) and take members off a shared counter.
+struct BgzfWriter::Crew {
+    std::mutex m; std::condition_variable start, done;
+    uint64_t generation = 0; unsigned busy = 0; bool stop = false;
+    const std::string *data = nullptr; std::atomic<size_t> next{0};
+    std::vector<char> slots; std::vector<size_t> sizes;          // member b of the current chunk: slots[b * kSlot .. + sizes[b])
+    std::vector<std::thread> helpers;
+    void members() {
+        const size_t n_blocks = sizes.size();
+        for (size_t b; (b = next.fetch_add(1)) < n_blocks;) {
+            const size_t off = b * kBlockIn, len = std::min(kBlockIn, data->size() - off);
+            sizes[b] = bgzf_block(data->data() + off, len, slots.data() + b * kSlot);
+        }
+    }
+    void helper() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> l(m);
+                start.wait(l, [&]() { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+            }
+            members();
+            { std::lock_guard<std::mutex> l(m); --busy; }
+            done.notify_all();
+        }
+    }
+    void compress(const std::string &d) {
+        data = &d; next.store(0);
+        sizes.assign((d.size() + kBlockIn - 1) / kBlockIn, 0);
+        if (slots.size() < sizes.size() * kSlot) slots.resize(sizes.size() * kSlot);
+        { std::lock_guard<std::mutex> l(m); ++generation; busy = (unsigned)helpers.size(); }
+        start.notify_all();
+        members();
+        std::unique_lock<std::mutex> l(m);
+        done.wait(l, [&]() { return busy == 0; });
+    }
+};
+
 void BgzfWriter::run() {
+    Crew crew;
+    unsigned nthr = std::thread::hardware_concurrency();
+    if (nthr < 1) nthr = 1;
+    if (nthr > 16) nthr = 16;
+    for (unsigned t = 1; t < nthr; ++t) crew.helpers.emplace_back([&crew]() { crew.helper(); });
     for (;;) {
         std::string chunk;
         {
             std::unique_lock<std::mutex> l(m_);
             cv_.wait(l, [&]() { return closing_ || !queue_.empty(); });
-            if (queue_.empty()) return;
+            if (queue_.empty()) break;
             chunk.swap(queue_.front()); queue_.pop_front();
         }
         cv_.notify_all();
-        compress_and_write(chunk);
+        crew.compress(chunk);
+        for (size_t b = 0; b < crew.sizes.size(); ++b)
+            if (fwrite(crew.slots.data() + b * kSlot, 1, crew.sizes[b], fp_) != crew.sizes[b]) failed_ = true;
     }
-}
-void BgzfWriter::compress_and_write(const std::string &data) {
-    const size_t n_blocks = (data.size() + kBlockIn - 1) / kBlockIn;
-    std::vector<std::string> comp(n_blocks);
-    unsigned nthr = std::thread::hardware_concurrency();
-    if (nthr < 1) nthr = 1;
-    if (nthr > 16) nthr = 16;
-    if (nthr > n_blocks) nthr = (unsigned)n_blocks;
-    auto work = [&](unsigned t) {
-        for (size_t b = t; b < n_blocks; b += nthr) {
-            const size_t off = b * kBlockIn, len = std::min(kBlockIn, data.size() - off);
-            comp[b] = bgzf_block(data.data() + off, len);
-        }
-    };
-    if (nthr == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nthr; ++t) th.emplace_back(work, t);
-        for (auto &x : th) x.join();
-    }
-    for (auto &c : comp)
-        if (fwrite(c.data(), 1, c.size(), fp_) != c.size()) failed_ = true;
+    { std::lock_guard<std::mutex> l(crew.m); crew.stop = true; }
+    crew.start.notify_all();
+    for (auto &t : crew.helpers) t.join();
 }
 bool BgzfWriter::close(std::string &err) {
     if (!fp_) return true;
@@ -488,11 +519,28 @@ extern "C" int fqb_bgzf_compress(const uint8_t *data, int64_t n, uint8_t *out, i
     if ((!data && n > 0) || n < 0 || (!out && cap > 0) || cap < 0 || !n_out) { fqb::set_error("bad argument"); return FQB_ERR_ARG; }
     int64_t o = 0;
     for (int64_t off = 0; off < n; off += (int64_t)fqb::kBlockIn) {
-        const std::string m = fqb::bgzf_block((const char *)data + off, (size_t)std::min<int64_t>((int64_t)fqb::kBlockIn, n - off));
-        if (o + (int64_t)m.size() > cap) { fqb::set_error("output buffer too small"); return FQB_ERR_ARG; }
-        memcpy(out + o, m.data(), m.size());
-        o += (int64_t)m.size();
+        std::vector<char> m(fqb::kSlot);
+        const size_t len = fqb::bgzf_block((const char *)data + off, (size_t)std::min<int64_t>((int64_t)fqb::kBlockIn, n - off), m.data());
+        if (o + (int64_t)len > cap) { fqb::set_error("output buffer too small"); return FQB_ERR_ARG; }
+        memcpy(out + o, m.data(), len);
+        o += (int64_t)len;
     }
     *n_out = o;
+    return FQB_OK;
+}
+
+// BgzfWriter itself on a buffer (test hook): data[0..n) handed to the writer in pieces of `piece` bytes, by write() when
+// owned == 0 and by write_owned() otherwise, into a BGZF file with its end-of-file member.
+extern "C" int fqb_bgzf_write_file(const char *path, const uint8_t *data, int64_t n, int64_t piece, int32_t owned) {
+    if (!path || (!data && n > 0) || n < 0 || piece < 1) { fqb::set_error("bad argument"); return FQB_ERR_ARG; }
+    fqb::BgzfWriter w;
+    std::string err;
+    if (!w.open(path, err)) { fqb::set_error(err); return FQB_ERR_IO; }
+    for (int64_t off = 0; off < n; off += piece) {
+        const size_t len = (size_t)std::min<int64_t>(piece, n - off);
+        if (owned) w.write_owned(std::string((const char *)data + off, len));
+        else w.write(data + off, len);
+    }
+    if (!w.close(err)) { fqb::set_error(err); return FQB_ERR_IO; }
     return FQB_OK;
 }

@@ -31,7 +31,7 @@ public:
 private:
     void hand_over(bool all);
     void run();
-    void compress_and_write(const std::string &chunk);
+    struct Crew;
     FILE *fp_ = nullptr;
     std::string pending_;
     bool failed_ = false;

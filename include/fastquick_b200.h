@@ -243,6 +243,10 @@ int fqb_gunzip(const uint8_t *gz, int64_t n_gz, uint8_t *out, int64_t cap, int32
  * member exactly as fqb_bam_emit's writer does (the library's own deflate, or zlib at FQB_BAM_LEVEL), members back to
  * back in out[0..cap), no end-of-file member; *n_out = bytes written.  cap >= n + 64 * (n / 0xff00 + 1) always fits. */
 int fqb_bgzf_compress(const uint8_t *data, int64_t n, uint8_t *out, int64_t cap, int64_t *n_out);
+/* The BAM writer's file layer on a buffer: data[0..n) handed to it in pieces of `piece` bytes (copied when owned == 0,
+ * as whole-record chunks that start their own members otherwise), compressed by its writer thread and helpers, closed
+ * with the BGZF end-of-file member. */
+int fqb_bgzf_write_file(const char *path, const uint8_t *data, int64_t n, int64_t piece, int32_t owned);
 void *fqb_host_alloc(size_t bytes);                /* pinned host memory for the feeder's batches */
 void fqb_host_free(void *p);
 uint64_t fqb_launch_count(const fqb_handle *h);   /* kernels launched by this handle so far */

@@ -103,3 +103,21 @@ def test_bgzf_zlib_level_switch():
         if lvl is not None: env["FQB_BAM_LEVEL"] = lvl
         sizes[lvl] = int(subprocess.check_output([sys.executable, "-c", code], env=env).split()[-1])
     assert sizes["0"] > 9000 * 23 and sizes["6"] < sizes["0"] // 20 and sizes[None] < sizes["0"] // 20
+
+
+@pytest.mark.parametrize("owned", [0, 1])
+def test_bgzf_writer_file(tmp_path, owned):
+    """BgzfWriter end to end (queue, writer thread, compression helpers): the file inflates to what was written, every
+    member holds at most 0xff00 bytes, and the last member is the empty end-of-file block."""
+    rng = np.random.default_rng(8)
+    data = b"".join(b"read_%07d\t%d\t" % (i, i * 13) + bytes(rng.integers(33, 74, 100, dtype=np.uint8)) + b"\n" for i in range(150000))
+    lib = fx.host_lib()
+    lib.fqb_bgzf_write_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_int64, C.c_int32]
+    for piece in (1 << 22, 100003, 977 if owned == 0 else 300007):
+        p = str(tmp_path / ("w%d_%d.bgzf" % (owned, piece)))
+        assert lib.fqb_bgzf_write_file(p.encode(), data, len(data), piece, owned) == 0, lib.fqb_last_error()
+        blob = open(p, "rb").read()
+        assert gzip.decompress(blob) == data
+        members = list(_members(blob))
+        assert members[-1] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+        assert all(struct.unpack("<I", m[-4:])[0] <= 0xff00 for m in members)
