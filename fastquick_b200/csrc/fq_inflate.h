@@ -13,7 +13,8 @@ class Inflater {
 public:
     enum Status { kOutputFull, kStreamEnd, kError };
     static constexpr size_t kWindow = 32768;        // history a match may reach back into
-    static constexpr size_t kOutSlack = 320;        // run() returns kOutputFull once fewer bytes than this are left
+    static constexpr size_t kOutSlack = 320;        // inside a Huffman block run() returns kOutputFull once fewer bytes than
+                                                    // this are left (a match and its over-copy fit); buffers must be larger
 
     void reset(const uint8_t *in, const uint8_t *in_end);
     // Decodes into [out, out_end), advancing out.  floor = lowest address a match may copy from (the bytes between
