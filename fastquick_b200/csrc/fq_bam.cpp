@@ -20,8 +20,8 @@ namespace fqb {
 namespace {
 constexpr size_t kBlockIn = 0xff00;       // payload bytes per block (htslib's BGZF_BLOCK_SIZE)
 
-// The BAM members are compressed by this library's one-shot deflate (fq_deflate.cpp: 2.5-3x the speed of zlib's level 1
-// for members ~3 % larger on FASTQ-like payload); FQB_BAM_LEVEL=0..9 asks for zlib at that level instead.  The records,
+// The BAM members are compressed by this library's one-shot deflate (fq_deflate.cpp: 2-2.5x the speed of zlib's level 1
+// for members ~4 % smaller on FASTQ-like payload); FQB_BAM_LEVEL=0..9 asks for zlib at that level instead.  The records,
 // not the compressed bytes, are what is compared with the reference's file.
 int bgzf_level() {
     static const int lvl = []() { const char *e = getenv("FQB_BAM_LEVEL"); const int v = e ? atoi(e) : -1; return v < 0 || v > 9 ? -1 : v; }();

