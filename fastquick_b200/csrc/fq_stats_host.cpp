@@ -300,6 +300,15 @@ static std::vector<double> adjusted_isize(const std::string &table, const std::s
     return f;
 }
 
+// GetInsertSizeDist's first half (src/StatCollector.cpp:1969-1985): both censoring directions, summed
+bool write_adjusted_isize(const std::string &table, const std::string &out_path) {
+    std::vector<double> f1 = adjusted_isize(table, "FwdOnly");
+    std::vector<double> f2 = adjusted_isize(table, "RevOnly");
+    std::ofstream fa(out_path);
+    for (size_t i = 0; i < f1.size(); ++i) { f1[i] = (f1[i] + f2[i]); fa << i << "\t" << f1[i] << std::endl; }
+    return (bool)fa;
+}
+
 // the reference calls these unqualified under `using namespace std`, i.e. with the float overloads where the argument is float
 #define REV_PHRED(x) std::pow(10.0, (x / (-10.0)))
 #define PHRED(x) (-10) * std::log10(x)
@@ -376,10 +385,7 @@ bool write_summary_files(const StatsTables &T, StatsTotals &S, const fqb_gap_opt
         }
     }
     {   // GetInsertSizeDist (1969-1997)
-        std::vector<double> f1 = adjusted_isize(prefix + ".InsertSizeTable", "FwdOnly");
-        std::vector<double> f2 = adjusted_isize(prefix + ".InsertSizeTable", "RevOnly");
-        std::ofstream fa(prefix + ".AdjustedInsertSizeDist");
-        for (size_t i = 0; i < f1.size(); ++i) { f1[i] = (f1[i] + f2[i]); fa << i << "\t" << f1[i] << endl; }
+        write_adjusted_isize(prefix + ".InsertSizeTable", prefix + ".AdjustedInsertSizeDist");
         std::ofstream fr(prefix + ".RawInsertSizeDist");
         for (uint32_t i = 0; i != 4096; ++i) fr << i << "\t" << (size_t)S.isize_dist[i] << endl;
     }
@@ -501,3 +507,10 @@ bool write_summary_files(const StatsTables &T, StatsTotals &S, const fqb_gap_opt
 }
 
 }  // namespace fqb
+
+// InsertSizeEstimator on a finished InsertSizeTable (host only; what fqb_stats_finish runs for <prefix>.AdjustedInsertSizeDist)
+extern "C" int fqb_isize_adjusted_file(const char *table_path, const char *out_path) {
+    if (!table_path || !out_path) return FQB_ERR_ARG;
+    { std::ifstream probe(table_path); if (!probe) return FQB_ERR_IO; }
+    return fqb::write_adjusted_isize(table_path, out_path) ? FQB_OK : FQB_ERR_IO;
+}

@@ -64,6 +64,9 @@ struct StatsTotals {
 void format_isize_line(const StatsTables &T, const PairStat &ps, const fqb_read_t &p, const fqb_read_t &q, const char *name, std::string &out);
 void append_isize_line(const StatsTables &T, const PairStat &ps, const fqb_read_t &p, const fqb_read_t &q, const char *name, std::string &out);
 
+// InsertSizeEstimator (src/InsertSizeEstimator.cpp:43-173) over a finished InsertSizeTable -> the AdjustedInsertSizeDist file
+bool write_adjusted_isize(const std::string &table, const std::string &out_path);
+
 // ProcessCore: writes <prefix>.{DepthDist,GCDist,EmpRepDist,EmpCycleDist,AdjustedInsertSizeDist,RawInsertSizeDist,
 // SexChromInfo,Pileup,FASTQ.csv,Sequence.csv,Summary,vcf}; <prefix>.InsertSizeTable must already be complete.
 bool write_summary_files(const StatsTables &T, StatsTotals &S, const fqb_gap_opt_t &g, const std::string &prefix, std::string &err);

@@ -181,6 +181,9 @@ int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride);
  * the call that joins them.  fqb_emit_sync is a no-op otherwise. */
 int fqb_emit_sync(fqb_handle *h);
 int fqb_stats_finish(fqb_handle *h, const char *out_prefix);
+/* InsertSizeEstimator (src/InsertSizeEstimator.cpp:43-173) alone, host only: <table_path> is a finished InsertSizeTable,
+ * <out_path> receives what fqb_stats_finish writes as <prefix>.AdjustedInsertSizeDist. */
+int fqb_isize_adjusted_file(const char *table_path, const char *out_path);
 /* Sharded runs (one handle per GPU, batches dealt round-robin): each handle writes the InsertSizeTable lines
  * (StatCollector::AddAlignment's `fout`, src/StatCollector.cpp:950) of its own batches.  fqb_stats_close_table
  * finishes a handle's file; fqb_stats_merge_tables, on the handle that will call fqb_stats_finish, splices the
