@@ -90,3 +90,17 @@ void fill_isize_penalty(const fqb_isize_t &ii, std::vector<int32_t> &t) {
 }
 
 }  // namespace fqb
+
+// The host half of infer_isize and the pairing penalty table on their own (host only; the device supplies the histogram
+// in the product path, fq_engine.cu: fqb_stage_pair).
+extern "C" int fqb_infer_isize_hist(const uint32_t *hist, int32_t max_len, double ap_prior, int64_t L, fqb_isize_t *ii) {
+    if (!hist || !ii || L <= 0) return FQB_ERR_ARG;
+    return fqb::infer_isize_hist(hist, max_len, ap_prior, L, *ii) ? 1 : 0;
+}
+extern "C" int64_t fqb_isize_penalty(const fqb_isize_t *ii, int32_t *out, int64_t cap) {
+    if (!ii || (!out && cap > 0) || cap < 0) return FQB_ERR_ARG;
+    std::vector<int32_t> t;
+    fqb::fill_isize_penalty(*ii, t);
+    for (int64_t i = 0; i < (int64_t)t.size() && i < cap; ++i) out[i] = t[(size_t)i];
+    return (int64_t)t.size();
+}

@@ -184,6 +184,14 @@ int fqb_stats_finish(fqb_handle *h, const char *out_prefix);
 /* InsertSizeEstimator (src/InsertSizeEstimator.cpp:43-173) alone, host only: <table_path> is a finished InsertSizeTable,
  * <out_path> receives what fqb_stats_finish writes as <prefix>.AdjustedInsertSizeDist. */
 int fqb_isize_adjusted_file(const char *table_path, const char *out_path);
+/* The host half of infer_isize (libbwa/bwape.c:49-117) on its own: hist[v] = number of pairs with both mapQ >= 20 and
+ * insert size v < 100000 (100,000 bins; the pair stage collects it on the device), max_len = the batch's longest read,
+ * L = the BWT's seq_len.  Returns 1 and fills *ii, or 0 when inference fails (fewer than 20 pairs, degenerate spread)
+ * and *ii is "unset" (avg = std = -1).  fqb_isize_penalty: the table pairing() reads, entry l =
+ * (int)(-4.343 * log(.5 * erfc(M_SQRT1_2 * fabs(l - avg) / std)) + .499) (libbwa/bwape.h:62) for l = 0..high_bayesian;
+ * returns the table's length and writes at most cap entries. */
+int fqb_infer_isize_hist(const uint32_t *hist, int32_t max_len, double ap_prior, int64_t L, fqb_isize_t *ii);
+int64_t fqb_isize_penalty(const fqb_isize_t *ii, int32_t *out, int64_t cap);
 /* Sharded runs (one handle per GPU, batches dealt round-robin): each handle writes the InsertSizeTable lines
  * (StatCollector::AddAlignment's `fout`, src/StatCollector.cpp:950) of its own batches.  fqb_stats_close_table
  * finishes a handle's file; fqb_stats_merge_tables, on the handle that will call fqb_stats_finish, splices the

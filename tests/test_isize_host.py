@@ -1,0 +1,99 @@
+"""Row a8, host half: the product's infer_isize over the device's insert-size histogram (fq_hostmath.cpp:
+infer_isize_hist) against the C oracle's restatement of libbwa/bwape.c:49-117 over the same pairs as a sorted array
+(oracle/fq_oracle_pe.c, itself pinned to the reference by the golden pair-stage rows).  Every field must be bit-equal:
+avg / std / ap_prior feed integer decisions in pairing() and mate rescue."""
+import ctypes as C
+import math
+import zlib
+
+import numpy as np
+import pytest
+
+import fx
+from fastquick_b200 import _abi
+
+L_BWT = 13_217_394          # 2 x l_pac of the 10k-marker index; only enters through ap_prior / L
+
+
+def _both(isizes, read_len=100, ap_prior=1e-5, mapq=None):
+    isizes = np.asarray(isizes, np.int64)
+    n = len(isizes)
+    rows = np.zeros(2 * n, _abi.READ_DTYPE)
+    rows["len"] = read_len
+    rows["pos"][0::2] = 5000
+    rows["pos"][1::2] = 5000 + isizes - read_len          # x = p1.pos + p1.len - p0.pos = isize (isize > read_len)
+    rows["mapQ"] = 37 if mapq is None else np.repeat(mapq, 2)
+    orc = fx.build_oracle()
+    orc.orc_infer_isize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int64]
+    want = _abi.ISize()
+    rc_o = orc.orc_infer_isize(n, rows.ctypes.data, C.byref(want), ap_prior, L_BWT)
+    keep = isizes if mapq is None else isizes[np.asarray(mapq) >= 20]
+    hist = np.bincount(keep[keep < 100000], minlength=100000).astype(np.uint32)
+    lib = fx.host_lib()
+    lib.fqb_infer_isize_hist.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_int64, C.c_void_p]
+    got = _abi.ISize()
+    rc_p = lib.fqb_infer_isize_hist(hist.ctypes.data, read_len, ap_prior, L_BWT, C.byref(got))
+    return rc_o, want, rc_p, got
+
+
+def _same(a, b):
+    for f in ("low", "high", "high_bayesian"):
+        assert getattr(a, f) == getattr(b, f), f
+    for f in ("avg", "std", "ap_prior"):
+        x, y = getattr(a, f), getattr(b, f)
+        assert x == y or (math.isnan(x) and math.isnan(y)), (f, x, y)
+
+
+CASES = {
+    "normal_300_30": lambda r: r.normal(300, 30, 5000),
+    "normal_500_80": lambda r: r.normal(500, 80, 262144),
+    "tight": lambda r: r.normal(250, 2, 400),
+    "twenty": lambda r: r.normal(300, 30, 20),
+    "outliers": lambda r: np.concatenate([r.normal(350, 40, 3000), r.uniform(2000, 99999, 200)]),
+    "bimodal": lambda r: np.concatenate([r.normal(200, 15, 2000), r.normal(900, 50, 2000)]),
+    "beyond_100k": lambda r: np.concatenate([r.normal(300, 30, 500), r.uniform(100000, 400000, 300)]),
+    "constant": lambda r: np.full(100, 321.0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_infer_isize_hist_matches_oracle(name):
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    isizes = np.maximum(CASES[name](rng).astype(np.int64), 101)
+    rc_o, want, rc_p, got = _both(isizes)
+    assert (rc_o == 0) == (rc_p == 1)
+    _same(want, got)
+    if name != "constant": assert rc_p == 1 and got.low <= got.avg <= got.high <= got.high_bayesian
+
+
+def test_infer_isize_hist_failure_and_mapq_filter():
+    rng = np.random.default_rng(4)
+    rc_o, want, rc_p, got = _both(np.maximum(rng.normal(300, 30, 19).astype(np.int64), 101))      # fewer than 20 pairs
+    assert rc_o == -1 and rc_p == 0 and got.avg == -1.0 and got.std == -1.0 and got.high == 0
+    isizes = np.maximum(rng.normal(300, 30, 4000).astype(np.int64), 101)
+    mapq = rng.choice([0, 10, 19, 20, 25, 37], 4000)                                               # only pairs with mapQ >= 20 count
+    rc_o, want, rc_p, got = _both(isizes, mapq=mapq)
+    assert rc_o == 0 and rc_p == 1
+    _same(want, got)
+
+
+def test_isize_penalty_table():
+    """fill_isize_penalty = the expression in __pairing_aux's macro (libbwa/bwape.h:62) for every insert size up to
+    high_bayesian, evaluated with the same libm."""
+    rng = np.random.default_rng(6)
+    _, _, rc, ii = _both(np.maximum(rng.normal(300, 30, 5000).astype(np.int64), 101))
+    assert rc == 1
+    lib = fx.host_lib()
+    lib.fqb_isize_penalty.restype = C.c_int64
+    lib.fqb_isize_penalty.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    n = lib.fqb_isize_penalty(C.byref(ii), None, 0)
+    assert n == ii.high_bayesian + 1
+    t = np.zeros(n, np.int32)
+    assert lib.fqb_isize_penalty(C.byref(ii), t.ctypes.data, n) == n
+    libm = C.CDLL("libm.so.6")
+    libm.erfc.restype = C.c_double; libm.erfc.argtypes = [C.c_double]
+    libm.log.restype = C.c_double; libm.log.argtypes = [C.c_double]
+    for l in list(range(0, n, 7)) + [n - 1, int(ii.avg)]:
+        v = -4.343 * libm.log(.5 * libm.erfc(math.sqrt(0.5) * abs(l - ii.avg) / ii.std)) + .499
+        assert t[l] == int(v), l                       # C's (int) truncates toward zero, as Python's int() does
+    assert t[int(ii.avg)] == 3 and t[0] > t[int(ii.avg) - 60] > t[int(ii.avg)]
