@@ -104,3 +104,11 @@ extern "C" int64_t fqb_isize_penalty(const fqb_isize_t *ii, int32_t *out, int64_
     for (int64_t i = 0; i < (int64_t)t.size() && i < cap; ++i) out[i] = t[(size_t)i];
     return (int64_t)t.size();
 }
+
+// The libm-dependent tables the engine ships to the device (bwa_cal_maxdiff per read length, g_log_n), host only.
+extern "C" int fqb_host_tables(const fqb_gap_opt_t *gopt, int32_t *maxdiff /*FQB_MAX_READ_LEN + 1*/, int32_t *log_n /*256*/) {
+    if (!gopt || !maxdiff || !log_n) return FQB_ERR_ARG;
+    fqb::fill_maxdiff_table(*gopt, maxdiff);
+    fqb::fill_log_n(log_n);
+    return FQB_OK;
+}

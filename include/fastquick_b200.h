@@ -192,6 +192,10 @@ int fqb_isize_adjusted_file(const char *table_path, const char *out_path);
  * returns the table's length and writes at most cap entries. */
 int fqb_infer_isize_hist(const uint32_t *hist, int32_t max_len, double ap_prior, int64_t L, fqb_isize_t *ii);
 int64_t fqb_isize_penalty(const fqb_isize_t *ii, int32_t *out, int64_t cap);
+/* The libm-dependent tables fqb_create evaluates on the host and keeps on the device: maxdiff[l] = bwa_cal_maxdiff(l, 0.02,
+ * gopt->fnr) (libbwa/bwtaln.c:58-70; gopt->max_diff when fnr <= 0) for l = 0..FQB_MAX_READ_LEN, and g_log_n
+ * (libbwa/bwase.c:602-606), 256 entries. */
+int fqb_host_tables(const fqb_gap_opt_t *gopt, int32_t *maxdiff, int32_t *log_n);
 /* Sharded runs (one handle per GPU, batches dealt round-robin): each handle writes the InsertSizeTable lines
  * (StatCollector::AddAlignment's `fout`, src/StatCollector.cpp:950) of its own batches.  fqb_stats_close_table
  * finishes a handle's file; fqb_stats_merge_tables, on the handle that will call fqb_stats_finish, splices the

@@ -97,3 +97,27 @@ def test_isize_penalty_table():
         v = -4.343 * libm.log(.5 * libm.erfc(math.sqrt(0.5) * abs(l - ii.avg) / ii.std)) + .499
         assert t[l] == int(v), l                       # C's (int) truncates toward zero, as Python's int() does
     assert t[int(ii.avg)] == 3 and t[0] > t[int(ii.avg) - 60] > t[int(ii.avg)]
+
+
+def test_maxdiff_and_log_n_tables_match_oracle():
+    """Rows a3 / a6: the tables fqb_create ships to the device against the oracle's bwa_cal_maxdiff (pinned to the
+    reference's in test_oracle_vs_ref.py) and g_log_n."""
+    lib, orc = fx.host_lib(), fx.build_oracle()
+    orc.orc_cal_maxdiff.argtypes = [C.c_int, C.c_double, C.c_double]
+    g = _abi.GapOpt()
+    lib.fqb_gap_opt_default(C.byref(g))
+    md = np.zeros(257, np.int32); ln = np.zeros(256, np.int32)
+    for fnr in (0.04, 0.02, 0.001):                              # 0.02 is FASTQuick's (SURVEY 8: max_diff 5 / 7 at 100 / 150 bp)
+        g.fnr = fnr
+        assert lib.fqb_host_tables(C.byref(g), md.ctypes.data, ln.ctypes.data) == 0
+        assert [int(v) for v in md] == [orc.orc_cal_maxdiff(l, 0.02, fnr) for l in range(257)]
+    assert md[100] == 8 and md[150] == 10                        # fnr 0.001
+    g.fnr = 0.04
+    lib.fqb_host_tables(C.byref(g), md.ctypes.data, ln.ctypes.data)
+    assert md[100] == 5 and md[150] == 6                         # bwa aln's documented values at its default fnr
+    g.fnr = -1.0; g.max_diff = 3
+    lib.fqb_host_tables(C.byref(g), md.ctypes.data, ln.ctypes.data)
+    assert (md == 3).all()
+    want = (C.c_int * 256)()
+    orc.orc_fill_log_n(want)
+    assert list(ln) == list(want) and ln[1] == 0 and ln[2] == 3 and ln[255] == 24
