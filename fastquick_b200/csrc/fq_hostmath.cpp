@@ -112,3 +112,10 @@ extern "C" int fqb_host_tables(const fqb_gap_opt_t *gopt, int32_t *maxdiff /*FQB
     fqb::fill_log_n(log_n);
     return FQB_OK;
 }
+
+// gap_init_stack's bucket count (libbwa/bwtgap.c:18) for a batch whose longest read has max_len bases, with the max_gapo
+// clamp of src/BwtMapper.cpp:73-81 applied: what sizes the per-read score-bucket heads in search_kernel.
+extern "C" int fqb_search_buckets(const fqb_gap_opt_t *gopt, int32_t max_len) {
+    if (!gopt || max_len < 0 || max_len > FQB_MAX_READ_LEN) return FQB_ERR_ARG;
+    return fqb::make_search_opt(*gopt, max_len).n_buckets;
+}

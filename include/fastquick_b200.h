@@ -196,6 +196,9 @@ int64_t fqb_isize_penalty(const fqb_isize_t *ii, int32_t *out, int64_t cap);
  * gopt->fnr) (libbwa/bwtaln.c:58-70; gopt->max_diff when fnr <= 0) for l = 0..FQB_MAX_READ_LEN, and g_log_n
  * (libbwa/bwase.c:602-606), 256 entries. */
 int fqb_host_tables(const fqb_gap_opt_t *gopt, int32_t *maxdiff, int32_t *log_n);
+/* n_stacks of gap_init_stack (libbwa/bwtgap.c:18) for a batch whose longest read has max_len bases, after the max_gapo
+ * clamp of src/BwtMapper.cpp:73-81: (max_diff + 1) * s_mm + (max_gapo + 1) * s_gapo + (max_gape + 1) * s_gape. */
+int fqb_search_buckets(const fqb_gap_opt_t *gopt, int32_t max_len);
 /* Sharded runs (one handle per GPU, batches dealt round-robin): each handle writes the InsertSizeTable lines
  * (StatCollector::AddAlignment's `fout`, src/StatCollector.cpp:950) of its own batches.  fqb_stats_close_table
  * finishes a handle's file; fqb_stats_merge_tables, on the handle that will call fqb_stats_finish, splices the

@@ -121,3 +121,18 @@ def test_maxdiff_and_log_n_tables_match_oracle():
     want = (C.c_int * 256)()
     orc.orc_fill_log_n(want)
     assert list(ln) == list(want) and ln[1] == 0 and ln[2] == 3 and ln[255] == 24
+
+
+def test_search_bucket_count():
+    """gap_init_stack: 3 (max_diff + 1) + 11 * 2 + 4 * 7 = 68 / 74 score buckets for 100 / 150 bp at FASTQuick's fnr 0.02
+    (SURVEY 8); max_gapo is clamped to max_diff when -o exceeds it."""
+    lib = fx.host_lib()
+    g = _abi.GapOpt()
+    lib.fqb_gap_opt_default(C.byref(g))
+    g.fnr = 0.02
+    assert lib.fqb_search_buckets(C.byref(g), 100) == 68 and lib.fqb_search_buckets(C.byref(g), 150) == 74
+    assert lib.fqb_search_buckets(C.byref(g), 10) == (1 + 1) * 3 + (1 + 1) * 11 + 7 * 4      # max_diff 1
+    g.max_gapo = 3
+    assert lib.fqb_search_buckets(C.byref(g), 100) == 6 * 3 + 4 * 11 + 7 * 4
+    assert lib.fqb_search_buckets(C.byref(g), 10) == 2 * 3 + 2 * 11 + 7 * 4                  # -o 3 clamped to max_diff 1
+    assert lib.fqb_search_buckets(C.byref(g), 1000) < 0
