@@ -1,4 +1,6 @@
-"""Row a8, host half: the product's infer_isize over the device's insert-size histogram (fq_hostmath.cpp:
+"""Host halves of the hot path, no GPU needed (rows a8, a3, a6, a4's bucket sizing).
+
+Row a8: the product's infer_isize over the device's insert-size histogram (fq_hostmath.cpp:
 infer_isize_hist) against the C oracle's restatement of libbwa/bwape.c:49-117 over the same pairs as a sorted array
 (oracle/fq_oracle_pe.c, itself pinned to the reference by the golden pair-stage rows).  Every field must be bit-equal:
 avg / std / ap_prior feed integer decisions in pairing() and mate rescue."""
