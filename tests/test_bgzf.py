@@ -121,3 +121,31 @@ def test_bgzf_writer_file(tmp_path, owned):
         members = list(_members(blob))
         assert members[-1] == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
         assert all(struct.unpack("<I", m[-4:])[0] <= 0xff00 for m in members)
+
+
+def test_bgzf_round_trip_property():
+    """Any byte string survives compress -> zlib inflate and compress -> the feeder's inflate loop (hypothesis draws
+    short and long inputs, low-entropy alphabets and repeated fragments)."""
+    hypothesis = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    lib = fx.host_lib()
+    lib.fqb_gunzip.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int64)]
+    fragments = st.lists(st.binary(min_size=1, max_size=40), min_size=1, max_size=12)
+    payload = st.one_of(
+        st.binary(max_size=3000),
+        st.builds(lambda fr, picks: b"".join(fr[i % len(fr)] for i in picks), fragments, st.lists(st.integers(0, 11), max_size=4000)),
+        st.builds(lambda alphabet, picks: bytes(alphabet[i % len(alphabet)] for i in picks), st.binary(min_size=1, max_size=6),
+                  st.lists(st.integers(0, 5), max_size=20000)))
+
+    @settings(max_examples=150, deadline=None)
+    @given(payload)
+    def check(data):
+        blob = _compress(data)
+        assert (gzip.decompress(blob) if blob else b"") == data
+        out = np.zeros(max(len(data), 1), np.uint8)
+        n = C.c_int64()
+        assert lib.fqb_gunzip(blob, len(blob), out.ctypes.data, len(data), 700, C.byref(n)) == 0
+        assert bytes(out[:n.value]) == data
+
+    check()
