@@ -209,3 +209,25 @@ def test_feeder_bgzf_member_checks(tmp_path):
         open(p, "wb").write(bytes(b))
         with pytest.raises(RuntimeError, match="BGZF"):
             _read_all(p, 100, 512)
+
+
+def test_inflate_property():
+    """zlib at any level / strategy / window size -> the feeder's inflate loop at any text-block size gives the input back."""
+    pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    fragments = st.lists(st.binary(min_size=1, max_size=60), min_size=1, max_size=10)
+    payload = st.one_of(
+        st.binary(max_size=5000),
+        st.builds(lambda fr, picks: b"".join(fr[i % len(fr)] for i in picks), fragments, st.lists(st.integers(0, 9), max_size=6000)))
+
+    @settings(max_examples=150, deadline=None)
+    @given(payload, st.integers(0, 9), st.sampled_from([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]),
+           st.integers(9, 15), st.integers(1, 9), st.sampled_from([0, 640, 1111, 40000]))
+    def check(data, level, strategy, wbits, mem, block_bytes):
+        co = zlib.compressobj(level, zlib.DEFLATED, 16 + wbits, mem, strategy)
+        blob = co.compress(data) + co.flush()
+        rc, out = _gunzip(blob, len(data), block_bytes)
+        assert rc == 0 and out == data
+
+    check()
