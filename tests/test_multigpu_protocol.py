@@ -4,6 +4,7 @@ reduction must equal the single-process totals."""
 import os
 import sys
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -58,18 +59,22 @@ def _worker(rank, world, n_batches, port, out):
     dist.destroy_process_group()
 
 
-def test_ring_hand_off_matches_single_process():
-    n_batches, world = 9, 2
+@pytest.mark.parametrize("n_batches,world,port", [(9, 2, 29531), (7, 3, 29541), (2, 4, 29551), (8, 4, 29561)])
+def test_ring_hand_off_matches_single_process(n_batches, world, port):
+    """Odd batch counts, a world that does not divide them, and more ranks than batches (idle ranks still take part in the
+    hand-off ring, the reduce and the gather)."""
     single = FakeEngine()
     multigpu.run_sharded(single, n_batches, 0, 1, torch.device("cpu"))
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, n_batches, 29531, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, n_batches, port, out), nprocs=world, join=True)
     merged = {}
     for r in range(world):
         merged.update(out[r][0])
     assert merged == single.log
     assert torch.equal(out[0][1], single.acc)
-    # rank 0 received exactly the variable-size state of rank 1
-    assert out[0][3] == {0: [out[1][2][0]], 1: [out[1][2][1]]}
-    assert sorted(out[0][2][1] + out[1][2][1]) == sorted(single.var[1])
+    # rank 0 received exactly the variable-size state of the other ranks, in rank order
+    # (a rank that holds nothing sends nothing)
+    want = {w: [out[r][2][w] for r in range(1, world) if out[r][2][w]] for w in (0, 1)}
+    assert {w: v for w, v in out[0][3].items() if v} == {w: v for w, v in want.items() if v}
+    assert sorted(sum((out[r][2][1] for r in range(world)), [])) == sorted(single.var[1])
