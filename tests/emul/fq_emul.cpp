@@ -15,6 +15,7 @@
 #include "../../fastquick_b200/csrc/fq_hostmath.h"
 #include "../../fastquick_b200/csrc/fq_index.h"
 #include "../../fastquick_b200/csrc/fq_relayout.h"
+#include "../../fastquick_b200/csrc/fq_stats_host.h"
 
 using namespace fqb;
 
@@ -221,6 +222,65 @@ int emul_sw_refine(void *h, const fqb_pe_opt_t *popt, int n_pairs, int stride, c
         correct_trimmed(s);
     }
     return 0;
+}
+
+}  // extern "C"
+
+// Row a12 without a GPU: the device function classify_pair (StatCollector::AddAlignment / ProcessPairStatus) over final
+// rows, pair by pair in file order with host-side accumulators, and the product's own InsertSizeTable formatter on the
+// PairStat it leaves.  State (insert-size histogram, duplicate keys, contig counters) persists across batches.
+struct EmulStats {
+    StatsTables T;
+    std::vector<uint32_t> contig_ctr, contig_first;
+    std::vector<unsigned long long> isize_dist, scalars, dup_keys;
+    unsigned long long dup_count = 0;
+    StatAccum A;
+    unsigned long long fsc[5] = {0, 0, 0, 0, 0};     // both_filtered, both_unmapped, low_mapq, retained, bases
+};
+
+extern "C" {
+
+void *emul_stats_open(void *h, const char *index_prefix, const fqb_gap_opt_t *gopt, char *err, int errlen) {
+    Emul *e = (Emul *)h;
+    EmulStats *s = new EmulStats();
+    std::string msg;
+    if (!build_stats_tables(e->idx, index_prefix, *gopt, "", s->T, msg)) { strncpy(err, msg.c_str(), errlen - 1); delete s; return nullptr; }
+    const size_t nc = s->T.contigs.size();
+    s->contig_ctr.assign(nc * 4, 0); s->contig_first.assign(nc, 0xffffffffu);
+    s->isize_dist.assign(4096, 0); s->scalars.assign(16, 0); s->dup_keys.assign(1u << 16, 0);
+    s->A.contig_ctr = s->contig_ctr.data(); s->A.contig_first = s->contig_first.data();
+    s->A.isize_dist = s->isize_dist.data(); s->A.scalars = s->scalars.data();
+    s->A.dup_keys = s->dup_keys.data(); s->A.dup_cap = (uint32_t)s->dup_keys.size(); s->A.dup_count = &s->dup_count;
+    return s;
+}
+void emul_stats_close(void *st) { delete (EmulStats *)st; }
+
+// rows: final rows of one batch (r = 2 * pair + end), modified as AddAlignment modifies them (bridge-check demotions).
+// Appends the batch's InsertSizeTable lines to out; returns their length, or -1 if cap is too small.
+long long emul_stats_batch(void *st, int n_pairs, unsigned long long pair_base, int cal_dup, fqb_read_t *rows, uint8_t *add_out, char *out, long long cap) {
+    EmulStats *s = (EmulStats *)st;
+    std::string text;
+    char name[32];
+    for (int p = 0; p < n_pairs; ++p) {
+        PairStat o;
+        classify_pair(s->T.contigs.data(), (int)s->T.contigs.size(), rows[2 * p], rows[2 * p + 1], (uint32_t)(pair_base + p), cal_dup, s->A, o);
+        s->fsc[0] += o.both_filtered; s->fsc[1] += o.both_unmapped; s->fsc[2] += o.low_mapq; s->fsc[3] += o.retained;
+        s->fsc[4] += (unsigned long long)(rows[2 * p].full_len + rows[2 * p + 1].full_len);
+        if (add_out) { add_out[2 * p] = o.add[0]; add_out[2 * p + 1] = o.add[1]; }
+        if (o.line_kind == 0) continue;
+        snprintf(name, sizeof name, "r%011llu", pair_base + p);
+        append_isize_line(s->T, o, rows[2 * p], rows[2 * p + 1], name, text);
+    }
+    if ((long long)text.size() > cap) return -1;
+    memcpy(out, text.data(), text.size());
+    return (long long)text.size();
+}
+void emul_stats_totals(void *st, unsigned long long *isize_dist /*4096*/, unsigned long long *fsc /*5*/, unsigned long long *scalars /*16*/, unsigned long long *dup_count) {
+    EmulStats *s = (EmulStats *)st;
+    memcpy(isize_dist, s->isize_dist.data(), 4096 * 8);
+    memcpy(fsc, s->fsc, sizeof s->fsc);
+    memcpy(scalars, s->scalars.data(), 16 * 8);
+    *dup_count = s->dup_count;
 }
 
 }  // extern "C"

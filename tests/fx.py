@@ -41,7 +41,7 @@ def build_oracle():
 
 def build_emul():
     srcs = [os.path.join(HERE, "emul", "fq_emul.cpp")] + [
-        os.path.join(REPO, "fastquick_b200", "csrc", f) for f in ("fq_index.cpp", "fq_relayout.cpp", "fq_hostmath.cpp")]
+        os.path.join(REPO, "fastquick_b200", "csrc", f) for f in ("fq_index.cpp", "fq_relayout.cpp", "fq_hostmath.cpp", "fq_stats_host.cpp")]
     import glob
     deps = srcs + glob.glob(os.path.join(REPO, "fastquick_b200", "csrc", "*.cuh")) + glob.glob(os.path.join(REPO, "fastquick_b200", "csrc", "*.h")) + \
         [os.path.join(REPO, "include", "fastquick_b200.h")]

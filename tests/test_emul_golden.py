@@ -72,3 +72,57 @@ def test_emulated_pair_sw_refine_against_golden(small_index, name):
     finally:
         lib.emul_close.argtypes = [C.c_void_p]
         lib.emul_close(h)
+
+
+@pytest.mark.parametrize("name", list(make_golden.CASES))
+def test_emulated_pair_classification_against_golden(small_index, name):
+    """Row a12: the device function classify_pair (AddAlignment / ProcessPairStatus) over the reference's final rows, then
+    the product's InsertSizeTable formatter: the lines must be the reference's InsertSizeTable, the insert-size histogram
+    its RawInsertSizeDist."""
+    arrs, g, n, batch = _case(small_index, name)
+    lib = fx.build_emul()
+    lib.emul_open.restype = C.c_void_p
+    lib.emul_stats_open.restype = C.c_void_p
+    lib.emul_stats_open.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_char_p, C.c_int]
+    lib.emul_stats_batch.restype = C.c_longlong
+    lib.emul_stats_batch.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_longlong]
+    lib.emul_stats_totals.argtypes = [C.c_void_p] * 5
+    lib.emul_stats_close.argtypes = [C.c_void_p]
+    lib.emul_close.argtypes = [C.c_void_p]
+    err = C.create_string_buffer(256)
+    h = C.c_void_p(lib.emul_open(small_index.prefix.encode(), err, 256))
+    assert h, err.value
+    gopt = _abi.GapOpt(); fx.host_lib().fqb_gap_opt_default(C.byref(gopt)); gopt.trim_qual = 15
+    cwd = os.getcwd()
+    os.chdir(small_index.dir)                     # the index's .param names its side files relative to its directory
+    try:
+        st = C.c_void_p(lib.emul_stats_open(h, small_index.prefix.encode(), C.byref(gopt), err, 256))
+        assert st, err.value
+    finally:
+        os.chdir(cwd)
+    try:
+        text = b""
+        n_add = 0
+        for b in range(n // batch):
+            rows = np.zeros(2 * batch, _abi.READ_DTYPE)
+            for e in (0, 1):
+                rows[e::2] = g["b%d_e%d_rows3" % (b, e)]
+            add = np.zeros(2 * batch, np.uint8)
+            buf = C.create_string_buffer(batch * 256)
+            k = lib.emul_stats_batch(st, batch, b * batch, 0, rows.ctypes.data_as(C.c_void_p), add.ctypes.data_as(C.c_void_p), buf, len(buf))
+            assert k >= 0
+            text += buf.raw[:k]
+            n_add += int(add.sum())
+        d = os.path.join(GOLD, "stats_" + name)
+        want = open(os.path.join(d, "InsertSizeTable"), "rb").read()
+        assert text.splitlines() == want.splitlines()
+        assert len(want.splitlines()) > 100 and n_add > 100
+        isize = np.zeros(4096, np.uint64); fsc = np.zeros(5, np.uint64); scal = np.zeros(16, np.uint64); dup = C.c_ulonglong()
+        lib.emul_stats_totals(st, isize.ctypes.data_as(C.c_void_p), fsc.ctypes.data_as(C.c_void_p), scal.ctypes.data_as(C.c_void_p), C.byref(dup))
+        raw = [l.split("\t") for l in open(os.path.join(d, "RawInsertSizeDist")).read().splitlines()]
+        assert [int(r[0]) for r in raw] == list(range(4096))
+        assert [int(r[1]) for r in raw] == [int(v) for v in isize]
+        assert int(fsc[4]) == 2 * n * arrs[0].shape[1]
+    finally:
+        lib.emul_stats_close(st)
+        lib.emul_close(h)
