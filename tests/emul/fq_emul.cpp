@@ -236,6 +236,10 @@ struct EmulStats {
     unsigned long long dup_count = 0;
     StatAccum A;
     unsigned long long fsc[5] = {0, 0, 0, 0, 0};     // both_filtered, both_unmapped, low_mapq, retained, bases
+    std::vector<uint32_t> depth, q20, q30;            // [n_sites]
+    std::vector<unsigned long long> emp;              // [4][256]
+    std::vector<PileupColumn> pileup;                 // [n_markers]
+    unsigned long long n_reads = 0;
 };
 
 extern "C" {
@@ -251,6 +255,9 @@ void *emul_stats_open(void *h, const char *index_prefix, const fqb_gap_opt_t *go
     s->A.contig_ctr = s->contig_ctr.data(); s->A.contig_first = s->contig_first.data();
     s->A.isize_dist = s->isize_dist.data(); s->A.scalars = s->scalars.data();
     s->A.dup_keys = s->dup_keys.data(); s->A.dup_cap = (uint32_t)s->dup_keys.size(); s->A.dup_count = &s->dup_count;
+    const size_t ns = s->T.n_sites ? s->T.n_sites : 1;
+    s->depth.assign(ns, 0); s->q20.assign(ns, 0); s->q30.assign(ns, 0); s->emp.assign(4 * 256, 0);
+    s->pileup.assign(s->T.markers.size(), PileupColumn());
     return s;
 }
 void emul_stats_close(void *st) { delete (EmulStats *)st; }
@@ -281,6 +288,80 @@ void emul_stats_totals(void *st, unsigned long long *isize_dist /*4096*/, unsign
     memcpy(fsc, s->fsc, sizeof s->fsc);
     memcpy(scalars, s->scalars.data(), 16 * 8);
     *dup_count = s->dup_count;
+}
+
+}  // extern "C"
+
+// Rows a13 / a14 without a GPU.  emul_stats_bases is a SERIAL RESTATEMENT of bases_kernel's per-base walk
+// (fq_stats_kernels.cu; AddSingleAlignment, src/StatCollector.cpp:424-621) - reads in file order, offsets in order, which
+// is the arrival order the kernel's tuple keys sort back into - so what it pins is everything around that loop: the
+// add[] decisions of classify_pair, the side tables of build_stats_tables and the writers of write_summary_files.
+extern "C" {
+
+int emul_stats_bases(void *st, void *h, int n_reads, int stride, const uint8_t *codes /*nt4, as sequenced*/, const uint8_t *quals /*ASCII*/,
+                     const fqb_read_t *rows, const uint8_t *add) {
+    EmulStats *s = (EmulStats *)st;
+    Emul *e = (Emul *)h;
+    const uint8_t *pac = e->idx.pac.data();
+    for (int r = 0; r < n_reads; ++r) {
+        if (!add[r]) continue;
+        const fqb_read_t &row = rows[r];
+        const uint8_t *fwd = codes + (size_t)r * stride, *ql = quals + (size_t)r * stride;
+        const int full = row.full_len;
+        for (int off = 0; off < full; ++off) {
+            bool is_m = false;
+            uint32_t x = 0;
+            if (row.has_cigar) {
+                int y = 0; uint32_t xx = row.pos;
+                for (int k = 0; k < row.n_cigar; ++k) {
+                    const int op = row.cigar[k] >> 14, cl = row.cigar[k] & 0x3fff;
+                    if (op == kOpM) { if (off < y + cl) { is_m = true; x = xx + (uint32_t)(off - y); break; } y += cl; xx += cl; }
+                    else if (op == kOpD) xx += cl;
+                    else { if (off < y + cl) break; y += cl; }
+                }
+            } else { is_m = off < row.len; x = row.pos + (uint32_t)off; }
+            if (!is_m) continue;
+            const int fo = row.strand ? full - 1 - off : off;
+            uint32_t rb = fwd[fo]; if (row.strand && rb < 4) rb = 3 - rb;
+            const uint32_t q = (uint32_t)ql[fo] - 33u;
+            const int cycle = fo;
+            const uint32_t site = s->T.site[x];
+            if (site & kSiteMarker) {
+                PileupColumn &c = s->pileup[(size_t)s->T.marker_at[x]];
+                c.seq.push_back("ACGTN"[rb > 4 ? 4 : rb]); c.qual.push_back((char)q); c.cycle.push_back(cycle);
+                c.maq.push_back((unsigned char)(row.mapQ + 33)); c.strand.push_back(row.strand != 0);
+            }
+            if ((site & kSiteMask) == kSiteNone) continue;
+            const uint32_t sid = site & kSiteMask;
+            ++s->depth[sid];
+            if ((int8_t)q >= 20) { ++s->q20[sid]; if ((int8_t)q >= 30) ++s->q30[sid]; }
+            const uint32_t refb = pac[x >> 2] >> ((~x & 3) << 1) & 3;
+            const bool mis = rb < 4 && refb != rb && !(site & kSiteDbsnp);
+            ++s->emp[0 * 256 + (q & 255)]; ++s->emp[2 * 256 + ((uint32_t)cycle & 255)];
+            if (mis) { ++s->emp[1 * 256 + (q & 255)]; ++s->emp[3 * 256 + ((uint32_t)cycle & 255)]; }
+        }
+    }
+    s->n_reads += (unsigned long long)n_reads;
+    return 0;
+}
+
+// StatsTotals from the accumulators, then the product's writers (the InsertSizeTable must already be at <prefix>.InsertSizeTable)
+int emul_stats_finish(void *st, const fqb_gap_opt_t *gopt, const char *out_prefix, const char *fq1, const char *fq2, char *err, int errlen) {
+    EmulStats *s = (EmulStats *)st;
+    StatsTotals S;
+    S.depth = s->depth; S.q20 = s->q20; S.q30 = s->q30; S.emp = s->emp; S.isize_dist = s->isize_dist;
+    S.num_pcr_dup = s->scalars[0]; S.num_pair_reads = s->scalars[1];
+    S.contig_ctr = s->contig_ctr; S.contig_first = s->contig_first;
+    S.pileup = s->pileup;
+    FileCounters F;
+    F.FileName1 = fq1; F.FileName2 = fq2;
+    F.TotalFiltered = (long long)s->fsc[0]; F.BwaUnmapped = (long long)s->fsc[1]; F.TotalMAPQ = (long long)s->fsc[2];
+    F.TotalRetained = (long long)s->fsc[3]; F.NumBase = (long long)s->fsc[4]; F.NumRead = (long long)s->n_reads;
+    S.files.push_back(F);
+    std::string msg;
+    if (s->scalars[2]) { strncpy(err, "insert size out of range or duplicate table full", errlen - 1); return -1; }
+    if (!write_summary_files(s->T, S, *gopt, out_prefix, msg)) { strncpy(err, msg.c_str(), errlen - 1); return -1; }
+    return 0;
 }
 
 }  // extern "C"

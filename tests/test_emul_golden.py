@@ -126,3 +126,58 @@ def test_emulated_pair_classification_against_golden(small_index, name):
     finally:
         lib.emul_stats_close(st)
         lib.emul_close(h)
+
+
+@pytest.mark.parametrize("name", list(make_golden.CASES))
+def test_emulated_statistics_files_against_golden(small_index, name, tmp_path):
+    """Rows a12-a14 end to end without a GPU: classify_pair (device function) decides which reads are added, a serial
+    restatement of bases_kernel's per-base walk fills the accumulators over the side tables of build_stats_tables, and the
+    product's write_summary_files writes the 12 files - compared with the reference's own (integers exact, floats 1e-9)."""
+    from test_golden import _same_text
+    arrs, g, n, batch = _case(small_index, name)
+    lib = fx.build_emul()
+    lib.emul_open.restype = C.c_void_p
+    lib.emul_stats_open.restype = C.c_void_p
+    lib.emul_stats_open.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_char_p, C.c_int]
+    lib.emul_stats_batch.restype = C.c_longlong
+    lib.emul_stats_batch.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p, C.c_char_p, C.c_longlong]
+    lib.emul_stats_bases.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.emul_stats_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+    lib.emul_stats_close.argtypes = [C.c_void_p]
+    lib.emul_close.argtypes = [C.c_void_p]
+    err = C.create_string_buffer(256)
+    h = C.c_void_p(lib.emul_open(small_index.prefix.encode(), err, 256))
+    assert h, err.value
+    gopt = _abi.GapOpt(); fx.host_lib().fqb_gap_opt_default(C.byref(gopt)); gopt.trim_qual = 15
+    mine = str(tmp_path / "mine")
+    cwd = os.getcwd()
+    os.chdir(small_index.dir)
+    st = None
+    try:
+        st = C.c_void_p(lib.emul_stats_open(h, small_index.prefix.encode(), C.byref(gopt), err, 256))
+        assert st, err.value
+        rl = arrs[0].shape[1]
+        with open(mine + ".InsertSizeTable", "wb") as table:
+            for b in range(n // batch):
+                rows = np.zeros(2 * batch, _abi.READ_DTYPE)
+                for e in (0, 1):
+                    rows[e::2] = g["b%d_e%d_rows3" % (b, e)]
+                add = np.zeros(2 * batch, np.uint8)
+                buf = C.create_string_buffer(batch * 256)
+                k = lib.emul_stats_batch(st, batch, b * batch, 1, rows.ctypes.data_as(C.c_void_p), add.ctypes.data_as(C.c_void_p), buf, len(buf))
+                assert k >= 0
+                table.write(buf.raw[:k])
+                sub = [np.ascontiguousarray(a[b * batch:(b + 1) * batch]) for a in arrs]
+                codes = np.zeros((2 * batch, rl), np.uint8); quals = np.zeros((2 * batch, rl), np.uint8)
+                codes[0::2] = fx.NT4[sub[0]]; codes[1::2] = fx.NT4[sub[2]]
+                quals[0::2] = sub[1]; quals[1::2] = sub[3]
+                assert lib.emul_stats_bases(st, h, 2 * batch, rl, codes.ctypes.data_as(C.c_void_p), quals.ctypes.data_as(C.c_void_p),
+                                            rows.ctypes.data_as(C.c_void_p), add.ctypes.data_as(C.c_void_p)) == 0
+        assert lib.emul_stats_finish(st, C.byref(gopt), mine.encode(), b"r1.fq", b"r2.fq", err, 256) == 0, err.value
+    finally:
+        os.chdir(cwd)
+        if st: lib.emul_stats_close(st)
+        lib.emul_close(h)
+    d = os.path.join(GOLD, "stats_" + name)
+    for ext in make_golden.STAT_FILES:
+        _same_text(os.path.join(d, ext), mine + "." + ext, sort_lines=(ext == "SexChromInfo"))
