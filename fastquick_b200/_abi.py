@@ -47,7 +47,7 @@ class ISize(C.Structure):
 
 class SynthRefCfg(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_long", C.c_int32), ("n_short", C.c_int32), ("n_x", C.c_int32),
-                ("n_y", C.c_int32), ("flank_short", C.c_int32), ("flank_long", C.c_int32), ("spacing", C.c_int32)]
+                ("n_y", C.c_int32), ("flank_short", C.c_int32), ("flank_long", C.c_int32), ("spacing", C.c_int32), ("n_dup", C.c_int32)]
 
 
 class SynthReadCfg(C.Structure):

@@ -46,7 +46,7 @@ struct fqb_synth { fqb::SynthRef ref; };
 void fqb_synth_ref_cfg_default(fqb_synth_ref_cfg_t *c) {
     fqb::SynthRefConfig d;
     c->seed = d.seed; c->n_long = d.n_long; c->n_short = d.n_short; c->n_x = d.n_x; c->n_y = d.n_y;
-    c->flank_short = d.flank_short; c->flank_long = d.flank_long; c->spacing = d.spacing;
+    c->flank_short = d.flank_short; c->flank_long = d.flank_long; c->spacing = d.spacing; c->n_dup = d.n_dup;
 }
 void fqb_synth_read_cfg_default(fqb_synth_read_cfg_t *c) {
     fqb::SynthReadConfig d;
@@ -58,8 +58,8 @@ int fqb_synth_create(const fqb_synth_ref_cfg_t *c, fqb_synth **out) {
     if (!c || !out) { fqb::set_error("null argument"); return FQB_ERR_ARG; }
     fqb::SynthRefConfig cfg;
     cfg.seed = c->seed; cfg.n_long = c->n_long; cfg.n_short = c->n_short; cfg.n_x = c->n_x; cfg.n_y = c->n_y;
-    cfg.flank_short = c->flank_short; cfg.flank_long = c->flank_long; cfg.spacing = c->spacing;
-    if (cfg.spacing < 2 * cfg.flank_long + 102 || cfg.n_long + cfg.n_short < 1) { fqb::set_error("bad synthetic reference shape"); return FQB_ERR_ARG; }
+    cfg.flank_short = c->flank_short; cfg.flank_long = c->flank_long; cfg.spacing = c->spacing; cfg.n_dup = c->n_dup;
+    if (cfg.spacing < 2 * cfg.flank_long + 102 || cfg.n_long + cfg.n_short < 1 || cfg.n_dup < 0 || cfg.flank_short < 230) { fqb::set_error("bad synthetic reference shape"); return FQB_ERR_ARG; }
     fqb_synth *s = new fqb_synth();
     fqb::synth_reference(cfg, s->ref);
     *out = s;

@@ -59,6 +59,22 @@ void synth_reference(const SynthRefConfig &cfg, SynthRef &out) {
             for (size_t k = 0; k < 32 && i + k < len; ++k, r >>= 2) s[i + k] = kBase[r & 3];
         }
     }
+    // Planted repeats: a random genome has none, so the paths that only repeats reach (several occurrences per SA interval,
+    // bwa_aln2seq_core's random pick, mapQ 0, pairing over many positions, XA lists) would never run.  Each copy takes the
+    // 200 bases that start 20 bases right of one marker and writes them at the same offset of another marker; its own
+    // generator keeps the main stream, and with it every existing fixture, unchanged.
+    if (cfg.n_dup > 0) {
+        Rng dup(cfg.seed ^ 0xD0B1E5EEDull);
+        std::vector<std::pair<int, int>> sites;                  // (chromosome, 0-based marker position)
+        for (int c = 0; c < 24; ++c) for (int m = 0; m < per_chrom[c]; ++m) sites.emplace_back(c, lead + cfg.spacing * m);
+        for (int d = 0; d < cfg.n_dup && sites.size() >= 2; ++d) {
+            const size_t a = dup.below((uint32_t)sites.size());
+            size_t b = dup.below((uint32_t)sites.size() - 1);
+            if (b >= a) ++b;
+            const std::string seg = out.chrom_seq[sites[a].first].substr((size_t)sites[a].second + 20, 200);
+            out.chrom_seq[sites[b].first].replace((size_t)sites[b].second + 20, 200, seg);
+        }
+    }
     // markers in genome (VCF) order; the first n_long autosomal records become long (RefBuilder::IsMaxNumMarker)
     int n_long_seen = 0;
     for (int c = 0; c < 24; ++c) {

@@ -26,6 +26,7 @@ struct SynthRefConfig {
     int n_long = 1000, n_short = 9000, n_x = 100, n_y = 97;
     int flank_short = 250, flank_long = 1000;
     int spacing = 3000;   // distance between neighbouring markers on a chromosome
+    int n_dup = 0;        // segments of 200 bases copied from one marker's flank into another's (exact repeats: REPEAT-type reads)
 };
 
 struct SynthRef {

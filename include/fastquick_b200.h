@@ -282,6 +282,7 @@ typedef struct {
     uint64_t seed;
     int32_t n_long, n_short, n_x, n_y;
     int32_t flank_short, flank_long, spacing;
+    int32_t n_dup;       /* 200-bp segments copied from one marker's flank into another's: exact repeats in the index (default 0) */
 } fqb_synth_ref_cfg_t;
 typedef struct {
     uint64_t seed;

@@ -65,13 +65,14 @@ class SynthIndex:
     """A small synthetic reduced reference, built by the product's fixture builder
     (validated byte-for-byte against `FASTQuick_ref index` in test_index_build.py)."""
 
-    def __init__(self, name, n_long=40, n_short=160, n_x=5, n_y=5, seed=0x5EED0001, with_rollhash=True):
+    def __init__(self, name, n_long=40, n_short=160, n_x=5, n_y=5, seed=0x5EED0001, with_rollhash=True, n_dup=0):
         lib = host_lib()
         self.dir = os.path.join(CACHE, name)
         os.makedirs(self.dir, exist_ok=True)
         cfg = _abi.SynthRefCfg()
         lib.fqb_synth_ref_cfg_default(C.byref(cfg))
         cfg.seed, cfg.n_long, cfg.n_short, cfg.n_x, cfg.n_y = seed, n_long, n_short, n_x, n_y
+        cfg.n_dup = n_dup                                    # planted 200-base repeats between flanks
         self.cfg = cfg
         self.h = C.c_void_p()
         assert lib.fqb_synth_create(C.byref(cfg), C.byref(self.h)) == 0, lib.fqb_last_error()

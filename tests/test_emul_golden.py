@@ -21,7 +21,8 @@ from test_golden import FIELDS, _case, _cigars_equal  # noqa: E402
 
 
 @pytest.mark.parametrize("name", list(make_golden.CASES))
-def test_emulated_pair_sw_refine_against_golden(small_index, name):
+def test_emulated_pair_sw_refine_against_golden(name):
+    small_index = make_golden.index_for(name)
     arrs, g, n, batch = _case(small_index, name)
     lib = fx.build_emul()
     lib.emul_open.restype = C.c_void_p
@@ -75,10 +76,11 @@ def test_emulated_pair_sw_refine_against_golden(small_index, name):
 
 
 @pytest.mark.parametrize("name", list(make_golden.CASES))
-def test_emulated_pair_classification_against_golden(small_index, name):
+def test_emulated_pair_classification_against_golden(name):
     """Row a12: the device function classify_pair (AddAlignment / ProcessPairStatus) over the reference's final rows, then
     the product's InsertSizeTable formatter: the lines must be the reference's InsertSizeTable, the insert-size histogram
     its RawInsertSizeDist."""
+    small_index = make_golden.index_for(name)
     arrs, g, n, batch = _case(small_index, name)
     lib = fx.build_emul()
     lib.emul_open.restype = C.c_void_p
@@ -129,11 +131,12 @@ def test_emulated_pair_classification_against_golden(small_index, name):
 
 
 @pytest.mark.parametrize("name", list(make_golden.CASES))
-def test_emulated_statistics_files_against_golden(small_index, name, tmp_path):
+def test_emulated_statistics_files_against_golden(name, tmp_path):
     """Rows a12-a14 end to end without a GPU: classify_pair (device function) decides which reads are added, a serial
     restatement of bases_kernel's per-base walk fills the accumulators over the side tables of build_stats_tables, and the
     product's write_summary_files writes the 12 files - compared with the reference's own (integers exact, floats 1e-9)."""
     from test_golden import _same_text
+    small_index = make_golden.index_for(name)
     arrs, g, n, batch = _case(small_index, name)
     lib = fx.build_emul()
     lib.emul_open.restype = C.c_void_p

@@ -13,7 +13,7 @@ import fx
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("case", ["stats_pe100", "stats_pe150_indel", "stats_pe100_higherr"])
+@pytest.mark.parametrize("case", ["stats_pe100", "stats_pe150_indel", "stats_pe100_higherr", "stats_pe100_repeats"])
 def test_adjusted_insert_size_dist_matches_reference(tmp_path, case):
     lib = fx.host_lib()
     lib.fqb_isize_adjusted_file.argtypes = [C.c_char_p, C.c_char_p]

@@ -108,6 +108,7 @@ def test_maxdiff_and_log_n_tables_match_oracle():
     orc.orc_cal_maxdiff.argtypes = [C.c_int, C.c_double, C.c_double]
     g = _abi.GapOpt()
     lib.fqb_gap_opt_default(C.byref(g))
+    lib.fqb_host_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     md = np.zeros(257, np.int32); ln = np.zeros(256, np.int32)
     for fnr in (0.04, 0.02, 0.001):                              # 0.02 is FASTQuick's (max_diff 5 / 7 at 100 / 150 bp)
         g.fnr = fnr
