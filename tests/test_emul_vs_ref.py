@@ -59,6 +59,15 @@ def test_lanes_free_list_arena(small_index, ref_required):
     _check(small_index, small_index.reads(600, read_len=100, seed=33), "emfl", arena_cap=70000)
 
 
+def test_lanes_repeats(ref_required):
+    """An index with planted exact repeats: SA intervals wider than one row, hits of equal score on both copies."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    index = make_golden.index_for("pe100_repeats")
+    _check(index, index.reads(1500, read_len=100, seed=78, sub_rate=0.02), "emrep")
+
+
 def test_occ_and_sa_against_oracle(small_index):
     import oracle_py
     lib, h = _emul(small_index)
