@@ -71,3 +71,31 @@ def test_drand48_stream_is_glibc(ref_required):
     libc.srand48(C.c_long(11))
     for _ in range(2000):
         assert lib.orc_drand48(C.byref(r)) == libc.drand48()
+
+
+def test_multi_hit_positions_on_repeats(ref_required):
+    """bwa_cal_pac_pos_pe's multi-hit lists (the XA candidates; src/BwtMapper.cpp:857-871) on an index with planted exact
+    repeats: every read that keeps other hits lists the same positions, in the same order, as the reference."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    index = make_golden.index_for("pe100_repeats")
+    n = 600
+    arrs = index.reads(n, read_len=100, seed=77)
+    fq = index.write_fastq("orcrep", arrs)
+    ref = fx.RefRun(index.prefix, fq[0], fq[1], trim_qual=15)
+    assert ref.next_batch() == n
+    orc = oracle_py.Oracle(index.prefix)
+    lens, filt, out, na = orc.align_batch(arrs, trim_qual=15, kmer_thresh=3, cap=8)
+    full = np.zeros(2 * n, np.int32)
+    full[0::2] = ref.rows(0, 0)["full_len"]; full[1::2] = ref.rows(0, 1)["full_len"]
+    rows, ii, multi = orc.pe_batch(lens, full, filt, out, na, cap=8, want_multi=True)
+    seen = 0
+    for e in (0, 1):
+        want, r1 = ref.multi(e), ref.rows(1, e)
+        np.testing.assert_array_equal(rows[e::2]["n_multi"], r1["n_multi"])
+        for i in np.where(r1["n_multi"] > 0)[0]:
+            k = int(r1["n_multi"][i])
+            assert want[i, :k, 0].tolist() == multi[2 * i + e, :k].tolist(), (e, i)
+            seen += 1
+    assert seen > 50
