@@ -1,4 +1,5 @@
 #include "fq_hostmath.h"
+#include "fq_common.h"
 #include <cmath>
 
 namespace fqb {
@@ -94,11 +95,11 @@ void fill_isize_penalty(const fqb_isize_t &ii, std::vector<int32_t> &t) {
 // The host half of infer_isize and the pairing penalty table on their own (host only; the device supplies the histogram
 // in the product path, fq_engine.cu: fqb_stage_pair).
 extern "C" int fqb_infer_isize_hist(const uint32_t *hist, int32_t max_len, double ap_prior, int64_t L, fqb_isize_t *ii) {
-    if (!hist || !ii || L <= 0) return FQB_ERR_ARG;
+    if (!hist || !ii || L <= 0) { fqb::set_error("bad argument"); return FQB_ERR_ARG; }
     return fqb::infer_isize_hist(hist, max_len, ap_prior, L, *ii) ? 1 : 0;
 }
 extern "C" int64_t fqb_isize_penalty(const fqb_isize_t *ii, int32_t *out, int64_t cap) {
-    if (!ii || (!out && cap > 0) || cap < 0) return FQB_ERR_ARG;
+    if (!ii || (!out && cap > 0) || cap < 0) { fqb::set_error("bad argument"); return FQB_ERR_ARG; }
     std::vector<int32_t> t;
     fqb::fill_isize_penalty(*ii, t);
     for (int64_t i = 0; i < (int64_t)t.size() && i < cap; ++i) out[i] = t[(size_t)i];
@@ -107,7 +108,7 @@ extern "C" int64_t fqb_isize_penalty(const fqb_isize_t *ii, int32_t *out, int64_
 
 // The libm-dependent tables the engine ships to the device (bwa_cal_maxdiff per read length, g_log_n), host only.
 extern "C" int fqb_host_tables(const fqb_gap_opt_t *gopt, int32_t *maxdiff /*FQB_MAX_READ_LEN + 1*/, int32_t *log_n /*256*/) {
-    if (!gopt || !maxdiff || !log_n) return FQB_ERR_ARG;
+    if (!gopt || !maxdiff || !log_n) { fqb::set_error("null argument"); return FQB_ERR_ARG; }
     fqb::fill_maxdiff_table(*gopt, maxdiff);
     fqb::fill_log_n(log_n);
     return FQB_OK;
@@ -116,6 +117,6 @@ extern "C" int fqb_host_tables(const fqb_gap_opt_t *gopt, int32_t *maxdiff /*FQB
 // gap_init_stack's bucket count (libbwa/bwtgap.c:18) for a batch whose longest read has max_len bases, with the max_gapo
 // clamp of src/BwtMapper.cpp:73-81 applied: what sizes the per-read score-bucket heads in search_kernel.
 extern "C" int fqb_search_buckets(const fqb_gap_opt_t *gopt, int32_t max_len) {
-    if (!gopt || max_len < 0 || max_len > FQB_MAX_READ_LEN) return FQB_ERR_ARG;
+    if (!gopt || max_len < 0 || max_len > FQB_MAX_READ_LEN) { fqb::set_error("bad argument"); return FQB_ERR_ARG; }
     return fqb::make_search_opt(*gopt, max_len).n_buckets;
 }

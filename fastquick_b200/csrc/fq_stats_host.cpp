@@ -1,6 +1,7 @@
 // See fq_stats_host.h.  Output formatting goes through std::ostream exactly like the
 // reference's writers, so doubles print with the same default 6-significant-digit rule.
 #include "fq_stats_host.h"
+#include "fq_common.h"
 
 #include <algorithm>
 #include <chrono>
@@ -510,7 +511,8 @@ bool write_summary_files(const StatsTables &T, StatsTotals &S, const fqb_gap_opt
 
 // InsertSizeEstimator on a finished InsertSizeTable (host only; what fqb_stats_finish runs for <prefix>.AdjustedInsertSizeDist)
 extern "C" int fqb_isize_adjusted_file(const char *table_path, const char *out_path) {
-    if (!table_path || !out_path) return FQB_ERR_ARG;
-    { std::ifstream probe(table_path); if (!probe) return FQB_ERR_IO; }
-    return fqb::write_adjusted_isize(table_path, out_path) ? FQB_OK : FQB_ERR_IO;
+    if (!table_path || !out_path) { fqb::set_error("null argument"); return FQB_ERR_ARG; }
+    { std::ifstream probe(table_path); if (!probe) { fqb::set_error(std::string("cannot read ") + table_path); return FQB_ERR_IO; } }
+    if (!fqb::write_adjusted_isize(table_path, out_path)) { fqb::set_error(std::string("cannot write ") + out_path); return FQB_ERR_IO; }
+    return FQB_OK;
 }

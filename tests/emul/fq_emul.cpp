@@ -19,6 +19,8 @@
 
 using namespace fqb;
 
+namespace fqb { void set_error(const std::string &) {} }     // the product's error slot lives in fq_capi_host.cpp, which the emulator does not link
+
 static unsigned long long g_stats[16];
 extern "C" void emul_stats(unsigned long long *o) { for (int i = 0; i < 16; ++i) { o[i] = g_stats[i]; g_stats[i] = 0; } }
 struct Emul {
