@@ -252,6 +252,7 @@ struct SearchLane {
     uint32_t n_pops, n_occ, n_blk;
 #ifdef FQB_LANE_STATS
     uint32_t st_iter, st_mempop, st_skip, st_exact, st_expand, st_push, st_hit, st_adiff, st_gapok, st_am;
+    uint32_t st_x[20]; int st_run;
 #define FQB_STAT(x) (++(x))
 #else
 #define FQB_STAT(x) ((void)0)
@@ -303,6 +304,10 @@ struct SearchLane {
         n_entries += cnt;
 #ifdef FQB_LANE_STATS
         st_push += cnt;
+        if (n_aln == 0) st_x[0] += cnt;                 // pushed before the first hit
+        if (n_mm + n_gapo + n_gape == 0) st_x[1] += cnt;  // children of a score-0 (root path) parent
+        if (n_aln > 0 && sc > best_score + opt->s_mm) st_x[2] += cnt;   // dead on arrival (post-hit, beyond the stop score)
+        st_x[3] += 1;                                    // groups
 #endif
         if (top + (uint32_t)cnt > arena_cap) { overflow = true; return; }
         uint32_t prev = bucket_head(sc), s = top;
@@ -324,7 +329,13 @@ struct SearchLane {
 
     // gap_pop (libbwa/bwtgap.c:66-79); the exact-match child of the previous expansion is
     // always the next entry popped, so it never leaves registers.
+#ifdef FQB_LANE_STATS
+    void flush_run() { if (st_run) { st_x[6]++; st_x[7 + (st_run >= 64 ? 6 : st_run >= 32 ? 5 : st_run >= 16 ? 4 : st_run >= 8 ? 3 : st_run >= 4 ? 2 : st_run >= 2 ? 1 : 0)] += st_run; } st_run = 0; }
+#endif
     FQB_HD void pop() {
+#ifdef FQB_LANE_STATS
+        if (!have_cur) flush_run();
+#endif
         --n_entries;
         ++n_pops;
         if (have_cur) { have_cur = false; return; }
@@ -480,6 +491,11 @@ struct SearchLane {
             }
         }
         if (allow_diff) FQB_STAT(st_adiff);
+#ifdef FQB_LANE_STATS
+        if (k == l) st_x[4]++;                           // expansions on a one-row interval
+        if (k == l && allow_diff) st_x[5]++;
+        if (!allow_diff) { ++st_run; } else flush_run();
+#endif
         if (allow_diff && allow_M) FQB_STAT(st_am);
         int gaps = n_gapo + n_gape;
         if (opt->mode & kModeLogGap) { int v = gaps, c = 0; while (v >>= 1) ++c; gaps = c / 2 + 1; }

@@ -272,6 +272,11 @@ uint64_t fqb_launch_count(const fqb_handle *h);   /* kernels launched by this ha
  * fqb_stage_align (bwt_cal_width + bwt_match_gap fast pass) and the number of batches covered */
 int fqb_rank_query_time(const fqb_handle *h, double *ms, uint64_t *launches);
 void *fqb_stream(fqb_handle *h);   /* the cudaStream_t the handle launches on (for event timing) */
+/* BW_L2, the roofline denominator of the rank-query kernels (occ primitives libbwa/bwt.h:89-222): every
+ * thread of a grid that fills all SMs issues independent 256-bit loads at pseudo-random unit_bytes-aligned offsets
+ * (unit_bytes = 32, 64 or 128 contiguous bytes per access, L1 bypassed) of a buffer_bytes buffer (8 MiB: L2-resident
+ * like the FM index); best and median GB/s of `reps` launches after two warm-up launches. */
+int fqb_measure_l2(int device, int64_t buffer_bytes, int32_t unit_bytes, int32_t reps, double *gbs_best, double *gbs_median);
 
 /* ---- synthetic fixtures (bench + tests; hs37d5/dbSNP are not available offline) ----
  * Not part of the drop-in surface: these stand in for `FASTQuick index` output

@@ -21,8 +21,8 @@ using namespace fqb;
 
 namespace fqb { void set_error(const std::string &) {} }     // the product's error slot lives in fq_capi_host.cpp, which the emulator does not link
 
-static unsigned long long g_stats[16];
-extern "C" void emul_stats(unsigned long long *o) { for (int i = 0; i < 16; ++i) { o[i] = g_stats[i]; g_stats[i] = 0; } }
+static unsigned long long g_stats[40];
+extern "C" void emul_stats(unsigned long long *o) { for (int i = 0; i < 40; ++i) { o[i] = g_stats[i]; g_stats[i] = 0; } }
 struct Emul {
     HostIndex idx;
     std::vector<Block32> blocks[2];
@@ -86,7 +86,7 @@ int emul_align(void *h, const fqb_gap_opt_t *gopt, int n, int stride, const uint
             lane.out = reinterpret_cast<Hit *>(out + (size_t)r * out_cap); lane.out_cap = out_cap;
             int n_ambig = 0;
             for (int j = 0; j < len; ++j) n_ambig += f[j] > 3;
-            lane.st_iter = lane.st_mempop = lane.st_skip = lane.st_exact = lane.st_expand = lane.st_push = lane.st_hit = lane.st_adiff = lane.st_gapok = lane.st_am = 0;
+            lane.st_iter = lane.st_mempop = lane.st_skip = lane.st_exact = lane.st_expand = lane.st_push = lane.st_hit = lane.st_adiff = lane.st_gapok = lane.st_am = 0; for (auto &x : lane.st_x) x = 0; lane.st_run = 0;
             LaneStatus st = lane.begin(len, maxdiff[len], n_ambig);
             while (st == kLaneRunning || st == kLaneHit) {
                 if (st == kLaneHit) lane.shadow_serial();
@@ -94,7 +94,7 @@ int emul_align(void *h, const fqb_gap_opt_t *gopt, int n, int stride, const uint
             }
             n_aln[r] = lane.n_aln; status[r] = (int32_t)st;
             g_stats[0] += lane.st_iter; g_stats[1] += lane.st_mempop; g_stats[2] += lane.st_skip; g_stats[3] += lane.st_exact;
-            g_stats[4] += lane.st_expand; g_stats[5] += lane.st_push; g_stats[6] += lane.st_hit; g_stats[7] += lane.top; g_stats[8] += 1; g_stats[9] += lane.st_adiff; g_stats[10] += lane.st_gapok; g_stats[11] += lane.st_am;
+            g_stats[4] += lane.st_expand; g_stats[5] += lane.st_push; g_stats[6] += lane.st_hit; g_stats[7] += lane.top; g_stats[8] += 1; g_stats[9] += lane.st_adiff; g_stats[10] += lane.st_gapok; g_stats[11] += lane.st_am; for (int q = 0; q < 20; ++q) g_stats[12 + q] += lane.st_x[q];
             if (pops_occ) { pops_occ[2 * r] = lane.n_pops; pops_occ[2 * r + 1] = lane.n_occ; }
         };
         if (arena_cap < 65535) { SearchLane<uint16_t, false> lane; lane.heads = heads16.data(); run(lane); }
