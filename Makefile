@@ -28,6 +28,14 @@ $(OBJ)/%.cu.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) in
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lz -lpthread -lcudart
 
+# development variant with per-kind round counters in search_kernel (tools/quick_bench.py --kstats)
+KOBJ := build/kobj
+kstats: fastquick_b200/libfastquick_b200_kstats.so
+fastquick_b200/libfastquick_b200_kstats.so: $(LIB)
+	mkdir -p $(KOBJ)
+	$(NVCC) $(NVFLAGS) -DFQB_KSTATS -c $(CSRC)/fq_kernels.cu -o $(KOBJ)/fq_kernels.cu.o 2> $(KOBJ)/fq_kernels.ptxas.log
+	$(NVCC) $(ARCH) -shared -o $@ $(filter-out $(OBJ)/fq_kernels.cu.o,$(OBJS)) $(KOBJ)/fq_kernels.cu.o -lz -lpthread -lcudart
+
 clean:
 	rm -rf build $(LIB)
-.PHONY: all clean
+.PHONY: all clean kstats

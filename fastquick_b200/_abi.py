@@ -91,8 +91,11 @@ def i32p(a):
     return a.ctypes.data_as(C.POINTER(C.c_int32))
 
 
-def load_library(path=LIB_PATH):
-    """Load the C-ABI library.  There is no CPU fallback: a missing library is an error."""
+def load_library(path=None):
+    """Load the C-ABI library.  There is no CPU fallback: a missing library is an error.
+    FQB_LIB_PATH (development only) names another build of the same library, e.g. `make kstats`."""
+    if path is None:
+        path = os.environ.get("FQB_LIB_PATH", LIB_PATH)
     if not os.path.exists(path):
         raise RuntimeError(
             f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
