@@ -29,11 +29,9 @@ t0 = time.time()
 rc = lib.emul_align(h, C.byref(g), 2 * n, L, _abi.u8p(codes), _abi.i32p(lens), 4096, 8, out.ctypes.data_as(C.c_void_p), _abi.i32p(na), _abi.i32p(st),
                     po.ctypes.data_as(C.POINTER(C.c_uint32)))
 print("emul %.1fs rc %d" % (time.time() - t0, rc))
-s = (C.c_ulonglong * 40)(); lib.emul_stats(s)
+s = (C.c_ulonglong * 16)(); lib.emul_stats(s)
 names = ["iter", "mempop", "skip", "exact", "expand", "push", "hit", "top", "reads", "adiff", "gapok", "am"]
 R = 2 * n
 for i, nm in enumerate(names):
     print("%-8s %12d  %.1f/read" % (nm, s[i], s[i] / R))
-for i in range(12, 40):
-    if s[i]: print("x%-7d %12d  %.2f/read" % (i, s[i], s[i] / R))
 print("pops/read %.1f occ/read %.1f; status!=1: %d; n_aln hist %s" % (po[:, 0].mean(), po[:, 1].mean(), (st != 1).sum(), np.bincount(np.clip(na, 0, 9))))
