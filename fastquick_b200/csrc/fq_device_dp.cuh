@@ -422,6 +422,7 @@ struct SwParams {
     double s_old_add;      // -4.343 * log(ap_prior / l_pac)
     int s_new_add;         // (int)(-4.343 * log(.5 * erfc(M_SQRT1_2 * 1.5) + .499))
     int64_t l_pac;
+    int on;                // popt->is_sw && ii.avg >= 0 (src/BwtMapper.cpp:1975): bwa_paired_sw runs for this batch
 };
 
 // bwa_paired_sw for one pair (libbwa/bwape.c:497-617), BWA_PET_STD.  Returns false if scratch was too small.

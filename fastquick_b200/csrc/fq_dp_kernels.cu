@@ -31,7 +31,8 @@ __device__ __forceinline__ bool next_item(uint32_t *cursor, uint32_t n, uint32_t
 }
 
 // head of bwa_paired_sw's per-pair loop: un-filter rescued mates, collect the pairs that qualify for mate rescue
-__global__ void sw_classify_kernel(DpView v, uint32_t *list, uint32_t *n_list) {
+__global__ void sw_classify_kernel(DpView v, const SwParams *spp, uint32_t *list, uint32_t *n_list) {
+    if (!spp->on) return;              // no mate rescue for this batch (infer_isize failed, or --no-sw)
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     bool need = false;
     if (p < (uint32_t)v.n_reads / 2) {
@@ -74,8 +75,9 @@ __device__ __forceinline__ bool next_item_warp(uint32_t *cursor, uint32_t n, uin
 }
 
 // mate rescue, one pair per warp; pairs whose window exceeds the shared-memory rows go to `retry`
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) sw_warp_kernel(DpView v, SwParams sp, DpPool pool, const uint32_t *list, const uint32_t *n_list,
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) sw_warp_kernel(DpView v, const SwParams *spp, DpPool pool, const uint32_t *list, const uint32_t *n_list,
                                                                        uint32_t *cursor, int smem_ints, int ref_cap, uint32_t *retry, uint32_t *n_retry) {
+    const SwParams sp = *spp;
     extern __shared__ int32_t dp_smem[];
     const WarpDp w = warp_scratch(pool, dp_smem, smem_ints, ref_cap);
     const uint32_t n = *n_list;
@@ -94,8 +96,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) sw_warp_kernel(DpView v, 
 }
 
 // one pair per lane, everything in global scratch (retry list)
-__global__ void __launch_bounds__(kDpThreads) sw_kernel(DpView v, SwParams sp, DpPool pool, const uint32_t *list, const uint32_t *n_list,
+__global__ void __launch_bounds__(kDpThreads) sw_kernel(DpView v, const SwParams *spp, DpPool pool, const uint32_t *list, const uint32_t *n_list,
                                                          uint32_t *cursor, uint32_t *err, uint32_t *huge_list, uint32_t *n_huge) {
+    const SwParams sp = *spp;
     DpScratch sc = lane_scratch(pool);
     const uint32_t n = *n_list;
     uint32_t j;
@@ -115,7 +118,8 @@ __global__ void __launch_bounds__(kDpThreads) sw_kernel(DpView v, SwParams sp, D
 // ---- very wide mate-rescue windows (fq_dp_warp.cuh): prepare the scan jobs, scan the slices, finish the pairs ----
 struct HugeBuf { HugeJob *jobs; uint32_t *slice_job; ScanBest *slice_best; uint32_t *ctr; };   // ctr: [0] n_jobs [1] n_slices [2] scan cursor [3] finish cursor
 
-__global__ void sw_huge_prepare_kernel(DpView v, SwParams sp, const uint32_t *huge_list, const uint32_t *n_huge, HugeBuf hb, int ref_cap, uint32_t *err) {
+__global__ void sw_huge_prepare_kernel(DpView v, const SwParams *spp, const uint32_t *huge_list, const uint32_t *n_huge, HugeBuf hb, int ref_cap, uint32_t *err) {
+    const SwParams sp = *spp;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n = *n_huge < kHugeMaxPairs ? *n_huge : kHugeMaxPairs;
     if (t >= n) return;
@@ -142,7 +146,8 @@ __global__ void sw_huge_prepare_kernel(DpView v, SwParams sp, const uint32_t *hu
     }
 }
 
-__global__ void __launch_bounds__(4 * 32) sw_huge_scan_kernel(DpView v, SwParams sp, HugeBuf hb, int smem_ints, int ref_cap) {
+__global__ void __launch_bounds__(4 * 32) sw_huge_scan_kernel(DpView v, const SwParams *spp, HugeBuf hb, int smem_ints, int ref_cap) {
+    const SwParams sp = *spp;
     extern __shared__ int32_t dp_smem[];
     const int wid = threadIdx.x >> 5;
     WarpDp w;
@@ -166,8 +171,9 @@ __global__ void __launch_bounds__(4 * 32) sw_huge_scan_kernel(DpView v, SwParams
     }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) sw_huge_finish_kernel(DpView v, SwParams sp, DpPool pool, const uint32_t *huge_list, const uint32_t *n_huge,
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) sw_huge_finish_kernel(DpView v, const SwParams *spp, DpPool pool, const uint32_t *huge_list, const uint32_t *n_huge,
                                                                               HugeBuf hb, int smem_ints, int ref_cap, uint32_t *err) {
+    const SwParams sp = *spp;
     extern __shared__ int32_t dp_smem[];
     const WarpDp w = warp_scratch(pool, dp_smem, smem_ints, ref_cap);
     const uint32_t n = *n_huge < kHugeMaxPairs ? *n_huge : kHugeMaxPairs;
@@ -308,9 +314,9 @@ static int warp_blocks(const DpPool &pool) {
 }
 
 // ctr: [0] n_list [1] cursor [2] n_retry [3] retry cursor (device words)
-void launch_sw(const DpView &v, const SwParams &sp, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, void *huge_mem,
+void launch_sw(const DpView &v, const SwParams *sp, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, void *huge_mem,
                cudaStream_t s) {
-    sw_classify_kernel<<<(v.n_reads / 2 + 255) / 256, 256, 0, s>>>(v, list, ctr);
+    sw_classify_kernel<<<(v.n_reads / 2 + 255) / 256, 256, 0, s>>>(v, sp, list, ctr);
     const int ints = 2 * kSwSmemInts;                                    // H and E rows of a <= 702-column window
     const int ref_cap = kSwSmemInts;                                     // reference codes of the window, one byte each
     const size_t smem = (size_t)ints * kWarpsPerBlock * 4 + (size_t)ref_cap * kWarpsPerBlock;

@@ -49,6 +49,13 @@ constexpr int kAlnCapSlow = 1024;       // per read in the overflow pass
 constexpr uint32_t kArenaFast = 4096;   // stack entries per lane in the fast pass (bump-allocated; pushes/read ~300 mean)
 constexpr uint32_t kArenaMid = 60000;   // overflow tier 1 (still 16-bit bucket heads)
 constexpr int kMidBlocks = 16;
+constexpr int kSpillCap = 16384;        // reads per batch that may need the overflow tiers (rows of d_aln_big); more is a limit error
+constexpr int kPenaltyCap = 1 << 16;    // entries of the pairing penalty table (index = insert size <= high_bayesian)
+// BatchSet::d_ctrs: [0] n_work [1] queue cursor [2] overflow reads of the fast pass; tier t (1, 2): [4t] n_work [4t+1] cursor
+// [4t+2] reads that overflowed tier t; [11] != 0: more than kSpillCap reads overflowed the fast pass
+constexpr int kCtrSpillFlag = 11;
+// d_status: words of the later stages of the current batch
+constexpr int kStSeErr = 0, kStBig = 1 /* [1] n_big [2] over kPairBigMax */, kStSw = 3 /* [3] n_sw [4] cursor */, kStDpErr = 5, kStTuples = 6;
 }  // namespace
 
 struct fqb_handle {
@@ -65,29 +72,41 @@ struct fqb_handle {
     DevBwt dbwt[2];
     int32_t *d_maxdiff = nullptr;
     int32_t h_maxdiff[FQB_MAX_READ_LEN + 1];
-    // batch buffers
+    // batch buffers.  Everything the align stage of a batch writes exists twice (BatchSet): batch n+1 is prepared and
+    // searched on the align stream while batch n goes through pairing / mate rescue / refinement / statistics on the
+    // main stream.  The plain members below (bv, wv, d_aln ...) are the view of the CURRENT set (use_set).
     int cap_reads = 0, lpad = 0, stride_cap = 0;
     int n_reads = 0, stride = 0;
-    // staging for host input, double-buffered: bases1, quals1, bases2, quals2 (+ lengths) of the batch being
-    // processed and of the batch fqb_prefetch_pairs is uploading on the copy stream meanwhile
-    uint8_t *d_in[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
-    int32_t *d_lens_in[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    struct BatchSet {
+        uint8_t *d_in[4] = {nullptr, nullptr, nullptr, nullptr};   // staging of the host input: bases1, quals1, bases2, quals2
+        int32_t *d_lens_in[2] = {nullptr, nullptr};
+        BatchView bv; WidthView wv;
+        Hit *d_aln = nullptr, *d_aln_big = nullptr;
+        int32_t *d_naln = nullptr, *d_spill_slot = nullptr;
+        uint32_t *d_overflow = nullptr, *d_work_sorted = nullptr, *d_order_bins = nullptr;
+        uint32_t *d_ctrs = nullptr;                 // 16 words, see kCtr*
+        int n_reads = 0, stride = 0; bool single_end = false;
+        int state = 0;                              // 0 free, 1 loaded, 2 align stage enqueued, 3 being paired (current)
+        cudaEvent_t ev_in = nullptr;                // upload complete
+        cudaEvent_t ev_free = nullptr;              // prep_kernel has consumed the staging arrays
+        cudaEvent_t ev_align = nullptr;             // align stage complete
+        cudaEvent_t ev_done = nullptr;              // the later stages no longer read this set
+        cudaEvent_t ev_rq[2] = {nullptr, nullptr};  // around the rank-query kernels (width + order + search)
+        bool rq_pending = false;
+        bool pre_valid = false;                     // staging holds a batch uploaded by fqb_prefetch_pairs, not consumed yet
+        const void *pre_key[4] = {nullptr, nullptr, nullptr, nullptr}; int pre_pairs = 0, pre_stride = 0;
+    } sets[2];
+    int cur = 0;                                    // set the stage-level calls work on
+    int fifo[2] = {-1, -1}; int n_fifo = 0;         // sets submitted (fqb_submit_pairs) and not collected yet, oldest first
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr, align_stream = nullptr;
     cudaEvent_t ev_rows[3] = {nullptr, nullptr, nullptr};   // rows final on the main stream / split done / copies done
-    cudaEvent_t ev_in[2] = {nullptr, nullptr};      // upload of set s complete
-    cudaEvent_t ev_free[2] = {nullptr, nullptr};    // prep_kernel has consumed set s
-    cudaEvent_t ev_rq[2] = {nullptr, nullptr};      // around the rank-query kernels (width + search) of a batch
-    double rq_ms = 0.0; uint64_t rq_launches = 0;   // accumulated device time of those launches
-    int cur_set = 0;                                // set the resident batch was loaded from
-    int pre_set = -1;                               // set holding a prefetched batch, -1 = none
-    const void *pre_key[4] = {nullptr, nullptr, nullptr, nullptr};
-    int pre_pairs = 0, pre_stride = 0;
+    double rq_ms = 0.0; uint64_t rq_launches = 0;   // accumulated device time of the rank-query launches
     BatchView bv;
     WidthView wv;
     Hit *d_aln = nullptr;
     int32_t *d_naln = nullptr;
     uint32_t *d_overflow = nullptr;
-    uint32_t *d_ctrs = nullptr;          // [0] n_work [1] cursor [2] n_overflow [3] cursor2
+    uint32_t *d_ctrs = nullptr;
     uint32_t *d_work_sorted = nullptr, *d_order_bins = nullptr;   // search queue, longest first
     unsigned long long *d_counters = nullptr;
     // search infrastructure
@@ -95,14 +114,31 @@ struct fqb_handle {
     uint4 *d_arena = nullptr;
     uint4 *d_arena_big = nullptr;
     uint4 *d_arena_mid = nullptr;
-    uint32_t arena_big_cap = 0;
     Hit *d_aln_big = nullptr;
     int32_t *d_spill_slot = nullptr;     // per read: row in d_aln_big or -1
-    int n_spill_cap = 0;
-    std::vector<uint32_t> h_overflow;
     SearchOpt sopt;
     bool batch_ready = false;
     uint64_t n_launches = 0;
+    // Per-batch parameters that depend on infer_isize live on the DEVICE (BatchCtl): the pair stage copies the insert-size
+    // histogram to pinned memory, a host callback in the stream (cudaLaunchHostFunc) runs the libm arithmetic and writes
+    // the parameters back, and the kernels that follow read them through pointers -- no host synchronisation per batch.
+    struct BatchCtl {
+        uint64_t rng_calls;               // draws of the drand48 stream consumed by earlier batches (libbwa/bwase.c:33-36)
+        uint64_t pad_;
+        fqb_isize_t last_ii;              // infer_isize's fallback (src/BwtMapper.cpp:780-781)
+        fqb_isize_t cur_ii;
+        PairParams pp;
+        SwParams sw;
+    };
+    BatchCtl *d_ctl = nullptr, *h_ctl = nullptr;          // h_ctl: pinned master copy (written by the callback)
+    struct PairXfer { uint64_t totals[2]; uint32_t hist[kIsizeBins + 1]; } *h_xfer = nullptr;   // pinned, device -> callback
+    int32_t *h_penalty = nullptr;                          // pinned, kPenaltyCap entries
+    uint32_t *d_status = nullptr, *h_status = nullptr;     // 16 status words of the batch in the later stages, see kSt*
+    uint32_t *h_ctrs = nullptr;                            // pinned copy of the current set's counters (overflow tiers)
+    bool status_pending = false;
+    std::string cb_error;                                  // set by the host callback (read after a synchronisation)
+    uint64_t tuples_bound = 0;                             // upper bound of the pile-up entries on the device
+    uint64_t prefetch_hits = 0;                            // batches fqb_stage_load found already uploaded by fqb_prefetch_pairs
     // paired-end resolution stage
     fqb_read_t *d_rows = nullptr, *d_rows_split = nullptr;
     PeScratch pesc = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -156,49 +192,70 @@ struct fqb_handle {
     uint32_t arena_fast = kArenaFast, arena_mid = kArenaMid;   // FQB_DEBUG_ARENA_FAST/_MID shrink them (tests of the overflow tiers)
 };
 
+static void use_set(fqb_handle *h, int si) {
+    fqb_handle::BatchSet &B = h->sets[si];
+    h->cur = si;
+    h->bv = B.bv; h->wv = B.wv; h->d_aln = B.d_aln; h->d_aln_big = B.d_aln_big; h->d_naln = B.d_naln; h->d_spill_slot = B.d_spill_slot;
+    h->d_overflow = B.d_overflow; h->d_work_sorted = B.d_work_sorted; h->d_order_bins = B.d_order_bins; h->d_ctrs = B.d_ctrs;
+    h->n_reads = B.n_reads; h->stride = B.stride; h->single_end = B.single_end;
+}
+
+static void sync_all(fqb_handle *h) {
+    if (h->align_stream) cudaStreamSynchronize(h->align_stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
+}
+
 static void free_batch(fqb_handle *h) {
-    for (auto &set : h->d_in) for (auto &p : set) { cudaFree(p); p = nullptr; }
-    for (auto &set : h->d_lens_in) for (auto &p : set) { cudaFree(p); p = nullptr; }
-    h->pre_set = -1;
-    cudaFree(h->bv.codes); cudaFree(h->bv.qual); cudaFree(h->bv.len); cudaFree(h->bv.full_len);
-    cudaFree(h->bv.filtered); cudaFree(h->bv.n_ambig); cudaFree(h->bv.work); cudaFree(h->d_work_sorted); h->d_work_sorted = nullptr;
-    cudaFree(h->wv.w); cudaFree(h->wv.sw);
-    cudaFree(h->d_aln); cudaFree(h->d_naln); cudaFree(h->d_overflow); cudaFree(h->d_spill_slot);
+    sync_all(h);
+    for (auto &B : h->sets) {
+        for (auto &p : B.d_in) { cudaFree(p); p = nullptr; }
+        for (auto &p : B.d_lens_in) { cudaFree(p); p = nullptr; }
+        cudaFree(B.bv.codes); cudaFree(B.bv.qual); cudaFree(B.bv.len); cudaFree(B.bv.full_len);
+        cudaFree(B.bv.filtered); cudaFree(B.bv.n_ambig); cudaFree(B.bv.work); cudaFree(B.d_work_sorted);
+        cudaFree(B.wv.w); cudaFree(B.wv.sw);
+        cudaFree(B.d_aln); cudaFree(B.d_aln_big); cudaFree(B.d_naln); cudaFree(B.d_overflow); cudaFree(B.d_spill_slot);
+        memset(&B.bv, 0, sizeof(B.bv)); memset(&B.wv, 0, sizeof(B.wv));
+        B.d_aln = B.d_aln_big = nullptr; B.d_naln = B.d_spill_slot = nullptr; B.d_overflow = B.d_work_sorted = nullptr;
+        B.state = 0; B.pre_valid = false; B.rq_pending = false;
+    }
+    h->n_fifo = 0;
     cudaFree(h->d_rows); cudaFree(h->d_rows_split); cudaFree(h->pesc.packed); cudaFree(h->pesc.scanned); cudaFree(h->pesc.scan_tmp); cudaFree(h->pesc.cum_extra);
-    cudaFree(h->pesc.multi_list); cudaFree(h->d_big_list); cudaFree(h->d_sw_list); cudaFree(h->d_refine_list);
-    h->d_sw_list = h->d_refine_list = nullptr;
+    cudaFree(h->pesc.multi_list); cudaFree(h->d_big_list); cudaFree(h->d_sw_list); cudaFree(h->d_refine_list); cudaFree(h->d_pstat);
+    h->d_sw_list = h->d_refine_list = nullptr; h->d_pstat = nullptr;
     h->d_rows = nullptr; h->pesc.packed = h->pesc.scanned = h->pesc.scan_tmp = h->pesc.cum_extra = nullptr; h->pesc.multi_list = nullptr; h->d_big_list = nullptr;
-    memset(&h->bv, 0, sizeof(h->bv)); memset(&h->wv, 0, sizeof(h->wv));
-    h->d_aln = nullptr; h->d_naln = nullptr; h->d_overflow = nullptr; h->d_spill_slot = nullptr;
     h->cap_reads = 0;
+    use_set(h, 0);
 }
 
 static int ensure_batch(fqb_handle *h, int n_reads, int stride) {
     if (n_reads <= h->cap_reads && stride <= h->stride_cap) return FQB_OK;
     free_batch(h);
     int cap = n_reads > 2 * FQB_BATCH_PAIRS ? n_reads : (n_reads > 65536 ? 2 * FQB_BATCH_PAIRS : 65536 * 2);
+    if (stride < h->stride_cap) stride = h->stride_cap;
     int lpad = (stride + 15) & ~15;
-    for (int st = 0; st < 2; ++st) {
-        for (int i = 0; i < 4; ++i) CU_CHECK(cudaMalloc(&h->d_in[st][i], (size_t)(cap / 2) * stride));
-        for (int i = 0; i < 2; ++i) CU_CHECK(cudaMalloc(&h->d_lens_in[st][i], (size_t)(cap / 2) * 4));
+    for (auto &B : h->sets) {
+        for (int i = 0; i < 4; ++i) CU_CHECK(cudaMalloc(&B.d_in[i], (size_t)(cap / 2) * stride));
+        for (int i = 0; i < 2; ++i) CU_CHECK(cudaMalloc(&B.d_lens_in[i], (size_t)(cap / 2) * 4));
+        CU_CHECK(cudaMalloc(&B.bv.codes, (size_t)cap * lpad));
+        CU_CHECK(cudaMalloc(&B.bv.qual, (size_t)cap * lpad));
+        CU_CHECK(cudaMalloc(&B.bv.len, (size_t)cap * 4));
+        CU_CHECK(cudaMalloc(&B.bv.full_len, (size_t)cap * 4));
+        CU_CHECK(cudaMalloc(&B.bv.filtered, (size_t)cap));
+        CU_CHECK(cudaMalloc(&B.bv.n_ambig, (size_t)cap));
+        CU_CHECK(cudaMalloc(&B.bv.work, (size_t)cap * 4));
+        CU_CHECK(cudaMalloc(&B.d_work_sorted, (size_t)cap * 4));
+        B.wv.wstride = stride + 1;
+        B.wv.sstride = h->gopt.seed_len + 1;
+        CU_CHECK(cudaMalloc(&B.wv.w, (size_t)cap * 2 * B.wv.wstride * 4));
+        CU_CHECK(cudaMalloc(&B.wv.sw, (size_t)cap * 2 * B.wv.sstride * 4));
+        CU_CHECK(cudaMalloc(&B.d_aln, (size_t)cap * kAlnCapFast * sizeof(Hit)));
+        CU_CHECK(cudaMalloc(&B.d_aln_big, (size_t)kSpillCap * kAlnCapSlow * sizeof(Hit)));
+        CU_CHECK(cudaMalloc(&B.d_naln, (size_t)cap * 4));
+        CU_CHECK(cudaMalloc(&B.d_overflow, (size_t)cap * 3 * 4));
+        CU_CHECK(cudaMalloc(&B.d_spill_slot, (size_t)cap * 4));
     }
-    CU_CHECK(cudaMalloc(&h->bv.codes, (size_t)cap * lpad));
-    CU_CHECK(cudaMalloc(&h->bv.qual, (size_t)cap * lpad));
-    CU_CHECK(cudaMalloc(&h->bv.len, (size_t)cap * 4));
-    CU_CHECK(cudaMalloc(&h->bv.full_len, (size_t)cap * 4));
-    CU_CHECK(cudaMalloc(&h->bv.filtered, (size_t)cap));
-    CU_CHECK(cudaMalloc(&h->bv.n_ambig, (size_t)cap));
-    CU_CHECK(cudaMalloc(&h->bv.work, (size_t)cap * 4));
-    CU_CHECK(cudaMalloc(&h->d_work_sorted, (size_t)cap * 4));
-    if (!h->d_order_bins) CU_CHECK(cudaMalloc(&h->d_order_bins, 32 * 4));
-    h->wv.wstride = stride + 1;
-    h->wv.sstride = h->gopt.seed_len + 1;
-    CU_CHECK(cudaMalloc(&h->wv.w, (size_t)cap * 2 * h->wv.wstride * 4));
-    CU_CHECK(cudaMalloc(&h->wv.sw, (size_t)cap * 2 * h->wv.sstride * 4));
-    CU_CHECK(cudaMalloc(&h->d_aln, (size_t)cap * kAlnCapFast * sizeof(Hit)));
-    CU_CHECK(cudaMalloc(&h->d_naln, (size_t)cap * 4));
-    CU_CHECK(cudaMalloc(&h->d_overflow, (size_t)cap * 3 * 4));
-    CU_CHECK(cudaMalloc(&h->d_spill_slot, (size_t)cap * 4));
     CU_CHECK(cudaMalloc(&h->d_rows, (size_t)cap * sizeof(fqb_read_t)));
     CU_CHECK(cudaMalloc(&h->d_rows_split, (size_t)cap * sizeof(fqb_read_t)));
     CU_CHECK(cudaMalloc(&h->pesc.packed, (size_t)cap * 8));
@@ -206,10 +263,12 @@ static int ensure_batch(fqb_handle *h, int n_reads, int stride) {
     CU_CHECK(cudaMalloc(&h->pesc.scan_tmp, ((size_t)cap / 1024 + 2) * 2 * 8));
     CU_CHECK(cudaMalloc(&h->pesc.cum_extra, (size_t)cap * 8));
     CU_CHECK(cudaMalloc(&h->pesc.multi_list, (size_t)cap * 4));
-    CU_CHECK(cudaMalloc(&h->d_big_list, (size_t)cap * 2));
+    CU_CHECK(cudaMalloc(&h->d_big_list, (size_t)kPairBigMax * 4));
     CU_CHECK(cudaMalloc(&h->d_sw_list, (size_t)cap * 4));        // n_pairs entries + n_pairs retry entries
     CU_CHECK(cudaMalloc(&h->d_refine_list, (size_t)cap * 8));    // n_reads entries + n_reads retry entries
+    CU_CHECK(cudaMalloc(&h->d_pstat, (size_t)(cap / 2) * sizeof(PairStat)));
     h->cap_reads = cap; h->lpad = lpad; h->stride_cap = stride;
+    use_set(h, 0);
     return FQB_OK;
 }
 
@@ -267,12 +326,33 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     CU_CHECK_H(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU_CHECK_H(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     CU_CHECK_H(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
-    for (auto &e : h->ev_rows) CU_CHECK_H(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) {
-        CU_CHECK_H(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
-        CU_CHECK_H(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
-        CU_CHECK_H(cudaEventCreate(&h->ev_rq[i]));
+    {   // the later stages run at a higher priority than the next batch's align stage: their blocks go first when SM room frees up
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CU_CHECK_H(cudaStreamCreateWithPriority(&h->align_stream, cudaStreamNonBlocking, lo));
     }
+    for (auto &e : h->ev_rows) CU_CHECK_H(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &B : h->sets) {
+        CU_CHECK_H(cudaEventCreateWithFlags(&B.ev_in, cudaEventDisableTiming));
+        CU_CHECK_H(cudaEventCreateWithFlags(&B.ev_free, cudaEventDisableTiming));
+        CU_CHECK_H(cudaEventCreateWithFlags(&B.ev_align, cudaEventDisableTiming));
+        CU_CHECK_H(cudaEventCreateWithFlags(&B.ev_done, cudaEventDisableTiming));
+        CU_CHECK_H(cudaEventCreate(&B.ev_rq[0])); CU_CHECK_H(cudaEventCreate(&B.ev_rq[1]));
+        CU_CHECK_H(cudaMalloc(&B.d_ctrs, 16 * 4));
+        CU_CHECK_H(cudaMemset(B.d_ctrs, 0, 16 * 4));
+        CU_CHECK_H(cudaMalloc(&B.d_order_bins, 32 * 4));
+    }
+    CU_CHECK_H(cudaMalloc(&h->d_ctl, sizeof(fqb_handle::BatchCtl)));
+    CU_CHECK_H(cudaMallocHost(&h->h_ctl, sizeof(fqb_handle::BatchCtl)));
+    CU_CHECK_H(cudaMallocHost(&h->h_xfer, sizeof(fqb_handle::PairXfer)));
+    CU_CHECK_H(cudaMallocHost(&h->h_penalty, (size_t)kPenaltyCap * 4));
+    CU_CHECK_H(cudaMalloc(&h->d_penalty, (size_t)kPenaltyCap * 4));
+    CU_CHECK_H(cudaMalloc(&h->d_status, 16 * 4));
+    CU_CHECK_H(cudaMemset(h->d_status, 0, 16 * 4));
+    CU_CHECK_H(cudaMallocHost(&h->h_status, 16 * 4));
+    CU_CHECK_H(cudaMallocHost(&h->h_ctrs, 16 * 4));
+    memset(h->h_status, 0, 16 * 4); memset(h->h_ctrs, 0, 16 * 4);
+    memset(h->h_ctl, 0, sizeof(fqb_handle::BatchCtl));
     for (int s = 0; s < 2; ++s) {
         std::vector<Block32> blocks;
         relayout_bwt(h->hidx.bwt[s], blocks);
@@ -290,9 +370,8 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     CU_CHECK_H(cudaMemcpy(h->d_pac, h->hidx.pac.data(), h->hidx.pac.size(), cudaMemcpyHostToDevice));
     CU_CHECK_H(cudaMalloc(&h->d_maxdiff, sizeof(h->h_maxdiff)));
     CU_CHECK_H(cudaMemcpy(h->d_maxdiff, h->h_maxdiff, sizeof(h->h_maxdiff), cudaMemcpyHostToDevice));
-    CU_CHECK_H(cudaMalloc(&h->d_ctrs, 16 * 4));
     CU_CHECK_H(cudaMalloc(&h->pesc.totals, 4 * 8));
-    CU_CHECK_H(cudaMalloc(&h->pesc.err_flag, 4));
+    h->pesc.err_flag = h->d_status + kStSeErr;
     CU_CHECK_H(cudaMalloc(&h->d_hist, (kIsizeBins + 1) * 4));
     {
         int32_t g[256];
@@ -303,6 +382,8 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     h->rng_x0 = lcg_seed(h->hidx.seed); h->rng_calls = 0;
     h->last_ii.avg = h->last_ii.std = -1.0; h->last_ii.ap_prior = 0; h->last_ii.low = h->last_ii.high = h->last_ii.high_bayesian = h->last_ii.pad_ = 0;
     h->cur_ii = h->last_ii;
+    h->h_ctl->rng_calls = 0; h->h_ctl->last_ii = h->last_ii; h->h_ctl->cur_ii = h->last_ii;
+    CU_CHECK_H(cudaMemcpy(h->d_ctl, h->h_ctl, sizeof(fqb_handle::BatchCtl), cudaMemcpyHostToDevice));
     CU_CHECK_H(cudaMalloc(&h->d_dpctr, 12 * 4));
     CU_CHECK_H(cudaMalloc(&h->d_counters, 16 * 8));
     CU_CHECK_H(cudaMemset(h->d_counters, 0, 16 * 8));
@@ -382,16 +463,24 @@ void fqb_destroy(fqb_handle *h) {
     cudaSetDevice(h->device);
     free_batch(h);
     for (int s = 0; s < 2; ++s) { cudaFree(h->d_blocks[s]); cudaFree(h->d_sa[s]); }
-    cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_ctrs); cudaFree(h->d_order_bins); cudaFree(h->d_counters);
-    cudaFree(h->d_arena); cudaFree(h->d_arena_mid); cudaFree(h->d_arena_big); cudaFree(h->d_aln_big);
-    cudaFree(h->pesc.totals); cudaFree(h->pesc.err_flag); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch); cudaFree(h->dp_pool.ints); cudaFree(h->dp_pool.bytes); cudaFree(h->d_dpctr); cudaFree(h->d_sw_huge);
+    cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_counters);
+    cudaFree(h->d_arena); cudaFree(h->d_arena_mid); cudaFree(h->d_arena_big);
+    for (auto &B : h->sets) {
+        cudaFree(B.d_ctrs); cudaFree(B.d_order_bins);
+        for (cudaEvent_t e : {B.ev_in, B.ev_free, B.ev_align, B.ev_done, B.ev_rq[0], B.ev_rq[1]}) if (e) cudaEventDestroy(e);
+    }
+    cudaFree(h->d_ctl); cudaFree(h->d_status); cudaFreeHost(h->h_ctl); cudaFreeHost(h->h_xfer); cudaFreeHost(h->h_penalty); cudaFreeHost(h->h_status); cudaFreeHost(h->h_ctrs);
+    // statistics accumulators (fqb_stats_open)
+    cudaFree(h->d_ctg); cudaFree(h->d_site); cudaFree(h->d_marker); cudaFree(h->d_depth); cudaFree(h->d_emp); cudaFree(h->d_contig_ctr);
+    cudaFree(h->d_dup_keys); cudaFree(h->d_tuples); cudaFree(h->d_ntuples);
+    cudaFree(h->pesc.totals); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch); cudaFree(h->dp_pool.ints); cudaFree(h->dp_pool.bytes); cudaFree(h->d_dpctr); cudaFree(h->d_sw_huge);
     cudaFreeHost(h->h_rows); cudaFreeHost(h->h_pstat); cudaFreeHost(h->h_bam_rows);
     cudaFree(h->d_multi_out); cudaFree(h->d_multi_list); cudaFree(h->d_multi_ctr); cudaFree(h->d_tuples_imp);
     if (h->bam_open) { std::string e; h->bam.close(e); }
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
+    if (h->align_stream) { cudaStreamSynchronize(h->align_stream); cudaStreamDestroy(h->align_stream); }
     for (auto &e : h->ev_rows) if (e) cudaEventDestroy(e);
-    for (int i = 0; i < 2; ++i) { if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]); if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]); if (h->ev_rq[i]) cudaEventDestroy(h->ev_rq[i]); }
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -405,144 +494,133 @@ int fqb_index_info(const fqb_handle *h, int64_t *l_pac, int32_t *n_contigs, uint
     return FQB_OK;
 }
 
-// ---- stage-level entry points ------------------------------------------------
+// ---- the per-batch chain ------------------------------------------------------
+// Every stage below only ENQUEUES work (kernels, copies, one host callback) on a stream; nothing waits for the device.
+// Errors a stage can only detect on the device are written to status words and read back at the end of the chain;
+// check_status() turns them into return codes after the caller-visible synchronisation point.
+}  // extern "C" (reopened below)
 
-int fqb_stage_load(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
-                   const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device) {
-    if (!h || n_pairs < 0 || stride < 1 || stride > FQB_MAX_READ_LEN) { set_error("bad batch shape"); return FQB_ERR_ARG; }
-    CU_CHECK(cudaSetDevice(h->device));
-    int rc = ensure_batch(h, 2 * n_pairs, stride);
-    if (rc) return rc;
-    h->n_reads = 2 * n_pairs; h->stride = stride;
-    if (!bases1 || !quals1 || (bases2 && !quals2)) { set_error("bases and qualities are required"); return FQB_ERR_ARG; }
-    h->single_end = bases2 == nullptr;
-    const uint8_t *src[4] = {bases1, quals1, bases2, quals2};
-    const int32_t *lsrc[2] = {lens1, lens2};
-    BatchView &b = h->bv;
-    b.n_reads = h->n_reads; b.stride_in = stride; b.lpad = h->lpad;
-    size_t bytes = (size_t)n_pairs * stride;
-    if (on_device) {
-        b.bases_in[0] = bases1; b.quals_in[0] = quals1; b.bases_in[1] = bases2; b.quals_in[1] = quals2;
-        b.lens_in[0] = lens1; b.lens_in[1] = lens2;
-    } else {
-        int set;
-        if (h->pre_set >= 0 && h->pre_pairs == n_pairs && h->pre_stride == stride && h->pre_key[0] == bases1 && h->pre_key[1] == quals1 &&
-            h->pre_key[2] == bases2 && h->pre_key[3] == quals2) {
-            set = h->pre_set;                                   // uploaded ahead of time by fqb_prefetch_pairs
-            CU_CHECK(cudaStreamWaitEvent(h->stream, h->ev_in[set], 0));
-        } else {
-            set = h->pre_set >= 0 ? 1 - h->pre_set : 0;         // do not disturb a pending prefetch of another batch
-            CU_CHECK(cudaStreamWaitEvent(h->stream, h->ev_free[set], 0));
-            for (int i = 0; i < 4; ++i) if (src[i]) CU_CHECK(cudaMemcpyAsync(h->d_in[set][i], src[i], bytes, cudaMemcpyHostToDevice, h->stream));
-            for (int i = 0; i < 2; ++i)
-                if (lsrc[i]) CU_CHECK(cudaMemcpyAsync(h->d_lens_in[set][i], lsrc[i], (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
-        }
-        if (set == h->pre_set) h->pre_set = -1;
-        h->cur_set = set;
-        b.bases_in[0] = h->d_in[set][0]; b.quals_in[0] = h->d_in[set][1];
-        b.bases_in[1] = bases2 ? h->d_in[set][2] : nullptr; b.quals_in[1] = bases2 ? h->d_in[set][3] : nullptr;
-        b.lens_in[0] = lens1 ? h->d_lens_in[set][0] : nullptr; b.lens_in[1] = lens2 ? h->d_lens_in[set][1] : nullptr;
-    }
-    b.n_work = h->d_ctrs;
-    h->batch_ready = true; h->align_done = h->pair_done = h->dp_done = h->stats_done = false;
-    return FQB_OK;
+// overflow tier t (1 or 2) takes over the reads the previous pass gave up on: its counters, and (tier 1) the rows of the
+// big hit buffer the reads will write to
+static __global__ void tier_setup_kernel(uint32_t *ctrs, int tier, const uint32_t *list, int32_t *spill_slot, uint32_t spill_cap) {
+    uint32_t n = ctrs[4 * (tier - 1) + 2];
+    if (tier == 1 && n > spill_cap) { n = spill_cap; if (blockIdx.x == 0 && threadIdx.x == 0) ctrs[kCtrSpillFlag] = 1; }
+    if (tier == 1)
+        for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) spill_slot[list[j]] = (int32_t)j;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctrs[4 * tier] = n; ctrs[4 * tier + 1] = 0; ctrs[4 * tier + 2] = 0; }
 }
 
-// a1..a5 on the resident batch: prep -> widths -> search (+ overflow pass with the big arena)
-int fqb_stage_align(fqb_handle *h) {
-    if (!h || !h->batch_ready) { set_error("no batch loaded"); return FQB_ERR_STATE; }
-    CU_CHECK(cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
-    CU_CHECK(cudaMemsetAsync(h->d_ctrs, 0, 16 * 4, st));
+static void harvest_rq(fqb_handle *h, fqb_handle::BatchSet &B, bool wait) {
+    if (!B.rq_pending) return;
+    if (wait) cudaEventSynchronize(B.ev_rq[1]);
+    else if (cudaEventQuery(B.ev_rq[1]) != cudaSuccess) return;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, B.ev_rq[0], B.ev_rq[1]) == cudaSuccess) { h->rq_ms += ms; ++h->rq_launches; }
+    B.rq_pending = false;
+}
+
+// a1..a5 of the batch in set si: prep -> widths -> queue order -> search -> overflow tiers (device-driven: the tier kernels
+// always run and find their work lists empty in the common case)
+static int enqueue_align(fqb_handle *h, int si, cudaStream_t st) {
+    fqb_handle::BatchSet &B = h->sets[si];
+    harvest_rq(h, B, true);
+    CU_CHECK(cudaMemsetAsync(B.d_ctrs, 0, 16 * 4, st));
     PrepParams pp;
     pp.trim_qual = h->gopt.trim_qual; pp.kmer_thresh = h->gopt.kmer_thresh; pp.is_il13 = h->gopt.is_il13; pp.roll = h->d_roll;
-    launch_prep(h->bv, pp, st);
-    CU_CHECK(cudaEventRecord(h->ev_free[h->cur_set], st));       // the staging set may be refilled from here on
+    launch_prep(B.bv, pp, st);
+    CU_CHECK(cudaEventRecord(B.ev_free, st));        // the staging arrays may be refilled from here on
     h->n_launches += 3;
-    CU_CHECK(cudaEventRecord(h->ev_rq[0], st));
-    launch_width(h->bv, h->wv, h->dbwt, h->gopt.seed_len, h->bv.work, h->bv.n_work, h->n_reads, h->d_counters, st);
+    CU_CHECK(cudaEventRecord(B.ev_rq[0], st));
+    launch_width(B.bv, B.wv, h->dbwt, h->gopt.seed_len, B.bv.work, B.bv.n_work, B.n_reads, h->d_counters, st);
 
-    h->sopt = make_search_opt(h->gopt, h->stride);
+    h->sopt = make_search_opt(h->gopt, B.stride);
     if (h->sopt.n_buckets > 128) { set_error("more than 128 score buckets"); return FQB_ERR_LIMIT; }
     if (!h->d_arena) {
         h->n_blocks16 = search_grid_blocks(h->sopt.n_buckets, true, h->device);
         CU_CHECK(cudaMalloc(&h->d_arena, (size_t)h->n_blocks16 * kSearchThreads * h->arena_fast * sizeof(uint4)));
+        CU_CHECK(cudaMalloc(&h->d_arena_mid, (size_t)kMidBlocks * kSearchThreads * h->arena_mid * sizeof(uint4)));
+        CU_CHECK(cudaMalloc(&h->d_arena_big, (size_t)kSearchThreads * ((size_t)h->gopt.max_entries + 64) * sizeof(uint4)));
     }
     SearchParams sp;
     sp.bwt[0] = h->dbwt[0]; sp.bwt[1] = h->dbwt[1];
     sp.opt = h->sopt; sp.maxdiff = h->d_maxdiff; sp.seed_len_opt = h->gopt.seed_len;
-    sp.work = h->bv.work; sp.n_work = h->d_ctrs; sp.cursor = h->d_ctrs + 1;
+    sp.work = B.bv.work; sp.n_work = B.d_ctrs; sp.cursor = B.d_ctrs + 1;
     sp.pops_out = nullptr;
     if (!getenv("FQB_NO_ORDER")) {
-        launch_order(h->bv, h->wv, h->bv.work, h->bv.n_work, h->n_reads, h->d_order_bins, h->d_work_sorted, st);
+        launch_order(B.bv, B.wv, B.bv.work, B.bv.n_work, B.n_reads, B.d_order_bins, B.d_work_sorted, st);
         h->n_launches += 2;
-        sp.work = h->d_work_sorted;
+        sp.work = B.d_work_sorted;
     }
     sp.arena = h->d_arena; sp.arena_cap = h->arena_fast;
-    sp.aln = h->d_aln; sp.aln_cap = kAlnCapFast; sp.n_aln = h->d_naln; sp.aln_row = nullptr;
-    sp.overflow = h->d_overflow; sp.n_overflow = h->d_ctrs + 2;
+    sp.aln = B.d_aln; sp.aln_cap = kAlnCapFast; sp.n_aln = B.d_naln; sp.aln_row = nullptr;
+    sp.overflow = B.d_overflow; sp.n_overflow = B.d_ctrs + 2;
     sp.counters = h->d_counters;
-    CU_CHECK(cudaMemsetAsync(h->d_naln, 0, (size_t)h->n_reads * 4, st));
-    CU_CHECK(cudaMemsetAsync(h->d_spill_slot, 0xff, (size_t)h->n_reads * 4, st));
-    launch_search(h->bv, h->wv, sp, true, false, h->n_blocks16, st);
+    CU_CHECK(cudaMemsetAsync(B.d_naln, 0, (size_t)B.n_reads * 4, st));
+    CU_CHECK(cudaMemsetAsync(B.d_spill_slot, 0xff, (size_t)B.n_reads * 4, st));
+    launch_search(B.bv, B.wv, sp, true, false, h->n_blocks16, st);
     CU_CHECK(cudaGetLastError());
-    CU_CHECK(cudaEventRecord(h->ev_rq[1], st));
-
-    uint32_t n_over = 0;
-    CU_CHECK(cudaMemcpyAsync(&n_over, h->d_ctrs + 2, 4, cudaMemcpyDeviceToHost, st));
-    CU_CHECK(cudaStreamSynchronize(st));
-    { float ms = 0.f; if (cudaEventElapsedTime(&ms, h->ev_rq[0], h->ev_rq[1]) == cudaSuccess) { h->rq_ms += ms; ++h->rq_launches; } }
+    CU_CHECK(cudaEventRecord(B.ev_rq[1], st));
+    B.rq_pending = true;
     // Rare reads whose stack or hit list outgrew the fast pass are redone from scratch with deeper arenas:
-    // tier 1 = 60k entries per lane on up to 16 blocks, tier 2 = as deep as the reference allows (max_entries).
-    for (int tier = 1; tier <= 2 && n_over; ++tier) {
-        if ((int)n_over > h->n_spill_cap) {
-            cudaFree(h->d_aln_big);
-            h->n_spill_cap = (int)n_over + 1024;
-            CU_CHECK(cudaMalloc(&h->d_aln_big, (size_t)h->n_spill_cap * kAlnCapSlow * sizeof(Hit)));
-        }
-        const bool heads16 = tier == 1;
-        const uint32_t cap = tier == 1 ? h->arena_mid : (uint32_t)h->gopt.max_entries + 64;
-        int blocks = tier == 1 ? (int)((n_over + kSearchThreads - 1) / kSearchThreads) : 1;
-        if (blocks > kMidBlocks) blocks = kMidBlocks;
-        uint4 *&arena = tier == 1 ? h->d_arena_mid : h->d_arena_big;
-        if (!arena) CU_CHECK(cudaMalloc(&arena, (size_t)(tier == 1 ? kMidBlocks : 1) * kSearchThreads * cap * sizeof(uint4)));
-        h->h_overflow.resize(n_over);
-        const uint32_t *list = tier == 1 ? h->d_overflow : h->d_overflow + h->cap_reads;
-        CU_CHECK(cudaMemcpyAsync(h->h_overflow.data(), list, (size_t)n_over * 4, cudaMemcpyDeviceToHost, st));
-        CU_CHECK(cudaStreamSynchronize(st));
+    // tier 1 = 60k entries per lane on 16 blocks, tier 2 = as deep as the reference allows (max_entries), one block.
+    for (int tier = 1; tier <= 2; ++tier) {
+        const uint32_t *list = tier == 1 ? B.d_overflow : B.d_overflow + h->cap_reads;
+        uint32_t *d_c = B.d_ctrs + 4 * tier;
+        tier_setup_kernel<<<32, 256, 0, st>>>(B.d_ctrs, tier, list, B.d_spill_slot, (uint32_t)kSpillCap);
         // widths were mutated by gap_shadow before the overflow: recompute them for these reads
-        uint32_t ctr[3] = {n_over, 0u, 0u};            // n_work, cursor, next tier's overflow count
-        uint32_t *d_c = h->d_ctrs + 4 * tier;
-        CU_CHECK(cudaMemcpyAsync(d_c, ctr, 12, cudaMemcpyHostToDevice, st));
-        launch_width(h->bv, h->wv, h->dbwt, h->gopt.seed_len, list, d_c, (int)n_over, nullptr, st);
-        std::vector<int32_t> slots(n_over);
-        for (uint32_t j = 0; j < n_over; ++j) slots[j] = (int32_t)j;
-        if (tier == 1)
-            for (uint32_t j = 0; j < n_over; ++j)
-                CU_CHECK(cudaMemcpyAsync(h->d_spill_slot + h->h_overflow[j], &slots[j], 4, cudaMemcpyHostToDevice, st));
+        launch_width(B.bv, B.wv, h->dbwt, h->gopt.seed_len, list, d_c, kSpillCap, nullptr, st);
         SearchParams s2 = sp;
         s2.work = list; s2.n_work = d_c; s2.cursor = d_c + 1;
-        s2.arena = arena; s2.arena_cap = cap;
-        s2.aln = h->d_aln_big; s2.aln_cap = kAlnCapSlow; s2.aln_row = h->d_spill_slot;
-        s2.overflow = h->d_overflow + h->cap_reads * (tier == 1 ? 1 : 2); s2.n_overflow = d_c + 2;
+        s2.arena = tier == 1 ? h->d_arena_mid : h->d_arena_big;
+        s2.arena_cap = tier == 1 ? h->arena_mid : (uint32_t)h->gopt.max_entries + 64;
+        s2.aln = B.d_aln_big; s2.aln_cap = kAlnCapSlow; s2.aln_row = B.d_spill_slot;
+        s2.overflow = B.d_overflow + h->cap_reads * (tier == 1 ? 1 : 2); s2.n_overflow = d_c + 2;
         s2.counters = nullptr; s2.pops_out = nullptr;
-        launch_search(h->bv, h->wv, s2, heads16, true, blocks, st);
-        h->n_launches += 2;
-        CU_CHECK(cudaGetLastError());
-        CU_CHECK(cudaMemcpyAsync(&n_over, d_c + 2, 4, cudaMemcpyDeviceToHost, st));
-        CU_CHECK(cudaStreamSynchronize(st));
+        launch_search(B.bv, B.wv, s2, tier == 1, true, tier == 1 ? kMidBlocks : 1, st);
+        h->n_launches += 3;
     }
-    if (n_over) { set_error("a read overflowed even the max_entries-deep arena or 1024 hits"); return FQB_ERR_LIMIT; }
-    h->align_done = true;
+    CU_CHECK(cudaGetLastError());
+    B.state = 2;
     return FQB_OK;
 }
 
-// a6-a9 on the aligned batch: bwa_cal_pac_pos_pe (src/BwtMapper.cpp:721-907)
-int fqb_stage_pair(fqb_handle *h) {
-    if (!h || !h->batch_ready || !h->align_done) { set_error("fqb_stage_pair: run fqb_stage_align first"); return FQB_ERR_STATE; }
-    if (h->n_reads > 1024 * 1024) { set_error("fqb_stage_pair: at most 524,288 pairs per batch"); return FQB_ERR_LIMIT; }
-    CU_CHECK(cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
+// infer_isize + the fallbacks of src/BwtMapper.cpp:779-786 and everything derived from the estimate, on the host with
+// glibc's libm, in stream order: runs on a CUDA callback thread between the histogram's copy to pinned
+// memory and the copy of the parameters back to the device.  Must not call the CUDA API.
+static void CUDART_CB pair_host_callback(void *user) {
+    fqb_handle *h = static_cast<fqb_handle *>(user);
+    fqb_handle::BatchCtl &C = *h->h_ctl;
+    C.rng_calls += h->h_xfer->totals[0];
+    fqb_isize_t ii;
+    infer_isize_hist(h->h_xfer->hist, (int)h->h_xfer->hist[kIsizeBins], h->popt.ap_prior, (int64_t)h->hidx.bwt[0].seq_len, ii);
+    if (ii.avg < 0.0 && C.last_ii.avg > 0.0) ii = C.last_ii;
+    if (h->popt.force_isize) { ii.low = ii.high = 0; ii.avg = ii.std = -1.0; }
+    C.cur_ii = ii; C.last_ii = ii;
+    std::vector<int32_t> pen;
+    fill_isize_penalty(ii, pen);
+    if (pen.size() > (size_t)kPenaltyCap) { h->cb_error = "insert-size estimate too wide for the pairing penalty table (high_bayesian >= 65536)"; pen.resize(kPenaltyCap); }
+    if (!pen.empty()) memcpy(h->h_penalty, pen.data(), pen.size() * 4);
+    PairParams &pp = C.pp;
+    pp.high = ii.high; pp.high_bayesian = ii.high_bayesian; pp.max_isize = h->popt.max_isize; pp.s_mm = h->gopt.s_mm;
+    pp.max_occ = h->popt.max_occ; pp.n_multi = h->popt.n_multi; pp.N_multi = h->popt.N_multi;
+    pp.penalty = h->d_penalty; pp.g_log_n = h->d_log_n;
+    pp.sw_on = 0;       // mate-rescue candidates are collected by the mate-rescue stage itself
+    SwParams &sw = C.sw;
+    sw.on = h->popt.is_sw && ii.avg >= 0.0 ? 1 : 0;
+    sw.avg = ii.avg; sw.std = ii.std; sw.l_pac = h->hidx.l_pac;
+    sw.s_old_add = sw.on ? -4.343 * std::log(ii.ap_prior / h->hidx.l_pac) : 0.0;               // libbwa/bwape.c:577
+    sw.s_new_add = (int)(-4.343 * std::log(.5 * std::erfc(M_SQRT1_2 * 1.5) + .499));           // libbwa/bwape.c:578
+    h->rng_calls = C.rng_calls; h->last_ii = C.last_ii; h->cur_ii = C.cur_ii;
+}
+// SingleEndMapper has no insert sizes: only the stream position moves on
+static void CUDART_CB se_host_callback(void *user) {
+    fqb_handle *h = static_cast<fqb_handle *>(user);
+    h->h_ctl->rng_calls += h->h_xfer->totals[0];
+    h->rng_calls = h->h_ctl->rng_calls;
+}
+
+// a6-a9 on the aligned batch (the current set): bwa_cal_pac_pos_pe (src/BwtMapper.cpp:721-907)
+static int enqueue_pair(fqb_handle *h, cudaStream_t st) {
     PeView v;
     v.n_reads = h->n_reads;
     v.aln = h->d_aln; v.aln_cap = kAlnCapFast; v.aln_big = h->d_aln_big; v.aln_big_cap = kAlnCapSlow;
@@ -550,84 +628,39 @@ int fqb_stage_pair(fqb_handle *h) {
     v.len = h->bv.len; v.full_len = h->bv.full_len; v.rows = h->d_rows; v.single_end = h->single_end ? 1 : 0;
     SeParams sp;
     sp.bwt[0] = h->dbwt[0]; sp.bwt[1] = h->dbwt[1]; sp.maxdiff = h->d_maxdiff; sp.g_log_n = h->d_log_n;
-    RngState rng{h->rng_x0, h->rng_calls};
+    const RngState rng{h->rng_x0, 0};                  // the stream position is read on the device (d_ctl->rng_calls)
+    CU_CHECK(cudaMemsetAsync(h->d_status, 0, 16 * 4, st));
     if (h->single_end) {
         // SingleEndMapper (src/BwtMapper.cpp:1335-1348): bwa_aln2seq_core(..., 1, N_OCC) + bwa_cal_pac_pos; no insert size, no pairing
-        CU_CHECK(cudaMemsetAsync(h->pesc.err_flag, 0, 4, st));
-        launch_se(v, sp, rng, h->pesc, st);
+        launch_se(v, sp, rng, &h->d_ctl->rng_calls, h->pesc, st);
         h->n_launches += 8;
-        uint64_t totals[2] = {0, 0};
-        uint32_t err = 0;
-        CU_CHECK(cudaMemcpyAsync(totals, h->pesc.totals, 16, cudaMemcpyDeviceToHost, st));
-        CU_CHECK(cudaMemcpyAsync(&err, h->pesc.err_flag, 4, cudaMemcpyDeviceToHost, st));
-        CU_CHECK(cudaMemsetAsync(h->d_ctrs + 12, 0, 16, st));
-        CU_CHECK(cudaStreamSynchronize(st));
+        CU_CHECK(cudaMemcpyAsync(h->h_xfer->totals, h->pesc.totals, 16, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaLaunchHostFunc(st, se_host_callback, h));
+        CU_CHECK(cudaMemcpyAsync(&h->d_ctl->rng_calls, &h->h_ctl->rng_calls, 8, cudaMemcpyHostToDevice, st));
         CU_CHECK(cudaGetLastError());
-        if (err) { set_error("drand48 returned exactly 0.0 for a read with one best interval (p = 2^-48 per read): unsupported"); return FQB_ERR_LIMIT; }
-        h->rng_calls += totals[0];
-        h->pair_done = true; h->dp_done = false;
         return FQB_OK;
     }
-    CU_CHECK(cudaMemsetAsync(h->pesc.err_flag, 0, 4, st));
+    if (h->popt.type != 1) { set_error("only BWA_PET_STD pairing is supported (SOLiD is dead code in the reference)"); return FQB_ERR_ARG; }
     CU_CHECK(cudaMemsetAsync(h->d_hist, 0, (kIsizeBins + 1) * 4, st));
-    launch_se(v, sp, rng, h->pesc, st);
+    launch_se(v, sp, rng, &h->d_ctl->rng_calls, h->pesc, st);
     launch_isize_hist(v, h->d_hist, h->d_hist + kIsizeBins, st);
     h->n_launches += 9;
-    h->h_hist.resize(kIsizeBins + 1);
-    uint64_t totals[2] = {0, 0};
-    uint32_t err = 0;
-    CU_CHECK(cudaMemcpyAsync(h->h_hist.data(), h->d_hist, (kIsizeBins + 1) * 4, cudaMemcpyDeviceToHost, st));
-    CU_CHECK(cudaMemcpyAsync(totals, h->pesc.totals, 16, cudaMemcpyDeviceToHost, st));
-    CU_CHECK(cudaMemcpyAsync(&err, h->pesc.err_flag, 4, cudaMemcpyDeviceToHost, st));
-    CU_CHECK(cudaStreamSynchronize(st));
+    CU_CHECK(cudaMemcpyAsync(h->h_xfer->hist, h->d_hist, (kIsizeBins + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaMemcpyAsync(h->h_xfer->totals, h->pesc.totals, 16, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaLaunchHostFunc(st, pair_host_callback, h));
+    CU_CHECK(cudaMemcpyAsync(h->d_ctl, h->h_ctl, sizeof(fqb_handle::BatchCtl), cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaMemcpyAsync(h->d_penalty, h->h_penalty, (size_t)kPenaltyCap * 4, cudaMemcpyHostToDevice, st));
+    if (!h->d_pair_scratch) CU_CHECK(cudaMalloc(&h->d_pair_scratch, (size_t)kPairBigMax * 8192 * 8));
+    launch_pair(v, h->dbwt, &h->d_ctl->pp, h->d_big_list, h->d_status + kStBig, h->d_sw_list, h->d_status + kStSw, st);
+    // pairs with many hit positions (repeats): global-memory scratch, one thread per pair (the count stays on the device)
+    launch_pair_big(v, h->dbwt, &h->d_ctl->pp, h->d_big_list, h->d_status + kStBig, h->d_pair_scratch, 8192, h->d_sw_list, h->d_status + kStSw, st);
+    h->n_launches += 2;
     CU_CHECK(cudaGetLastError());
-    if (err) { set_error("drand48 returned exactly 0.0 for a read with one best interval (p = 2^-48 per read): unsupported"); return FQB_ERR_LIMIT; }
-    h->rng_calls += totals[0];
-    // infer_isize + fallbacks (src/BwtMapper.cpp:779-786); libm on the host
-    fqb_isize_t ii;
-    infer_isize_hist(h->h_hist.data(), (int)h->h_hist[kIsizeBins], h->popt.ap_prior, (int64_t)h->hidx.bwt[0].seq_len, ii);
-    if (ii.avg < 0.0 && h->last_ii.avg > 0.0) ii = h->last_ii;
-    if (h->popt.force_isize) { ii.low = ii.high = 0; ii.avg = ii.std = -1.0; }
-    h->cur_ii = ii;
-    std::vector<int32_t> pen;
-    fill_isize_penalty(ii, pen);
-    if (pen.size() > h->penalty_cap) {
-        cudaFree(h->d_penalty);
-        h->penalty_cap = pen.size() + 1024;
-        CU_CHECK(cudaMalloc(&h->d_penalty, h->penalty_cap * 4));
-    }
-    if (!pen.empty()) CU_CHECK(cudaMemcpyAsync(h->d_penalty, pen.data(), pen.size() * 4, cudaMemcpyHostToDevice, st));
-    PairParams pp;
-    pp.high = ii.high; pp.high_bayesian = ii.high_bayesian; pp.max_isize = h->popt.max_isize; pp.s_mm = h->gopt.s_mm;
-    pp.max_occ = h->popt.max_occ; pp.n_multi = h->popt.n_multi; pp.N_multi = h->popt.N_multi;
-    pp.penalty = h->d_penalty; pp.g_log_n = h->d_log_n;
-    pp.sw_on = 0;       // mate-rescue candidates are collected by fqb_stage_sw_refine
-    if (h->popt.type != 1) { set_error("only BWA_PET_STD pairing is supported (SOLiD is dead code in the reference)"); return FQB_ERR_ARG; }
-    CU_CHECK(cudaMemsetAsync(h->d_ctrs + 12, 0, 16, st));     // [12] n_big [13] n_sw [14] sw cursor [15] dp error
-    launch_pair(v, h->dbwt, pp, h->d_big_list, h->d_ctrs + 12, h->d_sw_list, h->d_ctrs + 13, st);
-    h->n_launches += 1;
-    uint32_t n_big = 0;
-    CU_CHECK(cudaMemcpyAsync(&n_big, h->d_ctrs + 12, 4, cudaMemcpyDeviceToHost, st));
-    CU_CHECK(cudaStreamSynchronize(st));
-    if (n_big) {          // pairs with many hit positions (repeats): global-memory scratch, one thread per pair
-        const size_t per_pair = 8192;
-        if (n_big > 4096) { set_error("too many repeat-heavy pairs in one batch"); return FQB_ERR_LIMIT; }
-        if (!h->d_pair_scratch) CU_CHECK(cudaMalloc(&h->d_pair_scratch, (size_t)4096 * per_pair * 8));
-        launch_pair_big(v, h->dbwt, pp, h->d_big_list, h->d_ctrs + 12, (int)n_big, h->d_pair_scratch, per_pair, h->d_sw_list, h->d_ctrs + 13, st);
-        h->n_launches += 1;
-    }
-    CU_CHECK(cudaGetLastError());
-    h->last_ii = ii;
-    h->pair_done = true; h->dp_done = false;
     return FQB_OK;
 }
 
 // a10 + a11 on the paired batch: bwa_paired_sw (libbwa/bwape.c:463) then bwa_refine_gapped (libbwa/bwase.c:339)
-int fqb_stage_sw_refine(fqb_handle *h) {
-    if (!h || !h->pair_done) { set_error("fqb_stage_sw_refine: run fqb_stage_pair first"); return FQB_ERR_STATE; }
-    if (h->dp_done) return FQB_OK;
-    CU_CHECK(cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
+static int enqueue_sw_refine(fqb_handle *h, cudaStream_t st) {
     if (!h->dp_pool.ints) {
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
@@ -640,25 +673,144 @@ int fqb_stage_sw_refine(fqb_handle *h) {
     }
     DpView v;
     v.n_reads = h->n_reads; v.lpad = h->lpad; v.codes = h->bv.codes; v.pac = h->d_pac; v.l_pac = h->hidx.l_pac; v.rows = h->d_rows;
-    const fqb_isize_t &ii = h->cur_ii;
-    if (h->popt.is_sw && ii.avg >= 0.0 && !h->single_end) {
-        SwParams sp;
-        sp.avg = ii.avg; sp.std = ii.std; sp.l_pac = h->hidx.l_pac;
-        sp.s_old_add = -4.343 * std::log(ii.ap_prior / h->hidx.l_pac);                      // libbwa/bwape.c:577
-        sp.s_new_add = (int)(-4.343 * std::log(.5 * std::erfc(M_SQRT1_2 * 1.5) + .499));     // libbwa/bwape.c:578
-        CU_CHECK(cudaMemsetAsync(h->d_dpctr, 0, 12 * 4, st));
+    CU_CHECK(cudaMemsetAsync(h->d_dpctr, 0, 12 * 4, st));
+    if (h->popt.is_sw && !h->single_end) {       // whether the batch has an insert-size estimate is known on the device only (d_ctl->sw.on)
         if (!h->d_sw_huge) CU_CHECK(cudaMalloc(&h->d_sw_huge, launch_sw_huge_bytes()));
-        launch_sw(v, sp, h->dp_pool, h->d_sw_list, h->d_sw_list + h->cap_reads / 2, h->d_dpctr, h->d_dpctr + 8, h->d_sw_huge, st);
+        launch_sw(v, &h->d_ctl->sw, h->dp_pool, h->d_sw_list, h->d_sw_list + h->cap_reads / 2, h->d_dpctr, h->d_status + kStDpErr, h->d_sw_huge, st);
         h->n_launches += 6;      // classify, warp kernel, per-lane retry, and the three kernels of the very-wide-window path
     }
-    else CU_CHECK(cudaMemsetAsync(h->d_dpctr, 0, 12 * 4, st));
-    launch_refine(v, h->dp_pool, h->d_refine_list, h->d_refine_list + h->cap_reads, h->d_dpctr + 4, h->d_dpctr + 8, h->stride, st);
+    launch_refine(v, h->dp_pool, h->d_refine_list, h->d_refine_list + h->cap_reads, h->d_dpctr + 4, h->d_status + kStDpErr, h->stride, st);
     h->n_launches += 4;
-    uint32_t err = 0;
-    CU_CHECK(cudaMemcpyAsync(&err, h->d_dpctr + 8, 4, cudaMemcpyDeviceToHost, st));
-    CU_CHECK(cudaStreamSynchronize(st));
     CU_CHECK(cudaGetLastError());
-    if (err) { set_error("an alignment needed more DP scratch or CIGAR operations than provisioned"); return FQB_ERR_LIMIT; }
+    return FQB_OK;
+}
+
+// end of a batch's chain: bring the status words (and the set's overflow counters) to pinned memory
+static int enqueue_status(fqb_handle *h, cudaStream_t st) {
+    CU_CHECK(cudaMemcpyAsync(h->h_status, h->d_status, 16 * 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaMemcpyAsync(h->h_ctrs, h->d_ctrs, 16 * 4, cudaMemcpyDeviceToHost, st));
+    h->status_pending = true;
+    return FQB_OK;
+}
+// after a synchronisation of the main stream: what the device (or the callback) reported for the batches completed since
+static int check_status(fqb_handle *h) {
+    if (!h->status_pending) return FQB_OK;
+    h->status_pending = false;
+    const uint32_t *S = h->h_status, *K = h->h_ctrs;
+    if (!h->cb_error.empty()) { set_error(h->cb_error); h->cb_error.clear(); return FQB_ERR_LIMIT; }
+    if (K[kCtrSpillFlag]) { set_error("more than 16,384 reads of one batch outgrew the fast search pass"); return FQB_ERR_LIMIT; }
+    if (K[4 * 2 + 2]) { set_error("a read overflowed even the max_entries-deep arena or 1024 hits"); return FQB_ERR_LIMIT; }
+    if (S[kStSeErr]) { set_error("drand48 returned exactly 0.0 for a read with one best interval (p = 2^-48 per read): unsupported"); return FQB_ERR_LIMIT; }
+    if (S[kStBig + 1]) { set_error("too many repeat-heavy pairs in one batch"); return FQB_ERR_LIMIT; }
+    if (S[kStDpErr]) { set_error("an alignment needed more DP scratch or CIGAR operations than provisioned"); return FQB_ERR_LIMIT; }
+    return FQB_OK;
+}
+static int sync_and_check(fqb_handle *h) {
+    CU_CHECK(cudaStreamSynchronize(h->stream));
+    CU_CHECK(cudaGetLastError());
+    return check_status(h);
+}
+
+extern "C" {
+// ---- stage-level entry points ------------------------------------------------
+// upload (or adopt the device pointers of) one batch into set si
+static int load_set(fqb_handle *h, int si, cudaStream_t st, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
+                    const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device) {
+    fqb_handle::BatchSet &B = h->sets[si];
+    B.n_reads = 2 * n_pairs; B.stride = stride;
+    B.single_end = bases2 == nullptr;
+    const uint8_t *src[4] = {bases1, quals1, bases2, quals2};
+    const int32_t *lsrc[2] = {lens1, lens2};
+    BatchView &b = B.bv;
+    b.n_reads = B.n_reads; b.stride_in = stride; b.lpad = h->lpad;
+    const size_t bytes = (size_t)n_pairs * stride;
+    if (on_device) {
+        b.bases_in[0] = bases1; b.quals_in[0] = quals1; b.bases_in[1] = bases2; b.quals_in[1] = quals2;
+        b.lens_in[0] = lens1; b.lens_in[1] = lens2;
+    } else {
+        if (B.pre_valid && B.pre_pairs == n_pairs && B.pre_stride == stride && B.pre_key[0] == bases1 && B.pre_key[1] == quals1 &&
+            B.pre_key[2] == bases2 && B.pre_key[3] == quals2) {
+            CU_CHECK(cudaStreamWaitEvent(st, B.ev_in, 0));          // uploaded ahead of time by fqb_prefetch_pairs
+            ++h->prefetch_hits;
+        } else {
+            CU_CHECK(cudaStreamWaitEvent(st, B.ev_free, 0));
+            for (int i = 0; i < 4; ++i) if (src[i]) CU_CHECK(cudaMemcpyAsync(B.d_in[i], src[i], bytes, cudaMemcpyHostToDevice, st));
+            for (int i = 0; i < 2; ++i)
+                if (lsrc[i]) CU_CHECK(cudaMemcpyAsync(B.d_lens_in[i], lsrc[i], (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
+        }
+        B.pre_valid = false;
+        b.bases_in[0] = B.d_in[0]; b.quals_in[0] = B.d_in[1];
+        b.bases_in[1] = bases2 ? B.d_in[2] : nullptr; b.quals_in[1] = bases2 ? B.d_in[3] : nullptr;
+        b.lens_in[0] = lens1 ? B.d_lens_in[0] : nullptr; b.lens_in[1] = lens2 ? B.d_lens_in[1] : nullptr;
+    }
+    b.n_work = B.d_ctrs;
+    B.state = 1;
+    return FQB_OK;
+}
+static int check_shape(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1, const uint8_t *bases2, const uint8_t *quals2) {
+    if (!h || n_pairs < 0 || stride < 1 || stride > FQB_MAX_READ_LEN) { set_error("bad batch shape"); return FQB_ERR_ARG; }
+    if (!bases1 || !quals1 || (bases2 && !quals2)) { set_error("bases and qualities are required"); return FQB_ERR_ARG; }
+    return FQB_OK;
+}
+
+int fqb_stage_load(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
+                   const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device) {
+    if (int rc = check_shape(h, n_pairs, stride, bases1, quals1, bases2, quals2)) return rc;
+    if (h->n_fifo) { set_error("fqb_stage_load: batches submitted with fqb_submit_pairs are still in flight (collect them first)"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    int rc = ensure_batch(h, 2 * n_pairs, stride);
+    if (rc) return rc;
+    // the set holding this batch's prefetched upload, else the current one (unless ITS staging holds another prefetched batch)
+    int si = h->cur;
+    for (int k = 0; k < 2; ++k) {
+        const fqb_handle::BatchSet &B = h->sets[k];
+        if (!on_device && B.pre_valid && B.pre_pairs == n_pairs && B.pre_stride == stride && B.pre_key[0] == bases1 && B.pre_key[1] == quals1 &&
+            B.pre_key[2] == bases2 && B.pre_key[3] == quals2) si = k;
+    }
+    if (!on_device && h->sets[si].pre_valid && h->sets[si].pre_key[0] != bases1) si = 1 - si;
+    CU_CHECK(cudaStreamWaitEvent(h->stream, h->sets[si].ev_done, 0));
+    rc = load_set(h, si, h->stream, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, on_device);
+    if (rc) return rc;
+    use_set(h, si);
+    h->batch_ready = true; h->align_done = h->pair_done = h->dp_done = h->stats_done = false;
+    return FQB_OK;
+}
+
+// a1..a5 on the resident batch: prep -> widths -> search (+ overflow tiers)
+int fqb_stage_align(fqb_handle *h) {
+    if (!h || !h->batch_ready) { set_error("no batch loaded"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    int rc = enqueue_align(h, h->cur, h->stream);
+    if (rc) return rc;
+    if ((rc = enqueue_status(h, h->stream))) return rc;
+    if ((rc = sync_and_check(h))) return rc;
+    harvest_rq(h, h->sets[h->cur], true);
+    h->align_done = true;
+    return FQB_OK;
+}
+
+// a6-a9 on the aligned batch: bwa_cal_pac_pos_pe (src/BwtMapper.cpp:721-907)
+int fqb_stage_pair(fqb_handle *h) {
+    if (!h || !h->batch_ready || !h->align_done) { set_error("fqb_stage_pair: run fqb_stage_align first"); return FQB_ERR_STATE; }
+    if (h->n_reads > 1024 * 1024) { set_error("fqb_stage_pair: at most 524,288 pairs per batch"); return FQB_ERR_LIMIT; }
+    CU_CHECK(cudaSetDevice(h->device));
+    int rc = enqueue_pair(h, h->stream);
+    if (rc) return rc;
+    if ((rc = enqueue_status(h, h->stream))) return rc;
+    if ((rc = sync_and_check(h))) return rc;
+    h->pair_done = true; h->dp_done = false;
+    return FQB_OK;
+}
+
+// a10 + a11 on the paired batch: bwa_paired_sw (libbwa/bwape.c:463) then bwa_refine_gapped (libbwa/bwase.c:339)
+int fqb_stage_sw_refine(fqb_handle *h) {
+    if (!h || !h->pair_done) { set_error("fqb_stage_sw_refine: run fqb_stage_pair first"); return FQB_ERR_STATE; }
+    if (h->dp_done) return FQB_OK;
+    CU_CHECK(cudaSetDevice(h->device));
+    int rc = enqueue_sw_refine(h, h->stream);
+    if (rc) return rc;
+    if ((rc = enqueue_status(h, h->stream))) return rc;
+    if ((rc = sync_and_check(h))) return rc;
     h->dp_done = true;
     return FQB_OK;
 }
@@ -715,6 +867,7 @@ int fqb_stats_set_target_region(fqb_handle *h, const char *bed_path) {
 // RestoreVcfSites + SetGenomeSize (src/BwtMapper.cpp:225-226): side tables and accumulators
 int fqb_stats_open(fqb_handle *h, const char *index_prefix) {
     if (!h || !index_prefix) { set_error("null argument"); return FQB_ERR_ARG; }
+    if (h->stats_open) { set_error("fqb_stats_open: statistics are already open on this handle"); return FQB_ERR_STATE; }
     CU_CHECK(cudaSetDevice(h->device));
     std::string err;
     if (!build_stats_tables(h->hidx, index_prefix, h->gopt, h->target_bed, h->stabs, err)) { set_error(err); return FQB_ERR_IO; }
@@ -794,18 +947,19 @@ int fqb_stats_begin_file(fqb_handle *h, const char *out_prefix, const char *fq1,
 }
 
 // a12 + a13 on the finished batch: AddAlignment's decision tree per pair, then the per-base accumulation
-int fqb_stage_stats(fqb_handle *h) {
-    if (!h || !h->stats_open || !h->dp_done) { set_error("fqb_stage_stats: needs fqb_stats_open and a batch through fqb_stage_sw_refine"); return FQB_ERR_STATE; }
-    if (h->stats_done) return FQB_OK;
-    CU_CHECK(cudaSetDevice(h->device));
-    cudaStream_t st = h->stream;
+static int enqueue_stats(fqb_handle *h, cudaStream_t st) {
     if (h->files.empty()) h->files.push_back(FileCounters());
     const size_t np = (size_t)h->n_reads / 2, nc = h->stabs.contigs.size(), ns = h->stabs.n_sites ? h->stabs.n_sites : 1;
-    if (!h->d_pstat) CU_CHECK(cudaMalloc(&h->d_pstat, (size_t)(h->cap_reads / 2) * sizeof(PairStat)));
-    uint32_t nt = 0;
-    CU_CHECK(cudaMemcpyAsync(&nt, h->d_ntuples, 4, cudaMemcpyDeviceToHost, st));
-    CU_CHECK(cudaStreamSynchronize(st));
-    if ((uint64_t)nt + (uint64_t)h->n_reads * 2 > h->tuple_cap) { int rc = drain_tuples(h); if (rc) return rc; }
+    if (h->pairs_seen + np > (1ull << 31)) { set_error("more than 2^31 read pairs through one handle: the arrival-order keys would wrap"); return FQB_ERR_LIMIT; }
+    // pile-up entries accumulate on the device; a batch appends at most one per aligned base of a marker site, far fewer than
+    // 2 per read.  Drain them to the host (the one synchronisation of this stage, every few dozen batches) before they can overflow.
+    if (h->tuples_bound + (uint64_t)h->n_reads * 2 > h->tuple_cap) {
+        CU_CHECK(cudaStreamSynchronize(st));
+        int rc = drain_tuples(h);
+        if (rc) return rc;
+        h->tuples_bound = 0;
+    }
+    h->tuples_bound += (uint64_t)h->n_reads * 2;
     StatsView v;
     v.n_reads = h->n_reads; v.lpad = h->lpad; v.codes = h->bv.codes; v.qual = h->bv.qual; v.rows = h->d_rows; v.pstat = h->d_pstat;
     v.ctg = h->d_ctg; v.n_ctg = (int)nc; v.pair_base = (uint32_t)h->pairs_seen; v.cal_dup = 1; v.pac = h->d_pac;
@@ -824,6 +978,14 @@ int fqb_stage_stats(fqb_handle *h) {
     h->files.back().NumRead += (long long)n_in;
     add_scalar_kernel<<<1, 1, 0, st>>>(h->d_emp + 4 * 256 + 4096 + 8, n_in);     // NumRead, kept on the device too so that sharded runs sum it
     h->pairs_seen += np;
+    return FQB_OK;
+}
+int fqb_stage_stats(fqb_handle *h) {
+    if (!h || !h->stats_open || !h->dp_done) { set_error("fqb_stage_stats: needs fqb_stats_open and a batch through fqb_stage_sw_refine"); return FQB_ERR_STATE; }
+    if (h->stats_done) return FQB_OK;
+    CU_CHECK(cudaSetDevice(h->device));
+    int rc = enqueue_stats(h, h->stream);
+    if (rc) return rc;
     h->stats_done = true;
     return FQB_OK;
 }
@@ -973,17 +1135,28 @@ int fqb_stats_finish(fqb_handle *h, const char *out_prefix) {
 // ---- multi-GPU plumbing (row e): reads shard by batch with the index replicated; what crosses GPUs is
 // (1) the position of the drand48 stream + last_ii, handed from the rank that owns batch b to the owner of b+1, and
 // (2) at the end, the integer accumulators (NCCL reduce through torch.distributed on buffers exported here).
+// the state lives on the device (BatchCtl) with a pinned master copy the pair stage's callback updates: both calls first
+// wait for the batches in flight
+static int push_stream_state(fqb_handle *h) {
+    h->h_ctl->rng_calls = h->rng_calls; h->h_ctl->last_ii = h->last_ii;
+    CU_CHECK(cudaMemcpyAsync(h->d_ctl, h->h_ctl, offsetof(fqb_handle::BatchCtl, cur_ii), cudaMemcpyHostToDevice, h->stream));
+    return FQB_OK;
+}
 int fqb_get_stream_state(fqb_handle *h, uint64_t *rng_calls, fqb_isize_t *last_ii) {
     if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    CU_CHECK(cudaSetDevice(h->device));
+    CU_CHECK(cudaStreamSynchronize(h->stream));
     if (rng_calls) *rng_calls = h->rng_calls;
     if (last_ii) *last_ii = h->last_ii;
     return FQB_OK;
 }
 int fqb_set_stream_state(fqb_handle *h, uint64_t rng_calls, const fqb_isize_t *last_ii) {
     if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    CU_CHECK(cudaSetDevice(h->device));
+    CU_CHECK(cudaStreamSynchronize(h->stream));
     h->rng_calls = rng_calls;
     if (last_ii) h->last_ii = *last_ii;
-    return FQB_OK;
+    return push_stream_state(h);
 }
 int fqb_set_pair_base(fqb_handle *h, uint64_t first_pair) {     // global index of the next batch's first pair (pile-up / contig order keys)
     if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
@@ -1157,7 +1330,7 @@ int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fq
         CU_CHECK(cudaMemcpyAsync(rows1, h->d_rows_split, np * sizeof(fqb_read_t), cudaMemcpyDeviceToHost, h->stream));
         CU_CHECK(cudaMemcpyAsync(rows2, h->d_rows_split + np, np * sizeof(fqb_read_t), cudaMemcpyDeviceToHost, h->stream));
     }
-    CU_CHECK(cudaStreamSynchronize(h->stream));
+    if (int rc = sync_and_check(h)) return rc;
     if (ii_out) *ii_out = h->cur_ii;
     return FQB_OK;
 }
@@ -1189,15 +1362,17 @@ int fqb_rows_wait(fqb_handle *h) {
     if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
     CU_CHECK(cudaSetDevice(h->device));
     CU_CHECK(cudaEventSynchronize(h->ev_rows[2]));
-    return FQB_OK;
+    return sync_and_check(h);            // also reports what the device flagged for the batches completed since the last check
 }
 
 // restart the per-file state: srand48(bns->seed) and last_ii (PairEndMapper runs once per FASTQ pair)
 int fqb_reset_stream(fqb_handle *h) {
     if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    CU_CHECK(cudaSetDevice(h->device));
+    CU_CHECK(cudaStreamSynchronize(h->stream));
     h->rng_calls = 0;
     h->last_ii.avg = h->last_ii.std = -1.0; h->last_ii.low = h->last_ii.high = h->last_ii.high_bayesian = 0;
-    return FQB_OK;
+    return push_stream_state(h);
 }
 
 int fqb_stage_fetch_prep(fqb_handle *h, int32_t *len, int32_t *full_len, uint8_t *filtered, uint8_t *codes, int32_t codes_stride) {
@@ -1439,33 +1614,90 @@ int fqb_bam_close(fqb_handle *h) {
 // fqb_align_pairs / fqb_stage_load call with the same host pointers and shape picks it up without copying.
 int fqb_prefetch_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
                        const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2) {
-    if (!h || n_pairs < 0 || stride < 1 || stride > FQB_MAX_READ_LEN) { set_error("bad batch shape"); return FQB_ERR_ARG; }
+    if (int rc = check_shape(h, n_pairs, stride, bases1, quals1, bases2, quals2)) return rc;
     CU_CHECK(cudaSetDevice(h->device));
-    if (2 * n_pairs > h->cap_reads || stride > h->stride_cap) return FQB_OK;      // buffers not sized yet: the load will copy
-    const int set = 1 - h->cur_set;
+    if (2 * n_pairs > h->cap_reads || stride > h->stride_cap || h->n_fifo) return FQB_OK;      // buffers not sized yet: the load will copy
+    // into the staging arrays of the set that is not current, unless they still hold a prefetched batch nobody has
+    // loaded yet (the documented call order is prefetch(n+1) before align(n)): then the current set's, free once its
+    // prep_kernel has run
+    int si = 1 - h->cur;
+    if (h->sets[si].pre_valid) si = h->cur;
+    fqb_handle::BatchSet &B = h->sets[si];
+    if (B.pre_valid) return FQB_OK;                  // both hold unconsumed uploads: nothing to do, the load will copy
     const uint8_t *src[4] = {bases1, quals1, bases2, quals2};
     const int32_t *lsrc[2] = {lens1, lens2};
     const size_t bytes = (size_t)n_pairs * stride;
-    CU_CHECK(cudaStreamWaitEvent(h->copy_stream, h->ev_free[set], 0));
-    for (int i = 0; i < 4; ++i) if (src[i]) CU_CHECK(cudaMemcpyAsync(h->d_in[set][i], src[i], bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    CU_CHECK(cudaStreamWaitEvent(h->copy_stream, B.ev_free, 0));
+    for (int i = 0; i < 4; ++i) if (src[i]) CU_CHECK(cudaMemcpyAsync(B.d_in[i], src[i], bytes, cudaMemcpyHostToDevice, h->copy_stream));
     for (int i = 0; i < 2; ++i)
-        if (lsrc[i]) CU_CHECK(cudaMemcpyAsync(h->d_lens_in[set][i], lsrc[i], (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->copy_stream));
-    CU_CHECK(cudaEventRecord(h->ev_in[set], h->copy_stream));
-    h->pre_set = set; h->pre_pairs = n_pairs; h->pre_stride = stride;
-    for (int i = 0; i < 4; ++i) h->pre_key[i] = src[i];
+        if (lsrc[i]) CU_CHECK(cudaMemcpyAsync(B.d_lens_in[i], lsrc[i], (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->copy_stream));
+    CU_CHECK(cudaEventRecord(B.ev_in, h->copy_stream));
+    B.pre_valid = true; B.pre_pairs = n_pairs; B.pre_stride = stride;
+    for (int i = 0; i < 4; ++i) B.pre_key[i] = src[i];
     return FQB_OK;
 }
+uint64_t fqb_prefetch_hits(const fqb_handle *h) { return h ? h->prefetch_hits : 0; }
 
 int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
                     const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2,
                     fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out) {
     int rc = fqb_stage_load(h, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, 0);
     if (rc) return rc;
-    if ((rc = fqb_stage_align(h))) return rc;
-    if ((rc = fqb_stage_pair(h))) return rc;
-    if ((rc = fqb_stage_sw_refine(h))) return rc;
+    // the whole chain is enqueued at once; the only wait is for the result
+    if ((rc = enqueue_align(h, h->cur, h->stream))) return rc;
+    if ((rc = enqueue_pair(h, h->stream))) return rc;
+    if ((rc = enqueue_sw_refine(h, h->stream))) return rc;
+    if ((rc = enqueue_status(h, h->stream))) return rc;
+    h->align_done = h->pair_done = h->dp_done = true; h->stats_done = false;
     if (rows1 && rows2) return fqb_stage_fetch_rows(h, rows1, rows2, ii_out);
+    if ((rc = sync_and_check(h))) return rc;
     if (ii_out) *ii_out = h->cur_ii;
+    return FQB_OK;
+}
+
+// ---- pipelined form: submit batch n+1, then collect batch n ---------------------------------------------------
+// fqb_submit_pairs uploads a batch and enqueues its align stage (a1-a5) on the align stream, into the batch set that is
+// free; it returns at once.  fqb_collect_pairs takes the OLDEST submitted batch through pairing, mate rescue, refinement
+// and -- when statistics are open -- StatCollector's accumulation on the main stream, and starts the copy of its result
+// rows; it does not wait either.  The align stage of batch n+1 therefore runs on the GPU next to the later stages of
+// batch n, and nothing in the loop blocks the host: fqb_rows_wait (or any call that returns data) is the only wait.
+int fqb_submit_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
+                     const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device) {
+    if (int rc = check_shape(h, n_pairs, stride, bases1, quals1, bases2, quals2)) return rc;
+    if (h->n_fifo >= 2) { set_error("fqb_submit_pairs: two batches are already in flight; collect one first"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    if (2 * n_pairs > h->cap_reads || stride > h->stride_cap) {
+        if (h->n_fifo) { set_error("fqb_submit_pairs: the batch buffers must grow while a batch is in flight; collect it first"); return FQB_ERR_STATE; }
+        int rc = ensure_batch(h, 2 * n_pairs, stride);
+        if (rc) return rc;
+    }
+    // the set that is neither waiting in the queue nor (as the current set) possibly still read by the later stages of the
+    // batch collected last: with one batch queued that is the other one; ev_done orders us behind those stages
+    const int si = h->n_fifo ? 1 - h->fifo[0] : 1 - h->cur;
+    fqb_handle::BatchSet &B = h->sets[si];
+    CU_CHECK(cudaStreamWaitEvent(h->align_stream, B.ev_done, 0));
+    int rc = load_set(h, si, h->align_stream, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, on_device);
+    if (rc) return rc;
+    if ((rc = enqueue_align(h, si, h->align_stream))) return rc;
+    CU_CHECK(cudaEventRecord(B.ev_align, h->align_stream));
+    h->fifo[h->n_fifo++] = si;
+    return FQB_OK;
+}
+int fqb_collect_pairs(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2) {
+    if (!h || !h->n_fifo) { set_error("fqb_collect_pairs: no batch submitted"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    const int si = h->fifo[0];
+    h->fifo[0] = h->fifo[1]; --h->n_fifo;
+    use_set(h, si);
+    CU_CHECK(cudaStreamWaitEvent(h->stream, h->sets[si].ev_align, 0));
+    int rc = enqueue_pair(h, h->stream);
+    if (!rc) rc = enqueue_sw_refine(h, h->stream);
+    if (!rc && h->stats_open) rc = enqueue_stats(h, h->stream);
+    if (!rc) rc = enqueue_status(h, h->stream);
+    if (rc) return rc;
+    h->batch_ready = h->align_done = h->pair_done = h->dp_done = true; h->stats_done = h->stats_open;
+    if (rows1 && rows2) { if ((rc = fqb_stage_fetch_rows_async(h, rows1, rows2))) return rc; }
+    CU_CHECK(cudaEventRecord(h->sets[si].ev_done, h->stream));
     return FQB_OK;
 }
 

@@ -71,7 +71,8 @@ __global__ void se_multi_list_kernel(PeView v, const uint64_t *packed, const uin
 
 // one thread: reads with several best-score intervals, in read order
 __global__ void se_multi_seq_kernel(PeView v, const uint64_t *packed, const uint64_t *scanned, const uint32_t *list,
-                                    uint64_t *cum_extra, RngState rng, uint64_t *totals) {
+                                    uint64_t *cum_extra, RngState rng_, const uint64_t *calls, uint64_t *totals) {
+    const RngState rng{rng_.x0, rng_.calls + (calls ? *calls : 0)};
     if (blockIdx.x || threadIdx.x) return;
     const int n = v.n_reads;
     const uint32_t n_multi = n ? (uint32_t)((scanned[n - 1] + packed[n - 1]) >> 32) : 0;
@@ -90,7 +91,8 @@ __global__ void se_multi_seq_kernel(PeView v, const uint64_t *packed, const uint
 
 // SE pass of bwa_cal_pac_pos_pe (src/BwtMapper.cpp:744-776) for read r
 __global__ void se_final_kernel(PeView v, SeParams sp, const uint64_t *packed, const uint64_t *scanned, const uint32_t *list,
-                                const uint64_t *cum_extra, const uint64_t *totals, RngState rng, uint32_t *err_flag) {
+                                const uint64_t *cum_extra, const uint64_t *totals, RngState rng_, const uint64_t *calls, uint32_t *err_flag) {
+    const RngState rng{rng_.x0, rng_.calls + (calls ? *calls : 0)};
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= (uint32_t)v.n_reads) return;
     fqb_read_t row;
@@ -144,8 +146,9 @@ __global__ void isize_hist_kernel(PeView v, uint32_t *hist, uint32_t *max_len) {
     if ((threadIdx.x & 31) == 0) atomicMax(max_len, ml);
 }
 
-__global__ void __launch_bounds__(128) pair_kernel(PeView v, DevBwt b0, DevBwt b1, PairParams pp, uint32_t *big_list, uint32_t *n_big,
+__global__ void __launch_bounds__(128) pair_kernel(PeView v, DevBwt b0, DevBwt b1, const PairParams *ppp, uint32_t *big_list, uint32_t *n_big,
                                                     uint32_t *sw_list, uint32_t *n_sw) {
+    const PairParams pp = *ppp;
     __shared__ DevBwt s_bwt[2];
     if (threadIdx.x == 0) { s_bwt[0] = b0; s_bwt[1] = b1; }
     __syncthreads();
@@ -155,19 +158,24 @@ __global__ void __launch_bounds__(128) pair_kernel(PeView v, DevBwt b0, DevBwt b
     fqb_read_t r0 = v.rows[2 * p], r1 = v.rows[2 * p + 1];
     bool ok = pair_one(s_bwt, &r0, &r1, hits_of(v, 2 * p), n_hits_of(v, 2 * p), hits_of(v, 2 * p + 1), n_hits_of(v, 2 * p + 1),
                        pp, arr, kPairArrCap);
-    if (!ok) { big_list[atomicAdd(n_big, 1u)] = p; return; }
+    if (!ok) {                      // many hit positions (repeats): pair_big_kernel takes it; n_big[1] flags more than it can hold
+        const uint32_t slot = atomicAdd(n_big, 1u);
+        if (slot < kPairBigMax) big_list[slot] = p; else atomicExch(n_big + 1, p + 1);
+        return;
+    }
     if (sw_candidate(&r0, &r1, pp)) sw_list[atomicAdd(n_sw, 1u)] = p;
     v.rows[2 * p] = r0; v.rows[2 * p + 1] = r1;
 }
 
 // pairs with more hit positions than a thread sorts in registers/local memory: one thread each, scratch in global memory
-__global__ void pair_big_kernel(PeView v, DevBwt b0, DevBwt b1, PairParams pp, const uint32_t *big_list, const uint32_t *n_big,
+__global__ void pair_big_kernel(PeView v, DevBwt b0, DevBwt b1, const PairParams *ppp, const uint32_t *big_list, const uint32_t *n_big,
                                 uint64_t *scratch, size_t scratch_per_pair, uint32_t *sw_list, uint32_t *n_sw) {
+    const PairParams pp = *ppp;
     __shared__ DevBwt s_bwt[2];
     if (threadIdx.x == 0) { s_bwt[0] = b0; s_bwt[1] = b1; }
     __syncthreads();
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= *n_big) return;
+    if (j >= *n_big || j >= kPairBigMax) return;
     uint32_t p = big_list[j];
     fqb_read_t r0 = v.rows[2 * p], r1 = v.rows[2 * p + 1];
     pair_one(s_bwt, &r0, &r1, hits_of(v, 2 * p), n_hits_of(v, 2 * p), hits_of(v, 2 * p + 1), n_hits_of(v, 2 * p + 1), pp,
@@ -176,26 +184,26 @@ __global__ void pair_big_kernel(PeView v, DevBwt b0, DevBwt b1, PairParams pp, c
     v.rows[2 * p] = r0; v.rows[2 * p + 1] = r1;
 }
 
-void launch_se(const PeView &v, const SeParams &sp, const RngState &rng, PeScratch &sc, cudaStream_t s) {
+void launch_se(const PeView &v, const SeParams &sp, const RngState &rng, const uint64_t *calls, PeScratch &sc, cudaStream_t s) {
     const int n = v.n_reads, tb = 256, nb = (n + tb - 1) / tb;
     se_count_kernel<<<nb, tb, 0, s>>>(v, sc.packed);
     exclusive_scan_u64(sc.packed, sc.scanned, sc.scan_tmp, n, s);
     se_multi_list_kernel<<<nb, tb, 0, s>>>(v, sc.packed, sc.scanned, sc.multi_list);
-    se_multi_seq_kernel<<<1, 32, 0, s>>>(v, sc.packed, sc.scanned, sc.multi_list, sc.cum_extra, rng, sc.totals);
-    se_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(v, sp, sc.packed, sc.scanned, sc.multi_list, sc.cum_extra, sc.totals, rng, sc.err_flag);
+    se_multi_seq_kernel<<<1, 32, 0, s>>>(v, sc.packed, sc.scanned, sc.multi_list, sc.cum_extra, rng, calls, sc.totals);
+    se_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(v, sp, sc.packed, sc.scanned, sc.multi_list, sc.cum_extra, sc.totals, rng, calls, sc.err_flag);
 }
 void launch_isize_hist(const PeView &v, uint32_t *hist, uint32_t *max_len, cudaStream_t s) {
     const int np = v.n_reads / 2;
     isize_hist_kernel<<<(np + 255) / 256, 256, 0, s>>>(v, hist, max_len);
 }
-void launch_pair(const PeView &v, const DevBwt bwt[2], const PairParams &pp, uint32_t *big_list, uint32_t *n_big, uint32_t *sw_list,
+void launch_pair(const PeView &v, const DevBwt bwt[2], const PairParams *pp, uint32_t *big_list, uint32_t *n_big, uint32_t *sw_list,
                  uint32_t *n_sw, cudaStream_t s) {
     const int np = v.n_reads / 2;
     pair_kernel<<<(np + 127) / 128, 128, 0, s>>>(v, bwt[0], bwt[1], pp, big_list, n_big, sw_list, n_sw);
 }
-void launch_pair_big(const PeView &v, const DevBwt bwt[2], const PairParams &pp, const uint32_t *big_list, const uint32_t *n_big,
-                     int n_big_host, uint64_t *scratch, size_t scratch_per_pair, uint32_t *sw_list, uint32_t *n_sw, cudaStream_t s) {
-    pair_big_kernel<<<(n_big_host + 63) / 64, 64, 0, s>>>(v, bwt[0], bwt[1], pp, big_list, n_big, scratch, scratch_per_pair, sw_list, n_sw);
+void launch_pair_big(const PeView &v, const DevBwt bwt[2], const PairParams *pp, const uint32_t *big_list, const uint32_t *n_big,
+                     uint64_t *scratch, size_t scratch_per_pair, uint32_t *sw_list, uint32_t *n_sw, cudaStream_t s) {
+    pair_big_kernel<<<(kPairBigMax + 63) / 64, 64, 0, s>>>(v, bwt[0], bwt[1], pp, big_list, n_big, scratch, scratch_per_pair, sw_list, n_sw);
 }
 
 }  // namespace fqb

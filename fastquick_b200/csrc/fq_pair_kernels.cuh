@@ -27,11 +27,16 @@ struct PeScratch {
     uint32_t *multi_list, *err_flag;
 };
 
-void launch_se(const PeView &v, const SeParams &sp, const RngState &rng, PeScratch &sc, cudaStream_t s);
+// calls: optional DEVICE word added to rng.calls (the stream position handed from batch to batch stays on the device)
+void launch_se(const PeView &v, const SeParams &sp, const RngState &rng, const uint64_t *calls, PeScratch &sc, cudaStream_t s);
 void launch_isize_hist(const PeView &v, uint32_t *hist, uint32_t *max_len, cudaStream_t s);
-void launch_pair(const PeView &v, const DevBwt bwt[2], const PairParams &pp, uint32_t *big_list, uint32_t *n_big, uint32_t *sw_list,
+// pp: DEVICE pointer (written by the pair stage's host callback once infer_isize has run).  n_big: [0] pairs deferred to
+// pair_big_kernel, [1] != 0 when more than kPairBigMax pairs asked for it (a limit error).  launch_pair_big always runs its
+// fixed grid; it reads the count on the device.
+constexpr uint32_t kPairBigMax = 4096;
+void launch_pair(const PeView &v, const DevBwt bwt[2], const PairParams *pp, uint32_t *big_list, uint32_t *n_big, uint32_t *sw_list,
                  uint32_t *n_sw, cudaStream_t s);
-void launch_pair_big(const PeView &v, const DevBwt bwt[2], const PairParams &pp, const uint32_t *big_list, const uint32_t *n_big,
-                     int n_big_host, uint64_t *scratch, size_t scratch_per_pair, uint32_t *sw_list, uint32_t *n_sw, cudaStream_t s);
+void launch_pair_big(const PeView &v, const DevBwt bwt[2], const PairParams *pp, const uint32_t *big_list, const uint32_t *n_big,
+                     uint64_t *scratch, size_t scratch_per_pair, uint32_t *sw_list, uint32_t *n_sw, cudaStream_t s);
 
 }  // namespace fqb

@@ -142,6 +142,25 @@ int fqb_prefetch_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride,
                        const uint8_t *bases1, const uint8_t *quals1, const int32_t *lens1,
                        const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2);
 
+/* fqb_stage_load calls that found their batch already uploaded by fqb_prefetch_pairs (tests, tuning) */
+uint64_t fqb_prefetch_hits(const fqb_handle *h);
+
+/* ---- pipelined form of the per-batch body (src/BwtMapper.cpp:1905-1982: the reference reads batch n+1 on its IO
+ * workers while batch n is mapped) ----------------------------------------------------------------------------
+ * fqb_submit_pairs uploads a batch and enqueues its align stage (a1-a5: prep, k-mer filter, bwt_cal_width,
+ * bwt_match_gap) on a second stream, into whichever of the handle's two batch sets is free, and returns at once.
+ * fqb_collect_pairs takes the OLDEST submitted batch through bwa_cal_pac_pos_pe, bwa_paired_sw, bwa_refine_gapped and,
+ * when fqb_stats_open was called, StatCollector::AddAlignment's accumulation (= fqb_stage_stats), and starts the copy
+ * of its result rows into rows1/rows2 (may be NULL); it does not wait.  Call order: submit(0); then for every n:
+ * submit(n+1), collect(n).  At most two batches are in flight.  fqb_rows_wait blocks until the rows of the last
+ * collected batch are complete and returns any error the device reported for the batches finished since the last
+ * check; the stage-level fetch calls and fqb_stats_emit / fqb_bam_emit work on the batch collected last.
+ * on_device != 0: the pointers are device pointers (see fqb_stage_load). */
+int fqb_submit_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride,
+                     const uint8_t *bases1, const uint8_t *quals1, const int32_t *lens1,
+                     const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device);
+int fqb_collect_pairs(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2);
+
 /* ---- stage-level entry points (parity tests, bench, profiling) ---------------
  * The same kernels fqb_align_pairs sequences, one group at a time, on the batch
  * made resident by fqb_stage_load.  Read index r = 2*pair + end. */
