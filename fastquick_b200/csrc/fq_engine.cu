@@ -26,6 +26,8 @@
 #include <future>
 #include <mutex>
 #include <thread>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <cmath>
 #include "fq_relayout.h"
 #include "fq_synth.h"
@@ -138,6 +140,12 @@ struct fqb_handle {
     bool status_pending = false;
     std::string cb_error;                                  // set by the host callback (read after a synchronisation)
     uint64_t tuples_bound = 0;                             // upper bound of the pile-up entries on the device
+    // multi-GPU (row e): rank in the sharded run, the NCCL communicator of the end-of-run merge, and the hand-off ring's
+    // mailboxes (my own, and the next rank's mapped into this address space: IPC or peer access)
+    struct RingBox { unsigned long long words[7]; unsigned int seq, pad_; };
+    int comm_rank = 0, comm_world = 1;
+    ncclComm_t nccl = nullptr;
+    RingBox *ring_inbox = nullptr, *ring_next = nullptr; bool ring_next_ipc = false;
     uint64_t prefetch_hits = 0;                            // batches fqb_stage_load found already uploaded by fqb_prefetch_pairs
     // paired-end resolution stage
     fqb_read_t *d_rows = nullptr, *d_rows_split = nullptr;
@@ -444,6 +452,7 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
 }
 
 static int drain_post(fqb_handle *h, bool stats, bool bam);
+static void comm_release(fqb_handle *h);
 
 int fqb_kmer_tables_origin(const fqb_handle *h) { return h ? h->kmer_origin : 0; }
 
@@ -469,6 +478,7 @@ void fqb_destroy(fqb_handle *h) {
         cudaFree(B.d_ctrs); cudaFree(B.d_order_bins);
         for (cudaEvent_t e : {B.ev_in, B.ev_free, B.ev_align, B.ev_done, B.ev_rq[0], B.ev_rq[1]}) if (e) cudaEventDestroy(e);
     }
+    comm_release(h);
     cudaFree(h->d_ctl); cudaFree(h->d_status); cudaFreeHost(h->h_ctl); cudaFreeHost(h->h_xfer); cudaFreeHost(h->h_penalty); cudaFreeHost(h->h_status); cudaFreeHost(h->h_ctrs);
     // statistics accumulators (fqb_stats_open)
     cudaFree(h->d_ctg); cudaFree(h->d_site); cudaFree(h->d_marker); cudaFree(h->d_depth); cudaFree(h->d_emp); cudaFree(h->d_contig_ctr);
@@ -1305,6 +1315,258 @@ int fqb_stats_var_import(fqb_handle *h, int which, const void *src, uint64_t n) 
     return FQB_OK;
 }
 
+// ---- multi-GPU, native (row e) ---------------------------------------------------------------------------------
+// Reads shard by batch: global batch b goes to rank b % world, the index is replicated, and the path has no data-path
+// collective.  What crosses GPUs:
+//  (1) per batch, the 56 bytes bwa_cal_pac_pos_pe carries from batch to batch (position of the drand48 stream,
+//      libbwa/bwase.c:33-36 with srand48 once per file, src/BwtMapper.cpp:1817; last_ii, src/BwtMapper.cpp:779-781): the owner
+//      of batch b stores them into the mailbox of the owner of b+1 THROUGH PEER MEMORY (NVLink) with a one-thread kernel, and
+//      the receiver's pair stage starts with a one-thread kernel that waits for the mailbox's sequence number.  Both are
+//      stream-ordered and fit on an SM next to the persistent search kernel, so the hand-off never waits for the GPU to drain
+//      (an NCCL send/recv kernel would: it needs a whole CTA's worth of registers while the search grid holds every SM);
+//  (2) at the end of the run, the accumulators: one grouped ncclReduce (sum; first-touch contig order: min) onto rank 0, and
+//      the variable-size state (marker pile-up entries, distinct PCR-duplicate keys) with exact-size grouped ncclSend/ncclRecv.
+}  // extern "C" (reopened below)
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+// NCCL is resolved at first use (dlopen), so the library loads -- and a single GPU works -- where it is not installed
+NcclApi *nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) { api.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL); if (api.lib) break; }
+        if (!api.lib) return;
+#define FQB_NCCL_SYM(f) api.f = reinterpret_cast<decltype(api.f)>(dlsym(api.lib, "nccl" #f))
+        FQB_NCCL_SYM(GetUniqueId); FQB_NCCL_SYM(CommInitRank); FQB_NCCL_SYM(CommInitAll); FQB_NCCL_SYM(CommDestroy); FQB_NCCL_SYM(Reduce);
+        FQB_NCCL_SYM(AllGather); FQB_NCCL_SYM(Send); FQB_NCCL_SYM(Recv); FQB_NCCL_SYM(GroupStart); FQB_NCCL_SYM(GroupEnd); FQB_NCCL_SYM(GetErrorString);
+#undef FQB_NCCL_SYM
+        if (!api.GetUniqueId || !api.CommInitRank || !api.Reduce || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd || !api.AllGather) { dlclose(api.lib); api.lib = nullptr; }
+    });
+    return api.lib ? &api : nullptr;
+}
+}  // namespace
+#define NCCL_CHECK(expr)                                                                                        \
+    do {                                                                                                        \
+        ncclResult_t r_ = (expr);                                                                               \
+        if (r_ != ncclSuccess) { set_error(std::string(#expr) + ": " + (N->GetErrorString ? N->GetErrorString(r_) : "NCCL error")); return FQB_ERR_CUDA; } \
+    } while (0)
+
+// the 56 bytes at the head of BatchCtl (rng_calls, pad, last_ii) into the next rank's mailbox, then its sequence number
+static __global__ void ring_send_kernel(const unsigned long long *state, volatile unsigned long long *peer_words, volatile unsigned int *peer_seq, unsigned int seq) {
+    for (int i = 0; i < 7; ++i) peer_words[i] = state[i];
+    __threadfence_system();
+    *peer_seq = seq;
+}
+static __global__ void ring_recv_kernel(unsigned long long *state, const volatile unsigned long long *words, const volatile unsigned int *my_seq, unsigned int seq) {
+    while (*my_seq != seq) __nanosleep(100);
+    __threadfence_system();
+    for (int i = 0; i < 7; ++i) state[i] = words[i];
+}
+static_assert(offsetof(fqb_handle::BatchCtl, cur_ii) == 56, "the hand-off state is the first 56 bytes of BatchCtl");
+static void comm_release(fqb_handle *h) {
+    if (h->nccl) { if (NcclApi *N = nccl_api()) if (N->CommDestroy) N->CommDestroy(h->nccl); h->nccl = nullptr; }
+    if (h->ring_next && h->ring_next_ipc) cudaIpcCloseMemHandle(h->ring_next);
+    cudaFree(h->ring_inbox);
+    h->ring_next = h->ring_inbox = nullptr;
+}
+
+extern "C" {
+// mailbox of this handle for the hand-off ring; out64 receives its cudaIpcMemHandle_t (for ranks in other processes)
+int fqb_comm_ring_handle(fqb_handle *h, uint8_t *out64) {
+    if (!h || !out64) { set_error("null argument"); return FQB_ERR_ARG; }
+    CU_CHECK(cudaSetDevice(h->device));
+    if (!h->ring_inbox) {
+        CU_CHECK(cudaMalloc(&h->ring_inbox, sizeof(fqb_handle::RingBox)));
+        CU_CHECK(cudaMemset(h->ring_inbox, 0, sizeof(fqb_handle::RingBox)));
+    }
+    cudaIpcMemHandle_t ipc;
+    static_assert(sizeof(ipc) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CU_CHECK(cudaIpcGetMemHandle(&ipc, h->ring_inbox));
+    memcpy(out64, &ipc, 64);
+    return FQB_OK;
+}
+int fqb_comm_unique_id(uint8_t *out128) {
+    NcclApi *N = nccl_api();
+    if (!N) { set_error("NCCL (libnccl.so.2) is not available"); return FQB_ERR_IO; }
+    ncclUniqueId id;
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    NCCL_CHECK(N->GetUniqueId(&id));
+    memcpy(out128, &id, 128);
+    return FQB_OK;
+}
+// one process per GPU: every rank passes the same NCCL id (from rank 0's fqb_comm_unique_id) and all ranks' mailbox handles
+// (world x 64 bytes, from fqb_comm_ring_handle), both exchanged by the launcher
+int fqb_comm_init(fqb_handle *h, int rank, int world, const uint8_t *nccl_id128, const uint8_t *ring_handles) {
+    if (!h || world < 1 || rank < 0 || rank >= world) { set_error("fqb_comm_init: bad rank / world"); return FQB_ERR_ARG; }
+    CU_CHECK(cudaSetDevice(h->device));
+    h->comm_rank = rank; h->comm_world = world;
+    if (world == 1) return FQB_OK;
+    if (!nccl_id128 || !ring_handles) { set_error("fqb_comm_init: the NCCL id and the ring handles are required"); return FQB_ERR_ARG; }
+    if (!h->ring_inbox) { set_error("fqb_comm_init: call fqb_comm_ring_handle first"); return FQB_ERR_STATE; }
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, ring_handles + (size_t)((rank + 1) % world) * 64, 64);
+    void *peer = nullptr;
+    CU_CHECK(cudaIpcOpenMemHandle(&peer, ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->ring_next = static_cast<fqb_handle::RingBox *>(peer); h->ring_next_ipc = true;
+    NcclApi *N = nccl_api();
+    if (!N) { set_error("NCCL (libnccl.so.2) is not available"); return FQB_ERR_IO; }
+    ncclUniqueId id;
+    memcpy(&id, nccl_id128, 128);
+    NCCL_CHECK(N->CommInitRank(&h->nccl, world, id, rank));
+    return FQB_OK;
+}
+// the handles of ONE process, rank i = hs[i] (one per GPU; several on one GPU work for the ring, not for NCCL)
+int fqb_comm_init_local(fqb_handle **hs, int n) {
+    if (!hs || n < 1) { set_error("fqb_comm_init_local: no handles"); return FQB_ERR_ARG; }
+    bool distinct = true;
+    for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) if (hs[i]->device == hs[j]->device) distinct = false;
+    for (int i = 0; i < n; ++i) {
+        uint8_t tmp[64];
+        if (int rc = fqb_comm_ring_handle(hs[i], tmp)) return rc;
+        hs[i]->comm_rank = i; hs[i]->comm_world = n;
+    }
+    for (int i = 0; i < n && n > 1; ++i) {
+        fqb_handle *nx = hs[(i + 1) % n];
+        if (nx->device != hs[i]->device) {
+            CU_CHECK(cudaSetDevice(hs[i]->device));
+            cudaError_t e = cudaDeviceEnablePeerAccess(nx->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return FQB_ERR_CUDA; }
+            cudaGetLastError();
+        }
+        hs[i]->ring_next = nx->ring_inbox; hs[i]->ring_next_ipc = false;
+    }
+    if (n > 1 && distinct) {
+        NcclApi *N = nccl_api();
+        if (!N || !N->CommInitAll) { set_error("NCCL (libnccl.so.2) is not available"); return FQB_ERR_IO; }
+        std::vector<ncclComm_t> comms(n); std::vector<int> devs(n);
+        for (int i = 0; i < n; ++i) devs[i] = hs[i]->device;
+        NCCL_CHECK(N->CommInitAll(comms.data(), n, devs.data()));
+        for (int i = 0; i < n; ++i) hs[i]->nccl = comms[i];
+    }
+    return FQB_OK;
+}
+
+// fqb_collect_pairs for a sharded run.  global_batch: position of this batch in file order (this rank owns the batches with
+// global_batch % world == rank); first_pair: global index of its first pair; is_last: no batch follows in the file.  The pair
+// stage starts with the state the owner of global_batch - 1 left (unless this is batch 0 of the file) and hands its own on.
+int fqb_collect_pairs_sharded(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, uint64_t global_batch, uint64_t first_pair, int is_last) {
+    if (!h || !h->n_fifo) { set_error("fqb_collect_pairs_sharded: no batch submitted"); return FQB_ERR_STATE; }
+    if (h->comm_world > 1 && !h->ring_next) { set_error("fqb_collect_pairs_sharded: call fqb_comm_init first"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    const int si = h->fifo[0];
+    h->fifo[0] = h->fifo[1]; --h->n_fifo;
+    use_set(h, si);
+    h->pairs_seen = first_pair;
+    cudaStream_t st = h->stream;
+    CU_CHECK(cudaStreamWaitEvent(st, h->sets[si].ev_align, 0));
+    const bool ring = h->comm_world > 1;
+    unsigned long long *state = reinterpret_cast<unsigned long long *>(h->d_ctl);
+    if (ring && global_batch > 0) {
+        ring_recv_kernel<<<1, 1, 0, st>>>(state, h->ring_inbox->words, &h->ring_inbox->seq, (unsigned int)global_batch);
+        // the callback works on the pinned master copy: bring the received state there
+        CU_CHECK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, 56, cudaMemcpyDeviceToHost, st));
+        ++h->n_launches;
+    }
+    int rc = enqueue_pair(h, st);
+    if (rc) return rc;
+    if (ring && !is_last) {
+        ring_send_kernel<<<1, 1, 0, st>>>(state, h->ring_next->words, &h->ring_next->seq, (unsigned int)(global_batch + 1));
+        ++h->n_launches;
+    }
+    rc = enqueue_sw_refine(h, st);
+    if (rc) return rc;
+    h->batch_ready = h->align_done = h->pair_done = h->dp_done = true;
+    if (rows1 && rows2) { if ((rc = fqb_stage_fetch_rows_async(h, rows1, rows2))) return rc; }
+    if (h->stats_open) rc = enqueue_stats(h, st);
+    if (!rc) rc = enqueue_status(h, st);
+    if (rc) return rc;
+    h->stats_done = h->stats_open;
+    CU_CHECK(cudaEventRecord(h->sets[si].ev_done, st));
+    return FQB_OK;
+}
+
+// End of a sharded run, called by every rank: the fixed-size accumulators are summed onto rank 0 (one NCCL group), then the
+// ranks' pile-up entries and distinct duplicate keys go there with exact-size sends.  Rank 0 ends up with the state of an
+// unsharded run (fqb_stats_merge_tables + fqb_stats_finish follow there).  ms_out (optional): device time of the exchange.
+int fqb_comm_merge_stats(fqb_handle *h, double *ms_out) {
+    if (!h || !h->stats_open) { set_error("fqb_comm_merge_stats: statistics are not open"); return FQB_ERR_STATE; }
+    if (ms_out) *ms_out = 0.0;
+    if (h->comm_world == 1) return FQB_OK;
+    NcclApi *N = nccl_api();
+    if (!N || !h->nccl) { set_error("fqb_comm_merge_stats: no NCCL communicator (fqb_comm_init)"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int W = h->comm_world, me = h->comm_rank;
+    const size_t nc = h->stabs.contigs.size(), ns = h->stabs.n_sites ? h->stabs.n_sites : 1;
+    cudaEvent_t e0, e1;
+    CU_CHECK(cudaEventCreate(&e0)); CU_CHECK(cudaEventCreate(&e1));
+    CU_CHECK(cudaEventRecord(e0, st));
+    NCCL_CHECK(N->GroupStart());
+    NCCL_CHECK(N->Reduce(h->d_depth, h->d_depth, ns * 3, ncclUint32, ncclSum, 0, h->nccl, st));
+    NCCL_CHECK(N->Reduce(h->d_emp, h->d_emp, (size_t)kEmpWords, ncclUint64, ncclSum, 0, h->nccl, st));
+    NCCL_CHECK(N->Reduce(h->d_contig_ctr, h->d_contig_ctr, nc * 4, ncclUint32, ncclSum, 0, h->nccl, st));
+    NCCL_CHECK(N->Reduce(h->d_contig_ctr + nc * 4, h->d_contig_ctr + nc * 4, nc, ncclUint32, ncclMin, 0, h->nccl, st));
+    NCCL_CHECK(N->GroupEnd());
+    // how much variable-size state every rank holds
+    uint64_t mine[2] = {0, 0};
+    for (int which = 0; which < 2; ++which) { int rc = fqb_stats_var_count(h, which, &mine[which]); if (rc) return rc; }
+    uint64_t *d_cnt = nullptr;
+    CU_CHECK(cudaMalloc(&d_cnt, (size_t)(W + 1) * 16));
+    CU_CHECK(cudaMemcpyAsync(d_cnt + 2 * W, mine, 16, cudaMemcpyHostToDevice, st));
+    NCCL_CHECK(N->AllGather(d_cnt + 2 * W, d_cnt, 2, ncclUint64, h->nccl, st));
+    std::vector<uint64_t> cnt((size_t)W * 2);
+    CU_CHECK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)W * 16, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    cudaFree(d_cnt);
+    const size_t item[2] = {sizeof(PileupTuple), 8};
+    if (me != 0) {
+        void *buf[2] = {nullptr, nullptr};
+        for (int which = 0; which < 2; ++which)
+            if (mine[which]) {
+                CU_CHECK(cudaMalloc(&buf[which], mine[which] * item[which]));
+                int rc = fqb_stats_var_export(h, which, buf[which], mine[which]);
+                if (rc) return rc;
+            }
+        NCCL_CHECK(N->GroupStart());
+        for (int which = 0; which < 2; ++which) if (mine[which]) NCCL_CHECK(N->Send(buf[which], mine[which] * item[which], ncclUint8, 0, h->nccl, st));
+        NCCL_CHECK(N->GroupEnd());
+        CU_CHECK(cudaStreamSynchronize(st));
+        cudaFree(buf[0]); cudaFree(buf[1]);
+    } else {
+        std::vector<void *> buf((size_t)W * 2, nullptr);
+        for (int r = 1; r < W; ++r) for (int which = 0; which < 2; ++which)
+            if (cnt[2 * r + which]) CU_CHECK(cudaMalloc(&buf[2 * r + which], cnt[2 * r + which] * item[which]));
+        NCCL_CHECK(N->GroupStart());
+        for (int r = 1; r < W; ++r) for (int which = 0; which < 2; ++which)
+            if (cnt[2 * r + which]) NCCL_CHECK(N->Recv(buf[2 * r + which], cnt[2 * r + which] * item[which], ncclUint8, r, h->nccl, st));
+        NCCL_CHECK(N->GroupEnd());
+        for (int r = 1; r < W; ++r) for (int which = 0; which < 2; ++which)
+            if (cnt[2 * r + which]) { int rc = fqb_stats_var_import(h, which, buf[2 * r + which], cnt[2 * r + which]); if (rc) return rc; }
+        CU_CHECK(cudaStreamSynchronize(st));
+        for (void *b : buf) cudaFree(b);
+    }
+    CU_CHECK(cudaEventRecord(e1, st));
+    CU_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms_out) *ms_out = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return FQB_OK;
+}
+
 // result rows of the last completed stage: rows[e][i] = end e of pair i
 }  // extern "C" (reopened below)
 // out[end][pair] = in[pair][end], moved as 16-byte words (sizeof(fqb_read_t) = 6 x 16)
@@ -1692,11 +1954,14 @@ int fqb_collect_pairs(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2) {
     CU_CHECK(cudaStreamWaitEvent(h->stream, h->sets[si].ev_align, 0));
     int rc = enqueue_pair(h, h->stream);
     if (!rc) rc = enqueue_sw_refine(h, h->stream);
-    if (!rc && h->stats_open) rc = enqueue_stats(h, h->stream);
+    if (rc) return rc;
+    h->batch_ready = h->align_done = h->pair_done = h->dp_done = true;
+    // the rows are those fqb_align_pairs returns: before StatCollector::AddAlignment's bridge check demotes reads in place
+    if (rows1 && rows2) { if ((rc = fqb_stage_fetch_rows_async(h, rows1, rows2))) return rc; }
+    if (h->stats_open) rc = enqueue_stats(h, h->stream);
     if (!rc) rc = enqueue_status(h, h->stream);
     if (rc) return rc;
-    h->batch_ready = h->align_done = h->pair_done = h->dp_done = true; h->stats_done = h->stats_open;
-    if (rows1 && rows2) { if ((rc = fqb_stage_fetch_rows_async(h, rows1, rows2))) return rc; }
+    h->stats_done = h->stats_open;
     CU_CHECK(cudaEventRecord(h->sets[si].ev_done, h->stream));
     return FQB_OK;
 }

@@ -1,91 +1,50 @@
-"""Multi-GPU orchestration of the align stage: one process per GPU, `torch.distributed` for the plumbing.
+"""Launcher-side plumbing of a sharded run: one process per GPU, `torch.distributed` only to bootstrap.
 
-Batches of 262,144 pairs go round-robin to ranks (batch b -> rank b % world); the index is replicated.  The hot path has
-no data-path collective.  What does cross ranks:
-
-  * between `fqb_stage_align` and `fqb_stage_pair` of batch b, the owner of batch b-1 sends the position of the global
-    drand48 stream (draws consumed so far) and its insert-size estimate (`last_ii`): 8 + 48 bytes, point to point;
-  * at the end, the integer accumulators are reduced to rank 0 (sum; first-touch order: min), and the variable-size
-    state -- marker pile-up entries (tagged with their global pair index) and the distinct PCR-duplicate keys --
-    is gathered there; rank 0 then splices the ranks' InsertSizeTable batches into file order and writes the files.
-
-The engine is any object with the small interface used below, so the protocol is testable on CPU with gloo
-(tests/test_multigpu_protocol.py) and runs on NCCL in bench.py.
+Everything that touches data is in the C library: batches of 262,144 pairs go round-robin to ranks (batch b -> rank
+b % world) with the index replicated; `fqb_collect_pairs_sharded` receives the drand48 position + `last_ii` the owner of
+batch b-1 left (56 bytes, written into this rank's mailbox over NVLink peer memory) and hands its own on;
+`fqb_comm_merge_stats` reduces the accumulators onto rank 0 with NCCL and moves the pile-up entries / duplicate keys there.
+What is left for Python is the rendezvous (`bootstrap`: the NCCL id of rank 0 and every rank's mailbox handle travel over
+the process group the launcher already has) and the loop that deals the batches (`run_sharded`), which is written against a
+small engine interface so that it can be exercised on CPU with gloo (tests/test_multigpu_protocol.py).
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
-STATE_WORDS = 8    # rng_calls + isize_info_t (avg, std, ap_prior as f64 bit patterns; low, high, high_bayesian, pad as u32 pairs)
+
+def bootstrap(lib, h, rank, world):
+    """fqb_comm_init for handle `h`: exchange rank 0's NCCL unique id and all mailbox handles over torch.distributed."""
+    if world == 1:
+        assert lib.fqb_comm_init(h, 0, 1, None, None) == 0, lib.fqb_last_error()
+        return
+    box = (C.c_uint8 * 64)()
+    assert lib.fqb_comm_ring_handle(h, box) == 0, lib.fqb_last_error()
+    uid = (C.c_uint8 * 128)()
+    if rank == 0:
+        assert lib.fqb_comm_unique_id(uid) == 0, lib.fqb_last_error()
+    ids = [bytes(uid)]
+    dist.broadcast_object_list(ids, src=0)
+    boxes = [None] * world
+    dist.all_gather_object(boxes, bytes(box))
+    all_boxes = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(boxes))
+    uid = (C.c_uint8 * 128).from_buffer_copy(ids[0])
+    assert lib.fqb_comm_init(h, rank, world, uid, all_boxes) == 0, lib.fqb_last_error()
 
 
-def run_sharded(engine, n_batches, rank, world, device):
-    """Drive `engine` over this rank's batches with the cross-batch state handed along the ring.
+def run_sharded(engine, n_batches, rank, world, batch_pairs):
+    """Deal `n_batches` batches of one file over the ranks and drive this rank's share through the pipelined calls.
 
-    engine.align(b), engine.pair(b), engine.finish(b)     -- per-batch stages (finish = SW/refine + stats)
-    engine.get_state() -> list[int] (STATE_WORDS int64)   -- after pair(b)
-    engine.set_state(list[int])                           -- before pair(b)
+    engine.submit(b)                                  -- upload + align stage of global batch b (asynchronous)
+    engine.collect(b, first_pair, is_last)            -- pairing .. statistics of batch b, with the hand-off on either side
+    Batch b+world is submitted before batch b is collected, so its align stage overlaps the later stages of b.
     """
     mine = [b for b in range(n_batches) if b % world == rank]
-    for b in mine:
-        engine.align(b)                                     # heavy, no dependency on other batches
-        if b > 0:
-            src = (b - 1) % world
-            if src != rank:
-                buf = torch.zeros(STATE_WORDS, dtype=torch.int64, device=device)
-                dist.recv(buf, src=src)
-                engine.set_state(buf.tolist())
-        engine.pair(b)
-        if b + 1 < n_batches:
-            dst = (b + 1) % world
-            if dst != rank:
-                dist.send(torch.tensor(engine.get_state(), dtype=torch.int64, device=device), dst=dst)
-        engine.finish(b)
+    if mine:
+        engine.submit(mine[0])
+    for j, b in enumerate(mine):
+        if j + 1 < len(mine):
+            engine.submit(mine[j + 1])
+        engine.collect(b, b * batch_pairs, b == n_batches - 1)
     return mine
-
-
-def reduce_accumulators(groups, rank, world):
-    """groups: list of (tensor, op) living on this rank's device; reduced in place onto rank 0."""
-    if world == 1:
-        return
-    for t, op in groups:
-        dist.reduce(t, dst=0, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MIN)
-
-
-VAR_ITEM_BYTES = {0: 20, 1: 8}     # pile-up entries, duplicate keys (fqb_stats_var_*)
-
-
-def gather_variable(engine, rank, world, device):
-    """Gather the variable-size statistics state onto rank 0 (after reduce_accumulators + import of the sums).
-
-    engine.var_export(which) -> 1-D uint8 torch tensor (on `device` or on the host);  engine.var_import(which, uint8
-    tensor on `device`) on rank 0.
-    """
-    if world == 1:
-        return
-    import os
-    import time
-    verbose = bool(os.environ.get("FQB_BENCH_VERBOSE")) and rank == 0 and device.type == "cuda"
-    for which in sorted(VAR_ITEM_BYTES):
-        t0 = time.time()
-        mine = engine.var_export(which)
-        if verbose:
-            torch.cuda.synchronize(); t1 = time.time()
-        n = torch.tensor([mine.numel()], dtype=torch.int64, device=device)
-        sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-        dist.all_gather(sizes, n)
-        sizes = [int(x.item()) for x in sizes]
-        cap = max(max(sizes), 1)
-        buf = torch.zeros(cap, dtype=torch.uint8, device=device)
-        buf[: mine.numel()] = mine.to(device)
-        out = [torch.zeros(cap, dtype=torch.uint8, device=device) for _ in range(world)] if rank == 0 else None
-        dist.gather(buf, out, dst=0)
-        if verbose:
-            torch.cuda.synchronize(); t2 = time.time()
-        if rank == 0:
-            for r in range(1, world):
-                if sizes[r]:
-                    engine.var_import(which, out[r][: sizes[r]])
-        if verbose:
-            torch.cuda.synchronize(); t3 = time.time()
-            print("  var group %d: export %.1f ms, gather %.1f ms (%d bytes max), import %.1f ms" % (
-                which, (t1 - t0) * 1e3, (t2 - t1) * 1e3, cap, (t3 - t2) * 1e3), flush=True)

@@ -242,6 +242,25 @@ int fqb_stats_import(fqb_handle *h, int which, const void *src_device);
 int fqb_stats_var_count(fqb_handle *h, int which, uint64_t *n);
 int fqb_stats_var_export(fqb_handle *h, int which, void *dst, uint64_t cap);
 int fqb_stats_var_import(fqb_handle *h, int which, const void *src, uint64_t n);
+/* ---- multi-GPU in the library itself (host side stays C/C++: the loop to shard is src/BwtMapper.cpp:1796-2143, batch unit
+ * src/BwtMapper.h:36-37) -------------------------------------------------------------------------------------------
+ * Global batch b of a file belongs to rank b % world.  fqb_comm_ring_handle creates the handle's mailbox for the
+ * 56-byte hand-off (drand48 position + last_ii) and returns its cudaIpcMemHandle_t; fqb_comm_unique_id is
+ * ncclGetUniqueId.  One process per GPU: the launcher distributes rank 0's id and every rank's mailbox handle, then each
+ * rank calls fqb_comm_init (NCCL communicator for the end-of-run merge; the next rank's mailbox is mapped through CUDA
+ * IPC and written over NVLink by a one-thread kernel).  One process driving several GPUs: fqb_comm_init_local on all its
+ * handles (peer access instead of IPC).  fqb_collect_pairs_sharded is fqb_collect_pairs with the hand-off in the stream:
+ * global_batch = position of the batch in file order, first_pair = global index of its first pair, is_last = no batch
+ * follows in this file.  fqb_comm_merge_stats (every rank, after its last batch): grouped ncclReduce of the accumulators
+ * onto rank 0 (sum; first-touch contig order: min), then exact-size grouped ncclSend / ncclRecv of the pile-up entries and
+ * distinct PCR-duplicate keys, merged on rank 0; *ms_out = device time of the exchange.  Rank 0 then splices the ranks'
+ * InsertSizeTable batches (fqb_stats_merge_tables) and writes the files (fqb_stats_finish). */
+int fqb_comm_ring_handle(fqb_handle *h, uint8_t *out64);
+int fqb_comm_unique_id(uint8_t *out128);
+int fqb_comm_init(fqb_handle *h, int rank, int world, const uint8_t *nccl_id128, const uint8_t *ring_handles /* world x 64 */);
+int fqb_comm_init_local(fqb_handle **hs, int n);
+int fqb_collect_pairs_sharded(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, uint64_t global_batch, uint64_t first_pair, int is_last);
+int fqb_comm_merge_stats(fqb_handle *h, double *ms_out);
 int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
 /* asynchronous variant: the copies run on a side stream while the next batch is processed; fqb_rows_wait blocks until
  * rows1/rows2 of the last call are complete (pinned destination buffers for real overlap) */
