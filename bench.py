@@ -27,13 +27,34 @@ sys.path.insert(0, ROOT)
 from fastquick_b200 import _abi  # noqa: E402
 
 BATCH = _abi.FQB_BATCH_PAIRS
-READ_LEN = 100
-WORKLOAD = "synthetic 10M 2x100bp pairs (f_on=1, 1% subst, 0.1%+0.1% indel) vs synthetic 10,197-marker flank index"
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "FASTQuick_ref")
-NCU_DRAM_BYTES_PER_LAUNCH = 7.341e9   # search_kernel, one 262,144-pair launch: 3.499 GB read + 3.843 GB written (ncu capture r1f)
+NCU_DRAM_BYTES_PER_LAUNCH = 7.341e9   # search_kernel, one 262,144-pair launch of 2x100_10k: 3.499 GB read + 3.843 GB written (ncu capture r1f)
 REF_SAMPLE_PAIRS = 32768         # pairs per step of the reference arm / cpu_baseline sample unit
 STAGES = ("prep + k-mer filter + cal_width + match_gap + aln2seq/bwt_sa/mapQ + infer_isize + pairing + mate-rescue SW + gapped refinement + "
           "StatCollector pair classification and per-base pile-up/depth/quality/cycle accumulation (SURVEY 8 rows a1-a13)")
+# BASELINE.json configs[1..4] (+ SURVEY 8(d)'s secondary WGS-like mix); the default and the contract line is configs[1].
+# markers = (long, short, X, Y) flank counts of the synthetic reduced reference; reads = fqb_synth_read_cfg_t overrides
+CONFIGS = {
+    "2x100_10k": dict(read_len=100, markers=(1000, 9000, 100, 97), reads={},
+                      workload="synthetic 10M 2x100bp pairs (f_on=1, 1% subst, 0.1%+0.1% indel) vs synthetic 10,197-marker flank index"),
+    "2x150_10k": dict(read_len=150, markers=(1000, 9000, 100, 97), reads={},
+                      workload="synthetic 200M 2x150bp pairs (f_on=1, 1% subst, 0.1%+0.1% indel) vs synthetic 10,197-marker flank index (BASELINE configs[2])"),
+    "hapmap_higherr": dict(read_len=100, markers=(979, 8808, 0, 0), reads=dict(sub_rate=0.04, ins_rate=0.01, del_rate=0.01, max_indel_len=3),
+                           workload="synthetic 2x100bp pairs at 4% subst, 1%+1% indel (lengths 1-3) vs synthetic 9,787-marker flank index (hapmap_3.3 count, BASELINE configs[3])"),
+    "exome_2x150": dict(read_len=150, markers=(990, 8906, 0, 0), reads={},
+                        workload="synthetic 2x150bp pairs vs synthetic 9,896-marker flank index (exome marker count, BASELINE configs[4])"),
+    "wgs_mix": dict(read_len=100, markers=(1000, 9000, 100, 97), reads=dict(f_on=0.0021),
+                    workload="synthetic 2x100bp pairs, WGS-like mix: 0.21% on target, the rest uniform background (filter-bound; SURVEY 8(d) secondary)"),
+}
+CFG = CONFIGS["2x100_10k"]
+READ_LEN = 100
+WORKLOAD = CFG["workload"]
+
+
+def select_config(name):
+    global CFG, READ_LEN, WORKLOAD
+    CFG = CONFIGS[name]
+    READ_LEN, WORKLOAD = CFG["read_len"], CFG["workload"]
 
 
 def peaks():
@@ -85,6 +106,7 @@ class ClockSampler:
 def make_synth(lib):
     cfg = _abi.SynthRefCfg()
     lib.fqb_synth_ref_cfg_default(C.byref(cfg))          # 1000 long + 9000 short + 100 X + 97 Y markers
+    cfg.n_long, cfg.n_short, cfg.n_x, cfg.n_y = CFG["markers"]
     s = C.c_void_p()
     assert lib.fqb_synth_create(C.byref(cfg), C.byref(s)) == 0, lib.fqb_last_error()
     return s
@@ -94,6 +116,8 @@ def gen_reads(lib, synth, first_pair, n_pairs, out=None):
     rc = _abi.SynthReadCfg()
     lib.fqb_synth_read_cfg_default(C.byref(rc))
     rc.read_len = READ_LEN
+    for k, v in CFG["reads"].items():
+        setattr(rc, k, v)
     arrs = out if out is not None else [np.empty((n_pairs, READ_LEN), np.uint8) for _ in range(4)]
     assert lib.fqb_synth_reads(synth, C.byref(rc), C.c_int64(first_pair), C.c_int64(n_pairs),
                                *[_abi.u8p(a) for a in arrs], 0) == 0, lib.fqb_last_error()
@@ -153,7 +177,7 @@ def main_reference(args):
         "impl": "reference", "metric": "read-pairs/s (align+pileup)", "value": value, "unit": "read-pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_sec / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_step": REF_SAMPLE_PAIRS,
+        "config": {"workload": WORKLOAD, "name": args.config, "pairs_per_step": REF_SAMPLE_PAIRS,
                    "note": "reference FASTQuick align (k-mer filter, bwa aln/sampe, StatCollector, BAM) timed by its own "
                            "'Processed Pair End mapping' line; index load excluded"},
         "cpu_baseline": {"value": value, "unit": "read-pairs/s", "cores": cores, "kind": "reference",
@@ -165,53 +189,32 @@ def main_reference(args):
 
 # ----------------------------------------------------------------------------- GPU arm
 class Engine:
-    """The per-batch stages of the hot path over this rank's resident shard (interface of fastquick_b200.multigpu)."""
+    """This rank's shard driven through the library's pipelined calls (interface of fastquick_b200.multigpu.run_sharded):
+    batch b+world is submitted (upload + align stage on the align stream) before batch b is collected (pair / mate rescue /
+    refinement / statistics on the main stream, with the hand-off ring on either side when world > 1)."""
 
-    def __init__(self, lib, h, dev, n_pairs, rank, world):
-        self.lib, self.h, self.dev, self.n, self.rank, self.world = lib, h, dev, n_pairs, rank, world
-        self.base = 0           # local step index of global batch 0 of the current phase
+    def __init__(self, lib, h, n_pairs, world):
+        self.lib, self.h, self.n, self.world = lib, h, n_pairs, world
+        self.src, self.on_device, self.rows = None, 0, None       # set per timed phase
+        self.base = 0                                              # local step index of this phase's global batch 0
 
-    def _ptr(self, t):
+    @staticmethod
+    def _ptr(t):
         return C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_uint8))
 
-    def align(self, b):
-        d = self.dev[self.base + b // self.world]
-        lib, h = self.lib, self.h
-        assert lib.fqb_stage_load(h, self.n, READ_LEN, self._ptr(d[0]), self._ptr(d[1]), None, self._ptr(d[2]), self._ptr(d[3]), None, 1) == 0, lib.fqb_last_error()
-        assert lib.fqb_set_pair_base(h, C.c_uint64(b * self.n)) == 0
-        assert lib.fqb_stage_align(h) == 0, lib.fqb_last_error()
+    def submit(self, b):
+        d = self.src[self.base + b // self.world]
+        lib = self.lib
+        assert lib.fqb_submit_pairs(self.h, self.n, READ_LEN, self._ptr(d[0]), self._ptr(d[1]), None, self._ptr(d[2]), self._ptr(d[3]), None,
+                                    self.on_device) == 0, lib.fqb_last_error()
 
-    def pair(self, b):
-        assert self.lib.fqb_stage_pair(self.h) == 0, self.lib.fqb_last_error()
-
-    def finish(self, b):
-        assert self.lib.fqb_stage_sw_refine(self.h) == 0, self.lib.fqb_last_error()
-        assert self.lib.fqb_stage_stats(self.h) == 0, self.lib.fqb_last_error()
-
-    def var_export(self, which):
-        import torch
-        n = C.c_uint64(0)
-        assert self.lib.fqb_stats_var_count(self.h, which, C.byref(n)) == 0, self.lib.fqb_last_error()
-        item = 20 if which == 0 else 8
-        t = torch.empty(int(n.value) * item, dtype=torch.uint8, device="cuda")       # exported device to device
-        if n.value:
-            assert self.lib.fqb_stats_var_export(self.h, which, C.c_void_p(t.data_ptr()), n) == 0, self.lib.fqb_last_error()
-        return t
-
-    def var_import(self, which, t):
-        item = 20 if which == 0 else 8
-        t = t.contiguous()
-        assert self.lib.fqb_stats_var_import(self.h, which, C.c_void_p(t.data_ptr()), C.c_uint64(t.numel() // item)) == 0, self.lib.fqb_last_error()
-
-    def get_state(self):
-        calls, ii = C.c_uint64(0), _abi.ISize()
-        self.lib.fqb_get_stream_state(self.h, C.byref(calls), C.byref(ii))
-        raw = np.frombuffer(bytes(ii), dtype=np.int64)
-        return [int(calls.value)] + [int(x) for x in raw] + [0] * (7 - len(raw))
-
-    def set_state(self, s):
-        ii = _abi.ISize.from_buffer_copy(np.array(s[1:1 + C.sizeof(_abi.ISize) // 8], dtype=np.int64).tobytes())
-        self.lib.fqb_set_stream_state(self.h, C.c_uint64(int(s[0])), C.byref(ii))
+    def collect(self, b, first_pair, is_last):
+        lib = self.lib
+        r1 = r2 = None
+        if self.rows is not None:
+            dst = self.rows[(b // self.world) & 1]
+            r1, r2 = C.c_void_p(dst[0].data_ptr()), C.c_void_p(dst[1].data_ptr())
+        assert lib.fqb_collect_pairs_sharded(self.h, r1, r2, C.c_uint64(b), C.c_uint64(first_pair), int(is_last)) == 0, lib.fqb_last_error()
 
 
 def main_gpu(args):
@@ -241,7 +244,12 @@ def main_gpu(args):
     assert lib.fqb_synth_write_inputs(synth, work.encode()) == 0, lib.fqb_last_error()
     assert lib.fqb_synth_write_index(synth, os.path.join(work, "genome.fa").encode(), os.path.join(work, "dbsnp.vcf").encode(), prefix.encode(), 0) == 0, lib.fqb_last_error()
     assert lib.fqb_stats_open(h, prefix.encode()) == 0, lib.fqb_last_error()
+    multigpu.bootstrap(lib, h, rank, world)          # NCCL communicator + hand-off mailboxes, inside the library
     stream = torch.cuda.ExternalStream(lib.fqb_stream(h))
+
+    # BW_L2 of THIS box, measured now: random 64-byte reads over an 8 MiB buffer, all SMs, best of 10
+    l2_best, l2_med = C.c_double(0), C.c_double(0)
+    assert lib.fqb_measure_l2(local, C.c_int64(8 << 20), 64, 10, C.byref(l2_best), C.byref(l2_med)) == 0, lib.fqb_last_error()
 
     n_steps = args.warmup + args.steps
     n_pairs = args.pairs_per_step
@@ -254,55 +262,22 @@ def main_gpu(args):
         host.append(bufs)
     dev = [[b.cuda(non_blocking=True) for b in bufs] for bufs in host]   # whole shard resident in HBM
     torch.cuda.synchronize()
-    eng = Engine(lib, h, dev, n_pairs, rank, world)
-
-    # accumulator groups reduced to rank 0 at the end of the timed region (NCCL over NVLink)
-    groups = []
-    for which, dt, op in ((0, torch.int32, "sum"), (1, torch.int64, "sum"), (2, torch.int32, "sum"), (3, torch.int32, "min")):
-        nb = C.c_uint64(0)
-        assert lib.fqb_stats_group_bytes(h, which, C.byref(nb)) == 0
-        groups.append((which, torch.empty(int(nb.value) // (4 if dt == torch.int32 else 8), dtype=dt, device=device), op))
-
-    def reduce_stats():
-        if world == 1:
-            return
-        tt = [time.time()]
-        for which, t, op in groups:
-            assert lib.fqb_stats_export(h, which, C.c_void_p(t.data_ptr())) == 0, lib.fqb_last_error()
-        multigpu.reduce_accumulators([(t, op) for _, t, op in groups], rank, world)
-        if rank == 0:
-            for which, t, op in groups:
-                assert lib.fqb_stats_import(h, which, C.c_void_p(t.data_ptr())) == 0, lib.fqb_last_error()
-        torch.cuda.synchronize(); tt.append(time.time())
-        multigpu.gather_variable(eng, rank, world, device)      # pile-up entries + duplicate keys, after the sums
-        torch.cuda.synchronize(); tt.append(time.time())
-        if os.environ.get("FQB_BENCH_VERBOSE") and rank == 0:
-            print("reduce: fixed groups %.1f ms, variable state %.1f ms" % ((tt[1] - tt[0]) * 1e3, (tt[2] - tt[1]) * 1e3), file=sys.stderr, flush=True)
-
-    def ptr(t):
-        return C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_uint8))
-
+    eng = Engine(lib, h, n_pairs, world)
     rows_host = [[torch.empty((n_pairs, _abi.READ_DTYPE.itemsize), dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(2)]
-    ii_host = _abi.ISize()
+    merge_ms = []
 
-    def run_device(first_step, k):
+    def merge():
+        ms = C.c_double(0)
+        assert lib.fqb_comm_merge_stats(h, C.byref(ms)) == 0, lib.fqb_last_error()      # grouped ncclReduce + exact-size ncclSend/Recv
+        merge_ms.append(ms.value)
+
+    def run(first_step, k, e2e):
+        # device arm: inputs resident in HBM.  e2e arm: the public calls on pinned host buffers -- every step uploads its
+        # 4 input arrays and copies its result rows back, both inside the timed region
         eng.base = first_step
-        multigpu.run_sharded(eng, k * world, rank, world, device)
-
-    def run_e2e(first_step, k):
-        # the public per-batch calls: pinned host FASTQ arrays in, per-read result rows out, statistics accumulated.
-        # Uploads of batch s+1 and the row copies of batch s overlap the kernels of the neighbouring batches.
-        for s in range(first_step, first_step + k):
-            b = host[s]
-            if s + 1 < first_step + k:
-                nb = host[s + 1]
-                assert lib.fqb_prefetch_pairs(h, n_pairs, READ_LEN, ptr(nb[0]), ptr(nb[1]), None, ptr(nb[2]), ptr(nb[3]), None) == 0, lib.fqb_last_error()
-            rc = lib.fqb_align_pairs(h, n_pairs, READ_LEN, ptr(b[0]), ptr(b[1]), None, ptr(b[2]), ptr(b[3]), None, None, None, C.byref(ii_host))
-            assert rc == 0, lib.fqb_last_error()
-            assert lib.fqb_stage_stats(h) == 0, lib.fqb_last_error()
-            dst = rows_host[s & 1]
-            assert lib.fqb_stage_fetch_rows_async(h, C.c_void_p(dst[0].data_ptr()), C.c_void_p(dst[1].data_ptr())) == 0, lib.fqb_last_error()
-        assert lib.fqb_rows_wait(h) == 0, lib.fqb_last_error()
+        eng.src, eng.on_device, eng.rows = (host, 0, rows_host) if e2e else (dev, 1, None)
+        multigpu.run_sharded(eng, k * world, rank, world, n_pairs)
+        assert lib.fqb_rows_wait(h) == 0, lib.fqb_last_error()       # the one wait of the run: rows of the last batch + deferred status
 
     def rq_time():
         ms, nl = C.c_double(0.0), C.c_uint64(0)
@@ -314,11 +289,11 @@ def main_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, with_reduce):
+    def timed(e2e):
         lib.fqb_reset_stream(h)
-        fn(0, args.warmup)
-        if with_reduce:
-            reduce_stats()          # warm-up of the end-of-run exchange too (NCCL sets up its channels lazily)
+        run(0, args.warmup, e2e)
+        merge()                     # warm-up of the end-of-run exchange too (NCCL sets up its channels lazily)
+        assert lib.fqb_stats_reset(h) == 0, lib.fqb_last_error()     # the timed region starts from empty accumulators
         barrier()
         lib.fqb_reset_stream(h)
         c0 = (C.c_uint64 * 4)(); lib.fqb_stage_counters(h, c0)
@@ -326,13 +301,10 @@ def main_gpu(args):
         rq0 = rq_time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            fn(args.warmup, args.steps)
-            if with_reduce:
-                reduce_stats()
-                stream.wait_stream(torch.cuda.current_stream())
-            e1.record(stream)
+        e0.record(stream)
+        run(args.warmup, args.steps, e2e)
+        merge()
+        e1.record(stream)
         barrier()
         t1 = time.time()
         ms = e0.elapsed_time(e1)
@@ -348,16 +320,17 @@ def main_gpu(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    ms, ctr, launches, t0, t1, rq = timed(run_device, True)
+    ms, ctr, launches, t0, t1, rq = timed(False)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    ms_e2e = timed(run_e2e, True)[0]
+    merge_ms_device = merge_ms[-1]
+    ms_e2e = timed(True)[0]
 
     total_pairs = args.steps * n_pairs * world
     value = total_pairs / (ms * 1e-3)
     e2e_value = total_pairs / (ms_e2e * 1e-3)
     # roofline of the dominant kernels (bwt_cal_width + bwt_match_gap): algorithmic bytes = 64 B x N_blk,
     # N_blk counted on the device for exactly the reads processed in the timed region; clock = CUDA events recorded by
-    # the engine around those launches on its own stream, averaged over the launches of the timed region
+    # the engine around those launches on the stream they run on, averaged over the launches of the timed region
     hbm_peak, peak_kind = peaks()
     n_blk = ctr[2]
     rq_ms_per_launch = rq[0] / max(rq[1], 1)
@@ -376,25 +349,31 @@ def main_gpu(args):
         "metric": "read-pairs/s (align+pileup)", "value": value, "unit": "read-pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_step": n_pairs, "read_len": READ_LEN, "stages": STAGES,
-                   "l2_policy": "every step reads a different 105 MB batch; per-step working set (inputs+widths+stack arena) exceeds the 126 MB L2",
-                   "index": "10,197 markers, l_pac 6,608,697, replicated per GPU",
-                   "multi_gpu": "batches round-robin over ranks; drand48 position + last_ii handed rank to rank (56 B per batch); "
-                                "accumulators NCCL-reduced and pile-up entries / duplicate keys gathered to rank 0 inside the timed region"},
+        "config": {"workload": WORKLOAD, "name": args.config, "pairs_per_step": n_pairs, "read_len": READ_LEN, "stages": STAGES,
+                   "l2_policy": "every step reads a different %d MB batch; per-step working set (inputs+widths+stack arena) exceeds the 126 MB L2" % (4 * n_pairs * READ_LEN // 1000000),
+                   "index": "%d markers (counts of the named marker set; positions/alleles synthetic), replicated per GPU" % sum(CFG["markers"]),
+                   "pipeline": "fqb_submit_pairs(b+1) before fqb_collect_pairs_sharded(b): align stage of the next batch on a second stream, "
+                               "no host synchronisation per batch (one wait at the end of the run)",
+                   "multi_gpu": "batches round-robin over ranks; drand48 position + last_ii handed rank to rank through NVLink peer memory "
+                                "(56 B per batch, one-thread kernels); accumulators reduced with one NCCL group and pile-up entries / "
+                                "duplicate keys sent to rank 0 inside the timed region, all in the C library",
+                   "reference_arm_sample": "bench.py --impl reference times %d-pair samples of the same workload per step (the CPU path is ~1000x slower)" % REF_SAMPLE_PAIRS},
         "e2e": {"value": e2e_value, "unit": "read-pairs/s", "h2d_bytes_per_step": 4 * n_pairs * READ_LEN,
-                "d2h_bytes_per_step": int(2 * n_pairs * _abi.READ_DTYPE.itemsize)},
+                "d2h_bytes_per_step": int(2 * n_pairs * _abi.READ_DTYPE.itemsize), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n_pairs == BATCH else None,
+        "roofline": {"bound": "l2", "achieved": achieved, "peak": l2_best.value, "unit": "GB/s", "frac": achieved / l2_best.value,
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (n_pairs == BATCH and args.config == "2x100_10k") else None,
                      "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of search_kernel, ncu --set full capture r1f (profiles/r01_search_kernel_ncu.md)",
-                     "peak_kind": peak_kind + " HBM copy bandwidth (MEASURED_PEAKS.json)",
-                     "kernel": "width_kernel + search_kernel (rank queries of one 262,144-pair batch)",
+                     "peak_kind": "BW_L2 measured on this box in this run: fqb_measure_l2, random 64-byte reads over an 8 MiB buffer, all SMs, best of 10 (median %.1f)" % l2_med.value,
+                     "hbm_peak": hbm_peak, "hbm_peak_kind": peak_kind + " HBM copy bandwidth (MEASURED_PEAKS.json)", "frac_of_hbm_peak": achieved / hbm_peak,
+                     "kernel": "width_kernel + search_kernel (rank queries of one %d-pair batch)" % n_pairs,
                      "kernel_ms_per_launch": rq_ms_per_launch, "algorithmic_bytes_per_launch": bytes_per_launch,
                      "share_of_step": rq_ms_per_launch / (ms / args.steps),
                      "algorithmic": "64 B x N_blk occ-block touches of bwt_cal_width+bwt_match_gap, per GPU; N_blk/pair = %.1f" % (n_blk / (args.steps * n_pairs)),
-                     "note": "the FM index (10 MB) is L2-resident: these kernels are bound by issue slots and stack-pop latency, not by HBM bandwidth (DESIGN.md 3.3)",
+                     "note": "the FM index (10 MB) is L2-resident; the kernels are bound by dependent-latency x steps and instruction issue, not by bandwidth (DESIGN.md 3.3)",
                      "occ_block_touches_per_s_job": touches_per_s_job},
+        "exchange_ms": merge_ms_device,
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -421,9 +400,11 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="2x100_10k", choices=sorted(CONFIGS), help="workload (default: BASELINE.json configs[1], the contract line)")
     ap.add_argument("--pairs-per-step", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    select_config(args.config)
     if args.impl == "reference":
         main_reference(args)
     else:

@@ -911,6 +911,28 @@ int fqb_stats_open(fqb_handle *h, const char *index_prefix) {
     return FQB_OK;
 }
 
+// back to the state right after fqb_stats_open: every accumulator zero, no pile-up entries, no duplicate keys (a new run on
+// the same handle; bench.py separates its warm-up from its timed region with it)
+int fqb_stats_reset(fqb_handle *h) {
+    if (!h || !h->stats_open) { set_error("fqb_stats_reset: statistics are not open"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    if (int rc = drain_post(h, true, true)) return rc;
+    cudaStream_t st = h->stream;
+    const size_t nc = h->stabs.contigs.size(), ns = h->stabs.n_sites ? h->stabs.n_sites : 1;
+    CU_CHECK(cudaMemsetAsync(h->d_depth, 0, ns * 3 * 4, st));
+    CU_CHECK(cudaMemsetAsync(h->d_emp, 0, (kEmpWords + 1) * 8, st));
+    CU_CHECK(cudaMemsetAsync(h->d_contig_ctr, 0, nc * 4 * 4, st));
+    CU_CHECK(cudaMemsetAsync(h->d_contig_ctr + nc * 4, 0xff, nc * 4, st));
+    CU_CHECK(cudaMemsetAsync(h->d_dup_keys, 0, (size_t)h->dup_cap * 8, st));
+    CU_CHECK(cudaMemsetAsync(h->d_ntuples, 0, 4, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    h->tuples_host.clear(); h->n_tuples_imp = 0; h->tuples_bound = 0;
+    h->pairs_seen = 0;
+    for (auto &x : h->files_closed) x = 0;
+    h->files.clear();
+    return FQB_OK;
+}
+
 // The FileStatCollector counters live on the device as running totals; a file's own counters are the totals at its
 // end minus the totals when it began (collector.AddFSC(FSC), src/BwtMapper.cpp:254).
 // joins the deferred host phases; reports the first failure one of them met
@@ -1511,6 +1533,18 @@ int fqb_comm_merge_stats(fqb_handle *h, double *ms_out) {
     cudaStream_t st = h->stream;
     const int W = h->comm_world, me = h->comm_rank;
     const size_t nc = h->stabs.contigs.size(), ns = h->stabs.n_sites ? h->stabs.n_sites : 1;
+    // how much variable-size state every rank holds (this first collective also absorbs the skew between the ranks, so that
+    // the events below time the exchange itself)
+    uint64_t mine[2] = {0, 0};
+    for (int which = 0; which < 2; ++which) { int rc = fqb_stats_var_count(h, which, &mine[which]); if (rc) return rc; }
+    uint64_t *d_cnt = nullptr;
+    CU_CHECK(cudaMallocAsync(&d_cnt, (size_t)(W + 1) * 16, st));
+    CU_CHECK(cudaMemcpyAsync(d_cnt + 2 * W, mine, 16, cudaMemcpyHostToDevice, st));
+    NCCL_CHECK(N->AllGather(d_cnt + 2 * W, d_cnt, 2, ncclUint64, h->nccl, st));
+    std::vector<uint64_t> cnt((size_t)W * 2);
+    CU_CHECK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)W * 16, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    CU_CHECK(cudaFreeAsync(d_cnt, st));
     cudaEvent_t e0, e1;
     CU_CHECK(cudaEventCreate(&e0)); CU_CHECK(cudaEventCreate(&e1));
     CU_CHECK(cudaEventRecord(e0, st));
@@ -1520,43 +1554,59 @@ int fqb_comm_merge_stats(fqb_handle *h, double *ms_out) {
     NCCL_CHECK(N->Reduce(h->d_contig_ctr, h->d_contig_ctr, nc * 4, ncclUint32, ncclSum, 0, h->nccl, st));
     NCCL_CHECK(N->Reduce(h->d_contig_ctr + nc * 4, h->d_contig_ctr + nc * 4, nc, ncclUint32, ncclMin, 0, h->nccl, st));
     NCCL_CHECK(N->GroupEnd());
-    // how much variable-size state every rank holds
-    uint64_t mine[2] = {0, 0};
-    for (int which = 0; which < 2; ++which) { int rc = fqb_stats_var_count(h, which, &mine[which]); if (rc) return rc; }
-    uint64_t *d_cnt = nullptr;
-    CU_CHECK(cudaMalloc(&d_cnt, (size_t)(W + 1) * 16));
-    CU_CHECK(cudaMemcpyAsync(d_cnt + 2 * W, mine, 16, cudaMemcpyHostToDevice, st));
-    NCCL_CHECK(N->AllGather(d_cnt + 2 * W, d_cnt, 2, ncclUint64, h->nccl, st));
-    std::vector<uint64_t> cnt((size_t)W * 2);
-    CU_CHECK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)W * 16, cudaMemcpyDeviceToHost, st));
-    CU_CHECK(cudaStreamSynchronize(st));
-    cudaFree(d_cnt);
-    const size_t item[2] = {sizeof(PileupTuple), 8};
     if (me != 0) {
-        void *buf[2] = {nullptr, nullptr};
-        for (int which = 0; which < 2; ++which)
-            if (mine[which]) {
-                CU_CHECK(cudaMalloc(&buf[which], mine[which] * item[which]));
-                int rc = fqb_stats_var_export(h, which, buf[which], mine[which]);
-                if (rc) return rc;
-            }
+        // pile-up entries usually sit on the device in one piece (d_tuples): send them from there; the distinct duplicate
+        // keys are compacted out of the hash set first
+        const bool direct = h->tuples_host.empty() && h->n_tuples_imp == 0;
+        void *tup = direct ? (void *)h->d_tuples : nullptr, *keys = nullptr;
+        if (!direct && mine[0]) {
+            CU_CHECK(cudaMallocAsync(&tup, mine[0] * sizeof(PileupTuple), st));
+            int rc = fqb_stats_var_export(h, 0, tup, mine[0]);
+            if (rc) return rc;
+        }
+        if (mine[1]) {
+            CU_CHECK(cudaMallocAsync(&keys, (mine[1] + 1) * 8, st));
+            unsigned long long *kcnt = static_cast<unsigned long long *>(keys) + mine[1];
+            CU_CHECK(cudaMemsetAsync(kcnt, 0, 8, st));
+            dup_compact_kernel<<<(h->dup_cap + 255) / 256, 256, 0, st>>>(h->d_dup_keys, h->dup_cap, static_cast<unsigned long long *>(keys), kcnt);
+            ++h->n_launches;
+        }
         NCCL_CHECK(N->GroupStart());
-        for (int which = 0; which < 2; ++which) if (mine[which]) NCCL_CHECK(N->Send(buf[which], mine[which] * item[which], ncclUint8, 0, h->nccl, st));
+        if (mine[0]) NCCL_CHECK(N->Send(tup, mine[0] * sizeof(PileupTuple), ncclUint8, 0, h->nccl, st));
+        if (mine[1]) NCCL_CHECK(N->Send(keys, mine[1] * 8, ncclUint8, 0, h->nccl, st));
         NCCL_CHECK(N->GroupEnd());
-        CU_CHECK(cudaStreamSynchronize(st));
-        cudaFree(buf[0]); cudaFree(buf[1]);
+        if (!direct && tup) CU_CHECK(cudaFreeAsync(tup, st));
+        if (keys) CU_CHECK(cudaFreeAsync(keys, st));
     } else {
-        std::vector<void *> buf((size_t)W * 2, nullptr);
-        for (int r = 1; r < W; ++r) for (int which = 0; which < 2; ++which)
-            if (cnt[2 * r + which]) CU_CHECK(cudaMalloc(&buf[2 * r + which], cnt[2 * r + which] * item[which]));
+        // exact-size receives: the pile-up entries straight behind the ones imported so far, all ranks' keys into one buffer
+        uint64_t n_tup = 0, n_keys = 0;
+        for (int r = 1; r < W; ++r) { n_tup += cnt[2 * r]; n_keys += cnt[2 * r + 1]; }
+        if (h->n_tuples_imp + n_tup > h->cap_tuples_imp) {
+            const size_t cap = h->n_tuples_imp + n_tup;
+            PileupTuple *nb = nullptr;
+            CU_CHECK(cudaMalloc(&nb, cap * sizeof(PileupTuple)));
+            if (h->n_tuples_imp) CU_CHECK(cudaMemcpyAsync(nb, h->d_tuples_imp, h->n_tuples_imp * sizeof(PileupTuple), cudaMemcpyDeviceToDevice, st));
+            CU_CHECK(cudaStreamSynchronize(st));
+            cudaFree(h->d_tuples_imp);
+            h->d_tuples_imp = nb; h->cap_tuples_imp = cap;
+        }
+        unsigned long long *keys = nullptr;
+        if (n_keys) CU_CHECK(cudaMallocAsync(&keys, n_keys * 8, st));
         NCCL_CHECK(N->GroupStart());
-        for (int r = 1; r < W; ++r) for (int which = 0; which < 2; ++which)
-            if (cnt[2 * r + which]) NCCL_CHECK(N->Recv(buf[2 * r + which], cnt[2 * r + which] * item[which], ncclUint8, r, h->nccl, st));
+        uint64_t to = h->n_tuples_imp, ko = 0;
+        for (int r = 1; r < W; ++r) {
+            if (cnt[2 * r]) NCCL_CHECK(N->Recv(h->d_tuples_imp + to, cnt[2 * r] * sizeof(PileupTuple), ncclUint8, r, h->nccl, st));
+            if (cnt[2 * r + 1]) NCCL_CHECK(N->Recv(keys + ko, cnt[2 * r + 1] * 8, ncclUint8, r, h->nccl, st));
+            to += cnt[2 * r]; ko += cnt[2 * r + 1];
+        }
         NCCL_CHECK(N->GroupEnd());
-        for (int r = 1; r < W; ++r) for (int which = 0; which < 2; ++which)
-            if (cnt[2 * r + which]) { int rc = fqb_stats_var_import(h, which, buf[2 * r + which], cnt[2 * r + which]); if (rc) return rc; }
-        CU_CHECK(cudaStreamSynchronize(st));
-        for (void *b : buf) cudaFree(b);
+        h->n_tuples_imp += n_tup;
+        if (n_keys) {
+            // a key another rank also holds is one more duplicated pair (NumPCRDup += 2)
+            dup_merge_kernel<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(h->d_dup_keys, h->dup_cap, keys, n_keys, h->d_emp + kEmpWords, h->d_emp + (4 * 256 + 4096));
+            ++h->n_launches;
+            CU_CHECK(cudaFreeAsync(keys, st));
+        }
     }
     CU_CHECK(cudaEventRecord(e1, st));
     CU_CHECK(cudaEventSynchronize(e1));
@@ -1938,8 +1988,12 @@ int fqb_submit_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8
     const int si = h->n_fifo ? 1 - h->fifo[0] : 1 - h->cur;
     fqb_handle::BatchSet &B = h->sets[si];
     CU_CHECK(cudaStreamWaitEvent(h->align_stream, B.ev_done, 0));
-    int rc = load_set(h, si, h->align_stream, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, on_device);
+    // the upload runs on the copy stream (it only needs the staging arrays, free once the previous occupant's prep_kernel has
+    // run), so it overlaps the search of the batch before; the align stream picks it up through ev_in
+    int rc = load_set(h, si, h->copy_stream, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, on_device);
     if (rc) return rc;
+    CU_CHECK(cudaEventRecord(B.ev_in, h->copy_stream));
+    CU_CHECK(cudaStreamWaitEvent(h->align_stream, B.ev_in, 0));
     if ((rc = enqueue_align(h, si, h->align_stream))) return rc;
     CU_CHECK(cudaEventRecord(B.ev_align, h->align_stream));
     h->fifo[h->n_fifo++] = si;

@@ -190,6 +190,8 @@ int fqb_stage_sw_refine(fqb_handle *h);
 int fqb_stats_set_target_region(fqb_handle *h, const char *bed_path);
 int fqb_stats_open(fqb_handle *h, const char *index_prefix);
 int fqb_stats_begin_file(fqb_handle *h, const char *out_prefix, const char *fastq1, const char *fastq2);
+/* every accumulator back to zero (the state right after fqb_stats_open): a new run on the same handle */
+int fqb_stats_reset(fqb_handle *h);
 int fqb_stage_stats(fqb_handle *h);
 int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride);
 /* fqb_stats_emit and fqb_bam_emit copy what they need from the device, then format and write.  With FQB_ASYNC_EMIT=1 in the
