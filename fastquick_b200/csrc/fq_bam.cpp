@@ -499,11 +499,11 @@ void one_record(const BamContext &C, fqb_read_t &p, const fqb_read_t *mate_ptr, 
 }
 }  // namespace
 
-void bam_append_pair(const BamContext &C, fqb_read_t p, fqb_read_t q, const char *name, const uint8_t *bases_p, const uint8_t *quals_p,
+void bam_append_pair(const BamContext &C, fqb_read_t p, fqb_read_t q, const char *name, const char *name_q, const uint8_t *bases_p, const uint8_t *quals_p,
                      const uint8_t *bases_q, const uint8_t *quals_q, const XaHit *xa_p, int n_xa_p, const XaHit *xa_q, int n_xa_q,
                      const uint8_t *rseq_p, const uint8_t *rseq_q, std::string &out) {
     one_record(C, p, &q, name, bases_p, quals_p, xa_p, n_xa_p, rseq_p, out);       // may rewrite p's pos/strand (unmapped read of a half-mapped pair)
-    one_record(C, q, &p, name, bases_q, quals_q, xa_q, n_xa_q, rseq_q, out);
+    one_record(C, q, &p, name_q, bases_q, quals_q, xa_q, n_xa_q, rseq_q, out);
 }
 
 void bam_append_single(const BamContext &C, fqb_read_t p, const char *name, const uint8_t *bases, const uint8_t *quals, const XaHit *xa, int n_xa,

@@ -63,7 +63,7 @@ bool bam_prepare(const HostIndex &idx, const fqb_gap_opt_t &g, const std::vector
 // the reference's loop does, src/BwtMapper.cpp:2058-2066).
 // p, q: result rows (taken by value: SetSamRecord edits the unmapped read of a half-mapped pair).
 // bases/quals: the reads as they came from the FASTQ files (ASCII), full_len bytes each.
-void bam_append_pair(const BamContext &ctx, fqb_read_t p, fqb_read_t q, const char *name, const uint8_t *bases_p, const uint8_t *quals_p,
+void bam_append_pair(const BamContext &ctx, fqb_read_t p, fqb_read_t q, const char *name, const char *name_q, const uint8_t *bases_p, const uint8_t *quals_p,
                      const uint8_t *bases_q, const uint8_t *quals_q, const XaHit *xa_p, int n_xa_p, const XaHit *xa_q, int n_xa_q,
                      const uint8_t *rseq_p, const uint8_t *rseq_q, std::string &out);
 // rseq_p / rseq_q: the slot's p->rseq buffer as the reference's paired reader leaves it (see fqb_bam_emit), or nullptr

@@ -708,6 +708,7 @@ static int check_status(fqb_handle *h) {
     h->status_pending = false;
     const uint32_t *S = h->h_status, *K = h->h_ctrs;
     if (!h->cb_error.empty()) { set_error(h->cb_error); h->cb_error.clear(); return FQB_ERR_LIMIT; }
+    if (K[kPrepShortFlag]) { set_error("a read is shorter than 96 bases: the reference's k-mer filter reads bases 0..95 whatever the read length and sees stale buffer bytes there (src/BwtIndexer.cpp:443-450); unsupported -- disable the filter (kmer_thresh = 0) for such input"); return FQB_ERR_LIMIT; }
     if (K[kCtrSpillFlag]) { set_error("more than 16,384 reads of one batch outgrew the fast search pass"); return FQB_ERR_LIMIT; }
     if (K[4 * 2 + 2]) { set_error("a read overflowed even the max_entries-deep arena or 1024 hits"); return FQB_ERR_LIMIT; }
     if (S[kStSeErr]) { set_error("drand48 returned exactly 0.0 for a read with one best interval (p = 2^-48 per read): unsupported"); return FQB_ERR_LIMIT; }
@@ -960,6 +961,18 @@ static int close_current_file(fqb_handle *h) {
     return FQB_OK;
 }
 
+// the current file's FileStatCollector counters so far (src/BwtMapper.cpp:2116-2122 prints them when a file is done):
+// out6 = TotalFiltered, BwaUnmapped (both in pairs; the reference prints them x 2), TotalMAPQ, TotalRetained, NumBase, NumRead
+int fqb_stats_file_counters(fqb_handle *h, int64_t *out6) {
+    if (!h || !h->stats_open || !out6) { set_error("fqb_stats_file_counters: statistics are not open"); return FQB_ERR_STATE; }
+    CU_CHECK(cudaSetDevice(h->device));
+    CU_CHECK(cudaStreamSynchronize(h->stream));
+    unsigned long long sc[kEmpScalars];
+    CU_CHECK(cudaMemcpy(sc, h->d_emp + 4 * 256 + 4096, sizeof sc, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 6; ++k) out6[k] = (int64_t)sc[3 + k] - h->files_closed[k];
+    return FQB_OK;
+}
+
 // a new FASTQ pair: FileStatCollector FSC(fq1, fq2) (src/BwtMapper.cpp:249-254); the first call (re)creates <out_prefix>.InsertSizeTable
 int fqb_stats_begin_file(fqb_handle *h, const char *out_prefix, const char *fq1, const char *fq2) {
     if (!h || !h->stats_open) { set_error("fqb_stats_begin_file: call fqb_stats_open first"); return FQB_ERR_STATE; }
@@ -1024,7 +1037,8 @@ int fqb_stage_stats(fqb_handle *h) {
 
 // text emission for the last batch: one InsertSizeTable line per retained pair (ProcessPairStatus's fout lines).
 // names: n_pairs rows of name_stride bytes (NUL-padded), or null for the synthetic r%011lld names.
-int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride) {
+int fqb_stats_emit2(fqb_handle *h, const char *names, const char *names2, int32_t name_stride) {
+    if (!names2) names2 = names;
     if (!h || !h->stats_done) { set_error("fqb_stats_emit: run fqb_stage_stats first"); return FQB_ERR_STATE; }
     CU_CHECK(cudaSetDevice(h->device));
     if (int rc = drain_post(h, true, true)) return rc;                  // the previous batch's host phases read the staging written below
@@ -1044,7 +1058,7 @@ int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride) {
     if (!h->isize_table.is_open()) return FQB_OK;
     // host phase: format on several host threads (contiguous slices of the batch), write the slices in order.  `names` must
     // stay valid until the next fqb_stats_emit / fqb_bam_emit / fqb_stats_finish / fqb_bam_close call on this handle returns.
-    auto host_phase = [h, np, names, name_stride, first]() {
+    auto host_phase = [h, np, names, names2, name_stride, first]() {
         unsigned nthr = std::thread::hardware_concurrency();
         if (nthr < 1) nthr = 1;
         if (nthr > 16) nthr = 16;
@@ -1060,7 +1074,9 @@ int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride) {
                 const PairStat &ps = h->h_pstat[i];
                 if (ps.line_kind == 0) continue;
                 const char *name;
-                if (names) { nm.assign(names + i * (size_t)name_stride, strnlen(names + i * (size_t)name_stride, (size_t)name_stride)); name = nm.c_str(); }
+                // the line of a pair whose first read is unmapped carries the SECOND read's name (q->name, src/StatCollector.cpp:695,708)
+                const char *src = ps.line_kind == 2 ? names2 : names;
+                if (src) { nm.assign(src + i * (size_t)name_stride, strnlen(src + i * (size_t)name_stride, (size_t)name_stride)); name = nm.c_str(); }
                 else { snprintf(buf, sizeof buf, "r%011llu", (unsigned long long)(first + i)); name = buf; }
                 append_isize_line(h->stabs, ps, h->h_rows[2 * i], h->h_rows[2 * i + 1], name, o);
             }
@@ -1080,6 +1096,8 @@ int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride) {
     h->post_stats = std::async(std::launch::async, host_phase);
     return FQB_OK;
 }
+
+int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride) { return fqb_stats_emit2(h, names, nullptr, name_stride); }
 
 int fqb_emit_sync(fqb_handle *h) {
     if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
@@ -1769,8 +1787,9 @@ int fqb_bam_open(fqb_handle *h, const char *path, const char *rg_line) {
     return FQB_OK;
 }
 
-int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const uint8_t *bases1, const uint8_t *quals1,
-                 const uint8_t *bases2, const uint8_t *quals2, int32_t stride) {
+int fqb_bam_emit2(fqb_handle *h, const char *names, const char *names2, int32_t name_stride, const uint8_t *bases1, const uint8_t *quals1,
+                  const uint8_t *bases2, const uint8_t *quals2, int32_t stride) {
+    if (!names2) names2 = names;
     if (!h || !h->bam_open) { set_error("fqb_bam_emit: no BAM file open"); return FQB_ERR_STATE; }
     if (!h->dp_done || (h->stats_open && !h->stats_done)) { set_error("fqb_bam_emit: the batch must be through fqb_stage_sw_refine and fqb_stage_stats"); return FQB_ERR_STATE; }
     if (!bases1 || !quals1 || stride < 1 || (!h->single_end && (!bases2 || !quals2))) { set_error("fqb_bam_emit: the reads of the batch are required"); return FQB_ERR_ARG; }
@@ -1862,7 +1881,7 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
         const size_t lo = np * t / nthr, hi = np * (t + 1) / nthr;
         o.reserve((hi - lo) * 2 * (size_t)(160 + 3 * stride / 2));
         char buf[64];
-        std::string nm;
+        std::string nm, nm2;
         const uint8_t *nt4 = nt4_table();
         for (size_t i = lo; i < hi; ++i) {
             const fqb_read_t &p = h->h_bam_rows[2 * i], &q = h->h_bam_rows[2 * i + 1];
@@ -1883,10 +1902,12 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
             const char *name;
             if (names) { nm.assign(names + i * (size_t)name_stride, strnlen(names + i * (size_t)name_stride, (size_t)name_stride)); name = nm.c_str(); }
             else { snprintf(buf, sizeof buf, "r%011llu", (unsigned long long)(first + i)); name = buf; }
+            const char *name_q = name;             // the mates' names may differ (each record carries its own read's, SetSamRecord)
+            if (names2 && names2 != names) { nm2.assign(names2 + i * (size_t)name_stride, strnlen(names2 + i * (size_t)name_stride, (size_t)name_stride)); name_q = nm2.c_str(); }
             int n0 = 0, n1 = 0;
             const XaHit *x0 = p.n_multi ? xa_of((uint32_t)(2 * i), n0) : nullptr, *x1 = q.n_multi ? xa_of((uint32_t)(2 * i + 1), n1) : nullptr;
             if (h->single_end) bam_append_single(h->bam_ctx, p, name, bases1 + i * (size_t)stride, quals1 + i * (size_t)stride, x0, n0, o);
-            else bam_append_pair(h->bam_ctx, p, q, name, bases1 + i * (size_t)stride, quals1 + i * (size_t)stride, bases2 + i * (size_t)stride,
+            else bam_append_pair(h->bam_ctx, p, q, name, name_q, bases1 + i * (size_t)stride, quals1 + i * (size_t)stride, bases2 + i * (size_t)stride,
                                  quals2 + i * (size_t)stride, x0, n0, x1, n1, rs[0], rs[1], o);
         }
     };
@@ -1909,6 +1930,11 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const ui
     if (emit_inline()) { host_phase(); return drain_post(h, true, true); }
     h->post_bam = std::async(std::launch::async, host_phase);
     return FQB_OK;
+}
+
+int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const uint8_t *bases1, const uint8_t *quals1,
+                 const uint8_t *bases2, const uint8_t *quals2, int32_t stride) {
+    return fqb_bam_emit2(h, names, nullptr, name_stride, bases1, quals1, bases2, quals2, stride);
 }
 
 int fqb_bam_close(fqb_handle *h) {

@@ -60,6 +60,9 @@ __global__ void __launch_bounds__(256) prep_kernel(BatchView b, PrepParams p) {
         // kmer = (kmer << 2) | code over 32 bases == OR of shifted codes (N = 4 bleeds upward).
         bool filtered = false;
         if (p.kmer_thresh != 0) {
+            // The reference's filter always reads bases 0..95 of its per-slot buffer (src/BwtIndexer.cpp:443-450): for a
+            // shorter read it sees what an earlier read left there.  There is nothing to match: flag the batch.
+            if (full < 96 && lane == 0) b.n_work[kPrepShortFlag] = 1;
             uint64_t kmer[3];
 #pragma unroll
             for (int t = 0; t < 3; ++t) {

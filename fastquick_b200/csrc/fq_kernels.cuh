@@ -27,6 +27,7 @@ struct BatchView {
     uint32_t *n_work;
 };
 
+constexpr int kPrepShortFlag = 12;   // word of the batch counters (BatchView::n_work[...]) prep_kernel raises for a read shorter than the k-mer filter's 96 bases
 struct PrepParams {
     int trim_qual, kmer_thresh, is_il13;
     const uint8_t *roll;    // 6 x 2^29-byte bitmaps, or null when kmer_thresh == 0

@@ -217,14 +217,22 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
         std::thread next([&]() { if (good(N1)) load(N2); else N2.n[0] = N2.n[1] = 0; });      // IO(N+2) overlaps GPU(N) and H2D(N+1)
         if (fqb_align_pairs(h_, B.n[0], stride, B.b[0], B.q[0], B.l[0], B.b[1], B.q[1], B.l[1], nullptr, nullptr, nullptr) != FQB_OK) error("%s", fqb_last_error());
         if (fqb_stage_stats(h_) != FQB_OK) error("%s", fqb_last_error());
-        if (fqb_stats_emit(h_, B.nm[0], name_stride) != FQB_OK) error("%s", fqb_last_error());
-        if (bam_out_ && fqb_bam_emit(h_, B.nm[0], name_stride, B.b[0], B.q[0], B.b[1], B.q[1], stride) != FQB_OK) error("%s", fqb_last_error());
+        if (fqb_stats_emit2(h_, B.nm[0], B.nm[1], name_stride) != FQB_OK) error("%s", fqb_last_error());
+        if (bam_out_ && fqb_bam_emit2(h_, B.nm[0], B.nm[1], name_stride, B.b[0], B.q[0], B.b[1], B.q[1], stride) != FQB_OK) error("%s", fqb_last_error());
         FSC.NumRead += 2LL * B.n[0];
         if (FSC.NumRead % FQB_BATCH_PAIRS == 0) fprintf(stderr, "NOTICE - %lld sequences are processed.\n", FSC.NumRead);
         next.join();
         cur = (cur + 1) % kBufs;
     }
     notice("%lld sequences are loaded.", FSC.NumRead);
+    {   // src/BwtMapper.cpp:2116-2122
+        int64_t c[6];
+        if (fqb_stats_file_counters(h_, c) != FQB_OK) error("%s", fqb_last_error());
+        notice("%ld sequences are filtered.", (long)(c[0] * 2));
+        notice("%ld sequences are unmapped.", (long)(c[1] * 2));
+        notice("%ld sequences are discarded of low mapQ.", (long)c[2]);
+        notice("%ld sequences are retained for QC.", (long)c[3]);
+    }
     if (fqb_emit_sync(h_) != FQB_OK) error("%s", fqb_last_error());      // joins the writer threads before the buffers go
     for (auto &B : bufs) for (int e = 0; e < 2; ++e) { fqb_host_free(B.b[e]); fqb_host_free(B.q[e]); fqb_host_free(B.l[e]); fqb_host_free(B.nm[e]); }
     r[0].close(); r[1].close();
@@ -267,6 +275,12 @@ bool BwtMapper::SingleEndMapper(const std::string &fq1, const gap_opt_t *opt, Fi
         cur = (cur + 1) % kBufs;
     }
     notice("%lld sequences are loaded.", FSC.NumRead);
+    {   // src/BwtMapper.cpp:1395-1397 (the reference prints them after every batch; here once per file)
+        int64_t c[6];
+        if (fqb_stats_file_counters(h_, c) != FQB_OK) error("%s", fqb_last_error());
+        notice("%ld sequences are filtered.", (long)c[0]);
+        notice("%ld sequences are retained for QC.", (long)c[3]);
+    }
     if (fqb_emit_sync(h_) != FQB_OK) error("%s", fqb_last_error());
     for (auto &B : bufs) { fqb_host_free(B.b); fqb_host_free(B.q); fqb_host_free(B.l); fqb_host_free(B.nm); }
     fqb_feeder_close(fd);

@@ -131,6 +131,10 @@ int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride,
 int fqb_bam_open(fqb_handle *h, const char *path, const char *rg_line);
 int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride,
                  const uint8_t *bases1, const uint8_t *quals1, const uint8_t *bases2, const uint8_t *quals2, int32_t stride);
+/* the same with the names of the SECOND reads given separately (names2 = NULL: same as names): mates whose FASTQ names differ
+ * beyond a trailing /1 /2 keep their own names, as bwa_read_seq_with_hash_dev / SetSamRecord leave them */
+int fqb_bam_emit2(fqb_handle *h, const char *names, const char *names2, int32_t name_stride,
+                  const uint8_t *bases1, const uint8_t *quals1, const uint8_t *bases2, const uint8_t *quals2, int32_t stride);
 int fqb_bam_close(fqb_handle *h);
 
 /* The reference's IO workers read batch n+1 while batch n is being mapped
@@ -190,10 +194,16 @@ int fqb_stage_sw_refine(fqb_handle *h);
 int fqb_stats_set_target_region(fqb_handle *h, const char *bed_path);
 int fqb_stats_open(fqb_handle *h, const char *index_prefix);
 int fqb_stats_begin_file(fqb_handle *h, const char *out_prefix, const char *fastq1, const char *fastq2);
+/* counters of the current file so far, as the reference prints them after each file (src/BwtMapper.cpp:2116-2122):
+ * out6 = TotalFiltered, BwaUnmapped (pairs; printed x 2), TotalMAPQ, TotalRetained, NumBase, NumRead */
+int fqb_stats_file_counters(fqb_handle *h, int64_t *out6);
 /* every accumulator back to zero (the state right after fqb_stats_open): a new run on the same handle */
 int fqb_stats_reset(fqb_handle *h);
 int fqb_stage_stats(fqb_handle *h);
 int fqb_stats_emit(fqb_handle *h, const char *names, int32_t name_stride);
+/* names2: names of the second reads (NULL = same as names); a line for a pair whose first read is unmapped carries the second
+ * read's name (q->name, src/StatCollector.cpp:695,708) */
+int fqb_stats_emit2(fqb_handle *h, const char *names, const char *names2, int32_t name_stride);
 /* fqb_stats_emit and fqb_bam_emit copy what they need from the device, then format and write.  With FQB_ASYNC_EMIT=1 in the
  * environment that host phase runs on threads of its own while the caller submits the next batch (off by default: it only
  * pays on hosts with idle cores); the host arrays passed to the two calls (names, bases, quals) must then stay untouched
