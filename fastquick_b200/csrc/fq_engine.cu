@@ -146,6 +146,7 @@ struct fqb_handle {
     int comm_rank = 0, comm_world = 1;
     ncclComm_t nccl = nullptr;
     RingBox *ring_inbox = nullptr, *ring_next = nullptr; bool ring_next_ipc = false;
+    uint32_t ring_epoch = 0;                  // bumped by fqb_reset_stream (once per file, on every rank): a mailbox never matches a sequence number of an earlier file
     uint64_t prefetch_hits = 0;                            // batches fqb_stage_load found already uploaded by fqb_prefetch_pairs
     // paired-end resolution stage
     fqb_read_t *d_rows = nullptr, *d_rows_split = nullptr;
@@ -183,6 +184,7 @@ struct fqb_handle {
     std::vector<FileCounters> files;
     // BAM emission (row f1)
     BgzfWriter bam; bool bam_open = false; BamContext bam_ctx;
+    fqb_handle *bam_owner = nullptr;       // sharded run in one process: records go to this handle's BAM file (fqb_bam_attach)
     MultiOut *d_multi_out = nullptr; uint32_t *d_multi_list = nullptr, *d_multi_ctr = nullptr; uint32_t multi_cap = 0;
     fqb_read_t *h_bam_rows = nullptr; size_t h_bam_rows_cap = 0;
     // the reference's paired reader reuses its per-slot rseq buffers every second batch without clearing them, and SetSamRecord's
@@ -1515,7 +1517,7 @@ int fqb_collect_pairs_sharded(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows
     const bool ring = h->comm_world > 1;
     unsigned long long *state = reinterpret_cast<unsigned long long *>(h->d_ctl);
     if (ring && global_batch > 0) {
-        ring_recv_kernel<<<1, 1, 0, st>>>(state, h->ring_inbox->words, &h->ring_inbox->seq, (unsigned int)global_batch);
+        ring_recv_kernel<<<1, 1, 0, st>>>(state, h->ring_inbox->words, &h->ring_inbox->seq, h->ring_epoch << 20 | (unsigned int)(global_batch & 0xfffffu));
         // the callback works on the pinned master copy: bring the received state there
         CU_CHECK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, 56, cudaMemcpyDeviceToHost, st));
         ++h->n_launches;
@@ -1523,7 +1525,7 @@ int fqb_collect_pairs_sharded(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows
     int rc = enqueue_pair(h, st);
     if (rc) return rc;
     if (ring && !is_last) {
-        ring_send_kernel<<<1, 1, 0, st>>>(state, h->ring_next->words, &h->ring_next->seq, (unsigned int)(global_batch + 1));
+        ring_send_kernel<<<1, 1, 0, st>>>(state, h->ring_next->words, &h->ring_next->seq, h->ring_epoch << 20 | (unsigned int)((global_batch + 1) & 0xfffffu));
         ++h->n_launches;
     }
     rc = enqueue_sw_refine(h, st);
@@ -1702,6 +1704,7 @@ int fqb_reset_stream(fqb_handle *h) {
     CU_CHECK(cudaStreamSynchronize(h->stream));
     h->rng_calls = 0;
     h->last_ii.avg = h->last_ii.std = -1.0; h->last_ii.low = h->last_ii.high = h->last_ii.high_bayesian = 0;
+    ++h->ring_epoch;
     return push_stream_state(h);
 }
 
@@ -1790,7 +1793,8 @@ int fqb_bam_open(fqb_handle *h, const char *path, const char *rg_line) {
 int fqb_bam_emit2(fqb_handle *h, const char *names, const char *names2, int32_t name_stride, const uint8_t *bases1, const uint8_t *quals1,
                   const uint8_t *bases2, const uint8_t *quals2, int32_t stride) {
     if (!names2) names2 = names;
-    if (!h || !h->bam_open) { set_error("fqb_bam_emit: no BAM file open"); return FQB_ERR_STATE; }
+    fqb_handle *const o_ = (h && h->bam_owner) ? h->bam_owner : h;     // whose file, record context and read-buffer history
+    if (!h || !o_->bam_open) { set_error("fqb_bam_emit: no BAM file open"); return FQB_ERR_STATE; }
     if (!h->dp_done || (h->stats_open && !h->stats_done)) { set_error("fqb_bam_emit: the batch must be through fqb_stage_sw_refine and fqb_stage_stats"); return FQB_ERR_STATE; }
     if (!bases1 || !quals1 || stride < 1 || (!h->single_end && (!bases2 || !quals2))) { set_error("fqb_bam_emit: the reads of the batch are required"); return FQB_ERR_ARG; }
     CU_CHECK(cudaSetDevice(h->device));
@@ -1850,13 +1854,13 @@ int fqb_bam_emit2(fqb_handle *h, const char *names, const char *names2, int32_t 
         memcpy(x.cigar, mo[i].cigar, sizeof x.cigar);
     }
     const auto t_dev = std::chrono::steady_clock::now();
-    const int par = (int)(h->bam_batches & 1);
+    const int par = (int)(o_->bam_batches & 1);
     if (!h->single_end) {
-        if (h->rseq_stride != (size_t)stride) { for (auto &a : h->rseq_shadow) for (auto &b : a) b.clear(); h->rseq_stride = (size_t)stride; }
-        for (int e = 0; e < 2; ++e) if (h->rseq_shadow[par][e].size() < (size_t)(FQB_BATCH_PAIRS > np ? FQB_BATCH_PAIRS : np) * stride)
-            h->rseq_shadow[par][e].resize((size_t)(FQB_BATCH_PAIRS > np ? FQB_BATCH_PAIRS : np) * stride, 0);
+        if (o_->rseq_stride != (size_t)stride) { for (auto &a : o_->rseq_shadow) for (auto &b : a) b.clear(); o_->rseq_stride = (size_t)stride; }
+        for (int e = 0; e < 2; ++e) if (o_->rseq_shadow[par][e].size() < (size_t)(FQB_BATCH_PAIRS > np ? FQB_BATCH_PAIRS : np) * stride)
+            o_->rseq_shadow[par][e].resize((size_t)(FQB_BATCH_PAIRS > np ? FQB_BATCH_PAIRS : np) * stride, 0);
     }
-    ++h->bam_batches;
+    ++o_->bam_batches;
     const unsigned n_multi_hits = ctr[1];
     // host phase: records are formatted by several host threads over contiguous slices of the batch and handed to the BGZF
     // writer in order.  names / bases / quals must stay valid until the next fqb_stats_emit / fqb_bam_emit / fqb_stats_finish /
@@ -1890,7 +1894,7 @@ int fqb_bam_emit2(fqb_handle *h, const char *names, const char *names2, int32_t 
                 const fqb_read_t *rw[2] = {&p, &q};
                 const uint8_t *bs[2] = {bases1 + i * (size_t)stride, bases2 + i * (size_t)stride};
                 for (int e = 0; e < 2; ++e) {
-                    uint8_t *dst = h->rseq_shadow[par][e].data() + i * (size_t)stride;
+                    uint8_t *dst = o_->rseq_shadow[par][e].data() + i * (size_t)stride;
                     if (!rw[e]->filtered)
                         for (int k = 0; k < rw[e]->clip_len; ++k) { const uint8_t c = nt4[bs[e][rw[e]->clip_len - 1 - k]]; dst[k] = c < 4 ? (uint8_t)(3 - c) : (uint8_t)4; }
                     rs[e] = dst;
@@ -1906,8 +1910,8 @@ int fqb_bam_emit2(fqb_handle *h, const char *names, const char *names2, int32_t 
             if (names2 && names2 != names) { nm2.assign(names2 + i * (size_t)name_stride, strnlen(names2 + i * (size_t)name_stride, (size_t)name_stride)); name_q = nm2.c_str(); }
             int n0 = 0, n1 = 0;
             const XaHit *x0 = p.n_multi ? xa_of((uint32_t)(2 * i), n0) : nullptr, *x1 = q.n_multi ? xa_of((uint32_t)(2 * i + 1), n1) : nullptr;
-            if (h->single_end) bam_append_single(h->bam_ctx, p, name, bases1 + i * (size_t)stride, quals1 + i * (size_t)stride, x0, n0, o);
-            else bam_append_pair(h->bam_ctx, p, q, name, name_q, bases1 + i * (size_t)stride, quals1 + i * (size_t)stride, bases2 + i * (size_t)stride,
+            if (h->single_end) bam_append_single(o_->bam_ctx, p, name, bases1 + i * (size_t)stride, quals1 + i * (size_t)stride, x0, n0, o);
+            else bam_append_pair(o_->bam_ctx, p, q, name, name_q, bases1 + i * (size_t)stride, quals1 + i * (size_t)stride, bases2 + i * (size_t)stride,
                                  quals2 + i * (size_t)stride, x0, n0, x1, n1, rs[0], rs[1], o);
         }
     };
@@ -1919,7 +1923,7 @@ int fqb_bam_emit2(fqb_handle *h, const char *names, const char *names2, int32_t 
     }
     const auto t_fmt = std::chrono::steady_clock::now();
     size_t total = 0;
-    for (auto &o : parts) { total += o.size(); h->bam.write_owned(std::move(o)); }
+    for (auto &o : parts) { total += o.size(); o_->bam.write_owned(std::move(o)); }
     if (getenv("FQB_BAM_DEBUG")) {
         const auto t_end = std::chrono::steady_clock::now();
         fprintf(stderr, "bam_emit: %zu pairs, %u multi hits, %zu bytes, threads %u; device+copies %.1f ms, format %.1f ms, hand-over %.1f ms\n", np, n_multi_hits, total, nthr,
@@ -1927,7 +1931,7 @@ int fqb_bam_emit2(fqb_handle *h, const char *names, const char *names2, int32_t 
                 std::chrono::duration<double, std::milli>(t_end - t_fmt).count());
     }
     };
-    if (emit_inline()) { host_phase(); return drain_post(h, true, true); }
+    if (emit_inline() || h->bam_owner) { host_phase(); return drain_post(h, true, true); }      // records of several handles must reach a shared file in call order
     h->post_bam = std::async(std::launch::async, host_phase);
     return FQB_OK;
 }
@@ -1935,6 +1939,13 @@ int fqb_bam_emit2(fqb_handle *h, const char *names, const char *names2, int32_t 
 int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride, const uint8_t *bases1, const uint8_t *quals1,
                  const uint8_t *bases2, const uint8_t *quals2, int32_t stride) {
     return fqb_bam_emit2(h, names, nullptr, name_stride, bases1, quals1, bases2, quals2, stride);
+}
+
+// sharded run inside one process: the records this handle formats go, in call order, to `owner`'s BAM file
+int fqb_bam_attach(fqb_handle *h, fqb_handle *owner) {
+    if (!h || !owner || !owner->bam_open) { set_error("fqb_bam_attach: the owner has no BAM file open"); return FQB_ERR_STATE; }
+    h->bam_owner = owner == h ? nullptr : owner;
+    return FQB_OK;
 }
 
 int fqb_bam_close(fqb_handle *h) {

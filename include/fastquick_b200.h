@@ -135,6 +135,8 @@ int fqb_bam_emit(fqb_handle *h, const char *names, int32_t name_stride,
  * beyond a trailing /1 /2 keep their own names, as bwa_read_seq_with_hash_dev / SetSamRecord leave them */
 int fqb_bam_emit2(fqb_handle *h, const char *names, const char *names2, int32_t name_stride,
                   const uint8_t *bases1, const uint8_t *quals1, const uint8_t *bases2, const uint8_t *quals2, int32_t stride);
+/* sharded run inside one process (fqb_comm_init_local): the records handle h formats go, in call order, to owner's file */
+int fqb_bam_attach(fqb_handle *h, fqb_handle *owner);
 int fqb_bam_close(fqb_handle *h);
 
 /* The reference's IO workers read batch n+1 while batch n is being mapped
@@ -278,7 +280,8 @@ int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fq
  * rows1/rows2 of the last call are complete (pinned destination buffers for real overlap) */
 int fqb_stage_fetch_rows_async(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2);
 int fqb_rows_wait(fqb_handle *h);
-/* new FASTQ pair: restart the drand48 stream and forget last_ii (src/BwtMapper.cpp:1811-1817) */
+/* new FASTQ pair: restart the drand48 stream and forget last_ii (src/BwtMapper.cpp:1811-1817).  In a sharded run every rank
+ * calls it (or fqb_stats_begin_file, which does) once per file: it also starts a new epoch of the hand-off ring's sequence numbers */
 int fqb_reset_stream(fqb_handle *h);
 int fqb_stage_fetch_prep(fqb_handle *h, int32_t *len, int32_t *full_len, uint8_t *filtered,
                          uint8_t *codes, int32_t codes_stride);
