@@ -112,7 +112,8 @@ struct FastqReader {
 
 BwtMapper::BwtMapper(BwtIndexer &BwtIndex, const std::string &FQList, const std::string &Fastq_1, const std::string &Fastq_2,
                      const std::string &Prefix, const std::string &RefPath, const pe_opt_t *popt, gap_opt_t *opt,
-                     const std::string &targetRegionPath, int device) : prefix_(Prefix) {
+                     const std::string &targetRegionPath, const std::vector<int> &devices) : prefix_(Prefix) {
+    if (devices.empty()) error("no device given");
 
     fqb_gap_opt_t g; fqb_gap_opt_default(&g);
     g.s_mm = opt->s_mm; g.s_gapo = opt->s_gapo; g.s_gape = opt->s_gape; g.mode = opt->mode;
@@ -125,26 +126,40 @@ BwtMapper::BwtMapper(BwtIndexer &BwtIndex, const std::string &FQList, const std:
     p.max_isize = popt->max_isize; p.force_isize = popt->force_isize; p.max_occ = popt->max_occ; p.n_multi = popt->n_multi;
     p.N_multi = popt->N_multi; p.type = popt->type; p.is_sw = popt->is_sw; p.ap_prior = popt->ap_prior;
     double t_tmp = realtime();
-    if (fqb_create(RefPath.c_str(), &g, &p, device, &h_) != FQB_OK) error("%s", fqb_last_error());
+    hs_.assign(devices.size(), nullptr);
+    {   // one engine per device, created side by side (each builds its k-mer tables on its own GPU)
+        std::vector<std::thread> th;
+        std::vector<std::string> errs(devices.size());
+        for (size_t r = 0; r < devices.size(); ++r)
+            th.emplace_back([&, r]() { if (fqb_create(RefPath.c_str(), &g, &p, devices[r], &hs_[r]) != FQB_OK) errs[r] = fqb_last_error(); });
+        for (auto &t : th) t.join();
+        for (auto &e : errs) if (!e.empty()) error("%s", e.c_str());
+    }
+    h_ = hs_[0];
     notice("Index on the device (FM index, SA, pac, k-mer tables)...%f sec", realtime() - t_tmp);
     collector.Attach(h_);
-    if (targetRegionPath != "Empty" && fqb_stats_set_target_region(h_, targetRegionPath.c_str()) != FQB_OK) error("%s", fqb_last_error());
+    for (fqb_handle *h : hs_)
+        if (targetRegionPath != "Empty" && fqb_stats_set_target_region(h, targetRegionPath.c_str()) != FQB_OK) error("%s", fqb_last_error());
     t_tmp = realtime();
     collector.RestoreVcfSites(RefPath, opt);
+    for (size_t r = 1; r < hs_.size(); ++r) if (fqb_stats_open(hs_[r], RefPath.c_str()) != FQB_OK) error("%s", fqb_last_error());
     notice("Restore Variant Site Info...%f sec", realtime() - t_tmp);
+    if (hs_.size() > 1 && fqb_comm_init_local(hs_.data(), (int)hs_.size()) != FQB_OK) error("%s", fqb_last_error());
     bam_out_ = opt->out_bam != 0;
     if (bam_out_ && fqb_bam_open(h_, (Prefix + ".bam").c_str(), opt->RG.c_str()) != FQB_OK) error("%s", fqb_last_error());   // SetSamFileHeader + writeHeader
+    for (size_t r = 1; bam_out_ && r < hs_.size(); ++r) if (fqb_bam_attach(hs_[r], h_) != FQB_OK) error("%s", fqb_last_error());
     auto run_pair = [&](const std::string &f1, const std::string &f2) {
         notice("Processing Pair End mapping\t%s\t%s", f1.c_str(), f2.c_str());
         double t0 = realtime();
         FileStatCollector FSC(f1.c_str(), f2.c_str());
-        PairEndMapper(f1, f2, opt, FSC);
+        if (hs_.size() > 1) PairEndMapperSharded(f1, f2, opt, FSC); else PairEndMapper(f1, f2, opt, FSC);
         notice("Processed Pair End mapping in %f sec", realtime() - t0);
     };
     auto run_single = [&](const std::string &f1) {
         notice("Processing Single End mapping\t%s\n", f1.c_str());
         double t0 = realtime();
         FileStatCollector FSC(f1.c_str());
+        if (hs_.size() > 1) error("single-end input runs on one device (--device)");
         SingleEndMapper(f1, opt, FSC);
         notice("Processed Single End mapping in %f sec", realtime() - t0);
     };
@@ -164,11 +179,31 @@ BwtMapper::BwtMapper(BwtIndexer &BwtIndex, const std::string &FQList, const std:
     else run_single(Fastq_1);
     if (bam_out_ && fqb_bam_close(h_) != FQB_OK) error("%s", fqb_last_error());
     double t1 = realtime();
+    if (hs_.size() > 1) {
+        // end of a sharded run: NCCL reduce of the accumulators onto rank 0 + exact-size sends of the pile-up entries and
+        // duplicate keys (one host thread per device: the collectives of one communicator must be entered side by side),
+        // then the ranks' InsertSizeTable batches are spliced back into file order
+        std::vector<std::thread> th;
+        std::vector<std::string> errs(hs_.size());
+        for (size_t r = 0; r < hs_.size(); ++r)
+            th.emplace_back([&, r]() {
+                if (fqb_comm_merge_stats(hs_[r], nullptr) != FQB_OK) { errs[r] = fqb_last_error(); return; }
+                if (r > 0 && fqb_stats_close_table(hs_[r]) != FQB_OK) errs[r] = fqb_last_error();
+            });
+        for (auto &t : th) t.join();
+        for (auto &e : errs) if (!e.empty()) error("%s", e.c_str());
+        std::vector<std::string> shard(hs_.size() - 1);
+        std::vector<const char *> ptrs;
+        for (size_t r = 1; r < hs_.size(); ++r) { shard[r - 1] = Prefix + ".shard" + std::to_string(r); ptrs.push_back(shard[r - 1].c_str()); }
+        if (fqb_stats_merge_tables(h_, ptrs.data(), (int32_t)ptrs.size()) != FQB_OK) error("%s", fqb_last_error());
+        for (auto &sp : shard) { remove((sp + ".InsertSizeTable").c_str()); remove((sp + ".InsertSizeTable.idx").c_str()); }
+        remove((Prefix + ".InsertSizeTable.idx").c_str());
+    }
     collector.ProcessCore(Prefix, opt);
     notice("Calculate distributions... %f sec", realtime() - t1);
 }
 
-BwtMapper::~BwtMapper() { fqb_destroy(h_); }
+BwtMapper::~BwtMapper() { for (fqb_handle *h : hs_) fqb_destroy(h); }
 
 bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, const gap_opt_t *opt, FileStatCollector &FSC) {
     // --frac_samp draws once per record in file order (FastqReader::fill); everything else goes through the parallel feeder
@@ -240,6 +275,78 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
     return 0;
 }
 
+// PairEndMapper over several devices: global batch b of the file goes to device b % G.  One host thread deals the batches:
+// fqb_submit_pairs (upload + align stage, asynchronous) runs up to two batches ahead per device, fqb_collect_pairs_sharded
+// takes the batches in file order through pairing .. statistics with the hand-off inside the library, and the text / BAM
+// emission of batch b (the only calls that wait for the device) happens while the later batches are being aligned.
+bool BwtMapper::PairEndMapperSharded(const std::string &fq1, const std::string &fq2, const gap_opt_t *opt, FileStatCollector &FSC) {
+    if (opt->frac < 1.0) error("--frac_samp < 1 runs on one device (--device)");
+    const int G = (int)hs_.size();
+    fqb_feeder *fd[2] = {nullptr, nullptr};
+    if (fqb_feeder_open(fq1.c_str(), 0, &fd[0]) != FQB_OK || fqb_feeder_open(fq2.c_str(), 0, &fd[1]) != FQB_OK) error("Open fastq failed: %s", fqb_last_error());
+    for (int r = 0; r < G; ++r) {
+        const std::string pre = r == 0 ? prefix_ : prefix_ + ".shard" + std::to_string(r);
+        if (fqb_stats_begin_file(hs_[r], pre.c_str(), fq1.c_str(), fq2.c_str()) != FQB_OK) error("%s", fqb_last_error());
+    }
+    const int stride = opt->read_len < FQB_MAX_READ_LEN ? opt->read_len : FQB_MAX_READ_LEN, cap = FQB_BATCH_PAIRS, name_stride = 64;
+    const int K = 2 * G + 2;              // pinned batches: two in flight per device, one being emitted, one being read
+    struct Buf { uint8_t *b[2], *q[2]; int32_t *l[2]; char *nm[2]; int n[2]; };
+    std::vector<Buf> bufs((size_t)K);
+    for (auto &B : bufs)
+        for (int e = 0; e < 2; ++e) {
+            B.b[e] = (uint8_t *)fqb_host_alloc((size_t)cap * stride); B.q[e] = (uint8_t *)fqb_host_alloc((size_t)cap * stride);
+            B.l[e] = (int32_t *)fqb_host_alloc((size_t)cap * 4); B.nm[e] = (char *)fqb_host_alloc((size_t)cap * name_stride);
+            if (!B.b[e] || !B.q[e] || !B.l[e] || !B.nm[e]) error("pinned host allocation failed");
+            B.n[e] = 0;
+        }
+    int64_t b_load = 0, b_sub = 0, b_col = 0;      // batches read / submitted / collected so far
+    bool eof = false;
+    auto load = [&]() {
+        Buf &B = bufs[(size_t)(b_load % K)];
+        auto one = [&](int e) {
+            const int64_t n = fqb_feeder_fill(fd[e], cap, stride, B.b[e], B.q[e], B.l[e], B.nm[e], name_stride);
+            if (n < 0) error("%s", fqb_last_error());
+            B.n[e] = (int)n;
+        };
+        std::thread t0([&]() { one(0); });
+        one(1);
+        t0.join();
+        if (B.n[0] != B.n[1]) error("Abort, please make sure input pair of fastq files are in the same order!");
+        if (B.n[0] == 0) eof = true; else ++b_load;
+    };
+    for (;;) {
+        while (!eof && b_load < b_col + 2 * G + 1 && b_load - b_col < K - 1) load();
+        if (b_col >= b_load) break;
+        for (; b_sub < b_load && b_sub < b_col + 2 * G; ++b_sub) {
+            Buf &S = bufs[(size_t)(b_sub % K)];
+            if (fqb_submit_pairs(hs_[b_sub % G], S.n[0], stride, S.b[0], S.q[0], S.l[0], S.b[1], S.q[1], S.l[1], 0) != FQB_OK) error("%s", fqb_last_error());
+        }
+        Buf &B = bufs[(size_t)(b_col % K)];
+        fqb_handle *h = hs_[b_col % G];
+        const bool is_last = eof && b_col == b_load - 1;
+        if (fqb_collect_pairs_sharded(h, nullptr, nullptr, (uint64_t)b_col, pair_base_, is_last ? 1 : 0) != FQB_OK) error("%s", fqb_last_error());
+        if (fqb_stats_emit2(h, B.nm[0], B.nm[1], name_stride) != FQB_OK) error("%s", fqb_last_error());
+        if (bam_out_ && fqb_bam_emit2(h, B.nm[0], B.nm[1], name_stride, B.b[0], B.q[0], B.b[1], B.q[1], stride) != FQB_OK) error("%s", fqb_last_error());
+        pair_base_ += (uint64_t)B.n[0];
+        FSC.NumRead += 2LL * B.n[0];
+        if (FSC.NumRead % FQB_BATCH_PAIRS == 0) fprintf(stderr, "NOTICE - %lld sequences are processed.\n", FSC.NumRead);
+        ++b_col;
+    }
+    notice("%lld sequences are loaded.", FSC.NumRead);
+    {   // src/BwtMapper.cpp:2116-2122, summed over the devices
+        int64_t c[6] = {0, 0, 0, 0, 0, 0}, one[6];
+        for (fqb_handle *h : hs_) { if (fqb_stats_file_counters(h, one) != FQB_OK) error("%s", fqb_last_error()); for (int k = 0; k < 6; ++k) c[k] += one[k]; }
+        notice("%ld sequences are filtered.", (long)(c[0] * 2));
+        notice("%ld sequences are unmapped.", (long)(c[1] * 2));
+        notice("%ld sequences are discarded of low mapQ.", (long)c[2]);
+        notice("%ld sequences are retained for QC.", (long)c[3]);
+    }
+    for (fqb_handle *h : hs_) if (fqb_emit_sync(h) != FQB_OK) error("%s", fqb_last_error());
+    for (auto &B : bufs) for (int e = 0; e < 2; ++e) { fqb_host_free(B.b[e]); fqb_host_free(B.q[e]); fqb_host_free(B.l[e]); fqb_host_free(B.nm[e]); }
+    fqb_feeder_close(fd[0]); fqb_feeder_close(fd[1]);
+    return 0;
+}
+
 // BwtMapper::SingleEndMapper (src/BwtMapper.cpp:1266-1407): same stages on batches that carry first reads only
 bool BwtMapper::SingleEndMapper(const std::string &fq1, const gap_opt_t *opt, FileStatCollector &FSC) {
     fqb_feeder *fd = nullptr;
@@ -292,7 +399,8 @@ int runAlign(int argc, char **argv) {
     double t_real = realtime();
     gap_opt_t opt; pe_opt_t popt;
     std::string Fastq_1("Empty"), Fastq_2("Empty"), FaList("Empty"), BamIn("Empty"), Prefix("Empty"), IndexPrefix("Empty"), ReadGroup("@RG\tID:foo\tSM:bar");
-    int kmer_thresh = 3, opte = -1, device = 0;
+    int kmer_thresh = 3, opte = -1;
+    std::vector<int> devices{0};
     bool nonstop = false, il13 = false, loggap = false, sam_out = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -310,7 +418,18 @@ int runAlign(int argc, char **argv) {
         else if (a == "--is_sw") popt.is_sw = 1; else if (a == "--n_multi") popt.n_multi = atoi(val()); else if (a == "--N_multi") popt.N_multi = atoi(val());
         else if (a == "--ap_prior") popt.ap_prior = atof(val()); else if (a == "--force_isize") popt.force_isize = 1;
         else if (a == "--cal_dup") opt.cal_dup = 1; else if (a == "--frac_samp") opt.frac = atof(val());
-        else if (a == "--device") device = atoi(val());
+        else if (a == "--device") devices.assign(1, atoi(val()));
+        else if (a == "--devices") {                 // "0,1,2,3" or "0-7"
+            devices.clear();
+            std::string v = val(), tok;
+            std::stringstream ss(v);
+            while (std::getline(ss, tok, ',')) {
+                const size_t dash = tok.find('-');
+                if (dash != std::string::npos && dash > 0) { for (int d = atoi(tok.substr(0, dash).c_str()); d <= atoi(tok.substr(dash + 1).c_str()); ++d) devices.push_back(d); }
+                else if (!tok.empty()) devices.push_back(atoi(tok.c_str()));
+            }
+            if (devices.empty()) error("--devices needs a list such as 0,1 or 0-7");
+        }
         else error("unknown option %s", a.c_str());
     }
     if (opt.fnr >= 1.0) { opt.max_diff = (int)opt.fnr; opt.fnr = -1.0; }
@@ -343,7 +462,7 @@ int runAlign(int argc, char **argv) {
     notice("Load Index... %f sec", realtime() - t_tmp);
     t_tmp = realtime();
     if (TargetRegionPath != "Empty") notice("Read in target region from %s", TargetRegionPath.c_str());
-    BwtMapper Mapper(Indexer, FaList, Fastq_1, Fastq_2, Prefix, NewRef, &popt, &opt, TargetRegionPath, device);
+    BwtMapper Mapper(Indexer, FaList, Fastq_1, Fastq_2, Prefix, NewRef, &popt, &opt, TargetRegionPath, devices);
     notice("Mapping... %f sec", realtime() - t_tmp);
     notice("Real time: %.3f sec", realtime() - t_real);
     return 0;

@@ -69,12 +69,21 @@ class BwtMapper {
 public:
     BwtMapper(BwtIndexer &BwtIndex, const std::string &FQList, const std::string &Fastq_1, const std::string &Fastq_2,
               const std::string &Prefix, const std::string &RefPath, const pe_opt_t *popt, gap_opt_t *opt,
-              const std::string &targetRegionPath, int device = 0);
+              const std::string &targetRegionPath, int device = 0) : BwtMapper(BwtIndex, FQList, Fastq_1, Fastq_2, Prefix, RefPath, popt, opt, targetRegionPath, std::vector<int>{device}) {}
+    // the same stage on several GPUs of this host (`--devices 0,1,...`): batches of 262,144 pairs go round-robin to the devices
+    // (src/BwtMapper.h:36-37 is the unit), the index is replicated, and the library hands the drand48 position / last_ii from
+    // batch to batch and merges the statistics at the end (fqb_comm_*); every output file equals the single-GPU run's
+    BwtMapper(BwtIndexer &BwtIndex, const std::string &FQList, const std::string &Fastq_1, const std::string &Fastq_2,
+              const std::string &Prefix, const std::string &RefPath, const pe_opt_t *popt, gap_opt_t *opt,
+              const std::string &targetRegionPath, const std::vector<int> &devices);
     ~BwtMapper();
     bool PairEndMapper(const std::string &fq1, const std::string &fq2, const gap_opt_t *opt, FileStatCollector &FSC);
     bool SingleEndMapper(const std::string &fq1, const gap_opt_t *opt, FileStatCollector &FSC);
 private:
-    fqb_handle *h_ = nullptr;
+    bool PairEndMapperSharded(const std::string &fq1, const std::string &fq2, const gap_opt_t *opt, FileStatCollector &FSC);
+    fqb_handle *h_ = nullptr;              // rank 0: owns the BAM file and writes the statistics files
+    std::vector<fqb_handle *> hs_;         // one engine per device (hs_[0] == h_)
+    uint64_t pair_base_ = 0;               // global index of the next pair (sharded runs)
     StatCollector collector;
     std::string prefix_;
     bool bam_out_ = false;

@@ -140,3 +140,33 @@ def test_two_ranks_nccl_equals_one_rank(small_index, tmp_path):
         a = [l for l in open(one + "." + ext) if not l.startswith("##fileDate")]
         b = [l for l in open(two + "." + ext) if not l.startswith("##fileDate")]
         assert a == b, ext
+
+
+def test_cli_two_devices_equal_one_device(small_index, tmp_path):
+    """`FASTQuick_b200 align --devices 0,1` (C++ BwtMapper dealing the batches over two engines, hand-off ring and NCCL merge
+    inside the library) against `--device 0`: every statistics file and every BAM record.  70,000 pairs per batch would need
+    millions of reads; the batch size is the reference's 262,144, so the input is 600,000 pairs = three batches."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import subprocess
+    from test_gpu_stats import TEXT_FILES, _compare_files
+    from test_gpu_cli import CLI, _compare_bams
+    arrs = small_index.reads(600000, read_len=100, seed=2024, ins_rate=0.002, del_rate=0.002)
+    fq = small_index.write_fastq("clidev", arrs)
+    idx_prefix = small_index.prefix[: -len(".FASTQuick.fa")]
+    outs = {}
+    for tag, dev in (("one", ["--device", "0"]), ("two", ["--devices", "0,1"])):
+        out = os.path.join(small_index.dir, "clidev_" + tag)
+        cmd = [CLI, "align", "--fastq_1", fq[0], "--fastq_2", fq[1], "--index_prefix", idx_prefix, "--out_prefix", out, "--t", "8", "--q", "15"] + dev
+        r = subprocess.run(cmd, cwd=small_index.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        assert r.returncode == 0, r.stdout[-3000:]
+        outs[tag] = out
+    for ext in TEXT_FILES + ["FASTQ.csv"]:
+        _compare_files(outs["one"] + "." + ext, outs["two"] + "." + ext)
+    va = [l for l in open(outs["one"] + ".vcf") if not l.startswith("##fileDate")]
+    vb = [l for l in open(outs["two"] + ".vcf") if not l.startswith("##fileDate")]
+    assert va == vb
+    recs = _compare_bams(outs["one"] + ".bam", outs["two"] + ".bam")
+    assert len(recs) > 1000000
+    assert not os.path.exists(outs["two"] + ".shard1.InsertSizeTable")
