@@ -325,6 +325,21 @@ def main_gpu(args):
     merge_ms_device = merge_ms[-1]
     ms_e2e = timed(True)[0]
 
+    # the dominant kernels alone: in the pipelined loop the next batch's search shares the device with the later stages of the
+    # current one (and with the draining tail of the previous search), so a CUDA-event bracket there also counts time spent
+    # waiting for SM room.  For the roofline the same kernels are timed with nothing else on the device: the last batches of
+    # the timed region once more, stage by stage on one stream (fqb_stage_align), events around width + order + search.
+    iso_steps = min(3, args.steps)
+    c0 = (C.c_uint64 * 4)(); lib.fqb_stage_counters(h, c0)
+    rq0 = rq_time()
+    for s_ in range(n_steps - iso_steps, n_steps):
+        d = dev[s_]
+        assert lib.fqb_stage_load(h, n_pairs, READ_LEN, Engine._ptr(d[0]), Engine._ptr(d[1]), None, Engine._ptr(d[2]), Engine._ptr(d[3]), None, 1) == 0, lib.fqb_last_error()
+        assert lib.fqb_stage_align(h) == 0, lib.fqb_last_error()
+    c1 = (C.c_uint64 * 4)(); lib.fqb_stage_counters(h, c1)
+    rq1 = rq_time()
+    iso_ms, iso_n, iso_blk = rq1[0] - rq0[0], rq1[1] - rq0[1], int(c1[2] - c0[2])
+
     total_pairs = args.steps * n_pairs * world
     value = total_pairs / (ms * 1e-3)
     e2e_value = total_pairs / (ms_e2e * 1e-3)
@@ -333,8 +348,9 @@ def main_gpu(args):
     # the engine around those launches on the stream they run on, averaged over the launches of the timed region
     hbm_peak, peak_kind = peaks()
     n_blk = ctr[2]
-    rq_ms_per_launch = rq[0] / max(rq[1], 1)
-    bytes_per_launch = 64.0 * n_blk / max(rq[1], 1)
+    rq_ms_in_pipeline = rq[0] / max(rq[1], 1)
+    rq_ms_per_launch = iso_ms / max(iso_n, 1)
+    bytes_per_launch = 64.0 * iso_blk / max(iso_n, 1)
     achieved = bytes_per_launch / (rq_ms_per_launch * 1e-3) / 1e9
     touches_job = float(n_blk)
     if world > 1:
@@ -369,6 +385,10 @@ def main_gpu(args):
                      "hbm_peak": hbm_peak, "hbm_peak_kind": peak_kind + " HBM copy bandwidth (MEASURED_PEAKS.json)", "frac_of_hbm_peak": achieved / hbm_peak,
                      "kernel": "width_kernel + search_kernel (rank queries of one %d-pair batch)" % n_pairs,
                      "kernel_ms_per_launch": rq_ms_per_launch, "algorithmic_bytes_per_launch": bytes_per_launch,
+                     "kernel_timing": "CUDA events around width + order + search on their stream, the last %d batches of the timed region run once more "
+                                      "stage by stage with nothing else on the device" % iso_steps,
+                     "kernel_ms_in_pipeline": rq_ms_in_pipeline,
+                     "kernel_ms_in_pipeline_note": "the same bracket inside the timed region: includes waiting for SM room next to the other stream's kernels",
                      "share_of_step": rq_ms_per_launch / (ms / args.steps),
                      "algorithmic": "64 B x N_blk occ-block touches of bwt_cal_width+bwt_match_gap, per GPU; N_blk/pair = %.1f" % (n_blk / (args.steps * n_pairs)),
                      "note": "the FM index (10 MB) is L2-resident; the kernels are bound by dependent-latency x steps and instruction issue, not by bandwidth (DESIGN.md 3.3)",

@@ -100,7 +100,8 @@ struct fqb_handle {
     } sets[2];
     int cur = 0;                                    // set the stage-level calls work on
     int fifo[2] = {-1, -1}; int n_fifo = 0;         // sets submitted (fqb_submit_pairs) and not collected yet, oldest first
-    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr, align_stream = nullptr;
+    cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+    cudaStream_t align_stream[2] = {nullptr, nullptr};   // one per batch set: the search of batch n+1 fills the SMs the draining tail of batch n leaves idle
     cudaEvent_t ev_rows[3] = {nullptr, nullptr, nullptr};   // rows final on the main stream / split done / copies done
     double rq_ms = 0.0; uint64_t rq_launches = 0;   // accumulated device time of the rank-query launches
     BatchView bv;
@@ -113,9 +114,9 @@ struct fqb_handle {
     unsigned long long *d_counters = nullptr;
     // search infrastructure
     int n_blocks16 = 0;
-    uint4 *d_arena = nullptr;
-    uint4 *d_arena_big = nullptr;
-    uint4 *d_arena_mid = nullptr;
+    uint4 *d_arena[2] = {nullptr, nullptr};       // stack arenas of the fast pass and of the two overflow tiers, per batch set
+    uint4 *d_arena_big[2] = {nullptr, nullptr};   // (two align stages may be on the device at once)
+    uint4 *d_arena_mid[2] = {nullptr, nullptr};
     Hit *d_aln_big = nullptr;
     int32_t *d_spill_slot = nullptr;     // per read: row in d_aln_big or -1
     SearchOpt sopt;
@@ -211,7 +212,7 @@ static void use_set(fqb_handle *h, int si) {
 }
 
 static void sync_all(fqb_handle *h) {
-    if (h->align_stream) cudaStreamSynchronize(h->align_stream);
+    for (cudaStream_t a : h->align_stream) if (a) cudaStreamSynchronize(a);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->d2h_stream) cudaStreamSynchronize(h->d2h_stream);
@@ -339,7 +340,7 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     {   // the later stages run at a higher priority than the next batch's align stage: their blocks go first when SM room frees up
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        CU_CHECK_H(cudaStreamCreateWithPriority(&h->align_stream, cudaStreamNonBlocking, lo));
+        for (auto &a : h->align_stream) CU_CHECK_H(cudaStreamCreateWithPriority(&a, cudaStreamNonBlocking, lo));
     }
     for (auto &e : h->ev_rows) CU_CHECK_H(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &B : h->sets) {
@@ -475,7 +476,7 @@ void fqb_destroy(fqb_handle *h) {
     free_batch(h);
     for (int s = 0; s < 2; ++s) { cudaFree(h->d_blocks[s]); cudaFree(h->d_sa[s]); }
     cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_counters);
-    cudaFree(h->d_arena); cudaFree(h->d_arena_mid); cudaFree(h->d_arena_big);
+    for (int k = 0; k < 2; ++k) { cudaFree(h->d_arena[k]); cudaFree(h->d_arena_mid[k]); cudaFree(h->d_arena_big[k]); }
     for (auto &B : h->sets) {
         cudaFree(B.d_ctrs); cudaFree(B.d_order_bins);
         for (cudaEvent_t e : {B.ev_in, B.ev_free, B.ev_align, B.ev_done, B.ev_rq[0], B.ev_rq[1]}) if (e) cudaEventDestroy(e);
@@ -491,7 +492,7 @@ void fqb_destroy(fqb_handle *h) {
     if (h->bam_open) { std::string e; h->bam.close(e); }
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
-    if (h->align_stream) { cudaStreamSynchronize(h->align_stream); cudaStreamDestroy(h->align_stream); }
+    for (cudaStream_t a : h->align_stream) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
     for (auto &e : h->ev_rows) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -547,11 +548,11 @@ static int enqueue_align(fqb_handle *h, int si, cudaStream_t st) {
 
     h->sopt = make_search_opt(h->gopt, B.stride);
     if (h->sopt.n_buckets > 128) { set_error("more than 128 score buckets"); return FQB_ERR_LIMIT; }
-    if (!h->d_arena) {
+    if (!h->d_arena[si]) {
         h->n_blocks16 = search_grid_blocks(h->sopt.n_buckets, true, h->device);
-        CU_CHECK(cudaMalloc(&h->d_arena, (size_t)h->n_blocks16 * kSearchThreads * h->arena_fast * sizeof(uint4)));
-        CU_CHECK(cudaMalloc(&h->d_arena_mid, (size_t)kMidBlocks * kSearchThreads * h->arena_mid * sizeof(uint4)));
-        CU_CHECK(cudaMalloc(&h->d_arena_big, (size_t)kSearchThreads * ((size_t)h->gopt.max_entries + 64) * sizeof(uint4)));
+        CU_CHECK(cudaMalloc(&h->d_arena[si], (size_t)h->n_blocks16 * kSearchThreads * h->arena_fast * sizeof(uint4)));
+        CU_CHECK(cudaMalloc(&h->d_arena_mid[si], (size_t)kMidBlocks * kSearchThreads * h->arena_mid * sizeof(uint4)));
+        CU_CHECK(cudaMalloc(&h->d_arena_big[si], (size_t)kSearchThreads * ((size_t)h->gopt.max_entries + 64) * sizeof(uint4)));
     }
     SearchParams sp;
     sp.bwt[0] = h->dbwt[0]; sp.bwt[1] = h->dbwt[1];
@@ -563,7 +564,7 @@ static int enqueue_align(fqb_handle *h, int si, cudaStream_t st) {
         h->n_launches += 2;
         sp.work = B.d_work_sorted;
     }
-    sp.arena = h->d_arena; sp.arena_cap = h->arena_fast;
+    sp.arena = h->d_arena[si]; sp.arena_cap = h->arena_fast;
     sp.aln = B.d_aln; sp.aln_cap = kAlnCapFast; sp.n_aln = B.d_naln; sp.aln_row = nullptr;
     sp.overflow = B.d_overflow; sp.n_overflow = B.d_ctrs + 2;
     sp.counters = h->d_counters;
@@ -583,7 +584,7 @@ static int enqueue_align(fqb_handle *h, int si, cudaStream_t st) {
         launch_width(B.bv, B.wv, h->dbwt, h->gopt.seed_len, list, d_c, kSpillCap, nullptr, st);
         SearchParams s2 = sp;
         s2.work = list; s2.n_work = d_c; s2.cursor = d_c + 1;
-        s2.arena = tier == 1 ? h->d_arena_mid : h->d_arena_big;
+        s2.arena = tier == 1 ? h->d_arena_mid[si] : h->d_arena_big[si];
         s2.arena_cap = tier == 1 ? h->arena_mid : (uint32_t)h->gopt.max_entries + 64;
         s2.aln = B.d_aln_big; s2.aln_cap = kAlnCapSlow; s2.aln_row = B.d_spill_slot;
         s2.overflow = B.d_overflow + h->cap_reads * (tier == 1 ? 1 : 2); s2.n_overflow = d_c + 2;
@@ -2024,15 +2025,16 @@ int fqb_submit_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8
     // batch collected last: with one batch queued that is the other one; ev_done orders us behind those stages
     const int si = h->n_fifo ? 1 - h->fifo[0] : 1 - h->cur;
     fqb_handle::BatchSet &B = h->sets[si];
-    CU_CHECK(cudaStreamWaitEvent(h->align_stream, B.ev_done, 0));
+    cudaStream_t ast = h->align_stream[si];
+    CU_CHECK(cudaStreamWaitEvent(ast, B.ev_done, 0));
     // the upload runs on the copy stream (it only needs the staging arrays, free once the previous occupant's prep_kernel has
     // run), so it overlaps the search of the batch before; the align stream picks it up through ev_in
     int rc = load_set(h, si, h->copy_stream, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, on_device);
     if (rc) return rc;
     CU_CHECK(cudaEventRecord(B.ev_in, h->copy_stream));
-    CU_CHECK(cudaStreamWaitEvent(h->align_stream, B.ev_in, 0));
-    if ((rc = enqueue_align(h, si, h->align_stream))) return rc;
-    CU_CHECK(cudaEventRecord(B.ev_align, h->align_stream));
+    CU_CHECK(cudaStreamWaitEvent(ast, B.ev_in, 0));
+    if ((rc = enqueue_align(h, si, ast))) return rc;
+    CU_CHECK(cudaEventRecord(B.ev_align, ast));
     h->fifo[h->n_fifo++] = si;
     return FQB_OK;
 }
