@@ -181,6 +181,7 @@ struct fqb_handle {
     uint64_t pairs_seen = 0;                     // global pair index of the next batch
     std::vector<PileupColumn> pileup;
     std::vector<PileupTuple> tuples_host;          // pile-up entries drained from the device (own batches + imported ones)
+    unsigned long long *d_keys_imp = nullptr; size_t cap_keys_imp = 0;      // receive buffer of other ranks' duplicate keys (fqb_comm_merge_stats)
     PileupTuple *d_tuples_imp = nullptr; size_t n_tuples_imp = 0, cap_tuples_imp = 0;   // entries imported from other handles, kept on the device until the files are written
     std::vector<FileCounters> files;
     // BAM emission (row f1)
@@ -488,7 +489,7 @@ void fqb_destroy(fqb_handle *h) {
     cudaFree(h->d_dup_keys); cudaFree(h->d_tuples); cudaFree(h->d_ntuples);
     cudaFree(h->pesc.totals); cudaFree(h->d_hist); cudaFree(h->d_penalty); cudaFree(h->d_log_n); cudaFree(h->d_pair_scratch); cudaFree(h->dp_pool.ints); cudaFree(h->dp_pool.bytes); cudaFree(h->d_dpctr); cudaFree(h->d_sw_huge);
     cudaFreeHost(h->h_rows); cudaFreeHost(h->h_pstat); cudaFreeHost(h->h_bam_rows);
-    cudaFree(h->d_multi_out); cudaFree(h->d_multi_list); cudaFree(h->d_multi_ctr); cudaFree(h->d_tuples_imp);
+    cudaFree(h->d_multi_out); cudaFree(h->d_multi_list); cudaFree(h->d_multi_ctr); cudaFree(h->d_tuples_imp); cudaFree(h->d_keys_imp);
     if (h->bam_open) { std::string e; h->bam.close(e); }
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
@@ -1575,6 +1576,9 @@ int fqb_comm_merge_stats(fqb_handle *h, double *ms_out) {
     NCCL_CHECK(N->Reduce(h->d_contig_ctr, h->d_contig_ctr, nc * 4, ncclUint32, ncclSum, 0, h->nccl, st));
     NCCL_CHECK(N->Reduce(h->d_contig_ctr + nc * 4, h->d_contig_ctr + nc * 4, nc, ncclUint32, ncclMin, 0, h->nccl, st));
     NCCL_CHECK(N->GroupEnd());
+    cudaEvent_t e_red;
+    CU_CHECK(cudaEventCreate(&e_red));
+    CU_CHECK(cudaEventRecord(e_red, st));
     if (me != 0) {
         // pile-up entries usually sit on the device in one piece (d_tuples): send them from there; the distinct duplicate
         // keys are compacted out of the hash set first
@@ -1586,7 +1590,12 @@ int fqb_comm_merge_stats(fqb_handle *h, double *ms_out) {
             if (rc) return rc;
         }
         if (mine[1]) {
-            CU_CHECK(cudaMallocAsync(&keys, (mine[1] + 1) * 8, st));
+            if (mine[1] + 1 > h->cap_keys_imp) {
+                cudaFree(h->d_keys_imp);
+                h->cap_keys_imp = (mine[1] + 1) * 2 < (8u << 20) ? (8u << 20) : (mine[1] + 1) * 2;
+                CU_CHECK(cudaMalloc(&h->d_keys_imp, h->cap_keys_imp * 8));
+            }
+            keys = h->d_keys_imp;
             unsigned long long *kcnt = static_cast<unsigned long long *>(keys) + mine[1];
             CU_CHECK(cudaMemsetAsync(kcnt, 0, 8, st));
             dup_compact_kernel<<<(h->dup_cap + 255) / 256, 256, 0, st>>>(h->d_dup_keys, h->dup_cap, static_cast<unsigned long long *>(keys), kcnt);
@@ -1597,13 +1606,14 @@ int fqb_comm_merge_stats(fqb_handle *h, double *ms_out) {
         if (mine[1]) NCCL_CHECK(N->Send(keys, mine[1] * 8, ncclUint8, 0, h->nccl, st));
         NCCL_CHECK(N->GroupEnd());
         if (!direct && tup) CU_CHECK(cudaFreeAsync(tup, st));
-        if (keys) CU_CHECK(cudaFreeAsync(keys, st));
     } else {
         // exact-size receives: the pile-up entries straight behind the ones imported so far, all ranks' keys into one buffer
         uint64_t n_tup = 0, n_keys = 0;
         for (int r = 1; r < W; ++r) { n_tup += cnt[2 * r]; n_keys += cnt[2 * r + 1]; }
         if (h->n_tuples_imp + n_tup > h->cap_tuples_imp) {
-            const size_t cap = h->n_tuples_imp + n_tup;
+            // grown with headroom and kept: allocating inside the exchange costs tens of milliseconds
+            size_t cap = (h->n_tuples_imp + n_tup) * 2;
+            if (cap < (4u << 20)) cap = 4u << 20;
             PileupTuple *nb = nullptr;
             CU_CHECK(cudaMalloc(&nb, cap * sizeof(PileupTuple)));
             if (h->n_tuples_imp) CU_CHECK(cudaMemcpyAsync(nb, h->d_tuples_imp, h->n_tuples_imp * sizeof(PileupTuple), cudaMemcpyDeviceToDevice, st));
@@ -1611,8 +1621,12 @@ int fqb_comm_merge_stats(fqb_handle *h, double *ms_out) {
             cudaFree(h->d_tuples_imp);
             h->d_tuples_imp = nb; h->cap_tuples_imp = cap;
         }
-        unsigned long long *keys = nullptr;
-        if (n_keys) CU_CHECK(cudaMallocAsync(&keys, n_keys * 8, st));
+        if (n_keys > h->cap_keys_imp) {
+            cudaFree(h->d_keys_imp);
+            h->cap_keys_imp = n_keys * 2 < (32u << 20) ? (32u << 20) : n_keys * 2;
+            CU_CHECK(cudaMalloc(&h->d_keys_imp, h->cap_keys_imp * 8));
+        }
+        unsigned long long *keys = h->d_keys_imp;
         NCCL_CHECK(N->GroupStart());
         uint64_t to = h->n_tuples_imp, ko = 0;
         for (int r = 1; r < W; ++r) {
@@ -1626,13 +1640,19 @@ int fqb_comm_merge_stats(fqb_handle *h, double *ms_out) {
             // a key another rank also holds is one more duplicated pair (NumPCRDup += 2)
             dup_merge_kernel<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(h->d_dup_keys, h->dup_cap, keys, n_keys, h->d_emp + kEmpWords, h->d_emp + (4 * 256 + 4096));
             ++h->n_launches;
-            CU_CHECK(cudaFreeAsync(keys, st));
         }
     }
     CU_CHECK(cudaEventRecord(e1, st));
     CU_CHECK(cudaEventSynchronize(e1));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
+    if (getenv("FQB_COMM_DEBUG")) {
+        float m1 = 0.f;
+        cudaEventElapsedTime(&m1, e0, e_red);
+        fprintf(stderr, "rank %d merge: reduce %.2f ms, variable-size state %.2f ms (pile-up entries %llu, keys %llu)\n", me, m1, ms - m1,
+                (unsigned long long)mine[0], (unsigned long long)mine[1]);
+    }
+    cudaEventDestroy(e_red);
     if (ms_out) *ms_out = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return FQB_OK;
@@ -2067,8 +2087,11 @@ uint64_t fqb_launch_count(const fqb_handle *h) { return h ? h->n_launches : 0; }
 
 // device time (CUDA events on the handle's stream) spent in the rank-query kernels -- bwt_cal_width + queue ordering +
 // bwt_match_gap fast pass -- since creation, and the number of batches it covers; the roofline's "dominant kernel" clock
-int fqb_rank_query_time(const fqb_handle *h, double *ms, uint64_t *launches) {
+int fqb_rank_query_time(const fqb_handle *hc, double *ms, uint64_t *launches) {
+    fqb_handle *h = const_cast<fqb_handle *>(hc);
     if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
+    cudaSetDevice(h->device);
+    for (auto &B : h->sets) harvest_rq(h, B, true);       // brackets still in flight are waited for and counted
     if (ms) *ms = h->rq_ms;
     if (launches) *launches = h->rq_launches;
     return FQB_OK;
