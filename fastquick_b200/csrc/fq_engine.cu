@@ -1278,6 +1278,47 @@ static __global__ void dup_merge_kernel(unsigned long long *keys, uint32_t cap, 
     }
     atomicAdd(num_pcr_dup + 2, 1ull);      // scalars[2]: table full, reported as a limit error by fqb_stats_finish
 }
+// ---- cross-rank duplicate count of a sharded run, partitioned: key -> owner rank (hash), every owner counts the keys it
+// receives from more than one rank.  A key held by m ranks is m - 1 more duplicated pairs (NumPCRDup += 2 each).
+constexpr int kMaxRanks = 64;
+__device__ __forceinline__ uint32_t key_owner(unsigned long long key, int W) { return (uint32_t)((hash64(key) >> 32) % (unsigned long long)W); }
+static __global__ void dup_part_count_kernel(const unsigned long long *keys, uint32_t cap, int W, unsigned long long *counts) {
+    __shared__ unsigned int sh[kMaxRanks];
+    if (threadIdx.x < kMaxRanks) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[i];
+        if (k) atomicAdd(&sh[key_owner(k, W)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < W && sh[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)sh[threadIdx.x]);
+}
+// out: the keys grouped by owner (segment d starts at the sum of counts[0..d)); cursors: W zeroed words
+static __global__ void dup_part_scatter_kernel(const unsigned long long *keys, uint32_t cap, int W, const unsigned long long *counts,
+                                               unsigned long long *cursors, unsigned long long *out) {
+    __shared__ unsigned long long start[kMaxRanks];
+    if (threadIdx.x == 0) { unsigned long long acc = 0; for (int d = 0; d < W; ++d) { start[d] = acc; acc += counts[d]; } }
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[i];
+        if (!k) continue;
+        const uint32_t d = key_owner(k, W);
+        out[start[d] + atomicAdd(cursors + d, 1ull)] = k;
+    }
+}
+static __global__ void dup_cross_kernel(unsigned long long *table, unsigned long long mask, const unsigned long long *in, unsigned long long n,
+                                        unsigned long long *num_pcr_dup) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = in[i];
+    unsigned long long hh = hash64(key) & mask;
+    for (;;) {
+        const unsigned long long old = atomicCAS(table + hh, 0ull, key);
+        if (old == 0) return;
+        if (old == key) { atomicAdd(num_pcr_dup, 2ull); return; }
+        hh = (hh + 1) & mask;
+    }
+}
 extern "C" {
 // Variable-size statistics state of a sharded run: which = 0 pile-up entries (sizeof(PileupTuple) = 20 bytes each),
 // which = 1 the distinct PCR-duplicate keys (8 bytes each).  The handle that writes the files imports the other
@@ -1555,21 +1596,62 @@ int fqb_comm_merge_stats(fqb_handle *h, double *ms_out) {
     cudaStream_t st = h->stream;
     const int W = h->comm_world, me = h->comm_rank;
     const size_t nc = h->stabs.contigs.size(), ns = h->stabs.n_sites ? h->stabs.n_sites : 1;
-    // how much variable-size state every rank holds (this first collective also absorbs the skew between the ranks, so that
-    // the events below time the exchange itself)
-    uint64_t mine[2] = {0, 0};
-    for (int which = 0; which < 2; ++which) { int rc = fqb_stats_var_count(h, which, &mine[which]); if (rc) return rc; }
+    if (W > kMaxRanks) { set_error("fqb_comm_merge_stats: more than 64 ranks"); return FQB_ERR_LIMIT; }
+    // what every rank holds: its pile-up entries and, per owner rank, its distinct duplicate keys (this first collective also
+    // absorbs the skew between the ranks, so that the events below time the exchange itself)
+    uint64_t n_tup_mine = 0;
+    { int rc = fqb_stats_var_count(h, 0, &n_tup_mine); if (rc) return rc; }
+    const int RW = W + 1;                              // row: [pile-up entries, keys for owner 0 .. W-1]
     uint64_t *d_cnt = nullptr;
-    CU_CHECK(cudaMallocAsync(&d_cnt, (size_t)(W + 1) * 16, st));
-    CU_CHECK(cudaMemcpyAsync(d_cnt + 2 * W, mine, 16, cudaMemcpyHostToDevice, st));
-    NCCL_CHECK(N->AllGather(d_cnt + 2 * W, d_cnt, 2, ncclUint64, h->nccl, st));
-    std::vector<uint64_t> cnt((size_t)W * 2);
-    CU_CHECK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)W * 16, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaMallocAsync(&d_cnt, (size_t)(W + 2) * RW * 8, st));
+    uint64_t *d_row = d_cnt + (size_t)W * RW, *d_cur = d_row + RW;
+    CU_CHECK(cudaMemsetAsync(d_row, 0, (size_t)2 * RW * 8, st));
+    CU_CHECK(cudaMemcpyAsync(d_row, &n_tup_mine, 8, cudaMemcpyHostToDevice, st));
+    dup_part_count_kernel<<<1024, 256, 0, st>>>(h->d_dup_keys, h->dup_cap, W, reinterpret_cast<unsigned long long *>(d_row + 1));
+    NCCL_CHECK(N->AllGather(d_row, d_cnt, RW, ncclUint64, h->nccl, st));
+    std::vector<uint64_t> cnt((size_t)W * RW);
+    CU_CHECK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)W * RW * 8, cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaStreamSynchronize(st));
-    CU_CHECK(cudaFreeAsync(d_cnt, st));
+    auto keys_of = [&](int from, int to) { return cnt[(size_t)from * RW + 1 + to]; };
+    uint64_t n_mine = 0, n_recv = 0;
+    for (int d = 0; d < W; ++d) { n_mine += keys_of(me, d); n_recv += keys_of(d, me); }
     cudaEvent_t e0, e1;
     CU_CHECK(cudaEventCreate(&e0)); CU_CHECK(cudaEventCreate(&e1));
     CU_CHECK(cudaEventRecord(e0, st));
+    // ---- duplicate keys: all-to-all by owner, every owner counts what it sees more than once
+    {
+        unsigned long long tab = 1ull << 20;
+        while (tab < 2 * n_recv) tab <<= 1;
+        const size_t need = (size_t)n_mine + n_recv + tab;
+        if (need > h->cap_keys_imp) {
+            cudaFree(h->d_keys_imp);
+            h->cap_keys_imp = need + need / 2;
+            CU_CHECK(cudaMalloc(&h->d_keys_imp, h->cap_keys_imp * 8));
+        }
+        unsigned long long *send = h->d_keys_imp, *recv = send + n_mine, *table = recv + n_recv;
+        dup_part_scatter_kernel<<<1024, 256, 0, st>>>(h->d_dup_keys, h->dup_cap, W, reinterpret_cast<unsigned long long *>(d_row + 1),
+                                                      reinterpret_cast<unsigned long long *>(d_cur), send);
+        CU_CHECK(cudaMemsetAsync(table, 0, (size_t)tab * 8, st));
+        NCCL_CHECK(N->GroupStart());
+        uint64_t so = 0, ro = 0;
+        for (int d = 0; d < W; ++d) {
+            const uint64_t ns_ = keys_of(me, d), nr = keys_of(d, me);
+            if (d == me) { if (ns_) CU_CHECK(cudaMemcpyAsync(recv + ro, send + so, ns_ * 8, cudaMemcpyDeviceToDevice, st)); }
+            else {
+                if (ns_) NCCL_CHECK(N->Send(send + so, ns_ * 8, ncclUint8, d, h->nccl, st));
+                if (nr) NCCL_CHECK(N->Recv(recv + ro, nr * 8, ncclUint8, d, h->nccl, st));
+            }
+            so += ns_; ro += nr;
+        }
+        NCCL_CHECK(N->GroupEnd());
+        if (n_recv) dup_cross_kernel<<<(unsigned)((n_recv + 255) / 256), 256, 0, st>>>(table, tab - 1, recv, n_recv, h->d_emp + (4 * 256 + 4096));
+        h->n_launches += 3;
+    }
+    CU_CHECK(cudaFreeAsync(d_cnt, st));
+    cudaEvent_t e_keys;
+    CU_CHECK(cudaEventCreate(&e_keys));
+    CU_CHECK(cudaEventRecord(e_keys, st));
+    // ---- fixed-size accumulators (NumPCRDup now includes this rank's share of the cross-rank duplicates)
     NCCL_CHECK(N->GroupStart());
     NCCL_CHECK(N->Reduce(h->d_depth, h->d_depth, ns * 3, ncclUint32, ncclSum, 0, h->nccl, st));
     NCCL_CHECK(N->Reduce(h->d_emp, h->d_emp, (size_t)kEmpWords, ncclUint64, ncclSum, 0, h->nccl, st));
@@ -1579,37 +1661,20 @@ int fqb_comm_merge_stats(fqb_handle *h, double *ms_out) {
     cudaEvent_t e_red;
     CU_CHECK(cudaEventCreate(&e_red));
     CU_CHECK(cudaEventRecord(e_red, st));
+    // ---- pile-up entries to rank 0, exact sizes
     if (me != 0) {
-        // pile-up entries usually sit on the device in one piece (d_tuples): send them from there; the distinct duplicate
-        // keys are compacted out of the hash set first
-        const bool direct = h->tuples_host.empty() && h->n_tuples_imp == 0;
-        void *tup = direct ? (void *)h->d_tuples : nullptr, *keys = nullptr;
-        if (!direct && mine[0]) {
-            CU_CHECK(cudaMallocAsync(&tup, mine[0] * sizeof(PileupTuple), st));
-            int rc = fqb_stats_var_export(h, 0, tup, mine[0]);
+        const bool direct = h->tuples_host.empty() && h->n_tuples_imp == 0;      // usually on the device in one piece
+        void *tup = direct ? (void *)h->d_tuples : nullptr;
+        if (!direct && n_tup_mine) {
+            CU_CHECK(cudaMallocAsync(&tup, n_tup_mine * sizeof(PileupTuple), st));
+            int rc = fqb_stats_var_export(h, 0, tup, n_tup_mine);
             if (rc) return rc;
         }
-        if (mine[1]) {
-            if (mine[1] + 1 > h->cap_keys_imp) {
-                cudaFree(h->d_keys_imp);
-                h->cap_keys_imp = (mine[1] + 1) * 2 < (8u << 20) ? (8u << 20) : (mine[1] + 1) * 2;
-                CU_CHECK(cudaMalloc(&h->d_keys_imp, h->cap_keys_imp * 8));
-            }
-            keys = h->d_keys_imp;
-            unsigned long long *kcnt = static_cast<unsigned long long *>(keys) + mine[1];
-            CU_CHECK(cudaMemsetAsync(kcnt, 0, 8, st));
-            dup_compact_kernel<<<(h->dup_cap + 255) / 256, 256, 0, st>>>(h->d_dup_keys, h->dup_cap, static_cast<unsigned long long *>(keys), kcnt);
-            ++h->n_launches;
-        }
-        NCCL_CHECK(N->GroupStart());
-        if (mine[0]) NCCL_CHECK(N->Send(tup, mine[0] * sizeof(PileupTuple), ncclUint8, 0, h->nccl, st));
-        if (mine[1]) NCCL_CHECK(N->Send(keys, mine[1] * 8, ncclUint8, 0, h->nccl, st));
-        NCCL_CHECK(N->GroupEnd());
+        if (n_tup_mine) NCCL_CHECK(N->Send(tup, n_tup_mine * sizeof(PileupTuple), ncclUint8, 0, h->nccl, st));
         if (!direct && tup) CU_CHECK(cudaFreeAsync(tup, st));
     } else {
-        // exact-size receives: the pile-up entries straight behind the ones imported so far, all ranks' keys into one buffer
-        uint64_t n_tup = 0, n_keys = 0;
-        for (int r = 1; r < W; ++r) { n_tup += cnt[2 * r]; n_keys += cnt[2 * r + 1]; }
+        uint64_t n_tup = 0;
+        for (int r = 1; r < W; ++r) n_tup += cnt[(size_t)r * RW];
         if (h->n_tuples_imp + n_tup > h->cap_tuples_imp) {
             // grown with headroom and kept: allocating inside the exchange costs tens of milliseconds
             size_t cap = (h->n_tuples_imp + n_tup) * 2;
@@ -1621,38 +1686,27 @@ int fqb_comm_merge_stats(fqb_handle *h, double *ms_out) {
             cudaFree(h->d_tuples_imp);
             h->d_tuples_imp = nb; h->cap_tuples_imp = cap;
         }
-        if (n_keys > h->cap_keys_imp) {
-            cudaFree(h->d_keys_imp);
-            h->cap_keys_imp = n_keys * 2 < (32u << 20) ? (32u << 20) : n_keys * 2;
-            CU_CHECK(cudaMalloc(&h->d_keys_imp, h->cap_keys_imp * 8));
-        }
-        unsigned long long *keys = h->d_keys_imp;
         NCCL_CHECK(N->GroupStart());
-        uint64_t to = h->n_tuples_imp, ko = 0;
+        uint64_t to = h->n_tuples_imp;
         for (int r = 1; r < W; ++r) {
-            if (cnt[2 * r]) NCCL_CHECK(N->Recv(h->d_tuples_imp + to, cnt[2 * r] * sizeof(PileupTuple), ncclUint8, r, h->nccl, st));
-            if (cnt[2 * r + 1]) NCCL_CHECK(N->Recv(keys + ko, cnt[2 * r + 1] * 8, ncclUint8, r, h->nccl, st));
-            to += cnt[2 * r]; ko += cnt[2 * r + 1];
+            const uint64_t c = cnt[(size_t)r * RW];
+            if (c) NCCL_CHECK(N->Recv(h->d_tuples_imp + to, c * sizeof(PileupTuple), ncclUint8, r, h->nccl, st));
+            to += c;
         }
         NCCL_CHECK(N->GroupEnd());
         h->n_tuples_imp += n_tup;
-        if (n_keys) {
-            // a key another rank also holds is one more duplicated pair (NumPCRDup += 2)
-            dup_merge_kernel<<<(unsigned)((n_keys + 255) / 256), 256, 0, st>>>(h->d_dup_keys, h->dup_cap, keys, n_keys, h->d_emp + kEmpWords, h->d_emp + (4 * 256 + 4096));
-            ++h->n_launches;
-        }
     }
     CU_CHECK(cudaEventRecord(e1, st));
     CU_CHECK(cudaEventSynchronize(e1));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     if (getenv("FQB_COMM_DEBUG")) {
-        float m1 = 0.f;
-        cudaEventElapsedTime(&m1, e0, e_red);
-        fprintf(stderr, "rank %d merge: reduce %.2f ms, variable-size state %.2f ms (pile-up entries %llu, keys %llu)\n", me, m1, ms - m1,
-                (unsigned long long)mine[0], (unsigned long long)mine[1]);
+        float m1 = 0.f, m2 = 0.f;
+        cudaEventElapsedTime(&m1, e0, e_keys); cudaEventElapsedTime(&m2, e_keys, e_red);
+        fprintf(stderr, "rank %d merge: duplicate keys %.2f ms (%llu sent, %llu owned), reduce %.2f ms, pile-up entries %.2f ms (%llu)\n", me, m1,
+                (unsigned long long)n_mine, (unsigned long long)n_recv, m2, ms - m1 - m2, (unsigned long long)n_tup_mine);
     }
-    cudaEventDestroy(e_red);
+    cudaEventDestroy(e_red); cudaEventDestroy(e_keys);
     if (ms_out) *ms_out = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return FQB_OK;

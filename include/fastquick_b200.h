@@ -265,10 +265,12 @@ int fqb_stats_var_import(fqb_handle *h, int which, const void *src, uint64_t n);
  * IPC and written over NVLink by a one-thread kernel).  One process driving several GPUs: fqb_comm_init_local on all its
  * handles (peer access instead of IPC).  fqb_collect_pairs_sharded is fqb_collect_pairs with the hand-off in the stream:
  * global_batch = position of the batch in file order, first_pair = global index of its first pair, is_last = no batch
- * follows in this file.  fqb_comm_merge_stats (every rank, after its last batch): grouped ncclReduce of the accumulators
- * onto rank 0 (sum; first-touch contig order: min), then exact-size grouped ncclSend / ncclRecv of the pile-up entries and
- * distinct PCR-duplicate keys, merged on rank 0; *ms_out = device time of the exchange.  Rank 0 then splices the ranks'
- * InsertSizeTable batches (fqb_stats_merge_tables) and writes the files (fqb_stats_finish). */
+ * follows in this file.  fqb_comm_merge_stats (every rank, after its last batch; terminal for the run): the distinct
+ * PCR-duplicate keys go all-to-all to owner ranks chosen by hash (grouped ncclSend / ncclRecv, exact sizes) and every owner
+ * counts the keys more than one rank holds (a key in m ranks is m - 1 more duplicated pairs); one grouped ncclReduce brings
+ * the accumulators onto rank 0 (sum; first-touch contig order: min); the marker pile-up entries follow with exact-size
+ * sends.  *ms_out = device time of the exchange.  Rank 0 then splices the ranks' InsertSizeTable batches
+ * (fqb_stats_merge_tables) and writes the files (fqb_stats_finish). */
 int fqb_comm_ring_handle(fqb_handle *h, uint8_t *out64);
 int fqb_comm_unique_id(uint8_t *out128);
 int fqb_comm_init(fqb_handle *h, int rank, int world, const uint8_t *nccl_id128, const uint8_t *ring_handles /* world x 64 */);
