@@ -28,7 +28,7 @@ from fastquick_b200 import _abi  # noqa: E402
 
 BATCH = _abi.FQB_BATCH_PAIRS
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "FASTQuick_ref")
-NCU_DRAM_BYTES_PER_LAUNCH = 7.341e9   # search_kernel, one 262,144-pair launch of 2x100_10k: 3.499 GB read + 3.843 GB written (ncu capture r1f)
+NCU_DRAM_BYTES_PER_LAUNCH = 7.315e9   # search_kernel, one 262,144-pair launch of 2x100_10k: 3.476 GB read + 3.840 GB written (ncu capture r2a)
 REF_SAMPLE_PAIRS = 32768         # pairs per step of the reference arm / cpu_baseline sample unit
 STAGES = ("prep + k-mer filter + cal_width + match_gap + aln2seq/bwt_sa/mapQ + infer_isize + pairing + mate-rescue SW + gapped refinement + "
           "StatCollector pair classification and per-base pile-up/depth/quality/cycle accumulation (SURVEY 8 rows a1-a13)")
@@ -380,7 +380,7 @@ def main_gpu(args):
         "clocks": clocks,
         "roofline": {"bound": "l2", "achieved": achieved, "peak": l2_best.value, "unit": "GB/s", "frac": achieved / l2_best.value,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (n_pairs == BATCH and args.config == "2x100_10k") else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of search_kernel, ncu --set full capture r1f (profiles/r01_search_kernel_ncu.md)",
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of search_kernel, ncu --set full capture r2a (profiles/r02_search_kernel_ncu.md)",
                      "peak_kind": "BW_L2 measured on this box in this run: fqb_measure_l2, random 64-byte reads over an 8 MiB buffer, all SMs, best of 10 (median %.1f)" % l2_med.value,
                      "hbm_peak": hbm_peak, "hbm_peak_kind": peak_kind + " HBM copy bandwidth (MEASURED_PEAKS.json)", "frac_of_hbm_peak": achieved / hbm_peak,
                      "kernel": "width_kernel + search_kernel (rank queries of one %d-pair batch)" % n_pairs,
