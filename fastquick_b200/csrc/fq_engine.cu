@@ -633,8 +633,22 @@ static void CUDART_CB se_host_callback(void *user) {
     h->rng_calls = h->h_ctl->rng_calls;
 }
 
-// a6-a9 on the aligned batch (the current set): bwa_cal_pac_pos_pe (src/BwtMapper.cpp:721-907)
-static int enqueue_pair(fqb_handle *h, cudaStream_t st) {
+// the 56 bytes at the head of BatchCtl (rng_calls, pad, last_ii) into the next rank's mailbox, then its sequence number
+static __global__ void ring_send_kernel(const unsigned long long *state, volatile unsigned long long *peer_words, volatile unsigned int *peer_seq, unsigned int seq) {
+    for (int i = 0; i < 7; ++i) peer_words[i] = state[i];
+    __threadfence_system();
+    *peer_seq = seq;
+}
+static __global__ void ring_recv_kernel(unsigned long long *state, const volatile unsigned long long *words, const volatile unsigned int *my_seq, unsigned int seq) {
+    while (*my_seq != seq) __nanosleep(100);
+    __threadfence_system();
+    for (int i = 0; i < 7; ++i) state[i] = words[i];
+}
+// a6-a9 on the aligned batch (the current set): bwa_cal_pac_pos_pe (src/BwtMapper.cpp:721-907).
+// Sharded runs: recv_seq != 0 -> the stream position and last_ii come from this rank's mailbox once it shows recv_seq (the
+// wait sits behind the kernels that do not need them); send_seq != 0 -> they go to the next rank's mailbox as soon as the
+// host callback has produced them, before the pairing kernels.
+static int enqueue_pair(fqb_handle *h, cudaStream_t st, unsigned int recv_seq = 0, unsigned int send_seq = 0) {
     PeView v;
     v.n_reads = h->n_reads;
     v.aln = h->d_aln; v.aln_cap = kAlnCapFast; v.aln_big = h->d_aln_big; v.aln_big_cap = kAlnCapSlow;
@@ -644,25 +658,44 @@ static int enqueue_pair(fqb_handle *h, cudaStream_t st) {
     sp.bwt[0] = h->dbwt[0]; sp.bwt[1] = h->dbwt[1]; sp.maxdiff = h->d_maxdiff; sp.g_log_n = h->d_log_n;
     const RngState rng{h->rng_x0, 0};                  // the stream position is read on the device (d_ctl->rng_calls)
     CU_CHECK(cudaMemsetAsync(h->d_status, 0, 16 * 4, st));
+    unsigned long long *state = reinterpret_cast<unsigned long long *>(h->d_ctl);
+    auto ring_in = [&]() -> int {
+        if (!recv_seq) return FQB_OK;
+        ring_recv_kernel<<<1, 1, 0, st>>>(state, h->ring_inbox->words, &h->ring_inbox->seq, recv_seq);
+        CU_CHECK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, 56, cudaMemcpyDeviceToHost, st));      // the callback works on the pinned master copy
+        ++h->n_launches;
+        return FQB_OK;
+    };
+    auto ring_out = [&]() {
+        if (!send_seq) return;
+        ring_send_kernel<<<1, 1, 0, st>>>(state, h->ring_next->words, &h->ring_next->seq, send_seq);
+        ++h->n_launches;
+    };
     if (h->single_end) {
         // SingleEndMapper (src/BwtMapper.cpp:1335-1348): bwa_aln2seq_core(..., 1, N_OCC) + bwa_cal_pac_pos; no insert size, no pairing
-        launch_se(v, sp, rng, &h->d_ctl->rng_calls, h->pesc, st);
+        launch_se_prepare(v, h->pesc, st);
+        if (int rc = ring_in()) return rc;
+        launch_se_finish(v, sp, rng, &h->d_ctl->rng_calls, h->pesc, st);
         h->n_launches += 8;
         CU_CHECK(cudaMemcpyAsync(h->h_xfer->totals, h->pesc.totals, 16, cudaMemcpyDeviceToHost, st));
         CU_CHECK(cudaLaunchHostFunc(st, se_host_callback, h));
         CU_CHECK(cudaMemcpyAsync(&h->d_ctl->rng_calls, &h->h_ctl->rng_calls, 8, cudaMemcpyHostToDevice, st));
+        ring_out();
         CU_CHECK(cudaGetLastError());
         return FQB_OK;
     }
     if (h->popt.type != 1) { set_error("only BWA_PET_STD pairing is supported (SOLiD is dead code in the reference)"); return FQB_ERR_ARG; }
     CU_CHECK(cudaMemsetAsync(h->d_hist, 0, (kIsizeBins + 1) * 4, st));
-    launch_se(v, sp, rng, &h->d_ctl->rng_calls, h->pesc, st);
+    launch_se_prepare(v, h->pesc, st);
+    if (int rc = ring_in()) return rc;
+    launch_se_finish(v, sp, rng, &h->d_ctl->rng_calls, h->pesc, st);
     launch_isize_hist(v, h->d_hist, h->d_hist + kIsizeBins, st);
     h->n_launches += 9;
     CU_CHECK(cudaMemcpyAsync(h->h_xfer->hist, h->d_hist, (kIsizeBins + 1) * 4, cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaMemcpyAsync(h->h_xfer->totals, h->pesc.totals, 16, cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaLaunchHostFunc(st, pair_host_callback, h));
     CU_CHECK(cudaMemcpyAsync(h->d_ctl, h->h_ctl, sizeof(fqb_handle::BatchCtl), cudaMemcpyHostToDevice, st));
+    ring_out();
     CU_CHECK(cudaMemcpyAsync(h->d_penalty, h->h_penalty, (size_t)kPenaltyCap * 4, cudaMemcpyHostToDevice, st));
     if (!h->d_pair_scratch) CU_CHECK(cudaMalloc(&h->d_pair_scratch, (size_t)kPairBigMax * 8192 * 8));
     launch_pair(v, h->dbwt, &h->d_ctl->pp, h->d_big_list, h->d_status + kStBig, h->d_sw_list, h->d_status + kStSw, st);
@@ -1449,17 +1482,6 @@ NcclApi *nccl_api() {
         if (r_ != ncclSuccess) { set_error(std::string(#expr) + ": " + (N->GetErrorString ? N->GetErrorString(r_) : "NCCL error")); return FQB_ERR_CUDA; } \
     } while (0)
 
-// the 56 bytes at the head of BatchCtl (rng_calls, pad, last_ii) into the next rank's mailbox, then its sequence number
-static __global__ void ring_send_kernel(const unsigned long long *state, volatile unsigned long long *peer_words, volatile unsigned int *peer_seq, unsigned int seq) {
-    for (int i = 0; i < 7; ++i) peer_words[i] = state[i];
-    __threadfence_system();
-    *peer_seq = seq;
-}
-static __global__ void ring_recv_kernel(unsigned long long *state, const volatile unsigned long long *words, const volatile unsigned int *my_seq, unsigned int seq) {
-    while (*my_seq != seq) __nanosleep(100);
-    __threadfence_system();
-    for (int i = 0; i < 7; ++i) state[i] = words[i];
-}
 static_assert(offsetof(fqb_handle::BatchCtl, cur_ii) == 56, "the hand-off state is the first 56 bytes of BatchCtl");
 static void comm_release(fqb_handle *h) {
     if (h->nccl) { if (NcclApi *N = nccl_api()) if (N->CommDestroy) N->CommDestroy(h->nccl); h->nccl = nullptr; }
@@ -1558,19 +1580,10 @@ int fqb_collect_pairs_sharded(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows
     cudaStream_t st = h->stream;
     CU_CHECK(cudaStreamWaitEvent(st, h->sets[si].ev_align, 0));
     const bool ring = h->comm_world > 1;
-    unsigned long long *state = reinterpret_cast<unsigned long long *>(h->d_ctl);
-    if (ring && global_batch > 0) {
-        ring_recv_kernel<<<1, 1, 0, st>>>(state, h->ring_inbox->words, &h->ring_inbox->seq, h->ring_epoch << 20 | (unsigned int)(global_batch & 0xfffffu));
-        // the callback works on the pinned master copy: bring the received state there
-        CU_CHECK(cudaMemcpyAsync(h->h_ctl, h->d_ctl, 56, cudaMemcpyDeviceToHost, st));
-        ++h->n_launches;
-    }
-    int rc = enqueue_pair(h, st);
+    const unsigned int recv_seq = ring && global_batch > 0 ? (h->ring_epoch << 20 | (unsigned int)(global_batch & 0xfffffu)) : 0u;
+    const unsigned int send_seq = ring && !is_last ? (h->ring_epoch << 20 | (unsigned int)((global_batch + 1) & 0xfffffu)) : 0u;
+    int rc = enqueue_pair(h, st, recv_seq, send_seq);
     if (rc) return rc;
-    if (ring && !is_last) {
-        ring_send_kernel<<<1, 1, 0, st>>>(state, h->ring_next->words, &h->ring_next->seq, h->ring_epoch << 20 | (unsigned int)((global_batch + 1) & 0xfffffu));
-        ++h->n_launches;
-    }
     rc = enqueue_sw_refine(h, st);
     if (rc) return rc;
     h->batch_ready = h->align_done = h->pair_done = h->dp_done = true;
@@ -1624,8 +1637,9 @@ int fqb_comm_merge_stats(fqb_handle *h, double *ms_out) {
         while (tab < 2 * n_recv) tab <<= 1;
         const size_t need = (size_t)n_mine + n_recv + tab;
         if (need > h->cap_keys_imp) {
+            // kept for the life of the handle and sized generously (512 MB at least): allocating inside the exchange costs 10+ ms
             cudaFree(h->d_keys_imp);
-            h->cap_keys_imp = need + need / 2;
+            h->cap_keys_imp = need + need / 2 < (64u << 20) ? (64u << 20) : need + need / 2;
             CU_CHECK(cudaMalloc(&h->d_keys_imp, h->cap_keys_imp * 8));
         }
         unsigned long long *send = h->d_keys_imp, *recv = send + n_mine, *table = recv + n_recv;

@@ -184,11 +184,16 @@ __global__ void pair_big_kernel(PeView v, DevBwt b0, DevBwt b1, const PairParams
     v.rows[2 * p] = r0; v.rows[2 * p + 1] = r1;
 }
 
-void launch_se(const PeView &v, const SeParams &sp, const RngState &rng, const uint64_t *calls, PeScratch &sc, cudaStream_t s) {
+// the part of the SE pass that does not depend on the stream position: provisional draw counts, their prefix sums, the list
+// of reads with several best intervals (in a sharded run it overlaps the wait for the previous batch's owner)
+void launch_se_prepare(const PeView &v, PeScratch &sc, cudaStream_t s) {
     const int n = v.n_reads, tb = 256, nb = (n + tb - 1) / tb;
     se_count_kernel<<<nb, tb, 0, s>>>(v, sc.packed);
     exclusive_scan_u64(sc.packed, sc.scanned, sc.scan_tmp, n, s);
     se_multi_list_kernel<<<nb, tb, 0, s>>>(v, sc.packed, sc.scanned, sc.multi_list);
+}
+void launch_se_finish(const PeView &v, const SeParams &sp, const RngState &rng, const uint64_t *calls, PeScratch &sc, cudaStream_t s) {
+    const int n = v.n_reads;
     se_multi_seq_kernel<<<1, 32, 0, s>>>(v, sc.packed, sc.scanned, sc.multi_list, sc.cum_extra, rng, calls, sc.totals);
     se_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(v, sp, sc.packed, sc.scanned, sc.multi_list, sc.cum_extra, sc.totals, rng, calls, sc.err_flag);
 }

@@ -28,7 +28,8 @@ struct PeScratch {
 };
 
 // calls: optional DEVICE word added to rng.calls (the stream position handed from batch to batch stays on the device)
-void launch_se(const PeView &v, const SeParams &sp, const RngState &rng, const uint64_t *calls, PeScratch &sc, cudaStream_t s);
+void launch_se_prepare(const PeView &v, PeScratch &sc, cudaStream_t s);
+void launch_se_finish(const PeView &v, const SeParams &sp, const RngState &rng, const uint64_t *calls, PeScratch &sc, cudaStream_t s);
 void launch_isize_hist(const PeView &v, uint32_t *hist, uint32_t *max_len, cudaStream_t s);
 // pp: DEVICE pointer (written by the pair stage's host callback once infer_isize has run).  n_big: [0] pairs deferred to
 // pair_big_kernel, [1] != 0 when more than kPairBigMax pairs asked for it (a limit error).  launch_pair_big always runs its
