@@ -330,6 +330,9 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     fill_maxdiff_table(h->gopt, h->h_maxdiff);
     for (int l = 0; l <= FQB_MAX_READ_LEN; ++l)
         if (h->h_maxdiff[l] > 30) { set_error("max_diff > 30 is not supported"); delete h; return FQB_ERR_LIMIT; }
+    if (h->popt.n_multi < 0 || h->popt.n_multi + 1 > FQB_MAX_MULTI || h->popt.N_multi < 0 || h->popt.N_multi + 1 > FQB_MAX_MULTI) {
+        set_error("--n_multi / --N_multi above 10 are not supported (a result row reports at most 11 hits)"); delete h; return FQB_ERR_LIMIT;
+    }
     if (h->gopt.max_gapo > 14 || h->gopt.max_gape > 30 || h->gopt.seed_len > 255 || h->gopt.s_mm < 1 || h->gopt.s_gapo < 1 || h->gopt.s_gape < 1) {
         set_error("gap options outside the supported range"); delete h; return FQB_ERR_LIMIT;
     }

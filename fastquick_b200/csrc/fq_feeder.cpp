@@ -490,6 +490,11 @@ private:
                 const unsigned char *h = buf.data() + at;
                 if (h[0] != 0x1f || h[1] != 0x8b || !(h[3] & 4) || h[12] != 'B' || h[13] != 'C') { fail_.raise("not a BGZF member"); break; }
                 const size_t bsize = (size_t)(h[16] | (h[17] << 8)) + 1;
+                {   // untrusted input: the member must at least hold its header, its extra field and CRC32 + ISIZE, and a BGZF
+                    // member never inflates to more than 64 KiB (the inflate job sizes its output from the ISIZE fields)
+                    const size_t xlen = (size_t)h[10] | ((size_t)h[11] << 8);
+                    if (bsize < 12 + xlen + 8 || xlen < 6) { fail_.raise("corrupt BGZF member (BSIZE smaller than its own header)"); break; }
+                }
                 if (have - at < bsize) {
                     if (eof) { fail_.raise("truncated BGZF member"); break; }
                     memmove(buf.data(), buf.data() + at, have - at); have -= at; at = 0;
@@ -507,9 +512,19 @@ private:
             Failure *fail = &fail_;
             pool_->submit([g, fail]() {
                 size_t total = 0;
+                bool sane = true;
                 for (auto &mb : g->member) {
                     const unsigned char *t = g->comp.data() + mb.first + mb.second - 4;
-                    total += (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);     // ISIZE
+                    const size_t isize = (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);     // ISIZE
+                    if (isize > 65536) sane = false;
+                    total += isize;
+                }
+                if (!sane) {
+                    fail->raise("corrupt BGZF member (ISIZE above 64 KiB)");
+                    g->out = new_block(Inflater::kOutSlack); g->out->n = 0;
+                    { std::lock_guard<std::mutex> l(g->m); g->ready = true; }
+                    g->cv.notify_all();
+                    return;
                 }
                 g->out = new_block(total + Inflater::kOutSlack);
                 std::unique_ptr<Inflater> inf(new Inflater());

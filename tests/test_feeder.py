@@ -209,6 +209,17 @@ def test_feeder_bgzf_member_checks(tmp_path):
         open(p, "wb").write(bytes(b))
         with pytest.raises(RuntimeError, match="BGZF"):
             _read_all(p, 100, 512)
+    # header fields of an untrusted file: a BSIZE smaller than the member's own header + trailer, and an ISIZE beyond the
+    # 64 KiB a BGZF member can hold (it sizes the output buffer), must be refused before anything is read through them
+    for tag, patch in (("bsize_tiny", lambda b: b.__setitem__(slice(16, 18), bytes([3, 0]))),
+                       ("bsize_no_trailer", lambda b: b.__setitem__(slice(16, 18), bytes([20, 0]))),
+                       ("isize_huge", lambda b: b.__setitem__(slice(size0 - 4, size0), bytes([0xff, 0xff, 0xff, 0x7f])))):
+        b = bytearray(blob)
+        patch(b)
+        p = str(tmp_path / (tag + ".fq.gz"))
+        open(p, "wb").write(bytes(b))
+        with pytest.raises(RuntimeError, match="BGZF"):
+            _read_all(p, 100, 512)
 
 
 def test_inflate_property():
