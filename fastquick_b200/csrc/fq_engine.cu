@@ -169,6 +169,7 @@ struct fqb_handle {
     bool stats_open = false, stats_done = false;
     std::string target_bed;                      // --targetRegion, set before fqb_stats_open
     long long files_closed[6] = {0, 0, 0, 0, 0, 0}; // device totals already attributed to finished files
+    bool files_merged = false;                   // the per-file counters hold the sums over all ranks (fqb_comm_merge_stats)
     StatsTables stabs;
     ContigDev *d_ctg = nullptr;
     uint32_t *d_site = nullptr; int32_t *d_marker = nullptr;
@@ -970,7 +971,7 @@ int fqb_stats_reset(fqb_handle *h) {
     h->tuples_host.clear(); h->n_tuples_imp = 0; h->tuples_bound = 0;
     h->pairs_seen = 0;
     for (auto &x : h->files_closed) x = 0;
-    h->files.clear();
+    h->files.clear(); h->files_merged = false;
     return FQB_OK;
 }
 
@@ -991,7 +992,7 @@ static bool emit_inline() { static const bool v = getenv("FQB_ASYNC_EMIT") == nu
 
 static int close_current_file(fqb_handle *h) {
     if (int rc = drain_post(h, true, true)) return rc;
-    if (h->files.empty()) return FQB_OK;
+    if (h->files.empty() || h->files_merged) return FQB_OK;       // after fqb_comm_merge_stats the per-file counters are final
     CU_CHECK(cudaStreamSynchronize(h->stream));
     unsigned long long sc[kEmpScalars];
     CU_CHECK(cudaMemcpy(sc, h->d_emp + 4 * 256 + 4096, sizeof sc, cudaMemcpyDeviceToHost));
@@ -1613,6 +1614,33 @@ int fqb_comm_merge_stats(fqb_handle *h, double *ms_out) {
     const int W = h->comm_world, me = h->comm_rank;
     const size_t nc = h->stabs.contigs.size(), ns = h->stabs.n_sites ? h->stabs.n_sites : 1;
     if (W > kMaxRanks) { set_error("fqb_comm_merge_stats: more than 64 ranks"); return FQB_ERR_LIMIT; }
+    {   // per-file counters (FileStatCollector: one per FASTQ pair, src/BwtMapper.cpp:249-254): every rank closes its share of
+        // the last file, then the F x 6 table is summed onto rank 0
+        if (int rc = close_current_file(h)) return rc;
+        const size_t F = h->files.size();
+        if (F) {
+            std::vector<long long> fc(F * 6);
+            for (size_t f = 0; f < F; ++f) {
+                const FileCounters &x = h->files[f];
+                const long long v[6] = {x.TotalFiltered, x.BwaUnmapped, x.TotalMAPQ, x.TotalRetained, x.NumBase, x.NumRead};
+                for (int k = 0; k < 6; ++k) fc[f * 6 + k] = v[k];
+            }
+            long long *d_fc = nullptr;
+            CU_CHECK(cudaMallocAsync(&d_fc, F * 6 * 8, st));
+            CU_CHECK(cudaMemcpyAsync(d_fc, fc.data(), F * 6 * 8, cudaMemcpyHostToDevice, st));
+            NCCL_CHECK(N->Reduce(d_fc, d_fc, F * 6, ncclInt64, ncclSum, 0, h->nccl, st));
+            CU_CHECK(cudaMemcpyAsync(fc.data(), d_fc, F * 6 * 8, cudaMemcpyDeviceToHost, st));
+            CU_CHECK(cudaStreamSynchronize(st));
+            CU_CHECK(cudaFreeAsync(d_fc, st));
+            if (me == 0)
+                for (size_t f = 0; f < F; ++f) {
+                    FileCounters &x = h->files[f];
+                    x.TotalFiltered = fc[f * 6]; x.BwaUnmapped = fc[f * 6 + 1]; x.TotalMAPQ = fc[f * 6 + 2]; x.TotalRetained = fc[f * 6 + 3];
+                    x.NumBase = fc[f * 6 + 4]; x.NumRead = fc[f * 6 + 5];
+                }
+        }
+        h->files_merged = true;
+    }
     // what every rank holds: its pile-up entries and, per owner rank, its distinct duplicate keys (this first collective also
     // absorbs the skew between the ranks, so that the events below time the exchange itself)
     uint64_t n_tup_mine = 0;

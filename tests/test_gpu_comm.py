@@ -144,21 +144,27 @@ def test_two_ranks_nccl_equals_one_rank(small_index, tmp_path):
 
 def test_cli_two_devices_equal_one_device(small_index, tmp_path):
     """`FASTQuick_b200 align --devices 0,1` (C++ BwtMapper dealing the batches over two engines, hand-off ring and NCCL merge
-    inside the library) against `--device 0`: every statistics file and every BAM record.  70,000 pairs per batch would need
-    millions of reads; the batch size is the reference's 262,144, so the input is 600,000 pairs = three batches."""
+    inside the library) against `--device 0`: every statistics file and every BAM record.  The batch size is the reference's
+    262,144 pairs, so the input is two FASTQ pairs of 300,000 pairs each through --fq_list: two batches per file, and the
+    ring starts a new epoch (srand48, last_ii) with the second file."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
     import subprocess
     from test_gpu_stats import TEXT_FILES, _compare_files
     from test_gpu_cli import CLI, _compare_bams
-    arrs = small_index.reads(600000, read_len=100, seed=2024, ins_rate=0.002, del_rate=0.002)
-    fq = small_index.write_fastq("clidev", arrs)
+    lines = []
+    for k in (0, 1):
+        arrs = small_index.reads(300000, read_len=100, seed=2024 + k, ins_rate=0.002, del_rate=0.002, first_pair=k * 300000)
+        fq = small_index.write_fastq("clidev%d" % k, arrs, first_pair=k * 300000)
+        lines.append(fq[0] + "\t" + fq[1])
+    fq_list = os.path.join(small_index.dir, "clidev.list")
+    open(fq_list, "w").write("\n".join(lines) + "\n")
     idx_prefix = small_index.prefix[: -len(".FASTQuick.fa")]
     outs = {}
     for tag, dev in (("one", ["--device", "0"]), ("two", ["--devices", "0,1"])):
         out = os.path.join(small_index.dir, "clidev_" + tag)
-        cmd = [CLI, "align", "--fastq_1", fq[0], "--fastq_2", fq[1], "--index_prefix", idx_prefix, "--out_prefix", out, "--t", "8", "--q", "15"] + dev
+        cmd = [CLI, "align", "--fq_list", fq_list, "--index_prefix", idx_prefix, "--out_prefix", out, "--t", "8", "--q", "15"] + dev
         r = subprocess.run(cmd, cwd=small_index.dir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         assert r.returncode == 0, r.stdout[-3000:]
         outs[tag] = out
