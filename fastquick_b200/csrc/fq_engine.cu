@@ -661,7 +661,7 @@ static int enqueue_pair(fqb_handle *h, cudaStream_t st, unsigned int recv_seq = 
     SeParams sp;
     sp.bwt[0] = h->dbwt[0]; sp.bwt[1] = h->dbwt[1]; sp.maxdiff = h->d_maxdiff; sp.g_log_n = h->d_log_n;
     const RngState rng{h->rng_x0, 0};                  // the stream position is read on the device (d_ctl->rng_calls)
-    CU_CHECK(cudaMemsetAsync(h->d_status, 0, 16 * 4, st));
+    CU_CHECK(cudaMemsetAsync(h->d_status, 0, 15 * 4, st));      // word 15 is the sticky error word (status_fold_kernel)
     unsigned long long *state = reinterpret_cast<unsigned long long *>(h->d_ctl);
     auto ring_in = [&]() -> int {
         if (!recv_seq) return FQB_OK;
@@ -736,8 +736,21 @@ static int enqueue_sw_refine(fqb_handle *h, cudaStream_t st) {
     return FQB_OK;
 }
 
-// end of a batch's chain: bring the status words (and the set's overflow counters) to pinned memory
+// end of a batch's chain: fold what the device flagged for this batch into a sticky word (several chains may complete before
+// the host looks) and bring it, the status words and the set's overflow counters to pinned memory
+enum : uint32_t { kErrShortRead = 1, kErrSpillCap = 2, kErrDeepOverflow = 4, kErrDrandZero = 8, kErrBigPairs = 16, kErrDp = 32 };
+static __global__ void status_fold_kernel(const uint32_t *S, const uint32_t *K, uint32_t *sticky) {
+    uint32_t e = 0;
+    if (K[kPrepShortFlag]) e |= kErrShortRead;
+    if (K[kCtrSpillFlag]) e |= kErrSpillCap;
+    if (K[4 * 2 + 2]) e |= kErrDeepOverflow;
+    if (S[kStSeErr]) e |= kErrDrandZero;
+    if (S[kStBig + 1]) e |= kErrBigPairs;
+    if (S[kStDpErr]) e |= kErrDp;
+    if (e) atomicOr(sticky, e);
+}
 static int enqueue_status(fqb_handle *h, cudaStream_t st) {
+    status_fold_kernel<<<1, 1, 0, st>>>(h->d_status, h->d_ctrs, h->d_status + 15);
     CU_CHECK(cudaMemcpyAsync(h->h_status, h->d_status, 16 * 4, cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaMemcpyAsync(h->h_ctrs, h->d_ctrs, 16 * 4, cudaMemcpyDeviceToHost, st));
     h->status_pending = true;
@@ -747,15 +760,18 @@ static int enqueue_status(fqb_handle *h, cudaStream_t st) {
 static int check_status(fqb_handle *h) {
     if (!h->status_pending) return FQB_OK;
     h->status_pending = false;
-    const uint32_t *S = h->h_status, *K = h->h_ctrs;
     if (!h->cb_error.empty()) { set_error(h->cb_error); h->cb_error.clear(); return FQB_ERR_LIMIT; }
-    if (K[kPrepShortFlag]) { set_error("a read is shorter than 96 bases: the reference's k-mer filter reads bases 0..95 whatever the read length and sees stale buffer bytes there (src/BwtIndexer.cpp:443-450); unsupported -- disable the filter (kmer_thresh = 0) for such input"); return FQB_ERR_LIMIT; }
-    if (K[kCtrSpillFlag]) { set_error("more than 16,384 reads of one batch outgrew the fast search pass"); return FQB_ERR_LIMIT; }
-    if (K[4 * 2 + 2]) { set_error("a read overflowed even the max_entries-deep arena or 1024 hits"); return FQB_ERR_LIMIT; }
-    if (S[kStSeErr]) { set_error("drand48 returned exactly 0.0 for a read with one best interval (p = 2^-48 per read): unsupported"); return FQB_ERR_LIMIT; }
-    if (S[kStBig + 1]) { set_error("too many repeat-heavy pairs in one batch"); return FQB_ERR_LIMIT; }
-    if (S[kStDpErr]) { set_error("an alignment needed more DP scratch or CIGAR operations than provisioned"); return FQB_ERR_LIMIT; }
-    return FQB_OK;
+    const uint32_t e = h->h_status[15];
+    if (!e) return FQB_OK;
+    cudaMemsetAsync(h->d_status + 15, 0, 4, h->stream);          // reported: start afresh
+    h->h_status[15] = 0;
+    if (e & kErrShortRead) set_error("a read is shorter than 96 bases: the reference's k-mer filter reads bases 0..95 whatever the read length and sees stale buffer bytes there (src/BwtIndexer.cpp:443-450); unsupported -- disable the filter (kmer_thresh = 0) for such input");
+    else if (e & kErrSpillCap) set_error("more than 16,384 reads of one batch outgrew the fast search pass");
+    else if (e & kErrDeepOverflow) set_error("a read overflowed even the max_entries-deep arena or 1024 hits");
+    else if (e & kErrDrandZero) set_error("drand48 returned exactly 0.0 for a read with one best interval (p = 2^-48 per read): unsupported");
+    else if (e & kErrBigPairs) set_error("too many repeat-heavy pairs in one batch");
+    else set_error("an alignment needed more DP scratch or CIGAR operations than provisioned");
+    return FQB_ERR_LIMIT;
 }
 static int sync_and_check(fqb_handle *h) {
     CU_CHECK(cudaStreamSynchronize(h->stream));
