@@ -57,12 +57,14 @@ constexpr int kWarpsPerBlock = 8;
 constexpr uint32_t kHugeMaxPairs = 64, kHugeMaxJobs = 128, kHugeMaxSlices = 1u << 16;   // very wide windows per batch (rare)
 constexpr size_t kWarpSlab = 256u * 1024u;       // per-warp global slab: path ops + trace-back matrix
 
-// shared memory of a block: kWarpsPerBlock x smem_ints words of DP rows, then kWarpsPerBlock x ref_cap bytes of reference codes
-__device__ __forceinline__ WarpDp warp_scratch(const DpPool &pool, int32_t *smem, int smem_ints, int ref_cap) {
+// shared memory of a block: kWarpsPerBlock x smem_ints words of DP rows / trace-back, then kWarpsPerBlock x ref_cap bytes of
+// reference codes, then kWarpsPerBlock x ops_cap bytes of path ops
+__device__ __forceinline__ WarpDp warp_scratch(const DpPool &pool, int32_t *smem, int smem_ints, int ref_cap, int ops_cap) {
     const int wid = threadIdx.x >> 5;
     WarpDp w;
     w.sm = smem + (size_t)wid * smem_ints; w.n_ints = smem_ints;
     w.refc = reinterpret_cast<uint8_t *>(smem + (size_t)kWarpsPerBlock * smem_ints) + (size_t)wid * ref_cap; w.n_refc = ref_cap;
+    w.ops = reinterpret_cast<uint8_t *>(smem + (size_t)kWarpsPerBlock * smem_ints) + (size_t)kWarpsPerBlock * ref_cap + (size_t)wid * ops_cap; w.n_ops = ops_cap;
     w.gb = pool.bytes + ((size_t)blockIdx.x * kWarpsPerBlock + wid) * kWarpSlab; w.n_bytes = (int)kWarpSlab;
     w.lane = threadIdx.x & 31;
     return w;
@@ -75,11 +77,11 @@ __device__ __forceinline__ bool next_item_warp(uint32_t *cursor, uint32_t n, uin
 }
 
 // mate rescue, one pair per warp; pairs whose window exceeds the shared-memory rows go to `retry`
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) sw_warp_kernel(DpView v, const SwParams *spp, DpPool pool, const uint32_t *list, const uint32_t *n_list,
-                                                                       uint32_t *cursor, int smem_ints, int ref_cap, uint32_t *retry, uint32_t *n_retry) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) sw_warp_kernel(DpView v, const SwParams *spp, DpPool pool, const uint32_t *list, const uint32_t *n_list,
+                                                                       uint32_t *cursor, int smem_ints, int ref_cap, int ops_cap, uint32_t *retry, uint32_t *n_retry) {
     const SwParams sp = *spp;
     extern __shared__ int32_t dp_smem[];
-    const WarpDp w = warp_scratch(pool, dp_smem, smem_ints, ref_cap);
+    const WarpDp w = warp_scratch(pool, dp_smem, smem_ints, ref_cap, ops_cap);
     const uint32_t n = *n_list;
     uint32_t j;
     while (next_item_warp(cursor, n, j)) {
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(4 * 32) sw_huge_scan_kernel(DpView v, const Sw
     WarpDp w;
     w.sm = dp_smem + (size_t)wid * smem_ints; w.n_ints = smem_ints;
     w.refc = reinterpret_cast<uint8_t *>(dp_smem + (size_t)4 * smem_ints) + (size_t)wid * ref_cap; w.n_refc = ref_cap;
-    w.gb = nullptr; w.n_bytes = 0; w.lane = threadIdx.x & 31;
+    w.ops = nullptr; w.n_ops = 0; w.gb = nullptr; w.n_bytes = 0; w.lane = threadIdx.x & 31;
     const uint32_t n_sl = hb.ctr[1] < kHugeMaxSlices ? hb.ctr[1] : kHugeMaxSlices;
     uint32_t sidx;
     while (next_item_warp(hb.ctr + 2, n_sl, sidx)) {
@@ -172,10 +174,10 @@ __global__ void __launch_bounds__(4 * 32) sw_huge_scan_kernel(DpView v, const Sw
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) sw_huge_finish_kernel(DpView v, const SwParams *spp, DpPool pool, const uint32_t *huge_list, const uint32_t *n_huge,
-                                                                              HugeBuf hb, int smem_ints, int ref_cap, uint32_t *err) {
+                                                                              HugeBuf hb, int smem_ints, int ref_cap, int ops_cap, uint32_t *err) {
     const SwParams sp = *spp;
     extern __shared__ int32_t dp_smem[];
-    const WarpDp w = warp_scratch(pool, dp_smem, smem_ints, ref_cap);
+    const WarpDp w = warp_scratch(pool, dp_smem, smem_ints, ref_cap, ops_cap);
     const uint32_t n = *n_huge < kHugeMaxPairs ? *n_huge : kHugeMaxPairs;
     HugeView hv; hv.jobs = hb.jobs; hv.slice_best = hb.slice_best; hv.n_jobs = (int)(hb.ctr[0] < kHugeMaxJobs ? hb.ctr[0] : kHugeMaxJobs);
     uint32_t j;
@@ -208,10 +210,10 @@ __global__ void refine_classify_kernel(DpView v, uint32_t *list, uint32_t *n_lis
     if (need) list[base + __popc(m & ((1u << lane) - 1u))] = r;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) refine_warp_kernel(DpView v, DpPool pool, const uint32_t *list, const uint32_t *n_list,
-                                                                           uint32_t *cursor, int smem_ints, int ref_cap, uint32_t *retry, uint32_t *n_retry) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) refine_warp_kernel(DpView v, DpPool pool, const uint32_t *list, const uint32_t *n_list,
+                                                                           uint32_t *cursor, int smem_ints, int ref_cap, int ops_cap, uint32_t *retry, uint32_t *n_retry) {
     extern __shared__ int32_t dp_smem[];
-    const WarpDp w = warp_scratch(pool, dp_smem, smem_ints, ref_cap);
+    const WarpDp w = warp_scratch(pool, dp_smem, smem_ints, ref_cap, ops_cap);
     const uint32_t n = *n_list;
     uint32_t j;
     while (next_item_warp(cursor, n, j)) {
@@ -315,11 +317,13 @@ static int warp_blocks(const DpPool &pool) {
 
 // ctr: [0] n_list [1] cursor [2] n_retry [3] retry cursor (device words)
 void launch_sw(const DpView &v, const SwParams *sp, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, void *huge_mem,
-               cudaStream_t s) {
+               int max_read_len, cudaStream_t s) {
     sw_classify_kernel<<<(v.n_reads / 2 + 255) / 256, 256, 0, s>>>(v, sp, list, ctr);
-    const int ints = 2 * kSwSmemInts;                                    // H and E rows of a <= 702-column window
+    int ints = 2 * kSwSmemInts;                                          // H and E rows of a <= 702-column window (reverse pass) ...
+    if (ints < 17 * (max_read_len + 1)) ints = 17 * (max_read_len + 1);  // ... then the local region's global alignment: row constants + trace-back (64 B per row)
     const int ref_cap = kSwSmemInts;                                     // reference codes of the window, one byte each
-    const size_t smem = (size_t)ints * kWarpsPerBlock * 4 + (size_t)ref_cap * kWarpsPerBlock;
+    const int ops_cap = 768;                                             // path ops of the local region
+    const size_t smem = (size_t)ints * kWarpsPerBlock * 4 + (size_t)(ref_cap + ops_cap) * kWarpsPerBlock;
     // the rare very wide windows: buffers carved from huge_mem (launch_sw_huge_bytes())
     HugeBuf hb;
     char *hm = static_cast<char *>(huge_mem);
@@ -334,7 +338,7 @@ void launch_sw(const DpView &v, const SwParams *sp, const DpPool &pool, uint32_t
         sw_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, sp, pool, list, ctr, ctr + 1, err, huge_list, n_huge);
     else {
         cudaFuncSetAttribute(sw_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sw_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, sp, pool, list, ctr, ctr + 1, ints, ref_cap, retry, ctr + 2);
+        sw_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, sp, pool, list, ctr, ctr + 1, ints, ref_cap, ops_cap, retry, ctr + 2);
         sw_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, sp, pool, retry, ctr + 2, ctr + 3, err, huge_list, n_huge);
     }
     // windows wider than the per-lane scratch: sliced forward scan over all SMs, then the pair is finished by one warp
@@ -344,22 +348,26 @@ void launch_sw(const DpView &v, const SwParams *sp, const DpPool &pool, uint32_t
     cudaFuncSetAttribute(sw_huge_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
     sw_huge_scan_kernel<<<pool.n_blocks, 4 * 32, scan_smem, s>>>(v, sp, hb, scan_ints, scan_ref);
     cudaFuncSetAttribute(sw_huge_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sw_huge_finish_kernel<<<8, kWarpsPerBlock * 32, smem, s>>>(v, sp, pool, huge_list, n_huge, hb, ints, ref_cap, err);
+    sw_huge_finish_kernel<<<8, kWarpsPerBlock * 32, smem, s>>>(v, sp, pool, huge_list, n_huge, hb, ints, ref_cap, ops_cap, err);
 }
 size_t launch_sw_huge_bytes() {
     return 64 + kHugeMaxPairs * 4 + kHugeMaxJobs * sizeof(HugeJob) + (size_t)kHugeMaxSlices * 4 + (size_t)kHugeMaxSlices * sizeof(ScanBest);
 }
 void launch_refine(const DpView &v, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, int max_read_len, cudaStream_t s) {
     refine_classify_kernel<<<(v.n_reads + 255) / 256, 256, 0, s>>>(v, list, ctr);
-    int ints = 6 * (max_read_len + 16 + 1);                              // M/I/D rows, current and previous
+    const int wcols = max_read_len + 16 + 1;                             // window columns + 1 kept in shared memory
+    int ints = 6 * wcols;                                                // row-chunk form: M/I/D rows, current and previous
+    const int trace_ints = (wcols <= 129 ? 17 : 33) * (max_read_len + 1); // wavefront form: row constants + trace-back, 64 or 128 B per row
+    if (ints < trace_ints) ints = trace_ints;
     if ((size_t)ints * kWarpsPerBlock * 4 > 200u * 1024u) ints = (int)(200u * 1024u / (kWarpsPerBlock * 4));
-    const int ref_cap = (ints / 6 + 3) & ~3;                             // window columns + 1, padded to a word
-    const size_t smem = (size_t)ints * kWarpsPerBlock * 4 + (size_t)ref_cap * kWarpsPerBlock;
+    const int ref_cap = (wcols + 3) & ~3;                                // padded to a word
+    const int ops_cap = (wcols + max_read_len + 2 + 3) & ~3;
+    const size_t smem = (size_t)ints * kWarpsPerBlock * 4 + (size_t)(ref_cap + ops_cap) * kWarpsPerBlock;
     cudaFuncSetAttribute(refine_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (getenv("FQB_DP_NO_WARP"))
         refine_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, pool, list, ctr, ctr + 1, err);
     else {
-        refine_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, pool, list, ctr, ctr + 1, ints, ref_cap, retry, ctr + 2);
+        refine_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, pool, list, ctr, ctr + 1, ints, ref_cap, ops_cap, retry, ctr + 2);
         refine_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, pool, retry, ctr + 2, ctr + 3, err);
     }
     finish_kernel<<<(v.n_reads + 255) / 256, 256, 0, s>>>(v);

@@ -41,7 +41,7 @@ void launch_multi(const DpView &v, const MultiView &mv, const DpPool &pool, uint
 // huge_mem: launch_sw_huge_bytes() bytes of device memory for the very-wide-window path
 // sp: DEVICE pointer (the batch's parameters are written by the pair stage's host callback; sp->on == 0 turns the stage off)
 void launch_sw(const DpView &v, const SwParams *sp, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, void *huge_mem,
-               cudaStream_t s);
+               int max_read_len, cudaStream_t s);
 size_t launch_sw_huge_bytes();
 void launch_refine(const DpView &v, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, int max_read_len, cudaStream_t s);
 

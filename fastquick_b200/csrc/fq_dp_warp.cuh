@@ -1,12 +1,15 @@
 // Warp-cooperative dynamic programming for rows a10/a11 (device only): one alignment per WARP.
-// The 32 lanes sweep each DP row in chunks of 32 columns; the only in-row dependency (the gap that
-// extends along the row: F of the local pass, D of the global pass) is a (max,+) prefix scan over
-// the lanes, exact in integer arithmetic.  Rows live in shared memory, the trace-back matrix in a
-// warp-private slab of global memory (written coalesced, read back by lane 0).
+// Two forms.  The WAVEFRONT form (fq_dp_wave.cuh: a lane owns consecutive columns in registers, rows skewed over the lanes)
+// carries the forward pass of the local alignment and the banded global alignments whenever the window fits
+// (<= 768 columns / <= 255 columns).  The ROW-CHUNK form below (the 32 lanes sweep a row in chunks of 32 columns; the gap that
+// extends along the row -- F of the local pass, D of the global pass -- is a (max,+) prefix scan over the lanes, exact in
+// integer arithmetic; rows in shared memory, trace-back in a warp-private slab of global memory) carries the reverse pass
+// of the local alignment, whose band limits depend on the running maximum of the rows before, and everything wider.
 // Same recurrences, boundary rules and tie-breaks as fq_device_dp.cuh (which remains the
 // host-checkable statement of the logic and the fallback for windows that do not fit).
 #pragma once
 #include "fq_device_dp.cuh"
+#include "fq_dp_wave.cuh"
 
 namespace fqb {
 
@@ -15,7 +18,8 @@ namespace fqb {
 struct WarpDp {
     int32_t *sm; int n_ints;          // per-warp shared-memory rows
     uint8_t *refc; int n_refc;        // per-warp shared-memory copy of the reference window, one nt4 code per byte
-    uint8_t *gb; int n_bytes;         // per-warp global slab: [0, ops_cap) path ops, then the trace matrix
+    uint8_t *ops; int n_ops;          // per-warp shared memory: the path ops of the last global alignment
+    uint8_t *gb; int n_bytes;         // per-warp global slab: trace matrix of the row-chunk global alignment
     int lane;
 };
 
@@ -37,7 +41,7 @@ __device__ __forceinline__ bool warp_load_ref(const RefWin &R, const WarpDp &w) 
 // aln_sm_maq with a reference base that is never N: row-constant part hoisted (qn = read base is N)
 __device__ __forceinline__ int maq_row_score(uint32_t a, uint32_t qj, bool qn) { return qn ? -13 : (a == qj ? 11 : -19); }
 
-// aln_global_core, row-parallel.  Result broadcast to all lanes; path ops in w.gb[0 .. n_ops).
+// aln_global_core, row-parallel.  Result broadcast to all lanes; path ops in w.ops[0 .. n_ops).
 __device__ GlobalResult warp_global_align(const RefWin &R, int r0, int len1, const ReadSeq &Q, int q0, int len2, int gap_end, int band,
                                           const WarpDp &w) {
     GlobalResult res; res.score = 0; res.n_ops = 0; res.too_big = false;
@@ -51,9 +55,9 @@ __device__ GlobalResult warp_global_align(const RefWin &R, int r0, int len1, con
     const int tw = (b1 + b2 <= len1) ? (b1 + b2 + 1) : W;
     const int end_ge = gap_end >= 0 ? gap_end : kGapExt;
     const int ops_cap = len1 + len2 + 2;
-    if (6 * W > w.n_ints || (len2 + 1) * tw + ops_cap > w.n_bytes) { res.too_big = true; return res; }
+    if (6 * W > w.n_ints || (len2 + 1) * tw > w.n_bytes || ops_cap > w.n_ops) { res.too_big = true; return res; }
     int32_t *sm = w.sm;
-    uint8_t *tr = w.gb + ops_cap;
+    uint8_t *tr = w.gb;
 #define WROW(rw, which, i) sm[((rw) * 3 + (which)) * W + (i)]
 #define WTRC(j, i) tr[(j) * tw + ((i) - ((j) > b2 ? (j) - b2 : 0))]
     int cur = 0, last = 1;
@@ -135,13 +139,13 @@ __device__ GlobalResult warp_global_align(const RefWin &R, int r0, int len1, con
         if (WROW(last, 1, len1) > mx) { mx = WROW(last, 1, len1); type = (cell >> 2) & 3; ctype = kOpI; }
         if (WROW(last, 2, len1) > mx) { mx = WROW(last, 2, len1); type = (cell >> 4) & 3; ctype = kOpD; }
         int n = 0;
-        w.gb[n++] = (uint8_t)ctype;
+        w.ops[n++] = (uint8_t)ctype;
         do {
             if (ctype == kOpM) { --i; --j; } else if (ctype == kOpI) --j; else --i;
             cell = (i == 0 && j == 0) ? 0 : WTRC(j, i);
             ctype = type;
             type = ctype == kOpM ? (cell & 3) : ctype == kOpI ? ((cell >> 2) & 3) : ((cell >> 4) & 3);
-            w.gb[n++] = (uint8_t)ctype;
+            w.ops[n++] = (uint8_t)ctype;
         } while (i || j);
         score = mx; n_ops = n - 1;
     }
@@ -153,9 +157,23 @@ __device__ GlobalResult warp_global_align(const RefWin &R, int r0, int len1, con
     return res;
 }
 
+// the banded global alignment of a window whose codes sit in w.refc: wavefront form when the columns fit the registers
+// of the lanes and the trace-back fits the shared-memory rows (which are free at that point), row-chunk form otherwise
+__device__ GlobalResult warp_global_any(const RefWin &R, int r0, int len1, const ReadSeq &Q, int q0, int len2, int gap_end, int band, const WarpDp &w) {
+    // shared-memory rows: len2 + 1 words of per-row constants, then the trace-back (64 or 128 bytes per row)
+    const int avail = w.n_ints * 4 - (len2 + 1) * 4;
+    if (len1 <= 32 * 4 && len2 * 64 <= avail)
+        return wave_global_align<4, uint16_t>(w.refc, r0, len1, Q, q0, len2, gap_end, band, w.sm, reinterpret_cast<uint16_t *>(w.sm + len2 + 1), len2, w.ops, w.n_ops, w.lane);
+    if (len1 <= 32 * 6 && len2 * 128 <= avail)
+        return wave_global_align<6, uint32_t>(w.refc, r0, len1, Q, q0, len2, gap_end, band, w.sm, reinterpret_cast<uint32_t *>(w.sm + len2 + 1), len2, w.ops, w.n_ops, w.lane);
+    if (len1 <= 32 * 8 && len2 * 128 <= avail)
+        return wave_global_align<8, uint32_t>(w.refc, r0, len1, Q, q0, len2, gap_end, band, w.sm, reinterpret_cast<uint32_t *>(w.sm + len2 + 1), len2, w.ops, w.n_ops, w.lane);
+    return warp_global_align(R, r0, len1, Q, q0, len2, gap_end, band, w);
+}
+
 // aln_local_core (_thres = 1): forward and reverse passes row-parallel with an F prefix scan, then the global
 // alignment of the local region.  Previous-row state in shared memory: H[i] = h(i, previous row), E[i] = e(i, previous row).
-// All lanes return the same result; the path ops are left in w.gb[0 .. n_ops).
+// All lanes return the same result; the path ops are left in w.ops[0 .. n_ops).
 __device__ LocalResult warp_local_align(const RefWin &R, int len1, const ReadSeq &Q, int len2, const WarpDp &w) {
     LocalResult res; res.score = -1; res.n_ops = 0; res.start_i = res.start_j = res.end_i = res.end_j = 0; res.too_big = false;
     if (len1 == 0 || len2 == 0) return res;
@@ -165,6 +183,10 @@ __device__ LocalResult warp_local_align(const RefWin &R, int len1, const ReadSeq
     for (int i = lane; i < W; i += 32) { H[i] = 0; E[i] = 0; }
     __syncwarp();
     int score_f = 0, end_i = 0, end_j = 0;
+    if (len1 <= 32 * 8) wave_local_forward<8>(w.refc, len1, Q, len2, lane, score_f, end_i, end_j);
+    else if (len1 <= 32 * 16) wave_local_forward<16>(w.refc, len1, Q, len2, lane, score_f, end_i, end_j);
+    else if (len1 <= 32 * 24) wave_local_forward<24>(w.refc, len1, Q, len2, lane, score_f, end_i, end_j);
+    else
     for (int j = 1; j <= len2; ++j) {
         const uint32_t qj = Q.at(j - 1);
         const bool qn = qj > 3;
@@ -286,7 +308,7 @@ __device__ LocalResult warp_local_align(const RefWin &R, int len1, const ReadSeq
     ++jmax;
     GlobalResult g;
     for (int bw = kBandWidth;; bw <<= 1) {
-        g = warp_global_align(R, start_i - 1, end_i - start_i + 1, Q, start_j - 1, end_j - start_j + 1, -1, bw, w);
+        g = warp_global_any(R, start_i - 1, end_i - start_i + 1, Q, start_j - 1, end_j - start_j + 1, -1, bw, w);
         if (g.too_big) { res.too_big = true; return res; }
         if (g.score == score_r || score_f == g.score) break;
         if (bw > jmax) break;
@@ -414,7 +436,7 @@ struct WarpSwCore {
         long long b = *beg;
         uint32_t c = 0, c0 = 0, cl = 0;
         if (lane == 0) {
-            DpScratch sc; sc.ints = nullptr; sc.n_ints = 0; sc.bytes = w.gb; sc.n_bytes = w.n_bytes; sc.istride = sc.bstride = 1;
+            DpScratch sc; sc.ints = nullptr; sc.n_ints = 0; sc.bytes = w.ops; sc.n_bytes = w.n_ops; sc.istride = sc.bstride = 1;
             int64_t bb = *beg;
             nc = sw_post(R, Q, lr, &bb, cigar, &c, sc);
             b = bb;
@@ -437,11 +459,11 @@ __device__ int warp_refine_gapped(int64_t l_pac, const uint8_t *pac, const ReadS
     int64_t pos;
     const RefWin R = refine_window(l_pac, pac, Q.len, *pos_io, ext, &pos);
     if (!warp_load_ref(R, w)) return -1;
-    GlobalResult g = warp_global_align(R, 0, R.l, Q, 0, Q.len, kGapEnd, kBandWidth, w);
+    GlobalResult g = warp_global_any(R, 0, R.l, Q, 0, Q.len, kGapEnd, kBandWidth, w);
     if (g.too_big) return -1;
     int nc = 0;
     if (w.lane == 0) {
-        DpScratch sc; sc.ints = nullptr; sc.n_ints = 0; sc.bytes = w.gb; sc.n_bytes = w.n_bytes; sc.istride = sc.bstride = 1;
+        DpScratch sc; sc.ints = nullptr; sc.n_ints = 0; sc.bytes = w.ops; sc.n_bytes = w.n_ops; sc.istride = sc.bstride = 1;
         nc = refine_post(g, pos, ext, pos_io, cigar, cap, sc);
     }
     return __shfl_sync(FQB_FULL, nc, 0);

@@ -727,7 +727,7 @@ static int enqueue_sw_refine(fqb_handle *h, cudaStream_t st) {
     CU_CHECK(cudaMemsetAsync(h->d_dpctr, 0, 12 * 4, st));
     if (h->popt.is_sw && !h->single_end) {       // whether the batch has an insert-size estimate is known on the device only (d_ctl->sw.on)
         if (!h->d_sw_huge) CU_CHECK(cudaMalloc(&h->d_sw_huge, launch_sw_huge_bytes()));
-        launch_sw(v, &h->d_ctl->sw, h->dp_pool, h->d_sw_list, h->d_sw_list + h->cap_reads / 2, h->d_dpctr, h->d_status + kStDpErr, h->d_sw_huge, st);
+        launch_sw(v, &h->d_ctl->sw, h->dp_pool, h->d_sw_list, h->d_sw_list + h->cap_reads / 2, h->d_dpctr, h->d_status + kStDpErr, h->d_sw_huge, h->stride, st);
         h->n_launches += 6;      // classify, warp kernel, per-lane retry, and the three kernels of the very-wide-window path
     }
     launch_refine(v, h->dp_pool, h->d_refine_list, h->d_refine_list + h->cap_reads, h->d_dpctr + 4, h->d_status + kStDpErr, h->stride, st);
@@ -790,7 +790,7 @@ static int load_set(fqb_handle *h, int si, cudaStream_t st, int32_t n_pairs, int
     const uint8_t *src[4] = {bases1, quals1, bases2, quals2};
     const int32_t *lsrc[2] = {lens1, lens2};
     BatchView &b = B.bv;
-    b.n_reads = B.n_reads; b.stride_in = stride; b.lpad = h->lpad;
+    b.n_reads = B.n_reads; b.stride_in = stride; b.packed_stride = 0; b.lpad = h->lpad;
     const size_t bytes = (size_t)n_pairs * stride;
     if (on_device) {
         b.bases_in[0] = bases1; b.quals_in[0] = quals1; b.bases_in[1] = bases2; b.quals_in[1] = quals2;

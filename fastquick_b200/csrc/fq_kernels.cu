@@ -46,6 +46,30 @@ __global__ void __launch_bounds__(256) prep_kernel(BatchView b, PrepParams p) {
         uint8_t *qo = b.qual + (size_t)r * b.lpad;
         const int qadj = p.is_il13 ? 31 : 0;
         uint32_t codes[FQB_MAX_READ_LEN / 32];
+        if (b.packed_stride) {
+            // packed input (fqb_pack_reads): 2 bits per base, 16 bases per 32-bit word, rows aligned to 16 bytes -- the row is
+            // fetched with 128-bit loads by the first lanes and handed round with shuffles; bit 7 of a quality byte marks a
+            // base that is not A/C/G/T (nt4 code 4)
+            const uint4 *row = reinterpret_cast<const uint4 *>((e ? b.bases_in[1] : b.bases_in[0]) + (size_t)pr * b.packed_stride);
+            const int n_vec = b.packed_stride >> 4;              // <= 4 for reads up to 256 bases
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (lane < n_vec) v = __ldg(row + lane);
+#pragma unroll
+            for (int t = 0; t < FQB_MAX_READ_LEN / 32; ++t) {
+                const int j = lane + 32 * t;
+                // bases 32t .. 32t+31 live in words 2t and 2t+1 = components (2t & 3), (2t & 3) + 1 of vector t / 2
+                const uint32_t lo = (t & 1) ? v.z : v.x, hi = (t & 1) ? v.w : v.y;
+                const uint32_t w0 = __shfl_sync(FULL_MASK, lo, t >> 1), w1 = __shfl_sync(FULL_MASK, hi, t >> 1);
+                codes[t] = 0;
+                if (j < full) {
+                    const uint32_t q = qi[j];
+                    const uint32_t c2 = ((lane < 16 ? w0 : w1) >> (2 * (lane & 15))) & 3u;
+                    codes[t] = (q & 0x80u) ? 4u : c2;
+                    co[j] = (uint8_t)codes[t];
+                    qo[j] = (uint8_t)((q & 0x7fu) - qadj);
+                }
+            }
+        } else {
 #pragma unroll
         for (int t = 0; t < FQB_MAX_READ_LEN / 32; ++t) {
             int j = lane + 32 * t;
@@ -55,6 +79,7 @@ __global__ void __launch_bounds__(256) prep_kernel(BatchView b, PrepParams p) {
                 co[j] = (uint8_t)codes[t];
                 qo[j] = (uint8_t)(qi[j] - qadj);
             }
+        }
         }
         // ---- k-mer pre-filter: IsReadInHashByCountMoreChunck (src/BwtIndexer.cpp:441-456).
         // kmer = (kmer << 2) | code over 32 bases == OR of shifted codes (N = 4 bleeds upward).
@@ -88,7 +113,7 @@ __global__ void __launch_bounds__(256) prep_kernel(BatchView b, PrepParams p) {
             for (int base = full - 1; base >= 34; base -= 32) {
                 int l = base - lane;
                 bool valid = l >= 34;
-                int v = valid ? p.trim_qual - ((int)qi[l] - qadj - 33) : 0;
+                int v = valid ? p.trim_qual - ((int)(qi[l] & (b.packed_stride ? 0x7fu : 0xffu)) - qadj - 33) : 0;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     int t = __shfl_up_sync(FULL_MASK, v, d);

@@ -12,7 +12,8 @@ namespace fqb {
 // src/BwtMapper.cpp:744-765)
 struct BatchView {
     int n_reads;            // 2 * n_pairs
-    int stride_in;          // bytes per read in the ASCII input arrays
+    int stride_in;          // bytes per read in the ASCII input arrays (quality rows in packed form)
+    int packed_stride;      // 0: bases_in holds ASCII; else bytes per read of the 2-bit rows (multiple of 16), see fqb_pack_reads
     int lpad;               // bytes per read in codes/qual
     const uint8_t *bases_in[2];
     const uint8_t *quals_in[2];
