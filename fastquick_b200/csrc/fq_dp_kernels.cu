@@ -53,7 +53,7 @@ __global__ void sw_classify_kernel(DpView v, const SwParams *spp, uint32_t *list
     if (need) list[base + __popc(m & ((1u << lane) - 1u))] = p;
 }
 
-constexpr int kWarpsPerBlock = 8;
+constexpr int kWarpsPerBlock = 4;       // small blocks (<= 16 K registers): one fits beside a search grid that leaves a fifth of an SM free
 constexpr uint32_t kHugeMaxPairs = 64, kHugeMaxJobs = 128, kHugeMaxSlices = 1u << 16;   // very wide windows per batch (rare)
 constexpr size_t kWarpSlab = 256u * 1024u;       // per-warp global slab: path ops + trace-back matrix
 
@@ -77,7 +77,7 @@ __device__ __forceinline__ bool next_item_warp(uint32_t *cursor, uint32_t n, uin
 }
 
 // mate rescue, one pair per warp; pairs whose window exceeds the shared-memory rows go to `retry`
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) sw_warp_kernel(DpView v, const SwParams *spp, DpPool pool, const uint32_t *list, const uint32_t *n_list,
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) sw_warp_kernel(DpView v, const SwParams *spp, DpPool pool, const uint32_t *list, const uint32_t *n_list,
                                                                        uint32_t *cursor, int smem_ints, int ref_cap, int ops_cap, uint32_t *retry, uint32_t *n_retry) {
     const SwParams sp = *spp;
     extern __shared__ int32_t dp_smem[];
@@ -210,7 +210,7 @@ __global__ void refine_classify_kernel(DpView v, uint32_t *list, uint32_t *n_lis
     if (need) list[base + __popc(m & ((1u << lane) - 1u))] = r;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) refine_warp_kernel(DpView v, DpPool pool, const uint32_t *list, const uint32_t *n_list,
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 6) refine_warp_kernel(DpView v, DpPool pool, const uint32_t *list, const uint32_t *n_list,
                                                                            uint32_t *cursor, int smem_ints, int ref_cap, int ops_cap, uint32_t *retry, uint32_t *n_retry) {
     extern __shared__ int32_t dp_smem[];
     const WarpDp w = warp_scratch(pool, dp_smem, smem_ints, ref_cap, ops_cap);
@@ -218,12 +218,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) refine_warp_kernel(DpV
     uint32_t j;
     while (next_item_warp(cursor, n, j)) {
         const uint32_t r = list[j];
-        fqb_read_t s = v.rows[r];
-        ReadSeq Q; Q.fwd = v.codes + (size_t)r * v.lpad; Q.len = s.len; Q.strand = s.strand;
-        const int nc = warp_refine_gapped(v.l_pac, v.pac, Q, &s.pos, (s.strand ? 1 : -1) * (s.n_gapo + s.n_gape), s.cigar, FQB_MAX_CIGAR, w);
+        fqb_read_t *row = v.rows + r;                    // every lane reads the four scalars it needs; only lane 0 holds a CIGAR
+        ReadSeq Q; Q.fwd = v.codes + (size_t)r * v.lpad; Q.len = row->len; Q.strand = row->strand;
+        uint32_t pos = row->pos;
+        uint16_t cigar[FQB_MAX_CIGAR];
+        if (w.lane == 0)                                 // slots beyond n_cigar keep what they held (the per-lane kernel rewrites the whole row)
+            for (int k = 0; k < FQB_MAX_CIGAR; ++k) cigar[k] = row->cigar[k];
+        const int nc = warp_refine_gapped(v.l_pac, v.pac, Q, &pos, (Q.strand ? 1 : -1) * (row->n_gapo + row->n_gape), cigar, FQB_MAX_CIGAR, w);
         if (w.lane == 0) {
             if (nc < 0) retry[atomicAdd(n_retry, 1u)] = r;
-            else { s.n_cigar = (uint8_t)nc; s.has_cigar = 1; v.rows[r] = s; }
+            else {
+                for (int k = 0; k < FQB_MAX_CIGAR; ++k) row->cigar[k] = cigar[k];
+                row->pos = pos; row->n_cigar = (uint8_t)nc; row->has_cigar = 1;
+            }
         }
         __syncwarp();
     }
@@ -307,11 +314,11 @@ __global__ void finish_kernel(DpView v) {
     v.rows[r] = s;
 }
 
-// as many warp slabs as the byte pool holds, at most four blocks per SM (pool.n_blocks = 2 per SM)
+// as many warp slabs as the byte pool holds, at most eight blocks per SM (pool.n_blocks = 2 per SM)
 static int warp_blocks(const DpPool &pool) {
     const size_t pool_bytes = (size_t)pool.n_blocks * kDpThreads * pool.bytes_per_lane;
     size_t nb = pool_bytes / (kWarpSlab * kWarpsPerBlock);
-    if (nb > (size_t)pool.n_blocks * 2) nb = (size_t)pool.n_blocks * 2;
+    if (nb > (size_t)pool.n_blocks * 4) nb = (size_t)pool.n_blocks * 4;
     return (int)(nb < 1 ? 1 : nb);
 }
 

@@ -339,12 +339,14 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     }
 #define CU_CHECK_H(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e_)); fqb_destroy(h); return FQB_ERR_CUDA; } } while (0)
     CU_CHECK_H(cudaSetDevice(device));
-    CU_CHECK_H(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CU_CHECK_H(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    CU_CHECK_H(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
     {   // the later stages run at a higher priority than the next batch's align stage: their blocks go first when SM room frees up
+        // (lo = the numerically largest = least urgent value, which is also what a stream created without a priority gets)
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        const int main_prio = getenv("FQB_FLAT_PRIORITY") ? lo : hi;
+        CU_CHECK_H(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, main_prio));
+        CU_CHECK_H(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CU_CHECK_H(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
         for (auto &a : h->align_stream) CU_CHECK_H(cudaStreamCreateWithPriority(&a, cudaStreamNonBlocking, lo));
     }
     for (auto &e : h->ev_rows) CU_CHECK_H(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -401,8 +403,8 @@ static int create_common(fqb_handle *h, int device, fqb_handle **out) {
     h->h_ctl->rng_calls = 0; h->h_ctl->last_ii = h->last_ii; h->h_ctl->cur_ii = h->last_ii;
     CU_CHECK_H(cudaMemcpy(h->d_ctl, h->h_ctl, sizeof(fqb_handle::BatchCtl), cudaMemcpyHostToDevice));
     CU_CHECK_H(cudaMalloc(&h->d_dpctr, 12 * 4));
-    CU_CHECK_H(cudaMalloc(&h->d_counters, 16 * 8));
-    CU_CHECK_H(cudaMemset(h->d_counters, 0, 16 * 8));
+    CU_CHECK_H(cudaMalloc(&h->d_counters, 512 * 8));          // 16 counters + the timeline slots of the development build (make kstats)
+    CU_CHECK_H(cudaMemset(h->d_counters, 0, 512 * 8));
     if (h->gopt.kmer_thresh != 0) {     // 6 x 512 MiB membership tables (BwtIndexer::roll_hash_table)
         const size_t total = kRollTableBytes * kNumRollTables;
         CU_CHECK_H(cudaMalloc(&h->d_roll, total));
@@ -1804,21 +1806,23 @@ int fqb_stage_fetch_rows(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2, fq
 }
 
 // The same copy, asynchronous: the rows of the resident batch are split and copied on a second stream while the caller
-// goes on to the next batch (the engine only waits for the 20-us split before it overwrites its row buffer).
+// goes on to the next batch (the engine's own stream only runs the 20-us split).
 // fqb_rows_wait blocks until the destination buffers of the last fqb_stage_fetch_rows_async are complete.
 int fqb_stage_fetch_rows_async(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2) {
     if (!h || !h->pair_done || !rows1 || !rows2) { set_error("fqb_stage_fetch_rows_async: run fqb_stage_pair first"); return FQB_ERR_STATE; }
     CU_CHECK(cudaSetDevice(h->device));
     const size_t np = (size_t)h->n_reads / 2;
-    CU_CHECK(cudaEventRecord(h->ev_rows[0], h->stream));
-    CU_CHECK(cudaStreamWaitEvent(h->d2h_stream, h->ev_rows[0], 0));
+    // the split runs on the main stream itself (high priority: it finds SM room next to the resident search grid at once; on
+    // the copy-out stream it queued behind that grid and the next batch's later stages waited for it), the two contiguous
+    // copies on the copy-out stream.  The main stream only waits for the PREVIOUS batch's copies, which still read d_rows_split
+    CU_CHECK(cudaStreamWaitEvent(h->stream, h->ev_rows[2], 0));
     if (np) {
-        split_rows_kernel<<<(unsigned)((np * 2 * (sizeof(fqb_read_t) / 16) + 255) / 256), 256, 0, h->d2h_stream>>>(
+        split_rows_kernel<<<(unsigned)((np * 2 * (sizeof(fqb_read_t) / 16) + 255) / 256), 256, 0, h->stream>>>(
             reinterpret_cast<const uint4 *>(h->d_rows), reinterpret_cast<uint4 *>(h->d_rows_split), np);
         ++h->n_launches;
     }
-    CU_CHECK(cudaEventRecord(h->ev_rows[1], h->d2h_stream));
-    CU_CHECK(cudaStreamWaitEvent(h->stream, h->ev_rows[1], 0));          // later stages may overwrite d_rows only after the split
+    CU_CHECK(cudaEventRecord(h->ev_rows[0], h->stream));
+    CU_CHECK(cudaStreamWaitEvent(h->d2h_stream, h->ev_rows[0], 0));
     if (np) {
         CU_CHECK(cudaMemcpyAsync(rows1, h->d_rows_split, np * sizeof(fqb_read_t), cudaMemcpyDeviceToHost, h->d2h_stream));
         CU_CHECK(cudaMemcpyAsync(rows2, h->d_rows_split + np, np * sizeof(fqb_read_t), cudaMemcpyDeviceToHost, h->d2h_stream));
@@ -1903,6 +1907,13 @@ int fqb_stage_counters(fqb_handle *h, uint64_t *out4) {
         fprintf(stderr, "kstats iter %llu step %llu exh %llu hist", k[4], k[5], k[6]);
         for (int q = 0; q < 9; ++q) fprintf(stderr, " %llu", k[7 + q]);
         fprintf(stderr, "\n");
+        std::vector<unsigned long long> tl(512);
+        cudaMemcpy(tl.data(), h->d_counters, 512 * 8, cudaMemcpyDeviceToHost);
+        if (tl[16]) {
+            fprintf(stderr, "timeline dry %.2f ms end %.2f ms\n  bin(0.25ms): warps_left trips live/trip\n", (tl[17] > tl[16] ? (tl[17] - tl[16]) * 1e-6 : 0.0), (tl[18] - tl[16]) * 1e-6);
+            for (int q = 0; q < 128; ++q) if (tl[32 + q] || tl[160 + q]) fprintf(stderr, "  %3d %6llu %8llu %5.1f\n", q, tl[32 + q], tl[160 + q], tl[160 + q] ? (double)tl[288 + q] / tl[160 + q] : 0.0);
+            cudaMemset(h->d_counters + 16, 0, (512 - 16) * 8);
+        }
     }
     CU_CHECK(cudaMemcpy(&ov, h->d_ctrs + 2, 4, cudaMemcpyDeviceToHost));
     out4[0] = c[0]; out4[1] = c[1]; out4[2] = c[2]; out4[3] = ov;

@@ -301,6 +301,12 @@ __global__ void __launch_bounds__(kSearchThreads, kMinBlocks) search_kernel(cons
     unsigned long long pops = 0, occs = 0, blks = 0;
 #ifdef FQB_KSTATS
     unsigned long long ks_iter = 0, ks_step = 0, ks_exh = 0; unsigned ks_hist[9] = {0,0,0,0,0,0,0,0,0};
+    // timeline of the launch (development build only): slot 16 = start, 17 = when the queue ran dry, 18 = end (globaltimer ns);
+    // 32.. = warps leaving, 160.. = warp trips, 288.. = live lanes summed over those trips, all in 0.25-ms bins since the start
+    const bool ks_tl = p.counters && n_work > 4096;
+    auto ks_now = []() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
+    if (ks_tl && blockIdx.x == 0 && threadIdx.x == 0) p.counters[16] = ks_now();
+    bool ks_dry_seen = false;
 #endif
 
     for (;;) {
@@ -332,7 +338,13 @@ __global__ void __launch_bounds__(kSearchThreads, kMinBlocks) search_kernel(cons
         if (__all_sync(FULL_MASK, exhausted && !active)) break;
 #ifdef FQB_KSTATS
         { unsigned m1 = __ballot_sync(FULL_MASK, active && st == kLaneRunning), m2 = __ballot_sync(FULL_MASK, exhausted && !active);
-          if (lane_id == 0) { ks_iter++; ks_step += __popc(m1); ks_exh += __popc(m2); ks_hist[__popc(m1) >> 2]++; } }
+          if (lane_id == 0) { ks_iter++; ks_step += __popc(m1); ks_exh += __popc(m2); ks_hist[__popc(m1) >> 2]++; }
+          if (ks_tl && lane_id == 0) {
+              const unsigned long long t = ks_now(), t0 = *(volatile unsigned long long *)(p.counters + 16);
+              unsigned bin = t0 && t > t0 ? (unsigned)((t - t0) / 250000ull) : 0; if (bin > 127) bin = 127;
+              atomicAdd(p.counters + 160 + bin, 1ull); atomicAdd(p.counters + 288 + bin, (unsigned long long)__popc(m1));
+              if (m2 && !ks_dry_seen) { ks_dry_seen = true; atomicMax(p.counters + 17, t); }
+          } }
 #endif
         if (active && st == kLaneRunning) st = lane.step();
         warp_shadow(lane, active && st == kLaneHit, lane_id);
@@ -352,6 +364,11 @@ __global__ void __launch_bounds__(kSearchThreads, kMinBlocks) search_kernel(cons
     }
     if (lane_id == 0 && p.counters) { atomicAdd(p.counters, pops); atomicAdd(p.counters + 1, occs); atomicAdd(p.counters + 2, blks); }
 #ifdef FQB_KSTATS
+    if (ks_tl && lane_id == 0) {
+        const unsigned long long t = ks_now(), t0 = *(volatile unsigned long long *)(p.counters + 16);
+        unsigned bin = t0 && t > t0 ? (unsigned)((t - t0) / 250000ull) : 0; if (bin > 127) bin = 127;
+        atomicAdd(p.counters + 32 + bin, 1ull); atomicMax(p.counters + 18, t);
+    }
     if (lane_id == 0 && p.counters) { atomicAdd(p.counters + 4, ks_iter); atomicAdd(p.counters + 5, ks_step); atomicAdd(p.counters + 6, ks_exh);
         for (int q = 0; q < 9; ++q) atomicAdd(p.counters + 7 + q, (unsigned long long)ks_hist[q]); }
 #endif
