@@ -197,6 +197,7 @@ class Engine:
         self.lib, self.h, self.n, self.world = lib, h, n_pairs, world
         self.src, self.on_device, self.rows = None, 0, None       # set per timed phase
         self.base = 0                                              # local step index of this phase's global batch 0
+        self.packed_stride = 0                                     # > 0: the buffers hold the packed input form
 
     @staticmethod
     def _ptr(t):
@@ -205,8 +206,12 @@ class Engine:
     def submit(self, b):
         d = self.src[self.base + b // self.world]
         lib = self.lib
-        assert lib.fqb_submit_pairs(self.h, self.n, READ_LEN, self._ptr(d[0]), self._ptr(d[1]), None, self._ptr(d[2]), self._ptr(d[3]), None,
-                                    self.on_device) == 0, lib.fqb_last_error()
+        if self.packed_stride:
+            rc = lib.fqb_submit_pairs_packed(self.h, self.n, READ_LEN, self.packed_stride, self._ptr(d[0]), self._ptr(d[1]), None, self._ptr(d[2]), self._ptr(d[3]), None,
+                                             self.on_device)
+        else:
+            rc = lib.fqb_submit_pairs(self.h, self.n, READ_LEN, self._ptr(d[0]), self._ptr(d[1]), None, self._ptr(d[2]), self._ptr(d[3]), None, self.on_device)
+        assert rc == 0, lib.fqb_last_error()
 
     def collect(self, b, first_pair, is_last):
         lib = self.lib
@@ -254,15 +259,30 @@ def main_gpu(args):
     n_steps = args.warmup + args.steps
     n_pairs = args.pairs_per_step
     # this rank's shard of the workload: global batch b = s * world + rank
+    # Input form: what fqb_feeder_fill_packed emits -- 2-bit bases (32 / 48 bytes per 100 / 150-base read) and the quality
+    # bytes with the not-ACGT flag (--ascii-input: the ASCII rows of fqb_feeder_fill).  The batches are packed here, once,
+    # outside every timed region (in the CLI the feeder's parse workers do it).
+    lib.fqb_packed_stride.restype = C.c_int32
+    pstride = 0 if args.ascii_input else lib.fqb_packed_stride(READ_LEN)
     host = []
+    scratch = [np.empty((n_pairs, READ_LEN), np.uint8) for _ in range(4)] if pstride else None
     for s in range(n_steps):
         first = (s * world + rank) * n_pairs
-        bufs = [torch.empty((n_pairs, READ_LEN), dtype=torch.uint8).pin_memory() for _ in range(4)]
-        gen_reads(lib, synth, first, n_pairs, out=[b.numpy() for b in bufs])
+        if pstride:
+            gen_reads(lib, synth, first, n_pairs, out=scratch)
+            bufs = [torch.empty((n_pairs, pstride if (i & 1) == 0 else READ_LEN), dtype=torch.uint8).pin_memory() for i in range(4)]
+            for e in (0, 2):
+                assert lib.fqb_pack_reads(C.c_int64(n_pairs), READ_LEN, C.c_void_p(scratch[e].ctypes.data), C.c_void_p(scratch[e + 1].ctypes.data), pstride,
+                                          C.c_void_p(bufs[e].data_ptr()), C.c_void_p(bufs[e + 1].data_ptr())) == 0, lib.fqb_last_error()
+        else:
+            bufs = [torch.empty((n_pairs, READ_LEN), dtype=torch.uint8).pin_memory() for _ in range(4)]
+            gen_reads(lib, synth, first, n_pairs, out=[b.numpy() for b in bufs])
         host.append(bufs)
     dev = [[b.cuda(non_blocking=True) for b in bufs] for bufs in host]   # whole shard resident in HBM
     torch.cuda.synchronize()
     eng = Engine(lib, h, n_pairs, world)
+    eng.packed_stride = pstride
+    h2d_bytes = sum(int(b.numel()) for b in host[0])
     rows_host = [[torch.empty((n_pairs, _abi.READ_DTYPE.itemsize), dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(2)]
     merge_ms = []
 
@@ -334,7 +354,11 @@ def main_gpu(args):
     rq0 = rq_time()
     for s_ in range(n_steps - iso_steps, n_steps):
         d = dev[s_]
-        assert lib.fqb_stage_load(h, n_pairs, READ_LEN, Engine._ptr(d[0]), Engine._ptr(d[1]), None, Engine._ptr(d[2]), Engine._ptr(d[3]), None, 1) == 0, lib.fqb_last_error()
+        if pstride:
+            rc = lib.fqb_stage_load_packed(h, n_pairs, READ_LEN, pstride, Engine._ptr(d[0]), Engine._ptr(d[1]), None, Engine._ptr(d[2]), Engine._ptr(d[3]), None, 1)
+        else:
+            rc = lib.fqb_stage_load(h, n_pairs, READ_LEN, Engine._ptr(d[0]), Engine._ptr(d[1]), None, Engine._ptr(d[2]), Engine._ptr(d[3]), None, 1)
+        assert rc == 0, lib.fqb_last_error()
         assert lib.fqb_stage_align(h) == 0, lib.fqb_last_error()
     c1 = (C.c_uint64 * 4)(); lib.fqb_stage_counters(h, c1)
     rq1 = rq_time()
@@ -366,7 +390,9 @@ def main_gpu(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "name": args.config, "pairs_per_step": n_pairs, "read_len": READ_LEN, "stages": STAGES,
-                   "l2_policy": "every step reads a different %d MB batch; per-step working set (inputs+widths+stack arena) exceeds the 126 MB L2" % (4 * n_pairs * READ_LEN // 1000000),
+                   "l2_policy": "every step reads a different %d MB batch; per-step working set (inputs+widths+stack arena) exceeds the 126 MB L2" % (h2d_bytes // 1000000),
+                   "input_form": ("ASCII bases + qualities (fqb_feeder_fill)" if not pstride else
+                                  "packed: 2-bit bases, %d bytes per read, + quality bytes with the not-ACGT flag (what fqb_feeder_fill_packed emits; packed once, outside the timed regions)" % pstride),
                    "index": "%d markers (counts of the named marker set; positions/alleles synthetic), replicated per GPU" % sum(CFG["markers"]),
                    "pipeline": "fqb_submit_pairs(b+1) before fqb_collect_pairs_sharded(b): align stage of the next batch on a second stream, "
                                "no host synchronisation per batch (one wait at the end of the run)",
@@ -374,7 +400,7 @@ def main_gpu(args):
                                 "(56 B per batch, one-thread kernels); accumulators reduced with one NCCL group and pile-up entries / "
                                 "duplicate keys sent to rank 0 inside the timed region, all in the C library",
                    "reference_arm_sample": "bench.py --impl reference times %d-pair samples of the same workload per step (the CPU path is ~1000x slower)" % REF_SAMPLE_PAIRS},
-        "e2e": {"value": e2e_value, "unit": "read-pairs/s", "h2d_bytes_per_step": 4 * n_pairs * READ_LEN,
+        "e2e": {"value": e2e_value, "unit": "read-pairs/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": int(2 * n_pairs * _abi.READ_DTYPE.itemsize), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
@@ -423,6 +449,7 @@ def main():
     ap.add_argument("--config", default="2x100_10k", choices=sorted(CONFIGS), help="workload (default: BASELINE.json configs[1], the contract line)")
     ap.add_argument("--pairs-per-step", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ascii-input", action="store_true", help="hand the batches over as ASCII rows instead of the packed form")
     args = ap.parse_args()
     select_config(args.config)
     if args.impl == "reference":

@@ -119,6 +119,32 @@ int fqb_write_fastq_gz(const char *path, int which_end, int64_t first_pair, int6
     return FQB_OK;
 }
 
+// ---- packed input form (north_star: 2-bit bases, 128-bit loads on the device) ----
+int32_t fqb_packed_stride(int32_t stride) { return stride <= 0 ? 0 : ((stride + 63) / 64) * 16; }
+
+int fqb_pack_reads(int64_t n, int32_t stride, const uint8_t *bases, const uint8_t *quals, int32_t packed_stride, uint8_t *packed_out, uint8_t *quals_out) {
+    if (n < 0 || stride < 1 || !bases || !quals || !packed_out || !quals_out || packed_stride != fqb_packed_stride(stride)) {
+        fqb::set_error("fqb_pack_reads: bad arguments (packed_stride must be fqb_packed_stride(stride))"); return FQB_ERR_ARG;
+    }
+    // nst_nt4_table (libbwa/bntseq.c:38-55) over the bytes a FASTQ line can hold
+    uint8_t nt4[256];
+    for (int c = 0; c < 256; ++c) nt4[c] = 4;
+    nt4['A'] = nt4['a'] = 0; nt4['C'] = nt4['c'] = 1; nt4['G'] = nt4['g'] = 2; nt4['T'] = nt4['t'] = 3; nt4['-'] = 5;
+    for (int64_t r = 0; r < n; ++r) {
+        const uint8_t *b = bases + (size_t)r * stride, *q = quals + (size_t)r * stride;
+        uint32_t *w = reinterpret_cast<uint32_t *>(packed_out + (size_t)r * packed_stride);
+        uint8_t *qo = quals_out + (size_t)r * stride;
+        for (int k = 0; k < packed_stride / 4; ++k) w[k] = 0;
+        for (int j = 0; j < stride; ++j) {
+            if (q[j] & 0x80u) { fqb::set_error("fqb_pack_reads: a quality byte above 127"); return FQB_ERR_ARG; }
+            const uint32_t c = nt4[b[j]];
+            w[j >> 4] |= (c & 3u) << (2 * (j & 15));          // c - 4 for the codes above 3: 0 = N, 1 = '-'
+            qo[j] = (uint8_t)(q[j] | (c > 3 ? 0x80u : 0u));
+        }
+    }
+    return FQB_OK;
+}
+
 }  // extern "C"
 
 std::vector<fqb::FlankSeq> fqb_synth_flanks_internal(const fqb_synth *s) { return fqb::synth_flanks(s->ref); }

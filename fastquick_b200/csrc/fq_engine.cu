@@ -784,27 +784,29 @@ static int sync_and_check(fqb_handle *h) {
 extern "C" {
 // ---- stage-level entry points ------------------------------------------------
 // upload (or adopt the device pointers of) one batch into set si
+// packed_stride = 0: bases are ASCII rows of `stride` bytes; else 2-bit rows of packed_stride bytes (fqb_pack_reads) and
+// the quality rows carry the not-ACGT flag in bit 7
 static int load_set(fqb_handle *h, int si, cudaStream_t st, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
-                    const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device) {
+                    const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device, int32_t packed_stride = 0) {
     fqb_handle::BatchSet &B = h->sets[si];
     B.n_reads = 2 * n_pairs; B.stride = stride;
     B.single_end = bases2 == nullptr;
     const uint8_t *src[4] = {bases1, quals1, bases2, quals2};
     const int32_t *lsrc[2] = {lens1, lens2};
     BatchView &b = B.bv;
-    b.n_reads = B.n_reads; b.stride_in = stride; b.packed_stride = 0; b.lpad = h->lpad;
-    const size_t bytes = (size_t)n_pairs * stride;
+    b.n_reads = B.n_reads; b.stride_in = stride; b.packed_stride = packed_stride; b.lpad = h->lpad;
+    const size_t bytes = (size_t)n_pairs * stride, bytes_bases = (size_t)n_pairs * (packed_stride ? packed_stride : stride);
     if (on_device) {
         b.bases_in[0] = bases1; b.quals_in[0] = quals1; b.bases_in[1] = bases2; b.quals_in[1] = quals2;
         b.lens_in[0] = lens1; b.lens_in[1] = lens2;
     } else {
-        if (B.pre_valid && B.pre_pairs == n_pairs && B.pre_stride == stride && B.pre_key[0] == bases1 && B.pre_key[1] == quals1 &&
+        if (!packed_stride && B.pre_valid && B.pre_pairs == n_pairs && B.pre_stride == stride && B.pre_key[0] == bases1 && B.pre_key[1] == quals1 &&
             B.pre_key[2] == bases2 && B.pre_key[3] == quals2) {
             CU_CHECK(cudaStreamWaitEvent(st, B.ev_in, 0));          // uploaded ahead of time by fqb_prefetch_pairs
             ++h->prefetch_hits;
         } else {
             CU_CHECK(cudaStreamWaitEvent(st, B.ev_free, 0));
-            for (int i = 0; i < 4; ++i) if (src[i]) CU_CHECK(cudaMemcpyAsync(B.d_in[i], src[i], bytes, cudaMemcpyHostToDevice, st));
+            for (int i = 0; i < 4; ++i) if (src[i]) CU_CHECK(cudaMemcpyAsync(B.d_in[i], src[i], (i & 1) ? bytes : bytes_bases, cudaMemcpyHostToDevice, st));
             for (int i = 0; i < 2; ++i)
                 if (lsrc[i]) CU_CHECK(cudaMemcpyAsync(B.d_lens_in[i], lsrc[i], (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
         }
@@ -817,15 +819,19 @@ static int load_set(fqb_handle *h, int si, cudaStream_t st, int32_t n_pairs, int
     B.state = 1;
     return FQB_OK;
 }
-static int check_shape(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1, const uint8_t *bases2, const uint8_t *quals2) {
+static int check_shape(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1, const uint8_t *bases2, const uint8_t *quals2,
+                       int32_t packed_stride = 0) {
     if (!h || n_pairs < 0 || stride < 1 || stride > FQB_MAX_READ_LEN) { set_error("bad batch shape"); return FQB_ERR_ARG; }
+    if (packed_stride && ((packed_stride & 15) || packed_stride * 4 < stride || packed_stride > FQB_MAX_READ_LEN / 4)) {
+        set_error("packed rows are a multiple of 16 bytes that holds `stride` bases (fqb_packed_stride)"); return FQB_ERR_ARG;
+    }
     if (!bases1 || !quals1 || (bases2 && !quals2)) { set_error("bases and qualities are required"); return FQB_ERR_ARG; }
     return FQB_OK;
 }
 
-int fqb_stage_load(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
-                   const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device) {
-    if (int rc = check_shape(h, n_pairs, stride, bases1, quals1, bases2, quals2)) return rc;
+static int stage_load_impl(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
+                           const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device, int32_t packed_stride) {
+    if (int rc = check_shape(h, n_pairs, stride, bases1, quals1, bases2, quals2, packed_stride)) return rc;
     if (h->n_fifo) { set_error("fqb_stage_load: batches submitted with fqb_submit_pairs are still in flight (collect them first)"); return FQB_ERR_STATE; }
     CU_CHECK(cudaSetDevice(h->device));
     int rc = ensure_batch(h, 2 * n_pairs, stride);
@@ -839,11 +845,20 @@ int fqb_stage_load(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t
     }
     if (!on_device && h->sets[si].pre_valid && h->sets[si].pre_key[0] != bases1) si = 1 - si;
     CU_CHECK(cudaStreamWaitEvent(h->stream, h->sets[si].ev_done, 0));
-    rc = load_set(h, si, h->stream, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, on_device);
+    rc = load_set(h, si, h->stream, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, on_device, packed_stride);
     if (rc) return rc;
     use_set(h, si);
     h->batch_ready = true; h->align_done = h->pair_done = h->dp_done = h->stats_done = false;
     return FQB_OK;
+}
+int fqb_stage_load(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
+                   const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device) {
+    return stage_load_impl(h, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, on_device, 0);
+}
+int fqb_stage_load_packed(fqb_handle *h, int32_t n_pairs, int32_t stride, int32_t packed_stride, const uint8_t *packed1, const uint8_t *quals1,
+                          const int32_t *lens1, const uint8_t *packed2, const uint8_t *quals2, const int32_t *lens2, int on_device) {
+    if (packed_stride <= 0) { set_error("fqb_stage_load_packed: packed_stride must be positive"); return FQB_ERR_ARG; }
+    return stage_load_impl(h, n_pairs, stride, packed1, quals1, lens1, packed2, quals2, lens2, on_device, packed_stride);
 }
 
 // a1..a5 on the resident batch: prep -> widths -> search (+ overflow tiers)
@@ -2134,10 +2149,10 @@ int fqb_prefetch_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uin
 }
 uint64_t fqb_prefetch_hits(const fqb_handle *h) { return h ? h->prefetch_hits : 0; }
 
-int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
-                    const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2,
-                    fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out) {
-    int rc = fqb_stage_load(h, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, 0);
+static int align_pairs_impl(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
+                            const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2,
+                            fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out, int32_t packed_stride) {
+    int rc = stage_load_impl(h, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, 0, packed_stride);
     if (rc) return rc;
     // the whole chain is enqueued at once; the only wait is for the result
     if ((rc = enqueue_align(h, h->cur, h->stream))) return rc;
@@ -2150,6 +2165,18 @@ int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_
     if (ii_out) *ii_out = h->cur_ii;
     return FQB_OK;
 }
+int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
+                    const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2,
+                    fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out) {
+    return align_pairs_impl(h, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, rows1, rows2, ii_out, 0);
+}
+// the same batch in the packed input form (fqb_pack_reads / fqb_feeder_fill_packed): 2-bit bases, not-ACGT flag in bit 7 of the qualities
+int fqb_align_pairs_packed(fqb_handle *h, int32_t n_pairs, int32_t stride, int32_t packed_stride, const uint8_t *packed1, const uint8_t *quals1,
+                           const int32_t *lens1, const uint8_t *packed2, const uint8_t *quals2, const int32_t *lens2,
+                           fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out) {
+    if (packed_stride <= 0) { set_error("fqb_align_pairs_packed: packed_stride must be positive"); return FQB_ERR_ARG; }
+    return align_pairs_impl(h, n_pairs, stride, packed1, quals1, lens1, packed2, quals2, lens2, rows1, rows2, ii_out, packed_stride);
+}
 
 // ---- pipelined form: submit batch n+1, then collect batch n ---------------------------------------------------
 // fqb_submit_pairs uploads a batch and enqueues its align stage (a1-a5) on the align stream, into the batch set that is
@@ -2157,9 +2184,9 @@ int fqb_align_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_
 // and -- when statistics are open -- StatCollector's accumulation on the main stream, and starts the copy of its result
 // rows; it does not wait either.  The align stage of batch n+1 therefore runs on the GPU next to the later stages of
 // batch n, and nothing in the loop blocks the host: fqb_rows_wait (or any call that returns data) is the only wait.
-int fqb_submit_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
-                     const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device) {
-    if (int rc = check_shape(h, n_pairs, stride, bases1, quals1, bases2, quals2)) return rc;
+static int submit_impl(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
+                       const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device, int32_t packed_stride) {
+    if (int rc = check_shape(h, n_pairs, stride, bases1, quals1, bases2, quals2, packed_stride)) return rc;
     if (h->n_fifo >= 2) { set_error("fqb_submit_pairs: two batches are already in flight; collect one first"); return FQB_ERR_STATE; }
     CU_CHECK(cudaSetDevice(h->device));
     if (2 * n_pairs > h->cap_reads || stride > h->stride_cap) {
@@ -2175,7 +2202,7 @@ int fqb_submit_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8
     CU_CHECK(cudaStreamWaitEvent(ast, B.ev_done, 0));
     // the upload runs on the copy stream (it only needs the staging arrays, free once the previous occupant's prep_kernel has
     // run), so it overlaps the search of the batch before; the align stream picks it up through ev_in
-    int rc = load_set(h, si, h->copy_stream, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, on_device);
+    int rc = load_set(h, si, h->copy_stream, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, on_device, packed_stride);
     if (rc) return rc;
     CU_CHECK(cudaEventRecord(B.ev_in, h->copy_stream));
     CU_CHECK(cudaStreamWaitEvent(ast, B.ev_in, 0));
@@ -2183,6 +2210,15 @@ int fqb_submit_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8
     CU_CHECK(cudaEventRecord(B.ev_align, ast));
     h->fifo[h->n_fifo++] = si;
     return FQB_OK;
+}
+int fqb_submit_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uint8_t *bases1, const uint8_t *quals1,
+                     const int32_t *lens1, const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device) {
+    return submit_impl(h, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, on_device, 0);
+}
+int fqb_submit_pairs_packed(fqb_handle *h, int32_t n_pairs, int32_t stride, int32_t packed_stride, const uint8_t *packed1, const uint8_t *quals1,
+                            const int32_t *lens1, const uint8_t *packed2, const uint8_t *quals2, const int32_t *lens2, int on_device) {
+    if (packed_stride <= 0) { set_error("fqb_submit_pairs_packed: packed_stride must be positive"); return FQB_ERR_ARG; }
+    return submit_impl(h, n_pairs, stride, packed1, quals1, lens1, packed2, quals2, lens2, on_device, packed_stride);
 }
 int fqb_collect_pairs(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2) {
     if (!h || !h->n_fifo) { set_error("fqb_collect_pairs: no batch submitted"); return FQB_ERR_STATE; }

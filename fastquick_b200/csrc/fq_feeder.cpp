@@ -145,7 +145,15 @@ using BlockPtr = std::shared_ptr<Block>;
 struct Batch {
     int stride, name_stride;
     uint8_t *bases, *quals; int32_t *lens; char *names;
+    // optional second form of the same rows for the upload (fqb_feeder_fill_packed): 2-bit bases, qualities with the not-ACGT flag
+    int packed_stride = 0; uint8_t *packed = nullptr, *qflag = nullptr;
 };
+// nst_nt4_table (libbwa/bntseq.c:38-55); the packed rows store code & 3 and flag the codes above 3 in bit 7 of the quality
+struct Nt4Table {
+    uint8_t t[256];
+    Nt4Table() { for (int c = 0; c < 256; ++c) t[c] = 4; t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3; t['-'] = 5; }
+};
+static const Nt4Table kNt4;
 
 // first failure of any job of this feeder; reported by fill()
 struct Failure {
@@ -257,6 +265,17 @@ bool parse_record(const char *p, const char *end, const Batch &B, int slot, Fail
     memcpy(b, l[1], sl); memset(b + sl, 'N', (size_t)B.stride - sl);
     memcpy(q, l[3], sl); memset(q + sl, '!', (size_t)B.stride - sl);
     B.lens[slot] = (int32_t)sl;
+    if (B.packed) {
+        uint32_t *w = reinterpret_cast<uint32_t *>(B.packed + (size_t)slot * B.packed_stride);
+        uint8_t *qf = B.qflag + (size_t)slot * B.stride;
+        for (int k = 0; k < B.packed_stride / 4; ++k) w[k] = 0;
+        for (int j = 0; j < B.stride; ++j) {
+            if (q[j] & 0x80u) { fail.raise("quality byte above 127 in a FASTQ record"); return false; }
+            const uint32_t c = kNt4.t[b[j]];
+            w[j >> 4] |= (c & 3u) << (2 * (j & 15));
+            qf[j] = (uint8_t)(q[j] | (c > 3 ? 0x80u : 0u));
+        }
+    }
     const char *nb = l[0] + 1, *ne = nb;
     while (ne < e[0] && *ne != ' ' && *ne != '\t') ++ne;
     if (ne - nb > 2 && ne[-2] == '/' && (ne[-1] == '1' || ne[-1] == '2')) ne -= 2;
@@ -585,6 +604,18 @@ int fqb_feeder_format(const fqb_feeder *f) { return f ? f->f.kind() : -1; }
 int64_t fqb_feeder_fill(fqb_feeder *f, int32_t n_max, int32_t stride, uint8_t *bases, uint8_t *quals, int32_t *lens, char *names, int32_t name_stride) {
     if (!f || !bases || !quals || !lens || !names || n_max < 0 || stride < 1 || name_stride < 2) { fqb::set_error("bad argument"); return -1; }
     fqb::Batch B{stride, name_stride, bases, quals, lens, names};
+    std::string err;
+    const int n = f->f.fill(n_max, B, err);
+    if (n < 0) fqb::set_error(err);
+    return n;
+}
+
+int64_t fqb_feeder_fill_packed(fqb_feeder *f, int32_t n_max, int32_t stride, uint8_t *bases, uint8_t *quals, int32_t *lens, char *names, int32_t name_stride,
+                               int32_t packed_stride, uint8_t *packed, uint8_t *quals_flagged) {
+    if (!f || !bases || !quals || !lens || !names || n_max < 0 || stride < 1 || name_stride < 2 || !packed || !quals_flagged ||
+        packed_stride != ((stride + 63) / 64) * 16) { fqb::set_error("bad argument (packed_stride must be fqb_packed_stride(stride))"); return -1; }
+    fqb::Batch B{stride, name_stride, bases, quals, lens, names};
+    B.packed_stride = packed_stride; B.packed = packed; B.qflag = quals_flagged;
     std::string err;
     const int n = f->f.fill(n_max, B, err);
     if (n < 0) fqb::set_error(err);

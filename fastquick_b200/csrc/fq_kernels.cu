@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) prep_kernel(BatchView b, PrepParams p) {
         if (b.packed_stride) {
             // packed input (fqb_pack_reads): 2 bits per base, 16 bases per 32-bit word, rows aligned to 16 bytes -- the row is
             // fetched with 128-bit loads by the first lanes and handed round with shuffles; bit 7 of a quality byte marks a
-            // base that is not A/C/G/T (nt4 code 4)
+            // base that is not A/C/G/T, whose 2-bit field then holds nt4 code - 4 (0 = N and friends, 1 = '-')
             const uint4 *row = reinterpret_cast<const uint4 *>((e ? b.bases_in[1] : b.bases_in[0]) + (size_t)pr * b.packed_stride);
             const int n_vec = b.packed_stride >> 4;              // <= 4 for reads up to 256 bases
             uint4 v = make_uint4(0, 0, 0, 0);
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) prep_kernel(BatchView b, PrepParams p) {
                 if (j < full) {
                     const uint32_t q = qi[j];
                     const uint32_t c2 = ((lane < 16 ? w0 : w1) >> (2 * (lane & 15))) & 3u;
-                    codes[t] = (q & 0x80u) ? 4u : c2;
+                    codes[t] = (q & 0x80u) ? 4u + c2 : c2;
                     co[j] = (uint8_t)codes[t];
                     qo[j] = (uint8_t)((q & 0x7fu) - qadj);
                 }

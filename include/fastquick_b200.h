@@ -167,6 +167,30 @@ int fqb_submit_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride,
                      const uint8_t *bases2, const uint8_t *quals2, const int32_t *lens2, int on_device);
 int fqb_collect_pairs(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows2);
 
+/* ---- packed input form ------------------------------------------------------------------------------------------
+ * What bwa_read_seq_with_hash_dev (src/BwtMapper.cpp:543-590) produces per read before the aligner sees it is the nt4
+ * code of every base (nst_nt4_table, libbwa/bntseq.c:38-55) and its quality.  A batch can be handed over in that
+ * form directly, which is 264 instead of 400 bytes per 2 x 100 bp pair over PCIe and lets prep_kernel fetch a read's
+ * bases with 128-bit loads: `packed` rows hold 2 bits per base, 16 bases per little-endian 32-bit word from bit 0 up,
+ * fqb_packed_stride(stride) = 16 * ceil(stride / 64) bytes per read; the quality rows (`stride` bytes per read, as
+ * before) carry in bit 7 the flag "not A/C/G/T", and the 2-bit field of such a base holds its nt4 code minus 4 (0 for N
+ * and every other letter, 1 for '-').  fqb_pack_reads converts `n` ASCII rows (FQB_ERR_ARG on a quality byte above
+ * 127); fqb_feeder_fill_packed has the feeder's parse workers emit both forms.  The packed calls take the same
+ * lens / on_device arguments as their ASCII counterparts and give bit-identical results. */
+int32_t fqb_packed_stride(int32_t stride);
+int fqb_pack_reads(int64_t n, int32_t stride, const uint8_t *bases, const uint8_t *quals,
+                   int32_t packed_stride, uint8_t *packed_out, uint8_t *quals_out);
+int fqb_align_pairs_packed(fqb_handle *h, int32_t n_pairs, int32_t stride, int32_t packed_stride,
+                           const uint8_t *packed1, const uint8_t *quals1, const int32_t *lens1,
+                           const uint8_t *packed2, const uint8_t *quals2, const int32_t *lens2,
+                           fqb_read_t *rows1, fqb_read_t *rows2, fqb_isize_t *ii_out);
+int fqb_stage_load_packed(fqb_handle *h, int32_t n_pairs, int32_t stride, int32_t packed_stride,
+                          const uint8_t *packed1, const uint8_t *quals1, const int32_t *lens1,
+                          const uint8_t *packed2, const uint8_t *quals2, const int32_t *lens2, int on_device);
+int fqb_submit_pairs_packed(fqb_handle *h, int32_t n_pairs, int32_t stride, int32_t packed_stride,
+                            const uint8_t *packed1, const uint8_t *quals1, const int32_t *lens1,
+                            const uint8_t *packed2, const uint8_t *quals2, const int32_t *lens2, int on_device);
+
 /* ---- stage-level entry points (parity tests, bench, profiling) ---------------
  * The same kernels fqb_align_pairs sequences, one group at a time, on the batch
  * made resident by fqb_stage_load.  Read index r = 2*pair + end. */
@@ -307,6 +331,10 @@ int fqb_feeder_open(const char *path, int n_threads, fqb_feeder **out);
 int fqb_feeder_format(const fqb_feeder *f);         /* 0 plain text, 1 gzip stream, 2 BGZF */
 int64_t fqb_feeder_fill(fqb_feeder *f, int32_t n_max, int32_t stride, uint8_t *bases, uint8_t *quals,
                         int32_t *lens, char *names, int32_t name_stride);
+/* fill, plus the same rows in the packed upload form (see fqb_pack_reads): the workers that parse a record also pack it */
+int64_t fqb_feeder_fill_packed(fqb_feeder *f, int32_t n_max, int32_t stride, uint8_t *bases, uint8_t *quals,
+                               int32_t *lens, char *names, int32_t name_stride,
+                               int32_t packed_stride, uint8_t *packed, uint8_t *quals_flagged);
 void fqb_feeder_close(fqb_feeder *f);
 /* The feeder's gzip-stream path on a buffer: all members of gz[0..n_gz) decoded into out[0..cap), through text
  * blocks of block_bytes (<= 0: the feeder's 4 MiB) exactly as the feeder chains them; *n_out = bytes written.
