@@ -60,12 +60,12 @@ constexpr size_t kWarpSlab = 256u * 1024u;       // per-warp global slab: path o
 // shared memory of a block: kWarpsPerBlock x smem_ints words of DP rows / trace-back, then kWarpsPerBlock x ref_cap bytes of
 // reference codes, then kWarpsPerBlock x ops_cap bytes of path ops
 __device__ __forceinline__ WarpDp warp_scratch(const DpPool &pool, int32_t *smem, int smem_ints, int ref_cap, int ops_cap) {
-    const int wid = threadIdx.x >> 5;
+    const int wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;        // blocks of 1 .. kWarpsPerBlock warps (fewer when a warp's rows are large)
     WarpDp w;
     w.sm = smem + (size_t)wid * smem_ints; w.n_ints = smem_ints;
-    w.refc = reinterpret_cast<uint8_t *>(smem + (size_t)kWarpsPerBlock * smem_ints) + (size_t)wid * ref_cap; w.n_refc = ref_cap;
-    w.ops = reinterpret_cast<uint8_t *>(smem + (size_t)kWarpsPerBlock * smem_ints) + (size_t)kWarpsPerBlock * ref_cap + (size_t)wid * ops_cap; w.n_ops = ops_cap;
-    w.gb = pool.bytes + ((size_t)blockIdx.x * kWarpsPerBlock + wid) * kWarpSlab; w.n_bytes = (int)kWarpSlab;
+    w.refc = reinterpret_cast<uint8_t *>(smem + (size_t)wpb * smem_ints) + (size_t)wid * ref_cap; w.n_refc = ref_cap;
+    w.ops = reinterpret_cast<uint8_t *>(smem + (size_t)wpb * smem_ints) + (size_t)wpb * ref_cap + (size_t)wid * ops_cap; w.n_ops = ops_cap;
+    w.gb = pool.bytes + ((size_t)blockIdx.x * wpb + wid) * kWarpSlab; w.n_bytes = (int)kWarpSlab;
     w.lane = threadIdx.x & 31;
     return w;
 }
@@ -315,12 +315,16 @@ __global__ void finish_kernel(DpView v) {
 }
 
 // as many warp slabs as the byte pool holds, at most eight blocks per SM (pool.n_blocks = 2 per SM)
-static int warp_blocks(const DpPool &pool) {
+static int warp_blocks(const DpPool &pool, int wpb = kWarpsPerBlock) {
     const size_t pool_bytes = (size_t)pool.n_blocks * kDpThreads * pool.bytes_per_lane;
-    size_t nb = pool_bytes / (kWarpSlab * kWarpsPerBlock);
-    if (nb > (size_t)pool.n_blocks * 4) nb = (size_t)pool.n_blocks * 4;
+    size_t nb = pool_bytes / (kWarpSlab * wpb);
+    const size_t want = (size_t)pool.n_blocks * 16 / wpb;           // 32 warps per SM
+    if (nb > want) nb = want;
     return (int)(nb < 1 ? 1 : nb);
 }
+// warps per block: kWarpsPerBlock while a warp's share of shared memory is small; when it is large (long reads: the trace-back
+// of the refinement is 128 bytes per row) single-warp blocks pack an SM's shared memory without rounding losses
+static int warps_per_block(size_t smem_per_warp) { return smem_per_warp * kWarpsPerBlock <= 56u * 1024u ? kWarpsPerBlock : 1; }
 
 // ctr: [0] n_list [1] cursor [2] n_retry [3] retry cursor (device words)
 void launch_sw(const DpView &v, const SwParams *sp, const DpPool &pool, uint32_t *list, uint32_t *retry, uint32_t *ctr, uint32_t *err, void *huge_mem,
@@ -330,7 +334,8 @@ void launch_sw(const DpView &v, const SwParams *sp, const DpPool &pool, uint32_t
     if (ints < 17 * (max_read_len + 1)) ints = 17 * (max_read_len + 1);  // ... then the local region's global alignment: row constants + trace-back (64 B per row)
     const int ref_cap = kSwSmemInts;                                     // reference codes of the window, one byte each
     const int ops_cap = 768;                                             // path ops of the local region
-    const size_t smem = (size_t)ints * kWarpsPerBlock * 4 + (size_t)(ref_cap + ops_cap) * kWarpsPerBlock;
+    const int wpb = warps_per_block((size_t)ints * 4 + ref_cap + ops_cap);
+    const size_t smem = ((size_t)ints * 4 + (size_t)(ref_cap + ops_cap)) * wpb;
     // the rare very wide windows: buffers carved from huge_mem (launch_sw_huge_bytes())
     HugeBuf hb;
     char *hm = static_cast<char *>(huge_mem);
@@ -345,7 +350,7 @@ void launch_sw(const DpView &v, const SwParams *sp, const DpPool &pool, uint32_t
         sw_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, sp, pool, list, ctr, ctr + 1, err, huge_list, n_huge);
     else {
         cudaFuncSetAttribute(sw_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sw_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, sp, pool, list, ctr, ctr + 1, ints, ref_cap, ops_cap, retry, ctr + 2);
+        sw_warp_kernel<<<warp_blocks(pool, wpb), wpb * 32, smem, s>>>(v, sp, pool, list, ctr, ctr + 1, ints, ref_cap, ops_cap, retry, ctr + 2);
         sw_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, sp, pool, retry, ctr + 2, ctr + 3, err, huge_list, n_huge);
     }
     // windows wider than the per-lane scratch: sliced forward scan over all SMs, then the pair is finished by one warp
@@ -355,7 +360,7 @@ void launch_sw(const DpView &v, const SwParams *sp, const DpPool &pool, uint32_t
     cudaFuncSetAttribute(sw_huge_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
     sw_huge_scan_kernel<<<pool.n_blocks, 4 * 32, scan_smem, s>>>(v, sp, hb, scan_ints, scan_ref);
     cudaFuncSetAttribute(sw_huge_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    sw_huge_finish_kernel<<<8, kWarpsPerBlock * 32, smem, s>>>(v, sp, pool, huge_list, n_huge, hb, ints, ref_cap, ops_cap, err);
+    sw_huge_finish_kernel<<<8 * kWarpsPerBlock / wpb, wpb * 32, smem, s>>>(v, sp, pool, huge_list, n_huge, hb, ints, ref_cap, ops_cap, err);
 }
 size_t launch_sw_huge_bytes() {
     return 64 + kHugeMaxPairs * 4 + kHugeMaxJobs * sizeof(HugeJob) + (size_t)kHugeMaxSlices * 4 + (size_t)kHugeMaxSlices * sizeof(ScanBest);
@@ -366,15 +371,15 @@ void launch_refine(const DpView &v, const DpPool &pool, uint32_t *list, uint32_t
     int ints = 6 * wcols;                                                // row-chunk form: M/I/D rows, current and previous
     const int trace_ints = (wcols <= 129 ? 17 : 33) * (max_read_len + 1); // wavefront form: row constants + trace-back, 64 or 128 B per row
     if (ints < trace_ints) ints = trace_ints;
-    if ((size_t)ints * kWarpsPerBlock * 4 > 200u * 1024u) ints = (int)(200u * 1024u / (kWarpsPerBlock * 4));
     const int ref_cap = (wcols + 3) & ~3;                                // padded to a word
     const int ops_cap = (wcols + max_read_len + 2 + 3) & ~3;
-    const size_t smem = (size_t)ints * kWarpsPerBlock * 4 + (size_t)(ref_cap + ops_cap) * kWarpsPerBlock;
+    const int wpb = warps_per_block((size_t)ints * 4 + ref_cap + ops_cap);
+    const size_t smem = ((size_t)ints * 4 + (size_t)(ref_cap + ops_cap)) * wpb;
     cudaFuncSetAttribute(refine_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (getenv("FQB_DP_NO_WARP"))
         refine_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, pool, list, ctr, ctr + 1, err);
     else {
-        refine_warp_kernel<<<warp_blocks(pool), kWarpsPerBlock * 32, smem, s>>>(v, pool, list, ctr, ctr + 1, ints, ref_cap, ops_cap, retry, ctr + 2);
+        refine_warp_kernel<<<warp_blocks(pool, wpb), wpb * 32, smem, s>>>(v, pool, list, ctr, ctr + 1, ints, ref_cap, ops_cap, retry, ctr + 2);
         refine_kernel<<<pool.n_blocks, kDpThreads, 0, s>>>(v, pool, retry, ctr + 2, ctr + 3, err);
     }
     finish_kernel<<<(v.n_reads + 255) / 256, 256, 0, s>>>(v);
