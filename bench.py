@@ -339,7 +339,12 @@ def main_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        # wait for the sampler's first line: on a fresh box nvidia-smi takes a second to initialise NVML, and that start-up holds
+        # driver locks -- inside the timed region it showed up as a one-off 100 ms stall of the first arm
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 10.0:
+            time.sleep(0.05)
+        time.sleep(0.2)
     ms, ctr, launches, t0, t1, rq = timed(False)
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     merge_ms_device = merge_ms[-1]
