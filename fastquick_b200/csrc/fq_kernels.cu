@@ -277,7 +277,7 @@ __device__ __forceinline__ void warp_shadow(Lane &lane, bool has_hit, int lane_i
     __syncwarp();
 }
 
-template <typename HeadT, bool kFreeList, int kMinBlocks = 5>
+template <typename HeadT, bool kFreeList, int kMinBlocks = 640 / kSearchThreads>
 __global__ void __launch_bounds__(kSearchThreads, kMinBlocks) search_kernel(const __grid_constant__ BatchView b, const __grid_constant__ WidthView wv,
                                                                             const __grid_constant__ SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -393,7 +393,7 @@ int search_grid_blocks(int n_buckets, bool heads16, int device) {
     return n_sm * per_sm;
 }
 
-template <typename HeadT, bool kFreeList, int kMinBlocks = 5>
+template <typename HeadT, bool kFreeList, int kMinBlocks = 640 / kSearchThreads>
 static void launch_search_t(const BatchView &b, const WidthView &wv, const SearchParams &p, int n_blocks, cudaStream_t s) {
     size_t smem = (size_t)p.opt.n_buckets * kSearchThreads * sizeof(HeadT);
     cudaFuncSetAttribute(search_kernel<HeadT, kFreeList, kMinBlocks>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

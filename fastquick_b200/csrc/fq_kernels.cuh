@@ -64,6 +64,9 @@ void launch_width(const BatchView &b, const WidthView &wv, const DevBwt bwt[2], 
 // returns the number of thread blocks launched (persistent grid); heads16 selects the 16-bit head table
 int search_grid_blocks(int n_buckets, bool heads16, int device);
 void launch_search(const BatchView &b, const WidthView &wv, const SearchParams &p, bool heads16, bool free_list, int n_blocks, cudaStream_t s);
-constexpr int kSearchThreads = 128;
+#ifndef FQB_SEARCH_THREADS
+#define FQB_SEARCH_THREADS 128
+#endif
+constexpr int kSearchThreads = FQB_SEARCH_THREADS;      // 5 blocks of 128 per SM; a development build may pass another block size
 
 }  // namespace fqb
