@@ -51,6 +51,10 @@ constexpr int kAlnCapSlow = 1024;       // per read in the overflow pass
 constexpr uint32_t kArenaFast = 4096;   // stack entries per lane in the fast pass (bump-allocated; pushes/read ~300 mean)
 constexpr uint32_t kArenaMid = 60000;   // overflow tier 1 (still 16-bit bucket heads)
 constexpr int kMidBlocks = 16;
+// Batch sets (everything the align stage of a batch writes).  Three were measured as well (the align stage of batch n+2 then does
+// not wait for the later stages of batch n): the searches overlap more, the later stages get less room, the step stays at 24.5 ms
+// (profiles/r02_pipeline_timeline.md) -- two it is, at 13 GB each.
+constexpr int kSets = 2;
 constexpr int kSpillCap = 16384;        // reads per batch that may need the overflow tiers (rows of d_aln_big); more is a limit error
 constexpr int kPenaltyCap = 1 << 16;    // entries of the pairing penalty table (index = insert size <= high_bayesian)
 // BatchSet::d_ctrs: [0] n_work [1] queue cursor [2] overflow reads of the fast pass; tier t (1, 2): [4t] n_work [4t+1] cursor
@@ -97,11 +101,11 @@ struct fqb_handle {
         bool rq_pending = false;
         bool pre_valid = false;                     // staging holds a batch uploaded by fqb_prefetch_pairs, not consumed yet
         const void *pre_key[4] = {nullptr, nullptr, nullptr, nullptr}; int pre_pairs = 0, pre_stride = 0;
-    } sets[2];
+    } sets[kSets];
     int cur = 0;                                    // set the stage-level calls work on
-    int fifo[2] = {-1, -1}; int n_fifo = 0;         // sets submitted (fqb_submit_pairs) and not collected yet, oldest first
+    int fifo[kSets] = {}; int n_fifo = 0;         // sets submitted (fqb_submit_pairs) and not collected yet, oldest first
     cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
-    cudaStream_t align_stream[2] = {nullptr, nullptr};   // one per batch set: the search of batch n+1 fills the SMs the draining tail of batch n leaves idle
+    cudaStream_t align_stream[kSets] = {};   // one per batch set: the search of batch n+1 fills the SMs the draining tail of batch n leaves idle
     cudaEvent_t ev_rows[3] = {nullptr, nullptr, nullptr};   // rows final on the main stream / split done / copies done
     double rq_ms = 0.0; uint64_t rq_launches = 0;   // accumulated device time of the rank-query launches
     BatchView bv;
@@ -114,9 +118,9 @@ struct fqb_handle {
     unsigned long long *d_counters = nullptr;
     // search infrastructure
     int n_blocks16 = 0;
-    uint4 *d_arena[2] = {nullptr, nullptr};       // stack arenas of the fast pass and of the two overflow tiers, per batch set
-    uint4 *d_arena_big[2] = {nullptr, nullptr};   // (two align stages may be on the device at once)
-    uint4 *d_arena_mid[2] = {nullptr, nullptr};
+    uint4 *d_arena[kSets] = {};       // stack arenas of the fast pass and of the two overflow tiers, per batch set
+    uint4 *d_arena_big[kSets] = {};   // (two align stages may be on the device at once)
+    uint4 *d_arena_mid[kSets] = {};
     Hit *d_aln_big = nullptr;
     int32_t *d_spill_slot = nullptr;     // per read: row in d_aln_big or -1
     SearchOpt sopt;
@@ -141,6 +145,9 @@ struct fqb_handle {
     bool status_pending = false;
     std::string cb_error;                                  // set by the host callback (read after a synchronisation)
     uint64_t tuples_bound = 0;                             // upper bound of the pile-up entries on the device
+    // FQB_TIMELINE=1 (development): timing events per batch -- [0] align stage enqueued point reached, [1] search done,
+    // [2] later stages start, [3] later stages done -- printed relative to the first by fqb_rows_wait
+    std::vector<cudaEvent_t> tl_ev; cudaEvent_t tl_base = nullptr;
     // multi-GPU (row e): rank in the sharded run, the NCCL communicator of the end-of-run merge, and the hand-off ring's
     // mailboxes (my own, and the next rank's mapped into this address space: IPC or peer access)
     struct RingBox { unsigned long long words[7]; unsigned int seq, pad_; };
@@ -483,7 +490,7 @@ void fqb_destroy(fqb_handle *h) {
     free_batch(h);
     for (int s = 0; s < 2; ++s) { cudaFree(h->d_blocks[s]); cudaFree(h->d_sa[s]); }
     cudaFree(h->d_pac); cudaFree(h->d_roll); cudaFree(h->d_maxdiff); cudaFree(h->d_counters);
-    for (int k = 0; k < 2; ++k) { cudaFree(h->d_arena[k]); cudaFree(h->d_arena_mid[k]); cudaFree(h->d_arena_big[k]); }
+    for (int k = 0; k < kSets; ++k) { cudaFree(h->d_arena[k]); cudaFree(h->d_arena_mid[k]); cudaFree(h->d_arena_big[k]); }
     for (auto &B : h->sets) {
         cudaFree(B.d_ctrs); cudaFree(B.d_order_bins);
         for (cudaEvent_t e : {B.ev_in, B.ev_free, B.ev_align, B.ev_done, B.ev_rq[0], B.ev_rq[1]}) if (e) cudaEventDestroy(e);
@@ -838,12 +845,12 @@ static int stage_load_impl(fqb_handle *h, int32_t n_pairs, int32_t stride, const
     if (rc) return rc;
     // the set holding this batch's prefetched upload, else the current one (unless ITS staging holds another prefetched batch)
     int si = h->cur;
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < kSets; ++k) {
         const fqb_handle::BatchSet &B = h->sets[k];
         if (!on_device && B.pre_valid && B.pre_pairs == n_pairs && B.pre_stride == stride && B.pre_key[0] == bases1 && B.pre_key[1] == quals1 &&
             B.pre_key[2] == bases2 && B.pre_key[3] == quals2) si = k;
     }
-    if (!on_device && h->sets[si].pre_valid && h->sets[si].pre_key[0] != bases1) si = 1 - si;
+    if (!on_device && h->sets[si].pre_valid && h->sets[si].pre_key[0] != bases1) si = (si + 1) % kSets;
     CU_CHECK(cudaStreamWaitEvent(h->stream, h->sets[si].ev_done, 0));
     rc = load_set(h, si, h->stream, n_pairs, stride, bases1, quals1, lens1, bases2, quals2, lens2, on_device, packed_stride);
     if (rc) return rc;
@@ -1616,6 +1623,9 @@ int fqb_collect_pairs_sharded(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows
     h->pairs_seen = first_pair;
     cudaStream_t st = h->stream;
     CU_CHECK(cudaStreamWaitEvent(st, h->sets[si].ev_align, 0));
+    static const bool tl_on = getenv("FQB_TIMELINE") != nullptr;
+    auto tl_mark = [&](cudaStream_t s_) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); h->tl_ev.push_back(e); };
+    if (tl_on) tl_mark(st);
     const bool ring = h->comm_world > 1;
     const unsigned int recv_seq = ring && global_batch > 0 ? (h->ring_epoch << 20 | (unsigned int)(global_batch & 0xfffffu)) : 0u;
     const unsigned int send_seq = ring && !is_last ? (h->ring_epoch << 20 | (unsigned int)((global_batch + 1) & 0xfffffu)) : 0u;
@@ -1630,6 +1640,7 @@ int fqb_collect_pairs_sharded(fqb_handle *h, fqb_read_t *rows1, fqb_read_t *rows
     if (rc) return rc;
     h->stats_done = h->stats_open;
     CU_CHECK(cudaEventRecord(h->sets[si].ev_done, st));
+    if (tl_on) tl_mark(st);
     return FQB_OK;
 }
 
@@ -1849,6 +1860,13 @@ int fqb_rows_wait(fqb_handle *h) {
     if (!h) { set_error("null handle"); return FQB_ERR_ARG; }
     CU_CHECK(cudaSetDevice(h->device));
     CU_CHECK(cudaEventSynchronize(h->ev_rows[2]));
+    if (h->tl_base && !h->tl_ev.empty()) {
+        cudaDeviceSynchronize();
+        fprintf(stderr, "timeline (ms since the first submit; events in enqueue order: per submit [align start, align end], per collect [later start, later end])\n");
+        for (size_t k = 0; k < h->tl_ev.size(); ++k) { float ms = 0; cudaEventElapsedTime(&ms, h->tl_base, h->tl_ev[k]); fprintf(stderr, " %.2f", ms); cudaEventDestroy(h->tl_ev[k]); }
+        fprintf(stderr, "\n");
+        h->tl_ev.clear(); cudaEventDestroy(h->tl_base); h->tl_base = nullptr;
+    }
     return sync_and_check(h);            // also reports what the device flagged for the batches completed since the last check
 }
 
@@ -2131,7 +2149,7 @@ int fqb_prefetch_pairs(fqb_handle *h, int32_t n_pairs, int32_t stride, const uin
     // into the staging arrays of the set that is not current, unless they still hold a prefetched batch nobody has
     // loaded yet (the documented call order is prefetch(n+1) before align(n)): then the current set's, free once its
     // prep_kernel has run
-    int si = 1 - h->cur;
+    int si = (h->cur + 1) % kSets;
     if (h->sets[si].pre_valid) si = h->cur;
     fqb_handle::BatchSet &B = h->sets[si];
     if (B.pre_valid) return FQB_OK;                  // both hold unconsumed uploads: nothing to do, the load will copy
@@ -2196,7 +2214,13 @@ static int submit_impl(fqb_handle *h, int32_t n_pairs, int32_t stride, const uin
     }
     // the set that is neither waiting in the queue nor (as the current set) possibly still read by the later stages of the
     // batch collected last: with one batch queued that is the other one; ev_done orders us behind those stages
-    const int si = h->n_fifo ? 1 - h->fifo[0] : 1 - h->cur;
+    int si = -1;
+    for (int k = 1; k <= kSets && si < 0; ++k) {
+        const int c = (h->cur + k) % kSets;          // prefer a set other than the current one (k == kSets: the current one itself)
+        bool queued = false;
+        for (int q = 0; q < h->n_fifo; ++q) queued |= h->fifo[q] == c;
+        if (!queued) si = c;
+    }
     fqb_handle::BatchSet &B = h->sets[si];
     cudaStream_t ast = h->align_stream[si];
     CU_CHECK(cudaStreamWaitEvent(ast, B.ev_done, 0));
@@ -2206,8 +2230,12 @@ static int submit_impl(fqb_handle *h, int32_t n_pairs, int32_t stride, const uin
     if (rc) return rc;
     CU_CHECK(cudaEventRecord(B.ev_in, h->copy_stream));
     CU_CHECK(cudaStreamWaitEvent(ast, B.ev_in, 0));
+    static const bool tl_on = getenv("FQB_TIMELINE") != nullptr;
+    auto tl_mark = [&](cudaStream_t s_) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); h->tl_ev.push_back(e); };
+    if (tl_on) { if (!h->tl_base) { cudaEventCreate(&h->tl_base); cudaEventRecord(h->tl_base, ast); } tl_mark(ast); }
     if ((rc = enqueue_align(h, si, ast))) return rc;
     CU_CHECK(cudaEventRecord(B.ev_align, ast));
+    if (tl_on) tl_mark(ast);
     h->fifo[h->n_fifo++] = si;
     return FQB_OK;
 }
