@@ -48,7 +48,7 @@ using namespace fqb;
 namespace {
 constexpr int kAlnCapFast = 8;          // hits kept per read in the fast pass
 constexpr int kAlnCapSlow = 1024;       // per read in the overflow pass
-constexpr uint32_t kArenaFast = 4096;   // stack entries per lane in the fast pass (bump-allocated; pushes/read ~300 mean)
+constexpr uint32_t kArenaFast = 4096;   // stack entries per lane in the fast pass (bump-allocated; pushes/read ~300 mean); twice that for reads over 128 bases
 constexpr uint32_t kArenaMid = 60000;   // overflow tier 1 (still 16-bit bucket heads)
 constexpr int kMidBlocks = 16;
 // Batch sets (everything the align stage of a batch writes).  Three were measured as well (the align stage of batch n+2 then does
@@ -121,6 +121,7 @@ struct fqb_handle {
     uint4 *d_arena[kSets] = {};       // stack arenas of the fast pass and of the two overflow tiers, per batch set
     uint4 *d_arena_big[kSets] = {};   // (two align stages may be on the device at once)
     uint4 *d_arena_mid[kSets] = {};
+    uint32_t arena_fast_alloc[kSets] = {};        // entries per lane d_arena[k] was allocated with
     Hit *d_aln_big = nullptr;
     int32_t *d_spill_slot = nullptr;     // per read: row in d_aln_big or -1
     SearchOpt sopt;
@@ -562,11 +563,18 @@ static int enqueue_align(fqb_handle *h, int si, cudaStream_t st) {
 
     h->sopt = make_search_opt(h->gopt, B.stride);
     if (h->sopt.n_buckets > 128) { set_error("more than 128 score buckets"); return FQB_ERR_LIMIT; }
+    // Fast-pass arena: 4,096 entries per lane hold every read of a 2 x 100 bp batch; of 150-base reads (twice the pushes) about one
+    // per batch outgrows that, and its overflow tier is a single 10-ms chain behind the search (2x150_10k: 54.8 ms per step
+    // against 51.4 with 8,192 entries, 52.1 with 16,384).  FQB_DEBUG_ARENA_FAST pins the size (tests of the tiers).
+    const bool arena_pinned = getenv("FQB_DEBUG_ARENA_FAST") != nullptr;
+    const uint32_t want_fast = arena_pinned ? h->arena_fast : (B.stride > 128 ? 2 * kArenaFast : kArenaFast);
+    if (h->d_arena[si] && h->arena_fast_alloc[si] < want_fast) { CU_CHECK(cudaFree(h->d_arena[si])); h->d_arena[si] = nullptr; }   // longer reads than before
     if (!h->d_arena[si]) {
-        h->n_blocks16 = search_grid_blocks(h->sopt.n_buckets, true, h->device);
-        CU_CHECK(cudaMalloc(&h->d_arena[si], (size_t)h->n_blocks16 * kSearchThreads * h->arena_fast * sizeof(uint4)));
-        CU_CHECK(cudaMalloc(&h->d_arena_mid[si], (size_t)kMidBlocks * kSearchThreads * h->arena_mid * sizeof(uint4)));
-        CU_CHECK(cudaMalloc(&h->d_arena_big[si], (size_t)kSearchThreads * ((size_t)h->gopt.max_entries + 64) * sizeof(uint4)));
+        if (!h->n_blocks16) h->n_blocks16 = search_grid_blocks(h->sopt.n_buckets, true, h->device);
+        CU_CHECK(cudaMalloc(&h->d_arena[si], (size_t)h->n_blocks16 * kSearchThreads * want_fast * sizeof(uint4)));
+        h->arena_fast_alloc[si] = want_fast;
+        if (!h->d_arena_mid[si]) CU_CHECK(cudaMalloc(&h->d_arena_mid[si], (size_t)kMidBlocks * kSearchThreads * h->arena_mid * sizeof(uint4)));
+        if (!h->d_arena_big[si]) CU_CHECK(cudaMalloc(&h->d_arena_big[si], (size_t)kSearchThreads * ((size_t)h->gopt.max_entries + 64) * sizeof(uint4)));
     }
     SearchParams sp;
     sp.bwt[0] = h->dbwt[0]; sp.bwt[1] = h->dbwt[1];
@@ -578,7 +586,7 @@ static int enqueue_align(fqb_handle *h, int si, cudaStream_t st) {
         h->n_launches += 2;
         sp.work = B.d_work_sorted;
     }
-    sp.arena = h->d_arena[si]; sp.arena_cap = h->arena_fast;
+    sp.arena = h->d_arena[si]; sp.arena_cap = h->arena_fast_alloc[si];
     sp.aln = B.d_aln; sp.aln_cap = kAlnCapFast; sp.n_aln = B.d_naln; sp.aln_row = nullptr;
     sp.overflow = B.d_overflow; sp.n_overflow = B.d_ctrs + 2;
     sp.counters = h->d_counters;
