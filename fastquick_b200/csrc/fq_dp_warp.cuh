@@ -164,6 +164,8 @@ __device__ GlobalResult warp_global_any(const RefWin &R, int r0, int len1, const
     const int avail = w.n_ints * 4 - (len2 + 1) * 4;
     if (len1 <= 32 * 4 && len2 * 64 <= avail)
         return wave_global_align<4, uint16_t>(w.refc, r0, len1, Q, q0, len2, gap_end, band, w.sm, reinterpret_cast<uint16_t *>(w.sm + len2 + 1), len2, w.ops, w.n_ops, w.lane);
+    if (len1 <= 32 * 5 && len2 * 128 <= avail)       // the fewest columns per lane that fit 32 lanes: a step costs 30 + 37 CT instructions
+        return wave_global_align<5, uint32_t>(w.refc, r0, len1, Q, q0, len2, gap_end, band, w.sm, reinterpret_cast<uint32_t *>(w.sm + len2 + 1), len2, w.ops, w.n_ops, w.lane);
     if (len1 <= 32 * 6 && len2 * 128 <= avail)
         return wave_global_align<6, uint32_t>(w.refc, r0, len1, Q, q0, len2, gap_end, band, w.sm, reinterpret_cast<uint32_t *>(w.sm + len2 + 1), len2, w.ops, w.n_ops, w.lane);
     if (len1 <= 32 * 8 && len2 * 128 <= avail)
