@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(4 * 32) sw_huge_scan_kernel(DpView v, const Sw
     }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) sw_huge_finish_kernel(DpView v, const SwParams *spp, DpPool pool, const uint32_t *huge_list, const uint32_t *n_huge,
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) sw_huge_finish_kernel(DpView v, const SwParams *spp, DpPool pool, const uint32_t *huge_list, const uint32_t *n_huge,
                                                                               HugeBuf hb, int smem_ints, int ref_cap, int ops_cap, uint32_t *err) {
     const SwParams sp = *spp;
     extern __shared__ int32_t dp_smem[];

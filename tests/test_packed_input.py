@@ -137,3 +137,34 @@ def test_packed_calls_equal_ascii_calls(small_index):
         for e in (0, 1):
             assert out[mode][e].tobytes() == out["ascii"][e].tobytes(), (mode, e)
     assert int((out["ascii"][0]["type"] != 0).sum()) > 4000          # the batch did align
+
+
+@pytest.mark.gpu
+def test_packed_single_end_and_150_bases(small_index):
+    """Single-end input (no second reads) and 150-base reads (48-byte packed rows, three 128-bit loads) in the packed form."""
+    lib = fx.host_lib()
+    g = _abi.GapOpt()
+    lib.fqb_gap_opt_default(C.byref(g))
+    g.trim_qual = 15
+    for L, single in ((100, True), (150, False), (150, True)):
+        n = 3000
+        arrs = small_index.reads(n, read_len=L, seed=900 + L, sub_rate=0.015, ins_rate=0.003, del_rate=0.003)
+        arrs[0][::11, 5] = ord("N")
+        ps, pk1, qf1 = pack(lib, arrs[0], arrs[1])
+        _, pk2, qf2 = pack(lib, arrs[2], arrs[3])
+        out = []
+        for packed in (False, True):
+            h = C.c_void_p()
+            assert lib.fqb_create(small_index.prefix.encode(), C.byref(g), None, 0, C.byref(h)) == 0, lib.fqb_last_error()
+            rows = [np.zeros(n, _abi.READ_DTYPE) for _ in range(2)]
+            r1, r2 = rows[0].ctypes.data_as(C.c_void_p), rows[1].ctypes.data_as(C.c_void_p)
+            if packed:
+                rc = lib.fqb_align_pairs_packed(h, n, L, ps, _abi.u8p(pk1), _abi.u8p(qf1), None, None if single else _abi.u8p(pk2), None if single else _abi.u8p(qf2), None, r1, r2, None)
+            else:
+                rc = lib.fqb_align_pairs(h, n, L, _abi.u8p(arrs[0]), _abi.u8p(arrs[1]), None, None if single else _abi.u8p(arrs[2]), None if single else _abi.u8p(arrs[3]), None, r1, r2, None)
+            assert rc == 0, lib.fqb_last_error()
+            lib.fqb_destroy(h)
+            out.append(rows)
+        assert out[0][0].tobytes() == out[1][0].tobytes(), (L, single)
+        assert out[0][1].tobytes() == out[1][1].tobytes(), (L, single)
+        assert int((out[0][0]["type"] != 0).sum()) > n // 2
