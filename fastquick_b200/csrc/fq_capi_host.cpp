@@ -134,13 +134,19 @@ int fqb_pack_reads(int64_t n, int32_t stride, const uint8_t *bases, const uint8_
         const uint8_t *b = bases + (size_t)r * stride, *q = quals + (size_t)r * stride;
         uint32_t *w = reinterpret_cast<uint32_t *>(packed_out + (size_t)r * packed_stride);
         uint8_t *qo = quals_out + (size_t)r * stride;
-        for (int k = 0; k < packed_stride / 4; ++k) w[k] = 0;
-        for (int j = 0; j < stride; ++j) {
-            if (q[j] & 0x80u) { fqb::set_error("fqb_pack_reads: a quality byte above 127"); return FQB_ERR_ARG; }
-            const uint32_t c = nt4[b[j]];
-            w[j >> 4] |= (c & 3u) << (2 * (j & 15));          // c - 4 for the codes above 3: 0 = N, 1 = '-'
-            qo[j] = (uint8_t)(q[j] | (c > 3 ? 0x80u : 0u));
+        uint32_t q_or = 0;
+        for (int k = 0, j = 0; k < packed_stride / 4; ++k) {   // one word (16 bases) at a time
+            uint32_t acc = 0;
+            const int end = j + 16 < stride ? j + 16 : stride;
+            for (int sh = 0; j < end; ++j, sh += 2) {
+                const uint32_t c = nt4[b[j]];
+                acc |= (c & 3u) << sh;                        // c - 4 for the codes above 3: 0 = N, 1 = '-'
+                q_or |= q[j];
+                qo[j] = (uint8_t)(q[j] | ((c & 4u) << 5));    // codes 4 and 5 -> bit 7
+            }
+            w[k] = acc;
         }
+        if (q_or & 0x80u) { fqb::set_error("fqb_pack_reads: a quality byte above 127"); return FQB_ERR_ARG; }
     }
     return FQB_OK;
 }

@@ -268,13 +268,19 @@ bool parse_record(const char *p, const char *end, const Batch &B, int slot, Fail
     if (B.packed) {
         uint32_t *w = reinterpret_cast<uint32_t *>(B.packed + (size_t)slot * B.packed_stride);
         uint8_t *qf = B.qflag + (size_t)slot * B.stride;
-        for (int k = 0; k < B.packed_stride / 4; ++k) w[k] = 0;
-        for (int j = 0; j < B.stride; ++j) {
-            if (q[j] & 0x80u) { fail.raise("quality byte above 127 in a FASTQ record"); return false; }
-            const uint32_t c = kNt4.t[b[j]];
-            w[j >> 4] |= (c & 3u) << (2 * (j & 15));
-            qf[j] = (uint8_t)(q[j] | (c > 3 ? 0x80u : 0u));
+        uint32_t q_or = 0;
+        for (int k = 0, j = 0; k < B.packed_stride / 4; ++k) {          // one word (16 bases) at a time, accumulated in a register
+            uint32_t acc = 0;
+            const int end = j + 16 < B.stride ? j + 16 : B.stride;
+            for (int sh = 0; j < end; ++j, sh += 2) {
+                const uint32_t c = kNt4.t[b[j]];
+                acc |= (c & 3u) << sh;
+                q_or |= q[j];
+                qf[j] = (uint8_t)(q[j] | ((c & 4u) << 5));              // codes 4 and 5 -> bit 7
+            }
+            w[k] = acc;
         }
+        if (q_or & 0x80u) { fail.raise("quality byte above 127 in a FASTQ record"); return false; }
     }
     const char *nb = l[0] + 1, *ne = nb;
     while (ne < e[0] && *ne != ' ' && *ne != '\t') ++ne;
