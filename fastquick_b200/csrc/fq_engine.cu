@@ -51,10 +51,12 @@ constexpr int kAlnCapSlow = 1024;       // per read in the overflow pass
 constexpr uint32_t kArenaFast = 4096;   // stack entries per lane in the fast pass (bump-allocated; pushes/read ~300 mean); twice that for reads over 128 bases
 constexpr uint32_t kArenaMid = 60000;   // overflow tier 1 (still 16-bit bucket heads)
 constexpr int kMidBlocks = 16;
-// Batch sets (everything the align stage of a batch writes).  Three were measured as well (the align stage of batch n+2 then does
-// not wait for the later stages of batch n): the searches overlap more, the later stages get less room, the step stays at 24.5 ms
-// (profiles/r02_pipeline_timeline.md) -- two it is, at 13 GB each.
-constexpr int kSets = 2;
+// Batch sets (everything the align stage of a batch writes).  With two, the align stage of batch n+2 waits for the later stages of
+// batch n; with three it does not, so two align stages can be on the device beside the later stages of a third batch.  On the
+// alignment-bound workloads that changes nothing (the device is saturated: 24.5 ms per step either way), but where the align stage
+// is one long dependent chain -- filter-bound input, where a few 5,000-step reads are all the search has -- the chains of
+// consecutive batches overlap: wgs_mix 5.2 -> 4.2 ms per step (profiles/r02_pipeline_timeline.md).  13 GB per set at 100 bases.
+constexpr int kSets = 3;
 constexpr int kSpillCap = 16384;        // reads per batch that may need the overflow tiers (rows of d_aln_big); more is a limit error
 constexpr int kPenaltyCap = 1 << 16;    // entries of the pairing penalty table (index = insert size <= high_bayesian)
 // BatchSet::d_ctrs: [0] n_work [1] queue cursor [2] overflow reads of the fast pass; tier t (1, 2): [4t] n_work [4t+1] cursor
