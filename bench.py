@@ -28,6 +28,8 @@ from fastquick_b200 import _abi  # noqa: E402
 
 BATCH = _abi.FQB_BATCH_PAIRS
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "FASTQuick_ref")
+CLI_BIN = os.path.join(ROOT, "fastquick_b200", "FASTQuick_b200")
+CLI_SAMPLE_BATCHES = 6           # batches of the workload the command-line leg runs (FASTQ text on disk: 2 x 220 B per pair)
 NCU_DRAM_BYTES_PER_LAUNCH = 7.315e9   # search_kernel, one 262,144-pair launch of 2x100_10k: 3.476 GB read + 3.840 GB written (ncu capture r2a)
 REF_SAMPLE_PAIRS = 32768         # pairs per step of the reference arm / cpu_baseline sample unit
 STAGES = ("prep + k-mer filter + cal_width + match_gap + aln2seq/bwt_sa/mapQ + infer_isize + pairing + mate-rescue SW + gapped refinement + "
@@ -155,6 +157,63 @@ def run_reference_sample(lib, synth, workdir, first_pair, n_pairs, index_prefix=
         except OSError:
             pass
     return n_pairs / sec, sec, cores
+
+
+def write_fastq_text(path, end, first_pair, bases, quals):
+    """Plain-text FASTQ of one end (the records fqb_write_fastq_gz writes: @r%011d/<end>, bases, +, qualities), built with numpy."""
+    n, L = bases.shape
+    head = 16                                              # "@r" + 11 digits + "/e\n"
+    rec = np.empty((n, head + L + 3 + L + 1), np.uint8)
+    rec[:, 0], rec[:, 1] = ord("@"), ord("r")
+    idx = np.arange(first_pair, first_pair + n, dtype=np.int64)
+    for k in range(11):
+        rec[:, 12 - k] = (idx // 10 ** k) % 10 + 48
+    rec[:, 13], rec[:, 14], rec[:, 15] = ord("/"), 48 + end, 10
+    rec[:, head:head + L] = bases
+    rec[:, head + L:head + L + 3] = np.frombuffer(b"\n+\n", np.uint8)
+    rec[:, head + L + 3:head + 2 * L + 3] = quals
+    rec[:, -1] = 10
+    with open(path, "wb") as f:
+        f.write(rec.tobytes())
+
+
+def run_cli_sample(lib, synth, workdir, n_pairs):
+    """`FASTQuick_b200 align` -- the reference's command line on this library, FASTQ files in, statistics files and BAM out --
+    on n_pairs of the workload as plain-text FASTQ; returns pairs/s by the CLI's own 'Processed Pair End mapping' line (what
+    the reference arm reports for FASTQuick_ref) without and with BAM output."""
+    index_prefix = os.path.join(workdir, "bench.FASTQuick.fa")
+    if not os.path.exists(index_prefix + ".rollhash"):
+        assert lib.fqb_synth_write_inputs(synth, workdir.encode()) == 0, lib.fqb_last_error()
+        assert lib.fqb_synth_write_index(synth, os.path.join(workdir, "genome.fa").encode(),
+                                         os.path.join(workdir, "dbsnp.vcf").encode(), index_prefix.encode(), 1) == 0, lib.fqb_last_error()
+    fq = [os.path.join(workdir, "cli_%d.fq" % (e + 1)) for e in (0, 1)]
+    files = [open(p, "wb") for p in fq]
+    for f in files:
+        f.close()
+    chunk = BATCH
+    for first in range(0, n_pairs, chunk):                 # the reads of bench steps 0, 1, ...: same generator, same seeds
+        arrs = gen_reads(lib, synth, first, min(chunk, n_pairs - first))
+        for e in (0, 1):
+            part = fq[e] + ".part"
+            write_fastq_text(part, e + 1, first, arrs[2 * e], arrs[2 * e + 1])
+            with open(fq[e], "ab") as dst, open(part, "rb") as src:
+                dst.write(src.read())
+            os.remove(part)
+    out = {}
+    for tag, extra in (("stats", ["--sam_out"]), ("stats+bam", [])):
+        cmd = [CLI_BIN, "align", "--fastq_1", fq[0], "--fastq_2", fq[1], "--index_prefix", index_prefix[: -len(".FASTQuick.fa")],
+               "--out_prefix", os.path.join(workdir, "cli_out"), "--t", str(os.cpu_count() or 1), "--q", "15"] + extra
+        r = subprocess.run(cmd, cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+        m = re.search(r"Processed Pair End mapping in ([0-9.]+) sec", r.stdout)
+        if r.returncode or not m:
+            raise RuntimeError("FASTQuick_b200 align failed:\n" + r.stdout[-1500:])
+        out[tag] = n_pairs / float(m.group(1))
+    for f in fq + [os.path.join(workdir, "cli_out.bam")]:
+        try:
+            os.remove(f)
+        except OSError:
+            pass
+    return out
 
 
 def main_reference(args):
@@ -426,9 +485,24 @@ def main_gpu(args):
                      "occ_block_touches_per_s_job": touches_per_s_job},
         "exchange_ms": merge_ms_device,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    lib.fqb_destroy(h)                   # the host legs below run other processes on this GPU / these cores
+    workc = None
+    if world == 1 and not args.no_cli:
+        # like for like with the reference arm (its timer covers FASTQ decoding, the statistics text and the BAM): the same
+        # command line, on this library, timed by the same log line
         try:
             workc = tempfile.mkdtemp(prefix="fqb_cpu_")
+            n_c = CLI_SAMPLE_BATCHES * BATCH
+            rates = run_cli_sample(lib, synth, workc, n_c)
+            line["cli"] = {"value": rates["stats+bam"], "unit": "read-pairs/s", "value_without_bam": rates["stats"], "pairs": n_c,
+                           "what": "FASTQuick_b200 align --device 0 on %d pairs of the workload as plain-text FASTQ (feeder, upload, all stages, "
+                                   "InsertSizeTable text, BAM), by its 'Processed Pair End mapping' line; index load and the final "
+                                   "ProcessCore files excluded, as in the reference arm" % n_c}
+        except Exception as ex:
+            line["cli"] = {"value": None, "unit": "read-pairs/s", "what": "failed: %s" % str(ex)[:300]}
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            workc = workc or tempfile.mkdtemp(prefix="fqb_cpu_")
             n_s = REF_SAMPLE_PAIRS
             if os.path.exists(REF_BIN):
                 rate, sec, cores = run_reference_sample(lib, synth, workc, 0, n_s)
@@ -440,7 +514,6 @@ def main_gpu(args):
         except Exception as ex:  # the GPU numbers stand on their own
             line["cpu_baseline"] = {"value": None, "unit": "read-pairs/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % str(ex)[:200]}
     print(json.dumps(line))
-    lib.fqb_destroy(h)
     if world > 1:
         dist.destroy_process_group()
 
@@ -454,6 +527,7 @@ def main():
     ap.add_argument("--config", default="2x100_10k", choices=sorted(CONFIGS), help="workload (default: BASELINE.json configs[1], the contract line)")
     ap.add_argument("--pairs-per-step", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip the FASTQuick_b200 command-line leg (FASTQ files in, statistics files / BAM out)")
     ap.add_argument("--ascii-input", action="store_true", help="hand the batches over as ASCII rows instead of the packed form")
     args = ap.parse_args()
     select_config(args.config)

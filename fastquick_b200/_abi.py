@@ -75,7 +75,7 @@ assert READ_DTYPE.itemsize == 96, READ_DTYPE.itemsize
 EXPORTED_SYMBOLS = [
     "fqb_gap_opt_default", "fqb_pe_opt_default", "fqb_create", "fqb_destroy", "fqb_last_error",
     "fqb_index_info", "fqb_kmer_tables_origin", "fqb_kmer_tables_fetch", "fqb_align_pairs", "fqb_prefetch_pairs", "fqb_prefetch_hits", "fqb_submit_pairs", "fqb_collect_pairs", "fqb_packed_stride", "fqb_pack_reads", "fqb_align_pairs_packed", "fqb_stage_load_packed", "fqb_submit_pairs_packed", "fqb_comm_ring_handle", "fqb_comm_unique_id", "fqb_comm_init", "fqb_comm_init_local", "fqb_collect_pairs_sharded", "fqb_comm_merge_stats", "fqb_bam_open", "fqb_bam_emit", "fqb_bam_emit2", "fqb_bam_attach", "fqb_bam_close",
-    "fqb_stage_load", "fqb_stage_align", "fqb_get_stream_state", "fqb_set_stream_state", "fqb_set_pair_base", "fqb_stats_group_bytes", "fqb_stats_export", "fqb_stats_import",
+    "fqb_stage_load", "fqb_stage_align", "fqb_get_stream_state", "fqb_drand48_zero_index", "fqb_set_stream_state", "fqb_set_pair_base", "fqb_stats_group_bytes", "fqb_stats_export", "fqb_stats_import",
     "fqb_stats_set_target_region", "fqb_stats_open", "fqb_stats_begin_file", "fqb_stats_reset", "fqb_stats_file_counters", "fqb_stage_stats", "fqb_stats_emit", "fqb_stats_emit2", "fqb_emit_sync", "fqb_stats_finish", "fqb_isize_adjusted_file", "fqb_infer_isize_hist", "fqb_isize_penalty", "fqb_host_tables", "fqb_search_buckets", "fqb_stats_var_count", "fqb_stats_var_export", "fqb_stats_var_import", "fqb_stats_close_table", "fqb_stats_merge_tables",
     "fqb_stage_pair", "fqb_stage_sw_refine", "fqb_stage_fetch_rows", "fqb_stage_fetch_rows_async", "fqb_rows_wait", "fqb_reset_stream", "fqb_stage_fetch_prep", "fqb_stage_fetch_aln", "fqb_stage_counters", "fqb_launch_count", "fqb_rank_query_time", "fqb_stream", "fqb_measure_l2", "fqb_feeder_open", "fqb_feeder_format", "fqb_feeder_fill", "fqb_feeder_fill_packed", "fqb_feeder_close", "fqb_gunzip", "fqb_bgzf_compress", "fqb_bgzf_write_file", "fqb_host_alloc", "fqb_host_free",
     "fqb_index_from_flank_fasta", "fqb_synth_ref_cfg_default", "fqb_synth_read_cfg_default", "fqb_synth_create", "fqb_synth_destroy",

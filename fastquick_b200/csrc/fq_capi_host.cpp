@@ -18,6 +18,26 @@ extern "C" {
 
 const char *fqb_last_error(void) { return fqb::g_err.c_str(); }
 
+// 1-based number of the drand48() call that returns exactly 0.0 after srand48(seed).  X(n+1) = (a X(n) + c) mod 2^48 with a = 1
+// mod 4 and c odd has full period modulo every power of two, so X(n) mod 2^k depends on n mod 2^k only and the n with X(n) = 0
+// is found one bit at a time (48 jump-aheads).
+uint64_t fqb_drand48_zero_index(uint32_t seed) {
+    const uint64_t a0 = 0x5DEECE66Dull, c0 = 0xBull, mask = 0xFFFFFFFFFFFFull;
+    const uint64_t x0 = ((uint64_t)seed << 16) | 0x330Eull;              // srand48
+    auto advance = [&](uint64_t n) {                                      // state after n calls
+        uint64_t a = a0, c = c0, A = 1, Cc = 0;
+        while (n) {
+            if (n & 1) { A = (A * a) & mask; Cc = (Cc * a + c) & mask; }
+            c = ((a + 1) * c) & mask; a = (a * a) & mask; n >>= 1;
+        }
+        return (A * x0 + Cc) & mask;
+    };
+    uint64_t n = 0;
+    for (int k = 0; k < 48; ++k)
+        if (advance(n) & ((2ull << k) - 1)) n |= 1ull << k;
+    return n ? n : 1ull << 48;                                            // n == 0: the seed state itself, met again after a full period
+}
+
 // gap_init_opt(), libbwa/bwtaln.c:24-48; kmer_thresh: src/FASTQuick.cpp:174
 void fqb_gap_opt_default(fqb_gap_opt_t *o) {
     memset(o, 0, sizeof(*o));

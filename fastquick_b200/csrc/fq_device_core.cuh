@@ -35,10 +35,13 @@ namespace fqb {
 
 // One 32-byte rank block in ONE load: sm_100a has 256-bit global loads (LDG.E.256), so a rank query costs a single
 // request to a single L2 sector (the blocks are 32-byte aligned).  Host builds read the two halves.
+// kKeep: the load carries evict-last priorities (L1 and L2), so that the index outlives the streaming traffic around it.
+template <bool kKeep = false>
 FQB_HD void load_block(const uint4 *p, uint4 &cnt, uint4 &bases) {
 #if defined(__CUDA_ARCH__)
     unsigned long long a, b, c, d;
-    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    if (kKeep) asm("ld.global.nc.L1::evict_last.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    else asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
     cnt.x = (uint32_t)a; cnt.y = (uint32_t)(a >> 32); cnt.z = (uint32_t)b; cnt.w = (uint32_t)(b >> 32);
     bases.x = (uint32_t)c; bases.y = (uint32_t)(c >> 32); bases.z = (uint32_t)d; bases.w = (uint32_t)(d >> 32);
 #else
@@ -226,8 +229,17 @@ enum LaneMode { kModePop = 0, kModeExpand = 1, kModeExact = 2 };
 //   HeadT:     uint16_t when the arena holds < 65535 entries (fast pass), else uint32_t
 //   kFreeList: recycle popped slots through a free list (overflow pass; the fast pass
 //              only recycles the most recently popped slot and otherwise bump-allocates)
-template <typename HeadT, bool kFreeList>
+//   kVar:      memory-path variants of the device build (bump arena only; the results are the same whatever the value):
+//              bit 0  pop staging: every pop from memory starts an asynchronous copy (cp.async, 16 bytes) of the entry the
+//                     popped one chains to -- the next entry its score bucket will hand out -- into the lane's shared-memory
+//                     slot; the next pop finds it there instead of waiting for the arena in L2 / HBM.  Entries of the bump
+//                     arena are never rewritten within a read, so the staged copy is valid whenever its tag matches.
+//              bit 1  rank-block loads with evict-last priority in L1 and L2
+//              bit 2  stack entries stored with the evict-first (streaming) policy: two thirds of them are never read back
+//              bit 3  width bounds and read symbols loaded with evict-last priority in L1
+template <typename HeadT, bool kFreeList, int kVar = 0>
 struct SearchLane {
+    static constexpr bool kStage = (kVar & 1) && !kFreeList, kKeepIdx = (kVar & 2) != 0, kStreamSt = (kVar & 4) != 0, kKeepW = (kVar & 8) != 0;
     // wiring
     const DevBwt *bwt;         // [2]
     const SearchOpt *opt;
@@ -248,6 +260,14 @@ struct SearchLane {
     int mode;
     bool have_cur, overflow;
     uint32_t hit_x;            // interval size of the hit whose gap_shadow is pending
+#if defined(__CUDA_ARCH__)
+    // kStage: shared-space address of this lane's staging slot {uint4 entry, u32 tag = the entry's arena slot}: the slots are the
+    // first 32 x blockDim.x bytes of the block's dynamic shared memory (recomputed where needed, so that it holds no register)
+    __device__ __forceinline__ static uint32_t stage_slot() {
+        extern __shared__ __align__(16) unsigned char fqb_dyn_smem[];
+        return (uint32_t)__cvta_generic_to_shared(fqb_dyn_smem) + threadIdx.x * 32u;
+    }
+#endif
     // statistics
     uint32_t n_pops, n_occ, n_blk;
 #ifdef FQB_LANE_STATS
@@ -265,6 +285,24 @@ struct SearchLane {
     FQB_HD bool bucket_set(int s) const { return s < 64 ? (mask0 >> s) & 1 : (mask1 >> (s - 64)) & 1; }
     FQB_HD int diffs_left() const { return max_diff - (n_mm + n_gapo) - ((opt->mode & kModeGapE) ? n_gape : 0); }
 
+    FQB_HD void store_entry(uint32_t s, uint32_t x, uint32_t y, uint32_t z, uint32_t w_) {
+#if defined(__CUDA_ARCH__)
+        if (kStreamSt) { asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(arena + s), "r"(x), "r"(y), "r"(z), "r"(w_) : "memory"); return; }
+#endif
+        arena[s] = make_uint4(x, y, z, w_);
+    }
+    FQB_HD uint32_t load_w(const uint32_t *p_) const {
+#if defined(__CUDA_ARCH__)
+        if (kKeepW) { uint32_t v; asm volatile("ld.global.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p_) : "memory"); return v; }   // widths are rewritten by gap_shadow
+#endif
+        return *p_;
+    }
+    FQB_HD uint32_t load_sym(const uint8_t *p_) const {
+#if defined(__CUDA_ARCH__)
+        if (kKeepW) { uint32_t v; asm("ld.global.nc.L1::evict_last.u8 %0, [%1];" : "=r"(v) : "l"(p_)); return v; }
+#endif
+        return *p_;
+    }
     FQB_HD uint32_t alloc_slot() {
         if (kFreeList && free_head != kNoSlot) { uint32_t s = free_head; free_head = arena[s].w & kNoSlot; return s; }
         if (top < arena_cap) return top++;
@@ -282,7 +320,7 @@ struct SearchLane {
         ++n_entries;
         FQB_STAT(st_push);
         if (s == kNoSlot) return prev;
-        arena[s] = make_uint4(pk, pl, meta, (uint32_t)pldp << 22 | prev);
+        store_entry(s, pk, pl, meta, (uint32_t)pldp << 22 | prev);
         return s;
     }
     FQB_HD uint32_t bucket_head(int sc) { return bucket_set(sc) ? (uint32_t)head(sc) : kNoSlot; }
@@ -313,7 +351,7 @@ struct SearchLane {
         uint32_t prev = bucket_head(sc), s = top;
         _Pragma("unroll")
         for (int j = 0; j < N; ++j)
-            if (v[j]) { arena[s] = make_uint4(ek[j], el[j], em[j], ed[j] << 22 | prev); prev = s; ++s; }
+            if (v[j]) { store_entry(s, ek[j], el[j], em[j], ed[j] << 22 | prev); prev = s; ++s; }
         top = s;
         publish(sc, prev);
     }
@@ -342,11 +380,29 @@ struct SearchLane {
         FQB_STAT(st_mempop);
         int b = mask0 ? FQB_FFSLL(mask0) - 1 : 63 + FQB_FFSLL(mask1);
         uint32_t s = (uint32_t)head(b);
-        uint4 e = arena[s];
+        uint4 e;
+#if defined(__CUDA_ARCH__)
+        if (kStage) {
+            uint32_t tag;
+            const uint32_t stage_sa = stage_slot();
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tag) : "r"(stage_sa + 16u) : "memory");
+            if (tag == s) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(stage_sa) : "memory");
+            else e = arena[s];
+        } else
+#endif
+        e = arena[s];
         uint32_t prev = e.w & kNoSlot;
         if (prev == kNoSlot) { if (b < 64) mask0 &= ~(1ull << b); else mask1 &= ~(1ull << (b - 64)); }
         else {
             head(b) = (HeadT)prev;
+#if defined(__CUDA_ARCH__)
+            if (kStage) {
+                const uint32_t stage_sa = stage_slot();
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_sa), "l"(arena + prev) : "memory");
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(stage_sa + 16u), "r"(prev) : "memory");
+            }
+#endif
 #if defined(__CUDA_ARCH__) && defined(FQB_POP_PREFETCH)
             // the next pop from this bucket follows the chain: start pulling it towards the SM now (a whole step early)
             asm volatile(FQB_POP_PREFETCH " [%0];" ::"l"(arena + prev));
@@ -367,6 +423,9 @@ struct SearchLane {
         mask0 = mask1 = 0; top = 0; free_head = kNoSlot;
         have_cur = false; mode = kModePop; overflow = false;
         n_pops = n_occ = n_blk = 0; hit_x = 0;
+#if defined(__CUDA_ARCH__)
+        if (kStage) asm volatile("st.shared.u32 [%0], %1;" ::"r"(stage_slot() + 16u), "r"(kNoSlot) : "memory");   // nothing staged for this read yet
+#endif
         if (n_ambig > max_diff) return kLaneDone;
         push(0, len, 0, bwt[0].seq_len, 0, 0, 0, kStateM, 0);
         // second root (strand 1) is the top of bucket 0: keep it in registers
@@ -429,20 +488,20 @@ struct SearchLane {
         const uint32_t kk_ = no_k ? 0 : (k - 1) - ((k - 1) >= b.primary), ll_ = l - (l >= b.primary);
         const uint4 *pk = b.blocks + 2 * (size_t)(kk_ >> 6), *pl = b.blocks + 2 * (size_t)(ll_ >> 6);
         uint4 bk_c, bk_w;
-        load_block(pk, bk_c, bk_w);
+        load_block<kKeepIdx>(pk, bk_c, bk_w);
         const bool same_blk = (kk_ >> 6) == (ll_ >> 6);
         uint4 bl_c = bk_c, bl_w = bk_w;
-        if (!same_blk) load_block(pl, bl_c, bl_w);
-        const uint32_t c_here = fwd[len - i];                           // read_sym(i - 1), before complementing
-        const uint32_t c_next = i >= 2 ? fwd[len - i + 1] : 4u;         // read_sym(i - 2)
+        if (!same_blk) load_block<kKeepIdx>(pl, bl_c, bl_w);
+        const uint32_t c_here = load_sym(fwd + (len - i));                          // read_sym(i - 1), before complementing
+        const uint32_t c_next = i >= 2 ? load_sym(fwd + (len - i + 1)) : 4u;        // read_sym(i - 2)
         uint32_t w_hi = 0, w_lo = 0, s_hi = 0, s_lo = 0;
         const int ii = (i - 1) - (len - opt->seed_len);
         const bool seed_chk = sw[0] && ii > 0;
         if (mode != kModeExact) {
             const uint32_t *wp = wa();
-            w_hi = wp[i - 1];
-            if (i >= 2) w_lo = wp[i - 2];
-            if (seed_chk) { const uint32_t *sp = swa(); s_lo = sp[ii - 1]; s_hi = sp[ii]; }
+            w_hi = load_w(wp + (i - 1));
+            if (i >= 2) w_lo = load_w(wp + (i - 2));
+            if (seed_chk) { const uint32_t *sp = swa(); s_lo = load_w(sp + (ii - 1)); s_hi = load_w(sp + ii); }
         }
         const uint32_t sym_here = (a && c_here < 4) ? 3 - c_here : c_here;
         const uint32_t sym_next = (a && c_next < 4) ? 3 - c_next : c_next;

@@ -787,7 +787,7 @@ static int check_status(fqb_handle *h) {
     if (e & kErrShortRead) set_error("a read is shorter than 96 bases: the reference's k-mer filter reads bases 0..95 whatever the read length and sees stale buffer bytes there (src/BwtIndexer.cpp:443-450); unsupported -- disable the filter (kmer_thresh = 0) for such input");
     else if (e & kErrSpillCap) set_error("more than 16,384 reads of one batch outgrew the fast search pass");
     else if (e & kErrDeepOverflow) set_error("a read overflowed even the max_entries-deep arena or 1024 hits");
-    else if (e & kErrDrandZero) set_error("drand48 returned exactly 0.0 for a read with one best interval (p = 2^-48 per read): unsupported");
+    else if (e & kErrDrandZero) set_error("drand48 returned exactly 0.0 for a read with one best interval (draw number fqb_drand48_zero_index(seed) of the file's stream, once per 2^48 draws): unsupported");
     else if (e & kErrBigPairs) set_error("too many repeat-heavy pairs in one batch");
     else set_error("an alignment needed more DP scratch or CIGAR operations than provisioned");
     return FQB_ERR_LIMIT;

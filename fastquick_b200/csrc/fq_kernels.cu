@@ -277,18 +277,22 @@ __device__ __forceinline__ void warp_shadow(Lane &lane, bool has_hit, int lane_i
     __syncwarp();
 }
 
-template <typename HeadT, bool kFreeList, int kMinBlocks = 640 / kSearchThreads>
+// Shared memory of a block: -- kStage -- one 32-byte staging slot per lane (SearchLane::stage_slot), then the bucket heads
+// (n_buckets x kSearchThreads x HeadT, one column per lane).
+constexpr int kStageBytes = 32;
+template <typename HeadT, bool kFreeList, int kMinBlocks = 640 / kSearchThreads, int kVar = 0>
 __global__ void __launch_bounds__(kSearchThreads, kMinBlocks) search_kernel(const __grid_constant__ BatchView b, const __grid_constant__ WidthView wv,
                                                                             const __grid_constant__ SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    HeadT *heads = reinterpret_cast<HeadT *>(smem_raw);
+    constexpr bool kStage = (kVar & 1) && !kFreeList;
+    HeadT *heads = reinterpret_cast<HeadT *>(smem_raw + (kStage ? kSearchThreads * kStageBytes : 0));
     // search options and index descriptors are read straight from the kernel-parameter constant bank
     const DevBwt *s_bwt = p.bwt;
     const SearchOpt &s_opt = p.opt;
 
     const int lane_id = threadIdx.x & 31;
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    SearchLane<HeadT, kFreeList> lane;
+    SearchLane<HeadT, kFreeList, kVar> lane;
     lane.bwt = s_bwt; lane.opt = &s_opt;
     lane.arena = p.arena + gtid * p.arena_cap; lane.arena_cap = p.arena_cap;
     lane.heads = heads + threadIdx.x; lane.head_stride = blockDim.x;
@@ -379,12 +383,46 @@ static int search_occ_variant() {
     if (v < 0) { const char *e = getenv("FQB_SEARCH_OCC"); v = e ? atoi(e) : 1; }
     return v;
 }
+// memory-path variant of the fast pass (SearchLane kVar, a bit mask): FQB_SEARCH_VAR overrides the build's default.  Read at
+// every launch, so that tools/stage_ab.py can time all forms in one process on one batch.
+constexpr int kSearchVarDefault = 0;
+constexpr int kSearchVars = 16;
+static int search_mem_variant() {
+    const char *e = getenv("FQB_SEARCH_VAR");
+    const int v = e ? atoi(e) : kSearchVarDefault;
+    return v >= 0 && v < kSearchVars ? v : kSearchVarDefault;
+}
+template <int kVar> struct FastSearch {
+    static constexpr int kMinBlocks = 640 / kSearchThreads;
+    static size_t smem(int n_buckets) { return (size_t)n_buckets * kSearchThreads * 2 + ((kVar & 1) ? kSearchThreads * kStageBytes : 0); }
+    static int per_sm(int n_buckets) {
+        int v = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, search_kernel<uint16_t, false, kMinBlocks, kVar>, kSearchThreads, smem(n_buckets));
+        return v;
+    }
+    static void launch(const BatchView &b, const WidthView &wv, const SearchParams &p, int n_blocks, cudaStream_t s) {
+        const size_t sm = smem(p.opt.n_buckets);
+        cudaFuncSetAttribute(search_kernel<uint16_t, false, kMinBlocks, kVar>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        search_kernel<uint16_t, false, kMinBlocks, kVar><<<n_blocks, kSearchThreads, sm, s>>>(b, wv, p);
+    }
+};
+template <int kVar = kSearchVars - 1> struct FastSearchTable {
+    static int per_sm(int var, int n_buckets) { return var == kVar ? FastSearch<kVar>::per_sm(n_buckets) : FastSearchTable<kVar - 1>::per_sm(var, n_buckets); }
+    static void launch(int var, const BatchView &b, const WidthView &wv, const SearchParams &p, int n_blocks, cudaStream_t s) {
+        if (var == kVar) FastSearch<kVar>::launch(b, wv, p, n_blocks, s); else FastSearchTable<kVar - 1>::launch(var, b, wv, p, n_blocks, s);
+    }
+};
+template <> struct FastSearchTable<0> {
+    static int per_sm(int, int n_buckets) { return FastSearch<0>::per_sm(n_buckets); }
+    static void launch(int, const BatchView &b, const WidthView &wv, const SearchParams &p, int n_blocks, cudaStream_t s) { FastSearch<0>::launch(b, wv, p, n_blocks, s); }
+};
 
 int search_grid_blocks(int n_buckets, bool heads16, int device) {
     int per_sm = 0, n_sm = 148;
     size_t smem = (size_t)n_buckets * kSearchThreads * (heads16 ? 2 : 4);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-    if (heads16 && search_occ_variant() == 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint16_t, false, 6>, kSearchThreads, smem);
+    if (heads16 && search_mem_variant()) per_sm = FastSearchTable<>::per_sm(search_mem_variant(), n_buckets);
+    else if (heads16 && search_occ_variant() == 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint16_t, false, 6>, kSearchThreads, smem);
     else if (heads16 && search_occ_variant() == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint16_t, false, 8>, kSearchThreads, smem);
     else if (heads16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint16_t, false>, kSearchThreads, smem);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint32_t, true>, kSearchThreads, smem);
@@ -401,7 +439,8 @@ static void launch_search_t(const BatchView &b, const WidthView &wv, const Searc
 }
 
 void launch_search(const BatchView &b, const WidthView &wv, const SearchParams &p, bool heads16, bool free_list, int n_blocks, cudaStream_t s) {
-    if (heads16 && !free_list && search_occ_variant() == 6) launch_search_t<uint16_t, false, 6>(b, wv, p, n_blocks, s);
+    if (heads16 && !free_list && search_mem_variant()) FastSearchTable<>::launch(search_mem_variant(), b, wv, p, n_blocks, s);
+    else if (heads16 && !free_list && search_occ_variant() == 6) launch_search_t<uint16_t, false, 6>(b, wv, p, n_blocks, s);
     else if (heads16 && !free_list && search_occ_variant() == 8) launch_search_t<uint16_t, false, 8>(b, wv, p, n_blocks, s);
     else if (heads16 && !free_list) launch_search_t<uint16_t, false>(b, wv, p, n_blocks, s);
     else if (heads16) launch_search_t<uint16_t, true>(b, wv, p, n_blocks, s);

@@ -214,9 +214,11 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
     else if (fqb_feeder_open(fq1.c_str(), 0, &fd[0]) != FQB_OK || fqb_feeder_open(fq2.c_str(), 0, &fd[1]) != FQB_OK) error("Open fastq failed: %s", fqb_last_error());
     if (fqb_stats_begin_file(h_, prefix_.c_str(), fq1.c_str(), fq2.c_str()) != FQB_OK) error("%s", fqb_last_error());
     const int stride = opt->read_len < FQB_MAX_READ_LEN ? opt->read_len : FQB_MAX_READ_LEN, cap = FQB_BATCH_PAIRS, name_stride = 64;
-    // four pinned batches in flight: the GPU maps batch N, the copy stream uploads batch N+1, the feeder decodes batch N+2, and
-    // with FQB_ASYNC_EMIT the library's writer threads still format the InsertSizeTable lines and BAM records of batch N-1
-    // (the two IO workers of the reference, src/BwtMapper.cpp:1969-1982, become one feeder per end)
+    // Four pinned batches: batch N is collected (pairing .. statistics on the main stream) and its lines / records are
+    // formatted on the host while the align stage of batch N+1 -- submitted before -- runs on the align stream, and the
+    // feeder decodes batch N+2; the fourth buffer is the one FQB_ASYNC_EMIT's writer threads may still be reading
+    // (the two IO workers of the reference, src/BwtMapper.cpp:1969-1982, become one feeder per end; its "map batch N while
+    // batch N+1 is read" becomes fqb_submit_pairs(N+1) before fqb_collect_pairs(N))
     constexpr int kBufs = 4;
     struct Buf { uint8_t *b[2], *q[2]; int32_t *l[2]; char *nm[2]; int n[2]; } bufs[kBufs];
     for (auto &B : bufs)
@@ -241,17 +243,18 @@ bool BwtMapper::PairEndMapper(const std::string &fq1, const std::string &fq2, co
         t0.join();
     };
     auto good = [](const Buf &B) { return B.n[0] > 0 && B.n[1] > 0; };
+    auto submit = [&](const Buf &S) {     // upload + align stage, asynchronous; the buffers stay untouched until the batch has been emitted
+        if (S.n[0] != S.n[1]) error("Abort, please make sure input pair of fastq files are in the same order!");
+        if (fqb_submit_pairs(h_, S.n[0], stride, S.b[0], S.q[0], S.l[0], S.b[1], S.q[1], S.l[1], 0) != FQB_OK) error("%s", fqb_last_error());
+    };
     int cur = 0;
     load(bufs[0]);
-    if (good(bufs[0])) load(bufs[1]);
+    if (good(bufs[0])) { submit(bufs[0]); load(bufs[1]); }
     while (good(bufs[cur])) {
         Buf &B = bufs[cur], &N1 = bufs[(cur + 1) % kBufs], &N2 = bufs[(cur + 2) % kBufs];
-        if (B.n[0] != B.n[1]) error("Abort, please make sure input pair of fastq files are in the same order!");
-        if (good(N1) && N1.n[0] == N1.n[1] &&
-            fqb_prefetch_pairs(h_, N1.n[0], stride, N1.b[0], N1.q[0], N1.l[0], N1.b[1], N1.q[1], N1.l[1]) != FQB_OK) error("%s", fqb_last_error());
-        std::thread next([&]() { if (good(N1)) load(N2); else N2.n[0] = N2.n[1] = 0; });      // IO(N+2) overlaps GPU(N) and H2D(N+1)
-        if (fqb_align_pairs(h_, B.n[0], stride, B.b[0], B.q[0], B.l[0], B.b[1], B.q[1], B.l[1], nullptr, nullptr, nullptr) != FQB_OK) error("%s", fqb_last_error());
-        if (fqb_stage_stats(h_) != FQB_OK) error("%s", fqb_last_error());
+        if (good(N1)) submit(N1);
+        std::thread next([&]() { if (good(N1)) load(N2); else N2.n[0] = N2.n[1] = 0; });      // IO(N+2) overlaps GPU(N, N+1) and the emission of N
+        if (fqb_collect_pairs(h_, nullptr, nullptr) != FQB_OK) error("%s", fqb_last_error());   // includes StatCollector's accumulation
         if (fqb_stats_emit2(h_, B.nm[0], B.nm[1], name_stride) != FQB_OK) error("%s", fqb_last_error());
         if (bam_out_ && fqb_bam_emit2(h_, B.nm[0], B.nm[1], name_stride, B.b[0], B.q[0], B.b[1], B.q[1], stride) != FQB_OK) error("%s", fqb_last_error());
         FSC.NumRead += 2LL * B.n[0];

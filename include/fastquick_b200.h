@@ -268,6 +268,13 @@ int fqb_stats_merge_tables(fqb_handle *h, const char *const *other_prefixes, int
  * batch b+1 between fqb_stage_align and fqb_stage_pair.  At the end the integer accumulators are combined with
  * an NCCL reduce (groups 0-2: sum; group 3: min) on buffers moved with fqb_stats_export / fqb_stats_import. */
 int fqb_get_stream_state(fqb_handle *h, uint64_t *rng_calls, fqb_isize_t *last_ii);
+/* The one draw this library does not reproduce: bwa_aln2seq_core (libbwa/bwase.c:33-36) skips a read's only best interval
+ * when drand48() returns exactly 0.0 and then takes one draw instead of two; the device counts two draws for such reads
+ * and reports FQB_ERR_LIMIT should it ever meet that draw.  drand48 is a full-period 48-bit LCG, so after srand48(seed) it
+ * returns 0.0 exactly once per 2^48 draws: this returns the 1-based number of that draw (host arithmetic, no device needed).
+ * For the seed bns->seed = 11 of every BWA index it is draw 79,023,531,276,618 -- the stream restarts with every FASTQ pair
+ * (src/BwtMapper.cpp:1817), so a single input file would have to hold about 2e13 pairs to reach it. */
+uint64_t fqb_drand48_zero_index(uint32_t seed);
 int fqb_set_stream_state(fqb_handle *h, uint64_t rng_calls, const fqb_isize_t *last_ii);
 int fqb_set_pair_base(fqb_handle *h, uint64_t first_pair);
 int fqb_stats_group_bytes(fqb_handle *h, int which, uint64_t *bytes);

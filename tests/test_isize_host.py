@@ -139,3 +139,32 @@ def test_search_bucket_count():
     assert lib.fqb_search_buckets(C.byref(g), 100) == 6 * 3 + 4 * 11 + 7 * 4
     assert lib.fqb_search_buckets(C.byref(g), 10) == 2 * 3 + 2 * 11 + 7 * 4                  # -o 3 clamped to max_diff 1
     assert lib.fqb_search_buckets(C.byref(g), 1000) < 0
+
+
+def test_drand48_zero_draw_index():
+    """The draw at which drand48() returns exactly 0.0 (the one case the device's draw count does not follow,
+    libbwa/bwase.c:33-36): found by fqb_drand48_zero_index, checked by stepping the generator around it."""
+    import ctypes as C
+    lib = fx.host_lib()
+    lib.fqb_drand48_zero_index.restype = C.c_uint64
+    A, Cc, M = 0x5DEECE66D, 0xB, (1 << 48) - 1
+
+    def advance(x, n):
+        a, c, aa, cc = A, Cc, 1, 0
+        while n:
+            if n & 1:
+                aa, cc = (aa * a) & M, (cc * a + c) & M
+            c, a, n = ((a + 1) * c) & M, (a * a) & M, n >> 1
+        return (aa * x + cc) & M
+
+    for seed in (11, 0, 1, 12345, 0xffffffff):
+        n = int(lib.fqb_drand48_zero_index(C.c_uint32(seed)))
+        x0 = (seed << 16) | 0x330E
+        assert 1 <= n <= 1 << 48
+        assert advance(x0, n) == 0                      # drand48() == 0.0 at call n ...
+        assert advance(x0, n - 1) != 0 or n == 1 << 48  # ... and the closed form is not off by one
+    assert int(lib.fqb_drand48_zero_index(C.c_uint32(11))) == 79023531276618      # bns->seed of every BWA index
+    # brute force for a state that reaches zero soon: seed state X with a X + c = 0 (mod 2^48) is one step away
+    x = (-(Cc) * pow(A, -1, 1 << 48)) & M
+    if x & 0xffff == 0x330E and x >> 16 < 1 << 32:
+        assert int(lib.fqb_drand48_zero_index(C.c_uint32(x >> 16))) == 1
