@@ -199,6 +199,7 @@ def run_cli_sample(lib, synth, workdir, n_pairs):
             with open(fq[e], "ab") as dst, open(part, "rb") as src:
                 dst.write(src.read())
             os.remove(part)
+    os.sync()                                              # the FASTQ text just written is on its way to disk: not during the timed runs
     out = {}
     for tag, extra in (("stats", ["--sam_out"]), ("stats+bam", [])):
         cmd = [CLI_BIN, "align", "--fastq_1", fq[0], "--fastq_2", fq[1], "--index_prefix", index_prefix[: -len(".FASTQuick.fa")],

@@ -35,13 +35,10 @@ namespace fqb {
 
 // One 32-byte rank block in ONE load: sm_100a has 256-bit global loads (LDG.E.256), so a rank query costs a single
 // request to a single L2 sector (the blocks are 32-byte aligned).  Host builds read the two halves.
-// kKeep: the load carries evict-last priorities (L1 and L2), so that the index outlives the streaming traffic around it.
-template <bool kKeep = false>
 FQB_HD void load_block(const uint4 *p, uint4 &cnt, uint4 &bases) {
 #if defined(__CUDA_ARCH__)
     unsigned long long a, b, c, d;
-    if (kKeep) asm("ld.global.nc.L1::evict_last.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
-    else asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    asm("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
     cnt.x = (uint32_t)a; cnt.y = (uint32_t)(a >> 32); cnt.z = (uint32_t)b; cnt.w = (uint32_t)(b >> 32);
     bases.x = (uint32_t)c; bases.y = (uint32_t)(c >> 32); bases.z = (uint32_t)d; bases.w = (uint32_t)(d >> 32);
 #else
@@ -234,12 +231,12 @@ enum LaneMode { kModePop = 0, kModeExpand = 1, kModeExact = 2 };
 //                     popped one chains to -- the next entry its score bucket will hand out -- into the lane's shared-memory
 //                     slot; the next pop finds it there instead of waiting for the arena in L2 / HBM.  Entries of the bump
 //                     arena are never rewritten within a read, so the staged copy is valid whenever its tag matches.
-//              bit 1  rank-block loads with evict-last priority in L1 and L2
 //              bit 2  stack entries stored with the evict-first (streaming) policy: two thirds of them are never read back
-//              bit 3  width bounds and read symbols loaded with evict-last priority in L1
+//              (bits 1 and 3 were evict-last priorities on the rank-block and width loads: measured, no gain, removed --
+//              profiles/r02_search_memory_variants.md)
 template <typename HeadT, bool kFreeList, int kVar = 0>
 struct SearchLane {
-    static constexpr bool kStage = (kVar & 1) && !kFreeList, kKeepIdx = (kVar & 2) != 0, kStreamSt = (kVar & 4) != 0, kKeepW = (kVar & 8) != 0;
+    static constexpr bool kStage = (kVar & 1) && !kFreeList, kStreamSt = (kVar & 4) != 0;
     // wiring
     const DevBwt *bwt;         // [2]
     const SearchOpt *opt;
@@ -290,18 +287,6 @@ struct SearchLane {
         if (kStreamSt) { asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(arena + s), "r"(x), "r"(y), "r"(z), "r"(w_) : "memory"); return; }
 #endif
         arena[s] = make_uint4(x, y, z, w_);
-    }
-    FQB_HD uint32_t load_w(const uint32_t *p_) const {
-#if defined(__CUDA_ARCH__)
-        if (kKeepW) { uint32_t v; asm volatile("ld.global.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p_) : "memory"); return v; }   // widths are rewritten by gap_shadow
-#endif
-        return *p_;
-    }
-    FQB_HD uint32_t load_sym(const uint8_t *p_) const {
-#if defined(__CUDA_ARCH__)
-        if (kKeepW) { uint32_t v; asm("ld.global.nc.L1::evict_last.u8 %0, [%1];" : "=r"(v) : "l"(p_)); return v; }
-#endif
-        return *p_;
     }
     FQB_HD uint32_t alloc_slot() {
         if (kFreeList && free_head != kNoSlot) { uint32_t s = free_head; free_head = arena[s].w & kNoSlot; return s; }
@@ -488,20 +473,20 @@ struct SearchLane {
         const uint32_t kk_ = no_k ? 0 : (k - 1) - ((k - 1) >= b.primary), ll_ = l - (l >= b.primary);
         const uint4 *pk = b.blocks + 2 * (size_t)(kk_ >> 6), *pl = b.blocks + 2 * (size_t)(ll_ >> 6);
         uint4 bk_c, bk_w;
-        load_block<kKeepIdx>(pk, bk_c, bk_w);
+        load_block(pk, bk_c, bk_w);
         const bool same_blk = (kk_ >> 6) == (ll_ >> 6);
         uint4 bl_c = bk_c, bl_w = bk_w;
-        if (!same_blk) load_block<kKeepIdx>(pl, bl_c, bl_w);
-        const uint32_t c_here = load_sym(fwd + (len - i));                          // read_sym(i - 1), before complementing
-        const uint32_t c_next = i >= 2 ? load_sym(fwd + (len - i + 1)) : 4u;        // read_sym(i - 2)
+        if (!same_blk) load_block(pl, bl_c, bl_w);
+        const uint32_t c_here = fwd[len - i];                           // read_sym(i - 1), before complementing
+        const uint32_t c_next = i >= 2 ? fwd[len - i + 1] : 4u;         // read_sym(i - 2)
         uint32_t w_hi = 0, w_lo = 0, s_hi = 0, s_lo = 0;
         const int ii = (i - 1) - (len - opt->seed_len);
         const bool seed_chk = sw[0] && ii > 0;
         if (mode != kModeExact) {
             const uint32_t *wp = wa();
-            w_hi = load_w(wp + (i - 1));
-            if (i >= 2) w_lo = load_w(wp + (i - 2));
-            if (seed_chk) { const uint32_t *sp = swa(); s_lo = load_w(sp + (ii - 1)); s_hi = load_w(sp + ii); }
+            w_hi = wp[i - 1];
+            if (i >= 2) w_lo = wp[i - 2];
+            if (seed_chk) { const uint32_t *sp = swa(); s_lo = sp[ii - 1]; s_hi = sp[ii]; }
         }
         const uint32_t sym_here = (a && c_here < 4) ? 3 - c_here : c_here;
         const uint32_t sym_next = (a && c_next < 4) ? 3 - c_next : c_next;

@@ -383,14 +383,15 @@ static int search_occ_variant() {
     if (v < 0) { const char *e = getenv("FQB_SEARCH_OCC"); v = e ? atoi(e) : 1; }
     return v;
 }
-// memory-path variant of the fast pass (SearchLane kVar, a bit mask): FQB_SEARCH_VAR overrides the build's default.  Read at
-// every launch, so that tools/stage_ab.py can time all forms in one process on one batch.
-constexpr int kSearchVarDefault = 0;
-constexpr int kSearchVars = 16;
+// Memory-path form of the fast pass (SearchLane kVar, a bit mask): 5 = pop staging through shared memory + streaming stack
+// stores is the build's default (profiles/r02_search_memory_variants.md: filter-bound input +10 %, 150-base reads +3 %, the
+// 100-base contract workload unchanged); FQB_SEARCH_VAR = 0 / 1 / 4 / 5 overrides it.  Read at every launch, so that
+// tools/stage_ab.py can time the forms in one process on one batch.
+constexpr int kSearchVarDefault = 5;
 static int search_mem_variant() {
     const char *e = getenv("FQB_SEARCH_VAR");
     const int v = e ? atoi(e) : kSearchVarDefault;
-    return v >= 0 && v < kSearchVars ? v : kSearchVarDefault;
+    return v == 0 || v == 1 || v == 4 || v == 5 ? v : kSearchVarDefault;
 }
 template <int kVar> struct FastSearch {
     static constexpr int kMinBlocks = 640 / kSearchThreads;
@@ -406,22 +407,20 @@ template <int kVar> struct FastSearch {
         search_kernel<uint16_t, false, kMinBlocks, kVar><<<n_blocks, kSearchThreads, sm, s>>>(b, wv, p);
     }
 };
-template <int kVar = kSearchVars - 1> struct FastSearchTable {
-    static int per_sm(int var, int n_buckets) { return var == kVar ? FastSearch<kVar>::per_sm(n_buckets) : FastSearchTable<kVar - 1>::per_sm(var, n_buckets); }
-    static void launch(int var, const BatchView &b, const WidthView &wv, const SearchParams &p, int n_blocks, cudaStream_t s) {
-        if (var == kVar) FastSearch<kVar>::launch(b, wv, p, n_blocks, s); else FastSearchTable<kVar - 1>::launch(var, b, wv, p, n_blocks, s);
-    }
-};
-template <> struct FastSearchTable<0> {
-    static int per_sm(int, int n_buckets) { return FastSearch<0>::per_sm(n_buckets); }
-    static void launch(int, const BatchView &b, const WidthView &wv, const SearchParams &p, int n_blocks, cudaStream_t s) { FastSearch<0>::launch(b, wv, p, n_blocks, s); }
-};
+static int fast_search_per_sm(int var, int n_buckets) {
+    return var == 5 ? FastSearch<5>::per_sm(n_buckets) : var == 4 ? FastSearch<4>::per_sm(n_buckets) : FastSearch<1>::per_sm(n_buckets);
+}
+static void fast_search_launch(int var, const BatchView &b, const WidthView &wv, const SearchParams &p, int n_blocks, cudaStream_t s) {
+    if (var == 5) FastSearch<5>::launch(b, wv, p, n_blocks, s);
+    else if (var == 4) FastSearch<4>::launch(b, wv, p, n_blocks, s);
+    else FastSearch<1>::launch(b, wv, p, n_blocks, s);
+}
 
 int search_grid_blocks(int n_buckets, bool heads16, int device) {
     int per_sm = 0, n_sm = 148;
     size_t smem = (size_t)n_buckets * kSearchThreads * (heads16 ? 2 : 4);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-    if (heads16 && search_mem_variant()) per_sm = FastSearchTable<>::per_sm(search_mem_variant(), n_buckets);
+    if (heads16 && search_mem_variant()) per_sm = fast_search_per_sm(search_mem_variant(), n_buckets);
     else if (heads16 && search_occ_variant() == 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint16_t, false, 6>, kSearchThreads, smem);
     else if (heads16 && search_occ_variant() == 8) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint16_t, false, 8>, kSearchThreads, smem);
     else if (heads16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_kernel<uint16_t, false>, kSearchThreads, smem);
@@ -439,7 +438,7 @@ static void launch_search_t(const BatchView &b, const WidthView &wv, const Searc
 }
 
 void launch_search(const BatchView &b, const WidthView &wv, const SearchParams &p, bool heads16, bool free_list, int n_blocks, cudaStream_t s) {
-    if (heads16 && !free_list && search_mem_variant()) FastSearchTable<>::launch(search_mem_variant(), b, wv, p, n_blocks, s);
+    if (heads16 && !free_list && search_mem_variant()) fast_search_launch(search_mem_variant(), b, wv, p, n_blocks, s);
     else if (heads16 && !free_list && search_occ_variant() == 6) launch_search_t<uint16_t, false, 6>(b, wv, p, n_blocks, s);
     else if (heads16 && !free_list && search_occ_variant() == 8) launch_search_t<uint16_t, false, 8>(b, wv, p, n_blocks, s);
     else if (heads16 && !free_list) launch_search_t<uint16_t, false>(b, wv, p, n_blocks, s);

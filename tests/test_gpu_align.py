@@ -119,9 +119,9 @@ def test_counters_and_determinism(small_index):
 
 
 def test_memory_path_variants_give_the_same_hits(small_index, ref_required, monkeypatch):
-    """FQB_SEARCH_VAR selects how the fast search pass moves its data (pop staging through shared memory, cache policies of
-    the index / stack / width accesses: SearchLane kVar); every form must produce the reference's hit lists.  High-error
-    150-base reads keep the stacks busy (thousands of pops per read, several score buckets)."""
+    """FQB_SEARCH_VAR selects how the fast search pass moves its stack entries (SearchLane kVar: bit 0 pop staging through
+    shared memory, bit 2 streaming stores; the build's default is 5); every form must produce the reference's hit lists.
+    High-error 150-base reads keep the stacks busy (thousands of pops per read, several score buckets)."""
     arrs = small_index.reads(1500, read_len=150, seed=21, sub_rate=0.04, ins_rate=0.01, del_rate=0.01, max_indel_len=3)
     monkeypatch.setenv("FQB_SEARCH_VAR", "0")
     base = _compare_with_ref(small_index, arrs, "gvar")
@@ -130,7 +130,7 @@ def test_memory_path_variants_give_the_same_hits(small_index, ref_required, monk
         monkeypatch.setenv("FQB_SEARCH_VAR", "0")
         ref = _run_cuda(lib, h, arrs)
         assert (ref[5] == base).all()
-        for var in range(1, 16):
+        for var in (1, 4, 5):
             monkeypatch.setenv("FQB_SEARCH_VAR", str(var))
             got = _run_cuda(lib, h, arrs)
             assert (got[5] == ref[5]).all(), var
