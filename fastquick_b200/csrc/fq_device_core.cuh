@@ -257,6 +257,11 @@ struct SearchLane {
     int mode;
     bool have_cur, overflow;
     uint32_t hit_x;            // interval size of the hit whose gap_shadow is pending
+#if !defined(__CUDACC__)
+    // host instantiation (tests/emul): the staging slot is a member and the asynchronous copy an immediate one; st_stage_stale
+    // counts staged entries that differ from the arena's when they are used (the invariant kStage rests on: must stay 0)
+    uint4 stage_e; uint32_t stage_tag = 0x3fffffu; uint32_t st_stage_hit = 0, st_stage_miss = 0, st_stage_stale = 0;
+#endif
 #if defined(__CUDA_ARCH__)
     // kStage: shared-space address of this lane's staging slot {uint4 entry, u32 tag = the entry's arena slot}: the slots are the
     // first 32 x blockDim.x bytes of the block's dynamic shared memory (recomputed where needed, so that it holds no register)
@@ -375,6 +380,14 @@ struct SearchLane {
             if (tag == s) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(stage_sa) : "memory");
             else e = arena[s];
         } else
+#elif !defined(__CUDACC__)
+        if (kStage) {
+            if (stage_tag == s) {
+                e = stage_e; ++st_stage_hit;
+                const uint4 now = arena[s];
+                if (now.x != e.x || now.y != e.y || now.z != e.z || now.w != e.w) ++st_stage_stale;
+            } else { e = arena[s]; ++st_stage_miss; }
+        } else
 #endif
         e = arena[s];
         uint32_t prev = e.w & kNoSlot;
@@ -387,6 +400,8 @@ struct SearchLane {
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_sa), "l"(arena + prev) : "memory");
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(stage_sa + 16u), "r"(prev) : "memory");
             }
+#elif !defined(__CUDACC__)
+            if (kStage) { stage_e = arena[prev]; stage_tag = prev; }
 #endif
 #if defined(__CUDA_ARCH__) && defined(FQB_POP_PREFETCH)
             // the next pop from this bucket follows the chain: start pulling it towards the SM now (a whole step early)
@@ -410,6 +425,8 @@ struct SearchLane {
         n_pops = n_occ = n_blk = 0; hit_x = 0;
 #if defined(__CUDA_ARCH__)
         if (kStage) asm volatile("st.shared.u32 [%0], %1;" ::"r"(stage_slot() + 16u), "r"(kNoSlot) : "memory");   // nothing staged for this read yet
+#elif !defined(__CUDACC__)
+        stage_tag = kNoSlot;
 #endif
         if (n_ambig > max_diff) return kLaneDone;
         push(0, len, 0, bwt[0].seq_len, 0, 0, 0, kStateM, 0);

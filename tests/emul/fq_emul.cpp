@@ -23,6 +23,13 @@ namespace fqb { void set_error(const std::string &) {} }     // the product's er
 
 static unsigned long long g_stats[40];
 extern "C" void emul_stats(unsigned long long *o) { for (int i = 0; i < 40; ++i) { o[i] = g_stats[i]; g_stats[i] = 0; } }
+// emul_search_var(1): the fast-pass lane is instantiated with pop staging (SearchLane kVar bit 0: the staging slot and its tag
+// logic are the lane's own code, the asynchronous copy becomes an immediate one); emul_stage_stats: pops served from the slot,
+// pops that went to the arena, staged entries that differed from the arena's when used (must be 0), since the last call
+static int g_search_var = 0;
+static unsigned long long g_stage[3];
+extern "C" void emul_search_var(int v) { g_search_var = v; }
+extern "C" void emul_stage_stats(unsigned long long *o) { for (int i = 0; i < 3; ++i) { o[i] = g_stage[i]; g_stage[i] = 0; } }
 struct Emul {
     HostIndex idx;
     std::vector<Block32> blocks[2];
@@ -96,8 +103,10 @@ int emul_align(void *h, const fqb_gap_opt_t *gopt, int n, int stride, const uint
             g_stats[0] += lane.st_iter; g_stats[1] += lane.st_mempop; g_stats[2] += lane.st_skip; g_stats[3] += lane.st_exact;
             g_stats[4] += lane.st_expand; g_stats[5] += lane.st_push; g_stats[6] += lane.st_hit; g_stats[7] += lane.top; g_stats[8] += 1; g_stats[9] += lane.st_adiff; g_stats[10] += lane.st_gapok; g_stats[11] += lane.st_am; for (int q = 0; q < 20; ++q) g_stats[12 + q] += lane.st_x[q];
             if (pops_occ) { pops_occ[2 * r] = lane.n_pops; pops_occ[2 * r + 1] = lane.n_occ; }
+            g_stage[0] += lane.st_stage_hit; g_stage[1] += lane.st_stage_miss; g_stage[2] += lane.st_stage_stale;
         };
-        if (arena_cap < 65535) { SearchLane<uint16_t, false> lane; lane.heads = heads16.data(); run(lane); }
+        if (arena_cap < 65535 && (g_search_var & 1)) { SearchLane<uint16_t, false, 5> lane; lane.heads = heads16.data(); run(lane); }
+        else if (arena_cap < 65535) { SearchLane<uint16_t, false> lane; lane.heads = heads16.data(); run(lane); }
         else { SearchLane<uint32_t, true> lane; lane.heads = heads.data(); run(lane); }
     }
     return 0;

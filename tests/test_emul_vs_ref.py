@@ -20,11 +20,12 @@ def _emul(index):
     return lib, h
 
 
-def _check(index, arrs, tag, arena_cap=4096):
+def _check(index, arrs, tag, arena_cap=4096, search_var=0):
     fq = index.write_fastq(tag, arrs)
     ref = fx.RefRun(index.prefix, fq[0], fq[1], trim_qual=15)
     n = ref.next_batch()
     lib, h = _emul(index)
+    lib.emul_search_var(search_var)
     g = _abi.GapOpt()
     fx.host_lib().fqb_gap_opt_default(C.byref(g))
     g.trim_qual = 15
@@ -43,7 +44,11 @@ def _check(index, arrs, tag, arena_cap=4096):
         assert (st == 1).all()                                   # every lane ran to completion (no overflow)
         np.testing.assert_array_equal(na, cnt[keep])
         assert (out == pad[keep]).all()
+    lib.emul_search_var(0)
     lib.emul_close(h)
+    stage = (C.c_ulonglong * 3)()
+    lib.emul_stage_stats(stage)
+    return list(stage)
 
 
 def test_lanes_2x100(small_index, ref_required):
@@ -52,6 +57,18 @@ def test_lanes_2x100(small_index, ref_required):
 
 def test_lanes_2x150_indels(small_index, ref_required):
     _check(small_index, small_index.reads(1200, read_len=150, seed=32, sub_rate=0.03, ins_rate=0.01, del_rate=0.01, max_indel_len=3), "em150")
+
+
+def test_lanes_pop_staging(small_index, ref_required):
+    """The build's default form of the fast pass (SearchLane kVar = 5: pops served from a per-lane staging slot that is filled
+    when the entry before it in the bucket's chain is popped): same hit lists as the reference, most pops from memory are
+    served from the slot, and a staged entry never differs from the arena's (entries of the bump arena are written once)."""
+    arrs = small_index.reads(1200, read_len=150, seed=34, sub_rate=0.03, ins_rate=0.01, del_rate=0.01, max_indel_len=3)
+    plain = _check(small_index, arrs, "emst0")
+    hit, miss, stale = _check(small_index, arrs, "emst5", search_var=1)
+    assert plain == [0, 0, 0]
+    assert stale == 0
+    assert hit > 3 * miss > 0, (hit, miss)
 
 
 def test_lanes_free_list_arena(small_index, ref_required):
