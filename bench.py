@@ -471,7 +471,9 @@ def main_gpu(args):
         "clocks": clocks,
         "roofline": {"bound": "l2", "achieved": achieved, "peak": l2_best.value, "unit": "GB/s", "frac": achieved / l2_best.value,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (n_pairs == BATCH and args.config == "2x100_10k") else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of search_kernel, ncu --set full capture r2a (profiles/r02_search_kernel_ncu.md)",
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of search_kernel in its plain form (FQB_SEARCH_VAR=0), ncu --set full capture r2a "
+                                       "(profiles/r02_search_kernel_ncu.md); the default form since -- pop staging + streaming stack stores, "
+                                       "profiles/r02_search_memory_variants.md -- moves the same entries and was not re-captured",
                      "peak_kind": "BW_L2 measured on this box in this run: fqb_measure_l2, random 64-byte reads over an 8 MiB buffer, all SMs, best of 10 (median %.1f)" % l2_med.value,
                      "hbm_peak": hbm_peak, "hbm_peak_kind": peak_kind + " HBM copy bandwidth (MEASURED_PEAKS.json)", "frac_of_hbm_peak": achieved / hbm_peak,
                      "kernel": "width_kernel + search_kernel (rank queries of one %d-pair batch)" % n_pairs,
