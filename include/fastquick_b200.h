@@ -154,7 +154,7 @@ uint64_t fqb_prefetch_hits(const fqb_handle *h);
 /* ---- pipelined form of the per-batch body (src/BwtMapper.cpp:1905-1982: the reference reads batch n+1 on its IO
  * workers while batch n is mapped) ----------------------------------------------------------------------------
  * fqb_submit_pairs uploads a batch and enqueues its align stage (a1-a5: prep, k-mer filter, bwt_cal_width,
- * bwt_match_gap) on a second stream, into whichever of the handle's two batch sets is free, and returns at once.
+ * bwt_match_gap) on a second stream, into whichever of the handle's batch sets is free, and returns at once.
  * fqb_collect_pairs takes the OLDEST submitted batch through bwa_cal_pac_pos_pe, bwa_paired_sw, bwa_refine_gapped and,
  * when fqb_stats_open was called, StatCollector::AddAlignment's accumulation (= fqb_stage_stats), and starts the copy
  * of its result rows into rows1/rows2 (may be NULL); it does not wait.  Call order: submit(0); then for every n:
